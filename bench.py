@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- GFA -> CSR parse+build throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C2] [--impl ours|reference]
+
+A step = one pass of the hot path (tokenize -> node IDs -> triplets -> sort/dedup -> CSR) over one
+synthetic GFA text of the named configuration.  `value` is whole-job input GB/s with
+the text already resident in HBM and the CSR left resident in HBM (CUDA events on the launching
+stream, L2 flushed between steps, max over ranks); `e2e` is the same metric through the public
+Python API with a pinned HOST buffer in and host NumPy arrays out (H2D and D2H inside the timed
+region).  `roofline` is for the kernel with the largest share of the step, from per-launch CUDA
+events; `cpu_baseline` is the CPU oracle (C port of the reference's tokenizer/builder + SciPy)
+timed on this host.  `--impl reference` times that CPU path alone.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+HBM_FALLBACK_GBS = 6650.0  # B200_PROFILING.md fallback, used only if MEASURED_PEAKS.json is absent
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return float(json.loads(p.read_text())["hbm_gbs"]), "measured"
+    return HBM_FALLBACK_GBS, "fallback"
+
+
+def make_text(cfg_name: str, scale: float = 1.0, out=None, seed_shift: int = 0, id_base: int = 0):
+    from gfa2network_b200.synth import CONFIGS, synth_gfa
+
+    cfg = CONFIGS[cfg_name]
+    n_seg = max(2, int(cfg["n_seg"] * scale))
+    n_link = max(1, int(cfg["n_link"] * scale))
+    text = synth_gfa(n_seg, n_link, seed=cfg["seed"] + seed_shift, kind=cfg["kind"], seq_mean=cfg.get("seq_mean", 0),
+                     n_paths=cfg.get("n_paths", 0), n_walks=cfg.get("n_walks", 0), out=out, id_base=id_base)
+    return cfg, text, n_seg, n_link
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for k, nme in enumerate(names):
+                    if r[2 + k].lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_run(text, mode, fmt):
+    from oracle.oracle import oracle_convert_format, oracle_parse_gfa
+
+    t = time.perf_counter()
+    A = oracle_parse_gfa(text, **mode)
+    A = oracle_convert_format(A, fmt)
+    return time.perf_counter() - t, A
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port (the
+    reference itself is Python under /root/reference, which does not exist on the GPU box)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg, text, n_seg, n_link = make_text(args.config, args.scale)
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_oracle_run(text, cfg["mode"], cfg["fmt"])
+    times = []
+    for _ in range(args.steps):
+        dt, _A = cpu_oracle_run(text, cfg["mode"], cfg["fmt"])
+        times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    gbs = text.size / (ms * 1e6)
+    line = {
+        "impl": "reference", "metric": "gfa_to_csr_parse_build_GBps", "value": gbs, "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8/int32/f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.config, args.scale, n_seg, n_link, cfg), "text_bytes": int(text.size)},
+        "edges_per_s": n_link / (ms / 1e3),
+        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": 1, "kind": "port",
+                         "sample": f"full {args.config} text ({text.size} B), {args.steps} runs, C port of parser.py/builders.py + SciPy"},
+        "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_name(cfg_name, scale, n_seg, n_link, cfg):
+    mode = ",".join(f"{k}={v}" for k, v in cfg["mode"].items()) or "directed(default)"
+    kind = "GFA-1 S/L" if cfg["kind"] == 1 else "reference E-dialect S/E + RC:f"
+    return f"{cfg_name} synthetic {kind}: {n_seg} segments / {n_link} links, {mode}, {cfg['fmt'].upper()}" + ("" if scale == 1.0 else f" (scale {scale})")
+
+
+# algorithmic bytes per launch of each kernel: compulsory reads + writes only
+def algo_bytes(name, launches, st):
+    N, E, spe, M, n, cap, words, nnz, weighted = (st[k] for k in ("N", "E", "spe", "M", "n", "cap", "words", "nnz", "weighted"))
+    keyb = 8 + (4 if weighted else 0)
+    table = {
+        "k_tokenize": N + 4 * spe * E + (8 * E if weighted else 0),
+        "k_radix_hist": 8 * M,
+        "k_radix_scatter": 2 * keyb * M,
+        "k_emit_keys": 4 * spe * E + keyb * M,
+        "k_group_reduce": keyb * M + 4 * M + 8 * nnz,
+        "k_compact": 8 * M + 8 * M + 12 * nnz,
+        "k_mark_first": 32 * cap,
+        "k_assign_ids": 32 * cap + 12 * n,
+        "k_scan_exclusive": None,
+    }
+    return table.get(name)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from gfa2network_b200 import _capi, parse_gfa
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    # weak scaling: every rank parses + builds its own shard of the same shape
+    cfg, text_np, n_seg, n_link = make_text(args.config, args.scale, seed_shift=rank)
+    nbytes = int(text_np.size)
+    pinned = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    pinned.numpy()[:] = text_np
+    text_dev = pinned.to(dev, non_blocking=True)
+    torch.cuda.synchronize()
+
+    h = _capi.Handle(local)
+    stream = torch.cuda.current_stream()
+    h.set_stream(stream.cuda_stream)
+    h.set_profile(True)
+    mode = cfg["mode"]
+    want = {"csr": _capi.FMT_CSR, "csc": _capi.FMT_CSC, "coo": _capi.FMT_NATIVE}[cfg["fmt"]]
+    wt = mode.get("weight_tag")
+    wtb = wt.encode() if wt else None
+    params = _capi.Params(int(mode.get("directed", True)), int(mode.get("bidirected", False)), int(mode.get("keep_directed_bidir", False)),
+                          int(mode.get("asymmetric", False)), 0, _capi.DTYPES["float64"], want, 1, wtb, len(wtb) if wtb else 0, 0)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step():
+        rc = h.build(text_dev.data_ptr(), nbytes, params)
+        h.check(rc)
+
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ktot: dict[str, list[float]] = {}
+    launches = 0
+    torch.cuda.synchronize()
+    for i in range(args.steps):
+        flush.zero_()  # evict the text and the tables from L2 between steps (not timed)
+        ev[i][0].record(stream)
+        step()
+        ev[i][1].record(stream)
+        torch.cuda.synchronize()
+        for k, (ms, cnt) in h.kernel_times().items():
+            a = ktot.setdefault(k, [0.0, 0])
+            a[0] += ms
+            a[1] += cnt
+        launches += h.status().gpu_launches
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_step = total_ms / args.steps
+    diag = h.status()
+    sz = h.sizes()
+
+    # ---- e2e through the public API: pinned host text in, host CSR arrays out
+    fmt = cfg["fmt"]
+    e2e_steps = max(2, min(args.steps, 5))
+    host_in = pinned.numpy()
+    parse_gfa(host_in, build_graph=False, build_matrix=True, matrix_format=fmt, device=local, **mode)  # warm the default handle
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        A = parse_gfa(host_in, build_graph=False, build_matrix=True, matrix_format=fmt, device=local, **mode)
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    if A.format == "coo":
+        d2h = A.row.nbytes + A.col.nbytes + A.data.nbytes
+    else:
+        d2h = A.indptr.nbytes + A.indices.nbytes + A.data.nbytes
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- roofline of the dominant kernel
+    peak, peak_src = peaks()
+    M = int(diag.n_triplets) * (2 if (params.directed and not params.bidirected and not params.asymmetric) or
+                                   (params.bidirected and params.keep_directed_bidir and not params.asymmetric) else 1)
+    st = dict(N=nbytes, E=int(diag.n_edge_records), spe=4 if (params.bidirected and not params.keep_directed_bidir) else 2, M=M,
+              n=int(sz.n_nodes), cap=0, words=0, nnz=int(sz.nnz), weighted=bool(wtb))
+    kern = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in ktot.items()}
+    dom = max(kern, key=lambda k: kern[k]["ms_per_step"]) if kern else None
+    roof = None
+    if dom:
+        per_launch_ms = ktot[dom][0] / max(1, ktot[dom][1])
+        ab = algo_bytes(dom, ktot[dom][1], st)
+        if ab:
+            ach = ab / (per_launch_ms * 1e6)
+            roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": None, "algorithmic_bytes_per_launch": ab, "ms_per_launch": per_launch_ms,
+                    "share_of_step": kern[dom]["ms_per_step"] / ms_step}
+    # whole-path algorithmic bytes: text in + CSR + node names out
+    out_bytes = 4 * (sz.n_nodes + 1) + 12 * sz.nnz + sz.names_bytes + 8 * (sz.n_nodes + 1)
+    path_ach = (nbytes + out_bytes) / (ms_step * 1e6)
+    # ---- CPU baseline on this host (bounded: one full pass of the same text)
+    cpu_dt, _B = cpu_oracle_run(text_np, mode, fmt)
+    gbs = world * nbytes / (ms_step * 1e6)
+    line = {
+        "metric": "gfa_to_csr_parse_build_GBps", "value": gbs, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8/int32/f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.config, args.scale, n_seg, n_link, cfg), "text_bytes_per_gpu": nbytes,
+                   "l2": "flushed between steps (512 MiB write)", "nodes": int(sz.n_nodes), "nnz": int(sz.nnz),
+                   "sharding": "one shard of this shape per GPU, no exchange" if world > 1 else "single GPU"},
+        "edges_per_s": world * n_link / (ms_step / 1e3),
+        "path_roofline": {"algorithmic_bytes": int(nbytes + out_bytes), "achieved": path_ach, "peak": peak, "frac": path_ach / peak, "unit": "GB/s"},
+        "roofline": roof,
+        "kernels": kern,
+        "stage_ms": {k: float(diag.ms_stage[i]) for i, k in ((0, "tokenize+hash"), (1, "ids"), (3, "emit"), (4, "sort"), (5, "reduce"))},
+        "cpu_baseline": {"value": nbytes / (cpu_dt * 1e9), "unit": "GB/s", "cores": 1, "kind": "port",
+                         "sample": f"full {args.config} text ({nbytes} B), 1 run: C port of parser.py/builders.py + SciPy tocsr/maximum",
+                         "host_cores_available": os.cpu_count()},
+        "e2e": {"value": world * nbytes / (e2e_s * 1e9), "unit": "GB/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": e2e_s * 1e3, "api": "gfa2network_b200.parse_gfa(pinned uint8 buffer, matrix_format=...)"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="C2", choices=["C2", "C3", "C4", "C5"])
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

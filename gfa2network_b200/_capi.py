@@ -1,0 +1,190 @@
+"""ctypes binding of include/g2n.h (libg2n.so).  Thin: structs, prototypes, error mapping.
+
+The library is the only compute path.  If it cannot be loaded, or no CUDA device is usable,
+every entry point raises -- there is no CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+from . import _build
+
+G2N_OK, G2N_ERR_CUDA, G2N_ERR_INVALID, G2N_ERR_PARSE, G2N_ERR_UNSUPPORTED, G2N_ERR_INTERNAL = range(6)
+FMT_NATIVE, FMT_CSR, FMT_CSC, FMT_COO = 0, 1, 2, 3
+FMT_NAMES = {FMT_CSR: "csr", FMT_CSC: "csc", FMT_COO: "coo"}
+DTYPES = {"float64": 0, "float32": 1, "int32": 2, "int8": 3, "bool": 4}
+DTYPE_NP = {0: np.float64, 1: np.float32, 2: np.int32, 3: np.int8, 4: np.bool_}
+
+EXPORTS = [
+    "g2n_abi_version", "g2n_create", "g2n_destroy", "g2n_set_stream", "g2n_host_alloc", "g2n_host_free",
+    "g2n_build", "g2n_convert", "g2n_sizes", "g2n_fetch_matrix", "g2n_fetch_names", "g2n_device_result",
+    "g2n_status", "g2n_last_error", "g2n_coo_to_compressed", "g2n_set_profile", "g2n_kernel_times",
+]
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("directed", C.c_int32), ("bidirected", C.c_int32), ("keep_directed_bidir", C.c_int32),
+        ("asymmetric", C.c_int32), ("strip_orientation", C.c_int32), ("dtype", C.c_int32),
+        ("want_format", C.c_int32), ("text_on_device", C.c_int32),
+        ("weight_tag", C.c_char_p), ("weight_tag_len", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class Sizes(C.Structure):
+    _fields_ = [
+        ("n_nodes", C.c_uint64), ("nnz", C.c_uint64), ("names_bytes", C.c_uint64),
+        ("format", C.c_int32), ("index_bytes", C.c_int32), ("dtype", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class Diag(C.Structure):
+    _fields_ = [
+        ("err_kind", C.c_int32), ("unknown_byte", C.c_int32),
+        ("err_offset", C.c_uint64), ("unknown_offset", C.c_uint64),
+        ("n_records", C.c_uint64), ("n_edge_records", C.c_uint64), ("n_triplets", C.c_uint64),
+        ("n_long_keys", C.c_uint64), ("retries", C.c_uint32), ("gpu_launches", C.c_uint32),
+        ("ms_total", C.c_float), ("ms_h2d", C.c_float), ("ms_stage", C.c_float * 8),
+    ]
+
+
+class KTime(C.Structure):
+    _fields_ = [("name", C.c_char * 40), ("ms", C.c_float), ("launches", C.c_uint32)]
+
+
+_lib = None
+
+
+def lib_path() -> Path:
+    return _build.LIB
+
+
+def load():
+    """dlopen libg2n.so (building it first if the sources are newer) and set prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.build()
+    lib = C.CDLL(str(path))
+    vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int32
+    lib.g2n_abi_version.restype = C.c_int
+    lib.g2n_create.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.g2n_destroy.argtypes = [vp]
+    lib.g2n_destroy.restype = None
+    lib.g2n_set_stream.argtypes = [vp, vp]
+    lib.g2n_host_alloc.argtypes = [u64]
+    lib.g2n_host_alloc.restype = vp
+    lib.g2n_host_free.argtypes = [vp]
+    lib.g2n_host_free.restype = None
+    lib.g2n_build.argtypes = [vp, vp, u64, C.POINTER(Params)]
+    lib.g2n_convert.argtypes = [vp, i32]
+    lib.g2n_sizes.argtypes = [vp, C.POINTER(Sizes)]
+    lib.g2n_fetch_matrix.argtypes = [vp, vp, vp, vp]
+    lib.g2n_fetch_names.argtypes = [vp, vp, vp]
+    lib.g2n_device_result.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    lib.g2n_status.argtypes = [vp, C.POINTER(Diag)]
+    lib.g2n_last_error.argtypes = [vp]
+    lib.g2n_last_error.restype = C.c_char_p
+    lib.g2n_coo_to_compressed.argtypes = [vp, vp, vp, vp, u64, u64, i32, i32, vp, vp, vp, C.POINTER(u64)]
+    lib.g2n_set_profile.argtypes = [vp, C.c_int]
+    lib.g2n_kernel_times.argtypes = [vp, C.POINTER(KTime), C.c_int]
+    _lib = lib
+    return lib
+
+
+class G2NError(RuntimeError):
+    pass
+
+
+class Handle:
+    """One libg2n handle = one device, one stream, warm device scratch."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.g2n_create(device, C.byref(h))
+        if rc != G2N_OK or not h:
+            raise G2NError(
+                "g2n_create failed: no usable CUDA device (the GFA->matrix path has no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.g2n_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def last_error(self) -> str:
+        return (self.lib.g2n_last_error(self.h) or b"").decode(errors="replace")
+
+    def check(self, rc: int):
+        if rc == G2N_OK:
+            return
+        msg = self.last_error()
+        if rc == G2N_ERR_UNSUPPORTED:
+            raise NotImplementedError(msg)
+        if rc == G2N_ERR_INVALID:
+            raise ValueError(msg or "invalid argument")
+        raise G2NError(f"libg2n status {rc}: {msg}")
+
+    def set_stream(self, stream_ptr: int | None):
+        self.check(self.lib.g2n_set_stream(self.h, C.c_void_p(stream_ptr or 0)))
+
+    def set_profile(self, on: bool):
+        self.check(self.lib.g2n_set_profile(self.h, int(on)))
+
+    def kernel_times(self) -> dict[str, tuple[float, int]]:
+        buf = (KTime * 32)()
+        n = self.lib.g2n_kernel_times(self.h, buf, 32)
+        return {buf[i].name.decode(): (float(buf[i].ms), int(buf[i].launches)) for i in range(max(n, 0))}
+
+    def status(self) -> Diag:
+        d = Diag()
+        self.lib.g2n_status(self.h, C.byref(d))
+        return d
+
+    def sizes(self) -> Sizes:
+        s = Sizes()
+        self.check(self.lib.g2n_sizes(self.h, C.byref(s)))
+        return s
+
+    def build(self, text_ptr: int, nbytes: int, params: Params) -> int:
+        return self.lib.g2n_build(self.h, C.c_void_p(text_ptr), nbytes, C.byref(params))
+
+    def convert(self, fmt: int):
+        self.check(self.lib.g2n_convert(self.h, fmt))
+
+    def fetch_matrix(self):
+        s = self.sizes()
+        dt = DTYPE_NP[s.dtype]
+        n, nnz = s.n_nodes, s.nnz
+        a0 = np.empty(nnz if s.format == FMT_COO else n + 1, dtype=np.int32)
+        a1 = np.empty(nnz, dtype=np.int32)
+        data = np.empty(nnz, dtype=dt)
+        self.check(self.lib.g2n_fetch_matrix(self.h, a0.ctypes.data, a1.ctypes.data, data.ctypes.data))
+        return s, a0, a1, data
+
+    def fetch_names(self):
+        s = self.sizes()
+        names = np.empty(max(1, s.names_bytes), dtype=np.uint8)
+        offs = np.empty(s.n_nodes + 1, dtype=np.uint64)
+        self.check(self.lib.g2n_fetch_names(self.h, names.ctypes.data, offs.ctypes.data))
+        return names[: s.names_bytes], offs
+
+
+_default: dict[int, Handle] = {}
+
+
+def default_handle(device: int = 0) -> Handle:
+    h = _default.get(device)
+    if h is None or h.h is None:
+        h = _default[device] = Handle(device)
+    return h

@@ -1,0 +1,219 @@
+"""Host-side mirror of ``gfa2network.builders.parse_gfa`` for the matrix path.
+
+Same name, keyword arguments, return convention, exceptions, warnings and verbose strings as
+the reference (``gfa2network/builders.py:30-299``); the work itself -- tokenizer
+(``parser.py:114-361``), node-ID assignment and triplet emission (``builders.py:163-234``),
+``coo_matrix`` + ``maximum(A, A.T)`` (``builders.py:279-283``) -- runs in libg2n.so on the GPU.
+Combinations outside the hot path (graph building, igraph backend, split-on-alignment) fail
+loudly instead of silently computing something else.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import gzip
+import os
+import sys
+import warnings
+from pathlib import Path
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _capi
+
+_ERRORS = {
+    1: (ValueError, "Malformed L record"),  # parser.py:209
+    2: (ValueError, "Malformed E record"),  # parser.py:252
+    3: (ValueError, "Malformed C record"),  # parser.py:300
+    4: (ValueError, "Malformed P record"),  # parser.py:232
+    5: (ValueError, "Malformed O record"),  # parser.py:346
+    6: (IndexError, "list index out of range"),  # parser.py:163 fields[1]
+    7: (IndexError, "index out of range"),  # parser.py:220-221 u_field[-1]
+    9: (OverflowError, "int too large to convert to float"),  # builders.py:209
+    10: (NotImplementedError, "non-ASCII numeric weight tag value is outside the supported scope"),
+}
+
+
+def _default_device() -> int:
+    for k in ("G2N_DEVICE", "LOCAL_RANK"):
+        v = os.environ.get(k)
+        if v is not None and v.isdigit():
+            return int(v)
+    return 0
+
+
+class _Session:
+    """Ties a returned SciPy matrix to the device-resident result it was fetched from, so that
+    ``convert_format`` can finish COO -> CSR/CSC on the GPU (utils.py:55)."""
+
+    _serial = 0
+
+    def __init__(self, handle: _capi.Handle):
+        _Session._serial += 1
+        self.handle = handle
+        self.token = _Session._serial
+        handle._current_token = self.token
+
+    def live(self) -> bool:
+        return self.handle.h is not None and getattr(self.handle, "_current_token", None) == self.token
+
+
+def _read_source(path):
+    """Returns (host uint8 array | None, device pointer | None, nbytes, keepalive)."""
+    if hasattr(path, "is_cuda") and hasattr(path, "data_ptr"):  # torch tensor (extension)
+        t = path
+        if not t.is_cuda:
+            arr = t.numpy()
+            return np.ascontiguousarray(arr.view(np.uint8).reshape(-1)), None, arr.nbytes, t
+        if not t.is_contiguous():
+            raise ValueError("device text tensor must be contiguous")
+        return None, t.data_ptr(), t.numel() * t.element_size(), t
+    if isinstance(path, np.ndarray):
+        arr = np.ascontiguousarray(path).view(np.uint8).reshape(-1)
+        return arr, None, arr.size, arr
+    if isinstance(path, (bytes, bytearray, memoryview)):
+        arr = np.frombuffer(path, dtype=np.uint8)
+        return arr, None, arr.size, path
+    if isinstance(path, (str, Path)):
+        p = str(path) or "-"  # parser.py:104
+        if p == "-":
+            raw = sys.stdin.buffer.read()  # parser.py:105-106
+        elif p.endswith(".gz"):
+            with gzip.open(p, "rb") as fh:  # parser.py:108-109
+                raw = fh.read()
+        else:
+            arr = np.fromfile(p, dtype=np.uint8)  # parser.py:111
+            return arr, None, arr.size, arr
+        arr = np.frombuffer(raw, dtype=np.uint8)
+        return arr, None, arr.size, raw
+    if hasattr(path, "read"):  # binary file object, parser.py:90-92
+        raw = path.read()
+        arr = np.frombuffer(raw, dtype=np.uint8)
+        return arr, None, arr.size, raw
+    raise TypeError(f"unsupported GFA source: {type(path)!r}")
+
+
+def _raise_parse_error(diag, host):
+    kind = diag.err_kind
+    if kind == 8:
+        # UnicodeDecodeError from an orientation field: re-split the one offending line on the
+        # host to raise the identical exception (parser.py:214, 291-293, 337-339)
+        if host is not None:
+            off = int(diag.err_offset)
+            tail = host[off:off + (1 << 20)].tobytes()
+            line = tail.split(b"\n", 1)[0]
+            f = line.split(b"\t")
+            cand = {b"L": (4,), b"E": (3, 5), b"C": (2, 4)}.get(f[0], ())
+            for i in cand:
+                if i < len(f):
+                    f[i].decode()
+        raise UnicodeDecodeError("utf-8", b"", 0, 1, "invalid orientation field")
+    exc, msg = _ERRORS[kind]
+    raise exc(msg)
+
+
+def _node_list(handle, raw_bytes_id):
+    names, offs = handle.fetch_names()
+    blob = names.tobytes()
+    o = offs.tolist()
+    if raw_bytes_id:
+        return [blob[o[i]:o[i + 1]] for i in range(len(o) - 1)]
+    if blob.isascii():
+        s = blob.decode("ascii")
+        return [s[o[i]:o[i + 1]] for i in range(len(o) - 1)]
+    return [blob[o[i]:o[i + 1]].decode() for i in range(len(o) - 1)]  # builders.py:287
+
+
+def _matrix_from_handle(handle):
+    s, a0, a1, data = handle.fetch_matrix()
+    n = s.n_nodes
+    if s.format == _capi.FMT_COO:
+        return sp.coo_matrix((data, (a0, a1)), shape=(n, n))
+    cls = sp.csr_matrix if s.format == _capi.FMT_CSR else sp.csc_matrix
+    return cls((data, a1, a0), shape=(n, n))
+
+
+def parse_gfa(
+    path,
+    *,
+    build_graph: bool,
+    build_matrix: bool,
+    directed: bool = True,
+    weight_tag: str | None = None,
+    store_seq: bool = False,
+    store_tags: bool = False,
+    strip_orientation: bool = False,
+    verbose: bool = False,
+    bidirected: bool = False,
+    keep_directed_bidir: bool = False,
+    backend: str = "networkx",
+    dtype: str | object = "float64",
+    asymmetric: bool = False,
+    raw_bytes_id: bool = False,
+    return_node_list: bool = False,
+    max_tag_mb: float = 100.0,
+    split_on_alignment: bool = False,
+    matrix_format: str | None = None,
+    device: int | None = None,
+):
+    """Parse *path* on the GPU and return the adjacency matrix (and node list).
+
+    Drop-in for ``gfa2network.parse_gfa(..., build_graph=False, build_matrix=True)``
+    (``builders.py:30-50``).  Extensions, both optional: ``matrix_format`` ("csr"/"csc") fuses
+    ``convert_format`` into the device build; ``device`` selects the CUDA device.  ``path`` may
+    also be a bytes-like object, a uint8 NumPy array or a CUDA uint8 torch tensor.
+    """
+    if backend == "igraph":
+        raise NotImplementedError("backend='igraph' is outside the B200 GFA->matrix path (builders.py:95-109)")
+    if backend != "networkx":
+        raise ValueError(f"unknown backend {backend!r}")
+    if split_on_alignment:
+        raise NotImplementedError("split_on_alignment is outside the B200 GFA->matrix path (builders.py:110-128)")
+    if return_node_list and not build_matrix:
+        raise ValueError("return_node_list requires build_matrix=True")  # builders.py:130
+    if build_graph:
+        raise NotImplementedError(
+            "build_graph=True (NetworkX object graph) is outside the B200 GFA->matrix path; "
+            "use the reference for graphs (builders.py:138-142, 166-189, 235-256)")
+    dt = np.dtype(dtype)  # builders.py:280
+    if dt.name not in _capi.DTYPES:
+        raise NotImplementedError(f"dtype {dt.name!r}: the device path supports {sorted(_capi.DTYPES)}")
+    want = _capi.FMT_NATIVE
+    if matrix_format is not None:
+        mf = matrix_format.lower()
+        if mf not in {"csr", "csc", "coo", "dok"}:
+            raise ValueError("matrix-format must be csr|csc|coo|dok")  # utils.py:46
+        want = {"csr": _capi.FMT_CSR, "csc": _capi.FMT_CSC}.get(mf, _capi.FMT_NATIVE)
+
+    host, dev_ptr, nbytes, keep = _read_source(path)
+    handle = _capi.default_handle(_default_device() if device is None else device)
+    wt = weight_tag.encode() if weight_tag else None  # builders.py:206 "if weight_tag and ..."
+    params = _capi.Params(
+        int(bool(directed)), int(bool(bidirected)), int(bool(keep_directed_bidir)), int(bool(asymmetric)),
+        int(bool(strip_orientation)), _capi.DTYPES[dt.name], want, 0 if dev_ptr is None else 1,
+        wt, len(wt) if wt else 0, 0)
+    ptr = dev_ptr if dev_ptr is not None else (host.ctypes.data if nbytes else 0)
+    rc = handle.build(ptr, nbytes, params)
+    diag = handle.status()
+    if rc in (_capi.G2N_OK, _capi.G2N_ERR_PARSE):
+        if diag.unknown_byte >= 0:
+            # parser.py:125-131, once per parse, before any error of a later line
+            warnings.warn(
+                f"Skipping unsupported record: {bytes([diag.unknown_byte]).decode()}",
+                RuntimeWarning, stacklevel=2)
+        if verbose:
+            for k in range(500_000, int(diag.n_records) + 1, 500_000):  # builders.py:257-258
+                print(f"\r[{k:,} lines]", end="", file=sys.stderr)
+    if rc == _capi.G2N_ERR_PARSE:
+        _raise_parse_error(diag, host)
+    handle.check(rc)
+    if verbose:
+        print("\r[parse_gfa] done")  # builders.py:261
+    if not build_matrix:
+        return None
+    session = _Session(handle)
+    A = _matrix_from_handle(handle)
+    A._g2n_session = session
+    if return_node_list:
+        return A, _node_list(handle, raw_bytes_id)
+    return A

@@ -1,0 +1,68 @@
+"""``gfa2network convert`` surface (gfa2network/cli.py:22-135, 193-250) over the GPU path.
+Same flags, defaults, stdout/stderr strings and exit behaviour for ``convert --matrix``;
+the sub-commands that are not on the GFA->matrix path are not provided here."""
+from __future__ import annotations
+
+import argparse
+from pathlib import Path
+
+from .builders import parse_gfa
+from .utils import convert_format, save_matrix, save_node_map
+from .version import __version__
+
+
+def _parser() -> argparse.ArgumentParser:
+    ap = argparse.ArgumentParser(prog="gfa2network")
+    ap.add_argument("--version", action="version", version=f"gfa2network {__version__}")
+    ap.add_argument("--raw-bytes-id", action="store_true", help="Use raw bytes for node identifiers (legacy)")
+    ap.add_argument("--max-dense-gb", type=float, default=5.0, help="Abort dense matrix saves over N GB (default 5)")
+    ap.add_argument("--max-tag-mb", type=float, default=100.0, help="Warn when stored tags exceed N MB (default 100)")
+    sub = ap.add_subparsers(dest="cmd", required=True)
+    c = sub.add_parser("convert", help="Convert GFA to graph or matrix")
+    c.add_argument("gfa", help="Input *.gfa* file or - for stdin")
+    c.add_argument("--backend", choices=["networkx", "igraph"], default="networkx", help="Graph backend to use")
+    g = c.add_mutually_exclusive_group()
+    g.add_argument("--directed", dest="directed", action="store_true", default=True, help="Treat graph as directed")
+    g.add_argument("--undirected", dest="directed", action="store_false", help="Treat graph as undirected")
+    c.add_argument("--graph", action="store_true", help="Build a NetworkX object")
+    c.add_argument("--matrix", metavar="PATH", help="Write adjacency matrix to PATH (.npz|.npy|.csv)")
+    c.add_argument("--save-matrix", dest="matrix", metavar="PATH", help=argparse.SUPPRESS)
+    c.add_argument("--matrix-format", default="csr", help="Sparse format for .npz (csr|csc|coo|dok)")
+    c.add_argument("--dtype", choices=["bool", "int8", "int32", "float32", "float64"], default="float64",
+                   help="Data type for adjacency matrix")
+    c.add_argument("--asymmetric", action="store_true", help="Do not mirror upper triangle")
+    c.add_argument("--no-node-map", action="store_true", help="Do not write <matrix>.nodes.tsv sidecar")
+    c.add_argument("--weight-tag")
+    c.add_argument("--store-seq", action="store_true")
+    c.add_argument("--store-tags", action="store_true")
+    c.add_argument("--split-on-alignment", action="store_true", help="Split segments at alignment boundaries")
+    c.add_argument("--strip-orientation", action="store_true", help="Strip +/- from IDs (v0.1 behaviour)")
+    c.add_argument("--bidirected", action="store_true", help="Use bidirected representation")
+    c.add_argument("--keep-directed-bidir", action="store_true", help="Keep original directed bidirected behaviour")
+    c.add_argument("--verbose", action="store_true")
+    c.add_argument("-o", "--output", metavar="PATH", help="Write graph pickle to PATH")
+    return ap
+
+
+def main(argv: list[str] | None = None) -> None:
+    ap = _parser()
+    args = ap.parse_args(argv)
+    if not args.graph and not args.matrix:
+        ap.error("convert requires --graph or --matrix")  # cli.py:194-195
+    print(f"Using backend: {args.backend}")  # cli.py:198
+    want_nodes = bool(args.matrix) and not args.no_node_map  # cli.py:222
+    result = parse_gfa(
+        args.gfa, build_graph=args.graph, build_matrix=bool(args.matrix), directed=args.directed,
+        weight_tag=args.weight_tag, store_seq=args.store_seq, store_tags=args.store_tags,
+        strip_orientation=args.strip_orientation, verbose=args.verbose, bidirected=args.bidirected,
+        keep_directed_bidir=args.keep_directed_bidir, backend=args.backend, dtype=args.dtype,
+        asymmetric=args.asymmetric, raw_bytes_id=args.raw_bytes_id, return_node_list=want_nodes,
+        max_tag_mb=args.max_tag_mb, split_on_alignment=args.split_on_alignment)
+    A, nodes = result if want_nodes else (result, None)
+    A = convert_format(A, args.matrix_format, verbose=args.verbose)  # cli.py:239
+    try:
+        save_matrix(A, Path(args.matrix), verbose=args.verbose, max_dense_gb=args.max_dense_gb)
+    except MemoryError as exc:  # cli.py:247-248
+        raise SystemExit(str(exc)) from exc
+    if want_nodes:
+        save_node_map(nodes, Path(str(args.matrix) + ".nodes.tsv"))  # cli.py:249-250

@@ -1,0 +1,165 @@
+// common.cuh -- shared device helpers, counters and the single-pass prefix scan.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace g2n {
+
+#define G2N_SM_COUNT 148
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+// ---------------------------------------------------------------- cache-bypassing loads
+__device__ __forceinline__ u64 ld_volatile_u64(const u64* p)
+{
+    u64 v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ u32 ld_volatile_u32(const u32* p)
+{
+    u32 v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u64(u64* p, u64 v)
+{
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint4 ld_nc_v4(const void* p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// ---------------------------------------------------------------- warp / block scans
+__device__ __forceinline__ u32 warp_incl_scan(u32 v)
+{
+    const u32 lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= (u32)d) v += t;
+    }
+    return v;
+}
+__device__ __forceinline__ u64 warp_incl_scan64(u64 v)
+{
+    const u32 lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u64 t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= (u32)d) v += t;
+    }
+    return v;
+}
+
+// Block-wide exclusive scan of one u64 per thread; returns exclusive prefix, *total = block sum.
+// `sm` must hold (blockDim.x / 32 + 1) u64.  Ends with a __syncthreads().
+__device__ __forceinline__ u64 block_excl_scan64(u64 v, u64* sm, u64* total)
+{
+    const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    u64 inc = warp_incl_scan64(v);
+    if (lane == 31) sm[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        u64 w = lane < nw ? sm[lane] : 0;
+        u64 winc = warp_incl_scan64(w);
+        if (lane < nw) sm[lane] = winc - w;
+        if (lane == nw - 1) sm[nw] = winc;
+    }
+    __syncthreads();
+    u64 res = sm[wid] + inc - v;
+    *total = sm[nw];
+    __syncthreads();
+    return res;
+}
+
+// ---------------------------------------------------------------- decoupled look-back
+// state word: [63:62] flag (0 = empty, 1 = aggregate only, 2 = inclusive prefix) | [61:0] value
+#define LB_AGG (1ull << 62)
+#define LB_INC (2ull << 62)
+#define LB_VAL(x) ((x) & ((1ull << 62) - 1))
+
+// Called by ONE thread of the block that owns `tile` (tiles are handed out by an atomic ticket, so
+// every predecessor is already running).  Publishes `agg`, resolves and returns the exclusive prefix.
+__device__ __forceinline__ u64 lookback_exclusive(u64* state, u32 tile, u64 agg)
+{
+    if (tile == 0) {
+        st_volatile_u64(&state[0], LB_INC | agg);
+        return 0;
+    }
+    st_volatile_u64(&state[tile], LB_AGG | agg);
+    u64 excl = 0;
+    int t = (int)tile - 1;
+    while (true) {
+        u64 s = ld_volatile_u64(&state[t]);
+        const u64 flag = s >> 62;
+        if (flag == 0) continue;  // predecessor has not published yet
+        excl += LB_VAL(s);
+        if (flag == 2) break;
+        t--;
+    }
+    __threadfence();
+    st_volatile_u64(&state[tile], LB_INC | (excl + agg));
+    return excl;
+}
+
+// ---------------------------------------------------------------- generic exclusive scan
+// out[i] = sum_{j<i} load(j) for i in [0, n]; out has n+1 entries (out[n] = total).
+// grid: any size >= 1 (persistent, ticketed tiles of SCAN_TILE items); block: 256 threads.
+#define SCAN_ITEMS 8
+#define SCAN_TILE (256 * SCAN_ITEMS)
+
+template <typename Tout, class LoadOp>
+__global__ void __launch_bounds__(256) k_scan_exclusive(LoadOp load, Tout* __restrict__ out, u64 n,
+                                                         u64* __restrict__ state, u32* __restrict__ ticket)
+{
+    __shared__ u64 sm[10];
+    __shared__ u32 s_tile;
+    __shared__ u64 s_base;
+    const u64 n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    while (true) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const u32 tile = s_tile;
+        if (tile >= n_tiles) break;
+        const u64 base = (u64)tile * SCAN_TILE + (u64)threadIdx.x * SCAN_ITEMS;
+        u64 v[SCAN_ITEMS];
+        u64 sum = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            v[k] = (base + k < n) ? (u64)load(base + k) : 0;
+            sum += v[k];
+        }
+        u64 total;
+        u64 excl = block_excl_scan64(sum, sm, &total);
+        if (threadIdx.x == 0) s_base = lookback_exclusive(state, tile, total);
+        __syncthreads();
+        u64 run = s_base + excl;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            if (base + k < n) out[base + k] = (Tout)run;
+            run += v[k];
+        }
+        if (tile == n_tiles - 1 && threadIdx.x == 255) out[n] = (Tout)run;
+        __syncthreads();
+    }
+    if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) out[0] = (Tout)0;
+}
+
+template <typename T>
+struct LoadArray {
+    const T* p;
+    __device__ __forceinline__ u64 operator()(u64 i) const { return (u64)p[i]; }
+};
+struct LoadPopc {
+    const u32* p;
+    __device__ __forceinline__ u64 operator()(u64 i) const { return (u64)__popc(p[i]); }
+};
+
+}  // namespace g2n

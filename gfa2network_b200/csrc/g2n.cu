@@ -1,0 +1,772 @@
+// g2n.cu -- host orchestration and the C ABI (include/g2n.h) of the B200-native GFA -> sparse
+// adjacency path.  Stages on one CUDA stream:
+//   K1  k_tokenize        line scan + field split + node-key hashing + edge-record emission (tokenize.cuh)
+//   K2  k_mark_first / k_assign_ids / k_gather_names   first-appearance ranking -> node IDs   (ids.cuh)
+//   K3  k_emit_coo | k_emit_keys                        COO triplets / sort keys               (ids.cuh)
+//   K4  k_radix_hist / k_radix_scatter / k_group_reduce / k_compact   sort + dedup/sum (+max) (sort.cuh)
+// No CPU fallback exists: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/g2n.h"
+#include "sort.cuh"
+
+using namespace g2n;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T* as() const { return (T*)p; }
+};
+
+struct KTimer {
+    const char* name;
+    cudaEvent_t a, b;
+};
+
+enum { EV_START = 0, EV_H2D, EV_TOKENIZE, EV_IDS, EV_EMIT, EV_SORT, EV_REDUCE, EV_COUNT };
+
+}  // namespace
+
+struct g2n_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    std::string err;
+    cudaEvent_t ev[EV_COUNT];
+    // device buffers (kept between builds: a warm handle allocates nothing)
+    DevBuf text, table, edge_slots, edge_w, longs, tile_state, cnt, bitmap, wprefix, slot_id, id2slot, name_len, name_off, names;
+    DevBuf keysA, keysB, payA, payB, tile_hist, val, flag, pos, major_count, indptr, indices, data, row, col, scan_state;
+    DevBuf up_row, up_col, up_data;
+    Counters* h_cnt = nullptr;  // pinned
+    u64* h_tail = nullptr;      // pinned: {nnz, names_bytes}
+    // capacity hints learnt from previous builds
+    u64 hint_keys = 0, hint_edges = 0, hint_long = 0;
+    // state of the last build
+    g2n_params params;
+    uint8_t weight_tag[64];
+    const uint8_t* d_text = nullptr;
+    u64 nbytes = 0;
+    bool built = false;
+    bool have_edges = false;
+    u64 n_nodes = 0, nnz = 0, names_bytes = 0, n_edges = 0, n_triplets = 0;
+    u32 table_cap = 0;
+    int tpe = 1, spe = 2;
+    bool symmax = false;
+    int result_format = G2N_FMT_COO;
+    bool names_ready = false;
+    g2n_diag diag;
+    u32 launches = 0;
+    // optional per-kernel timing (g2n_set_profile): one event pair per launch
+    bool profile = false;
+    std::vector<KTimer> ktimers;
+    size_t kt_used = 0;
+};
+
+namespace {
+
+#define CK(call)                                                                      \
+    do {                                                                              \
+        cudaError_t _e = (call);                                                      \
+        if (_e != cudaSuccess) {                                                      \
+            char _b[512];                                                             \
+            snprintf(_b, sizeof _b, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            h->err = _b;                                                              \
+            return G2N_ERR_CUDA;                                                      \
+        }                                                                             \
+    } while (0)
+
+// Brackets one kernel launch: counts it and, in profile mode, times it with an event pair.
+struct KScope {
+    g2n_handle* h;
+    bool on;
+    KScope(g2n_handle* h_, const char* name) : h(h_), on(h_->profile)
+    {
+        h->launches++;
+        if (!on) return;
+        if (h->kt_used == h->ktimers.size()) {
+            KTimer t;
+            t.name = name;
+            cudaEventCreate(&t.a);
+            cudaEventCreate(&t.b);
+            h->ktimers.push_back(t);
+        }
+        h->ktimers[h->kt_used].name = name;
+        cudaEventRecord(h->ktimers[h->kt_used].a, h->stream);
+    }
+    ~KScope()
+    {
+        if (!on) return;
+        cudaEventRecord(h->ktimers[h->kt_used].b, h->stream);
+        h->kt_used++;
+    }
+};
+
+inline u32 grid_for(u64 work_items, u32 per_block, u32 waves = 8)
+{
+    u64 blocks = (work_items + per_block - 1) / per_block;
+    u64 cap = (u64)G2N_SM_COUNT * waves;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (u32)blocks;
+}
+
+inline u32 next_pow2(u64 x)
+{
+    u64 p = 1;
+    while (p < x) p <<= 1;
+    return (u32)p;
+}
+
+inline int ceil_log2(u64 n)
+{
+    int b = 0;
+    while ((1ull << b) < n) b++;
+    return b < 1 ? 1 : b;
+}
+
+// exclusive scan launcher: out[0..n], out[n] = total
+template <typename Tout, class LoadOp>
+int launch_scan(g2n_handle* h, LoadOp load, Tout* out, u64 n)
+{
+    const u64 n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    CK(h->scan_state.ensure((n_tiles + 2) * sizeof(u64)));
+    CK(cudaMemsetAsync(h->scan_state.p, 0, (n_tiles + 2) * sizeof(u64), h->stream));
+    u64* state = h->scan_state.as<u64>() + 1;
+    u32* ticket = (u32*)h->scan_state.p;
+    { KScope ks(h, "k_scan_exclusive"); k_scan_exclusive<Tout, LoadOp><<<grid_for(n_tiles, 1, 4), 256, 0, h->stream>>>(load, out, n, state, ticket); }
+    CK(cudaGetLastError());
+    return G2N_OK;
+}
+
+// stable LSD radix sort over key bits [1, 1 + total_bits); returns with *keys / *pay pointing at the sorted data
+int radix_sort(g2n_handle* h, u64 M, int total_bits, bool has_payload, u64** keys, u32** pay)
+{
+    u64* in = h->keysA.as<u64>();
+    u64* out = h->keysB.as<u64>();
+    u32* pin = has_payload ? h->payA.as<u32>() : nullptr;
+    u32* pout = has_payload ? h->payB.as<u32>() : nullptr;
+    const u32 n_tiles = (u32)((M + RS_TILE - 1) / RS_TILE);
+    CK(h->tile_hist.ensure(((u64)RS_RADIX * n_tiles + 1) * sizeof(u32)));
+    u32* hist = h->tile_hist.as<u32>();
+    const int passes = (total_bits + 7) / 8;
+    for (int p = 0; p < passes; p++) {
+        const int shift = 1 + 8 * p;
+        const int bits = (total_bits - 8 * p) < 8 ? (total_bits - 8 * p) : 8;
+        const u32 mask = (1u << bits) - 1u;
+        const u32 grid = grid_for(n_tiles, 1, 8);
+        { KScope ks(h, "k_radix_hist"); k_radix_hist<<<grid, RS_THREADS, 0, h->stream>>>(in, M, shift, mask, hist, n_tiles); }
+        LoadArray<u32> ld{hist};
+        int rc = launch_scan<u32>(h, ld, hist, (u64)RS_RADIX * n_tiles);
+        if (rc) return rc;
+        {
+            KScope ks(h, "k_radix_scatter");
+            if (has_payload) k_radix_scatter<true><<<grid, RS_THREADS, 0, h->stream>>>(in, pin, out, pout, M, shift, mask, hist, n_tiles);
+            else k_radix_scatter<false><<<grid, RS_THREADS, 0, h->stream>>>(in, pin, out, pout, M, shift, mask, hist, n_tiles);
+        }
+        CK(cudaGetLastError());
+        u64* t = in; in = out; out = t;
+        u32* tp = pin; pin = pout; pout = tp;
+    }
+    *keys = in;
+    *pay = pin;
+    return G2N_OK;
+}
+
+size_t dtype_size(int dt)
+{
+    switch (dt) {
+        case G2N_DTYPE_F64: return 8;
+        case G2N_DTYPE_F32: return 4;
+        case G2N_DTYPE_I32: return 4;
+        default: return 1;
+    }
+}
+
+// sorted keys -> indptr / indices / data (device).  w_typed: already-cast weights indexed by payload.
+template <typename T>
+int reduce_typed(g2n_handle* h, const u64* keys, const u32* pay, const double* w_f64, const T* w_typed, u64 M, int sym, int mbits, u64 n)
+{
+    CK(h->val.ensure((M + 1) * sizeof(T)));
+    CK(h->flag.ensure((M + 1) * sizeof(u32)));
+    CK(h->pos.ensure((M + 2) * sizeof(u32)));
+    CK(h->major_count.ensure((n + 2) * sizeof(u32)));
+    CK(h->indptr.ensure((n + 2) * sizeof(int32_t)));
+    CK(h->indices.ensure((M + 1) * sizeof(int32_t)));
+    CK(h->data.ensure((M + 1) * sizeof(T)));
+    { KScope ks(h, "k_group_reduce"); k_group_reduce<T><<<grid_for(M, 256), 256, 0, h->stream>>>(keys, pay, w_f64, w_typed, M, sym, h->val.as<T>(), h->flag.as<u32>()); }
+    CK(cudaGetLastError());
+    LoadArray<u32> ldf{h->flag.as<u32>()};
+    int rc = launch_scan<u32>(h, ldf, h->pos.as<u32>(), M);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(h->major_count.p, 0, (n + 2) * sizeof(u32), h->stream));
+    { KScope ks(h, "k_compact"); k_compact<T><<<grid_for(M, 256), 256, 0, h->stream>>>(keys, h->val.as<T>(), h->flag.as<u32>(), h->pos.as<u32>(), M, mbits,
+                                                          h->indices.as<int32_t>(), h->data.as<T>(), h->major_count.as<u32>()); }
+    CK(cudaGetLastError());
+    LoadArray<u32> ldc{h->major_count.as<u32>()};
+    rc = launch_scan<int32_t>(h, ldc, h->indptr.as<int32_t>(), n);
+    if (rc) return rc;
+    // nnz = pos[M]
+    CK(cudaMemcpyAsync(&h->h_tail[0], h->pos.as<u32>() + M, sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
+    return G2N_OK;
+}
+
+int reduce_dispatch(g2n_handle* h, int dtype, const u64* keys, const u32* pay, const double* w_f64, const void* w_typed, u64 M, int sym,
+                    int mbits, u64 n)
+{
+    switch (dtype) {
+        case G2N_DTYPE_F64: return reduce_typed<double>(h, keys, pay, w_f64, (const double*)w_typed, M, sym, mbits, n);
+        case G2N_DTYPE_F32: return reduce_typed<float>(h, keys, pay, w_f64, (const float*)w_typed, M, sym, mbits, n);
+        case G2N_DTYPE_I32: return reduce_typed<int32_t>(h, keys, pay, w_f64, (const int32_t*)w_typed, M, sym, mbits, n);
+        case G2N_DTYPE_I8: return reduce_typed<int8_t>(h, keys, pay, w_f64, (const int8_t*)w_typed, M, sym, mbits, n);
+        case G2N_DTYPE_BOOL: return reduce_typed<BoolT>(h, keys, pay, w_f64, (const BoolT*)w_typed, M, sym, mbits, n);
+    }
+    h->err = "unknown dtype";
+    return G2N_ERR_INVALID;
+}
+
+int empty_compressed(g2n_handle* h, u64 n)
+{
+    CK(h->indptr.ensure((n + 2) * sizeof(int32_t)));
+    CK(cudaMemsetAsync(h->indptr.p, 0, (n + 2) * sizeof(int32_t), h->stream));
+    CK(h->indices.ensure(16));
+    CK(h->data.ensure(16));
+    h->h_tail[0] = 0;
+    return G2N_OK;
+}
+
+EmitParams emit_params(g2n_handle* h)
+{
+    EmitParams E;
+    E.edge_slots = h->edge_slots.as<u32>();
+    E.edge_w = h->params.weight_tag_len > 0 ? h->edge_w.as<double>() : nullptr;
+    E.slot_id = h->slot_id.as<u32>();
+    E.n_edges = (u32)h->n_edges;
+    E.slots_per_edge = h->spe;
+    E.tpe = h->tpe;
+    return E;
+}
+
+// K3 + K4 for a compressed result of the current build.  fmt: G2N_FMT_CSR | G2N_FMT_CSC
+int build_compressed(g2n_handle* h, int fmt)
+{
+    const u64 n = h->n_nodes;
+    const u64 T = h->n_edges * (u64)h->tpe;
+    const int sym = h->symmax ? 1 : 0;
+    const u64 M = sym ? 2 * T : T;
+    h->result_format = fmt;
+    if (M == 0 || n == 0) {
+        int rc = empty_compressed(h, n);
+        CK(cudaEventRecord(h->ev[EV_EMIT], h->stream));
+        CK(cudaEventRecord(h->ev[EV_SORT], h->stream));
+        CK(cudaEventRecord(h->ev[EV_REDUCE], h->stream));
+        return rc;
+    }
+    if (M >= 0xFFFFFFF0ull) { h->err = "more than 2^32 triplets in one build"; return G2N_ERR_UNSUPPORTED; }
+    const bool weighted = h->params.weight_tag_len > 0;
+    const int mbits = ceil_log2(n);
+    CK(h->keysA.ensure((M + 1) * sizeof(u64)));
+    CK(h->keysB.ensure((M + 1) * sizeof(u64)));
+    if (weighted) {
+        CK(h->payA.ensure((M + 1) * sizeof(u32)));
+        CK(h->payB.ensure((M + 1) * sizeof(u32)));
+    }
+    // for a symmetric result CSC arrays equal CSR arrays; sort by row either way
+    const int csc = (!sym && fmt == G2N_FMT_CSC) ? 1 : 0;
+    { KScope ks(h, "k_emit_keys"); k_emit_keys<<<grid_for(T, 256), 256, 0, h->stream>>>(emit_params(h), sym, csc, mbits, h->keysA.as<u64>(), weighted ? h->payA.as<u32>() : nullptr); }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev[EV_EMIT], h->stream));
+    u64* keys;
+    u32* pay;
+    int rc = radix_sort(h, M, 2 * mbits, weighted, &keys, &pay);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev[EV_SORT], h->stream));
+    rc = reduce_dispatch(h, h->params.dtype, keys, pay, weighted ? h->edge_w.as<double>() : nullptr, nullptr, M, sym, mbits, n);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev[EV_REDUCE], h->stream));
+    return G2N_OK;
+}
+
+template <typename T>
+int emit_coo_typed(g2n_handle* h, u64 T_)
+{
+    CK(h->data.ensure((T_ + 1) * sizeof(T)));
+    { KScope ks(h, "k_emit_coo"); k_emit_coo<T><<<grid_for(T_, 256), 256, 0, h->stream>>>(emit_params(h), h->row.as<int32_t>(), h->col.as<int32_t>(), h->data.as<T>()); }
+    CK(cudaGetLastError());
+    return G2N_OK;
+}
+
+int build_coo(g2n_handle* h)
+{
+    const u64 T = h->n_edges * (u64)h->tpe;
+    h->result_format = G2N_FMT_COO;
+    CK(h->row.ensure((T + 1) * sizeof(int32_t)));
+    CK(h->col.ensure((T + 1) * sizeof(int32_t)));
+    int rc = G2N_OK;
+    if (T > 0) {
+        switch (h->params.dtype) {
+            case G2N_DTYPE_F64: rc = emit_coo_typed<double>(h, T); break;
+            case G2N_DTYPE_F32: rc = emit_coo_typed<float>(h, T); break;
+            case G2N_DTYPE_I32: rc = emit_coo_typed<int32_t>(h, T); break;
+            case G2N_DTYPE_I8: rc = emit_coo_typed<int8_t>(h, T); break;
+            case G2N_DTYPE_BOOL: rc = emit_coo_typed<BoolT>(h, T); break;
+            default: h->err = "unknown dtype"; return G2N_ERR_INVALID;
+        }
+    } else {
+        CK(h->data.ensure(16));
+    }
+    h->h_tail[0] = T;
+    CK(cudaEventRecord(h->ev[EV_EMIT], h->stream));
+    CK(cudaEventRecord(h->ev[EV_SORT], h->stream));
+    CK(cudaEventRecord(h->ev[EV_REDUCE], h->stream));
+    return rc;
+}
+
+int finish_result(g2n_handle* h)
+{
+    CK(cudaStreamSynchronize(h->stream));
+    h->nnz = (h->result_format == G2N_FMT_COO) ? h->h_tail[0] : (u64)(u32)h->h_tail[0];
+    h->names_bytes = h->h_tail[1];
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev[EV_START], h->ev[EV_REDUCE]);
+    h->diag.ms_total = ms;
+    cudaEventElapsedTime(&h->diag.ms_h2d, h->ev[EV_START], h->ev[EV_H2D]);
+    cudaEventElapsedTime(&h->diag.ms_stage[0], h->ev[EV_H2D], h->ev[EV_TOKENIZE]);
+    cudaEventElapsedTime(&h->diag.ms_stage[1], h->ev[EV_TOKENIZE], h->ev[EV_IDS]);
+    cudaEventElapsedTime(&h->diag.ms_stage[3], h->ev[EV_IDS], h->ev[EV_EMIT]);
+    cudaEventElapsedTime(&h->diag.ms_stage[4], h->ev[EV_EMIT], h->ev[EV_SORT]);
+    cudaEventElapsedTime(&h->diag.ms_stage[5], h->ev[EV_SORT], h->ev[EV_REDUCE]);
+    h->diag.gpu_launches = h->launches;
+    h->diag.n_triplets = h->n_edges * (u64)h->tpe;
+    return G2N_OK;
+}
+
+}  // namespace
+
+// =====================================================================================
+extern "C" {
+
+int g2n_abi_version(void) { return G2N_ABI_VERSION; }
+
+int g2n_create(int device, g2n_handle** out)
+{
+    if (!out) return G2N_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return G2N_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return G2N_ERR_CUDA;
+    g2n_handle* h = new g2n_handle();
+    h->device = device;
+    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return G2N_ERR_CUDA; }
+    h->stream = h->own_stream;
+    for (int i = 0; i < EV_COUNT; i++) cudaEventCreate(&h->ev[i]);
+    if (cudaHostAlloc((void**)&h->h_cnt, sizeof(Counters), cudaHostAllocDefault) != cudaSuccess ||
+        cudaHostAlloc((void**)&h->h_tail, 4 * sizeof(u64), cudaHostAllocDefault) != cudaSuccess) {
+        delete h;
+        return G2N_ERR_CUDA;
+    }
+    memset(&h->diag, 0, sizeof(h->diag));
+    h->diag.unknown_byte = -1;
+    *out = h;
+    return G2N_OK;
+}
+
+void g2n_destroy(g2n_handle* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    DevBuf* bufs[] = {&h->text, &h->table, &h->edge_slots, &h->edge_w, &h->longs, &h->tile_state, &h->cnt, &h->bitmap, &h->wprefix,
+                      &h->slot_id, &h->id2slot, &h->name_len, &h->name_off, &h->names, &h->keysA, &h->keysB, &h->payA, &h->payB,
+                      &h->tile_hist, &h->val, &h->flag, &h->pos, &h->major_count, &h->indptr, &h->indices, &h->data, &h->row, &h->col,
+                      &h->scan_state, &h->up_row, &h->up_col, &h->up_data};
+    for (DevBuf* b : bufs) b->release();
+    for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(h->ev[i]);
+    for (KTimer& t : h->ktimers) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    if (h->h_cnt) cudaFreeHost(h->h_cnt);
+    if (h->h_tail) cudaFreeHost(h->h_tail);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+int g2n_set_stream(g2n_handle* h, void* cuda_stream)
+{
+    if (!h) return G2N_ERR_INVALID;
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return G2N_OK;
+}
+
+void* g2n_host_alloc(uint64_t nbytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, nbytes ? nbytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void g2n_host_free(void* p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+int g2n_set_profile(g2n_handle* h, int on)
+{
+    if (!h) return G2N_ERR_INVALID;
+    h->profile = on != 0;
+    return G2N_OK;
+}
+
+int g2n_kernel_times(g2n_handle* h, g2n_ktime* out, int cap)
+{
+    if (!h || (!out && cap > 0)) return -1;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    int n = 0;
+    for (size_t i = 0; i < h->kt_used; i++) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, h->ktimers[i].a, h->ktimers[i].b) != cudaSuccess) continue;
+        int j = 0;
+        for (; j < n; j++)
+            if (strcmp(out[j].name, h->ktimers[i].name) == 0) break;
+        if (j == n) {
+            if (n >= cap) continue;
+            memset(&out[n], 0, sizeof(out[n]));
+            strncpy(out[n].name, h->ktimers[i].name, sizeof(out[n].name) - 1);
+            n++;
+        }
+        out[j].ms += ms;
+        out[j].launches++;
+    }
+    return n;
+}
+
+const char* g2n_last_error(g2n_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int g2n_status(g2n_handle* h, g2n_diag* out)
+{
+    if (!h || !out) return G2N_ERR_INVALID;
+    *out = h->diag;
+    return G2N_OK;
+}
+
+int g2n_build(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n_params* p)
+{
+    if (!h || !p || (!text && nbytes)) return G2N_ERR_INVALID;
+    h->err.clear();
+    h->built = false;
+    h->have_edges = false;
+    h->names_ready = false;
+    if (p->dtype < G2N_DTYPE_F64 || p->dtype > G2N_DTYPE_BOOL) { h->err = "unknown dtype"; return G2N_ERR_INVALID; }
+    if (p->want_format < G2N_FMT_NATIVE || p->want_format > G2N_FMT_CSC) { h->err = "unknown want_format"; return G2N_ERR_INVALID; }
+    if (p->weight_tag_len > 64) { h->err = "weight tag longer than 64 bytes"; return G2N_ERR_UNSUPPORTED; }
+    if (nbytes >= (1ull << 46)) { h->err = "input larger than 2^46 bytes"; return G2N_ERR_UNSUPPORTED; }
+    h->params = *p;
+    if (p->weight_tag && p->weight_tag_len > 0) memcpy(h->weight_tag, p->weight_tag, p->weight_tag_len);
+    else h->params.weight_tag_len = 0;
+    h->params.weight_tag = h->weight_tag;
+    CK(cudaSetDevice(h->device));
+    h->launches = 0;
+    h->kt_used = 0;
+    memset(&h->diag, 0, sizeof(h->diag));
+    h->diag.unknown_byte = -1;
+
+    CK(cudaEventRecord(h->ev[EV_START], h->stream));
+    if (p->text_on_device) {
+        h->d_text = text;
+    } else {
+        CK(h->text.ensure(nbytes + 64));
+        if (nbytes) CK(cudaMemcpyAsync(h->text.p, text, nbytes, cudaMemcpyHostToDevice, h->stream));
+        h->d_text = h->text.as<uint8_t>();
+    }
+    h->nbytes = nbytes;
+    CK(cudaEventRecord(h->ev[EV_H2D], h->stream));
+
+    const bool graph_directed = p->keep_directed_bidir || (!p->bidirected && p->directed);  // builders.py:143
+    h->symmax = graph_directed && !p->asymmetric;                                           // builders.py:282
+    h->spe = (p->bidirected && !p->keep_directed_bidir) ? 4 : 2;
+    h->tpe = graph_directed ? 1 : (h->spe == 4 ? 4 : 2);
+    const bool weighted = h->params.weight_tag_len > 0;
+
+    const u64 n_tiles64 = (nbytes + TK_TILE - 1) / TK_TILE;
+    const u32 n_tiles = (u32)n_tiles64;
+    u64 keys_cap = h->hint_keys ? h->hint_keys + h->hint_keys / 16 + 64 : nbytes / 24 + 1024;
+    u64 edge_cap = h->hint_edges ? h->hint_edges + 64 : nbytes / 20 + 1024;
+    u64 long_cap = h->hint_long ? h->hint_long + h->hint_long / 4 + 1024 : 65536;
+    u64 seed = 0x51ed270b7a2d4c1full;
+    Counters& hc = *h->h_cnt;
+    for (u32 attempt = 0;; attempt++) {
+        if (attempt > 12) { h->err = "capacity retry limit exceeded"; return G2N_ERR_INTERNAL; }
+        h->diag.retries = attempt;
+        if (edge_cap > 0xFFFFFFF0ull) { h->err = "more than 2^32 edge records"; return G2N_ERR_UNSUPPORTED; }
+        const u32 cap = next_pow2(2 * keys_cap < 1024 ? 1024 : 2 * keys_cap);
+        if (2 * keys_cap > (1ull << 31)) { h->err = "more than 2^30 distinct node keys"; return G2N_ERR_UNSUPPORTED; }
+        h->table_cap = cap;
+        CK(h->table.ensure((size_t)cap * sizeof(Slot)));
+        CK(cudaMemsetAsync(h->table.p, 0, (size_t)cap * sizeof(Slot), h->stream));
+        CK(h->edge_slots.ensure((edge_cap + 1) * h->spe * sizeof(u32)));
+        if (weighted) CK(h->edge_w.ensure((edge_cap + 1) * sizeof(double)));
+        CK(h->longs.ensure((long_cap + 1) * sizeof(LongDesc)));
+        CK(h->tile_state.ensure(((size_t)n_tiles + 1) * sizeof(u64)));
+        CK(cudaMemsetAsync(h->tile_state.p, 0, ((size_t)n_tiles + 1) * sizeof(u64), h->stream));
+        CK(h->cnt.ensure(sizeof(Counters)));
+        memset(&hc, 0, sizeof(hc));
+        hc.first_error = ~0ull;
+        hc.first_unknown = ~0ull;
+        CK(cudaMemcpyAsync(h->cnt.p, &hc, sizeof(Counters), cudaMemcpyHostToDevice, h->stream));
+        if (n_tiles > 0) {
+            ScanParams P;
+            memset(&P, 0, sizeof(P));
+            P.text = h->d_text;
+            P.nbytes = nbytes;
+            P.table = h->table.as<Slot>();
+            P.table_mask = cap - 1;
+            P.table_max_keys = (u32)(cap / 2 + cap / 8);
+            P.edge_slots = h->edge_slots.as<u32>();
+            P.edge_w = weighted ? h->edge_w.as<double>() : nullptr;
+            P.edge_cap = (u32)edge_cap;
+            P.longs = h->longs.as<LongDesc>();
+            P.long_cap = (u32)long_cap;
+            P.tile_state = h->tile_state.as<u64>();
+            P.cnt = h->cnt.as<Counters>();
+            P.n_tiles = n_tiles;
+            P.bidirected = p->bidirected ? 1 : 0;
+            P.slots_per_edge = h->spe;
+            P.strip_orientation = p->strip_orientation ? 1 : 0;
+            P.wt_len = h->params.weight_tag_len;
+            P.seed = seed;
+            memcpy(P.wt, h->weight_tag, sizeof(P.wt));
+            { KScope ks(h, "k_tokenize"); k_tokenize<<<grid_for(n_tiles, 1, 4), TK_THREADS, 0, h->stream>>>(P); }
+            CK(cudaGetLastError());
+        }
+        CK(cudaEventRecord(h->ev[EV_TOKENIZE], h->stream));
+        CK(cudaMemcpyAsync(&hc, h->cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        bool retry = false;
+        if (hc.flags & CF_TABLE_FULL) { keys_cap = keys_cap * 4 > hc.n_keys * 2ull ? keys_cap * 4 : hc.n_keys * 2ull; retry = true; }
+        if (hc.flags & CF_EDGE_FULL) { edge_cap = (u64)hc.n_edges + 64; retry = true; }
+        if (hc.flags & CF_LONG_FULL) { long_cap = (u64)hc.n_long * 2 + 1024; retry = true; }
+        if (!retry && hc.collision) { seed = seed * 6364136223846793005ull + 1442695040888963407ull; retry = true; }
+        if (!retry) break;
+    }
+    h->hint_keys = hc.n_keys;
+    h->hint_edges = hc.n_edges;
+    h->hint_long = hc.n_long;
+    // ---- diagnostics: first error / first unknown record in file order
+    h->diag.n_records = hc.n_records;
+    h->diag.n_edge_records = hc.n_edges;
+    h->diag.n_long_keys = hc.n_long;
+    if (hc.first_error != ~0ull) {
+        h->diag.err_kind = (int32_t)(hc.first_error & 0xFF);
+        h->diag.err_offset = hc.first_error >> 8;
+    }
+    if (hc.first_unknown != ~0ull && (hc.first_error == ~0ull || (hc.first_unknown >> 8) < (hc.first_error >> 8))) {
+        h->diag.unknown_byte = (int32_t)(hc.first_unknown & 0xFF);
+        h->diag.unknown_offset = hc.first_unknown >> 8;
+    }
+    if (h->diag.err_kind) {
+        h->diag.gpu_launches = h->launches;
+        h->err = "input holds a record the reference raises on";
+        return G2N_ERR_PARSE;
+    }
+    const u64 n = hc.n_keys;
+    const u64 E = hc.n_edges;
+    const u64 R = hc.n_records;
+    if (n > 0x7FFFFFFFull) { h->err = "more than 2^31-1 nodes (int64 indices) is out of scope"; return G2N_ERR_UNSUPPORTED; }
+    h->n_nodes = n;
+    h->n_edges = E;
+    // ---- K2: node IDs
+    const u32 cap = h->table_cap;
+    const u64 words = (4 * R + 31) / 32 + 1;
+    CK(h->bitmap.ensure(words * sizeof(u32)));
+    CK(h->wprefix.ensure((words + 2) * sizeof(u32)));
+    CK(h->slot_id.ensure((size_t)cap * sizeof(u32)));
+    CK(h->id2slot.ensure((n + 1) * sizeof(u32)));
+    CK(h->name_len.ensure((n + 1) * sizeof(u32)));
+    CK(h->name_off.ensure((n + 2) * sizeof(u64)));
+    if (n > 0) {
+        CK(cudaMemsetAsync(h->bitmap.p, 0, words * sizeof(u32), h->stream));
+        { KScope ks(h, "k_mark_first"); k_mark_first<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->table.as<Slot>(), cap, h->bitmap.as<u32>()); }
+        LoadPopc lp{h->bitmap.as<u32>()};
+        int rc = launch_scan<u32>(h, lp, h->wprefix.as<u32>(), words);
+        if (rc) return rc;
+        { KScope ks(h, "k_assign_ids"); k_assign_ids<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->table.as<Slot>(), cap, h->bitmap.as<u32>(), h->wprefix.as<u32>(),
+                                                                 h->slot_id.as<u32>(), h->id2slot.as<u32>(), h->name_len.as<u32>()); }
+        CK(cudaGetLastError());
+        LoadArray<u32> ln{h->name_len.as<u32>()};
+        rc = launch_scan<u64>(h, ln, (u64*)h->name_off.as<u64>(), n);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(&h->h_tail[1], h->name_off.as<u64>() + n, sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
+    } else {
+        CK(cudaMemsetAsync(h->name_off.p, 0, 2 * sizeof(u64), h->stream));
+        h->h_tail[1] = 0;
+    }
+    CK(cudaEventRecord(h->ev[EV_IDS], h->stream));
+    h->have_edges = true;
+    // ---- K3 + K4
+    int rc;
+    if (h->symmax) rc = build_compressed(h, p->want_format == G2N_FMT_CSC ? G2N_FMT_CSC : G2N_FMT_CSR);
+    else if (p->want_format == G2N_FMT_NATIVE) rc = build_coo(h);
+    else rc = build_compressed(h, p->want_format);
+    if (rc) return rc;
+    rc = finish_result(h);
+    if (rc) return rc;
+    h->built = true;
+    return G2N_OK;
+}
+
+int g2n_convert(g2n_handle* h, int32_t want_format)
+{
+    if (!h || !h->built || !h->have_edges) return G2N_ERR_INVALID;
+    if (want_format != G2N_FMT_CSR && want_format != G2N_FMT_CSC) { h->err = "convert target must be CSR or CSC"; return G2N_ERR_INVALID; }
+    CK(cudaSetDevice(h->device));
+    if (h->result_format == want_format) return G2N_OK;
+    if (h->symmax) { h->result_format = want_format; return G2N_OK; }  // symmetric: same arrays
+    CK(cudaEventRecord(h->ev[EV_START], h->stream));
+    CK(cudaEventRecord(h->ev[EV_H2D], h->stream));
+    CK(cudaEventRecord(h->ev[EV_TOKENIZE], h->stream));
+    CK(cudaEventRecord(h->ev[EV_IDS], h->stream));
+    int rc = build_compressed(h, want_format);
+    if (rc) return rc;
+    const u64 keep_names = h->names_bytes;
+    h->h_tail[1] = keep_names;
+    return finish_result(h);
+}
+
+int g2n_sizes(g2n_handle* h, g2n_sizes_t* out)
+{
+    if (!h || !out || !h->built) return G2N_ERR_INVALID;
+    out->n_nodes = h->n_nodes;
+    out->nnz = h->nnz;
+    out->names_bytes = h->names_bytes;
+    out->format = h->result_format;
+    out->index_bytes = 4;
+    out->dtype = h->params.dtype;
+    out->reserved = 0;
+    return G2N_OK;
+}
+
+int g2n_device_result(g2n_handle* h, void** a0, void** a1, void** data)
+{
+    if (!h || !h->built) return G2N_ERR_INVALID;
+    const bool coo = h->result_format == G2N_FMT_COO;
+    if (a0) *a0 = coo ? h->row.p : h->indptr.p;
+    if (a1) *a1 = coo ? h->col.p : h->indices.p;
+    if (data) *data = h->data.p;
+    return G2N_OK;
+}
+
+int g2n_fetch_matrix(g2n_handle* h, void* a0, void* a1, void* data)
+{
+    if (!h || !h->built) return G2N_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    const size_t ds = dtype_size(h->params.dtype);
+    if (h->result_format == G2N_FMT_COO) {
+        if (h->nnz) {
+            CK(cudaMemcpyAsync(a0, h->row.p, h->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaMemcpyAsync(a1, h->col.p, h->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaMemcpyAsync(data, h->data.p, h->nnz * ds, cudaMemcpyDeviceToHost, h->stream));
+        }
+    } else {
+        CK(cudaMemcpyAsync(a0, h->indptr.p, (h->n_nodes + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        if (h->nnz) {
+            CK(cudaMemcpyAsync(a1, h->indices.p, h->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaMemcpyAsync(data, h->data.p, h->nnz * ds, cudaMemcpyDeviceToHost, h->stream));
+        }
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return G2N_OK;
+}
+
+int g2n_fetch_names(g2n_handle* h, uint8_t* names, uint64_t* offsets)
+{
+    if (!h || !h->built) return G2N_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (!h->names_ready) {
+        CK(h->names.ensure(h->names_bytes + 16));
+        if (h->n_nodes > 0) {
+            { KScope ks(h, "k_gather_names"); k_gather_names<<<grid_for(h->n_nodes, 256), 256, 0, h->stream>>>(h->table.as<Slot>(), h->id2slot.as<u32>(), h->name_off.as<u64>(),
+                                                                              (u32)h->n_nodes, h->d_text, h->longs.as<LongDesc>(),
+                                                                              h->names.as<uint8_t>()); }
+            CK(cudaGetLastError());
+        }
+        h->names_ready = true;
+    }
+    CK(cudaMemcpyAsync(offsets, h->name_off.p, (h->n_nodes + 1) * sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
+    if (h->names_bytes) CK(cudaMemcpyAsync(names, h->names.p, h->names_bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return G2N_OK;
+}
+
+int g2n_coo_to_compressed(g2n_handle* h, const int32_t* row, const int32_t* col, const void* data, uint64_t nnz_in, uint64_t n,
+                          int32_t dtype, int32_t want_format, int32_t* indptr, int32_t* indices, void* data_out, uint64_t* nnz_out)
+{
+    if (!h || !indptr || !nnz_out) return G2N_ERR_INVALID;
+    if (want_format != G2N_FMT_CSR && want_format != G2N_FMT_CSC) { h->err = "target must be CSR or CSC"; return G2N_ERR_INVALID; }
+    if (dtype < G2N_DTYPE_F64 || dtype > G2N_DTYPE_BOOL) { h->err = "unknown dtype"; return G2N_ERR_INVALID; }
+    if (n > 0x7FFFFFFFull || nnz_in >= 0xFFFFFFF0ull) { h->err = "int64 indices are out of scope"; return G2N_ERR_UNSUPPORTED; }
+    CK(cudaSetDevice(h->device));
+    h->built = false;
+    h->have_edges = false;
+    const size_t ds = dtype_size(dtype);
+    if (nnz_in == 0 || n == 0) {
+        memset(indptr, 0, (n + 1) * sizeof(int32_t));
+        *nnz_out = 0;
+        return G2N_OK;
+    }
+    CK(h->up_row.ensure(nnz_in * sizeof(int32_t)));
+    CK(h->up_col.ensure(nnz_in * sizeof(int32_t)));
+    CK(h->up_data.ensure(nnz_in * ds));
+    CK(cudaMemcpyAsync(h->up_row.p, row, nnz_in * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->up_col.p, col, nnz_in * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->up_data.p, data, nnz_in * ds, cudaMemcpyHostToDevice, h->stream));
+    const int mbits = ceil_log2(n);
+    CK(h->keysA.ensure((nnz_in + 1) * sizeof(u64)));
+    CK(h->keysB.ensure((nnz_in + 1) * sizeof(u64)));
+    CK(h->payA.ensure((nnz_in + 1) * sizeof(u32)));
+    CK(h->payB.ensure((nnz_in + 1) * sizeof(u32)));
+    KScope ks_keys(h, "k_keys_from_coo");
+    k_keys_from_coo<<<grid_for(nnz_in, 256), 256, 0, h->stream>>>(h->up_row.as<int32_t>(), h->up_col.as<int32_t>(), nnz_in,
+                                                                 want_format == G2N_FMT_CSC ? 1 : 0, mbits, h->keysA.as<u64>(), h->payA.as<u32>());
+    CK(cudaGetLastError());
+    u64* keys;
+    u32* pay;
+    int rc = radix_sort(h, nnz_in, 2 * mbits, true, &keys, &pay);
+    if (rc) return rc;
+    rc = reduce_dispatch(h, dtype, keys, pay, nullptr, h->up_data.p, nnz_in, 0, mbits, n);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    const u64 nnz = (u32)h->h_tail[0];
+    *nnz_out = nnz;
+    CK(cudaMemcpyAsync(indptr, h->indptr.p, (n + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (nnz) {
+        CK(cudaMemcpyAsync(indices, h->indices.p, nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(data_out, h->data.p, nnz * ds, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return G2N_OK;
+}
+
+}  // extern "C"

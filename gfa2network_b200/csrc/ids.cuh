@@ -1,0 +1,154 @@
+// ids.cuh -- K2b: first-appearance ranking -> node IDs and the node-name table; K3: COO emission.
+//
+// Node IDs reproduce the reference's `node2idx[n] = len(node2idx)` (builders.py:194-198, 219-221):
+// every key's slot holds the minimum order (record ordinal << 2 | sub-rank) over all its mentions;
+// one bit per (record, sub-rank) marks the positions that are first appearances, and a key's ID is
+// the number of marked bits below its own.  Triplet order follows add_mat_edge (builders.py:218-234).
+#pragma once
+#include "tokenize.cuh"
+
+namespace g2n {
+
+// bit (order) of `bitmap` set for every occupied slot
+__global__ void __launch_bounds__(256) k_mark_first(const Slot* __restrict__ table, u32 cap, u32* __restrict__ bitmap)
+{
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+        const Slot s = table[i];
+        if (s.k0 == 0 && s.k1 == 0) continue;
+        const u64 order = ~s.first_inv;
+        atomicOr(&bitmap[order >> 5], 1u << (order & 31));
+    }
+}
+
+__device__ __forceinline__ u32 slot_key_len(const Slot& s)
+{
+    const u32 top = (u32)(s.k1 >> 56);
+    return top == 0xFF ? (u32)((s.k1 >> 32) & 0xFFFFFF) : top - 1;
+}
+
+// slot -> id ; id -> slot ; id -> name length
+__global__ void __launch_bounds__(256) k_assign_ids(const Slot* __restrict__ table, u32 cap, const u32* __restrict__ bitmap,
+                                                     const u32* __restrict__ wprefix, u32* __restrict__ slot_id,
+                                                     u32* __restrict__ id2slot, u32* __restrict__ name_len)
+{
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+        const Slot s = table[i];
+        if (s.k0 == 0 && s.k1 == 0) continue;
+        const u64 order = ~s.first_inv;
+        const u32 wd = (u32)(order >> 5), bit = (u32)(order & 31);
+        const u32 id = wprefix[wd] + __popc(bitmap[wd] & ((1u << bit) - 1u));
+        slot_id[i] = id;
+        id2slot[id] = i;
+        name_len[id] = slot_key_len(s);
+    }
+}
+
+// names[name_off[id] ...] = key bytes of node id (builders.py:284-288 node list, raw bytes)
+__global__ void __launch_bounds__(256) k_gather_names(const Slot* __restrict__ table, const u32* __restrict__ id2slot,
+                                                       const u64* __restrict__ name_off, u32 n, const uint8_t* __restrict__ text,
+                                                       const LongDesc* __restrict__ longs, uint8_t* __restrict__ names)
+{
+    for (u32 id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
+        const Slot s = table[id2slot[id]];
+        uint8_t* dst = names + name_off[id];
+        const u32 top = (u32)(s.k1 >> 56);
+        if (top != 0xFF) {
+            const u32 L = top - 1;
+            for (u32 j = 0; j < L; j++) dst[j] = (uint8_t)((j < 8 ? s.k0 >> (8 * j) : s.k1 >> (8 * (j - 8))) & 0xFF);
+        } else {
+            const LongDesc d = longs[s.rep - 1];
+            const u32 L = d.base_len + (d.has_ori ? 1 + d.ori_len : 0);
+            for (u32 j = 0; j < L; j++) dst[j] = long_byte(text, d, j);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- dtype helpers
+// The reference casts the float64 weight list to `dtype` when the COO matrix is built
+// (builders.py:281 -> scipy/_coo.py), i.e. BEFORE duplicates are summed.
+struct BoolT { uint8_t v; };
+
+template <typename T> __device__ __forceinline__ T cast_weight(double w) { return (T)w; }
+template <> __device__ __forceinline__ int8_t cast_weight<int8_t>(double w) { return (int8_t)(int)w; }
+template <> __device__ __forceinline__ BoolT cast_weight<BoolT>(double w) { BoolT b; b.v = (w != 0.0) ? 1 : 0; return b; }
+
+template <typename T> __device__ __forceinline__ T add_t(T a, T b) { return a + b; }
+template <> __device__ __forceinline__ int8_t add_t<int8_t>(int8_t a, int8_t b) { return (int8_t)((int)a + (int)b); }
+template <> __device__ __forceinline__ BoolT add_t<BoolT>(BoolT a, BoolT b) { BoolT r; r.v = a.v | b.v; return r; }  // npy_bool_wrapper +
+template <typename T> __device__ __forceinline__ bool lt_t(T a, T b) { return a < b; }
+template <> __device__ __forceinline__ bool lt_t<BoolT>(BoolT a, BoolT b) { return a.v < b.v; }
+template <typename T> __device__ __forceinline__ bool nz_t(T a) { return a != (T)0; }
+template <> __device__ __forceinline__ bool nz_t<BoolT>(BoolT a) { return a.v != 0; }
+template <typename T> __device__ __forceinline__ T zero_t() { return (T)0; }
+template <> __device__ __forceinline__ BoolT zero_t<BoolT>() { BoolT b; b.v = 0; return b; }
+
+// ---------------------------------------------------------------- K3: emission
+struct EmitParams {
+    const u32* edge_slots;
+    const double* edge_w;  // NULL when no weight tag: every weight is 1.0
+    const u32* slot_id;
+    u32 n_edges;
+    int slots_per_edge;    // 2 | 4
+    int tpe;               // triplets per edge record: 1 (graph_directed) | 2 | 4
+};
+
+__device__ __forceinline__ void edge_triplet(const EmitParams& E, u32 e, int k, u32& r, u32& c)
+{
+    // builders.py:222-234: (a,b) [, (b,a)] [, (c,d), (d,c)] with c = v:flip(ot), d = u:flip(of)
+    const u32* s = E.edge_slots + (u64)e * E.slots_per_edge;
+    const u32 a = E.slot_id[s[(k & 2)]], b = E.slot_id[s[(k & 2) + 1]];
+    if (k & 1) { r = b; c = a; } else { r = a; c = b; }
+}
+
+// raw COO in emission order: row, col (int32) and data (dtype)
+template <typename T>
+__global__ void __launch_bounds__(256) k_emit_coo(const EmitParams E, int32_t* __restrict__ row, int32_t* __restrict__ col, T* __restrict__ data)
+{
+    const u64 total = (u64)E.n_edges * E.tpe;
+    for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (u64)gridDim.x * blockDim.x) {
+        const u32 e = (u32)(t / E.tpe);
+        const int k = (int)(t % E.tpe);
+        u32 r, c;
+        edge_triplet(E, e, k, r, c);
+        row[t] = (int32_t)r;
+        col[t] = (int32_t)c;
+        data[t] = cast_weight<T>(E.edge_w ? E.edge_w[e] : 1.0);
+    }
+}
+
+// Sort keys for the compressed build.  key = ((major << mbits | minor) << 1) | dir ; payload = edge index.
+//   sym == 0: one key per triplet, major = row (CSR) or col (CSC)                    (utils.py:55 tocsr/tocsc)
+//   sym == 1: two keys per triplet: (row, col, dir 0) and (col, row, dir 1)         (builders.py:283 maximum(A, A.T))
+__global__ void __launch_bounds__(256) k_emit_keys(const EmitParams E, int sym, int csc, int mbits, u64* __restrict__ keys, u32* __restrict__ payload)
+{
+    const u64 total = (u64)E.n_edges * E.tpe;
+    for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (u64)gridDim.x * blockDim.x) {
+        const u32 e = (u32)(t / E.tpe);
+        const int k = (int)(t % E.tpe);
+        u32 r, c;
+        edge_triplet(E, e, k, r, c);
+        if (sym) {
+            keys[2 * t] = ((((u64)r << mbits) | c) << 1);
+            keys[2 * t + 1] = ((((u64)c << mbits) | r) << 1) | 1ull;
+            if (payload) { payload[2 * t] = e; payload[2 * t + 1] = e; }
+        } else {
+            const u32 major = csc ? c : r, minor = csc ? r : c;
+            keys[t] = (((u64)major << mbits) | minor) << 1;
+            if (payload) payload[t] = e;
+        }
+    }
+}
+
+// Same, from caller-provided COO arrays (g2n_coo_to_compressed): payload = triplet index.
+__global__ void __launch_bounds__(256) k_keys_from_coo(const int32_t* __restrict__ row, const int32_t* __restrict__ col, u64 nnz,
+                                                        int csc, int mbits, u64* __restrict__ keys, u32* __restrict__ payload)
+{
+    for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < nnz; t += (u64)gridDim.x * blockDim.x) {
+        const u32 r = (u32)row[t], c = (u32)col[t];
+        const u32 major = csc ? c : r, minor = csc ? r : c;
+        keys[t] = (((u64)major << mbits) | minor) << 1;
+        payload[t] = (u32)t;
+    }
+}
+
+}  // namespace g2n

@@ -1,0 +1,168 @@
+/*
+ * g2n.h -- C ABI of the B200-native GFA -> sparse adjacency path (libg2n.so).
+ *
+ * The reference (sclipman/gfa2network) is pure Python and has no FFI of its own; the
+ * boundary it exposes for this path is
+ *     gfa2network/builders.py:30-50   parse_gfa(path, *, build_matrix=True, directed, weight_tag,
+ *                                     strip_orientation, bidirected, keep_directed_bidir, dtype,
+ *                                     asymmetric, raw_bytes_id, return_node_list, ...)
+ *     gfa2network/utils.py:40-63      convert_format(A, fmt)
+ *     gfa2network/cli.py:193-250      `gfa2network convert --matrix ... --matrix-format ...`
+ * Each entry point below names the reference lines it replaces.  The Python host mirror
+ * (gfa2network_b200/builders.py, utils.py, cli.py) binds these with ctypes; INTEGRATION.md
+ * shows the stub a maintainer of the reference would add.
+ *
+ * Conventions: extern "C", plain pointers and sizes, int status returns (0 = G2N_OK).
+ * The caller allocates every output buffer after g2n_sizes(); the library never frees
+ * caller memory and owns all device scratch for the handle's lifetime.  A handle is not
+ * thread-safe; separate handles may be used from separate threads.  There is no CPU
+ * fallback: without a CUDA device g2n_create fails with G2N_ERR_CUDA.
+ */
+#ifndef G2N_H
+#define G2N_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define G2N_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------------- */
+#define G2N_OK 0
+#define G2N_ERR_CUDA 1        /* CUDA runtime failure: g2n_last_error() has the driver string */
+#define G2N_ERR_INVALID 2     /* bad argument / call order */
+#define G2N_ERR_PARSE 3       /* the input holds a record the reference raises on: see g2n_diag */
+#define G2N_ERR_UNSUPPORTED 4 /* declared out of scope (e.g. > 2^31-1 nodes, weight tag > 64 bytes) */
+#define G2N_ERR_INTERNAL 5
+
+/* ---- first-error kinds (g2n_diag.err_kind); map 1:1 to the reference's exceptions ------ */
+#define G2N_PE_NONE 0
+#define G2N_PE_MALFORMED_L 1      /* ValueError("Malformed L record")   parser.py:208-209 */
+#define G2N_PE_MALFORMED_E 2      /* ValueError("Malformed E record")   parser.py:251-252 */
+#define G2N_PE_MALFORMED_C 3      /* ValueError("Malformed C record")   parser.py:299-300 */
+#define G2N_PE_MALFORMED_P 4      /* ValueError("Malformed P record")   parser.py:231-232 */
+#define G2N_PE_MALFORMED_O 5      /* ValueError("Malformed O record")   parser.py:345-346 */
+#define G2N_PE_S_NO_ID 6          /* IndexError  fields[1]              parser.py:163 */
+#define G2N_PE_COMPACT_EMPTY 7    /* IndexError  u_field[-1] on b""     parser.py:220-221 */
+#define G2N_PE_ORI_UTF8 8         /* UnicodeDecodeError  ori.decode()   parser.py:214,291,293,337,339 */
+#define G2N_PE_WEIGHT_OVERFLOW 9  /* OverflowError float(int)           builders.py:209 */
+#define G2N_PE_UNSUPPORTED_NUM 10 /* non-ASCII numeric weight value: outside parity scope, loud */
+
+/* ---- enums -------------------------------------------------------------------------- */
+#define G2N_DTYPE_F64 0
+#define G2N_DTYPE_F32 1
+#define G2N_DTYPE_I32 2
+#define G2N_DTYPE_I8 3
+#define G2N_DTYPE_BOOL 4
+
+#define G2N_FMT_NATIVE 0 /* what parse_gfa returns: CSR for sym-max modes, raw COO otherwise (builders.py:281-283) */
+#define G2N_FMT_CSR 1    /* convert_format(parse_gfa(...), "csr")  (utils.py:55) */
+#define G2N_FMT_CSC 2    /* convert_format(parse_gfa(...), "csc") */
+#define G2N_FMT_COO 3    /* result format code only: raw COO triplets in emission order */
+
+typedef struct g2n_handle g2n_handle;
+
+/* Mirrors the keyword arguments of parse_gfa that reach the matrix path (builders.py:30-50). */
+typedef struct g2n_params {
+    int32_t directed;            /* builders.py:35 */
+    int32_t bidirected;          /* builders.py:41 */
+    int32_t keep_directed_bidir; /* builders.py:42 */
+    int32_t asymmetric;          /* builders.py:45 */
+    int32_t strip_orientation;   /* builders.py:39 */
+    int32_t dtype;               /* G2N_DTYPE_*  (builders.py:44, cli.py:92-97) */
+    int32_t want_format;         /* G2N_FMT_NATIVE | G2N_FMT_CSR | G2N_FMT_CSC */
+    int32_t text_on_device;      /* 1: `text` is a device pointer on the handle's device */
+    const uint8_t *weight_tag;   /* UTF-8 bytes of weight_tag or NULL (builders.py:36, 205-209) */
+    int32_t weight_tag_len;
+    int32_t reserved;
+} g2n_params;
+
+typedef struct g2n_sizes_t {
+    uint64_t n_nodes;
+    uint64_t nnz;          /* stored entries of the result (raw triplets for COO) */
+    uint64_t names_bytes;  /* total bytes of all node names */
+    int32_t format;        /* G2N_FMT_CSR | G2N_FMT_CSC | G2N_FMT_COO */
+    int32_t index_bytes;   /* 4 (SciPy picks int32 below 2^31-1; larger is G2N_ERR_UNSUPPORTED) */
+    int32_t dtype;         /* G2N_DTYPE_* of the data array */
+    int32_t reserved;
+} g2n_sizes_t;
+
+typedef struct g2n_diag {
+    int32_t err_kind;        /* G2N_PE_* of the first offending line in file order, 0 if none */
+    int32_t unknown_byte;    /* first byte of the first unsupported record (parser.py:125-131) that
+                                precedes the error line, -1 if none */
+    uint64_t err_offset;     /* byte offset of the start of the offending line */
+    uint64_t unknown_offset; /* byte offset of that unsupported record */
+    uint64_t n_records;      /* records the reference's parser would have yielded (S L E C P O) */
+    uint64_t n_edge_records; /* L + E + C */
+    uint64_t n_triplets;     /* COO triplets emitted (builders.py:222-228) */
+    uint64_t n_long_keys;    /* node keys longer than the 15-byte inline form */
+    uint32_t retries;        /* capacity / hash-seed retries of the last build */
+    uint32_t gpu_launches;   /* kernels launched by the last build */
+    float ms_total;          /* device time of the last build, CUDA events on the handle's stream */
+    float ms_h2d;            /* host->device copy of the text (0 when text_on_device) */
+    float ms_stage[8];       /* scan+hash, ids, names, emit, sort, reduce, (spare) */
+} g2n_diag;
+
+/* Create a handle on CUDA device `device`.  Fails (G2N_ERR_CUDA) without a usable GPU. */
+int g2n_create(int device, g2n_handle **out);
+void g2n_destroy(g2n_handle *h);
+
+/* Use an existing CUDA stream (cudaStream_t) for all work of this handle; NULL = handle's own. */
+int g2n_set_stream(g2n_handle *h, void *cuda_stream);
+
+/* Pinned host staging memory (so callers can read files straight into DMA-able buffers). */
+void *g2n_host_alloc(uint64_t nbytes);
+void g2n_host_free(void *p);
+
+/* The hot path.  Replaces the tokenizer loop (parser.py:114-176), node-ID assignment and triplet
+ * emission (builders.py:163-234), coo_matrix + maximum(A, A.T) (builders.py:279-283) and, when
+ * want_format is CSR/CSC, convert_format (utils.py:40-63).  Results stay resident on the device
+ * until the next build or g2n_destroy.  On G2N_ERR_PARSE consult g2n_status(). */
+int g2n_build(g2n_handle *h, const uint8_t *text, uint64_t nbytes, const g2n_params *p);
+
+/* Convert the device-resident raw COO of the last build to CSR/CSC in place of calling
+ * convert_format(A, fmt) on the host (utils.py:55).  No-op if already in that format. */
+int g2n_convert(g2n_handle *h, int32_t want_format);
+
+int g2n_sizes(g2n_handle *h, g2n_sizes_t *out);
+
+/* Copy the result to caller memory.  CSR/CSC: a0 = indptr (n_nodes+1), a1 = indices (nnz);
+ * COO: a0 = row (nnz), a1 = col (nnz); data = nnz elements of the result dtype. */
+int g2n_fetch_matrix(g2n_handle *h, void *a0, void *a1, void *data);
+
+/* Node names in ID order (builders.py:284-288): `names` = names_bytes bytes,
+ * `offsets` = n_nodes+1 uint64 offsets into it. */
+int g2n_fetch_names(g2n_handle *h, uint8_t *names, uint64_t *offsets);
+
+/* Device pointers of the resident result (for device-side consumers / benchmarks). */
+int g2n_device_result(g2n_handle *h, void **a0, void **a1, void **data);
+
+/* Per-kernel timing of the last build (CUDA event pair around every launch, on the handle's
+ * stream).  g2n_set_profile(h, 1) turns it on; g2n_kernel_times fills up to `cap` entries
+ * (one per kernel name: summed milliseconds and launch count) and returns how many. */
+typedef struct g2n_ktime {
+    char name[40];
+    float ms;
+    uint32_t launches;
+} g2n_ktime;
+int g2n_set_profile(g2n_handle *h, int on);
+int g2n_kernel_times(g2n_handle *h, g2n_ktime *out, int cap);
+
+int g2n_status(g2n_handle *h, g2n_diag *out);
+const char *g2n_last_error(g2n_handle *h);
+int g2n_abi_version(void);
+
+/* Standalone stage 4 (SciPy COO -> CSR/CSC with duplicate summing, utils.py:55 on a user matrix):
+ * host COO arrays in, host compressed arrays out.  *nnz_out receives the stored-entry count;
+ * indptr has n+1 entries; indices/data need capacity nnz_in. */
+int g2n_coo_to_compressed(g2n_handle *h, const int32_t *row, const int32_t *col, const void *data,
+                          uint64_t nnz_in, uint64_t n, int32_t dtype, int32_t want_format,
+                          int32_t *indptr, int32_t *indices, void *data_out, uint64_t *nnz_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* G2N_H */

@@ -293,6 +293,7 @@ static int py_float(const uint8_t *s, int64_t n, double *out)
 static int weight_from_tags(const span_t *fields, int nf, int first, const ora_params *pr, int *has_w, double *w)
 {
     *has_w = 0;
+    int huge = 0;
     if (!pr->weight_tag || pr->weight_tag_len == 0) return 0;
     for (int i = first; i < nf; i++) {
         const uint8_t *f = fields[i].p;
@@ -314,20 +315,23 @@ static int weight_from_tags(const span_t *fields, int nf, int first, const ora_p
             int64_t nd; int neg;
             if (py_int_syntax(val, vlen, buf, &nd, &neg)) {
                 double d = strtod(buf, NULL); /* == float(int(value)), round-half-even */
-                if (isinf(d)) { free(buf); return ORA_ERR_WEIGHT_OVERFLOW; }
+                /* an int too large for a double only raises (builders.py:209) if a later tag
+                 * does not overwrite it: remember it as +-inf, checked after the loop */
+                huge = isinf(d);
                 *w = neg ? -d : d; *has_w = 1;
             } /* else: ValueError -> entry left unchanged (parser.py:190-191) */
             free(buf);
         } else if (typlen == 1 && c1[1] == 'f') {
             if (!all_ascii(val, vlen)) return ORA_ERR_UNSUPPORTED_NUM;
             double d;
-            if (py_float(val, vlen, &d)) { *w = d; *has_w = 1; }
+            if (py_float(val, vlen, &d)) { *w = d; *has_w = 1; huge = 0; }
         } else {
             /* B -> list, anything else -> str: not int/float, so weight falls back to 1.0
              * (builders.py:208) and overrides any earlier numeric value (dict overwrite) */
-            *has_w = 0;
+            *has_w = 0; huge = 0;
         }
     }
+    if (*has_w && huge) return ORA_ERR_WEIGHT_OVERFLOW;
     return 0;
 }
 

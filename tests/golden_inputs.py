@@ -91,6 +91,7 @@ LITERAL_CASES: list[tuple[str, bytes]] = [
     ("weights_signs", b"L\ta\t+\tb\t+\t0M\tRC:f:-2.5\nL\tb\t+\ta\t+\t0M\tRC:f:1.5\nL\tc\t+\td\t+\t0M\tRC:i:0\nL\td\t+\te\t+\t0M\tRC:i:-4\n"
                       b"L\te\t+\tf\t+\t0M\tRC:i:2\nL\te\t+\tf\t+\t0M\tRC:i:-2\nL\tf\t+\te\t+\t0M\tRC:i:-7\n"),
     ("weight_overflow", b"S\ta\t*\nL\ta\t+\tb\t+\t0M\tRC:i:" + b"9" * 400 + b"\n"),
+    ("weight_overflow_overwritten", b"L\ta\t+\tb\t+\t0M\tRC:i:" + b"9" * 400 + b"\tRC:i:5\nL\ta\t+\tc\t+\t0M\tRC:i:-" + b"9" * 400 + b"\tRC:Z:x\n"),
     ("weight_int_digit_limit", b"L\ta\t+\tb\t+\t0M\tRC:i:3\tRC:i:" + b"1" * 4301 + b"\n"),
     ("weight_float_long", b"L\ta\t+\tb\t+\t0M\tRC:f:" + b"1" * 400 + b"\nL\ta\t+\tc\t+\t0M\tRC:f:0." + b"0" * 400 + b"7\n"),
     ("weight_bad_utf8_tag", b"L\ta\t+\tb\t+\t0M\tRC:i:5\tRC:i:\xff9\nL\ta\t+\tc\t+\t0M\tR\xc3\xa9:i:5\tRC:f:3\n"),

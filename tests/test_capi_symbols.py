@@ -1,0 +1,63 @@
+"""CPU-only checks of the boundary: the C-ABI library builds, loads and exports every symbol
+include/g2n.h declares; the product path fails loudly without a GPU (no CPU fallback)."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _declared():
+    text = (ROOT / "include" / "g2n.h").read_text()
+    return sorted(set(re.findall(r"\b(g2n_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from gfa2network_b200 import _capi
+
+    lib = _capi.load()
+    names = _declared()
+    assert len(names) >= 14
+    for name in names:
+        assert hasattr(lib, name), name
+    assert sorted(_capi.EXPORTS) == names
+    assert lib.g2n_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    from gfa2network_b200 import _capi
+
+    assert ctypes.sizeof(_capi.Params) == 48
+    assert ctypes.sizeof(_capi.Sizes) == 40
+    assert ctypes.sizeof(_capi.Diag) == 104
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from gfa2network_b200 import _capi, parse_gfa
+
+    with pytest.raises(_capi.G2NError, match="no CPU fallback"):
+        parse_gfa(b"S\ta\t*\n", build_graph=False, build_matrix=True)
+
+
+def test_out_of_scope_arguments_fail_loudly():
+    from gfa2network_b200 import parse_gfa
+
+    with pytest.raises(ValueError, match="return_node_list requires build_matrix=True"):
+        parse_gfa(b"", build_graph=False, build_matrix=False, return_node_list=True)
+    for kw in (dict(backend="igraph"), dict(split_on_alignment=True)):
+        with pytest.raises(NotImplementedError):
+            parse_gfa(b"", build_graph=False, build_matrix=True, **kw)
+    with pytest.raises(NotImplementedError):
+        parse_gfa(b"", build_graph=True, build_matrix=True)
+
+
+def test_product_never_imports_oracle():
+    for p in (ROOT / "gfa2network_b200").rglob("*"):
+        if p.suffix in {".py", ".cu", ".cuh", ".h", ".c"}:
+            assert "oracle" not in p.read_text().replace("CPU oracle", "").replace("the oracle", "").lower() or p.name in {"synth.c", "synth.py"}, p
