@@ -47,6 +47,7 @@ class Diag(C.Structure):
         ("n_records", C.c_uint64), ("n_edge_records", C.c_uint64), ("n_triplets", C.c_uint64),
         ("n_long_keys", C.c_uint64), ("retries", C.c_uint32), ("gpu_launches", C.c_uint32),
         ("ms_total", C.c_float), ("ms_h2d", C.c_float), ("ms_stage", C.c_float * 8),
+        ("warn_flags", C.c_uint32), ("reserved", C.c_uint32),
     ]
 
 

@@ -209,6 +209,9 @@ def parse_gfa(
     handle.check(rc)
     if verbose:
         print("\r[parse_gfa] done")  # builders.py:261
+    if build_matrix and diag.warn_flags & 1:
+        # NumPy's float64 -> float32 list cast inside sp.coo_matrix (builders.py:281)
+        warnings.warn("overflow encountered in cast", RuntimeWarning, stacklevel=2)
     if not build_matrix:
         return None
     session = _Session(handle)

@@ -556,6 +556,7 @@ int g2n_build(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n_par
             P.slots_per_edge = h->spe;
             P.strip_orientation = p->strip_orientation ? 1 : 0;
             P.wt_len = h->params.weight_tag_len;
+            P.dtype = p->dtype;
             P.seed = seed;
             memcpy(P.wt, h->weight_tag, sizeof(P.wt));
             { KScope ks(h, "k_tokenize"); k_tokenize<<<grid_for(n_tiles, 1, 4), TK_THREADS, 0, h->stream>>>(P); }
@@ -578,6 +579,7 @@ int g2n_build(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n_par
     h->diag.n_records = hc.n_records;
     h->diag.n_edge_records = hc.n_edges;
     h->diag.n_long_keys = hc.n_long;
+    if (hc.flags & CF_CAST_OVERFLOW) h->diag.warn_flags |= G2N_WARN_CAST_OVERFLOW;
     if (hc.first_error != ~0ull) {
         h->diag.err_kind = (int32_t)(hc.first_error & 0xFF);
         h->diag.err_offset = hc.first_error >> 8;

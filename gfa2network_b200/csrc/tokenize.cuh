@@ -61,6 +61,7 @@ struct Counters {
 #define CF_TABLE_FULL 1u
 #define CF_EDGE_FULL 2u
 #define CF_LONG_FULL 4u
+#define CF_CAST_OVERFLOW 8u
 
 struct ScanParams {
     const uint8_t* text;
@@ -80,6 +81,7 @@ struct ScanParams {
     int slots_per_edge;  // 2, or 4 for bidirected without keep_directed_bidir
     int strip_orientation;
     int wt_len;
+    int dtype;  // G2N_DTYPE_* the weights will be cast to (only used to flag float32 overflow)
     u64 seed;
     uint8_t wt[64];
 };
@@ -494,7 +496,11 @@ __device__ __forceinline__ void parse_line(const ScanParams& P, const Win& w, u6
         } else {
             reinterpret_cast<uint2*>(P.edge_slots)[edge_ord] = make_uint2(su, sv);
         }
-        if (want_w) P.edge_w[edge_ord] = ws.has ? ws.w : 1.0;
+        if (want_w) {
+            const double wv = ws.has ? ws.w : 1.0;
+            P.edge_w[edge_ord] = wv;
+            if (P.dtype == G2N_DTYPE_F32 && isfinite(wv) && isinf((float)wv)) atomicOr(&P.cnt->flags, CF_CAST_OVERFLOW);
+        }
     }
 }
 
@@ -539,7 +545,7 @@ __global__ void __launch_bounds__(TK_THREADS) k_tokenize(const ScanParams P)
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const u32 eq = __vcmpeq4(ww[k], 0x0A0A0A0Au) & 0x01010101u;  // 1 per matching byte
-                    const u32 bits = (eq * 0x08040201u) >> 24;                  // gather to 4 bits
+                    const u32 bits = (eq * 0x01020408u) >> 24;                  // gather to 4 bits (byte k -> bit k)
                     m |= (bits & 0xF) << (4 * k);
                 }
                 reinterpret_cast<unsigned short*>(s_nl)[piece - 1] = (unsigned short)m;

@@ -104,7 +104,12 @@ typedef struct g2n_diag {
     float ms_total;          /* device time of the last build, CUDA events on the handle's stream */
     float ms_h2d;            /* host->device copy of the text (0 when text_on_device) */
     float ms_stage[8];       /* scan+hash, ids, names, emit, sort, reduce, (spare) */
+    uint32_t warn_flags;     /* G2N_WARN_* */
+    uint32_t reserved;
 } g2n_diag;
+
+#define G2N_WARN_CAST_OVERFLOW 1u /* a finite float64 weight became inf in the float32 cast: NumPy's
+                                     RuntimeWarning("overflow encountered in cast") at builders.py:281 */
 
 /* Create a handle on CUDA device `device`.  Fails (G2N_ERR_CUDA) without a usable GPU. */
 int g2n_create(int device, g2n_handle **out);

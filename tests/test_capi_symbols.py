@@ -31,7 +31,7 @@ def test_struct_layouts_match_header():
 
     assert ctypes.sizeof(_capi.Params) == 48
     assert ctypes.sizeof(_capi.Sizes) == 40
-    assert ctypes.sizeof(_capi.Diag) == 104
+    assert ctypes.sizeof(_capi.Diag) == 112
 
 
 def test_no_cpu_fallback():
