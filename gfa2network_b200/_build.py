@@ -33,7 +33,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not Path(nvcc).exists():
         raise RuntimeError("nvcc not found: libg2n.so cannot be built (there is no CPU fallback)")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB), str(CSRC / "g2n.cu")]
+    extra = os.environ.get("G2N_NVCC_EXTRA", "").split()
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-o", str(LIB), str(CSRC / "g2n.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -35,6 +35,27 @@ __device__ __forceinline__ uint4 ld_nc_v4(const void* p)
                  : "l"(p));
     return r;
 }
+// L2 eviction-priority policies: streamed input must not push the hash table out of the 126 MB L2
+__device__ __forceinline__ u64 policy_evict_first()
+{
+    u64 pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ u64 policy_evict_last()
+{
+    u64 pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint4 ld_stream_v4(const void* p, u64 pol)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
 
 // ---------------------------------------------------------------- warp / block scans
 __device__ __forceinline__ u32 warp_incl_scan(u32 v)
@@ -85,27 +106,47 @@ __device__ __forceinline__ u64 block_excl_scan64(u64 v, u64* sm, u64* total)
 #define LB_INC (2ull << 62)
 #define LB_VAL(x) ((x) & ((1ull << 62) - 1))
 
-// Called by ONE thread of the block that owns `tile` (tiles are handed out by an atomic ticket, so
-// every predecessor is already running).  Publishes `agg`, resolves and returns the exclusive prefix.
+__device__ __forceinline__ u64 warp_sum64(u64 v)
+{
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+// Called by all 32 lanes of ONE warp of the block that owns `tile` (tiles are handed out by an atomic
+// ticket, so every predecessor is already running).  Publishes `agg`, resolves and returns the
+// exclusive prefix (in every lane).  32 predecessors are inspected per round.
 __device__ __forceinline__ u64 lookback_exclusive(u64* state, u32 tile, u64 agg)
 {
+    const u32 lane = threadIdx.x & 31;
     if (tile == 0) {
-        st_volatile_u64(&state[0], LB_INC | agg);
+        if (lane == 0) st_volatile_u64(&state[0], LB_INC | agg);
         return 0;
     }
-    st_volatile_u64(&state[tile], LB_AGG | agg);
+    if (lane == 0) st_volatile_u64(&state[tile], LB_AGG | agg);
     u64 excl = 0;
-    int t = (int)tile - 1;
+    long long base = (long long)tile - 1;
     while (true) {
-        u64 s = ld_volatile_u64(&state[t]);
+        const long long idx = base - (long long)lane;
+        const u64 s = idx >= 0 ? ld_volatile_u64(&state[idx]) : LB_INC;  // virtual tile -1: inclusive 0
         const u64 flag = s >> 62;
-        if (flag == 0) continue;  // predecessor has not published yet
-        excl += LB_VAL(s);
-        if (flag == 2) break;
-        t--;
+        const u32 ready = __ballot_sync(0xffffffffu, flag != 0);
+        const u32 inc = __ballot_sync(0xffffffffu, flag == 2);
+        if (inc) {
+            const int first = __ffs(inc) - 1;  // nearest predecessor holding an inclusive prefix
+            const u32 need = first == 31 ? 0xffffffffu : ((2u << first) - 1u);
+            if ((ready & need) != need) continue;  // a nearer tile has not published yet
+            excl += warp_sum64((int)lane <= first ? LB_VAL(s) : 0ull);
+            break;
+        }
+        if (ready != 0xffffffffu) continue;
+        excl += warp_sum64(LB_VAL(s));
+        base -= 32;
     }
-    __threadfence();
-    st_volatile_u64(&state[tile], LB_INC | (excl + agg));
+    if (lane == 0) {
+        __threadfence();
+        st_volatile_u64(&state[tile], LB_INC | (excl + agg));
+    }
     return excl;
 }
 
@@ -138,7 +179,10 @@ __global__ void __launch_bounds__(256) k_scan_exclusive(LoadOp load, Tout* __res
         }
         u64 total;
         u64 excl = block_excl_scan64(sum, sm, &total);
-        if (threadIdx.x == 0) s_base = lookback_exclusive(state, tile, total);
+        if (threadIdx.x < 32) {
+            const u64 e = lookback_exclusive(state, tile, total);
+            if (threadIdx.x == 0) s_base = e;
+        }
         __syncthreads();
         u64 run = s_base + excl;
 #pragma unroll

@@ -59,13 +59,13 @@ struct g2n_handle {
     std::string err;
     cudaEvent_t ev[EV_COUNT];
     // device buffers (kept between builds: a warm handle allocates nothing)
-    DevBuf text, table, edge_slots, edge_w, longs, tile_state, cnt, bitmap, wprefix, slot_id, id2slot, name_len, name_off, names;
+    DevBuf text, table, tfirst, trep, defer, edge_slots, edge_w, longs, tile_state, cnt, bitmap, wprefix, slot_id, id2slot, name_len, name_off, names;
     DevBuf keysA, keysB, payA, payB, tile_hist, val, flag, pos, major_count, indptr, indices, data, row, col, scan_state;
     DevBuf up_row, up_col, up_data;
     Counters* h_cnt = nullptr;  // pinned
     u64* h_tail = nullptr;      // pinned: {nnz, names_bytes}
     // capacity hints learnt from previous builds
-    u64 hint_keys = 0, hint_edges = 0, hint_long = 0;
+    u64 hint_keys = 0, hint_edges = 0, hint_long = 0, hint_defer = 0;
     // state of the last build
     g2n_params params;
     uint8_t weight_tag[64];
@@ -400,7 +400,7 @@ void g2n_destroy(g2n_handle* h)
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf* bufs[] = {&h->text, &h->table, &h->edge_slots, &h->edge_w, &h->longs, &h->tile_state, &h->cnt, &h->bitmap, &h->wprefix,
+    DevBuf* bufs[] = {&h->text, &h->table, &h->tfirst, &h->trep, &h->defer, &h->edge_slots, &h->edge_w, &h->longs, &h->tile_state, &h->cnt, &h->bitmap, &h->wprefix,
                       &h->slot_id, &h->id2slot, &h->name_len, &h->name_off, &h->names, &h->keysA, &h->keysB, &h->payA, &h->payB,
                       &h->tile_hist, &h->val, &h->flag, &h->pos, &h->major_count, &h->indptr, &h->indices, &h->data, &h->row, &h->col,
                       &h->scan_state, &h->up_row, &h->up_col, &h->up_data};
@@ -486,6 +486,8 @@ int g2n_build(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n_par
     h->params = *p;
     if (p->weight_tag && p->weight_tag_len > 0) memcpy(h->weight_tag, p->weight_tag, p->weight_tag_len);
     else h->params.weight_tag_len = 0;
+    for (int i = 0; i < h->params.weight_tag_len; i++)
+        if (h->weight_tag[i] == ':') { h->params.weight_tag_len = 0; break; }  // tag names never hold ':' (parser.py:184)
     h->params.weight_tag = h->weight_tag;
     CK(cudaSetDevice(h->device));
     h->launches = 0;
@@ -512,23 +514,31 @@ int g2n_build(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n_par
 
     const u64 n_tiles64 = (nbytes + TK_TILE - 1) / TK_TILE;
     const u32 n_tiles = (u32)n_tiles64;
-    u64 keys_cap = h->hint_keys ? h->hint_keys + h->hint_keys / 16 + 64 : nbytes / 24 + 1024;
+    u64 keys_cap = h->hint_keys ? h->hint_keys + 64 : nbytes / 24 + 1024;
     u64 edge_cap = h->hint_edges ? h->hint_edges + 64 : nbytes / 20 + 1024;
     u64 long_cap = h->hint_long ? h->hint_long + h->hint_long / 4 + 1024 : 65536;
+    u64 defer_cap = h->hint_defer ? h->hint_defer + h->hint_defer / 4 + 1024 : (nbytes / 2048 > 65536 ? nbytes / 2048 : 65536);
     u64 seed = 0x51ed270b7a2d4c1full;
     Counters& hc = *h->h_cnt;
     for (u32 attempt = 0;; attempt++) {
         if (attempt > 12) { h->err = "capacity retry limit exceeded"; return G2N_ERR_INTERNAL; }
         h->diag.retries = attempt;
         if (edge_cap > 0xFFFFFFF0ull) { h->err = "more than 2^32 edge records"; return G2N_ERR_UNSUPPORTED; }
-        const u32 cap = next_pow2(2 * keys_cap < 1024 ? 1024 : 2 * keys_cap);
-        if (2 * keys_cap > (1ull << 31)) { h->err = "more than 2^30 distinct node keys"; return G2N_ERR_UNSUPPORTED; }
+        // load factor in (0.35, 0.7]: the smaller the table, the more of it stays resident in L2
+        const u64 want_slots = keys_cap + keys_cap / 2 - keys_cap / 16;
+        const u32 cap = next_pow2(want_slots < 1024 ? 1024 : want_slots);
+        if (want_slots > (1ull << 31)) { h->err = "more than 2^30 distinct node keys"; return G2N_ERR_UNSUPPORTED; }
         h->table_cap = cap;
-        CK(h->table.ensure((size_t)cap * sizeof(Slot)));
-        CK(cudaMemsetAsync(h->table.p, 0, (size_t)cap * sizeof(Slot), h->stream));
+        CK(h->table.ensure((size_t)cap * sizeof(TKey)));
+        CK(h->tfirst.ensure((size_t)cap * sizeof(u32)));
+        CK(h->trep.ensure((size_t)cap * sizeof(u32)));
+        CK(cudaMemsetAsync(h->table.p, 0, (size_t)cap * sizeof(TKey), h->stream));
+        CK(cudaMemsetAsync(h->tfirst.p, 0, (size_t)cap * sizeof(u32), h->stream));
+        CK(cudaMemsetAsync(h->trep.p, 0, (size_t)cap * sizeof(u32), h->stream));
         CK(h->edge_slots.ensure((edge_cap + 1) * h->spe * sizeof(u32)));
         if (weighted) CK(h->edge_w.ensure((edge_cap + 1) * sizeof(double)));
         CK(h->longs.ensure((long_cap + 1) * sizeof(LongDesc)));
+        CK(h->defer.ensure((defer_cap + 1) * sizeof(DeferEnt)));
         CK(h->tile_state.ensure(((size_t)n_tiles + 1) * sizeof(u64)));
         CK(cudaMemsetAsync(h->tile_state.p, 0, ((size_t)n_tiles + 1) * sizeof(u64), h->stream));
         CK(h->cnt.ensure(sizeof(Counters)));
@@ -536,19 +546,23 @@ int g2n_build(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n_par
         hc.first_error = ~0ull;
         hc.first_unknown = ~0ull;
         CK(cudaMemcpyAsync(h->cnt.p, &hc, sizeof(Counters), cudaMemcpyHostToDevice, h->stream));
+        ScanParams P;
+        memset(&P, 0, sizeof(P));
         if (n_tiles > 0) {
-            ScanParams P;
-            memset(&P, 0, sizeof(P));
             P.text = h->d_text;
             P.nbytes = nbytes;
-            P.table = h->table.as<Slot>();
+            P.tkeys = h->table.as<TKey>();
+            P.tfirst = h->tfirst.as<u32>();
+            P.trep = h->trep.as<u32>();
             P.table_mask = cap - 1;
-            P.table_max_keys = (u32)(cap / 2 + cap / 8);
+            P.table_max_keys = (u32)(cap / 2 + cap / 4);
             P.edge_slots = h->edge_slots.as<u32>();
             P.edge_w = weighted ? h->edge_w.as<double>() : nullptr;
             P.edge_cap = (u32)edge_cap;
             P.longs = h->longs.as<LongDesc>();
             P.long_cap = (u32)long_cap;
+            P.defer = h->defer.as<DeferEnt>();
+            P.defer_cap = (u32)defer_cap;
             P.tile_state = h->tile_state.as<u64>();
             P.cnt = h->cnt.as<Counters>();
             P.n_tiles = n_tiles;
@@ -565,16 +579,31 @@ int g2n_build(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n_par
         CK(cudaEventRecord(h->ev[EV_TOKENIZE], h->stream));
         CK(cudaMemcpyAsync(&hc, h->cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
+        const u32 fatal = CF_TABLE_FULL | CF_EDGE_FULL | CF_LONG_FULL | CF_DEFER_FULL;
+        if (!(hc.flags & fatal) && hc.n_defer > 0) {
+            // lines the hot kernel handed over: generic byte-wise parser, one line per thread
+            { KScope ks(h, "k_tokenize_slow"); k_tokenize_slow<<<grid_for(hc.n_defer, 128), 128, 0, h->stream>>>(P, hc.n_defer); }
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(h->ev[EV_TOKENIZE], h->stream));
+            CK(cudaMemcpyAsync(&hc, h->cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+        }
         bool retry = false;
+        if (hc.flags & CF_DEFER_FULL) { defer_cap = defer_cap * 8 > (u64)hc.n_defer + 1024 ? defer_cap * 8 : (u64)hc.n_defer + 1024; retry = true; }
         if (hc.flags & CF_TABLE_FULL) { keys_cap = keys_cap * 4 > hc.n_keys * 2ull ? keys_cap * 4 : hc.n_keys * 2ull; retry = true; }
         if (hc.flags & CF_EDGE_FULL) { edge_cap = (u64)hc.n_edges + 64; retry = true; }
         if (hc.flags & CF_LONG_FULL) { long_cap = (u64)hc.n_long * 2 + 1024; retry = true; }
         if (!retry && hc.collision) { seed = seed * 6364136223846793005ull + 1442695040888963407ull; retry = true; }
         if (!retry) break;
     }
+#ifdef TK_TIMING
+    fprintf(stderr, "[tk_timing] cycles/CTA-sum: ticket %llu stage %llu pass1+scan %llu lookback %llu list+sync %llu pass2 %llu tail %llu\n",
+            hc.phase[0], hc.phase[1], hc.phase[2], hc.phase[3], hc.phase[4], hc.phase[5], hc.phase[6]);
+#endif
     h->hint_keys = hc.n_keys;
     h->hint_edges = hc.n_edges;
     h->hint_long = hc.n_long;
+    h->hint_defer = hc.n_defer;
     // ---- diagnostics: first error / first unknown record in file order
     h->diag.n_records = hc.n_records;
     h->diag.n_edge_records = hc.n_edges;
@@ -593,6 +622,7 @@ int g2n_build(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n_par
         h->err = "input holds a record the reference raises on";
         return G2N_ERR_PARSE;
     }
+    if (hc.n_records >= (1u << 30) - 1) { h->err = "more than 2^30 records in one build"; return G2N_ERR_UNSUPPORTED; }
     const u64 n = hc.n_keys;
     const u64 E = hc.n_edges;
     const u64 R = hc.n_records;
@@ -610,11 +640,11 @@ int g2n_build(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n_par
     CK(h->name_off.ensure((n + 2) * sizeof(u64)));
     if (n > 0) {
         CK(cudaMemsetAsync(h->bitmap.p, 0, words * sizeof(u32), h->stream));
-        { KScope ks(h, "k_mark_first"); k_mark_first<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->table.as<Slot>(), cap, h->bitmap.as<u32>()); }
+        { KScope ks(h, "k_mark_first"); k_mark_first<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->table.as<TKey>(), h->tfirst.as<u32>(), cap, h->bitmap.as<u32>()); }
         LoadPopc lp{h->bitmap.as<u32>()};
         int rc = launch_scan<u32>(h, lp, h->wprefix.as<u32>(), words);
         if (rc) return rc;
-        { KScope ks(h, "k_assign_ids"); k_assign_ids<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->table.as<Slot>(), cap, h->bitmap.as<u32>(), h->wprefix.as<u32>(),
+        { KScope ks(h, "k_assign_ids"); k_assign_ids<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->table.as<TKey>(), h->tfirst.as<u32>(), cap, h->bitmap.as<u32>(), h->wprefix.as<u32>(),
                                                                  h->slot_id.as<u32>(), h->id2slot.as<u32>(), h->name_len.as<u32>()); }
         CK(cudaGetLastError());
         LoadArray<u32> ln{h->name_len.as<u32>()};
@@ -709,7 +739,7 @@ int g2n_fetch_names(g2n_handle* h, uint8_t* names, uint64_t* offsets)
     if (!h->names_ready) {
         CK(h->names.ensure(h->names_bytes + 16));
         if (h->n_nodes > 0) {
-            { KScope ks(h, "k_gather_names"); k_gather_names<<<grid_for(h->n_nodes, 256), 256, 0, h->stream>>>(h->table.as<Slot>(), h->id2slot.as<u32>(), h->name_off.as<u64>(),
+            { KScope ks(h, "k_gather_names"); k_gather_names<<<grid_for(h->n_nodes, 256), 256, 0, h->stream>>>(h->table.as<TKey>(), h->trep.as<u32>(), h->id2slot.as<u32>(), h->name_off.as<u64>(),
                                                                               (u32)h->n_nodes, h->d_text, h->longs.as<LongDesc>(),
                                                                               h->names.as<uint8_t>()); }
             CK(cudaGetLastError());

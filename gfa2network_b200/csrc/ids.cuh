@@ -6,57 +6,61 @@
 // the number of marked bits below its own.  Triplet order follows add_mat_edge (builders.py:218-234).
 #pragma once
 #include "tokenize.cuh"
+#include "tokenize_slow.cuh"
 
 namespace g2n {
 
 // bit (order) of `bitmap` set for every occupied slot
-__global__ void __launch_bounds__(256) k_mark_first(const Slot* __restrict__ table, u32 cap, u32* __restrict__ bitmap)
+__global__ void __launch_bounds__(256) k_mark_first(const TKey* __restrict__ tkeys, const u32* __restrict__ tfirst, u32 cap,
+                                                     u32* __restrict__ bitmap)
 {
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
-        const Slot s = table[i];
-        if (s.k0 == 0 && s.k1 == 0) continue;
-        const u64 order = ~s.first_inv;
+        const TKey k = tkeys[i];
+        if (k.x == 0 && k.y == 0) continue;
+        const u32 order = ~tfirst[i];
         atomicOr(&bitmap[order >> 5], 1u << (order & 31));
     }
 }
 
-__device__ __forceinline__ u32 slot_key_len(const Slot& s)
+__device__ __forceinline__ u32 slot_key_len(u64 k1)
 {
-    const u32 top = (u32)(s.k1 >> 56);
-    return top == 0xFF ? (u32)((s.k1 >> 32) & 0xFFFFFF) : top - 1;
+    const u32 top = (u32)(k1 >> 56);
+    return top == 0xFF ? (u32)((k1 >> 32) & 0xFFFFFF) : top - 1;
 }
 
 // slot -> id ; id -> slot ; id -> name length
-__global__ void __launch_bounds__(256) k_assign_ids(const Slot* __restrict__ table, u32 cap, const u32* __restrict__ bitmap,
-                                                     const u32* __restrict__ wprefix, u32* __restrict__ slot_id,
-                                                     u32* __restrict__ id2slot, u32* __restrict__ name_len)
+__global__ void __launch_bounds__(256) k_assign_ids(const TKey* __restrict__ tkeys, const u32* __restrict__ tfirst, u32 cap,
+                                                     const u32* __restrict__ bitmap, const u32* __restrict__ wprefix,
+                                                     u32* __restrict__ slot_id, u32* __restrict__ id2slot, u32* __restrict__ name_len)
 {
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
-        const Slot s = table[i];
-        if (s.k0 == 0 && s.k1 == 0) continue;
-        const u64 order = ~s.first_inv;
-        const u32 wd = (u32)(order >> 5), bit = (u32)(order & 31);
+        const TKey k = tkeys[i];
+        if (k.x == 0 && k.y == 0) continue;
+        const u32 order = ~tfirst[i];
+        const u32 wd = order >> 5, bit = order & 31;
         const u32 id = wprefix[wd] + __popc(bitmap[wd] & ((1u << bit) - 1u));
         slot_id[i] = id;
         id2slot[id] = i;
-        name_len[id] = slot_key_len(s);
+        name_len[id] = slot_key_len(k.y);
     }
 }
 
 // names[name_off[id] ...] = key bytes of node id (builders.py:284-288 node list, raw bytes)
-__global__ void __launch_bounds__(256) k_gather_names(const Slot* __restrict__ table, const u32* __restrict__ id2slot,
-                                                       const u64* __restrict__ name_off, u32 n, const uint8_t* __restrict__ text,
-                                                       const LongDesc* __restrict__ longs, uint8_t* __restrict__ names)
+__global__ void __launch_bounds__(256) k_gather_names(const TKey* __restrict__ tkeys, const u32* __restrict__ trep,
+                                                       const u32* __restrict__ id2slot, const u64* __restrict__ name_off, u32 n,
+                                                       const uint8_t* __restrict__ text, const LongDesc* __restrict__ longs,
+                                                       uint8_t* __restrict__ names)
 {
     for (u32 id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
-        const Slot s = table[id2slot[id]];
+        const u32 slot = id2slot[id];
+        const TKey k = tkeys[slot];
         uint8_t* dst = names + name_off[id];
-        const u32 top = (u32)(s.k1 >> 56);
+        const u32 top = (u32)(k.y >> 56);
         if (top != 0xFF) {
             const u32 L = top - 1;
-            for (u32 j = 0; j < L; j++) dst[j] = (uint8_t)((j < 8 ? s.k0 >> (8 * j) : s.k1 >> (8 * (j - 8))) & 0xFF);
+            for (u32 j = 0; j < L; j++) dst[j] = (uint8_t)((j < 8 ? k.x >> (8 * j) : k.y >> (8 * (j - 8))) & 0xFF);
         } else {
-            const LongDesc d = longs[s.rep - 1];
+            const LongDesc d = longs[trep[slot] - 1];
             const u32 L = d.base_len + (d.has_ori ? 1 + d.ori_len : 0);
             for (u32 j = 0; j < L; j++) dst[j] = long_byte(text, d, j);
         }

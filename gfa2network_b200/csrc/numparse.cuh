@@ -259,7 +259,7 @@ G2N_HDN inline int parse_py_number(const Src& src, int64_t n, bool is_float, boo
         if (ne == 0) return NUM_BAD;
         exp10 += eneg ? -e : e;
     }
-    if (w == 0) { *out = bits_to_double(sign); return NUM_OK; }
+    if (w == 0) { *out = bits_to_double(is_float ? sign : 0); return NUM_OK; }  // float(int("-0")) is +0.0
     // decimal magnitude cut-offs (value = w.xxx * 10^(exp10 + nsig - 1 ...)); keep q in table range
     uint64_t bits;
     if (exp10 + nsig > 310) bits = 0x7FFull << 52;

@@ -1,0 +1,317 @@
+// table.cuh -- shared types of the tokenizer kernels and the GPU open-addressing hash of node keys.
+//
+// One pass over the text.  Each CTA takes 16 KiB byte tiles (ticketed, so a decoupled look-back can
+// carry the record / edge-record ordinals across tiles), stages the tile plus a look-ahead window in
+// shared memory, classifies newlines 16 bytes at a time, and lets each thread parse the lines that
+// START in its 64-byte chunk.  Node keys are inserted straight into an open-addressing table
+// (inline 15-byte keys, 128-bit CAS); the table keeps, per key, the minimum (record ordinal,
+// sub-rank) -- the reference's first-appearance order (builders.py:194-198, 219-221).
+//
+// Reference semantics implemented here (gfa2network/parser.py unless noted):
+//   :114-132  newline-only line split, first-byte filter, one-shot unknown-record warning
+//   :133-134  split on TAB; only a 1-byte first field matches a record type
+//   :135-163  S -> fields[1]           :206-227  L (GFA-1 and compact forms)
+//   :249-295  E (coord / orientation)  :297-341  C            :229-247, 343-361  P / O (field count only)
+//   :179-204  tags -> builders.py:205-209 weight
+//   builders.py:190-234  node registration order and (in emit.cuh) triplet order
+#pragma once
+#include "common.cuh"
+#include "numparse.cuh"
+#include "../../include/g2n.h"
+
+namespace g2n {
+
+#define TK_TILE 16384
+#define TK_LOOK 2016
+#define TK_PRE 32
+#define TK_WIN (TK_PRE + TK_TILE + TK_LOOK)
+#define TK_THREADS 256
+#define TK_CHUNK (TK_TILE / TK_THREADS)  // 64 bytes per thread
+#define TK_WORDS (TK_WIN / 32)           // 32-bit mask words covering the window
+#define TK_NF 0xFFFFFFFFu
+
+// Hash table: open addressing over 64-byte buckets of four 16-byte keys (two 256-bit loads per probe
+// step, issued together), structure-of-arrays so that the part every mention touches stays small
+// enough to live in L2 (1 M nodes: 32 MB of keys + 8 MB of `first`):
+//   tkeys[slot]  16-byte key: <= 15 inline bytes + (len+1) in the top byte, or a 0xFF-tagged hash for
+//                long keys
+//   tfirst[slot] ~min(order) as u32 (atomicMax, fire and forget); order = record_ordinal << 2 | sub-rank
+//   trep[slot]   long keys only: 1 + index of a LongDesc holding the key's bytes
+typedef ulonglong2 TKey;
+#define TB_SLOTS 4  // keys per bucket
+
+struct DeferEnt {
+    u64 off;  // global offset of the first byte of the line
+    u32 rec_ord, edge_ord;
+};
+
+struct LongDesc {
+    u64 base_off;
+    u64 ori_off;
+    u32 base_len;
+    u32 ori_len;   // bytes of the orientation string (may be 0)
+    u32 ori_char;  // used when ori_len == 1
+    u32 has_ori;   // 1: key is base + ':' + ori
+};
+
+struct Counters {
+    u64 first_error;    // min (line_offset << 8 | kind); ~0 if none
+    u64 first_unknown;  // min (line_offset << 8 | first byte); ~0 if none
+    u32 n_records;
+    u32 n_edges;
+    u32 n_keys;
+    u32 n_long;
+    u32 flags;
+    u32 ticket;
+    u32 scan_ticket;
+    u32 collision;
+    u32 n_defer;
+    u32 pad0;
+    u64 nnz;
+    u64 aux[4];
+    u64 phase[8];  // -DTK_TIMING: clock64() cycles per kernel phase, summed over CTAs (thread 0 view)
+};
+#define CF_TABLE_FULL 1u
+#define CF_EDGE_FULL 2u
+#define CF_LONG_FULL 4u
+#define CF_CAST_OVERFLOW 8u
+#define CF_DEFER_FULL 16u
+
+struct ScanParams {
+    const uint8_t* text;
+    u64 nbytes;
+    TKey* tkeys;
+    u32* tfirst;
+    u32* trep;
+    u32 table_mask;  // slots - 1 (slots is a power of two >= TB_SLOTS)
+    u32 table_max_keys;
+    u32* edge_slots;
+    double* edge_w;
+    u32 edge_cap;
+    LongDesc* longs;
+    u32 long_cap;
+    struct DeferEnt* defer;  // lines the hot kernel hands to k_tokenize_slow
+    u32 defer_cap;
+    u64* tile_state;
+    Counters* cnt;
+    u32 n_tiles;
+    int bidirected;
+    int slots_per_edge;  // 2, or 4 for bidirected without keep_directed_bidir
+    int strip_orientation;
+    int wt_len;
+    int dtype;  // G2N_DTYPE_* the weights will be cast to (only used to flag float32 overflow)
+    u64 seed;
+    uint8_t wt[64];
+};
+
+// ---------------------------------------------------------------- byte window
+struct Win {
+    const uint8_t* sm;  // shared-memory copy of [base, base + wlen), if any
+    const uint8_t* g;
+    u64 base;
+    u64 n;
+    u64 wlen;
+    __device__ __forceinline__ uint8_t operator()(u64 p) const
+    {
+        if (p >= n) return '\n';
+        const u64 d = p - base;
+        if (d < wlen) return sm[d];
+        return g[p];
+    }
+};
+
+struct Span {
+    u64 off;
+    u32 len;
+};
+
+struct SpanSrc {
+    const Win& w;
+    u64 off;
+    __device__ __forceinline__ uint8_t operator()(int64_t i) const { return w(off + (u64)i); }
+};
+
+// A node key: base bytes, optionally followed by ':' + orientation (builders.py:193, 211-212, 234)
+struct KeyDesc {
+    u64 base_off;
+    u64 ori_off;
+    u32 base_len;
+    u32 ori_len;   // bytes of the orientation string (may be 0: key ends with ':')
+    u32 ori_char;  // literal when ori_len == 1
+    u32 has_ori;   // 0: plain key (not bidirected)
+    __device__ __forceinline__ u32 total_len() const { return base_len + (has_ori ? 1 + ori_len : 0); }
+    __device__ __forceinline__ uint8_t byte(const Win& w, u32 i) const
+    {
+        if (i < base_len) return w(base_off + i);
+        if (i == base_len) return ':';
+        if (ori_len == 1) return (uint8_t)ori_char;
+        return w(ori_off + (i - base_len - 1));
+    }
+};
+
+__device__ __forceinline__ u64 mix64(u64 x)
+{
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdULL;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33;
+    return x;
+}
+
+__device__ __forceinline__ void cas128(TKey* s, u64 n0, u64 n1, u64& o0, u64& o1)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .b128 c, v, o;\n\t"
+        "mov.b128 c, {%2, %3};\n\t"
+        "mov.b128 v, {%4, %5};\n\t"
+        "atom.global.relaxed.gpu.cas.b128 o, [%6], c, v;\n\t"
+        "mov.b128 {%0, %1}, o;\n\t"
+        "}"
+        : "=l"(o0), "=l"(o1)
+        : "l"(0ull), "l"(0ull), "l"(n0), "l"(n1), "l"(s)
+        : "memory");
+}
+
+// two keys (one 32-byte sector) per 256-bit load; table sectors are kept in L2 (evict_last) while the
+// text streams through (evict_first)
+__device__ __forceinline__ void ld_key2(const TKey* s, u64 (&k)[4])
+{
+    u64 pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("ld.global.cg.L2::cache_hint.v4.u64 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=l"(k[0]), "=l"(k[1]), "=l"(k[2]), "=l"(k[3])
+                 : "l"(s), "l"(pol)
+                 : "memory");
+}
+
+// Build the 128-bit table key for a node key.
+__device__ __forceinline__ void make_key(const Win& w, const KeyDesc& kd, u64 seed, u64& k0, u64& k1, bool& is_long)
+{
+    const u32 L = kd.total_len();
+    if (L <= 15) {
+        u64 a = 0, b = 0;
+        for (u32 i = 0; i < L; i++) {
+            const u64 c = kd.byte(w, i);
+            if (i < 8) a |= c << (8 * i); else b |= c << (8 * (i - 8));
+        }
+        k0 = a;
+        k1 = b | ((u64)(L + 1) << 56);
+        is_long = false;
+    } else {
+        u64 h1 = seed ^ 0x9e3779b97f4a7c15ULL, h2 = ~seed * 0xd6e8feb86659fd93ULL;
+        for (u32 i = 0; i < L; i++) {
+            const u64 c = kd.byte(w, i);
+            h1 = (h1 ^ c) * 0x100000001b3ULL;
+            h2 = (h2 + c + 1) * 0xc2b2ae3d27d4eb4fULL;
+            h2 ^= h2 >> 29;
+        }
+        k0 = mix64(h1 ^ (h2 << 1));
+        k1 = (0xFFull << 56) | ((u64)(L & 0xFFFFFF) << 32) | (mix64(h2 + h1) & 0xFFFFFFFFull);
+        is_long = true;
+    }
+}
+
+// bytes of a stored long key, read from global text only (any thread, any time)
+__device__ __forceinline__ uint8_t long_byte(const uint8_t* text, const LongDesc& d, u32 i)
+{
+    if (i < d.base_len) return text[d.base_off + i];
+    if (i == d.base_len) return ':';
+    if (d.ori_len == 1) return (uint8_t)d.ori_char;
+    return text[d.ori_off + (i - d.base_len - 1)];
+}
+
+// Lookup-or-insert of a ready 128-bit key, split in two so that several probes can be in flight:
+// probe_issue() starts the loads of the home slot, probe_finish() walks the probe sequence.
+struct Probe {
+    u64 k0, k1;
+    u64 lo[4], hi[4];  // the four keys of the current bucket: lo = slots 0,1 ; hi = slots 2,3
+    u32 i;             // first slot of the current bucket
+};
+
+__device__ __forceinline__ void probe_issue(const ScanParams& P, Probe& pr)
+{
+    pr.i = ((u32)mix64(pr.k0 ^ (pr.k1 * 0x9e3779b97f4a7c15ULL)) & P.table_mask) & ~(u32)(TB_SLOTS - 1);
+    ld_key2(&P.tkeys[pr.i], pr.lo);
+    ld_key2(&P.tkeys[pr.i + 2], pr.hi);
+}
+
+// Examines one slot whose key was loaded as (s0, s1): claims it if empty.  Returns true if the slot
+// now holds our key.
+__device__ __forceinline__ bool probe_slot(const ScanParams& P, u32 slot, u64 k0, u64 k1, u64 s0, u64 s1, u32& claimed)
+{
+    if (s0 == 0 && s1 == 0) {
+        cas128(&P.tkeys[slot], k0, k1, s0, s1);
+        if (s0 == 0 && s1 == 0) { claimed++; return true; }
+    }
+    return s0 == k0 && s1 == k1;
+}
+
+// Returns the slot index (0xFFFFFFFF if the table is full).  `claimed` is incremented when this call
+// created the key.  Records min(order) as atomicMax(~order) -- fire and forget.
+__device__ __forceinline__ u32 probe_finish(const ScanParams& P, Probe& pr, u64 order, u32& claimed)
+{
+    const u64 k0 = pr.k0, k1 = pr.k1;
+    u32 i = pr.i, probes = 0, slot;
+    while (true) {
+        // slots are examined in order; an empty slot ends the probe sequence (it is claimed)
+        if (probe_slot(P, i, k0, k1, pr.lo[0], pr.lo[1], claimed)) { slot = i; break; }
+        if (probe_slot(P, i + 1, k0, k1, pr.lo[2], pr.lo[3], claimed)) { slot = i + 1; break; }
+        if (probe_slot(P, i + 2, k0, k1, pr.hi[0], pr.hi[1], claimed)) { slot = i + 2; break; }
+        if (probe_slot(P, i + 3, k0, k1, pr.hi[2], pr.hi[3], claimed)) { slot = i + 3; break; }
+        i = (i + TB_SLOTS) & P.table_mask;
+        if (++probes > 2048u || TB_SLOTS * probes > P.table_mask) { atomicOr(&P.cnt->flags, CF_TABLE_FULL); return 0xFFFFFFFFu; }
+        ld_key2(&P.tkeys[i], pr.lo);
+        ld_key2(&P.tkeys[i + 2], pr.hi);
+    }
+    atomicMax(&P.tfirst[slot], ~(u32)order);
+    return slot;
+}
+
+__device__ __forceinline__ u32 table_probe(const ScanParams& P, u64 k0, u64 k1, u64 order, u32& claimed)
+{
+    Probe pr;
+    pr.k0 = k0; pr.k1 = k1;
+    probe_issue(P, pr);
+    return probe_finish(P, pr, order, claimed);
+}
+
+// Generic lookup-or-insert from a key descriptor (any length, any orientation string).
+__device__ __forceinline__ u32 table_insert(const ScanParams& P, const Win& w, const KeyDesc& kd, u64 order, u32& claimed)
+{
+    u64 k0, k1;
+    bool is_long;
+    make_key(w, kd, P.seed, k0, k1, is_long);
+    const u32 i = table_probe(P, k0, k1, order, claimed);
+    if (i == 0xFFFFFFFFu) return i;
+    if (is_long) {
+        // keep / verify the bytes behind a hashed key: every arrival is compared with some earlier
+        // arrival, so all mentions that share the slot are byte-equal unless `collision` is raised
+        u32 r = ld_volatile_u32(&P.trep[i]);
+        if (r == 0) {
+            const u32 idx = atomicAdd(&P.cnt->n_long, 1u);
+            if (idx >= P.long_cap) { atomicOr(&P.cnt->flags, CF_LONG_FULL); return i; }
+            LongDesc d;
+            d.base_off = kd.base_off; d.ori_off = kd.ori_off; d.base_len = kd.base_len;
+            d.ori_len = kd.ori_len; d.ori_char = kd.ori_char; d.has_ori = kd.has_ori;
+            P.longs[idx] = d;
+            __threadfence();
+            r = atomicExch(&P.trep[i], idx + 1);
+        }
+        if (r != 0) {
+            __threadfence();
+            const volatile LongDesc* vd = &P.longs[r - 1];
+            LongDesc d;
+            d.base_off = vd->base_off; d.ori_off = vd->ori_off; d.base_len = vd->base_len;
+            d.ori_len = vd->ori_len; d.ori_char = vd->ori_char; d.has_ori = vd->has_ori;
+            const u32 L = kd.total_len();
+            bool same = (d.base_len + (d.has_ori ? 1 + d.ori_len : 0)) == L;
+            for (u32 j = 0; same && j < L; j++) same = long_byte(P.text, d, j) == kd.byte(w, j);
+            if (!same) atomicExch(&P.cnt->collision, 1u);
+        }
+    }
+    return i;
+}
+
+}  // namespace g2n

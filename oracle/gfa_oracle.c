@@ -318,7 +318,7 @@ static int weight_from_tags(const span_t *fields, int nf, int first, const ora_p
                 /* an int too large for a double only raises (builders.py:209) if a later tag
                  * does not overwrite it: remember it as +-inf, checked after the loop */
                 huge = isinf(d);
-                *w = neg ? -d : d; *has_w = 1;
+                *w = (neg && d != 0.0) ? -d : d; *has_w = 1; /* float(int("-0")) is +0.0 */
             } /* else: ValueError -> entry left unchanged (parser.py:190-191) */
             free(buf);
         } else if (typlen == 1 && c1[1] == 'f') {

@@ -88,6 +88,8 @@ LITERAL_CASES: list[tuple[str, bytes]] = [
                          b"L\ta\t+\tt\t+\t0M\tRC:f:3.14159\nL\ta\t+\tu\t+\t0M\tRC:f:0.001\nL\ta\t+\tv\t+\t0M\tRC:f:12345.678\n"
                          b"L\ta\t+\tw\t+\t0M\tRC:f:1e-400\nL\ta\t+\tx\t+\t0M\tRC:i:18446744073709551616\nL\ta\t+\ty\t+\t0M\tRC:f:7.038531e-26\n"
                          b"L\ta\t+\tz\t+\t0M\tRC:f:1e22\nL\ta\t+\taa\t+\t0M\tRC:f:1e-22\nL\ta\t+\tab\t+\t0M\tRC:f:9e15\n"),
+    ("weights_neg_zero", b"L\ta\t+\tb\t+\t0M\tRC:i:-0\nL\ta\t+\tc\t+\t0M\tRC:f:-0\nL\ta\t+\td\t+\t0M\tRC:f:-0.0\nL\ta\t+\te\t+\t0M\tRC:i:-00\n"
+                         b"L\ta\t+\tf\t+\t0M\tA:B:i:3\tRC:f:+2.50\nL\ta\t+\tg\t+\t0M\tRC:f:00012.5000\nL\ta\t+\th\t+\t0M\tRC:f:123456789012345.6\n"),
     ("weights_signs", b"L\ta\t+\tb\t+\t0M\tRC:f:-2.5\nL\tb\t+\ta\t+\t0M\tRC:f:1.5\nL\tc\t+\td\t+\t0M\tRC:i:0\nL\td\t+\te\t+\t0M\tRC:i:-4\n"
                       b"L\te\t+\tf\t+\t0M\tRC:i:2\nL\te\t+\tf\t+\t0M\tRC:i:-2\nL\tf\t+\te\t+\t0M\tRC:i:-7\n"),
     ("weight_overflow", b"S\ta\t*\nL\ta\t+\tb\t+\t0M\tRC:i:" + b"9" * 400 + b"\n"),
@@ -131,6 +133,7 @@ MODES: list[dict] = [
     {"dtype": "bool"},
     {"dtype": "bool", "directed": False},
     {"dtype": "int32", "directed": False},
+    {"weight_tag": "A:B", "asymmetric": True},
 ]
 
 # ---------------------------------------------------------------------------- fuzz inputs
