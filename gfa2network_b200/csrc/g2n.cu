@@ -3,7 +3,7 @@
 //   K1  k_tokenize        line scan + field split + node-key hashing + edge-record emission (tokenize.cuh)
 //   K2  k_mark_first / k_assign_ids / k_gather_names   first-appearance ranking -> node IDs   (ids.cuh)
 //   K3  k_emit_coo | k_emit_keys                        COO triplets / sort keys               (ids.cuh)
-//   K4  k_radix_hist / k_radix_scatter / k_group_reduce / k_compact   sort + dedup/sum (+max) (sort.cuh)
+//   K4  k_rows_count / k_rows_scatter / k_rows_big / k_rows_finalize    row bucketing + dedup/sum (+max) (rowsort.cuh)
 // No CPU fallback exists: every entry point needs a CUDA device.
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -13,7 +13,7 @@
 #include <vector>
 
 #include "../../include/g2n.h"
-#include "sort.cuh"
+#include "rowsort.cuh"
 
 using namespace g2n;
 
@@ -59,11 +59,11 @@ struct g2n_handle {
     std::string err;
     cudaEvent_t ev[EV_COUNT];
     // device buffers (kept between builds: a warm handle allocates nothing)
-    DevBuf text, table, tfirst, trep, defer, edge_slots, edge_w, longs, tile_state, cnt, bitmap, wprefix, slot_id, id2slot, name_len, name_off, names;
-    DevBuf keysA, keysB, payA, payB, tile_hist, val, flag, pos, major_count, indptr, indices, data, row, col, scan_state;
+    DevBuf text, table, tfirst, trep, defer, edge_slots, edge_w, longs, tile_info, tile_base, cnt, bitmap, wprefix, slot_id, id2slot, name_len, name_off, names;
+    DevBuf rowcnt, rowptr, entries, w_emit, biglist, indptr, indices, data, row, col, scan_state;
     DevBuf up_row, up_col, up_data;
     Counters* h_cnt = nullptr;  // pinned
-    u64* h_tail = nullptr;      // pinned: {nnz, names_bytes}
+    u64* h_tail = nullptr;      // pinned: {nnz, names_bytes, tile_base total}
     // capacity hints learnt from previous builds
     u64 hint_keys = 0, hint_edges = 0, hint_long = 0, hint_defer = 0;
     // state of the last build
@@ -75,6 +75,7 @@ struct g2n_handle {
     bool have_edges = false;
     u64 n_nodes = 0, nnz = 0, names_bytes = 0, n_edges = 0, n_triplets = 0;
     u32 table_cap = 0;
+    u32 n_tiles = 0;
     int tpe = 1, spe = 2;
     bool symmax = false;
     int result_format = G2N_FMT_COO;
@@ -163,40 +164,6 @@ int launch_scan(g2n_handle* h, LoadOp load, Tout* out, u64 n)
     return G2N_OK;
 }
 
-// stable LSD radix sort over key bits [1, 1 + total_bits); returns with *keys / *pay pointing at the sorted data
-int radix_sort(g2n_handle* h, u64 M, int total_bits, bool has_payload, u64** keys, u32** pay)
-{
-    u64* in = h->keysA.as<u64>();
-    u64* out = h->keysB.as<u64>();
-    u32* pin = has_payload ? h->payA.as<u32>() : nullptr;
-    u32* pout = has_payload ? h->payB.as<u32>() : nullptr;
-    const u32 n_tiles = (u32)((M + RS_TILE - 1) / RS_TILE);
-    CK(h->tile_hist.ensure(((u64)RS_RADIX * n_tiles + 1) * sizeof(u32)));
-    u32* hist = h->tile_hist.as<u32>();
-    const int passes = (total_bits + 7) / 8;
-    for (int p = 0; p < passes; p++) {
-        const int shift = 1 + 8 * p;
-        const int bits = (total_bits - 8 * p) < 8 ? (total_bits - 8 * p) : 8;
-        const u32 mask = (1u << bits) - 1u;
-        const u32 grid = grid_for(n_tiles, 1, 8);
-        { KScope ks(h, "k_radix_hist"); k_radix_hist<<<grid, RS_THREADS, 0, h->stream>>>(in, M, shift, mask, hist, n_tiles); }
-        LoadArray<u32> ld{hist};
-        int rc = launch_scan<u32>(h, ld, hist, (u64)RS_RADIX * n_tiles);
-        if (rc) return rc;
-        {
-            KScope ks(h, "k_radix_scatter");
-            if (has_payload) k_radix_scatter<true><<<grid, RS_THREADS, 0, h->stream>>>(in, pin, out, pout, M, shift, mask, hist, n_tiles);
-            else k_radix_scatter<false><<<grid, RS_THREADS, 0, h->stream>>>(in, pin, out, pout, M, shift, mask, hist, n_tiles);
-        }
-        CK(cudaGetLastError());
-        u64* t = in; in = out; out = t;
-        u32* tp = pin; pin = pout; pout = tp;
-    }
-    *keys = in;
-    *pay = pin;
-    return G2N_OK;
-}
-
 size_t dtype_size(int dt)
 {
     switch (dt) {
@@ -207,43 +174,44 @@ size_t dtype_size(int dt)
     }
 }
 
-// sorted keys -> indptr / indices / data (device).  w_typed: already-cast weights indexed by payload.
+// rowptr (u32, n+1) and entries (u64, M) are ready: sort every row, sum duplicates, write the result.
 template <typename T>
-int reduce_typed(g2n_handle* h, const u64* keys, const u32* pay, const double* w_f64, const T* w_typed, u64 M, int sym, int mbits, u64 n)
+int rows_finalize_typed(g2n_handle* h, u64 M, u64 n, int sym, const double* w_emit, const T* w_typed)
 {
-    CK(h->val.ensure((M + 1) * sizeof(T)));
-    CK(h->flag.ensure((M + 1) * sizeof(u32)));
-    CK(h->pos.ensure((M + 2) * sizeof(u32)));
-    CK(h->major_count.ensure((n + 2) * sizeof(u32)));
+    const u32 n32 = (u32)n;
     CK(h->indptr.ensure((n + 2) * sizeof(int32_t)));
     CK(h->indices.ensure((M + 1) * sizeof(int32_t)));
     CK(h->data.ensure((M + 1) * sizeof(T)));
-    { KScope ks(h, "k_group_reduce"); k_group_reduce<T><<<grid_for(M, 256), 256, 0, h->stream>>>(keys, pay, w_f64, w_typed, M, sym, h->val.as<T>(), h->flag.as<u32>()); }
+    CK(h->biglist.ensure((n + 2) * sizeof(u32)));
+    u32* bigcount = h->biglist.as<u32>() + n + 1;
+    CK(cudaMemsetAsync(bigcount, 0, sizeof(u32), h->stream));
+    { KScope ks(h, "k_rows_find_big"); k_rows_find_big<<<grid_for(n, 256), 256, 0, h->stream>>>(h->rowptr.as<u32>(), n32, h->biglist.as<u32>(), bigcount); }
+    { KScope ks(h, "k_rows_big"); k_rows_big<<<G2N_SM_COUNT, 256, 0, h->stream>>>(h->rowptr.as<u32>(), h->biglist.as<u32>(), bigcount, h->entries.as<u64>()); }
+    const u64 n_groups = (n + 31) / 32;
+    CK(h->scan_state.ensure((n_groups + 2) * sizeof(u64)));
+    CK(cudaMemsetAsync(h->scan_state.p, 0, (n_groups + 2) * sizeof(u64), h->stream));
+    u64* state = h->scan_state.as<u64>() + 1;
+    u32* ticket = (u32*)h->scan_state.p;
+    u64* nnz_dev = (u64*)&h->cnt.as<Counters>()->nnz;
+    {
+        KScope ks(h, "k_rows_finalize");
+        k_rows_finalize<T><<<grid_for(n_groups, RS_WARPS, 8), RS_WARPS * 32, 0, h->stream>>>(
+            h->rowptr.as<u32>(), h->entries.as<u64>(), n32, sym, w_emit, w_typed, h->indptr.as<int32_t>(), h->indices.as<int32_t>(),
+            h->data.as<T>(), state, ticket, nnz_dev);
+    }
     CK(cudaGetLastError());
-    LoadArray<u32> ldf{h->flag.as<u32>()};
-    int rc = launch_scan<u32>(h, ldf, h->pos.as<u32>(), M);
-    if (rc) return rc;
-    CK(cudaMemsetAsync(h->major_count.p, 0, (n + 2) * sizeof(u32), h->stream));
-    { KScope ks(h, "k_compact"); k_compact<T><<<grid_for(M, 256), 256, 0, h->stream>>>(keys, h->val.as<T>(), h->flag.as<u32>(), h->pos.as<u32>(), M, mbits,
-                                                          h->indices.as<int32_t>(), h->data.as<T>(), h->major_count.as<u32>()); }
-    CK(cudaGetLastError());
-    LoadArray<u32> ldc{h->major_count.as<u32>()};
-    rc = launch_scan<int32_t>(h, ldc, h->indptr.as<int32_t>(), n);
-    if (rc) return rc;
-    // nnz = pos[M]
-    CK(cudaMemcpyAsync(&h->h_tail[0], h->pos.as<u32>() + M, sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&h->h_tail[0], nnz_dev, sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
     return G2N_OK;
 }
 
-int reduce_dispatch(g2n_handle* h, int dtype, const u64* keys, const u32* pay, const double* w_f64, const void* w_typed, u64 M, int sym,
-                    int mbits, u64 n)
+int rows_finalize(g2n_handle* h, int dtype, u64 M, u64 n, int sym, const double* w_emit, const void* w_typed)
 {
     switch (dtype) {
-        case G2N_DTYPE_F64: return reduce_typed<double>(h, keys, pay, w_f64, (const double*)w_typed, M, sym, mbits, n);
-        case G2N_DTYPE_F32: return reduce_typed<float>(h, keys, pay, w_f64, (const float*)w_typed, M, sym, mbits, n);
-        case G2N_DTYPE_I32: return reduce_typed<int32_t>(h, keys, pay, w_f64, (const int32_t*)w_typed, M, sym, mbits, n);
-        case G2N_DTYPE_I8: return reduce_typed<int8_t>(h, keys, pay, w_f64, (const int8_t*)w_typed, M, sym, mbits, n);
-        case G2N_DTYPE_BOOL: return reduce_typed<BoolT>(h, keys, pay, w_f64, (const BoolT*)w_typed, M, sym, mbits, n);
+        case G2N_DTYPE_F64: return rows_finalize_typed<double>(h, M, n, sym, w_emit, (const double*)w_typed);
+        case G2N_DTYPE_F32: return rows_finalize_typed<float>(h, M, n, sym, w_emit, (const float*)w_typed);
+        case G2N_DTYPE_I32: return rows_finalize_typed<int32_t>(h, M, n, sym, w_emit, (const int32_t*)w_typed);
+        case G2N_DTYPE_I8: return rows_finalize_typed<int8_t>(h, M, n, sym, w_emit, (const int8_t*)w_typed);
+        case G2N_DTYPE_BOOL: return rows_finalize_typed<BoolT>(h, M, n, sym, w_emit, (const BoolT*)w_typed);
     }
     h->err = "unknown dtype";
     return G2N_ERR_INVALID;
@@ -259,13 +227,20 @@ int empty_compressed(g2n_handle* h, u64 n)
     return G2N_OK;
 }
 
+struct LoadTileCounts {
+    const TileInfo* p;
+    __device__ __forceinline__ u64 operator()(u64 i) const { return ((u64)p[i].n_rec << 32) | (u64)p[i].n_edge; }
+};
+
 EmitParams emit_params(g2n_handle* h)
 {
     EmitParams E;
     E.edge_slots = h->edge_slots.as<u32>();
     E.edge_w = h->params.weight_tag_len > 0 ? h->edge_w.as<double>() : nullptr;
     E.slot_id = h->slot_id.as<u32>();
-    E.n_edges = (u32)h->n_edges;
+    E.tile_info = h->tile_info.as<TileInfo>();
+    E.tile_base = h->tile_base.as<u64>();
+    E.n_tiles = h->n_tiles;
     E.slots_per_edge = h->spe;
     E.tpe = h->tpe;
     return E;
@@ -288,24 +263,25 @@ int build_compressed(g2n_handle* h, int fmt)
     }
     if (M >= 0xFFFFFFF0ull) { h->err = "more than 2^32 triplets in one build"; return G2N_ERR_UNSUPPORTED; }
     const bool weighted = h->params.weight_tag_len > 0;
-    const int mbits = ceil_log2(n);
-    CK(h->keysA.ensure((M + 1) * sizeof(u64)));
-    CK(h->keysB.ensure((M + 1) * sizeof(u64)));
-    if (weighted) {
-        CK(h->payA.ensure((M + 1) * sizeof(u32)));
-        CK(h->payB.ensure((M + 1) * sizeof(u32)));
-    }
-    // for a symmetric result CSC arrays equal CSR arrays; sort by row either way
+    // for a symmetric result CSC arrays equal CSR arrays; bucket by row either way
     const int csc = (!sym && fmt == G2N_FMT_CSC) ? 1 : 0;
-    { KScope ks(h, "k_emit_keys"); k_emit_keys<<<grid_for(T, 256), 256, 0, h->stream>>>(emit_params(h), sym, csc, mbits, h->keysA.as<u64>(), weighted ? h->payA.as<u32>() : nullptr); }
+    CK(h->rowcnt.ensure((n + 2) * sizeof(u32)));
+    CK(h->rowptr.ensure((n + 2) * sizeof(u32)));
+    CK(h->entries.ensure((M + 1) * sizeof(u64)));
+    if (weighted) CK(h->w_emit.ensure((T + 1) * sizeof(double)));
+    CK(cudaMemsetAsync(h->rowcnt.p, 0, (n + 2) * sizeof(u32), h->stream));
+    const EmitParams E = emit_params(h);
+    const u32 egrid = grid_for((u64)h->n_tiles * 32, 256);
+    { KScope ks(h, "k_rows_count"); k_rows_count<<<egrid, 256, 0, h->stream>>>(E, sym, csc, h->rowcnt.as<u32>(), weighted ? h->w_emit.as<double>() : nullptr); }
     CK(cudaGetLastError());
-    CK(cudaEventRecord(h->ev[EV_EMIT], h->stream));
-    u64* keys;
-    u32* pay;
-    int rc = radix_sort(h, M, 2 * mbits, weighted, &keys, &pay);
+    LoadArray<u32> ldc{h->rowcnt.as<u32>()};
+    int rc = launch_scan<u32>(h, ldc, h->rowptr.as<u32>(), n);
     if (rc) return rc;
+    CK(cudaEventRecord(h->ev[EV_EMIT], h->stream));
+    { KScope ks(h, "k_rows_scatter"); k_rows_scatter<<<egrid, 256, 0, h->stream>>>(E, sym, csc, h->rowptr.as<u32>(), h->rowcnt.as<u32>(), h->entries.as<u64>()); }
+    CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev[EV_SORT], h->stream));
-    rc = reduce_dispatch(h, h->params.dtype, keys, pay, weighted ? h->edge_w.as<double>() : nullptr, nullptr, M, sym, mbits, n);
+    rc = rows_finalize(h, h->params.dtype, M, n, sym, weighted ? h->w_emit.as<double>() : nullptr, nullptr);
     if (rc) return rc;
     CK(cudaEventRecord(h->ev[EV_REDUCE], h->stream));
     return G2N_OK;
@@ -315,7 +291,7 @@ template <typename T>
 int emit_coo_typed(g2n_handle* h, u64 T_)
 {
     CK(h->data.ensure((T_ + 1) * sizeof(T)));
-    { KScope ks(h, "k_emit_coo"); k_emit_coo<T><<<grid_for(T_, 256), 256, 0, h->stream>>>(emit_params(h), h->row.as<int32_t>(), h->col.as<int32_t>(), h->data.as<T>()); }
+    { KScope ks(h, "k_emit_coo"); k_emit_coo<T><<<grid_for((u64)h->n_tiles * 32, 256), 256, 0, h->stream>>>(emit_params(h), h->row.as<int32_t>(), h->col.as<int32_t>(), h->data.as<T>()); }
     CK(cudaGetLastError());
     return G2N_OK;
 }
@@ -349,7 +325,7 @@ int build_coo(g2n_handle* h)
 int finish_result(g2n_handle* h)
 {
     CK(cudaStreamSynchronize(h->stream));
-    h->nnz = (h->result_format == G2N_FMT_COO) ? h->h_tail[0] : (u64)(u32)h->h_tail[0];
+    h->nnz = h->h_tail[0];
     h->names_bytes = h->h_tail[1];
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev[EV_START], h->ev[EV_REDUCE]);
@@ -400,9 +376,8 @@ void g2n_destroy(g2n_handle* h)
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf* bufs[] = {&h->text, &h->table, &h->tfirst, &h->trep, &h->defer, &h->edge_slots, &h->edge_w, &h->longs, &h->tile_state, &h->cnt, &h->bitmap, &h->wprefix,
-                      &h->slot_id, &h->id2slot, &h->name_len, &h->name_off, &h->names, &h->keysA, &h->keysB, &h->payA, &h->payB,
-                      &h->tile_hist, &h->val, &h->flag, &h->pos, &h->major_count, &h->indptr, &h->indices, &h->data, &h->row, &h->col,
+    DevBuf* bufs[] = {&h->text, &h->table, &h->tfirst, &h->trep, &h->defer, &h->edge_slots, &h->edge_w, &h->longs, &h->tile_info, &h->tile_base, &h->cnt, &h->bitmap, &h->wprefix,
+                      &h->slot_id, &h->id2slot, &h->name_len, &h->name_off, &h->names, &h->rowcnt, &h->rowptr, &h->entries, &h->w_emit, &h->biglist, &h->indptr, &h->indices, &h->data, &h->row, &h->col,
                       &h->scan_state, &h->up_row, &h->up_col, &h->up_data};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(h->ev[i]);
@@ -512,8 +487,9 @@ int g2n_build(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n_par
     h->tpe = graph_directed ? 1 : (h->spe == 4 ? 4 : 2);
     const bool weighted = h->params.weight_tag_len > 0;
 
-    const u64 n_tiles64 = (nbytes + TK_TILE - 1) / TK_TILE;
+    const u64 n_tiles64 = (nbytes + WT_TILE - 1) / WT_TILE;
     const u32 n_tiles = (u32)n_tiles64;
+    h->n_tiles = n_tiles;
     u64 keys_cap = h->hint_keys ? h->hint_keys + 64 : nbytes / 24 + 1024;
     u64 edge_cap = h->hint_edges ? h->hint_edges + 64 : nbytes / 20 + 1024;
     u64 long_cap = h->hint_long ? h->hint_long + h->hint_long / 4 + 1024 : 65536;
@@ -530,17 +506,17 @@ int g2n_build(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n_par
         if (want_slots > (1ull << 31)) { h->err = "more than 2^30 distinct node keys"; return G2N_ERR_UNSUPPORTED; }
         h->table_cap = cap;
         CK(h->table.ensure((size_t)cap * sizeof(TKey)));
-        CK(h->tfirst.ensure((size_t)cap * sizeof(u32)));
+        CK(h->tfirst.ensure((size_t)cap * sizeof(u64)));
         CK(h->trep.ensure((size_t)cap * sizeof(u32)));
         CK(cudaMemsetAsync(h->table.p, 0, (size_t)cap * sizeof(TKey), h->stream));
-        CK(cudaMemsetAsync(h->tfirst.p, 0, (size_t)cap * sizeof(u32), h->stream));
+        CK(cudaMemsetAsync(h->tfirst.p, 0, (size_t)cap * sizeof(u64), h->stream));
         CK(cudaMemsetAsync(h->trep.p, 0, (size_t)cap * sizeof(u32), h->stream));
         CK(h->edge_slots.ensure((edge_cap + 1) * h->spe * sizeof(u32)));
         if (weighted) CK(h->edge_w.ensure((edge_cap + 1) * sizeof(double)));
         CK(h->longs.ensure((long_cap + 1) * sizeof(LongDesc)));
         CK(h->defer.ensure((defer_cap + 1) * sizeof(DeferEnt)));
-        CK(h->tile_state.ensure(((size_t)n_tiles + 1) * sizeof(u64)));
-        CK(cudaMemsetAsync(h->tile_state.p, 0, ((size_t)n_tiles + 1) * sizeof(u64), h->stream));
+        CK(h->tile_info.ensure(((size_t)n_tiles + 1) * sizeof(TileInfo)));
+        CK(h->tile_base.ensure(((size_t)n_tiles + 2) * sizeof(u64)));
         CK(h->cnt.ensure(sizeof(Counters)));
         memset(&hc, 0, sizeof(hc));
         hc.first_error = ~0ull;
@@ -552,10 +528,11 @@ int g2n_build(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n_par
             P.text = h->d_text;
             P.nbytes = nbytes;
             P.tkeys = h->table.as<TKey>();
-            P.tfirst = h->tfirst.as<u32>();
+            P.tfirst = h->tfirst.as<u64>();
             P.trep = h->trep.as<u32>();
             P.table_mask = cap - 1;
             P.table_max_keys = (u32)(cap / 2 + cap / 4);
+            P.n_tiles = n_tiles;
             P.edge_slots = h->edge_slots.as<u32>();
             P.edge_w = weighted ? h->edge_w.as<double>() : nullptr;
             P.edge_cap = (u32)edge_cap;
@@ -563,7 +540,7 @@ int g2n_build(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n_par
             P.long_cap = (u32)long_cap;
             P.defer = h->defer.as<DeferEnt>();
             P.defer_cap = (u32)defer_cap;
-            P.tile_state = h->tile_state.as<u64>();
+            P.tile_info = h->tile_info.as<TileInfo>();
             P.cnt = h->cnt.as<Counters>();
             P.n_tiles = n_tiles;
             P.bidirected = p->bidirected ? 1 : 0;
@@ -573,8 +550,15 @@ int g2n_build(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n_par
             P.dtype = p->dtype;
             P.seed = seed;
             memcpy(P.wt, h->weight_tag, sizeof(P.wt));
-            { KScope ks(h, "k_tokenize"); k_tokenize<<<grid_for(n_tiles, 1, 4), TK_THREADS, 0, h->stream>>>(P); }
+            { KScope ks(h, "k_tokenize"); k_tokenize<<<grid_for(n_tiles, WT_WARPS, TK_MIN_BLOCKS), WT_WARPS * 32, 0, h->stream>>>(P); }
             CK(cudaGetLastError());
+            // (records, edge records) before every tile; the grand totals come back with the counters
+            LoadTileCounts ltc{h->tile_info.as<TileInfo>()};
+            int rc = launch_scan<u64>(h, ltc, h->tile_base.as<u64>(), n_tiles);
+            if (rc) return rc;
+            CK(cudaMemcpyAsync(&h->h_tail[2], h->tile_base.as<u64>() + n_tiles, sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
+        } else {
+            h->h_tail[2] = 0;
         }
         CK(cudaEventRecord(h->ev[EV_TOKENIZE], h->stream));
         CK(cudaMemcpyAsync(&hc, h->cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
@@ -589,24 +573,23 @@ int g2n_build(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n_par
             CK(cudaStreamSynchronize(h->stream));
         }
         bool retry = false;
+        if (hc.edge_alloc > edge_cap) hc.flags |= CF_EDGE_FULL;
+        if (n_tiles > 0 && hc.n_keys > (u32)(cap / 2 + cap / 4)) hc.flags |= CF_TABLE_FULL;
         if (hc.flags & CF_DEFER_FULL) { defer_cap = defer_cap * 8 > (u64)hc.n_defer + 1024 ? defer_cap * 8 : (u64)hc.n_defer + 1024; retry = true; }
         if (hc.flags & CF_TABLE_FULL) { keys_cap = keys_cap * 4 > hc.n_keys * 2ull ? keys_cap * 4 : hc.n_keys * 2ull; retry = true; }
-        if (hc.flags & CF_EDGE_FULL) { edge_cap = (u64)hc.n_edges + 64; retry = true; }
+        if (hc.flags & CF_EDGE_FULL) { edge_cap = (u64)hc.edge_alloc + 64; retry = true; }
         if (hc.flags & CF_LONG_FULL) { long_cap = (u64)hc.n_long * 2 + 1024; retry = true; }
         if (!retry && hc.collision) { seed = seed * 6364136223846793005ull + 1442695040888963407ull; retry = true; }
         if (!retry) break;
     }
-#ifdef TK_TIMING
-    fprintf(stderr, "[tk_timing] cycles/CTA-sum: ticket %llu stage %llu pass1+scan %llu lookback %llu list+sync %llu pass2 %llu tail %llu\n",
-            hc.phase[0], hc.phase[1], hc.phase[2], hc.phase[3], hc.phase[4], hc.phase[5], hc.phase[6]);
-#endif
     h->hint_keys = hc.n_keys;
-    h->hint_edges = hc.n_edges;
+    h->hint_edges = hc.edge_alloc;
     h->hint_long = hc.n_long;
     h->hint_defer = hc.n_defer;
     // ---- diagnostics: first error / first unknown record in file order
-    h->diag.n_records = hc.n_records;
-    h->diag.n_edge_records = hc.n_edges;
+    const u64 R = h->h_tail[2] >> 32;
+    h->diag.n_records = R;
+    h->diag.n_edge_records = hc.edge_alloc;
     h->diag.n_long_keys = hc.n_long;
     if (hc.flags & CF_CAST_OVERFLOW) h->diag.warn_flags |= G2N_WARN_CAST_OVERFLOW;
     if (hc.first_error != ~0ull) {
@@ -622,10 +605,9 @@ int g2n_build(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n_par
         h->err = "input holds a record the reference raises on";
         return G2N_ERR_PARSE;
     }
-    if (hc.n_records >= (1u << 30) - 1) { h->err = "more than 2^30 records in one build"; return G2N_ERR_UNSUPPORTED; }
+    if (R >= (1ull << 30) - 1) { h->err = "more than 2^30 records in one build"; return G2N_ERR_UNSUPPORTED; }
     const u64 n = hc.n_keys;
-    const u64 E = hc.n_edges;
-    const u64 R = hc.n_records;
+    const u64 E = hc.edge_alloc;
     if (n > 0x7FFFFFFFull) { h->err = "more than 2^31-1 nodes (int64 indices) is out of scope"; return G2N_ERR_UNSUPPORTED; }
     h->n_nodes = n;
     h->n_edges = E;
@@ -640,11 +622,11 @@ int g2n_build(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n_par
     CK(h->name_off.ensure((n + 2) * sizeof(u64)));
     if (n > 0) {
         CK(cudaMemsetAsync(h->bitmap.p, 0, words * sizeof(u32), h->stream));
-        { KScope ks(h, "k_mark_first"); k_mark_first<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->table.as<TKey>(), h->tfirst.as<u32>(), cap, h->bitmap.as<u32>()); }
+        { KScope ks(h, "k_mark_first"); k_mark_first<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->table.as<TKey>(), h->tfirst.as<u64>(), cap, h->tile_base.as<u64>(), h->bitmap.as<u32>()); }
         LoadPopc lp{h->bitmap.as<u32>()};
         int rc = launch_scan<u32>(h, lp, h->wprefix.as<u32>(), words);
         if (rc) return rc;
-        { KScope ks(h, "k_assign_ids"); k_assign_ids<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->table.as<TKey>(), h->tfirst.as<u32>(), cap, h->bitmap.as<u32>(), h->wprefix.as<u32>(),
+        { KScope ks(h, "k_assign_ids"); k_assign_ids<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->table.as<TKey>(), h->tfirst.as<u64>(), cap, h->tile_base.as<u64>(), h->bitmap.as<u32>(), h->wprefix.as<u32>(),
                                                                  h->slot_id.as<u32>(), h->id2slot.as<u32>(), h->name_len.as<u32>()); }
         CK(cudaGetLastError());
         LoadArray<u32> ln{h->name_len.as<u32>()};
@@ -774,23 +756,23 @@ int g2n_coo_to_compressed(g2n_handle* h, const int32_t* row, const int32_t* col,
     CK(cudaMemcpyAsync(h->up_row.p, row, nnz_in * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->up_col.p, col, nnz_in * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->up_data.p, data, nnz_in * ds, cudaMemcpyHostToDevice, h->stream));
-    const int mbits = ceil_log2(n);
-    CK(h->keysA.ensure((nnz_in + 1) * sizeof(u64)));
-    CK(h->keysB.ensure((nnz_in + 1) * sizeof(u64)));
-    CK(h->payA.ensure((nnz_in + 1) * sizeof(u32)));
-    CK(h->payB.ensure((nnz_in + 1) * sizeof(u32)));
-    KScope ks_keys(h, "k_keys_from_coo");
-    k_keys_from_coo<<<grid_for(nnz_in, 256), 256, 0, h->stream>>>(h->up_row.as<int32_t>(), h->up_col.as<int32_t>(), nnz_in,
-                                                                 want_format == G2N_FMT_CSC ? 1 : 0, mbits, h->keysA.as<u64>(), h->payA.as<u32>());
+    CK(h->rowcnt.ensure((n + 2) * sizeof(u32)));
+    CK(h->rowptr.ensure((n + 2) * sizeof(u32)));
+    CK(h->entries.ensure((nnz_in + 1) * sizeof(u64)));
+    CK(h->cnt.ensure(sizeof(Counters)));
+    CK(cudaMemsetAsync(h->rowcnt.p, 0, (n + 2) * sizeof(u32), h->stream));
+    const int csc = want_format == G2N_FMT_CSC ? 1 : 0;
+    { KScope ks(h, "k_coo_count"); k_coo_count<<<grid_for(nnz_in, 256), 256, 0, h->stream>>>(h->up_row.as<int32_t>(), h->up_col.as<int32_t>(), nnz_in, csc, h->rowcnt.as<u32>()); }
     CK(cudaGetLastError());
-    u64* keys;
-    u32* pay;
-    int rc = radix_sort(h, nnz_in, 2 * mbits, true, &keys, &pay);
+    LoadArray<u32> ldc{h->rowcnt.as<u32>()};
+    int rc = launch_scan<u32>(h, ldc, h->rowptr.as<u32>(), n);
     if (rc) return rc;
-    rc = reduce_dispatch(h, dtype, keys, pay, nullptr, h->up_data.p, nnz_in, 0, mbits, n);
+    { KScope ks(h, "k_coo_scatter"); k_coo_scatter<<<grid_for(nnz_in, 256), 256, 0, h->stream>>>(h->up_row.as<int32_t>(), h->up_col.as<int32_t>(), nnz_in, csc, h->rowptr.as<u32>(), h->rowcnt.as<u32>(), h->entries.as<u64>()); }
+    CK(cudaGetLastError());
+    rc = rows_finalize(h, dtype, nnz_in, n, 0, nullptr, h->up_data.p);
     if (rc) return rc;
     CK(cudaStreamSynchronize(h->stream));
-    const u64 nnz = (u32)h->h_tail[0];
+    const u64 nnz = h->h_tail[0];
     *nnz_out = nnz;
     CK(cudaMemcpyAsync(indptr, h->indptr.p, (n + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     if (nnz) {

@@ -1,24 +1,33 @@
 // ids.cuh -- K2b: first-appearance ranking -> node IDs and the node-name table; K3: COO emission.
 //
 // Node IDs reproduce the reference's `node2idx[n] = len(node2idx)` (builders.py:194-198, 219-221):
-// every key's slot holds the minimum order (record ordinal << 2 | sub-rank) over all its mentions;
-// one bit per (record, sub-rank) marks the positions that are first appearances, and a key's ID is
-// the number of marked bits below its own.  Triplet order follows add_mat_edge (builders.py:218-234).
+// every key's slot holds the minimum order (tile, record index in tile, sub-rank) over all its
+// mentions; with the exclusive scan of the per-tile record counts that is a global record ordinal, one
+// bit per (record, sub-rank) marks the positions that are first appearances, and a key's ID is the
+// number of marked bits below its own.  Triplet order follows add_mat_edge (builders.py:218-234).
 #pragma once
 #include "tokenize.cuh"
 #include "tokenize_slow.cuh"
 
 namespace g2n {
 
-// bit (order) of `bitmap` set for every occupied slot
-__global__ void __launch_bounds__(256) k_mark_first(const TKey* __restrict__ tkeys, const u32* __restrict__ tfirst, u32 cap,
-                                                     u32* __restrict__ bitmap)
+// tile_base[t] = (records before tile t) << 32 | (edge records before tile t)
+__device__ __forceinline__ u32 order_bit(const u64* __restrict__ tile_base, u64 order)
+{
+    const u32 tile = (u32)(order >> 12);
+    const u32 rec = (u32)(tile_base[tile] >> 32) + (u32)((order >> 2) & 1023u);
+    return (rec << 2) | (u32)(order & 3u);
+}
+
+// bit (global record ordinal << 2 | sub-rank) of `bitmap` set for every occupied slot
+__global__ void __launch_bounds__(256) k_mark_first(const TKey* __restrict__ tkeys, const u64* __restrict__ tfirst, u32 cap,
+                                                     const u64* __restrict__ tile_base, u32* __restrict__ bitmap)
 {
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
         const TKey k = tkeys[i];
         if (k.x == 0 && k.y == 0) continue;
-        const u32 order = ~tfirst[i];
-        atomicOr(&bitmap[order >> 5], 1u << (order & 31));
+        const u32 bit = order_bit(tile_base, ~tfirst[i]);
+        atomicOr(&bitmap[bit >> 5], 1u << (bit & 31));
     }
 }
 
@@ -29,15 +38,16 @@ __device__ __forceinline__ u32 slot_key_len(u64 k1)
 }
 
 // slot -> id ; id -> slot ; id -> name length
-__global__ void __launch_bounds__(256) k_assign_ids(const TKey* __restrict__ tkeys, const u32* __restrict__ tfirst, u32 cap,
-                                                     const u32* __restrict__ bitmap, const u32* __restrict__ wprefix,
-                                                     u32* __restrict__ slot_id, u32* __restrict__ id2slot, u32* __restrict__ name_len)
+__global__ void __launch_bounds__(256) k_assign_ids(const TKey* __restrict__ tkeys, const u64* __restrict__ tfirst, u32 cap,
+                                                     const u64* __restrict__ tile_base, const u32* __restrict__ bitmap,
+                                                     const u32* __restrict__ wprefix, u32* __restrict__ slot_id,
+                                                     u32* __restrict__ id2slot, u32* __restrict__ name_len)
 {
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
         const TKey k = tkeys[i];
         if (k.x == 0 && k.y == 0) continue;
-        const u32 order = ~tfirst[i];
-        const u32 wd = order >> 5, bit = order & 31;
+        const u32 ob = order_bit(tile_base, ~tfirst[i]);
+        const u32 wd = ob >> 5, bit = ob & 31;
         const u32 id = wprefix[wd] + __popc(bitmap[wd] & ((1u << bit) - 1u));
         slot_id[i] = id;
         id2slot[id] = i;
@@ -87,19 +97,24 @@ template <typename T> __device__ __forceinline__ T zero_t() { return (T)0; }
 template <> __device__ __forceinline__ BoolT zero_t<BoolT>() { BoolT b; b.v = 0; return b; }
 
 // ---------------------------------------------------------------- K3: emission
+// Edge records live in edge_slots in per-tile ranges (tile_info[t].edge_alloc, claimed in arrival
+// order); file order is tile order, so the emission index of tile t's j-th edge record is
+// (edges before tile t) + j.  One warp walks one tile.
 struct EmitParams {
     const u32* edge_slots;
     const double* edge_w;  // NULL when no weight tag: every weight is 1.0
     const u32* slot_id;
-    u32 n_edges;
+    const TileInfo* tile_info;
+    const u64* tile_base;  // exclusive scan of (n_rec << 32 | n_edge) over tiles
+    u32 n_tiles;
     int slots_per_edge;    // 2 | 4
     int tpe;               // triplets per edge record: 1 (graph_directed) | 2 | 4
 };
 
-__device__ __forceinline__ void edge_triplet(const EmitParams& E, u32 e, int k, u32& r, u32& c)
+__device__ __forceinline__ void edge_triplet(const EmitParams& E, u32 stored, int k, u32& r, u32& c)
 {
     // builders.py:222-234: (a,b) [, (b,a)] [, (c,d), (d,c)] with c = v:flip(ot), d = u:flip(of)
-    const u32* s = E.edge_slots + (u64)e * E.slots_per_edge;
+    const u32* s = E.edge_slots + (u64)stored * E.slots_per_edge;
     const u32 a = E.slot_id[s[(k & 2)]], b = E.slot_id[s[(k & 2) + 1]];
     if (k & 1) { r = b; c = a; } else { r = a; c = b; }
 }
@@ -108,37 +123,50 @@ __device__ __forceinline__ void edge_triplet(const EmitParams& E, u32 e, int k, 
 template <typename T>
 __global__ void __launch_bounds__(256) k_emit_coo(const EmitParams E, int32_t* __restrict__ row, int32_t* __restrict__ col, T* __restrict__ data)
 {
-    const u64 total = (u64)E.n_edges * E.tpe;
-    for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (u64)gridDim.x * blockDim.x) {
-        const u32 e = (u32)(t / E.tpe);
-        const int k = (int)(t % E.tpe);
-        u32 r, c;
-        edge_triplet(E, e, k, r, c);
-        row[t] = (int32_t)r;
-        col[t] = (int32_t)c;
-        data[t] = cast_weight<T>(E.edge_w ? E.edge_w[e] : 1.0);
+    const u32 lane = threadIdx.x & 31;
+    const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (u32 tile = warp; tile < E.n_tiles; tile += n_warps) {
+        const TileInfo ti = E.tile_info[tile];
+        if (ti.n_edge == 0) continue;
+        const u64 out0 = (u64)(u32)E.tile_base[tile] * E.tpe;
+        const u32 cnt = ti.n_edge * E.tpe;
+        for (u32 j = lane; j < cnt; j += 32) {
+            const u32 stored = ti.edge_alloc + j / E.tpe;
+            u32 r, c;
+            edge_triplet(E, stored, (int)(j % E.tpe), r, c);
+            row[out0 + j] = (int32_t)r;
+            col[out0 + j] = (int32_t)c;
+            data[out0 + j] = cast_weight<T>(E.edge_w ? E.edge_w[stored] : 1.0);
+        }
     }
 }
 
-// Sort keys for the compressed build.  key = ((major << mbits | minor) << 1) | dir ; payload = edge index.
+// Sort keys for the compressed build.  key = ((major << mbits | minor) << 1) | dir ; payload = stored edge index.
 //   sym == 0: one key per triplet, major = row (CSR) or col (CSC)                    (utils.py:55 tocsr/tocsc)
 //   sym == 1: two keys per triplet: (row, col, dir 0) and (col, row, dir 1)         (builders.py:283 maximum(A, A.T))
 __global__ void __launch_bounds__(256) k_emit_keys(const EmitParams E, int sym, int csc, int mbits, u64* __restrict__ keys, u32* __restrict__ payload)
 {
-    const u64 total = (u64)E.n_edges * E.tpe;
-    for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (u64)gridDim.x * blockDim.x) {
-        const u32 e = (u32)(t / E.tpe);
-        const int k = (int)(t % E.tpe);
-        u32 r, c;
-        edge_triplet(E, e, k, r, c);
-        if (sym) {
-            keys[2 * t] = ((((u64)r << mbits) | c) << 1);
-            keys[2 * t + 1] = ((((u64)c << mbits) | r) << 1) | 1ull;
-            if (payload) { payload[2 * t] = e; payload[2 * t + 1] = e; }
-        } else {
-            const u32 major = csc ? c : r, minor = csc ? r : c;
-            keys[t] = (((u64)major << mbits) | minor) << 1;
-            if (payload) payload[t] = e;
+    const u32 lane = threadIdx.x & 31;
+    const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (u32 tile = warp; tile < E.n_tiles; tile += n_warps) {
+        const TileInfo ti = E.tile_info[tile];
+        if (ti.n_edge == 0) continue;
+        const u64 out0 = (u64)(u32)E.tile_base[tile] * E.tpe;
+        const u32 cnt = ti.n_edge * E.tpe;
+        for (u32 j = lane; j < cnt; j += 32) {
+            const u32 stored = ti.edge_alloc + j / E.tpe;
+            u32 r, c;
+            edge_triplet(E, stored, (int)(j % E.tpe), r, c);
+            const u64 t = out0 + j;
+            if (sym) {
+                keys[2 * t] = ((((u64)r << mbits) | c) << 1);
+                keys[2 * t + 1] = ((((u64)c << mbits) | r) << 1) | 1ull;
+                if (payload) { payload[2 * t] = stored; payload[2 * t + 1] = stored; }
+            } else {
+                const u32 major = csc ? c : r, minor = csc ? r : c;
+                keys[t] = (((u64)major << mbits) | minor) << 1;
+                if (payload) payload[t] = stored;
+            }
         }
     }
 }

@@ -1,19 +1,8 @@
 // table.cuh -- shared types of the tokenizer kernels and the GPU open-addressing hash of node keys.
 //
-// One pass over the text.  Each CTA takes 16 KiB byte tiles (ticketed, so a decoupled look-back can
-// carry the record / edge-record ordinals across tiles), stages the tile plus a look-ahead window in
-// shared memory, classifies newlines 16 bytes at a time, and lets each thread parse the lines that
-// START in its 64-byte chunk.  Node keys are inserted straight into an open-addressing table
-// (inline 15-byte keys, 128-bit CAS); the table keeps, per key, the minimum (record ordinal,
-// sub-rank) -- the reference's first-appearance order (builders.py:194-198, 219-221).
-//
-// Reference semantics implemented here (gfa2network/parser.py unless noted):
-//   :114-132  newline-only line split, first-byte filter, one-shot unknown-record warning
-//   :133-134  split on TAB; only a 1-byte first field matches a record type
-//   :135-163  S -> fields[1]           :206-227  L (GFA-1 and compact forms)
-//   :249-295  E (coord / orientation)  :297-341  C            :229-247, 343-361  P / O (field count only)
-//   :179-204  tags -> builders.py:205-209 weight
-//   builders.py:190-234  node registration order and (in emit.cuh) triplet order
+// The table maps node keys (segment names, optionally with a ":+" / ":-" orientation suffix) to slots
+// and keeps, per key, the minimum `order` over all its mentions -- the reference's first-appearance
+// order (builders.py:194-198, 219-221).  IDs are derived from those minima in ids.cuh.
 #pragma once
 #include "common.cuh"
 #include "numparse.cuh"
@@ -21,28 +10,45 @@
 
 namespace g2n {
 
-#define TK_TILE 16384
-#define TK_LOOK 2016
-#define TK_PRE 32
-#define TK_WIN (TK_PRE + TK_TILE + TK_LOOK)
-#define TK_THREADS 256
-#define TK_CHUNK (TK_TILE / TK_THREADS)  // 64 bytes per thread
-#define TK_WORDS (TK_WIN / 32)           // 32-bit mask words covering the window
+// Tokenizer geometry: one warp owns one 2 KiB tile (64 bytes per lane) plus a look-ahead window.
+#define WT_TILE 2048
+#define WT_PRE 32
+#define WT_LOOK 992
+#define WT_WIN (WT_PRE + WT_TILE + WT_LOOK)  // 3072 bytes staged per tile
+#define WT_WORDS (WT_WIN / 32)               // 32-bit mask words covering the window
+#define WT_WARPS 8                           // warps (tiles in flight) per CTA
+#define WT_LIST 256                          // record lines per batch of the compacted list
 #define TK_NF 0xFFFFFFFFu
 
-// Hash table: open addressing over 64-byte buckets of four 16-byte keys (two 256-bit loads per probe
-// step, issued together), structure-of-arrays so that the part every mention touches stays small
-// enough to live in L2 (1 M nodes: 32 MB of keys + 8 MB of `first`):
+// `order` of a node mention: [63:12] tile, [11:2] record index within the tile (a 2 KiB tile holds at
+// most 1024 records), [1:0] sub-rank inside the record (builders.py:230-234: u, v, v', u').
+// File order == increasing order, and no tile needs to know anything about any other tile.
+__device__ __forceinline__ unsigned long long make_order(unsigned tile, unsigned rec_idx, unsigned sub)
+{
+    return ((unsigned long long)tile << 12) | ((unsigned long long)rec_idx << 2) | sub;
+}
+
+struct TileInfo {
+    unsigned n_rec;       // records yielded by this tile (S L E C P O)
+    unsigned n_edge;      // edge records (L E C)
+    unsigned edge_alloc;  // first edge_slots index of this tile's edge records
+    unsigned pad;
+};
+
+// Hash table: open addressing over 32-byte buckets of two 16-byte keys (one 256-bit load = one L2
+// sector per probe step), structure-of-arrays so that the part every mention touches stays small
+// enough to live in L2 (1 M nodes: 32 MB of keys + 16 MB of `first`):
 //   tkeys[slot]  16-byte key: <= 15 inline bytes + (len+1) in the top byte, or a 0xFF-tagged hash for
 //                long keys
-//   tfirst[slot] ~min(order) as u32 (atomicMax, fire and forget); order = record_ordinal << 2 | sub-rank
+//   tfirst[slot] ~min(order) as u64 (atomicMax, fire and forget)
 //   trep[slot]   long keys only: 1 + index of a LongDesc holding the key's bytes
 typedef ulonglong2 TKey;
-#define TB_SLOTS 4  // keys per bucket
+#define TB_SLOTS 2  // keys per bucket
 
 struct DeferEnt {
     u64 off;  // global offset of the first byte of the line
-    u32 rec_ord, edge_ord;
+    u32 tile;
+    unsigned short rec_idx, edge_idx;  // within the tile
 };
 
 struct LongDesc {
@@ -62,7 +68,7 @@ struct Counters {
     u32 n_keys;
     u32 n_long;
     u32 flags;
-    u32 ticket;
+    u32 edge_alloc;  // edge_slots entries handed out so far (one atomicAdd per tile)
     u32 scan_ticket;
     u32 collision;
     u32 n_defer;
@@ -81,7 +87,7 @@ struct ScanParams {
     const uint8_t* text;
     u64 nbytes;
     TKey* tkeys;
-    u32* tfirst;
+    u64* tfirst;
     u32* trep;
     u32 table_mask;  // slots - 1 (slots is a power of two >= TB_SLOTS)
     u32 table_max_keys;
@@ -92,7 +98,7 @@ struct ScanParams {
     u32 long_cap;
     struct DeferEnt* defer;  // lines the hot kernel hands to k_tokenize_slow
     u32 defer_cap;
-    u64* tile_state;
+    TileInfo* tile_info;
     Counters* cnt;
     u32 n_tiles;
     int bidirected;
@@ -226,15 +232,14 @@ __device__ __forceinline__ uint8_t long_byte(const uint8_t* text, const LongDesc
 // probe_issue() starts the loads of the home slot, probe_finish() walks the probe sequence.
 struct Probe {
     u64 k0, k1;
-    u64 lo[4], hi[4];  // the four keys of the current bucket: lo = slots 0,1 ; hi = slots 2,3
-    u32 i;             // first slot of the current bucket
+    u64 b[4];  // the two keys of the current bucket
+    u32 i;     // first slot of the current bucket
 };
 
 __device__ __forceinline__ void probe_issue(const ScanParams& P, Probe& pr)
 {
     pr.i = ((u32)mix64(pr.k0 ^ (pr.k1 * 0x9e3779b97f4a7c15ULL)) & P.table_mask) & ~(u32)(TB_SLOTS - 1);
-    ld_key2(&P.tkeys[pr.i], pr.lo);
-    ld_key2(&P.tkeys[pr.i + 2], pr.hi);
+    ld_key2(&P.tkeys[pr.i], pr.b);
 }
 
 // Examines one slot whose key was loaded as (s0, s1): claims it if empty.  Returns true if the slot
@@ -256,16 +261,13 @@ __device__ __forceinline__ u32 probe_finish(const ScanParams& P, Probe& pr, u64 
     u32 i = pr.i, probes = 0, slot;
     while (true) {
         // slots are examined in order; an empty slot ends the probe sequence (it is claimed)
-        if (probe_slot(P, i, k0, k1, pr.lo[0], pr.lo[1], claimed)) { slot = i; break; }
-        if (probe_slot(P, i + 1, k0, k1, pr.lo[2], pr.lo[3], claimed)) { slot = i + 1; break; }
-        if (probe_slot(P, i + 2, k0, k1, pr.hi[0], pr.hi[1], claimed)) { slot = i + 2; break; }
-        if (probe_slot(P, i + 3, k0, k1, pr.hi[2], pr.hi[3], claimed)) { slot = i + 3; break; }
+        if (probe_slot(P, i, k0, k1, pr.b[0], pr.b[1], claimed)) { slot = i; break; }
+        if (probe_slot(P, i + 1, k0, k1, pr.b[2], pr.b[3], claimed)) { slot = i + 1; break; }
         i = (i + TB_SLOTS) & P.table_mask;
-        if (++probes > 2048u || TB_SLOTS * probes > P.table_mask) { atomicOr(&P.cnt->flags, CF_TABLE_FULL); return 0xFFFFFFFFu; }
-        ld_key2(&P.tkeys[i], pr.lo);
-        ld_key2(&P.tkeys[i + 2], pr.hi);
+        if (++probes > 4096u || TB_SLOTS * probes > P.table_mask) { atomicOr(&P.cnt->flags, CF_TABLE_FULL); return 0xFFFFFFFFu; }
+        ld_key2(&P.tkeys[i], pr.b);
     }
-    atomicMax(&P.tfirst[slot], ~(u32)order);
+    atomicMax(&P.tfirst[slot], ~order);
     return slot;
 }
 

@@ -1,28 +1,30 @@
 // tokenize.cuh -- K1+K2 hot kernel: fused line scan, field split, node-key hashing and edge-record
 // emission for the record shapes real GFA files are made of.
 //
-// One pass over the text.  Each CTA takes 16 KiB byte tiles (ticketed, so a decoupled look-back can
-// carry the record / edge-record ordinals across tiles), stages the tile plus a look-ahead window in
-// shared memory, classifies '\n' and '\t' 16 bytes at a time into bitmasks, compacts the starts of the
-// record lines, and parses one line per thread per round from the separator bitmask (no byte loops).
+// One pass over the text, no dependency between tiles.  Each WARP owns 2 KiB tiles (64 bytes per
+// lane): it stages the tile plus a look-ahead window in shared memory, classifies '\n' and '\t' 16
+// bytes at a time into bitmasks, compacts the starts of its record lines with warp shuffles, and
+// parses one line per lane per round from the separator bitmask (no byte loops, no block barriers).
 // Node keys of <= 15 bytes are packed inline into a 128-bit table key and inserted with a 128-bit CAS;
-// the table keeps, per key, the minimum (record ordinal, sub-rank) -- the reference's
-// first-appearance order (builders.py:194-198, 219-221).
+// the table keeps, per key, the minimum `order` = (tile, record index in tile, sub-rank) -- file
+// order, i.e. the reference's first-appearance order (builders.py:194-198, 219-221) -- so no prefix
+// over earlier tiles is needed while parsing.  Edge records are written to a per-tile range of
+// edge_slots claimed with one atomicAdd; per-tile counts go to tile_info and are scanned afterwards.
 //
 // Handled here: S (any), P/O (field count), L in GFA-1 form with one-byte orientations
 // (parser.py:210-216), E in the reference's coord form (parser.py:254-288), weight tags whose value is
 // a plain decimal (parser.py:179-204, builders.py:205-209).  Every other line -- compact L,
 // orientation-only E, C, lenient numbers, long keys, errors, lines longer than the window -- is
 // appended to the deferred list and parsed by k_tokenize_slow (tokenize_slow.cuh) with the generic
-// byte-wise parser; since every mention carries its record ordinal the result does not depend on
-// which kernel handled a line.
+// byte-wise parser; since every mention carries its order the result does not depend on which kernel
+// handled a line.
 #pragma once
 #include "table.cuh"
 
 namespace g2n {
 
 struct Tile {
-    const uint8_t* win;  // shared-memory window, TK_WIN bytes (+ 32 bytes of slack)
+    const uint8_t* win;  // shared-memory window, WT_WIN bytes (+ 32 bytes of slack)
     const u32* nlm;      // bit o: window byte o is '\n'
     const u32* spm;      // bit o: window byte o is '\t' or '\n'
     u64 wbase;           // global offset of window byte 0 (wraps for tile 0)
@@ -34,7 +36,7 @@ __device__ __forceinline__ u32 find_sep(const Tile& t, u32 pos)
     u32 w = pos >> 5;
     u32 m = t.spm[w] & (0xFFFFFFFFu << (pos & 31));
     while (m == 0) {
-        if (++w >= TK_WORDS) return TK_NF;
+        if (++w >= WT_WORDS) return TK_NF;
         m = t.spm[w];
     }
     return (w << 5) + (u32)__ffs(m) - 1u;
@@ -146,12 +148,12 @@ __device__ __forceinline__ void node_issue(const ScanParams& P, const Tile& t, P
     probe_issue(P, pr);
 }
 
-__device__ __forceinline__ void defer_line(const ScanParams& P, u64 off, u32 rec_ord, u32 edge_ord)
+__device__ __forceinline__ void defer_line(const ScanParams& P, u64 off, u32 tile, u32 rec_idx, u32 edge_idx)
 {
     const u32 idx = atomicAdd(&P.cnt->n_defer, 1u);
     if (idx < P.defer_cap) {
         DeferEnt d;
-        d.off = off; d.rec_ord = rec_ord; d.edge_ord = edge_ord;
+        d.off = off; d.tile = tile; d.rec_idx = (unsigned short)rec_idx; d.edge_idx = (unsigned short)edge_idx;
         P.defer[idx] = d;
     } else {
         atomicOr(&P.cnt->flags, CF_DEFER_FULL);
@@ -160,11 +162,10 @@ __device__ __forceinline__ void defer_line(const ScanParams& P, u64 off, u32 rec
 
 // Common record shapes, parsed from the separator bitmask.  Returns false when the line must go to the
 // generic parser (rare shapes, errors, long keys, fields running past the window).
-__device__ __forceinline__ bool parse_line_fast(const ScanParams& P, const Tile& t, u32 s, u32 rec_ord, u32 edge_ord, u32& claimed)
+__device__ __forceinline__ bool parse_line_fast(const ScanParams& P, const Tile& t, u32 s, u64 order0, u32 edge_ord, u32& claimed)
 {
     const uint8_t c0 = t.win[s];
     if (t.win[s + 1] != '\t') return false;  // record with no fields at all: error paths
-    const u64 order0 = (u64)rec_ord << 2;
     const u32 p1 = s + 2;
     const u32 e1 = find_sep(t, p1);
     if (e1 == TK_NF) return false;
@@ -260,83 +261,77 @@ __device__ __forceinline__ bool parse_line_fast(const ScanParams& P, const Tile&
 
 // ---------------------------------------------------------------- the kernel
 #ifndef TK_MIN_BLOCKS
-#define TK_MIN_BLOCKS 3
+#define TK_MIN_BLOCKS 4
 #endif
-#define TK_LIST_CAP 4096  // record lines of one tile handled per batch through the compacted list
 
-__global__ void __launch_bounds__(TK_THREADS, TK_MIN_BLOCKS) k_tokenize(const __grid_constant__ ScanParams P)
+__global__ void __launch_bounds__(WT_WARPS * 32, TK_MIN_BLOCKS) k_tokenize(const __grid_constant__ ScanParams P)
 {
-    __shared__ __align__(16) uint8_t s_win[TK_WIN + 32];
-    __shared__ u32 s_nl[TK_WORDS];
-    __shared__ u32 s_sp[TK_WORDS];
-    __shared__ u32 s_list[TK_LIST_CAP];  // [15:0] window offset of the line, [31:16] edge ordinal within the tile
-    __shared__ u64 s_scan[TK_THREADS / 32 + 2];
-    __shared__ u32 s_tile;
-    __shared__ u64 s_base;
+    __shared__ __align__(16) uint8_t s_win[WT_WARPS][WT_WIN + 32];
+    __shared__ u32 s_nl[WT_WARPS][WT_WORDS];
+    __shared__ u32 s_sp[WT_WARPS][WT_WORDS];
+    __shared__ u32 s_list[WT_WARPS][WT_LIST];  // [15:0] window offset of the line, [31:16] edge index within the tile
 
-    const u32 tid = threadIdx.x;
+    const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint8_t* win = s_win[wid];
+    u32* nlm = s_nl[wid];
+    u32* spm = s_sp[wid];
+    u32* list = s_list[wid];
     const u64 pol_text = policy_evict_first();
-    u32 claimed = 0;
-#ifdef TK_TIMING
-    long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long tq = clock64();
-#define TK_MARK(k) do { const long long _n = clock64(); tph[k] += _n - tq; tq = _n; } while (0)
-#else
-#define TK_MARK(k) do { } while (0)
-#endif
-    if (tid < 8) reinterpret_cast<u32*>(s_win + TK_WIN)[tid] = 0x0A0A0A0Au;  // slack read by key_inline
-    while (true) {
-        if (tid == 0) s_tile = atomicAdd(&P.cnt->ticket, 1u);
-        __syncthreads();
-        const u32 tile = s_tile;
-        if (tile >= P.n_tiles) break;
-        TK_MARK(0);
-        const u64 t0 = (u64)tile * TK_TILE;
-        const u64 wbase = t0 - TK_PRE;  // wraps for tile 0: only ever used as wbase + offset
+    if (lane < 8) reinterpret_cast<u32*>(win + WT_WIN)[lane] = 0x0A0A0A0Au;  // slack read by key_inline
+    const u32 n_warps = gridDim.x * WT_WARPS;
+    for (u32 tile = blockIdx.x * WT_WARPS + wid; tile < P.n_tiles; tile += n_warps) {
+        const u64 t0 = (u64)tile * WT_TILE;
+        const u64 wbase = t0 - WT_PRE;  // wraps for tile 0: only ever used as wbase + offset
+        __syncwarp();                   // every lane is done with the previous tile's window
         // ---- stage [t0 - 32, t0 + TILE + LOOK) in shared memory; classify '\n' and '\t' 16 bytes at a time
-        for (u32 piece = tid; piece < TK_WIN / 16; piece += TK_THREADS) {
+        uint4 v[WT_WIN / 16 / 32];
+#pragma unroll
+        for (int k = 0; k < WT_WIN / 16 / 32; k++) {
+            const u32 piece = lane + 32 * k;
             const u64 g = wbase + (u64)piece * 16;  // global offset of this 16-byte piece
-            uint4 v;
-            if (tile == 0 && piece < TK_PRE / 16) {
-                v = make_uint4(0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au);  // virtual '\n' before byte 0
+            if (tile == 0 && piece < WT_PRE / 16) {
+                v[k] = make_uint4(0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au);  // virtual '\n' before byte 0
             } else if (g + 16 <= P.nbytes) {
-                v = ld_stream_v4(P.text + g, pol_text);
+                v[k] = ld_stream_v4(P.text + g, pol_text);
             } else {
                 uint8_t tmp[16];
 #pragma unroll
-                for (int k = 0; k < 16; k++) tmp[k] = (g + k < P.nbytes) ? P.text[g + k] : (uint8_t)'\n';
-                v = *reinterpret_cast<uint4*>(tmp);
+                for (int b = 0; b < 16; b++) tmp[b] = (g + b < P.nbytes) ? P.text[g + b] : (uint8_t)'\n';
+                v[k] = *reinterpret_cast<uint4*>(tmp);
             }
-            reinterpret_cast<uint4*>(s_win)[piece] = v;
-            u32 mn = 0, mt = 0;
-            const u32 ww[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const u32 eqn = __vcmpeq4(ww[k], 0x0A0A0A0Au) & 0x01010101u;  // 1 per matching byte
-                const u32 eqt = __vcmpeq4(ww[k], 0x09090909u) & 0x01010101u;
-                mn |= (((eqn * 0x01020408u) >> 24) & 0xF) << (4 * k);  // byte k -> bit k
-                mt |= (((eqt * 0x01020408u) >> 24) & 0xF) << (4 * k);
-            }
-            reinterpret_cast<unsigned short*>(s_nl)[piece] = (unsigned short)mn;
-            reinterpret_cast<unsigned short*>(s_sp)[piece] = (unsigned short)(mn | mt);
         }
-        __syncthreads();
-        TK_MARK(1);
-        Tile t{s_win, s_nl, s_sp, wbase};
+#pragma unroll
+        for (int k = 0; k < WT_WIN / 16 / 32; k++) {
+            const u32 piece = lane + 32 * k;
+            reinterpret_cast<uint4*>(win)[piece] = v[k];
+            u32 mn = 0, mt = 0;
+            const u32 ww[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const u32 eqn = __vcmpeq4(ww[b], 0x0A0A0A0Au) & 0x01010101u;  // 1 per matching byte
+                const u32 eqt = __vcmpeq4(ww[b], 0x09090909u) & 0x01010101u;
+                mn |= (((eqn * 0x01020408u) >> 24) & 0xF) << (4 * b);  // byte b -> bit b
+                mt |= (((eqt * 0x01020408u) >> 24) & 0xF) << (4 * b);
+            }
+            reinterpret_cast<unsigned short*>(nlm)[piece] = (unsigned short)mn;
+            reinterpret_cast<unsigned short*>(spm)[piece] = (unsigned short)(mn | mt);
+        }
+        __syncwarp();
+        Tile t{win, nlm, spm, wbase};
         // ---- line starts in my 64-byte chunk: a line starts right after every '\n'
-        const u32 c = 1 + tid * 2;  // mask word of my first 32 bytes (window offset 32 + 64 tid)
-        const u64 nl = (u64)s_nl[c] | ((u64)s_nl[c + 1] << 32);
-        u64 ls = (nl << 1) | (u64)(s_nl[c - 1] >> 31);
-        const u64 chunk0 = t0 + (u64)tid * TK_CHUNK;
+        const u32 c = 1 + lane * 2;  // mask word of my first 32 bytes (window offset 32 + 64 lane)
+        const u64 nl = (u64)nlm[c] | ((u64)nlm[c + 1] << 32);
+        u64 ls = (nl << 1) | (u64)(nlm[c - 1] >> 31);
+        const u64 chunk0 = t0 + (u64)lane * 64;
         if (chunk0 >= P.nbytes) ls = 0;
         else if (chunk0 + 64 > P.nbytes) ls &= (1ull << (P.nbytes - chunk0)) - 1;
-        const u32 woff0 = TK_PRE + tid * TK_CHUNK;
-        // ---- pass 1: classify my lines; keep only yielded records (bit set in `rec`), edges in `edg`
+        const u32 woff0 = WT_PRE + lane * 64;
+        // ---- classify my lines; keep only yielded records (bit set in `rec`), edge records in `edg`
         u64 rec = 0, edg = 0;
         for (u64 m = ls; m; m &= m - 1) {
             const int bit = __ffsll((long long)m) - 1;
             const u32 off = woff0 + bit;
-            const uint8_t c0 = s_win[off], c1 = s_win[off + 1];
+            const uint8_t c0 = win[off], c1 = win[off + 1];
             const bool known = (c0 == 'S' || c0 == 'L' || c0 == 'P' || c0 == 'E' || c0 == 'C' || c0 == 'O');
             if (known && (c1 == '\t' || c1 == '\n')) {
                 rec |= 1ull << bit;
@@ -346,70 +341,52 @@ __global__ void __launch_bounds__(TK_THREADS, TK_MIN_BLOCKS) k_tokenize(const __
                 if (val < ld_volatile_u64(&P.cnt->first_unknown)) atomicMin(&P.cnt->first_unknown, val);
             }
         }
-        u64 total;
-        const u64 packed = ((u64)__popcll(rec) << 32) | (u64)__popcll(edg);
-        const u64 excl = block_excl_scan64(packed, s_scan, &total);
-        TK_MARK(2);
-        if (tid < 32) {
-            const u64 e = lookback_exclusive(P.tile_state, tile, total);
-            if (tid == 0) s_base = e;
+        // ---- warp scan of (records, edges): index of my first record / edge inside the tile
+        const u32 packed = ((u32)__popcll(rec) << 16) | (u32)__popcll(edg);
+        const u32 inc = warp_incl_scan(packed);
+        const u32 tot = __shfl_sync(0xffffffffu, inc, 31);
+        const u32 n_rec_tile = tot >> 16, n_edge_tile = tot & 0xFFFFu;
+        const u32 my_rec0 = (inc - packed) >> 16, my_edge0 = (inc - packed) & 0xFFFFu;
+        // one atomicAdd claims this tile's range of edge_slots; the abort flag rides along
+        u32 alloc = 0, aborted = 0;
+        if (lane == 0) {
+            if (n_edge_tile) alloc = atomicAdd(&P.cnt->edge_alloc, n_edge_tile);
+            aborted = ld_volatile_u32(&P.cnt->flags) & (CF_TABLE_FULL | CF_DEFER_FULL);
+            TileInfo ti;
+            ti.n_rec = n_rec_tile; ti.n_edge = n_edge_tile; ti.edge_alloc = alloc; ti.pad = 0;
+            P.tile_info[tile] = ti;
         }
-        TK_MARK(3);
-        const u32 n_rec_tile = (u32)(total >> 32);
-        __syncthreads();
-        TK_MARK(4);
-        const u32 rec_base = (u32)(s_base >> 32), edge_base = (u32)s_base;
-        // ---- pass 2: parse, hash, emit (skipped once a capacity overflow has been flagged: the host
-        // grows the buffers and reruns).  Record lines are compacted into s_list (TK_LIST_CAP per batch;
-        // one batch unless the tile holds very short lines) and handed out one line per thread per round,
-        // so neighbouring threads parse neighbouring lines.
-        const bool aborted = (ld_volatile_u32(&P.cnt->flags) & (CF_TABLE_FULL | CF_DEFER_FULL)) != 0;
-        for (u32 lo = 0; lo < n_rec_tile && !aborted; lo += TK_LIST_CAP) {
+        alloc = __shfl_sync(0xffffffffu, alloc, 0);
+        aborted = __shfl_sync(0xffffffffu, aborted, 0);
+        u32 claimed = 0;
+        // ---- parse, hash, emit.  Record lines are compacted into `list` (WT_LIST per batch; one batch
+        // unless the tile holds very short lines) and handed out one line per lane per round, so
+        // neighbouring lanes parse neighbouring lines.
+        for (u32 lo = 0; lo < n_rec_tile && !aborted; lo += WT_LIST) {
             {
-                u32 ri = (u32)(excl >> 32), ei = (u32)excl;
+                u32 ri = my_rec0, ei = my_edge0;
                 for (u64 m = rec; m; m &= m - 1) {
                     const int bit = __ffsll((long long)m) - 1;
-                    if (ri - lo < TK_LIST_CAP) s_list[ri - lo] = (woff0 + bit) | (ei << 16);  // offset | edge ordinal in tile
+                    if (ri - lo < WT_LIST) list[ri - lo] = (woff0 + bit) | (ei << 16);
                     ri++;
                     ei += (u32)((edg >> bit) & 1);
                 }
             }
-            __syncthreads();
-            const u32 nb = min(n_rec_tile - lo, (u32)TK_LIST_CAP);
-            for (u32 i = tid; i < nb; i += TK_THREADS) {
-                const u32 ent = s_list[i];
-                const u32 off = ent & 0xFFFFu;
-                const u32 rec_ord = rec_base + lo + i, edge_ord = edge_base + (ent >> 16);
-                if (!parse_line_fast(P, t, off, rec_ord, edge_ord, claimed)) defer_line(P, wbase + off, rec_ord, edge_ord);
+            __syncwarp();
+            const u32 nb = min(n_rec_tile - lo, (u32)WT_LIST);
+            for (u32 i = lane; i < nb; i += 32) {
+                const u32 ent = list[i];
+                const u32 off = ent & 0xFFFFu, eidx = ent >> 16;
+                if (!parse_line_fast(P, t, off, make_order(tile, lo + i, 0), alloc + eidx, claimed))
+                    defer_line(P, wbase + off, tile, lo + i, eidx);
             }
-            if (lo + TK_LIST_CAP < n_rec_tile) __syncthreads();
+            __syncwarp();
         }
-        TK_MARK(5);
-        if (tile == P.n_tiles - 1 && tid == 0) {
-            // the last tile knows the grand totals
-            const u32 nr = rec_base + n_rec_tile, ne = edge_base + (u32)total;
-            P.cnt->n_records = nr;
-            P.cnt->n_edges = ne;
-            if (ne > P.edge_cap) atomicOr(&P.cnt->flags, CF_EDGE_FULL);
-        }
-        // new keys of this tile: one atomic per warp
-        {
-            u32 wsum = claimed;
+        // new keys of this tile: one fire-and-forget atomic per warp (the host checks the load factor)
 #pragma unroll
-            for (int d = 16; d; d >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, d);
-            if ((tid & 31) == 0 && wsum) {
-                const u32 before = atomicAdd(&P.cnt->n_keys, wsum);
-                if (before + wsum > P.table_max_keys) atomicOr(&P.cnt->flags, CF_TABLE_FULL);
-            }
-            claimed = 0;
-        }
-        __syncthreads();
-        TK_MARK(6);
+        for (int d = 16; d; d >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, d);
+        if (lane == 0 && claimed) atomicAdd(&P.cnt->n_keys, claimed);
     }
-#ifdef TK_TIMING
-    if (tid == 0)
-        for (int k = 0; k < 8; k++) atomicAdd(&P.cnt->phase[k], (u64)tph[k]);
-#endif
 }
 
 }  // namespace g2n

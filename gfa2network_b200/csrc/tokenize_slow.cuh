@@ -153,12 +153,11 @@ __device__ __forceinline__ KeyDesc node_key(const ScanParams& P, const Win& w, S
 }
 
 // Handles one line that starts at global offset p.  rec_ord / edge_ord are this line's ordinals.
-__device__ __forceinline__ void parse_line_body(const ScanParams& P, const Win& w, u64 p, u32 rec_ord, u32 edge_ord, u32& claimed)
+__device__ __forceinline__ void parse_line_body(const ScanParams& P, const Win& w, u64 p, u64 order0, u32 edge_ord, u32& claimed)
 {
     const uint8_t c0 = w(p);
     Cursor cur{p + 2, w(p + 1) == '\n'};
     Span f1, f2, f3, f4, f5, f6, f7, f8, ft;
-    const u64 order0 = (u64)rec_ord << 2;
     if (c0 == 'S') {
         if (!next_field(w, cur, f1)) { report_error(P.cnt, p, G2N_PE_S_NO_ID); return; }
         if (P.bidirected) {
@@ -278,7 +277,7 @@ __global__ void __launch_bounds__(128) k_tokenize_slow(const __grid_constant__ S
     Win w{nullptr, P.text, 0, P.nbytes, 0};
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_defer; i += gridDim.x * blockDim.x) {
         const DeferEnt d = P.defer[i];
-        parse_line_body(P, w, d.off, d.rec_ord, d.edge_ord, claimed);
+        parse_line_body(P, w, d.off, make_order(d.tile, d.rec_idx, 0), P.tile_info[d.tile].edge_alloc + d.edge_idx, claimed);
     }
     if (claimed) {
         const u32 before = atomicAdd(&P.cnt->n_keys, claimed);

@@ -115,6 +115,32 @@ def test_segments_with_sequences_vs_oracle():
     assert nodes == onodes
 
 
+def test_hub_rows_vs_oracle():
+    """Rows far above the one-lane limit (64) and above the shared-memory bitonic limit (4096):
+    a hub linked to 12 000 spokes, with duplicate and reverse links and integer weights."""
+    import random
+
+    from oracle.oracle import oracle_convert_format, oracle_parse_gfa
+
+    parse, convert = _api()
+    r = random.Random(5)
+    lines = ["S\thub\t*", "S\tmid\t*"]
+    for i in range(12000):
+        lines.append(f"L\thub\t+\tn{i % 9000}\t-\t0M\tRC:i:{r.randrange(1, 50)}")
+    for i in range(300):
+        lines.append(f"L\tn{r.randrange(9000)}\t+\tmid\t+\t0M\tRC:i:{r.randrange(1, 9)}")
+    for i in range(3000):
+        lines.append(f"L\tn{r.randrange(9000)}\t-\thub\t+\t0M")
+    text = ("\n".join(lines) + "\n").encode()
+    for mode in (dict(weight_tag="RC"), dict(weight_tag="RC", directed=False), dict(asymmetric=True), dict(bidirected=True, weight_tag="RC")):
+        A, nodes = parse(text, return_node_list=True, **mode)
+        B, onodes = oracle_parse_gfa(text, return_node_list=True, **mode)
+        _same(A, B, f"hub raw {mode}")
+        assert nodes == onodes
+        for fmt in ("csr", "csc"):
+            _same(convert(A, fmt), oracle_convert_format(B, fmt), f"hub {fmt} {mode}")
+
+
 def test_full_size_c2_properties():
     """BASELINE.json configs[1] at full size: size-independent properties + oracle check."""
     from gfa2network_b200.synth import CONFIGS, synth_gfa
