@@ -164,12 +164,13 @@ class Handle:
         self.check(self.lib.g2n_convert(self.h, fmt))
 
     def fetch_matrix(self):
+        """Result arrays as NumPy arrays backed by pinned host memory (DMA target of the D2H copy)."""
         s = self.sizes()
         dt = DTYPE_NP[s.dtype]
         n, nnz = s.n_nodes, s.nnz
-        a0 = np.empty(nnz if s.format == FMT_COO else n + 1, dtype=np.int32)
-        a1 = np.empty(nnz, dtype=np.int32)
-        data = np.empty(nnz, dtype=dt)
+        a0 = pinned_empty(nnz if s.format == FMT_COO else n + 1, np.int32)
+        a1 = pinned_empty(nnz, np.int32)
+        data = pinned_empty(nnz, dt)
         self.check(self.lib.g2n_fetch_matrix(self.h, a0.ctypes.data, a1.ctypes.data, data.ctypes.data))
         return s, a0, a1, data
 
@@ -181,6 +182,43 @@ class Handle:
         return names[: s.names_bytes], offs
 
 
+class _PinnedBlock:
+    """Owner of one g2n_host_alloc allocation; freed when the last NumPy view dies."""
+
+    def __init__(self, nbytes: int):
+        self.lib = load()
+        self.ptr = self.lib.g2n_host_alloc(max(1, nbytes))
+        if not self.ptr:
+            raise MemoryError(f"g2n_host_alloc({nbytes}) failed")
+        self.nbytes = nbytes
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.lib.g2n_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def pinned_empty(count: int, dtype) -> np.ndarray:
+    """np.empty(count, dtype) in page-locked host memory (falls back to nothing: raises on failure)."""
+    dt = np.dtype(dtype)
+    nbytes = int(count) * dt.itemsize
+    if nbytes == 0:
+        return np.empty(0, dtype=dt)
+    blk = _PinnedBlock(nbytes)
+    buf = (C.c_uint8 * nbytes).from_address(blk.ptr)
+    arr = np.frombuffer(buf, dtype=dt, count=int(count))
+    # keep the allocation alive as long as any view of the array is
+    _keepalive[id(buf)] = blk
+    import weakref
+
+    weakref.finalize(buf, _keepalive.pop, id(buf), None)
+    return arr
+
+
+_keepalive: dict[int, _PinnedBlock] = {}
 _default: dict[int, Handle] = {}
 
 

@@ -125,12 +125,24 @@ def _node_list(handle, raw_bytes_id):
 
 
 def _matrix_from_handle(handle):
+    """SciPy matrix over the fetched arrays.  The arrays come straight from the device build (sorted,
+    in range, right dtypes), so SciPy's O(nnz) constructor validation is skipped by filling an empty
+    matrix object."""
     s, a0, a1, data = handle.fetch_matrix()
     n = s.n_nodes
     if s.format == _capi.FMT_COO:
-        return sp.coo_matrix((data, (a0, a1)), shape=(n, n))
+        A = sp.coo_matrix((n, n), dtype=data.dtype)
+        A.data = data
+        if hasattr(A, "coords"):
+            A.coords = (a0, a1)
+        else:  # SciPy < 1.13
+            A.row, A.col = a0, a1
+        A.has_canonical_format = False
+        return A
     cls = sp.csr_matrix if s.format == _capi.FMT_CSR else sp.csc_matrix
-    return cls((data, a1, a0), shape=(n, n))
+    A = cls((n, n), dtype=data.dtype)
+    A.data, A.indices, A.indptr = data, a1, a0
+    return A
 
 
 def parse_gfa(

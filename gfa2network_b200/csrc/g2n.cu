@@ -3,7 +3,7 @@
 //   K1  k_tokenize        line scan + field split + node-key hashing + edge-record emission (tokenize.cuh)
 //   K2  k_mark_first / k_assign_ids / k_gather_names   first-appearance ranking -> node IDs   (ids.cuh)
 //   K3  k_emit_coo | k_emit_keys                        COO triplets / sort keys               (ids.cuh)
-//   K4  k_rows_count / k_rows_scatter / k_rows_big / k_rows_finalize    row bucketing + dedup/sum (+max) (rowsort.cuh)
+//   K4  k_rows_count / k_rows_scatter / k_rows_big / k_rows_sort / k_rows_write   row bucketing + dedup/sum (+max) (rowsort.cuh)
 // No CPU fallback exists: every entry point needs a CUDA device.
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -60,7 +60,7 @@ struct g2n_handle {
     cudaEvent_t ev[EV_COUNT];
     // device buffers (kept between builds: a warm handle allocates nothing)
     DevBuf text, table, tfirst, trep, defer, edge_slots, edge_w, longs, tile_info, tile_base, cnt, bitmap, wprefix, slot_id, id2slot, name_len, name_off, names;
-    DevBuf rowcnt, rowptr, entries, w_emit, biglist, indptr, indices, data, row, col, scan_state;
+    DevBuf rowcnt, rowptr, entries, w_emit, biglist, ucnt, indptr, indices, data, row, col, scan_state;
     DevBuf up_row, up_col, up_data;
     Counters* h_cnt = nullptr;  // pinned
     u64* h_tail = nullptr;      // pinned: {nnz, names_bytes, tile_base total}
@@ -80,6 +80,8 @@ struct g2n_handle {
     bool symmax = false;
     int result_format = G2N_FMT_COO;
     bool names_ready = false;
+    bool nnz_in_tail3 = false;  // nnz arrives as int32 in h_tail[3] (compressed builds)
+    bool edges_are_ids = false; // edge_slots were translated to node IDs in place
     g2n_diag diag;
     u32 launches = 0;
     // optional per-kernel timing (g2n_set_profile): one event pair per launch
@@ -143,13 +145,6 @@ inline u32 next_pow2(u64 x)
     return (u32)p;
 }
 
-inline int ceil_log2(u64 n)
-{
-    int b = 0;
-    while ((1ull << b) < n) b++;
-    return b < 1 ? 1 : b;
-}
-
 // exclusive scan launcher: out[0..n], out[n] = total
 template <typename Tout, class LoadOp>
 int launch_scan(g2n_handle* h, LoadOp load, Tout* out, u64 n)
@@ -188,19 +183,17 @@ int rows_finalize_typed(g2n_handle* h, u64 M, u64 n, int sym, const double* w_em
     { KScope ks(h, "k_rows_find_big"); k_rows_find_big<<<grid_for(n, 256), 256, 0, h->stream>>>(h->rowptr.as<u32>(), n32, h->biglist.as<u32>(), bigcount); }
     { KScope ks(h, "k_rows_big"); k_rows_big<<<G2N_SM_COUNT, 256, 0, h->stream>>>(h->rowptr.as<u32>(), h->biglist.as<u32>(), bigcount, h->entries.as<u64>()); }
     const u64 n_groups = (n + 31) / 32;
-    CK(h->scan_state.ensure((n_groups + 2) * sizeof(u64)));
-    CK(cudaMemsetAsync(h->scan_state.p, 0, (n_groups + 2) * sizeof(u64), h->stream));
-    u64* state = h->scan_state.as<u64>() + 1;
-    u32* ticket = (u32*)h->scan_state.p;
-    u64* nnz_dev = (u64*)&h->cnt.as<Counters>()->nnz;
-    {
-        KScope ks(h, "k_rows_finalize");
-        k_rows_finalize<T><<<grid_for(n_groups, RS_WARPS, 8), RS_WARPS * 32, 0, h->stream>>>(
-            h->rowptr.as<u32>(), h->entries.as<u64>(), n32, sym, w_emit, w_typed, h->indptr.as<int32_t>(), h->indices.as<int32_t>(),
-            h->data.as<T>(), state, ticket, nnz_dev);
-    }
+    CK(h->ucnt.ensure((n + 2) * sizeof(u32)));
+    { KScope ks(h, "k_rows_sort"); k_rows_sort<T><<<grid_for(n_groups, RS_WARPS, 12), RS_WARPS * 32, 0, h->stream>>>(h->rowptr.as<u32>(), h->entries.as<u64>(), n32, sym, w_emit, w_typed, h->ucnt.as<u32>()); }
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(&h->h_tail[0], nnz_dev, sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
+    LoadArray<u32> ldu{h->ucnt.as<u32>()};
+    int rc = launch_scan<int32_t>(h, ldu, h->indptr.as<int32_t>(), n);
+    if (rc) return rc;
+    { KScope ks(h, "k_rows_write"); k_rows_write<T><<<grid_for(n, 256), 256, 0, h->stream>>>(h->rowptr.as<u32>(), h->entries.as<u64>(), n32, sym, w_emit, w_typed, h->indptr.as<int32_t>(), h->indices.as<int32_t>(), h->data.as<T>()); }
+    CK(cudaGetLastError());
+    // nnz = indptr[n]
+    CK(cudaMemcpyAsync(&h->h_tail[3], h->indptr.as<int32_t>() + n, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    h->nnz_in_tail3 = true;
     return G2N_OK;
 }
 
@@ -243,6 +236,8 @@ EmitParams emit_params(g2n_handle* h)
     E.n_tiles = h->n_tiles;
     E.slots_per_edge = h->spe;
     E.tpe = h->tpe;
+    E.ids_ready = h->edges_are_ids ? 1 : 0;
+    E.write_ids = 0;
     return E;
 }
 
@@ -270,10 +265,14 @@ int build_compressed(g2n_handle* h, int fmt)
     CK(h->entries.ensure((M + 1) * sizeof(u64)));
     if (weighted) CK(h->w_emit.ensure((T + 1) * sizeof(double)));
     CK(cudaMemsetAsync(h->rowcnt.p, 0, (n + 2) * sizeof(u32), h->stream));
-    const EmitParams E = emit_params(h);
+    EmitParams E = emit_params(h);
+    E.write_ids = 1;  // the count pass leaves node IDs in edge_slots for the scatter pass (and later converts)
     const u32 egrid = grid_for((u64)h->n_tiles * 32, 256);
     { KScope ks(h, "k_rows_count"); k_rows_count<<<egrid, 256, 0, h->stream>>>(E, sym, csc, h->rowcnt.as<u32>(), weighted ? h->w_emit.as<double>() : nullptr); }
     CK(cudaGetLastError());
+    h->edges_are_ids = true;
+    E.ids_ready = 1;
+    E.write_ids = 0;
     LoadArray<u32> ldc{h->rowcnt.as<u32>()};
     int rc = launch_scan<u32>(h, ldc, h->rowptr.as<u32>(), n);
     if (rc) return rc;
@@ -325,7 +324,8 @@ int build_coo(g2n_handle* h)
 int finish_result(g2n_handle* h)
 {
     CK(cudaStreamSynchronize(h->stream));
-    h->nnz = h->h_tail[0];
+    h->nnz = h->nnz_in_tail3 ? (u64)(u32)h->h_tail[3] : h->h_tail[0];
+    h->nnz_in_tail3 = false;
     h->names_bytes = h->h_tail[1];
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev[EV_START], h->ev[EV_REDUCE]);
@@ -361,7 +361,7 @@ int g2n_create(int device, g2n_handle** out)
     h->stream = h->own_stream;
     for (int i = 0; i < EV_COUNT; i++) cudaEventCreate(&h->ev[i]);
     if (cudaHostAlloc((void**)&h->h_cnt, sizeof(Counters), cudaHostAllocDefault) != cudaSuccess ||
-        cudaHostAlloc((void**)&h->h_tail, 4 * sizeof(u64), cudaHostAllocDefault) != cudaSuccess) {
+        cudaHostAlloc((void**)&h->h_tail, 8 * sizeof(u64), cudaHostAllocDefault) != cudaSuccess) {
         delete h;
         return G2N_ERR_CUDA;
     }
@@ -377,7 +377,7 @@ void g2n_destroy(g2n_handle* h)
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->text, &h->table, &h->tfirst, &h->trep, &h->defer, &h->edge_slots, &h->edge_w, &h->longs, &h->tile_info, &h->tile_base, &h->cnt, &h->bitmap, &h->wprefix,
-                      &h->slot_id, &h->id2slot, &h->name_len, &h->name_off, &h->names, &h->rowcnt, &h->rowptr, &h->entries, &h->w_emit, &h->biglist, &h->indptr, &h->indices, &h->data, &h->row, &h->col,
+                      &h->slot_id, &h->id2slot, &h->name_len, &h->name_off, &h->names, &h->rowcnt, &h->rowptr, &h->entries, &h->w_emit, &h->biglist, &h->ucnt, &h->indptr, &h->indices, &h->data, &h->row, &h->col,
                       &h->scan_state, &h->up_row, &h->up_col, &h->up_data};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(h->ev[i]);
@@ -454,6 +454,7 @@ int g2n_build(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n_par
     h->built = false;
     h->have_edges = false;
     h->names_ready = false;
+    h->edges_are_ids = false;
     if (p->dtype < G2N_DTYPE_F64 || p->dtype > G2N_DTYPE_BOOL) { h->err = "unknown dtype"; return G2N_ERR_INVALID; }
     if (p->want_format < G2N_FMT_NATIVE || p->want_format > G2N_FMT_CSC) { h->err = "unknown want_format"; return G2N_ERR_INVALID; }
     if (p->weight_tag_len > 64) { h->err = "weight tag longer than 64 bytes"; return G2N_ERR_UNSUPPORTED; }
@@ -772,7 +773,8 @@ int g2n_coo_to_compressed(g2n_handle* h, const int32_t* row, const int32_t* col,
     rc = rows_finalize(h, dtype, nnz_in, n, 0, nullptr, h->up_data.p);
     if (rc) return rc;
     CK(cudaStreamSynchronize(h->stream));
-    const u64 nnz = h->h_tail[0];
+    const u64 nnz = (u64)(u32)h->h_tail[3];
+    h->nnz_in_tail3 = false;
     *nnz_out = nnz;
     CK(cudaMemcpyAsync(indptr, h->indptr.p, (n + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     if (nnz) {

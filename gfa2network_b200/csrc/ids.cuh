@@ -101,7 +101,7 @@ template <> __device__ __forceinline__ BoolT zero_t<BoolT>() { BoolT b; b.v = 0;
 // order); file order is tile order, so the emission index of tile t's j-th edge record is
 // (edges before tile t) + j.  One warp walks one tile.
 struct EmitParams {
-    const u32* edge_slots;
+    u32* edge_slots;       // per stored edge record: table slots of its endpoints, or -- once ids_ready -- node IDs
     const double* edge_w;  // NULL when no weight tag: every weight is 1.0
     const u32* slot_id;
     const TileInfo* tile_info;
@@ -109,13 +109,76 @@ struct EmitParams {
     u32 n_tiles;
     int slots_per_edge;    // 2 | 4
     int tpe;               // triplets per edge record: 1 (graph_directed) | 2 | 4
+    int ids_ready;         // edge_slots already hold node IDs (translated in place by an earlier pass)
+    int write_ids;         // translate in place during this pass
 };
 
-__device__ __forceinline__ void edge_triplet(const EmitParams& E, u32 stored, int k, u32& r, u32& c)
+#define EM_UNROLL 4
+
+// Walks the edge records in emission order, EM_UNROLL records per lane in flight, and calls
+// f(stored, t0, id[4]) where t0 is the emission index of the record's first triplet.  The triplets of a
+// record are (builders.py:222-234): (a,b) [, (b,a)] [, (c,d), (d,c)] with a = id[0], b = id[1],
+// c = id[2] = v:flip(ot), d = id[3] = u:flip(of).
+template <class F>
+__device__ __forceinline__ void for_each_edge(const EmitParams& E, F f)
 {
-    // builders.py:222-234: (a,b) [, (b,a)] [, (c,d), (d,c)] with c = v:flip(ot), d = u:flip(of)
-    const u32* s = E.edge_slots + (u64)stored * E.slots_per_edge;
-    const u32 a = E.slot_id[s[(k & 2)]], b = E.slot_id[s[(k & 2) + 1]];
+    const u32 lane = threadIdx.x & 31;
+    const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (u32 tile = warp; tile < E.n_tiles; tile += n_warps) {
+        const TileInfo ti = E.tile_info[tile];
+        if (ti.n_edge == 0) continue;
+        const u32 e0 = (u32)E.tile_base[tile];  // edge records before this tile
+        for (u32 j0 = 0; j0 < ti.n_edge; j0 += 32 * EM_UNROLL) {
+            u32 id[EM_UNROLL][4];
+#pragma unroll
+            for (int u = 0; u < EM_UNROLL; u++) {
+                const u32 j = j0 + u * 32 + lane;
+                if (j < ti.n_edge) {
+                    const u32* s = E.edge_slots + (u64)(ti.edge_alloc + j) * E.slots_per_edge;
+                    if (E.slots_per_edge == 4) {
+                        const uint4 q = *reinterpret_cast<const uint4*>(s);
+                        id[u][0] = q.x; id[u][1] = q.y; id[u][2] = q.z; id[u][3] = q.w;
+                    } else {
+                        const uint2 q = *reinterpret_cast<const uint2*>(s);
+                        id[u][0] = q.x; id[u][1] = q.y; id[u][2] = 0; id[u][3] = 0;
+                    }
+                }
+            }
+            if (!E.ids_ready) {
+#pragma unroll
+                for (int u = 0; u < EM_UNROLL; u++) {
+                    const u32 j = j0 + u * 32 + lane;
+                    if (j < ti.n_edge) {
+                        id[u][0] = E.slot_id[id[u][0]];
+                        id[u][1] = E.slot_id[id[u][1]];
+                        if (E.slots_per_edge == 4) { id[u][2] = E.slot_id[id[u][2]]; id[u][3] = E.slot_id[id[u][3]]; }
+                    }
+                }
+                if (E.write_ids) {
+#pragma unroll
+                    for (int u = 0; u < EM_UNROLL; u++) {
+                        const u32 j = j0 + u * 32 + lane;
+                        if (j < ti.n_edge) {
+                            u32* s = E.edge_slots + (u64)(ti.edge_alloc + j) * E.slots_per_edge;
+                            if (E.slots_per_edge == 4) *reinterpret_cast<uint4*>(s) = make_uint4(id[u][0], id[u][1], id[u][2], id[u][3]);
+                            else *reinterpret_cast<uint2*>(s) = make_uint2(id[u][0], id[u][1]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < EM_UNROLL; u++) {
+                const u32 j = j0 + u * 32 + lane;
+                if (j < ti.n_edge) f(ti.edge_alloc + j, (e0 + j) * (u32)E.tpe, id[u]);
+            }
+        }
+    }
+}
+
+// k-th triplet of a record
+__device__ __forceinline__ void record_triplet(const u32 (&id)[4], int k, u32& r, u32& c)
+{
+    const u32 a = id[k & 2], b = id[(k & 2) + 1];
     if (k & 1) { r = b; c = a; } else { r = a; c = b; }
 }
 
@@ -123,64 +186,16 @@ __device__ __forceinline__ void edge_triplet(const EmitParams& E, u32 stored, in
 template <typename T>
 __global__ void __launch_bounds__(256) k_emit_coo(const EmitParams E, int32_t* __restrict__ row, int32_t* __restrict__ col, T* __restrict__ data)
 {
-    const u32 lane = threadIdx.x & 31;
-    const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (u32 tile = warp; tile < E.n_tiles; tile += n_warps) {
-        const TileInfo ti = E.tile_info[tile];
-        if (ti.n_edge == 0) continue;
-        const u64 out0 = (u64)(u32)E.tile_base[tile] * E.tpe;
-        const u32 cnt = ti.n_edge * E.tpe;
-        for (u32 j = lane; j < cnt; j += 32) {
-            const u32 stored = ti.edge_alloc + j / E.tpe;
+    for_each_edge(E, [&](u32 stored, u32 t0, const u32 (&id)[4]) {
+        const T w = cast_weight<T>(E.edge_w ? E.edge_w[stored] : 1.0);
+        for (int k = 0; k < E.tpe; k++) {
             u32 r, c;
-            edge_triplet(E, stored, (int)(j % E.tpe), r, c);
-            row[out0 + j] = (int32_t)r;
-            col[out0 + j] = (int32_t)c;
-            data[out0 + j] = cast_weight<T>(E.edge_w ? E.edge_w[stored] : 1.0);
+            record_triplet(id, k, r, c);
+            row[t0 + k] = (int32_t)r;
+            col[t0 + k] = (int32_t)c;
+            data[t0 + k] = w;
         }
-    }
-}
-
-// Sort keys for the compressed build.  key = ((major << mbits | minor) << 1) | dir ; payload = stored edge index.
-//   sym == 0: one key per triplet, major = row (CSR) or col (CSC)                    (utils.py:55 tocsr/tocsc)
-//   sym == 1: two keys per triplet: (row, col, dir 0) and (col, row, dir 1)         (builders.py:283 maximum(A, A.T))
-__global__ void __launch_bounds__(256) k_emit_keys(const EmitParams E, int sym, int csc, int mbits, u64* __restrict__ keys, u32* __restrict__ payload)
-{
-    const u32 lane = threadIdx.x & 31;
-    const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (u32 tile = warp; tile < E.n_tiles; tile += n_warps) {
-        const TileInfo ti = E.tile_info[tile];
-        if (ti.n_edge == 0) continue;
-        const u64 out0 = (u64)(u32)E.tile_base[tile] * E.tpe;
-        const u32 cnt = ti.n_edge * E.tpe;
-        for (u32 j = lane; j < cnt; j += 32) {
-            const u32 stored = ti.edge_alloc + j / E.tpe;
-            u32 r, c;
-            edge_triplet(E, stored, (int)(j % E.tpe), r, c);
-            const u64 t = out0 + j;
-            if (sym) {
-                keys[2 * t] = ((((u64)r << mbits) | c) << 1);
-                keys[2 * t + 1] = ((((u64)c << mbits) | r) << 1) | 1ull;
-                if (payload) { payload[2 * t] = stored; payload[2 * t + 1] = stored; }
-            } else {
-                const u32 major = csc ? c : r, minor = csc ? r : c;
-                keys[t] = (((u64)major << mbits) | minor) << 1;
-                if (payload) payload[t] = stored;
-            }
-        }
-    }
-}
-
-// Same, from caller-provided COO arrays (g2n_coo_to_compressed): payload = triplet index.
-__global__ void __launch_bounds__(256) k_keys_from_coo(const int32_t* __restrict__ row, const int32_t* __restrict__ col, u64 nnz,
-                                                        int csc, int mbits, u64* __restrict__ keys, u32* __restrict__ payload)
-{
-    for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < nnz; t += (u64)gridDim.x * blockDim.x) {
-        const u32 r = (u32)row[t], c = (u32)col[t];
-        const u32 major = csc ? c : r, minor = csc ? r : c;
-        keys[t] = (((u64)major << mbits) | minor) << 1;
-        payload[t] = (u32)t;
-    }
+    });
 }
 
 }  // namespace g2n

@@ -6,10 +6,11 @@
 //   exclusive scan   cnt -> rowptr                                                (common.cuh)
 //   k_rows_scatter   entry (minor, dir, emission index) -> rowptr[major] + ticket (any order inside a row)
 //   k_rows_big       rows longer than RS_SMALL are sorted in place by a whole CTA (bitonic; rare)
-//   k_rows_finalize  one lane per row: insertion sort by (minor, dir, emission index) in shared memory,
-//                    left-to-right duplicate sum, optional max(S, S^T), and -- with a decoupled
-//                    look-back over 32-row groups -- direct output of indptr / indices / data
-// Every triplet is read twice and written once; the sorted order inside a row is total (the emission
+//   k_rows_sort      one lane per row: insertion sort by (minor, dir, emission index) in shared memory,
+//                    count of the entries the row will store (duplicates summed, zeros of max() dropped)
+//   exclusive scan   counts -> indptr
+//   k_rows_write     one lane per row: left-to-right duplicate sum, optional max(S, S^T), output
+// No kernel waits on another CTA; the sorted order inside a row is total (the emission
 // index breaks ties), so the result is deterministic and duplicate weights are summed in emission
 // order exactly like SciPy does for rows of <= 16 stored entries.
 //
@@ -31,37 +32,31 @@ __device__ __forceinline__ u32 rs_minor(u64 e) { return (u32)(e >> 33); }
 __device__ __forceinline__ u32 rs_dir(u64 e) { return (u32)(e >> 32) & 1u; }
 __device__ __forceinline__ u32 rs_t(u64 e) { return (u32)e; }
 
-// Walks the triplets of the build in emission order and calls f(major, minor, dir, t).
+// Entries of one edge record:  g(major, minor, dir, t)
 //   sym == 0: one entry per triplet, major = row (CSR) or col (CSC)
 //   sym == 1: two entries per triplet: (row, col, dir 0) and (col, row, dir 1)   [max(S, S^T)]
-template <class F>
-__device__ __forceinline__ void for_each_entry(const EmitParams& E, int sym, int csc, F f)
+template <class G>
+__device__ __forceinline__ void record_entries(const u32 (&id)[4], int tpe, u32 t0, int sym, int csc, G g)
 {
-    const u32 lane = threadIdx.x & 31;
-    const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (u32 tile = warp; tile < E.n_tiles; tile += n_warps) {
-        const TileInfo ti = E.tile_info[tile];
-        if (ti.n_edge == 0) continue;
-        const u32 out0 = (u32)E.tile_base[tile] * E.tpe;
-        const u32 cnt = ti.n_edge * E.tpe;
-        for (u32 j = lane; j < cnt; j += 32) {
-            const u32 stored = ti.edge_alloc + j / E.tpe;
-            u32 r, c;
-            edge_triplet(E, stored, (int)(j % E.tpe), r, c);
-            const u32 t = out0 + j;
-            if (sym) { f(r, c, 0u, t, stored); f(c, r, 1u, t, stored); }
-            else if (csc) f(c, r, 0u, t, stored);
-            else f(r, c, 0u, t, stored);
-        }
+    for (int k = 0; k < tpe; k++) {
+        u32 r, c;
+        record_triplet(id, k, r, c);
+        if (sym) { g(r, c, 0u, t0 + k); g(c, r, 1u, t0 + k); }
+        else if (csc) g(c, r, 0u, t0 + k);
+        else g(r, c, 0u, t0 + k);
     }
 }
 
-// histogram of majors; also lays the weights out in emission order (w_emit[t]) when there are any
+// histogram of majors; translates edge_slots to node IDs in place and lays the weights out in emission
+// order (w_emit[t]) when there are any
 __global__ void __launch_bounds__(256) k_rows_count(const EmitParams E, int sym, int csc, u32* __restrict__ cnt, double* __restrict__ w_emit)
 {
-    for_each_entry(E, sym, csc, [&](u32 major, u32, u32 dir, u32 t, u32 stored) {
-        atomicAdd(&cnt[major], 1u);
-        if (w_emit && dir == 0) w_emit[t] = E.edge_w[stored];
+    for_each_edge(E, [&](u32 stored, u32 t0, const u32 (&id)[4]) {
+        record_entries(id, E.tpe, t0, sym, csc, [&](u32 major, u32, u32, u32) { atomicAdd(&cnt[major], 1u); });
+        if (w_emit) {
+            const double w = E.edge_w[stored];
+            for (int k = 0; k < E.tpe; k++) w_emit[t0 + k] = w;
+        }
     });
 }
 
@@ -70,9 +65,12 @@ __global__ void __launch_bounds__(256) k_rows_count(const EmitParams E, int sym,
 __global__ void __launch_bounds__(256) k_rows_scatter(const EmitParams E, int sym, int csc, const u32* __restrict__ rowptr,
                                                        u32* __restrict__ cnt, u64* __restrict__ entries)
 {
-    for_each_entry(E, sym, csc, [&](u32 major, u32 minor, u32 dir, u32 t, u32) {
-        const u32 k = atomicSub(&cnt[major], 1u) - 1u;
-        entries[rowptr[major] + k] = rs_entry(minor, dir, t);
+    for_each_edge(E, [&](u32, u32 t0, const u32 (&id)[4]) {
+        record_entries(id, E.tpe, t0, sym, csc, [&](u32 major, u32 minor, u32 dir, u32 t) {
+            const u32 base = rowptr[major];
+            const u32 k = atomicSub(&cnt[major], 1u) - 1u;
+            entries[base + k] = rs_entry(minor, dir, t);
+        });
     });
 }
 
@@ -198,22 +196,19 @@ __device__ __forceinline__ void insertion_sort(u64* a, u32 len)
     }
 }
 
-// One warp per group of 32 consecutive rows, one lane per row.
+// Pass A: one warp per group of 32 consecutive rows, one lane per row: sort the row (staged in shared
+// memory when the group fits), write it back, count the entries it will store.
 template <typename T>
-__global__ void __launch_bounds__(RS_WARPS * 32) k_rows_finalize(const u32* __restrict__ rowptr, u64* __restrict__ entries, u32 n, int sym,
-                                                                  const double* __restrict__ w_emit, const T* __restrict__ w_typed,
-                                                                  int32_t* __restrict__ indptr, int32_t* __restrict__ indices, T* __restrict__ data,
-                                                                  u64* __restrict__ lb_state, u32* __restrict__ ticket, u64* __restrict__ nnz_out)
+__global__ void __launch_bounds__(RS_WARPS * 32) k_rows_sort(const u32* __restrict__ rowptr, u64* __restrict__ entries, u32 n, int sym,
+                                                              const double* __restrict__ w_emit, const T* __restrict__ w_typed,
+                                                              u32* __restrict__ ucnt)
 {
     __shared__ u64 s_ent[RS_WARPS][RS_GROUP_CAP];
     const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     u64* sm = s_ent[wid];
     const u32 n_groups = (n + 31) / 32;
-    while (true) {
-        u32 g = 0;
-        if (lane == 0) g = atomicAdd(ticket, 1u);
-        g = __shfl_sync(0xffffffffu, g, 0);
-        if (g >= n_groups) break;
+    const u32 warp = blockIdx.x * RS_WARPS + wid, n_warps = gridDim.x * RS_WARPS;
+    for (u32 g = warp; g < n_groups; g += n_warps) {
         const u32 r = g * 32 + lane;
         const bool live = r < n;
         const u32 lo = live ? rowptr[r] : 0, hi = live ? rowptr[r + 1] : 0;
@@ -223,33 +218,38 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_rows_finalize(const u32* __re
         const u32 g_len = g_hi - g_lo;
         const bool all_small = __all_sync(0xffffffffu, len <= RS_SMALL);
         const bool staged = all_small && g_len <= RS_GROUP_CAP;
+        __syncwarp();
         u64* a;
         if (staged) {
             for (u32 i = lane; i < g_len; i += 32) sm[i] = entries[g_lo + i];
             __syncwarp();
             a = sm + (lo - g_lo);
         } else {
-            a = entries + lo;  // sort in place in global memory (rows > RS_SMALL were sorted by k_rows_big)
+            a = entries + lo;  // in place in global memory (rows > RS_SMALL were sorted by k_rows_big)
         }
         if (len > 1 && len <= RS_SMALL) insertion_sort(a, len);
-        // first walk: how many stored entries does my row produce?
         const u32 mine = walk_row<T>(a, len, sym, w_emit, w_typed, [](u32, u32, T) {});
-        const u32 inc = warp_incl_scan(mine);
-        const u32 g_total = __shfl_sync(0xffffffffu, inc, 31);
-        const u64 g_base = lookback_exclusive(lb_state, g, (u64)g_total);
-        const u32 out0 = (u32)g_base + inc - mine;
-        if (live) indptr[r] = (int32_t)out0;
-        // second walk: write indices / data at their final positions
-        walk_row<T>(a, len, sym, w_emit, w_typed, [&](u32 k, u32 minor, T v) {
+        if (live) ucnt[r] = mine;
+        if (staged) {
+            __syncwarp();
+            for (u32 i = lane; i < g_len; i += 32) entries[g_lo + i] = sm[i];
+        }
+    }
+}
+
+// Pass B: indptr is known; one lane per row walks its sorted entries and writes indices / data.
+template <typename T>
+__global__ void __launch_bounds__(256) k_rows_write(const u32* __restrict__ rowptr, const u64* __restrict__ entries, u32 n, int sym,
+                                                     const double* __restrict__ w_emit, const T* __restrict__ w_typed,
+                                                     const int32_t* __restrict__ indptr, int32_t* __restrict__ indices, T* __restrict__ data)
+{
+    for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        const u32 lo = rowptr[r], len = rowptr[r + 1] - lo;
+        const u32 out0 = (u32)indptr[r];
+        walk_row<T>(entries + lo, len, sym, w_emit, w_typed, [&](u32 k, u32 minor, T v) {
             indices[out0 + k] = (int32_t)minor;
             data[out0 + k] = v;
         });
-        if (g == n_groups - 1 && lane == 31) {
-            const u64 total = g_base + g_total;
-            indptr[n] = (int32_t)total;
-            *nnz_out = total;
-        }
-        __syncwarp();
     }
 }
 
