@@ -21,6 +21,7 @@ EXPORTS = [
     "g2n_abi_version", "g2n_create", "g2n_destroy", "g2n_set_stream", "g2n_host_alloc", "g2n_host_free",
     "g2n_build", "g2n_convert", "g2n_sizes", "g2n_fetch_matrix", "g2n_fetch_names", "g2n_device_result",
     "g2n_status", "g2n_last_error", "g2n_coo_to_compressed", "g2n_set_profile", "g2n_kernel_times",
+    "g2n_dist_scan", "g2n_dist_export", "g2n_dist_merge", "g2n_dist_entries", "g2n_dist_slab",
 ]
 
 
@@ -37,7 +38,13 @@ class Sizes(C.Structure):
     _fields_ = [
         ("n_nodes", C.c_uint64), ("nnz", C.c_uint64), ("names_bytes", C.c_uint64),
         ("format", C.c_int32), ("index_bytes", C.c_int32), ("dtype", C.c_int32), ("reserved", C.c_int32),
+        ("slab_rows", C.c_uint64),
     ]
+
+
+class DistInfo(C.Structure):
+    _fields_ = [("n_keys", C.c_uint64), ("n_tiles", C.c_uint64), ("n_records", C.c_uint64),
+                ("n_edge_records", C.c_uint64), ("n_entries", C.c_uint64), ("reserved", C.c_uint64)]
 
 
 class Diag(C.Structure):
@@ -89,6 +96,12 @@ def load():
     lib.g2n_last_error.argtypes = [vp]
     lib.g2n_last_error.restype = C.c_char_p
     lib.g2n_coo_to_compressed.argtypes = [vp, vp, vp, vp, u64, u64, i32, i32, vp, vp, vp, C.POINTER(u64)]
+    pu64 = C.POINTER(u64)
+    lib.g2n_dist_scan.argtypes = [vp, vp, u64, C.POINTER(Params), C.POINTER(DistInfo)]
+    lib.g2n_dist_export.argtypes = [vp, vp, vp]
+    lib.g2n_dist_merge.argtypes = [vp, vp, u64, pu64, vp, u64, pu64, u64, C.c_int, pu64]
+    lib.g2n_dist_entries.argtypes = [vp, C.c_int, u64, u64, vp, u64, pu64]
+    lib.g2n_dist_slab.argtypes = [vp, vp, u64, u64, u64]
     lib.g2n_set_profile.argtypes = [vp, C.c_int]
     lib.g2n_kernel_times.argtypes = [vp, C.POINTER(KTime), C.c_int]
     _lib = lib
@@ -168,7 +181,7 @@ class Handle:
         s = self.sizes()
         dt = DTYPE_NP[s.dtype]
         n, nnz = s.n_nodes, s.nnz
-        a0 = pinned_empty(nnz if s.format == FMT_COO else n + 1, np.int32)
+        a0 = pinned_empty(nnz if s.format == FMT_COO else s.slab_rows + 1, np.int32)
         a1 = pinned_empty(nnz, np.int32)
         data = pinned_empty(nnz, dt)
         self.check(self.lib.g2n_fetch_matrix(self.h, a0.ctypes.data, a1.ctypes.data, data.ctypes.data))
@@ -182,43 +195,80 @@ class Handle:
         return names[: s.names_bytes], offs
 
 
-class _PinnedBlock:
-    """Owner of one g2n_host_alloc allocation; freed when the last NumPy view dies."""
+class _PinnedPool:
+    """Size-classed cache of page-locked host blocks.  cudaHostAlloc / cudaFreeHost cost tens of
+    milliseconds for result-sized buffers, so blocks are recycled when their NumPy views die."""
 
-    def __init__(self, nbytes: int):
-        self.lib = load()
-        self.ptr = self.lib.g2n_host_alloc(max(1, nbytes))
-        if not self.ptr:
-            raise MemoryError(f"g2n_host_alloc({nbytes}) failed")
-        self.nbytes = nbytes
+    MAX_CACHED = 8 << 30
 
-    def __del__(self):
+    def __init__(self):
+        self.free: dict[int, list[int]] = {}
+        self.cached = 0
+
+    @staticmethod
+    def size_class(nbytes: int) -> int:
+        n = max(nbytes, 4096)
+        k = max(n.bit_length() - 4, 0)
+        return ((n + (1 << k) - 1) >> k) << k  # <= 12.5 % above the request
+
+    def take(self, nbytes: int) -> tuple[int, int]:
+        cls = self.size_class(nbytes)
+        lst = self.free.get(cls)
+        if lst:
+            self.cached -= cls
+            return lst.pop(), cls
+        ptr = load().g2n_host_alloc(cls)
+        if not ptr:
+            self.trim(0)
+            ptr = load().g2n_host_alloc(cls)
+            if not ptr:
+                raise MemoryError(f"g2n_host_alloc({cls}) failed")
+        return ptr, cls
+
+    def give(self, ptr: int, cls: int):
+        if self.cached + cls > self.MAX_CACHED:
+            load().g2n_host_free(ptr)
+            return
+        self.free.setdefault(cls, []).append(ptr)
+        self.cached += cls
+
+    def trim(self, keep_bytes: int = 0):
+        for cls, lst in list(self.free.items()):
+            while lst and self.cached > keep_bytes:
+                load().g2n_host_free(lst.pop())
+                self.cached -= cls
+
+
+_pool = _PinnedPool()
+
+
+def _release(key: int):
+    ent = _keepalive.pop(key, None)
+    if ent is not None:
         try:
-            if self.ptr:
-                self.lib.g2n_host_free(self.ptr)
-                self.ptr = None
+            _pool.give(*ent)
         except Exception:
             pass
 
 
 def pinned_empty(count: int, dtype) -> np.ndarray:
-    """np.empty(count, dtype) in page-locked host memory (falls back to nothing: raises on failure)."""
+    """np.empty(count, dtype) in page-locked host memory (DMA target / source); raises on failure."""
+    import weakref
+
     dt = np.dtype(dtype)
     nbytes = int(count) * dt.itemsize
     if nbytes == 0:
         return np.empty(0, dtype=dt)
-    blk = _PinnedBlock(nbytes)
-    buf = (C.c_uint8 * nbytes).from_address(blk.ptr)
+    ptr, cls = _pool.take(nbytes)
+    buf = (C.c_uint8 * nbytes).from_address(ptr)
     arr = np.frombuffer(buf, dtype=dt, count=int(count))
-    # keep the allocation alive as long as any view of the array is
-    _keepalive[id(buf)] = blk
-    import weakref
-
-    weakref.finalize(buf, _keepalive.pop, id(buf), None)
+    # the block goes back to the pool when the last view of the array is gone
+    _keepalive[id(buf)] = (ptr, cls)
+    weakref.finalize(buf, _release, id(buf))
     return arr
 
 
-_keepalive: dict[int, _PinnedBlock] = {}
+_keepalive: dict[int, tuple[int, int]] = {}
 _default: dict[int, Handle] = {}
 
 

@@ -1,0 +1,162 @@
+// dist.cuh -- device side of the multi-GPU build (one process per GPU; the host moves the exchange
+// buffers between ranks with NCCL, see gfa2network_b200/dist.py and SURVEY.md 8(e)).
+//
+//   phase 1  every rank tokenizes its own byte range (k_tokenize, local table, local `order`)
+//   phase 2  k_dist_export: local distinct keys + their first local order  -> all-gather ->
+//            k_dist_insert: every rank builds the same global table keyed by the same bytes, keeping the
+//            global first appearance (records before the rank + records before the tile + index in tile);
+//            IDs by the same bitmap ranking as on one GPU; k_dist_localmap: local slot -> global ID
+//   phase 3  k_dist_dest_count / k_dist_dest_scatter: row entries bucketed by owner(row) -> all-to-all ->
+//            k_pairs_count / k_pairs_scatter + the single-GPU row sort: each rank builds its CSR slab
+// Restricted to inline (<= 15 byte) keys and unweighted builds; the host mirror refuses anything else.
+#pragma once
+#include "rowsort.cuh"
+
+namespace g2n {
+
+struct DistKey {
+    u64 k0, k1;
+    u64 order;  // local order (export) -- rewritten to the global order by the receiver
+    u64 pad;
+};
+
+// local distinct keys (any order)
+__global__ void __launch_bounds__(256) k_dist_export(const TKey* __restrict__ tkeys, const u64* __restrict__ tfirst, u32 cap,
+                                                      DistKey* __restrict__ out, u32* __restrict__ counter)
+{
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+        const TKey k = tkeys[i];
+        if (k.x == 0 && k.y == 0) continue;
+        const u32 j = atomicAdd(counter, 1u);
+        DistKey d;
+        d.k0 = k.x; d.k1 = k.y; d.order = ~tfirst[i]; d.pad = 0;
+        out[j] = d;
+    }
+}
+
+struct DistMergeParams {
+    const DistKey* keys;     // world * key_stride entries
+    const u64* tile_base;    // world * tile_stride entries: per-rank exclusive scan of (n_rec << 32 | n_edge)
+    u64 key_stride, tile_stride;
+    u64 n_keys[8];
+    u64 rec_base[8];         // records before each rank
+    int world;
+};
+
+// insert every rank's keys with their GLOBAL order = global record ordinal << 2 | sub-rank
+__global__ void __launch_bounds__(256) k_dist_insert(const ScanParams P, const DistMergeParams D)
+{
+    u32 claimed = 0;
+    for (int s = 0; s < D.world; s++) {
+        const DistKey* keys = D.keys + (u64)s * D.key_stride;
+        const u64* tb = D.tile_base + (u64)s * D.tile_stride;
+        for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < D.n_keys[s]; i += (u64)gridDim.x * blockDim.x) {
+            const DistKey d = keys[i];
+            const u64 tile = d.order >> 12;
+            const u64 rec = D.rec_base[s] + (tb[tile] >> 32) + ((d.order >> 2) & 1023u);
+            table_probe(P, d.k0, d.k1, (rec << 2) | (d.order & 3u), claimed);
+        }
+    }
+    if (claimed) atomicAdd(&P.cnt->n_keys, claimed);
+}
+
+// global table: order already is the bit index
+__global__ void __launch_bounds__(256) k_dist_mark(const TKey* __restrict__ tkeys, const u64* __restrict__ tfirst, u32 cap, u32* __restrict__ bitmap)
+{
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+        const TKey k = tkeys[i];
+        if (k.x == 0 && k.y == 0) continue;
+        const u64 bit = ~tfirst[i];
+        atomicOr(&bitmap[bit >> 5], 1u << (bit & 31));
+    }
+}
+
+__global__ void __launch_bounds__(256) k_dist_assign(const TKey* __restrict__ tkeys, const u64* __restrict__ tfirst, u32 cap,
+                                                      const u32* __restrict__ bitmap, const u32* __restrict__ wprefix,
+                                                      u32* __restrict__ slot_id, u32* __restrict__ id2slot, u32* __restrict__ name_len)
+{
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+        const TKey k = tkeys[i];
+        if (k.x == 0 && k.y == 0) continue;
+        const u64 ob = ~tfirst[i];
+        const u32 wd = (u32)(ob >> 5), bit = (u32)(ob & 31);
+        const u32 id = wprefix[wd] + __popc(bitmap[wd] & ((1u << bit) - 1u));
+        slot_id[i] = id;
+        id2slot[id] = i;
+        name_len[id] = slot_key_len(k.y);
+    }
+}
+
+// local slot -> global node ID (lookup of the local key in the global table; it is always present)
+__global__ void __launch_bounds__(256) k_dist_localmap(const TKey* __restrict__ ltkeys, u32 lcap, const TKey* __restrict__ gtkeys, u32 gmask,
+                                                        const u32* __restrict__ gslot_id, u32* __restrict__ lslot_id)
+{
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < lcap; i += gridDim.x * blockDim.x) {
+        const TKey k = ltkeys[i];
+        if (k.x == 0 && k.y == 0) continue;
+        u32 j = ((u32)mix64(k.x ^ (k.y * 0x9e3779b97f4a7c15ULL)) & gmask) & ~(u32)(TB_SLOTS - 1);
+        u32 found = 0xFFFFFFFFu;
+        for (u32 probes = 0; probes <= gmask; probes += TB_SLOTS) {
+            const TKey a = gtkeys[j], b = gtkeys[j + 1];
+            if (a.x == k.x && a.y == k.y) { found = j; break; }
+            if (b.x == k.x && b.y == k.y) { found = j + 1; break; }
+            if ((a.x == 0 && a.y == 0) || (b.x == 0 && b.y == 0)) break;
+            j = (j + TB_SLOTS) & gmask;
+        }
+        lslot_id[i] = found == 0xFFFFFFFFu ? 0xFFFFFFFFu : gslot_id[found];
+    }
+}
+
+// ---------------------------------------------------------------- phase 3
+struct DistPair {
+    u64 entry;  // minor << 33 | dir << 32 | global emission index of the triplet
+    u64 major;
+};
+
+__global__ void __launch_bounds__(256) k_dist_dest_count(const EmitParams E, int sym, int csc, u32 rows_per, u32* __restrict__ dest_cnt)
+{
+    __shared__ u32 s_cnt[8];
+    if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for_each_edge(E, [&](u32, u32 t0, const u32 (&id)[4]) {
+        record_entries(id, E.tpe, t0, sym, csc, [&](u32 major, u32, u32, u32) { atomicAdd(&s_cnt[major / rows_per], 1u); });
+    });
+    __syncthreads();
+    if (threadIdx.x < 8 && s_cnt[threadIdx.x]) atomicAdd(&dest_cnt[threadIdx.x], s_cnt[threadIdx.x]);
+}
+
+// dest_off[d] = first send-buffer index of destination d; dest_cur[d] counts entries written so far
+__global__ void __launch_bounds__(256) k_dist_dest_scatter(const EmitParams E, int sym, int csc, u32 rows_per, u32 t_base,
+                                                            const u32* __restrict__ dest_off, u32* __restrict__ dest_cur,
+                                                            DistPair* __restrict__ send)
+{
+    for_each_edge(E, [&](u32, u32 t0, const u32 (&id)[4]) {
+        record_entries(id, E.tpe, t0, sym, csc, [&](u32 major, u32 minor, u32 dir, u32 t) {
+            const u32 d = major / rows_per;
+            const u32 k = atomicAdd(&dest_cur[d], 1u);
+            DistPair p;
+            p.entry = rs_entry(minor, dir, t_base + t);
+            p.major = major;
+            send[dest_off[d] + k] = p;
+        });
+    });
+}
+
+__global__ void __launch_bounds__(256) k_pairs_count(const DistPair* __restrict__ pairs, u64 n, u32 row0, u32* __restrict__ cnt)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+        atomicAdd(&cnt[(u32)pairs[i].major - row0], 1u);
+}
+
+__global__ void __launch_bounds__(256) k_pairs_scatter(const DistPair* __restrict__ pairs, u64 n, u32 row0, const u32* __restrict__ rowptr,
+                                                        u32* __restrict__ cnt, u64* __restrict__ entries)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const DistPair p = pairs[i];
+        const u32 major = (u32)p.major - row0;
+        const u32 k = atomicSub(&cnt[major], 1u) - 1u;
+        entries[rowptr[major] + k] = p.entry;
+    }
+}
+
+}  // namespace g2n

@@ -13,7 +13,7 @@
 #include <vector>
 
 #include "../../include/g2n.h"
-#include "rowsort.cuh"
+#include "dist.cuh"
 
 using namespace g2n;
 
@@ -73,7 +73,12 @@ struct g2n_handle {
     u64 nbytes = 0;
     bool built = false;
     bool have_edges = false;
-    u64 n_nodes = 0, nnz = 0, names_bytes = 0, n_edges = 0, n_triplets = 0;
+    u64 n_nodes = 0, nnz = 0, names_bytes = 0, n_edges = 0, n_triplets = 0, n_records = 0, n_long = 0;
+    // multi-GPU state
+    bool slab_mode = false;
+    u64 slab_rows = 0, n_global = 0;
+    u32 gcap = 0;
+    DevBuf gtable, gfirst, gslot_id, dest_cnt;
     u32 table_cap = 0;
     u32 n_tiles = 0;
     int tpe = 1, spe = 2;
@@ -447,7 +452,8 @@ int g2n_status(g2n_handle* h, g2n_diag* out)
     return G2N_OK;
 }
 
-int g2n_build(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n_params* p)
+// Phase 1 of every build: text -> hash table (min order per key), tile_info / tile_base, edge_slots.
+static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n_params* p)
 {
     if (!h || !p || (!text && nbytes)) return G2N_ERR_INVALID;
     h->err.clear();
@@ -612,7 +618,15 @@ int g2n_build(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n_par
     if (n > 0x7FFFFFFFull) { h->err = "more than 2^31-1 nodes (int64 indices) is out of scope"; return G2N_ERR_UNSUPPORTED; }
     h->n_nodes = n;
     h->n_edges = E;
-    // ---- K2: node IDs
+    h->n_records = R;
+    h->n_long = hc.n_long;
+    return G2N_OK;
+}
+
+// Phase 2 on one GPU: first-appearance ranking -> node IDs (slot_id, id2slot, name lengths / offsets).
+static int ids_phase(g2n_handle* h)
+{
+    const u64 n = h->n_nodes, R = h->n_records;
     const u32 cap = h->table_cap;
     const u64 words = (4 * R + 31) / 32 + 1;
     CK(h->bitmap.ensure(words * sizeof(u32)));
@@ -640,8 +654,17 @@ int g2n_build(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n_par
     }
     CK(cudaEventRecord(h->ev[EV_IDS], h->stream));
     h->have_edges = true;
+    return G2N_OK;
+}
+
+int g2n_build(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n_params* p)
+{
+    int rc = tokenize_phase(h, text, nbytes, p);
+    if (rc) return rc;
+    h->slab_mode = false;
+    rc = ids_phase(h);
+    if (rc) return rc;
     // ---- K3 + K4
-    int rc;
     if (h->symmax) rc = build_compressed(h, p->want_format == G2N_FMT_CSC ? G2N_FMT_CSC : G2N_FMT_CSR);
     else if (p->want_format == G2N_FMT_NATIVE) rc = build_coo(h);
     else rc = build_compressed(h, p->want_format);
@@ -673,13 +696,14 @@ int g2n_convert(g2n_handle* h, int32_t want_format)
 int g2n_sizes(g2n_handle* h, g2n_sizes_t* out)
 {
     if (!h || !out || !h->built) return G2N_ERR_INVALID;
-    out->n_nodes = h->n_nodes;
+    out->n_nodes = h->n_nodes;  /* in slab mode: nodes of the whole graph (= number of columns) */
     out->nnz = h->nnz;
     out->names_bytes = h->names_bytes;
     out->format = h->result_format;
     out->index_bytes = 4;
     out->dtype = h->params.dtype;
     out->reserved = 0;
+    out->slab_rows = h->slab_mode ? h->slab_rows : h->n_nodes;
     return G2N_OK;
 }
 
@@ -705,7 +729,8 @@ int g2n_fetch_matrix(g2n_handle* h, void* a0, void* a1, void* data)
             CK(cudaMemcpyAsync(data, h->data.p, h->nnz * ds, cudaMemcpyDeviceToHost, h->stream));
         }
     } else {
-        CK(cudaMemcpyAsync(a0, h->indptr.p, (h->n_nodes + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        const u64 rows = h->slab_mode ? h->slab_rows : h->n_nodes;
+        CK(cudaMemcpyAsync(a0, h->indptr.p, (rows + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
         if (h->nnz) {
             CK(cudaMemcpyAsync(a1, h->indices.p, h->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
             CK(cudaMemcpyAsync(data, h->data.p, h->nnz * ds, cudaMemcpyDeviceToHost, h->stream));
@@ -722,7 +747,7 @@ int g2n_fetch_names(g2n_handle* h, uint8_t* names, uint64_t* offsets)
     if (!h->names_ready) {
         CK(h->names.ensure(h->names_bytes + 16));
         if (h->n_nodes > 0) {
-            { KScope ks(h, "k_gather_names"); k_gather_names<<<grid_for(h->n_nodes, 256), 256, 0, h->stream>>>(h->table.as<TKey>(), h->trep.as<u32>(), h->id2slot.as<u32>(), h->name_off.as<u64>(),
+            { KScope ks(h, "k_gather_names"); k_gather_names<<<grid_for(h->n_nodes, 256), 256, 0, h->stream>>>(h->slab_mode ? h->gtable.as<TKey>() : h->table.as<TKey>(), h->trep.as<u32>(), h->id2slot.as<u32>(), h->name_off.as<u64>(),
                                                                               (u32)h->n_nodes, h->d_text, h->longs.as<LongDesc>(),
                                                                               h->names.as<uint8_t>()); }
             CK(cudaGetLastError());
@@ -782,6 +807,196 @@ int g2n_coo_to_compressed(g2n_handle* h, const int32_t* row, const int32_t* col,
         CK(cudaMemcpyAsync(data_out, h->data.p, nnz * ds, cudaMemcpyDeviceToHost, h->stream));
     }
     CK(cudaStreamSynchronize(h->stream));
+    return G2N_OK;
+}
+
+// =====================================================================================
+// multi-GPU phases.  One handle per rank; the caller moves the buffers between ranks.
+
+int g2n_dist_scan(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n_params* p, g2n_dist_info* out)
+{
+    if (!out) return G2N_ERR_INVALID;
+    if (p && p->weight_tag && p->weight_tag_len > 0) { if (h) h->err = "multi-GPU builds are unweighted in this version"; return G2N_ERR_UNSUPPORTED; }
+    int rc = tokenize_phase(h, text, nbytes, p);
+    if (rc) return rc;
+    if (h->n_long) { h->err = "multi-GPU builds need node names of <= 15 bytes (13 with --bidirected) in this version"; return G2N_ERR_UNSUPPORTED; }
+    out->n_keys = h->n_nodes;
+    out->n_tiles = h->n_tiles;
+    out->n_records = h->n_records;
+    out->n_edge_records = h->n_edges;
+    out->n_entries = h->n_edges * (u64)h->tpe * (h->symmax ? 2 : 1);
+    out->reserved = 0;
+    return G2N_OK;
+}
+
+int g2n_dist_export(g2n_handle* h, void* dev_keys, void* dev_tile_base)
+{
+    if (!h || !dev_tile_base || (!dev_keys && h->n_nodes)) return G2N_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(h->dest_cnt.ensure(64 * sizeof(u32)));
+    CK(cudaMemsetAsync(h->dest_cnt.p, 0, 64 * sizeof(u32), h->stream));
+    if (h->n_nodes) {
+        KScope ks(h, "k_dist_export");
+        k_dist_export<<<grid_for(h->table_cap, 256), 256, 0, h->stream>>>(h->table.as<TKey>(), h->tfirst.as<u64>(), h->table_cap, (DistKey*)dev_keys, h->dest_cnt.as<u32>());
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(dev_tile_base, h->tile_base.p, ((size_t)h->n_tiles + 1) * sizeof(u64), cudaMemcpyDeviceToDevice, h->stream));
+    return G2N_OK;
+}
+
+int g2n_dist_merge(g2n_handle* h, const void* dev_keys_all, uint64_t key_stride, const uint64_t* n_keys, const void* dev_tile_base_all,
+                   uint64_t tile_stride, const uint64_t* rec_base, uint64_t total_records, int world, uint64_t* n_global_out)
+{
+    if (!h || !n_keys || !rec_base || !n_global_out || world < 1 || world > 8) return G2N_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    u64 total_keys = 0;
+    for (int s = 0; s < world; s++) total_keys += n_keys[s];
+    if (total_records >= (1ull << 30) - 1) { h->err = "more than 2^30 records across all ranks"; return G2N_ERR_UNSUPPORTED; }
+    const u64 want_slots = total_keys + total_keys / 2 + 64;
+    const u32 gcap = next_pow2(want_slots < 1024 ? 1024 : want_slots);
+    h->gcap = gcap;
+    CK(h->gtable.ensure((size_t)gcap * sizeof(TKey)));
+    CK(h->gfirst.ensure((size_t)gcap * sizeof(u64)));
+    CK(h->gslot_id.ensure((size_t)gcap * sizeof(u32)));
+    CK(cudaMemsetAsync(h->gtable.p, 0, (size_t)gcap * sizeof(TKey), h->stream));
+    CK(cudaMemsetAsync(h->gfirst.p, 0, (size_t)gcap * sizeof(u64), h->stream));
+    Counters& hc = *h->h_cnt;
+    memset(&hc, 0, sizeof(hc));
+    hc.first_error = ~0ull;
+    hc.first_unknown = ~0ull;
+    CK(cudaMemcpyAsync(h->cnt.p, &hc, sizeof(Counters), cudaMemcpyHostToDevice, h->stream));
+    ScanParams P;
+    memset(&P, 0, sizeof(P));
+    P.tkeys = h->gtable.as<TKey>();
+    P.tfirst = h->gfirst.as<u64>();
+    P.table_mask = gcap - 1;
+    P.cnt = h->cnt.as<Counters>();
+    DistMergeParams D;
+    memset(&D, 0, sizeof(D));
+    D.keys = (const DistKey*)dev_keys_all;
+    D.tile_base = (const u64*)dev_tile_base_all;
+    D.key_stride = key_stride;
+    D.tile_stride = tile_stride;
+    D.world = world;
+    for (int s = 0; s < world; s++) { D.n_keys[s] = n_keys[s]; D.rec_base[s] = rec_base[s]; }
+    if (total_keys) {
+        KScope ks(h, "k_dist_insert");
+        k_dist_insert<<<grid_for(total_keys / world + 1, 256), 256, 0, h->stream>>>(P, D);
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&hc, h->cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (hc.flags & CF_TABLE_FULL) { h->err = "global table overflow"; return G2N_ERR_INTERNAL; }
+    const u64 n = hc.n_keys;
+    if (n > 0x7FFFFFFFull) { h->err = "more than 2^31-1 nodes (int64 indices) is out of scope"; return G2N_ERR_UNSUPPORTED; }
+    h->n_global = n;
+    *n_global_out = n;
+    // global IDs: same bitmap ranking, the order already is the bit index
+    const u64 words = (4 * total_records + 31) / 32 + 1;
+    CK(h->bitmap.ensure(words * sizeof(u32)));
+    CK(h->wprefix.ensure((words + 2) * sizeof(u32)));
+    CK(h->id2slot.ensure((n + 1) * sizeof(u32)));
+    CK(h->name_len.ensure((n + 1) * sizeof(u32)));
+    CK(h->name_off.ensure((n + 2) * sizeof(u64)));
+    CK(h->slot_id.ensure((size_t)h->table_cap * sizeof(u32)));
+    if (n > 0) {
+        CK(cudaMemsetAsync(h->bitmap.p, 0, words * sizeof(u32), h->stream));
+        { KScope ks(h, "k_dist_mark"); k_dist_mark<<<grid_for(gcap, 256), 256, 0, h->stream>>>(h->gtable.as<TKey>(), h->gfirst.as<u64>(), gcap, h->bitmap.as<u32>()); }
+        LoadPopc lp{h->bitmap.as<u32>()};
+        int rc = launch_scan<u32>(h, lp, h->wprefix.as<u32>(), words);
+        if (rc) return rc;
+        { KScope ks(h, "k_dist_assign"); k_dist_assign<<<grid_for(gcap, 256), 256, 0, h->stream>>>(h->gtable.as<TKey>(), h->gfirst.as<u64>(), gcap, h->bitmap.as<u32>(), h->wprefix.as<u32>(), h->gslot_id.as<u32>(), h->id2slot.as<u32>(), h->name_len.as<u32>()); }
+        LoadArray<u32> ln{h->name_len.as<u32>()};
+        rc = launch_scan<u64>(h, ln, (u64*)h->name_off.as<u64>(), n);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(&h->h_tail[1], h->name_off.as<u64>() + n, sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
+        { KScope ks(h, "k_dist_localmap"); k_dist_localmap<<<grid_for(h->table_cap, 256), 256, 0, h->stream>>>(h->table.as<TKey>(), h->table_cap, h->gtable.as<TKey>(), gcap - 1, h->gslot_id.as<u32>(), h->slot_id.as<u32>()); }
+        CK(cudaGetLastError());
+    } else {
+        CK(cudaMemsetAsync(h->name_off.p, 0, 2 * sizeof(u64), h->stream));
+        h->h_tail[1] = 0;
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    h->names_bytes = h->h_tail[1];
+    h->have_edges = true;
+    h->edges_are_ids = false;
+    return G2N_OK;
+}
+
+int g2n_dist_entries(g2n_handle* h, int world, uint64_t rows_per_rank, uint64_t edge_base, void* dev_send, uint64_t send_cap,
+                     uint64_t* dest_counts)
+{
+    if (!h || !dest_counts || world < 1 || world > 8 || rows_per_rank == 0) return G2N_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    const int sym = h->symmax ? 1 : 0;
+    const u64 triplet_base = edge_base * (u64)h->tpe;  // emission index of this rank's first triplet
+    const u64 M = h->n_edges * (u64)h->tpe * (sym ? 2 : 1);
+    if (M > send_cap) { h->err = "send buffer too small"; return G2N_ERR_INVALID; }
+    if (triplet_base + h->n_edges * (u64)h->tpe >= 0xFFFFFFF0ull) { h->err = "more than 2^32 triplets across all ranks"; return G2N_ERR_UNSUPPORTED; }
+    const int csc = (!sym && h->params.want_format == G2N_FMT_CSC) ? 1 : 0;
+    CK(h->dest_cnt.ensure(64 * sizeof(u32)));
+    u32* cnt = h->dest_cnt.as<u32>();
+    CK(cudaMemsetAsync(cnt, 0, 64 * sizeof(u32), h->stream));
+    EmitParams E = emit_params(h);
+    E.write_ids = 1;
+    const u32 egrid = grid_for((u64)h->n_tiles * 32, 256);
+    if (M) {
+        { KScope ks(h, "k_dist_dest_count"); k_dist_dest_count<<<egrid, 256, 0, h->stream>>>(E, sym, csc, (u32)rows_per_rank, cnt); }
+        CK(cudaGetLastError());
+        h->edges_are_ids = true;
+        E.ids_ready = 1;
+        E.write_ids = 0;
+    }
+    u32 hcnt[8];
+    CK(cudaMemcpyAsync(hcnt, cnt, 8 * sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    u32 off[8];
+    u32 run = 0;
+    for (int d = 0; d < 8; d++) { off[d] = run; run += d < world ? hcnt[d] : 0; }
+    for (int d = 0; d < world; d++) dest_counts[d] = hcnt[d];
+    if (M) {
+        CK(cudaMemcpyAsync(cnt + 16, off, 8 * sizeof(u32), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemsetAsync(cnt + 32, 0, 8 * sizeof(u32), h->stream));
+        { KScope ks(h, "k_dist_dest_scatter"); k_dist_dest_scatter<<<egrid, 256, 0, h->stream>>>(E, sym, csc, (u32)rows_per_rank, (u32)triplet_base, cnt + 16, cnt + 32, (DistPair*)dev_send); }
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return G2N_OK;
+}
+
+int g2n_dist_slab(g2n_handle* h, const void* dev_pairs, uint64_t n_pairs, uint64_t row0, uint64_t n_rows)
+{
+    if (!h || (!dev_pairs && n_pairs)) return G2N_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    const int sym = h->symmax ? 1 : 0;
+    h->slab_mode = true;
+    h->slab_rows = n_rows;
+    h->n_nodes = h->n_global;
+    h->result_format = (!sym && h->params.want_format == G2N_FMT_CSC) ? G2N_FMT_CSC : G2N_FMT_CSR;
+    if (n_pairs >= 0xFFFFFFF0ull) { h->err = "more than 2^32 entries in one slab"; return G2N_ERR_UNSUPPORTED; }
+    CK(h->rowcnt.ensure((n_rows + 2) * sizeof(u32)));
+    CK(h->rowptr.ensure((n_rows + 2) * sizeof(u32)));
+    CK(h->entries.ensure((n_pairs + 1) * sizeof(u64)));
+    CK(cudaMemsetAsync(h->rowcnt.p, 0, (n_rows + 2) * sizeof(u32), h->stream));
+    if (n_pairs) {
+        KScope ks(h, "k_pairs_count");
+        k_pairs_count<<<grid_for(n_pairs, 256), 256, 0, h->stream>>>((const DistPair*)dev_pairs, n_pairs, (u32)row0, h->rowcnt.as<u32>());
+    }
+    CK(cudaGetLastError());
+    LoadArray<u32> ldc{h->rowcnt.as<u32>()};
+    int rc = launch_scan<u32>(h, ldc, h->rowptr.as<u32>(), n_rows);
+    if (rc) return rc;
+    if (n_pairs) {
+        KScope ks(h, "k_pairs_scatter");
+        k_pairs_scatter<<<grid_for(n_pairs, 256), 256, 0, h->stream>>>((const DistPair*)dev_pairs, n_pairs, (u32)row0, h->rowptr.as<u32>(), h->rowcnt.as<u32>(), h->entries.as<u64>());
+    }
+    CK(cudaGetLastError());
+    rc = rows_finalize(h, h->params.dtype, n_pairs, n_rows, sym, nullptr, nullptr);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    h->nnz = (u64)(u32)h->h_tail[3];
+    h->nnz_in_tail3 = false;
+    h->built = true;
     return G2N_OK;
 }
 

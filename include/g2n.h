@@ -87,6 +87,7 @@ typedef struct g2n_sizes_t {
     int32_t index_bytes;   /* 4 (SciPy picks int32 below 2^31-1; larger is G2N_ERR_UNSUPPORTED) */
     int32_t dtype;         /* G2N_DTYPE_* of the data array */
     int32_t reserved;
+    uint64_t slab_rows;    /* rows held by this handle (== n_nodes except for a multi-GPU slab) */
 } g2n_sizes_t;
 
 typedef struct g2n_diag {
@@ -166,6 +167,41 @@ int g2n_abi_version(void);
 int g2n_coo_to_compressed(g2n_handle *h, const int32_t *row, const int32_t *col, const void *data,
                           uint64_t nnz_in, uint64_t n, int32_t dtype, int32_t want_format,
                           int32_t *indptr, int32_t *indices, void *data_out, uint64_t *nnz_out);
+
+/* ---- multi-GPU phases -----------------------------------------------------
+ * One process and one handle per GPU.  The library does the device work of each phase; the caller
+ * moves the exchange buffers between ranks (gfa2network_b200/dist.py uses torch.distributed / NCCL):
+ *   g2n_dist_scan     tokenize this rank's byte range (parser.py:114-361, builders.py:190-234 locally)
+ *   g2n_dist_export   distinct local node keys + first local appearance, and the per-tile record prefix
+ *   (all-gather)
+ *   g2n_dist_merge    global dictionary: every rank derives the same global node IDs (the reference's
+ *                     first-appearance numbering over the concatenated shards) and maps its edges to them
+ *   g2n_dist_entries  row entries bucketed by owner rank (row block = rows_per_rank consecutive IDs)
+ *   (all-to-all)
+ *   g2n_dist_slab     duplicate sum / max(S, S^T) for the rows this rank owns -> CSR slab
+ *                     (builders.py:279-283, utils.py:55); fetch with g2n_sizes / g2n_fetch_matrix
+ * Restrictions of this version: unweighted builds, node names of <= 15 bytes, <= 8 ranks. */
+typedef struct g2n_dist_info {
+    uint64_t n_keys;         /* distinct node keys in this shard */
+    uint64_t n_tiles;
+    uint64_t n_records;
+    uint64_t n_edge_records;
+    uint64_t n_entries;      /* row entries this rank will send (triplets, x2 in the max(S,S^T) mode) */
+    uint64_t reserved;
+} g2n_dist_info;
+
+int g2n_dist_scan(g2n_handle *h, const uint8_t *text, uint64_t nbytes, const g2n_params *p, g2n_dist_info *out);
+/* dev_keys: n_keys x 32 bytes {key[16], order u64, pad u64}; dev_tile_base: (n_tiles + 1) x u64 */
+int g2n_dist_export(g2n_handle *h, void *dev_keys, void *dev_tile_base);
+/* dev_keys_all / dev_tile_base_all: `world` blocks of key_stride / tile_stride elements (rank order) */
+int g2n_dist_merge(g2n_handle *h, const void *dev_keys_all, uint64_t key_stride, const uint64_t *n_keys,
+                   const void *dev_tile_base_all, uint64_t tile_stride, const uint64_t *rec_base,
+                   uint64_t total_records, int world, uint64_t *n_global_out);
+/* edge_base: edge records of all lower ranks (keeps emission order global);
+ * dev_send: n_entries x 16 bytes {entry u64, row u64}, grouped by destination; dest_counts[world] out */
+int g2n_dist_entries(g2n_handle *h, int world, uint64_t rows_per_rank, uint64_t edge_base, void *dev_send,
+                     uint64_t send_cap, uint64_t *dest_counts);
+int g2n_dist_slab(g2n_handle *h, const void *dev_pairs, uint64_t n_pairs, uint64_t row0, uint64_t n_rows);
 
 #ifdef __cplusplus
 }

@@ -30,7 +30,8 @@ def test_struct_layouts_match_header():
     from gfa2network_b200 import _capi
 
     assert ctypes.sizeof(_capi.Params) == 48
-    assert ctypes.sizeof(_capi.Sizes) == 40
+    assert ctypes.sizeof(_capi.Sizes) == 48
+    assert ctypes.sizeof(_capi.DistInfo) == 48
     assert ctypes.sizeof(_capi.Diag) == 112
 
 
