@@ -31,6 +31,9 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 HBM_FALLBACK_GBS = 6650.0  # B200_PROFILING.md fallback, used only if MEASURED_PEAKS.json is absent
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+# (profiles/*.md name the capture each figure comes from); null where no capture exists yet
+TRAFFIC = {"k_tokenize": 209_834_496}
 
 
 def peaks():
@@ -40,14 +43,19 @@ def peaks():
     return HBM_FALLBACK_GBS, "fallback"
 
 
-def make_text(cfg_name: str, scale: float = 1.0, out=None, seed_shift: int = 0, id_base: int = 0):
+def make_text(cfg_name: str, scale: float = 1.0, out=None, rank: int = 0, world: int = 1):
+    """Rank `rank`'s shard of the workload: the named configuration per GPU (weak scaling).  With
+    world > 1 the shards form ONE graph: rank r holds segments [r*n_seg, (r+1)*n_seg) and its links; the
+    10 % "uniform" link targets are drawn over all ranks' segments, so dictionary merge and edge
+    exchange are exercised."""
     from gfa2network_b200.synth import CONFIGS, synth_gfa
 
     cfg = CONFIGS[cfg_name]
     n_seg = max(2, int(cfg["n_seg"] * scale))
     n_link = max(1, int(cfg["n_link"] * scale))
-    text = synth_gfa(n_seg, n_link, seed=cfg["seed"] + seed_shift, kind=cfg["kind"], seq_mean=cfg.get("seq_mean", 0),
-                     n_paths=cfg.get("n_paths", 0), n_walks=cfg.get("n_walks", 0), out=out, id_base=id_base)
+    text = synth_gfa(n_seg, n_link, seed=cfg["seed"] + 1000 * rank, kind=cfg["kind"], seq_mean=cfg.get("seq_mean", 0),
+                     n_paths=cfg.get("n_paths", 0), n_walks=cfg.get("n_walks", 0), out=out, id_base=rank * n_seg,
+                     uniform_range=(0, world * n_seg) if world > 1 else (0, 0), header=(rank == 0))
     return cfg, text, n_seg, n_link
 
 
@@ -138,20 +146,23 @@ def workload_name(cfg_name, scale, n_seg, n_link, cfg):
     return f"{cfg_name} synthetic {kind}: {n_seg} segments / {n_link} links, {mode}, {cfg['fmt'].upper()}" + ("" if scale == 1.0 else f" (scale {scale})")
 
 
-# algorithmic bytes per launch of each kernel: compulsory reads + writes only (DESIGN.md section 5)
-def algo_bytes(name, launches, st):
-    N, E, spe, M, n, cap, words, nnz, weighted = (st[k] for k in ("N", "E", "spe", "M", "n", "cap", "words", "nnz", "weighted"))
-    keyb = 8 + (4 if weighted else 0)
+# algorithmic bytes per launch of each kernel: compulsory reads + writes only (DESIGN.md section 4)
+def algo_bytes(name, st):
+    N, E, spe, M, n, nnz, weighted, world = (st[k] for k in ("N", "E", "spe", "M", "n", "nnz", "weighted", "world"))
     table = {
         "k_tokenize": N + 4 * spe * E + (8 * E if weighted else 0),
-        "k_radix_hist": 8 * M,
-        "k_radix_scatter": 2 * keyb * M,
-        "k_emit_keys": 4 * spe * E + keyb * M,
-        "k_group_reduce": keyb * M + 4 * M + 8 * nnz,
-        "k_compact": 8 * M + 8 * M + 12 * nnz,
-        "k_mark_first": 32 * cap,
-        "k_assign_ids": 32 * cap + 12 * n,
-        "k_scan_exclusive": None,
+        "k_mark_first": 24 * 2 * n,
+        "k_assign_ids": 24 * 2 * n + 12 * n,
+        "k_rows_count": 2 * 4 * spe * E + 4 * M + (16 * E if weighted else 0),
+        "k_rows_scatter": 4 * spe * E + 12 * M,
+        "k_rows_sort": 16 * M + 4 * n,
+        "k_rows_write": 8 * M + 12 * nnz + 8 * n,
+        "k_emit_coo": 4 * spe * E + 16 * M,
+        "k_dist_insert": 32 * n,            # n = global nodes: every rank inserts every rank's distinct keys
+        "k_dist_dest_count": 2 * 4 * spe * E,
+        "k_dist_dest_scatter": 4 * spe * E + 16 * M,
+        "k_pairs_count": 16 * M,
+        "k_pairs_scatter": 24 * M,
     }
     return table.get(name)
 
@@ -170,19 +181,28 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
-    # weak scaling: every rank parses + builds its own shard of the same shape
-    cfg, text_np, n_seg, n_link = make_text(args.config, args.scale, seed_shift=rank)
+    # weak scaling: every rank holds one shard of the configuration's shape
+    cfg, text_np, n_seg, n_link = make_text(args.config, args.scale, rank=rank, world=world)
     nbytes = int(text_np.size)
     pinned = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
     pinned.numpy()[:] = text_np
     text_dev = pinned.to(dev, non_blocking=True)
     torch.cuda.synchronize()
 
-    h = _capi.Handle(local)
     stream = torch.cuda.current_stream()
-    h.set_stream(stream.cuda_stream)
-    h.set_profile(True)
     mode = cfg["mode"]
+    builder = None
+    if world > 1:
+        from gfa2network_b200.dist import DistBuilder
+
+        if mode.get("weight_tag"):
+            raise SystemExit("multi-GPU bench: weighted configurations are not supported yet")
+        builder = DistBuilder(local)
+        h = builder.local.h
+    else:
+        h = _capi.Handle(local)
+        h.set_stream(stream.cuda_stream)
+    h.set_profile(True)
     want = {"csr": _capi.FMT_CSR, "csc": _capi.FMT_CSC, "coo": _capi.FMT_NATIVE}[cfg["fmt"]]
     wt = mode.get("weight_tag")
     wtb = wt.encode() if wt else None
@@ -190,9 +210,14 @@ def run_ours(args):
                           int(mode.get("asymmetric", False)), 0, _capi.DTYPES["float64"], want, 1, wtb, len(wtb) if wtb else 0, 0)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
+    dmode = {k: v for k, v in mode.items() if k != "weight_tag"}
+    state = {}
+
     def step():
-        rc = h.build(text_dev.data_ptr(), nbytes, params)
-        h.check(rc)
+        if builder is not None:
+            state["res"] = builder.build(text_dev, matrix_format=cfg["fmt"] if cfg["fmt"] != "coo" else "csr", **dmode)
+        else:
+            h.check(h.build(text_dev.data_ptr(), nbytes, params))
 
     for _ in range(max(args.warmup, 3)):
         flush.zero_()
@@ -230,16 +255,34 @@ def run_ours(args):
     ms_step = total_ms / args.steps
     diag = h.status()
     sz = h.sizes()
+    n_edges_rank = int(diag.n_edge_records)
 
     # ---- e2e through the public API: pinned host text in, host CSR arrays out
     fmt = cfg["fmt"]
     e2e_steps = max(2, min(args.steps, 5))
     host_in = pinned.numpy()
-    parse_gfa(host_in, build_graph=False, build_matrix=True, matrix_format=fmt, device=local, **mode)  # warm the default handle
+    if builder is None:
+        def e2e_call():
+            return parse_gfa(host_in, build_graph=False, build_matrix=True, matrix_format=fmt, device=local, **mode)
+    else:
+        class _Slab:  # the public multi-GPU call: DistBuilder.build on this rank's shard + fetch of its CSR slab
+            pass
+
+        def e2e_call():
+            dev_text = pinned.to(dev, non_blocking=True)
+            builder.build(dev_text, matrix_format=fmt if fmt != "coo" else "csr", **dmode)
+            ip, ix, dt = builder.fetch_slab()
+            o = _Slab()
+            o.format, o.indptr, o.indices, o.data = "csr", ip, ix, dt
+            return o
+    e2e_call()  # warm
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        A = parse_gfa(host_in, build_graph=False, build_matrix=True, matrix_format=fmt, device=local, **mode)
+        A = e2e_call()
+    torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
@@ -256,26 +299,33 @@ def run_ours(args):
         return
     # ---- roofline of the dominant kernel
     peak, peak_src = peaks()
-    M = int(diag.n_triplets) * (2 if (params.directed and not params.bidirected and not params.asymmetric) or
-                                   (params.bidirected and params.keep_directed_bidir and not params.asymmetric) else 1)
-    st = dict(N=nbytes, E=int(diag.n_edge_records), spe=4 if (params.bidirected and not params.keep_directed_bidir) else 2, M=M,
-              n=int(sz.n_nodes), cap=0, words=0, nnz=int(sz.nnz), weighted=bool(wtb))
+    graph_directed = bool(params.keep_directed_bidir or (not params.bidirected and params.directed))
+    spe = 4 if (params.bidirected and not params.keep_directed_bidir) else 2
+    tpe = 1 if graph_directed else (4 if spe == 4 else 2)
+    E_rank = int(diag.n_edge_records)
+    M = E_rank * tpe * (2 if (graph_directed and not params.asymmetric) else 1)
+    st = dict(N=nbytes, E=E_rank, spe=spe, M=M, n=int(sz.n_nodes), nnz=int(sz.nnz), weighted=bool(wtb), world=world)
     kern = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in ktot.items()}
     dom = max(kern, key=lambda k: kern[k]["ms_per_step"]) if kern else None
     roof = None
     if dom:
         per_launch_ms = ktot[dom][0] / max(1, ktot[dom][1])
-        ab = algo_bytes(dom, ktot[dom][1], st)
+        ab = algo_bytes(dom, st)
         if ab:
             ach = ab / (per_launch_ms * 1e6)
             roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": None, "algorithmic_bytes_per_launch": ab, "ms_per_launch": per_launch_ms,
+                    "frac": ach / peak, "traffic": TRAFFIC.get(dom), "algorithmic_bytes_per_launch": ab, "ms_per_launch": per_launch_ms,
                     "share_of_step": kern[dom]["ms_per_step"] / ms_step}
     # whole-path algorithmic bytes: text in + CSR + node names out
     out_bytes = 4 * (sz.n_nodes + 1) + 12 * sz.nnz + sz.names_bytes + 8 * (sz.n_nodes + 1)
     path_ach = (nbytes + out_bytes) / (ms_step * 1e6)
-    # ---- CPU baseline on this host (bounded: one full pass of the same text)
-    cpu_dt, _B = cpu_oracle_run(text_np, mode, fmt)
+    # ---- CPU baseline on this host (rank 0, N=1 only; bounded: one full pass of the same text)
+    cpu_base = None
+    if world == 1:
+        cpu_dt, _B = cpu_oracle_run(text_np, mode, fmt)
+        cpu_base = {"value": nbytes / (cpu_dt * 1e9), "unit": "GB/s", "cores": 1, "kind": "port",
+                    "sample": f"full {args.config} text ({nbytes} B), 1 run: C port of parser.py/builders.py + SciPy tocsr/maximum",
+                    "host_cores_available": os.cpu_count()}
     gbs = world * nbytes / (ms_step * 1e6)
     line = {
         "metric": "gfa_to_csr_parse_build_GBps", "value": gbs, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
@@ -283,17 +333,18 @@ def run_ours(args):
         "dtype": "u8/int32/f64", "data": "synthetic",
         "config": {"workload": workload_name(args.config, args.scale, n_seg, n_link, cfg), "text_bytes_per_gpu": nbytes,
                    "l2": "flushed between steps (512 MiB write)", "nodes": int(sz.n_nodes), "nnz": int(sz.nnz),
-                   "sharding": "one shard of this shape per GPU, no exchange" if world > 1 else "single GPU"},
+                   "sharding": ("one shard of this shape per GPU; NCCL all-gather of the node dictionary, all-to-all of row entries "
+                                "by owner row block, per-GPU CSR slab") if world > 1 else "single GPU"},
         "edges_per_s": world * n_link / (ms_step / 1e3),
         "path_roofline": {"algorithmic_bytes": int(nbytes + out_bytes), "achieved": path_ach, "peak": peak, "frac": path_ach / peak, "unit": "GB/s"},
         "roofline": roof,
         "kernels": kern,
         "stage_ms": {k: float(diag.ms_stage[i]) for i, k in ((0, "tokenize+hash"), (1, "ids"), (3, "emit"), (4, "sort"), (5, "reduce"))},
-        "cpu_baseline": {"value": nbytes / (cpu_dt * 1e9), "unit": "GB/s", "cores": 1, "kind": "port",
-                         "sample": f"full {args.config} text ({nbytes} B), 1 run: C port of parser.py/builders.py + SciPy tocsr/maximum",
-                         "host_cores_available": os.cpu_count()},
+        "cpu_baseline": cpu_base,
         "e2e": {"value": world * nbytes / (e2e_s * 1e9), "unit": "GB/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": e2e_s * 1e3, "api": "gfa2network_b200.parse_gfa(pinned uint8 buffer, matrix_format=...)"},
+                "ms_per_step": e2e_s * 1e3,
+                "api": "gfa2network_b200.parse_gfa(pinned uint8 buffer, matrix_format=...)" if world == 1 else
+                       "gfa2network_b200.dist.DistBuilder.build(shard) + fetch_slab() per rank (bytes are per rank)"},
         "gpu_launches": launches,
         "clocks": clocks,
     }

@@ -448,6 +448,8 @@ const char* g2n_last_error(g2n_handle* h) { return h ? h->err.c_str() : "null ha
 int g2n_status(g2n_handle* h, g2n_diag* out)
 {
     if (!h || !out) return G2N_ERR_INVALID;
+    h->diag.gpu_launches = h->launches;
+    h->diag.n_triplets = h->n_edges * (u64)h->tpe;
     *out = h->diag;
     return G2N_OK;
 }

@@ -44,6 +44,8 @@ typedef struct {
     int32_t n_walks;       /* W lines walking all segments */
     int32_t interleave;    /* 0: all S then all L ; > 0: alternate blocks of this many S / 3x L lines */
     int32_t header;        /* 1: emit H line */
+    uint64_t uni_base, uni_n; /* id range of the 10 % "uniform" link targets (0,0: this shard's own segments);
+                                 lets the shards of a multi-GPU run reference each other's segments */
 } synth_params;
 
 /* upper bound of the bytes g2n_synth writes */
@@ -88,14 +90,14 @@ static uint8_t *emit_link(uint8_t *p, const synth_params *sp, const link_t *l)
 {
     const char of = (l->o & 1) ? '-' : '+', ot = (l->o & 2) ? '-' : '+';
     if (sp->kind == 1) {
-        *p++ = 'L'; *p++ = '\t'; *p++ = 's'; p = put_u64(p, sp->id_base + l->u);
-        *p++ = '\t'; *p++ = (uint8_t)of; *p++ = '\t'; *p++ = 's'; p = put_u64(p, sp->id_base + l->v);
+        *p++ = 'L'; *p++ = '\t'; *p++ = 's'; p = put_u64(p, l->u);
+        *p++ = '\t'; *p++ = (uint8_t)of; *p++ = '\t'; *p++ = 's'; p = put_u64(p, l->v);
         *p++ = '\t'; *p++ = (uint8_t)ot; *p++ = '\t'; *p++ = '0'; *p++ = 'M'; *p++ = '\n';
     } else {
         const uint64_t len = 10 + (l->k % 90);
-        *p++ = 'E'; *p++ = '\t'; *p++ = '*'; *p++ = '\t'; *p++ = 's'; p = put_u64(p, sp->id_base + l->u); *p++ = (uint8_t)of;
+        *p++ = 'E'; *p++ = '\t'; *p++ = '*'; *p++ = '\t'; *p++ = 's'; p = put_u64(p, l->u); *p++ = (uint8_t)of;
         *p++ = '\t'; *p++ = '0'; *p++ = '\t'; p = put_u64(p, len);
-        *p++ = '\t'; *p++ = 's'; p = put_u64(p, sp->id_base + l->v); *p++ = (uint8_t)ot;
+        *p++ = '\t'; *p++ = 's'; p = put_u64(p, l->v); *p++ = (uint8_t)ot;
         *p++ = '\t'; *p++ = '0'; *p++ = '\t'; p = put_u64(p, len); *p++ = '\t'; p = put_u64(p, len); *p++ = 'M';
         p = put_str(p, "\tRC:f:");
         /* k/8 for k in [1, 8000]: exactly representable, sums are order independent */
@@ -120,9 +122,9 @@ uint64_t g2n_synth(uint8_t *buf, uint64_t cap, const synth_params *sp)
         uint64_t r = sm64(&rng);
         if (j > 16 && (r % 100) == 0) { links[j] = links[sm64(&rng) % j]; continue; }
         link_t l;
-        l.u = (uint32_t)(sm64(&rng) % n);
-        if ((r >> 8) % 10 == 0) l.v = (uint32_t)(sm64(&rng) % n);
-        else { uint64_t v = l.u + 1 + ((r >> 16) % 8); l.v = (uint32_t)(v >= n ? n - 1 : v); }
+        l.u = (uint32_t)(sp->id_base + sm64(&rng) % n);
+        if ((r >> 8) % 10 == 0) l.v = (uint32_t)(sp->uni_n ? sp->uni_base + sm64(&rng) % sp->uni_n : sp->id_base + sm64(&rng) % n);
+        else { uint64_t v = l.u + 1 + ((r >> 16) % 8); l.v = (uint32_t)(v >= sp->id_base + n ? sp->id_base + n - 1 : v); }
         l.o = (uint8_t)((r >> 24) & 3);
         l.k = (uint16_t)(r >> 32);
         links[j] = l;

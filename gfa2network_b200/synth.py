@@ -18,7 +18,7 @@ LIB = PKG / "libg2nsynth.so"
 class _SP(C.Structure):
     _fields_ = [("n_seg", C.c_uint64), ("n_link", C.c_uint64), ("seed", C.c_uint64), ("id_base", C.c_uint64),
                 ("kind", C.c_int32), ("seq_mean", C.c_int32), ("n_paths", C.c_int32), ("n_walks", C.c_int32),
-                ("interleave", C.c_int32), ("header", C.c_int32)]
+                ("interleave", C.c_int32), ("header", C.c_int32), ("uni_base", C.c_uint64), ("uni_n", C.c_uint64)]
 
 
 def build(force: bool = False) -> Path:
@@ -43,10 +43,11 @@ def _load():
 
 
 def synth_gfa(n_seg: int, n_link: int, *, seed: int = 2, kind: int = 1, seq_mean: int = 0, n_paths: int = 0,
-              n_walks: int = 0, interleave: int = 0, header: bool = True, id_base: int = 0, out: np.ndarray | None = None) -> np.ndarray:
+              n_walks: int = 0, interleave: int = 0, header: bool = True, id_base: int = 0, uniform_range: tuple[int, int] = (0, 0),
+              out: np.ndarray | None = None) -> np.ndarray:
     """Returns a uint8 array holding the GFA text (a view into *out* when given)."""
     lib = _load()
-    sp = _SP(n_seg, n_link, seed, id_base, kind, seq_mean, n_paths, n_walks, interleave, int(header))
+    sp = _SP(n_seg, n_link, seed, id_base, kind, seq_mean, n_paths, n_walks, interleave, int(header), uniform_range[0], uniform_range[1])
     bound = int(lib.g2n_synth_bound(C.byref(sp)))
     buf = out if out is not None else np.empty(bound, dtype=np.uint8)
     if buf.size < bound:
