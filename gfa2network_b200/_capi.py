@@ -150,7 +150,8 @@ class Handle:
         raise G2NError(f"libg2n status {rc}: {msg}")
 
     def set_stream(self, stream_ptr: int | None):
-        self.check(self.lib.g2n_set_stream(self.h, C.c_void_p(stream_ptr or 0)))
+        """cudaStream_t as an integer (0 = the CUDA default stream); None = the handle's own stream."""
+        self.check(self.lib.g2n_set_stream(self.h, C.c_void_p(-1 if stream_ptr is None else stream_ptr)))
 
     def set_profile(self, on: bool):
         self.check(self.lib.g2n_set_profile(self.h, int(on)))

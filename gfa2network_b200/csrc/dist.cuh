@@ -125,21 +125,48 @@ __global__ void __launch_bounds__(256) k_dist_dest_count(const EmitParams E, int
     if (threadIdx.x < 8 && s_cnt[threadIdx.x]) atomicAdd(&dest_cnt[threadIdx.x], s_cnt[threadIdx.x]);
 }
 
-// dest_off[d] = first send-buffer index of destination d; dest_cur[d] counts entries written so far
-__global__ void __launch_bounds__(256) k_dist_dest_scatter(const EmitParams E, int sym, int csc, u32 rows_per, u32 t_base,
+// dest_off[d] = first send-buffer index of destination d; dest_cur[d] = entries reserved so far.
+// One warp per tile: count the tile's entries per destination in shared memory, reserve the ranges
+// with one global atomic per destination, then write (requires edge_slots to hold node IDs already).
+__global__ void __launch_bounds__(256) k_dist_dest_scatter(const EmitParams E, int sym, int csc, u32 rows_per, u32 t_base, int world,
                                                             const u32* __restrict__ dest_off, u32* __restrict__ dest_cur,
                                                             DistPair* __restrict__ send)
 {
-    for_each_edge(E, [&](u32, u32 t0, const u32 (&id)[4]) {
-        record_entries(id, E.tpe, t0, sym, csc, [&](u32 major, u32 minor, u32 dir, u32 t) {
-            const u32 d = major / rows_per;
-            const u32 k = atomicAdd(&dest_cur[d], 1u);
-            DistPair p;
-            p.entry = rs_entry(minor, dir, t_base + t);
-            p.major = major;
-            send[dest_off[d] + k] = p;
-        });
-    });
+    __shared__ u32 s_cnt[8][8];
+    __shared__ u32 s_base[8][8];
+    const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (u32 tile = warp; tile < E.n_tiles; tile += n_warps) {
+        const TileInfo ti = E.tile_info[tile];
+        if (ti.n_edge == 0) continue;
+        const u32 e0 = (u32)E.tile_base[tile];
+        if (lane < 8) s_cnt[wid][lane] = 0;
+        __syncwarp();
+        for (int pass = 0; pass < 2; pass++) {
+            for (u32 j = lane; j < ti.n_edge; j += 32) {
+                const u32* sl = E.edge_slots + (u64)(ti.edge_alloc + j) * E.slots_per_edge;
+                u32 id[4] = {sl[0], sl[1], 0, 0};
+                if (E.slots_per_edge == 4) { id[2] = sl[2]; id[3] = sl[3]; }
+                record_entries(id, E.tpe, (e0 + j) * (u32)E.tpe, sym, csc, [&](u32 major, u32 minor, u32 dir, u32 t) {
+                    const u32 d = major / rows_per;
+                    const u32 k = atomicAdd(&s_cnt[wid][d], 1u);
+                    if (pass) {
+                        DistPair p;
+                        p.entry = rs_entry(minor, dir, t_base + t);
+                        p.major = major;
+                        send[s_base[wid][d] + k] = p;
+                    }
+                });
+            }
+            __syncwarp();
+            if (pass == 0 && lane < (u32)world) {
+                const u32 c = s_cnt[wid][lane];
+                s_base[wid][lane] = dest_off[lane] + (c ? atomicAdd(&dest_cur[lane], c) : 0u);
+                s_cnt[wid][lane] = 0;
+            }
+            __syncwarp();
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256) k_pairs_count(const DistPair* __restrict__ pairs, u64 n, u32 row0, u32* __restrict__ cnt)

@@ -396,7 +396,9 @@ void g2n_destroy(g2n_handle* h)
 int g2n_set_stream(g2n_handle* h, void* cuda_stream)
 {
     if (!h) return G2N_ERR_INVALID;
-    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    // (void*)-1: the handle's own non-blocking stream; anything else, including NULL (the CUDA default
+    // stream), is used as given so that work is ordered with the caller's stream
+    h->stream = cuda_stream == (void*)-1 ? h->own_stream : (cudaStream_t)cuda_stream;
     return G2N_OK;
 }
 
@@ -959,7 +961,7 @@ int g2n_dist_entries(g2n_handle* h, int world, uint64_t rows_per_rank, uint64_t 
     if (M) {
         CK(cudaMemcpyAsync(cnt + 16, off, 8 * sizeof(u32), cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemsetAsync(cnt + 32, 0, 8 * sizeof(u32), h->stream));
-        { KScope ks(h, "k_dist_dest_scatter"); k_dist_dest_scatter<<<egrid, 256, 0, h->stream>>>(E, sym, csc, (u32)rows_per_rank, (u32)triplet_base, cnt + 16, cnt + 32, (DistPair*)dev_send); }
+        { KScope ks(h, "k_dist_dest_scatter"); k_dist_dest_scatter<<<egrid, 256, 0, h->stream>>>(E, sym, csc, (u32)rows_per_rank, (u32)triplet_base, world, cnt + 16, cnt + 32, (DistPair*)dev_send); }
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(h->stream));
     }

@@ -116,7 +116,9 @@ typedef struct g2n_diag {
 int g2n_create(int device, g2n_handle **out);
 void g2n_destroy(g2n_handle *h);
 
-/* Use an existing CUDA stream (cudaStream_t) for all work of this handle; NULL = handle's own. */
+/* Use an existing CUDA stream (cudaStream_t) for all work of this handle.  NULL is the CUDA default
+ * stream (e.g. PyTorch's default stream); (void*)-1 selects the handle's own non-blocking stream,
+ * which is also the initial state. */
 int g2n_set_stream(g2n_handle *h, void *cuda_stream);
 
 /* Pinned host staging memory (so callers can read files straight into DMA-able buffers). */
