@@ -182,10 +182,14 @@ __device__ __forceinline__ void cas128(TKey* s, u64 n0, u64 n1, u64& o0, u64& o1
 
 // two keys (one 32-byte sector) per 256-bit load; table sectors are kept in L2 (evict_last) while the
 // text streams through (evict_first)
-__device__ __forceinline__ void ld_key2(const TKey* s, u64 (&k)[4])
+__device__ __forceinline__ u64 table_policy()
 {
     u64 pol;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void ld_key2(const TKey* s, u64 (&k)[4], u64 pol)
+{
     asm volatile("ld.global.cg.L2::cache_hint.v4.u64 {%0, %1, %2, %3}, [%4], %5;"
                  : "=l"(k[0]), "=l"(k[1]), "=l"(k[2]), "=l"(k[3])
                  : "l"(s), "l"(pol)
@@ -234,12 +238,15 @@ struct Probe {
     u64 k0, k1;
     u64 b[4];  // the two keys of the current bucket
     u32 i;     // first slot of the current bucket
+    u32 step;  // bucket stride of the probe sequence (double hashing: odd number of buckets)
 };
 
-__device__ __forceinline__ void probe_issue(const ScanParams& P, Probe& pr)
+__device__ __forceinline__ void probe_issue(const ScanParams& P, Probe& pr, u64 pol)
 {
-    pr.i = ((u32)mix64(pr.k0 ^ (pr.k1 * 0x9e3779b97f4a7c15ULL)) & P.table_mask) & ~(u32)(TB_SLOTS - 1);
-    ld_key2(&P.tkeys[pr.i], pr.b);
+    const u64 h = mix64(pr.k0 ^ (pr.k1 * 0x9e3779b97f4a7c15ULL));
+    pr.i = ((u32)h & P.table_mask) & ~(u32)(TB_SLOTS - 1);
+    pr.step = (((u32)(h >> 40) << 1) | 1u) * TB_SLOTS;  // odd multiple of the bucket size: visits every bucket
+    ld_key2(&P.tkeys[pr.i], pr.b, pol);
 }
 
 // Examines one slot whose key was loaded as (s0, s1): claims it if empty.  Returns true if the slot
@@ -255,7 +262,7 @@ __device__ __forceinline__ bool probe_slot(const ScanParams& P, u32 slot, u64 k0
 
 // Returns the slot index (0xFFFFFFFF if the table is full).  `claimed` is incremented when this call
 // created the key.  Records min(order) as atomicMax(~order) -- fire and forget.
-__device__ __forceinline__ u32 probe_finish(const ScanParams& P, Probe& pr, u64 order, u32& claimed)
+__device__ __forceinline__ u32 probe_finish(const ScanParams& P, Probe& pr, u64 order, u32& claimed, u64 pol)
 {
     const u64 k0 = pr.k0, k1 = pr.k1;
     u32 i = pr.i, probes = 0, slot;
@@ -263,9 +270,9 @@ __device__ __forceinline__ u32 probe_finish(const ScanParams& P, Probe& pr, u64 
         // slots are examined in order; an empty slot ends the probe sequence (it is claimed)
         if (probe_slot(P, i, k0, k1, pr.b[0], pr.b[1], claimed)) { slot = i; break; }
         if (probe_slot(P, i + 1, k0, k1, pr.b[2], pr.b[3], claimed)) { slot = i + 1; break; }
-        i = (i + TB_SLOTS) & P.table_mask;
+        i = (i + pr.step) & P.table_mask;
         if (++probes > 4096u || TB_SLOTS * probes > P.table_mask) { atomicOr(&P.cnt->flags, CF_TABLE_FULL); return 0xFFFFFFFFu; }
-        ld_key2(&P.tkeys[i], pr.b);
+        ld_key2(&P.tkeys[i], pr.b, pol);
     }
     atomicMax(&P.tfirst[slot], ~order);
     return slot;
@@ -273,10 +280,11 @@ __device__ __forceinline__ u32 probe_finish(const ScanParams& P, Probe& pr, u64 
 
 __device__ __forceinline__ u32 table_probe(const ScanParams& P, u64 k0, u64 k1, u64 order, u32& claimed)
 {
+    const u64 pol = table_policy();
     Probe pr;
     pr.k0 = k0; pr.k1 = k1;
-    probe_issue(P, pr);
-    return probe_finish(P, pr, order, claimed);
+    probe_issue(P, pr, pol);
+    return probe_finish(P, pr, order, claimed, pol);
 }
 
 // Generic lookup-or-insert from a key descriptor (any length, any orientation string).

@@ -28,6 +28,7 @@ struct Tile {
     const u32* nlm;      // bit o: window byte o is '\n'
     const u32* spm;      // bit o: window byte o is '\t' or '\n'
     u64 wbase;           // global offset of window byte 0 (wraps for tile 0)
+    u64 pol;             // L2 evict_last policy for hash-table sectors
 };
 
 // first separator (TAB or newline) at or after window offset pos; TK_NF if none inside the window
@@ -145,7 +146,7 @@ __device__ __forceinline__ bool fast_weight(const ScanParams& P, const Tile& t, 
 __device__ __forceinline__ void node_issue(const ScanParams& P, const Tile& t, Probe& pr, u32 off, u32 len, u32 ori)
 {
     key_inline(t, off, len, P.bidirected != 0, ori, pr.k0, pr.k1);
-    probe_issue(P, pr);
+    probe_issue(P, pr, t.pol);
 }
 
 __device__ __forceinline__ void defer_line(const ScanParams& P, u64 off, u32 tile, u32 rec_idx, u32 edge_idx)
@@ -177,8 +178,8 @@ __device__ __forceinline__ bool parse_line_fast(const ScanParams& P, const Tile&
         Probe a, b;
         node_issue(P, t, a, p1, len, '+');
         if (P.bidirected) node_issue(P, t, b, p1, len, '-');
-        probe_finish(P, a, order0, claimed);
-        if (P.bidirected) probe_finish(P, b, order0 | 1, claimed);
+        probe_finish(P, a, order0, claimed, t.pol);
+        if (P.bidirected) probe_finish(P, b, order0 | 1, claimed, t.pol);
         return true;
     }
     if (c0 == 'P' || c0 == 'O') return t.win[e1] == '\t';  // >= 3 fields; otherwise the generic parser raises
@@ -241,13 +242,13 @@ __device__ __forceinline__ bool parse_line_fast(const ScanParams& P, const Tile&
     Probe na, nb;
     node_issue(P, t, na, uo, ul, oc_u);
     node_issue(P, t, nb, vo, vl, oc_v);
-    const u32 su = probe_finish(P, na, order0, claimed);
-    const u32 sv = probe_finish(P, nb, order0 | 1, claimed);
+    const u32 su = probe_finish(P, na, order0, claimed, t.pol);
+    const u32 sv = probe_finish(P, nb, order0 | 1, claimed, t.pol);
     if (P.slots_per_edge == 4) {
         node_issue(P, t, na, vo, vl, oc_v == '+' ? '-' : '+');
         node_issue(P, t, nb, uo, ul, oc_u == '+' ? '-' : '+');
-        const u32 sv2 = probe_finish(P, na, order0 | 2, claimed);
-        const u32 su2 = probe_finish(P, nb, order0 | 3, claimed);
+        const u32 sv2 = probe_finish(P, na, order0 | 2, claimed, t.pol);
+        const u32 su2 = probe_finish(P, nb, order0 | 3, claimed, t.pol);
         if (edge_ord < P.edge_cap) reinterpret_cast<uint4*>(P.edge_slots)[edge_ord] = make_uint4(su, sv, sv2, su2);
     } else if (edge_ord < P.edge_cap) {
         reinterpret_cast<uint2*>(P.edge_slots)[edge_ord] = make_uint2(su, sv);
@@ -277,6 +278,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, TK_MIN_BLOCKS) k_tokenize(const
     u32* spm = s_sp[wid];
     u32* list = s_list[wid];
     const u64 pol_text = policy_evict_first();
+    const u64 pol_table = table_policy();
     if (lane < 8) reinterpret_cast<u32*>(win + WT_WIN)[lane] = 0x0A0A0A0Au;  // slack read by key_inline
     const u32 n_warps = gridDim.x * WT_WARPS;
     for (u32 tile = blockIdx.x * WT_WARPS + wid; tile < P.n_tiles; tile += n_warps) {
@@ -317,7 +319,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, TK_MIN_BLOCKS) k_tokenize(const
             reinterpret_cast<unsigned short*>(spm)[piece] = (unsigned short)(mn | mt);
         }
         __syncwarp();
-        Tile t{win, nlm, spm, wbase};
+        Tile t{win, nlm, spm, wbase, pol_table};
         // ---- line starts in my 64-byte chunk: a line starts right after every '\n'
         const u32 c = 1 + lane * 2;  // mask word of my first 32 bytes (window offset 32 + 64 lane)
         const u64 nl = (u64)nlm[c] | ((u64)nlm[c + 1] << 32);
