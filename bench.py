@@ -254,6 +254,8 @@ def run_ours(args):
     total_ms = float(t.item())
     ms_step = total_ms / args.steps
     diag = h.status()
+    nb = C.c_uint64()
+    h.check(h.lib.g2n_names_bytes(h.h, C.byref(nb)))  # untimed: only sizes the name table for the byte accounting
     sz = h.sizes()
     n_edges_rank = int(diag.n_edge_records)
 

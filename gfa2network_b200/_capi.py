@@ -19,7 +19,7 @@ DTYPE_NP = {0: np.float64, 1: np.float32, 2: np.int32, 3: np.int8, 4: np.bool_}
 
 EXPORTS = [
     "g2n_abi_version", "g2n_create", "g2n_destroy", "g2n_set_stream", "g2n_host_alloc", "g2n_host_free",
-    "g2n_build", "g2n_convert", "g2n_sizes", "g2n_fetch_matrix", "g2n_fetch_names", "g2n_device_result",
+    "g2n_build", "g2n_convert", "g2n_sizes", "g2n_fetch_matrix", "g2n_names_bytes", "g2n_fetch_names", "g2n_device_result",
     "g2n_status", "g2n_last_error", "g2n_coo_to_compressed", "g2n_set_profile", "g2n_kernel_times",
     "g2n_dist_scan", "g2n_dist_export", "g2n_dist_merge", "g2n_dist_entries", "g2n_dist_slab",
 ]
@@ -90,6 +90,7 @@ def load():
     lib.g2n_convert.argtypes = [vp, i32]
     lib.g2n_sizes.argtypes = [vp, C.POINTER(Sizes)]
     lib.g2n_fetch_matrix.argtypes = [vp, vp, vp, vp]
+    lib.g2n_names_bytes.argtypes = [vp, C.POINTER(u64)]
     lib.g2n_fetch_names.argtypes = [vp, vp, vp]
     lib.g2n_device_result.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lib.g2n_status.argtypes = [vp, C.POINTER(Diag)]
@@ -189,11 +190,13 @@ class Handle:
         return s, a0, a1, data
 
     def fetch_names(self):
+        nb = C.c_uint64()
+        self.check(self.lib.g2n_names_bytes(self.h, C.byref(nb)))
         s = self.sizes()
-        names = np.empty(max(1, s.names_bytes), dtype=np.uint8)
+        names = np.empty(max(1, nb.value), dtype=np.uint8)
         offs = np.empty(s.n_nodes + 1, dtype=np.uint64)
         self.check(self.lib.g2n_fetch_names(self.h, names.ctypes.data, offs.ctypes.data))
-        return names[: s.names_bytes], offs
+        return names[: nb.value], offs
 
 
 class _PinnedPool:

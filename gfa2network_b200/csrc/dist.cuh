@@ -177,14 +177,12 @@ __global__ void __launch_bounds__(256) k_pairs_count(const DistPair* __restrict_
         atomicAdd(&cnt[(u32)pairs[i].major - row0], 1u);
 }
 
-__global__ void __launch_bounds__(256) k_pairs_scatter(const DistPair* __restrict__ pairs, u64 n, u32 row0, const u32* __restrict__ rowptr,
-                                                        u32* __restrict__ cnt, u64* __restrict__ entries)
+__global__ void __launch_bounds__(256) k_pairs_scatter(const DistPair* __restrict__ pairs, u64 n, u32 row0, u32* __restrict__ cursor,
+                                                        u64* __restrict__ entries)
 {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
         const DistPair p = pairs[i];
-        const u32 major = (u32)p.major - row0;
-        const u32 k = atomicSub(&cnt[major], 1u) - 1u;
-        entries[rowptr[major] + k] = p.entry;
+        entries[atomicAdd(&cursor[(u32)p.major - row0], 1u)] = p.entry;
     }
 }
 

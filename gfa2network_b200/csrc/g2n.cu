@@ -85,6 +85,7 @@ struct g2n_handle {
     bool symmax = false;
     int result_format = G2N_FMT_COO;
     bool names_ready = false;
+    bool names_sized = false;
     bool nnz_in_tail3 = false;  // nnz arrives as int32 in h_tail[3] (compressed builds)
     bool edges_are_ids = false; // edge_slots were translated to node IDs in place
     g2n_diag diag;
@@ -282,7 +283,8 @@ int build_compressed(g2n_handle* h, int fmt)
     int rc = launch_scan<u32>(h, ldc, h->rowptr.as<u32>(), n);
     if (rc) return rc;
     CK(cudaEventRecord(h->ev[EV_EMIT], h->stream));
-    { KScope ks(h, "k_rows_scatter"); k_rows_scatter<<<egrid, 256, 0, h->stream>>>(E, sym, csc, h->rowptr.as<u32>(), h->rowcnt.as<u32>(), h->entries.as<u64>()); }
+    CK(cudaMemcpyAsync(h->rowcnt.p, h->rowptr.p, (n + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, h->stream));  // cursors
+    { KScope ks(h, "k_rows_scatter"); k_rows_scatter<<<egrid, 256, 0, h->stream>>>(E, sym, csc, h->rowcnt.as<u32>(), h->entries.as<u64>()); }
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev[EV_SORT], h->stream));
     rc = rows_finalize(h, h->params.dtype, M, n, sym, weighted ? h->w_emit.as<double>() : nullptr, nullptr);
@@ -331,7 +333,6 @@ int finish_result(g2n_handle* h)
     CK(cudaStreamSynchronize(h->stream));
     h->nnz = h->nnz_in_tail3 ? (u64)(u32)h->h_tail[3] : h->h_tail[0];
     h->nnz_in_tail3 = false;
-    h->names_bytes = h->h_tail[1];
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev[EV_START], h->ev[EV_REDUCE]);
     h->diag.ms_total = ms;
@@ -648,16 +649,30 @@ static int ids_phase(g2n_handle* h)
         { KScope ks(h, "k_assign_ids"); k_assign_ids<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->table.as<TKey>(), h->tfirst.as<u64>(), cap, h->tile_base.as<u64>(), h->bitmap.as<u32>(), h->wprefix.as<u32>(),
                                                                  h->slot_id.as<u32>(), h->id2slot.as<u32>(), h->name_len.as<u32>()); }
         CK(cudaGetLastError());
+    }
+    h->names_sized = false;  // name offsets are scanned on demand (g2n_names_bytes / g2n_fetch_names)
+    CK(cudaEventRecord(h->ev[EV_IDS], h->stream));
+    h->have_edges = true;
+    return G2N_OK;
+}
+
+// name_len -> name_off (exclusive scan) and the total; only when somebody asks for the node names
+static int size_names(g2n_handle* h)
+{
+    if (h->names_sized) return G2N_OK;
+    const u64 n = h->n_nodes;
+    if (n > 0) {
         LoadArray<u32> ln{h->name_len.as<u32>()};
-        rc = launch_scan<u64>(h, ln, (u64*)h->name_off.as<u64>(), n);
+        int rc = launch_scan<u64>(h, ln, (u64*)h->name_off.as<u64>(), n);
         if (rc) return rc;
         CK(cudaMemcpyAsync(&h->h_tail[1], h->name_off.as<u64>() + n, sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
     } else {
         CK(cudaMemsetAsync(h->name_off.p, 0, 2 * sizeof(u64), h->stream));
         h->h_tail[1] = 0;
     }
-    CK(cudaEventRecord(h->ev[EV_IDS], h->stream));
-    h->have_edges = true;
+    CK(cudaStreamSynchronize(h->stream));
+    h->names_bytes = h->h_tail[1];
+    h->names_sized = true;
     return G2N_OK;
 }
 
@@ -692,8 +707,6 @@ int g2n_convert(g2n_handle* h, int32_t want_format)
     CK(cudaEventRecord(h->ev[EV_IDS], h->stream));
     int rc = build_compressed(h, want_format);
     if (rc) return rc;
-    const u64 keep_names = h->names_bytes;
-    h->h_tail[1] = keep_names;
     return finish_result(h);
 }
 
@@ -702,7 +715,7 @@ int g2n_sizes(g2n_handle* h, g2n_sizes_t* out)
     if (!h || !out || !h->built) return G2N_ERR_INVALID;
     out->n_nodes = h->n_nodes;  /* in slab mode: nodes of the whole graph (= number of columns) */
     out->nnz = h->nnz;
-    out->names_bytes = h->names_bytes;
+    out->names_bytes = h->names_sized ? h->names_bytes : 0;  /* filled once g2n_names_bytes ran */
     out->format = h->result_format;
     out->index_bytes = 4;
     out->dtype = h->params.dtype;
@@ -744,10 +757,24 @@ int g2n_fetch_matrix(g2n_handle* h, void* a0, void* a1, void* data)
     return G2N_OK;
 }
 
+int g2n_names_bytes(g2n_handle* h, uint64_t* out)
+{
+    if (!h || !out || !h->built) return G2N_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    int rc = size_names(h);
+    if (rc) return rc;
+    *out = h->names_bytes;
+    return G2N_OK;
+}
+
 int g2n_fetch_names(g2n_handle* h, uint8_t* names, uint64_t* offsets)
 {
     if (!h || !h->built) return G2N_ERR_INVALID;
     CK(cudaSetDevice(h->device));
+    {
+        int rc = size_names(h);
+        if (rc) return rc;
+    }
     if (!h->names_ready) {
         CK(h->names.ensure(h->names_bytes + 16));
         if (h->n_nodes > 0) {
@@ -797,7 +824,8 @@ int g2n_coo_to_compressed(g2n_handle* h, const int32_t* row, const int32_t* col,
     LoadArray<u32> ldc{h->rowcnt.as<u32>()};
     int rc = launch_scan<u32>(h, ldc, h->rowptr.as<u32>(), n);
     if (rc) return rc;
-    { KScope ks(h, "k_coo_scatter"); k_coo_scatter<<<grid_for(nnz_in, 256), 256, 0, h->stream>>>(h->up_row.as<int32_t>(), h->up_col.as<int32_t>(), nnz_in, csc, h->rowptr.as<u32>(), h->rowcnt.as<u32>(), h->entries.as<u64>()); }
+    CK(cudaMemcpyAsync(h->rowcnt.p, h->rowptr.p, (n + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, h->stream));  // cursors
+    { KScope ks(h, "k_coo_scatter"); k_coo_scatter<<<grid_for(nnz_in, 256), 256, 0, h->stream>>>(h->up_row.as<int32_t>(), h->up_col.as<int32_t>(), nnz_in, csc, h->rowcnt.as<u32>(), h->entries.as<u64>()); }
     CK(cudaGetLastError());
     rc = rows_finalize(h, dtype, nnz_in, n, 0, nullptr, h->up_data.p);
     if (rc) return rc;
@@ -922,6 +950,7 @@ int g2n_dist_merge(g2n_handle* h, const void* dev_keys_all, uint64_t key_stride,
     }
     CK(cudaStreamSynchronize(h->stream));
     h->names_bytes = h->h_tail[1];
+    h->names_sized = true;
     h->have_edges = true;
     h->edges_are_ids = false;
     return G2N_OK;
@@ -992,7 +1021,8 @@ int g2n_dist_slab(g2n_handle* h, const void* dev_pairs, uint64_t n_pairs, uint64
     if (rc) return rc;
     if (n_pairs) {
         KScope ks(h, "k_pairs_scatter");
-        k_pairs_scatter<<<grid_for(n_pairs, 256), 256, 0, h->stream>>>((const DistPair*)dev_pairs, n_pairs, (u32)row0, h->rowptr.as<u32>(), h->rowcnt.as<u32>(), h->entries.as<u64>());
+        CK(cudaMemcpyAsync(h->rowcnt.p, h->rowptr.p, (n_rows + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, h->stream));  // cursors
+        k_pairs_scatter<<<grid_for(n_pairs, 256), 256, 0, h->stream>>>((const DistPair*)dev_pairs, n_pairs, (u32)row0, h->rowcnt.as<u32>(), h->entries.as<u64>());
     }
     CK(cudaGetLastError());
     rc = rows_finalize(h, h->params.dtype, n_pairs, n_rows, sym, nullptr, nullptr);

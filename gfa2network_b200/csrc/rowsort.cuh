@@ -4,7 +4,7 @@
 // radix sort of (row, col) keys the build is a counting sort by row followed by an in-row sort:
 //   k_rows_count     one atomic per triplet into cnt[major]                       (histogram)
 //   exclusive scan   cnt -> rowptr                                                (common.cuh)
-//   k_rows_scatter   entry (minor, dir, emission index) -> rowptr[major] + ticket (any order inside a row)
+//   k_rows_scatter   entry (minor, dir, emission index) -> atomicAdd(cursor[major]) (any order inside a row)
 //   k_rows_big       rows longer than RS_SMALL are sorted in place by a whole CTA (bitonic; rare)
 //   k_rows_sort      one lane per row: insertion sort by (minor, dir, emission index) in shared memory,
 //                    count of the entries the row will store (duplicates summed, zeros of max() dropped)
@@ -60,16 +60,13 @@ __global__ void __launch_bounds__(256) k_rows_count(const EmitParams E, int sym,
     });
 }
 
-// cnt[major] counts down to 0 while the entries of a row are dropped into its range (order inside the
-// range is arbitrary; the in-row sort restores a total order)
-__global__ void __launch_bounds__(256) k_rows_scatter(const EmitParams E, int sym, int csc, const u32* __restrict__ rowptr,
-                                                       u32* __restrict__ cnt, u64* __restrict__ entries)
+// cursor[major] starts at rowptr[major]; one atomicAdd hands out the entry's position inside the row's
+// range (order inside the range is arbitrary; the in-row sort restores a total order)
+__global__ void __launch_bounds__(256) k_rows_scatter(const EmitParams E, int sym, int csc, u32* __restrict__ cursor, u64* __restrict__ entries)
 {
     for_each_edge(E, [&](u32, u32 t0, const u32 (&id)[4]) {
         record_entries(id, E.tpe, t0, sym, csc, [&](u32 major, u32 minor, u32 dir, u32 t) {
-            const u32 base = rowptr[major];
-            const u32 k = atomicSub(&cnt[major], 1u) - 1u;
-            entries[base + k] = rs_entry(minor, dir, t);
+            entries[atomicAdd(&cursor[major], 1u)] = rs_entry(minor, dir, t);
         });
     });
 }
@@ -81,12 +78,11 @@ __global__ void __launch_bounds__(256) k_coo_count(const int32_t* __restrict__ r
         atomicAdd(&cnt[(u32)(csc ? col[t] : row[t])], 1u);
 }
 __global__ void __launch_bounds__(256) k_coo_scatter(const int32_t* __restrict__ row, const int32_t* __restrict__ col, u64 nnz, int csc,
-                                                      const u32* __restrict__ rowptr, u32* __restrict__ cnt, u64* __restrict__ entries)
+                                                      u32* __restrict__ cursor, u64* __restrict__ entries)
 {
     for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < nnz; t += (u64)gridDim.x * blockDim.x) {
         const u32 major = (u32)(csc ? col[t] : row[t]), minor = (u32)(csc ? row[t] : col[t]);
-        const u32 k = atomicSub(&cnt[major], 1u) - 1u;
-        entries[rowptr[major] + k] = rs_entry(minor, 0u, (u32)t);
+        entries[atomicAdd(&cursor[major], 1u)] = rs_entry(minor, 0u, (u32)t);
     }
 }
 

@@ -141,6 +141,10 @@ int g2n_sizes(g2n_handle *h, g2n_sizes_t *out);
  * COO: a0 = row (nnz), a1 = col (nnz); data = nnz elements of the result dtype. */
 int g2n_fetch_matrix(g2n_handle *h, void *a0, void *a1, void *data);
 
+/* Total bytes of all node names.  The name table is sized lazily (callers that never ask for the node
+ * list pay nothing); g2n_sizes().names_bytes is valid after this call. */
+int g2n_names_bytes(g2n_handle *h, uint64_t *out);
+
 /* Node names in ID order (builders.py:284-288): `names` = names_bytes bytes,
  * `offsets` = n_nodes+1 uint64 offsets into it. */
 int g2n_fetch_names(g2n_handle *h, uint8_t *names, uint64_t *offsets);
