@@ -33,7 +33,7 @@ sys.path.insert(0, str(ROOT))
 HBM_FALLBACK_GBS = 6650.0  # B200_PROFILING.md fallback, used only if MEASURED_PEAKS.json is absent
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
 # (profiles/*.md name the capture each figure comes from); null where no capture exists yet
-TRAFFIC = {"k_tokenize": 209_834_496}
+TRAFFIC = {("C2", "k_tokenize"): 204_025_088}  # profiles/r1_ncu_full.md
 
 
 def peaks():
@@ -322,7 +322,7 @@ def run_ours(args):
         if ab:
             ach = ab / (per_launch_ms * 1e6)
             roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": TRAFFIC.get(dom), "algorithmic_bytes_per_launch": ab, "ms_per_launch": per_launch_ms,
+                    "frac": ach / peak, "traffic": TRAFFIC.get((args.config, dom)) if args.scale == 1.0 and world == 1 else None, "algorithmic_bytes_per_launch": ab, "ms_per_launch": per_launch_ms,
                     "share_of_step": kern[dom]["ms_per_step"] / ms_step}
     # whole-path algorithmic bytes: text in + CSR + node names out
     out_bytes = 4 * (sz.n_nodes + 1) + 12 * sz.nnz + sz.names_bytes + 8 * (sz.n_nodes + 1)
