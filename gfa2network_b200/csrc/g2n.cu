@@ -562,7 +562,19 @@ static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, c
             P.dtype = p->dtype;
             P.seed = seed;
             memcpy(P.wt, h->weight_tag, sizeof(P.wt));
-            { KScope ks(h, "k_tokenize"); k_tokenize<<<grid_for(n_tiles, WT_WARPS, TK_MIN_BLOCKS), WT_WARPS * 32, 0, h->stream>>>(P); }
+            {
+                KScope ks(h, "k_tokenize");
+                const dim3 grid(grid_for(n_tiles, WT_WARPS, TK_MIN_BLOCKS)), block(WT_WARPS * 32);
+                const int tm = (P.bidirected ? TM_BIDIR : 0) | (P.slots_per_edge == 4 ? TM_FOUR : 0) | (P.wt_len > 0 ? TM_WEIGHT : 0);
+                switch (tm) {  // bidirected keys x four slots x weights: the combinations parse_gfa can ask for
+                    case 0: k_tokenize<0><<<grid, block, 0, h->stream>>>(P); break;
+                    case TM_WEIGHT: k_tokenize<TM_WEIGHT><<<grid, block, 0, h->stream>>>(P); break;
+                    case TM_BIDIR: k_tokenize<TM_BIDIR><<<grid, block, 0, h->stream>>>(P); break;
+                    case TM_BIDIR | TM_WEIGHT: k_tokenize<TM_BIDIR | TM_WEIGHT><<<grid, block, 0, h->stream>>>(P); break;
+                    case TM_BIDIR | TM_FOUR: k_tokenize<TM_BIDIR | TM_FOUR><<<grid, block, 0, h->stream>>>(P); break;
+                    default: k_tokenize<TM_BIDIR | TM_FOUR | TM_WEIGHT><<<grid, block, 0, h->stream>>>(P); break;
+                }
+            }
             CK(cudaGetLastError());
             // (records, edge records) before every tile; the grand totals come back with the counters
             LoadTileCounts ltc{h->tile_info.as<TileInfo>()};

@@ -143,10 +143,26 @@ __device__ __forceinline__ bool fast_weight(const ScanParams& P, const Tile& t, 
     return true;
 }
 
+// MODE bits select the specialisation of the hot kernel (dead paths compile away: smaller code,
+// fewer registers): 1 = bidirected keys, 2 = four slots per edge record, 4 = weight tag present
+#define TM_BIDIR 1
+#define TM_FOUR 2
+#define TM_WEIGHT 4
+
+template <int MODE>
 __device__ __forceinline__ void node_issue(const ScanParams& P, const Tile& t, Probe& pr, u32 off, u32 len, u32 ori)
 {
-    key_inline(t, off, len, P.bidirected != 0, ori, pr.k0, pr.k1);
+    key_inline(t, off, len, (MODE & TM_BIDIR) != 0, ori, pr.k0, pr.k1);
     probe_issue(P, pr, t.pol);
+}
+
+// the first separators of a short line from one 64-bit slice of the separator mask starting at `pos`
+__device__ __forceinline__ u64 sep_slice(const Tile& t, u32 pos)
+{
+    const u32 w = pos >> 5, sh = pos & 31;
+    const u32 a = t.spm[w], b = t.spm[w + 1], c = t.spm[w + 2];  // spm has two words of slack
+    const u32 lo = __funnelshift_r(a, b, sh), hi = __funnelshift_r(b, c, sh);
+    return (u64)lo | ((u64)hi << 32);
 }
 
 __device__ __forceinline__ void defer_line(const ScanParams& P, u64 off, u32 tile, u32 rec_idx, u32 edge_idx)
@@ -163,39 +179,43 @@ __device__ __forceinline__ void defer_line(const ScanParams& P, u64 off, u32 til
 
 // Common record shapes, parsed from the separator bitmask.  Returns false when the line must go to the
 // generic parser (rare shapes, errors, long keys, fields running past the window).
+template <int MODE>
 __device__ __forceinline__ bool parse_line_fast(const ScanParams& P, const Tile& t, u32 s, u64 order0, u32 edge_ord, u32& claimed)
 {
+    constexpr bool BIDIR = (MODE & TM_BIDIR) != 0;
+    constexpr bool FOUR = (MODE & TM_FOUR) != 0;
+    constexpr bool want_w = (MODE & TM_WEIGHT) != 0;
     const uint8_t c0 = t.win[s];
     if (t.win[s + 1] != '\t') return false;  // record with no fields at all: error paths
     const u32 p1 = s + 2;
     const u32 e1 = find_sep(t, p1);
     if (e1 == TK_NF) return false;
-    const u32 maxlen = P.bidirected ? 13u : 15u;  // longest base that still fits the inline key
+    const u32 maxlen = BIDIR ? 13u : 15u;  // longest base that still fits the inline key
     if (c0 == 'S') {
         // parser.py:135-163 -> builders.py:190-198: only fields[1] matters
         const u32 len = e1 - p1;
         if (len > maxlen) return false;
         Probe a, b;
-        node_issue(P, t, a, p1, len, '+');
-        if (P.bidirected) node_issue(P, t, b, p1, len, '-');
+        node_issue<MODE>(P, t, a, p1, len, '+');
+        if (BIDIR) node_issue<MODE>(P, t, b, p1, len, '-');
         probe_finish(P, a, order0, claimed, t.pol);
-        if (P.bidirected) probe_finish(P, b, order0 | 1, claimed, t.pol);
+        if (BIDIR) probe_finish(P, b, order0 | 1, claimed, t.pol);
         return true;
     }
     if (c0 == 'P' || c0 == 'O') return t.win[e1] == '\t';  // >= 3 fields; otherwise the generic parser raises
     if (t.win[e1] != '\t') return false;
-    const bool want_w = P.wt_len > 0;
     u32 uo, ul, vo, vl, oc_u, oc_v, tag_from;
     if (c0 == 'L') {
-        // GFA-1 form with one-byte orientations (parser.py:210-216)
-        const u32 e2 = find_sep(t, e1 + 1);
-        if (e2 == TK_NF || t.win[e2] != '\t' || e2 != e1 + 2) return false;
+        // GFA-1 form with one-byte orientations (parser.py:210-216): L u o v o [ovl [tags]]
+        // the four separators after fields[1] come from one 64-bit slice of the separator mask
+        u64 m = sep_slice(t, e1 + 1);
+        if (__popcll(m) < 3) return false;  // line longer than the slice (or malformed): generic parser
+        const u32 e2 = e1 + 1 + (u32)__ffsll((long long)m) - 1; m &= m - 1;
+        const u32 e3 = e1 + 1 + (u32)__ffsll((long long)m) - 1; m &= m - 1;
+        const u32 e4 = e1 + 1 + (u32)__ffsll((long long)m) - 1; m &= m - 1;
+        if (e2 != e1 + 2 || e4 != e3 + 2 || t.win[e2] != '\t' || t.win[e3] != '\t') return false;
         oc_u = t.win[e1 + 1];
         if (oc_u != '+' && oc_u != '-') return false;
-        const u32 e3 = find_sep(t, e2 + 1);
-        if (e3 == TK_NF || t.win[e3] != '\t') return false;
-        const u32 e4 = find_sep(t, e3 + 1);
-        if (e4 == TK_NF || e4 != e3 + 2) return false;
         oc_v = t.win[e3 + 1];
         if (oc_v >= 0x80) return false;
         uo = p1; ul = e1 - p1; vo = e2 + 1; vl = e3 - e2 - 1;
@@ -240,13 +260,13 @@ __device__ __forceinline__ bool parse_line_fast(const ScanParams& P, const Tile&
     if (want_w && !fast_weight(P, t, tag_from, wv)) return false;
     // registration order u:of, v:ot, v:flip(ot), u:flip(of)  (builders.py:230-234); two probes in flight
     Probe na, nb;
-    node_issue(P, t, na, uo, ul, oc_u);
-    node_issue(P, t, nb, vo, vl, oc_v);
+    node_issue<MODE>(P, t, na, uo, ul, oc_u);
+    node_issue<MODE>(P, t, nb, vo, vl, oc_v);
     const u32 su = probe_finish(P, na, order0, claimed, t.pol);
     const u32 sv = probe_finish(P, nb, order0 | 1, claimed, t.pol);
-    if (P.slots_per_edge == 4) {
-        node_issue(P, t, na, vo, vl, oc_v == '+' ? '-' : '+');
-        node_issue(P, t, nb, uo, ul, oc_u == '+' ? '-' : '+');
+    if (FOUR) {
+        node_issue<MODE>(P, t, na, vo, vl, oc_v == '+' ? '-' : '+');
+        node_issue<MODE>(P, t, nb, uo, ul, oc_u == '+' ? '-' : '+');
         const u32 sv2 = probe_finish(P, na, order0 | 2, claimed, t.pol);
         const u32 su2 = probe_finish(P, nb, order0 | 3, claimed, t.pol);
         if (edge_ord < P.edge_cap) reinterpret_cast<uint4*>(P.edge_slots)[edge_ord] = make_uint4(su, sv, sv2, su2);
@@ -262,14 +282,15 @@ __device__ __forceinline__ bool parse_line_fast(const ScanParams& P, const Tile&
 
 // ---------------------------------------------------------------- the kernel
 #ifndef TK_MIN_BLOCKS
-#define TK_MIN_BLOCKS 4
+#define TK_MIN_BLOCKS 3
 #endif
 
+template <int MODE>
 __global__ void __launch_bounds__(WT_WARPS * 32, TK_MIN_BLOCKS) k_tokenize(const __grid_constant__ ScanParams P)
 {
     __shared__ __align__(16) uint8_t s_win[WT_WARPS][WT_WIN + 32];
     __shared__ u32 s_nl[WT_WARPS][WT_WORDS];
-    __shared__ u32 s_sp[WT_WARPS][WT_WORDS];
+    __shared__ u32 s_sp[WT_WARPS][WT_WORDS + 2];  // + 2 words of slack for sep_slice
     __shared__ u32 s_list[WT_WARPS][WT_LIST];  // [15:0] window offset of the line, [31:16] edge index within the tile
 
     const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -280,6 +301,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, TK_MIN_BLOCKS) k_tokenize(const
     const u64 pol_text = policy_evict_first();
     const u64 pol_table = table_policy();
     if (lane < 8) reinterpret_cast<u32*>(win + WT_WIN)[lane] = 0x0A0A0A0Au;  // slack read by key_inline
+    if (lane < 2) spm[WT_WORDS + lane] = 0;
     const u32 n_warps = gridDim.x * WT_WARPS;
     for (u32 tile = blockIdx.x * WT_WARPS + wid; tile < P.n_tiles; tile += n_warps) {
         const u64 t0 = (u64)tile * WT_TILE;
@@ -379,7 +401,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, TK_MIN_BLOCKS) k_tokenize(const
             for (u32 i = lane; i < nb; i += 32) {
                 const u32 ent = list[i];
                 const u32 off = ent & 0xFFFFu, eidx = ent >> 16;
-                if (!parse_line_fast(P, t, off, make_order(tile, lo + i, 0), alloc + eidx, claimed))
+                if (!parse_line_fast<MODE>(P, t, off, make_order(tile, lo + i, 0), alloc + eidx, claimed))
                     defer_line(P, wbase + off, tile, lo + i, eidx);
             }
             __syncwarp();
