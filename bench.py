@@ -67,21 +67,30 @@ class ClockSampler:
         self.rows = []
         self.proc = None
 
-    def start(self):
+    def start(self, wait_s: float = 5.0):
+        """nvidia-smi needs a few hundred ms to print its first row: start before the warm-up and wait
+        for that row, so that the timed region itself is covered by samples."""
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            t0 = time.perf_counter()
+            while not self.rows and time.perf_counter() - t0 < wait_s:
+                time.sleep(0.02)
         except Exception:
             self.proc = None
+
+    def mark(self):
+        """number of rows seen so far (to cut the sample list at region boundaries)"""
+        return len(self.rows)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
-    def stop(self):
+    def stop(self, lo: int = 0, hi: int | None = None):
         if self.proc:
             self.proc.terminate()
             try:
@@ -90,7 +99,7 @@ class ClockSampler:
                 self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[lo:hi]:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -202,7 +211,6 @@ def run_ours(args):
     else:
         h = _capi.Handle(local)
         h.set_stream(stream.cuda_stream)
-    h.set_profile(True)
     want = {"csr": _capi.FMT_CSR, "csc": _capi.FMT_CSC, "coo": _capi.FMT_NATIVE}[cfg["fmt"]]
     wt = mode.get("weight_tag")
     wtb = wt.encode() if wt else None
@@ -219,17 +227,19 @@ def run_ours(args):
         else:
             h.check(h.build(text_dev.data_ptr(), nbytes, params))
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # before the warm-up: nvidia-smi's first row takes a few hundred ms
     for _ in range(max(args.warmup, 3)):
         flush.zero_()
         step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    mark0 = sampler.mark()
+    # timed region: K steps, per-step CUDA events on the launching stream, no per-kernel events
+    h.set_profile(False)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    ktot: dict[str, list[float]] = {}
     launches = 0
     torch.cuda.synchronize()
     for i in range(args.steps):
@@ -237,22 +247,35 @@ def run_ours(args):
         ev[i][0].record(stream)
         step()
         ev[i][1].record(stream)
-        torch.cuda.synchronize()
-        for k, (ms, cnt) in h.kernel_times().items():
-            a = ktot.setdefault(k, [0.0, 0])
-            a[0] += ms
-            a[1] += cnt
         launches += h.status().gpu_launches
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    mark1 = sampler.mark()
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     ms_step = total_ms / args.steps
+    # per-kernel durations: a second pass of the same steps with one CUDA-event pair around every launch
+    # (g2n_set_profile); kept out of the timed region because the event records themselves cost time
+    h.set_profile(True)
+    ktot: dict[str, list[float]] = {}
+    ksteps = max(1, min(args.steps, 20))
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(ksteps)]
+    for i in range(ksteps):
+        flush.zero_()
+        kev[i][0].record(stream)
+        step()
+        kev[i][1].record(stream)
+        torch.cuda.synchronize()
+        for k, (ms, cnt) in h.kernel_times().items():
+            a = ktot.setdefault(k, [0.0, 0])
+            a[0] += ms
+            a[1] += cnt
+    ms_step_profiled = sum(a.elapsed_time(b) for a, b in kev) / ksteps
+    h.set_profile(False)
     diag = h.status()
     nb = C.c_uint64()
     h.check(h.lib.g2n_names_bytes(h.h, C.byref(nb)))  # untimed: only sizes the name table for the byte accounting
@@ -305,6 +328,14 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    # clocks: samples taken inside the timed region when it was long enough to hold some, else the
+    # whole loaded window (timed region + e2e loop); `window` says which
+    if mark1 - mark0 >= 3:
+        clocks = sampler.stop(mark0, mark1)
+        clocks["window"] = "timed region"
+    else:
+        clocks = sampler.stop(mark0, None)
+        clocks["window"] = "timed region + e2e loop (timed region shorter than 3 sampling periods)"
     # ---- roofline of the dominant kernel
     peak, peak_src = peaks()
     graph_directed = bool(params.keep_directed_bidir or (not params.bidirected and params.directed))
@@ -313,7 +344,7 @@ def run_ours(args):
     E_rank = int(diag.n_edge_records)
     M = E_rank * tpe * (2 if (graph_directed and not params.asymmetric) else 1)
     st = dict(N=nbytes, E=E_rank, spe=spe, M=M, n=int(sz.n_nodes), nnz=int(sz.nnz), weighted=bool(wtb), world=world)
-    kern = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in ktot.items()}
+    kern = {k: {"ms_per_step": v[0] / ksteps, "launches_per_step": v[1] / ksteps} for k, v in ktot.items()}
     dom = max(kern, key=lambda k: kern[k]["ms_per_step"]) if kern else None
     roof = None
     if dom:
@@ -347,6 +378,7 @@ def run_ours(args):
         "path_roofline": {"algorithmic_bytes": int(nbytes + out_bytes), "achieved": path_ach, "peak": peak, "frac": path_ach / peak, "unit": "GB/s"},
         "roofline": roof,
         "kernels": kern,
+        "kernel_timing": {"how": "second pass with a CUDA-event pair around every launch", "steps": ksteps, "ms_per_step_with_events": ms_step_profiled},
         "stage_ms": {k: float(diag.ms_stage[i]) for i, k in ((0, "tokenize+hash"), (1, "ids"), (3, "emit"), (4, "sort"), (5, "reduce"))},
         "cpu_baseline": cpu_base,
         "e2e": {"value": world * nbytes / (e2e_s * 1e9), "unit": "GB/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(d2h),
@@ -364,7 +396,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", default="C2", choices=["C2", "C3", "C4", "C5"])
     ap.add_argument("--scale", type=float, default=1.0)

@@ -20,7 +20,7 @@ DTYPE_NP = {0: np.float64, 1: np.float32, 2: np.int32, 3: np.int8, 4: np.bool_}
 EXPORTS = [
     "g2n_abi_version", "g2n_create", "g2n_destroy", "g2n_set_stream", "g2n_host_alloc", "g2n_host_free",
     "g2n_build", "g2n_convert", "g2n_sizes", "g2n_fetch_matrix", "g2n_names_bytes", "g2n_fetch_names", "g2n_device_result",
-    "g2n_status", "g2n_last_error", "g2n_coo_to_compressed", "g2n_set_profile", "g2n_kernel_times",
+    "g2n_status", "g2n_last_error", "g2n_coo_to_compressed", "g2n_set_profile", "g2n_set_speculation", "g2n_kernel_times",
     "g2n_dist_scan", "g2n_dist_export", "g2n_dist_merge", "g2n_dist_entries", "g2n_dist_slab",
 ]
 
@@ -54,7 +54,7 @@ class Diag(C.Structure):
         ("n_records", C.c_uint64), ("n_edge_records", C.c_uint64), ("n_triplets", C.c_uint64),
         ("n_long_keys", C.c_uint64), ("retries", C.c_uint32), ("gpu_launches", C.c_uint32),
         ("ms_total", C.c_float), ("ms_h2d", C.c_float), ("ms_stage", C.c_float * 8),
-        ("warn_flags", C.c_uint32), ("reserved", C.c_uint32),
+        ("warn_flags", C.c_uint32), ("speculative", C.c_uint32),
     ]
 
 
@@ -104,6 +104,7 @@ def load():
     lib.g2n_dist_entries.argtypes = [vp, C.c_int, u64, u64, vp, u64, pu64]
     lib.g2n_dist_slab.argtypes = [vp, vp, u64, u64, u64]
     lib.g2n_set_profile.argtypes = [vp, C.c_int]
+    lib.g2n_set_speculation.argtypes = [vp, C.c_int]
     lib.g2n_kernel_times.argtypes = [vp, C.POINTER(KTime), C.c_int]
     _lib = lib
     return lib
@@ -156,6 +157,11 @@ class Handle:
 
     def set_profile(self, on: bool):
         self.check(self.lib.g2n_set_profile(self.h, int(on)))
+
+    def set_speculation(self, on: bool):
+        """Repeat builds of the same input size and mode skip the host round trip after the tokenizer
+        (include/g2n.h: g2n_set_speculation); on by default."""
+        self.check(self.lib.g2n_set_speculation(self.h, int(on)))
 
     def kernel_times(self) -> dict[str, tuple[float, int]]:
         buf = (KTime * 32)()

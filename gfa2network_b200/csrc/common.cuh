@@ -151,18 +151,22 @@ __device__ __forceinline__ u64 lookback_exclusive(u64* state, u32 tile, u64 agg)
 }
 
 // ---------------------------------------------------------------- generic exclusive scan
-// out[i] = sum_{j<i} load(j) for i in [0, n]; out has n+1 entries (out[n] = total).
+// out[i] = sum_{j<i} load(j) for i in [0, n]; out has n+1 entries (out[n] = total).  `out2`, if given,
+// receives a second copy (the row cursors of the scatter pass).  n = *n_dev when n_dev is given (sizes that
+// only the device knows, see DevSizes), else n_host.
 // grid: any size >= 1 (persistent, ticketed tiles of SCAN_TILE items); block: 256 threads.
+// `state` (one word per tile) and `ticket` must be zero at launch.
 #define SCAN_ITEMS 8
 #define SCAN_TILE (256 * SCAN_ITEMS)
 
 template <typename Tout, class LoadOp>
-__global__ void __launch_bounds__(256) k_scan_exclusive(LoadOp load, Tout* __restrict__ out, u64 n,
-                                                         u64* __restrict__ state, u32* __restrict__ ticket)
+__global__ void __launch_bounds__(256) k_scan_exclusive(LoadOp load, Tout* __restrict__ out, Tout* __restrict__ out2, u64 n_host,
+                                                         const u32* __restrict__ n_dev, u64* __restrict__ state, u32* __restrict__ ticket)
 {
     __shared__ u64 sm[10];
     __shared__ u32 s_tile;
     __shared__ u64 s_base;
+    const u64 n = n_dev ? (u64)*n_dev : n_host;
     const u64 n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     while (true) {
         if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
@@ -187,13 +191,22 @@ __global__ void __launch_bounds__(256) k_scan_exclusive(LoadOp load, Tout* __res
         u64 run = s_base + excl;
 #pragma unroll
         for (int k = 0; k < SCAN_ITEMS; k++) {
-            if (base + k < n) out[base + k] = (Tout)run;
+            if (base + k < n) {
+                out[base + k] = (Tout)run;
+                if (out2) out2[base + k] = (Tout)run;
+            }
             run += v[k];
         }
-        if (tile == n_tiles - 1 && threadIdx.x == 255) out[n] = (Tout)run;
+        if (tile == n_tiles - 1 && threadIdx.x == 255) {
+            out[n] = (Tout)run;
+            if (out2) out2[n] = (Tout)run;
+        }
         __syncthreads();
     }
-    if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) out[0] = (Tout)0;
+    if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+        out[0] = (Tout)0;
+        if (out2) out2[0] = (Tout)0;
+    }
 }
 
 template <typename T>

@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(256) k_dist_dest_scatter(const EmitParams E, i
     __shared__ u32 s_base[8][8];
     const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    if (!E.ds->ok) return;
     for (u32 tile = warp; tile < E.n_tiles; tile += n_warps) {
         const TileInfo ti = E.tile_info[tile];
         if (ti.n_edge == 0) continue;

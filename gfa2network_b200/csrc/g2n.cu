@@ -59,13 +59,42 @@ struct g2n_handle {
     std::string err;
     cudaEvent_t ev[EV_COUNT];
     // device buffers (kept between builds: a warm handle allocates nothing)
-    DevBuf text, table, tfirst, trep, defer, edge_slots, edge_w, longs, tile_info, tile_base, cnt, bitmap, wprefix, slot_id, id2slot, name_len, name_off, names;
-    DevBuf rowcnt, rowptr, entries, w_emit, biglist, ucnt, indptr, indices, data, row, col, scan_state;
+    DevBuf text, defer, edge_slots, edge_w, longs, tile_info, tile_base, wprefix, slot_id, id2slot, name_len, name_off, names;
+    DevBuf rowptr, cursor, entries, w_emit, biglist, ucnt, indptr, indices, data, row, col, scan_state;
     DevBuf up_row, up_col, up_data;
-    Counters* h_cnt = nullptr;  // pinned
-    u64* h_tail = nullptr;      // pinned: {nnz, names_bytes, tile_base total}
+    // zero-initialised state, one memset per arena and build:
+    //   zearly  hash table (keys | first | rep), counters + DevSizes, look-back state of the tile scan
+    //   zids    first-appearance bitmap, look-back state of its scan
+    //   zrows   row histogram, long-row counter, look-back state of the two row scans
+    DevBuf zearly, zids, zrows;
+    TKey* d_tkeys = nullptr;
+    u64* d_tfirst = nullptr;
+    u32* d_trep = nullptr;
+    Ctl* d_ctl = nullptr;
+    Counters* d_cnt = nullptr;
+    DevSizes* d_ds = nullptr;
+    u64* d_scan_tiles = nullptr;
+    u32* d_bitmap = nullptr;
+    u64* d_scan_words = nullptr;
+    u32* d_rowcnt = nullptr;
+    u32* d_bigcount = nullptr;
+    u64* d_scan_rows[2] = {nullptr, nullptr};
+    size_t zids_bytes = 0, zrows_bytes = 0;
+    Ctl* h_ctl = nullptr;       // pinned copy of the counters + device-side sizes
+    Counters* h_cnt = nullptr;  // = &h_ctl->c
+    u64* h_tail = nullptr;      // pinned: {-, names_bytes, tile_base total, -}
     // capacity hints learnt from previous builds
-    u64 hint_keys = 0, hint_edges = 0, hint_long = 0, hint_defer = 0;
+    u64 hint_keys = 0, hint_edges = 0, hint_long = 0, hint_defer = 0, hint_records = 0;
+    // A build whose shape (input size + mode) equals the previous one runs speculatively: buffers are
+    // sized from the hints, every size-dependent kernel reads the actual sizes from DevSizes, and the
+    // host looks at the counters once, at the end.  A miss (DevSizes.ok == 0) re-runs the build with
+    // the host round trip after the tokenizer.
+    u64 hint_sig = 0;
+    bool hint_valid = false;
+    bool speculate = true;  // g2n_set_option("speculate", 0) turns it off
+    bool spec = false;      // the current build is speculative
+    bool slow_ran = false;
+    u64 cap_n = 0, cap_E = 0, cap_R = 0;  // what this build's buffers were sized for
     // state of the last build
     g2n_params params;
     uint8_t weight_tag[64];
@@ -86,7 +115,6 @@ struct g2n_handle {
     int result_format = G2N_FMT_COO;
     bool names_ready = false;
     bool names_sized = false;
-    bool nnz_in_tail3 = false;  // nnz arrives as int32 in h_tail[3] (compressed builds)
     bool edges_are_ids = false; // edge_slots were translated to node IDs in place
     g2n_diag diag;
     u32 launches = 0;
@@ -151,17 +179,40 @@ inline u32 next_pow2(u64 x)
     return (u32)p;
 }
 
-// exclusive scan launcher: out[0..n], out[n] = total
+// exclusive scan launcher: out[0..n], out[n] = total (also into out2 if given).  n_cap bounds n on the
+// host (grid, look-back state); n_dev, if given, holds the actual n on the device.  `state` is a
+// zeroed region of n_cap / SCAN_TILE + 3 words out of an arena, or NULL: memset a private one.
+inline size_t scan_state_bytes(u64 n_cap) { return ((n_cap + SCAN_TILE - 1) / SCAN_TILE + 3) * sizeof(u64); }
+
 template <typename Tout, class LoadOp>
-int launch_scan(g2n_handle* h, LoadOp load, Tout* out, u64 n)
+int launch_scan(g2n_handle* h, LoadOp load, Tout* out, Tout* out2, u64 n_cap, const u32* n_dev, u64* state_region)
 {
-    const u64 n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-    CK(h->scan_state.ensure((n_tiles + 2) * sizeof(u64)));
-    CK(cudaMemsetAsync(h->scan_state.p, 0, (n_tiles + 2) * sizeof(u64), h->stream));
-    u64* state = h->scan_state.as<u64>() + 1;
-    u32* ticket = (u32*)h->scan_state.p;
-    { KScope ks(h, "k_scan_exclusive"); k_scan_exclusive<Tout, LoadOp><<<grid_for(n_tiles, 1, 4), 256, 0, h->stream>>>(load, out, n, state, ticket); }
+    const u64 n_tiles = (n_cap + SCAN_TILE - 1) / SCAN_TILE;
+    if (!state_region) {
+        CK(h->scan_state.ensure(scan_state_bytes(n_cap)));
+        CK(cudaMemsetAsync(h->scan_state.p, 0, scan_state_bytes(n_cap), h->stream));
+        state_region = h->scan_state.as<u64>();
+    }
+    u64* state = state_region + 1;
+    u32* ticket = (u32*)state_region;
+    { KScope ks(h, "k_scan_exclusive"); k_scan_exclusive<Tout, LoadOp><<<grid_for(n_tiles, 1, 4), 256, 0, h->stream>>>(load, out, out2, n_cap, n_dev, state, ticket); }
     CK(cudaGetLastError());
+    return G2N_OK;
+}
+
+// zrows arena: row histogram | long-row counter | look-back state of the rowptr and indptr scans
+int layout_zrows(g2n_handle* h, u64 n_cap)
+{
+    const size_t a = ((n_cap + 2) * sizeof(u32) + 255) & ~(size_t)255;
+    const size_t b = 256;
+    const size_t c = (scan_state_bytes(n_cap) + 255) & ~(size_t)255;
+    CK(h->zrows.ensure(a + b + 2 * c));
+    uint8_t* base = h->zrows.as<uint8_t>();
+    h->d_rowcnt = (u32*)base;
+    h->d_bigcount = (u32*)(base + a);
+    h->d_scan_rows[0] = (u64*)(base + a + b);
+    h->d_scan_rows[1] = (u64*)(base + a + b + c);
+    h->zrows_bytes = a + b + 2 * c;
     return G2N_OK;
 }
 
@@ -175,31 +226,27 @@ size_t dtype_size(int dt)
     }
 }
 
-// rowptr (u32, n+1) and entries (u64, M) are ready: sort every row, sum duplicates, write the result.
+// rowptr (u32, rows+1) and entries (u64, M) are ready: sort every row, sum duplicates, write the result.
+// M and n are host-side bounds (exact or capacities); the kernels read the actual row count from DevSizes.
 template <typename T>
 int rows_finalize_typed(g2n_handle* h, u64 M, u64 n, int sym, const double* w_emit, const T* w_typed)
 {
-    const u32 n32 = (u32)n;
+    const u32* n_dev = &h->d_ds->rows;
     CK(h->indptr.ensure((n + 2) * sizeof(int32_t)));
     CK(h->indices.ensure((M + 1) * sizeof(int32_t)));
     CK(h->data.ensure((M + 1) * sizeof(T)));
     CK(h->biglist.ensure((n + 2) * sizeof(u32)));
-    u32* bigcount = h->biglist.as<u32>() + n + 1;
-    CK(cudaMemsetAsync(bigcount, 0, sizeof(u32), h->stream));
-    { KScope ks(h, "k_rows_find_big"); k_rows_find_big<<<grid_for(n, 256), 256, 0, h->stream>>>(h->rowptr.as<u32>(), n32, h->biglist.as<u32>(), bigcount); }
-    { KScope ks(h, "k_rows_big"); k_rows_big<<<G2N_SM_COUNT, 256, 0, h->stream>>>(h->rowptr.as<u32>(), h->biglist.as<u32>(), bigcount, h->entries.as<u64>()); }
+    { KScope ks(h, "k_rows_find_big"); k_rows_find_big<<<grid_for(n, 256), 256, 0, h->stream>>>(h->rowptr.as<u32>(), n_dev, h->biglist.as<u32>(), h->d_bigcount); }
+    { KScope ks(h, "k_rows_big"); k_rows_big<<<G2N_SM_COUNT, 256, 0, h->stream>>>(h->rowptr.as<u32>(), h->biglist.as<u32>(), h->d_bigcount, h->entries.as<u64>()); }
     const u64 n_groups = (n + 31) / 32;
     CK(h->ucnt.ensure((n + 2) * sizeof(u32)));
-    { KScope ks(h, "k_rows_sort"); k_rows_sort<T><<<grid_for(n_groups, RS_WARPS, 12), RS_WARPS * 32, 0, h->stream>>>(h->rowptr.as<u32>(), h->entries.as<u64>(), n32, sym, w_emit, w_typed, h->ucnt.as<u32>()); }
+    { KScope ks(h, "k_rows_sort"); k_rows_sort<T><<<grid_for(n_groups, RS_WARPS, 12), RS_WARPS * 32, 0, h->stream>>>(h->rowptr.as<u32>(), h->entries.as<u64>(), n_dev, sym, w_emit, w_typed, h->ucnt.as<u32>()); }
     CK(cudaGetLastError());
     LoadArray<u32> ldu{h->ucnt.as<u32>()};
-    int rc = launch_scan<int32_t>(h, ldu, h->indptr.as<int32_t>(), n);
+    int rc = launch_scan<int32_t>(h, ldu, h->indptr.as<int32_t>(), nullptr, n, n_dev, h->d_scan_rows[1]);
     if (rc) return rc;
-    { KScope ks(h, "k_rows_write"); k_rows_write<T><<<grid_for(n, 256), 256, 0, h->stream>>>(h->rowptr.as<u32>(), h->entries.as<u64>(), n32, sym, w_emit, w_typed, h->indptr.as<int32_t>(), h->indices.as<int32_t>(), h->data.as<T>()); }
+    { KScope ks(h, "k_rows_write"); k_rows_write<T><<<grid_for(n, 256), 256, 0, h->stream>>>(h->rowptr.as<u32>(), h->entries.as<u64>(), n_dev, sym, w_emit, w_typed, h->indptr.as<int32_t>(), h->indices.as<int32_t>(), h->data.as<T>(), &h->d_ds->nnz); }
     CK(cudaGetLastError());
-    // nnz = indptr[n]
-    CK(cudaMemcpyAsync(&h->h_tail[3], h->indptr.as<int32_t>() + n, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-    h->nnz_in_tail3 = true;
     return G2N_OK;
 }
 
@@ -214,16 +261,6 @@ int rows_finalize(g2n_handle* h, int dtype, u64 M, u64 n, int sym, const double*
     }
     h->err = "unknown dtype";
     return G2N_ERR_INVALID;
-}
-
-int empty_compressed(g2n_handle* h, u64 n)
-{
-    CK(h->indptr.ensure((n + 2) * sizeof(int32_t)));
-    CK(cudaMemsetAsync(h->indptr.p, 0, (n + 2) * sizeof(int32_t), h->stream));
-    CK(h->indices.ensure(16));
-    CK(h->data.ensure(16));
-    h->h_tail[0] = 0;
-    return G2N_OK;
 }
 
 struct LoadTileCounts {
@@ -244,47 +281,47 @@ EmitParams emit_params(g2n_handle* h)
     E.tpe = h->tpe;
     E.ids_ready = h->edges_are_ids ? 1 : 0;
     E.write_ids = 0;
+    E.ds = h->d_ds;
     return E;
 }
 
-// K3 + K4 for a compressed result of the current build.  fmt: G2N_FMT_CSR | G2N_FMT_CSC
-int build_compressed(g2n_handle* h, int fmt)
+// K3 + K4 for a compressed result of the current build.  fmt: G2N_FMT_CSR | G2N_FMT_CSC.
+// Sizes on the host are this build's capacities (cap_n nodes, cap_E edge records): exact after a host
+// round trip, hints in a speculative build; the kernels read the actual ones from DevSizes.
+// `zeroed`: the zrows arena was already laid out and cleared for this build.
+int build_compressed(g2n_handle* h, int fmt, bool zeroed)
 {
-    const u64 n = h->n_nodes;
-    const u64 T = h->n_edges * (u64)h->tpe;
+    const u64 n = h->cap_n;
+    const u64 T = h->cap_E * (u64)h->tpe;
     const int sym = h->symmax ? 1 : 0;
     const u64 M = sym ? 2 * T : T;
     h->result_format = fmt;
-    if (M == 0 || n == 0) {
-        int rc = empty_compressed(h, n);
-        CK(cudaEventRecord(h->ev[EV_EMIT], h->stream));
-        CK(cudaEventRecord(h->ev[EV_SORT], h->stream));
-        CK(cudaEventRecord(h->ev[EV_REDUCE], h->stream));
-        return rc;
-    }
     if (M >= 0xFFFFFFF0ull) { h->err = "more than 2^32 triplets in one build"; return G2N_ERR_UNSUPPORTED; }
     const bool weighted = h->params.weight_tag_len > 0;
     // for a symmetric result CSC arrays equal CSR arrays; bucket by row either way
     const int csc = (!sym && fmt == G2N_FMT_CSC) ? 1 : 0;
-    CK(h->rowcnt.ensure((n + 2) * sizeof(u32)));
+    if (!zeroed) {
+        int rc = layout_zrows(h, n);
+        if (rc) return rc;
+        CK(cudaMemsetAsync(h->zrows.p, 0, h->zrows_bytes, h->stream));
+    }
     CK(h->rowptr.ensure((n + 2) * sizeof(u32)));
+    CK(h->cursor.ensure((n + 2) * sizeof(u32)));
     CK(h->entries.ensure((M + 1) * sizeof(u64)));
     if (weighted) CK(h->w_emit.ensure((T + 1) * sizeof(double)));
-    CK(cudaMemsetAsync(h->rowcnt.p, 0, (n + 2) * sizeof(u32), h->stream));
     EmitParams E = emit_params(h);
     E.write_ids = 1;  // the count pass leaves node IDs in edge_slots for the scatter pass (and later converts)
     const u32 egrid = grid_for((u64)h->n_tiles * 32, 256);
-    { KScope ks(h, "k_rows_count"); k_rows_count<<<egrid, 256, 0, h->stream>>>(E, sym, csc, h->rowcnt.as<u32>(), weighted ? h->w_emit.as<double>() : nullptr); }
+    { KScope ks(h, "k_rows_count"); k_rows_count<<<egrid, 256, 0, h->stream>>>(E, sym, csc, h->d_rowcnt, weighted ? h->w_emit.as<double>() : nullptr); }
     CK(cudaGetLastError());
     h->edges_are_ids = true;
     E.ids_ready = 1;
     E.write_ids = 0;
-    LoadArray<u32> ldc{h->rowcnt.as<u32>()};
-    int rc = launch_scan<u32>(h, ldc, h->rowptr.as<u32>(), n);
+    LoadArray<u32> ldc{h->d_rowcnt};
+    int rc = launch_scan<u32>(h, ldc, h->rowptr.as<u32>(), h->cursor.as<u32>(), n, &h->d_ds->rows, h->d_scan_rows[0]);  // rowptr + cursors
     if (rc) return rc;
     CK(cudaEventRecord(h->ev[EV_EMIT], h->stream));
-    CK(cudaMemcpyAsync(h->rowcnt.p, h->rowptr.p, (n + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, h->stream));  // cursors
-    { KScope ks(h, "k_rows_scatter"); k_rows_scatter<<<egrid, 256, 0, h->stream>>>(E, sym, csc, h->rowcnt.as<u32>(), h->entries.as<u64>()); }
+    { KScope ks(h, "k_rows_scatter"); k_rows_scatter<<<egrid, 256, 0, h->stream>>>(E, sym, csc, h->cursor.as<u32>(), h->entries.as<u64>()); }
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev[EV_SORT], h->stream));
     rc = rows_finalize(h, h->params.dtype, M, n, sym, weighted ? h->w_emit.as<double>() : nullptr, nullptr);
@@ -304,35 +341,65 @@ int emit_coo_typed(g2n_handle* h, u64 T_)
 
 int build_coo(g2n_handle* h)
 {
-    const u64 T = h->n_edges * (u64)h->tpe;
+    const u64 T = h->cap_E * (u64)h->tpe;
     h->result_format = G2N_FMT_COO;
     CK(h->row.ensure((T + 1) * sizeof(int32_t)));
     CK(h->col.ensure((T + 1) * sizeof(int32_t)));
     int rc = G2N_OK;
-    if (T > 0) {
-        switch (h->params.dtype) {
-            case G2N_DTYPE_F64: rc = emit_coo_typed<double>(h, T); break;
-            case G2N_DTYPE_F32: rc = emit_coo_typed<float>(h, T); break;
-            case G2N_DTYPE_I32: rc = emit_coo_typed<int32_t>(h, T); break;
-            case G2N_DTYPE_I8: rc = emit_coo_typed<int8_t>(h, T); break;
-            case G2N_DTYPE_BOOL: rc = emit_coo_typed<BoolT>(h, T); break;
-            default: h->err = "unknown dtype"; return G2N_ERR_INVALID;
-        }
-    } else {
-        CK(h->data.ensure(16));
+    switch (h->params.dtype) {
+        case G2N_DTYPE_F64: rc = emit_coo_typed<double>(h, T); break;
+        case G2N_DTYPE_F32: rc = emit_coo_typed<float>(h, T); break;
+        case G2N_DTYPE_I32: rc = emit_coo_typed<int32_t>(h, T); break;
+        case G2N_DTYPE_I8: rc = emit_coo_typed<int8_t>(h, T); break;
+        case G2N_DTYPE_BOOL: rc = emit_coo_typed<BoolT>(h, T); break;
+        default: h->err = "unknown dtype"; return G2N_ERR_INVALID;
     }
-    h->h_tail[0] = T;
     CK(cudaEventRecord(h->ev[EV_EMIT], h->stream));
     CK(cudaEventRecord(h->ev[EV_SORT], h->stream));
     CK(cudaEventRecord(h->ev[EV_REDUCE], h->stream));
     return rc;
 }
 
+// first error / first unknown record in file order, counts
+void collect_diag(g2n_handle* h, const Counters& hc, u64 n_records)
+{
+    h->diag.n_records = n_records;
+    h->diag.n_edge_records = hc.edge_alloc;
+    h->diag.n_long_keys = hc.n_long;
+    if (hc.flags & CF_CAST_OVERFLOW) h->diag.warn_flags |= G2N_WARN_CAST_OVERFLOW;
+    const u64 first_error = ~hc.first_error_inv, first_unknown = ~hc.first_unknown_inv;  // ~0 if none
+    if (first_error != ~0ull) {
+        h->diag.err_kind = (int32_t)(first_error & 0xFF);
+        h->diag.err_offset = first_error >> 8;
+    }
+    if (first_unknown != ~0ull && (first_error == ~0ull || (first_unknown >> 8) < (first_error >> 8))) {
+        h->diag.unknown_byte = (int32_t)(first_unknown & 0xFF);
+        h->diag.unknown_offset = first_unknown >> 8;
+    }
+}
+
+#define G2N_SPEC_MISS 1000  // internal: the speculative build has to be repeated with a host round trip
+
+// The one host round trip of a build: counters + device-side sizes come back, timings are read.
 int finish_result(g2n_handle* h)
 {
+    CK(cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    h->nnz = h->nnz_in_tail3 ? (u64)(u32)h->h_tail[3] : h->h_tail[0];
-    h->nnz_in_tail3 = false;
+    const DevSizes& ds = h->h_ctl->s;
+    if (!ds.ok) {
+        if (h->spec) return G2N_SPEC_MISS;
+        h->err = "device-side size check failed after a host-checked tokenizer pass";
+        return G2N_ERR_INTERNAL;
+    }
+    if (h->spec) {
+        const Counters& hc = *h->h_cnt;
+        collect_diag(h, hc, ds.R);
+        h->n_nodes = ds.n;
+        h->n_edges = ds.E;
+        h->n_records = ds.R;
+        h->n_long = hc.n_long;
+    }
+    h->nnz = ds.nnz;
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev[EV_START], h->ev[EV_REDUCE]);
     h->diag.ms_total = ms;
@@ -344,6 +411,7 @@ int finish_result(g2n_handle* h)
     cudaEventElapsedTime(&h->diag.ms_stage[5], h->ev[EV_SORT], h->ev[EV_REDUCE]);
     h->diag.gpu_launches = h->launches;
     h->diag.n_triplets = h->n_edges * (u64)h->tpe;
+    h->diag.speculative = h->spec ? 1 : 0;
     return G2N_OK;
 }
 
@@ -366,11 +434,12 @@ int g2n_create(int device, g2n_handle** out)
     if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return G2N_ERR_CUDA; }
     h->stream = h->own_stream;
     for (int i = 0; i < EV_COUNT; i++) cudaEventCreate(&h->ev[i]);
-    if (cudaHostAlloc((void**)&h->h_cnt, sizeof(Counters), cudaHostAllocDefault) != cudaSuccess ||
+    if (cudaHostAlloc((void**)&h->h_ctl, sizeof(Ctl), cudaHostAllocDefault) != cudaSuccess ||
         cudaHostAlloc((void**)&h->h_tail, 8 * sizeof(u64), cudaHostAllocDefault) != cudaSuccess) {
         delete h;
         return G2N_ERR_CUDA;
     }
+    h->h_cnt = &h->h_ctl->c;
     memset(&h->diag, 0, sizeof(h->diag));
     h->diag.unknown_byte = -1;
     *out = h;
@@ -382,13 +451,13 @@ void g2n_destroy(g2n_handle* h)
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf* bufs[] = {&h->text, &h->table, &h->tfirst, &h->trep, &h->defer, &h->edge_slots, &h->edge_w, &h->longs, &h->tile_info, &h->tile_base, &h->cnt, &h->bitmap, &h->wprefix,
-                      &h->slot_id, &h->id2slot, &h->name_len, &h->name_off, &h->names, &h->rowcnt, &h->rowptr, &h->entries, &h->w_emit, &h->biglist, &h->ucnt, &h->indptr, &h->indices, &h->data, &h->row, &h->col,
-                      &h->scan_state, &h->up_row, &h->up_col, &h->up_data};
+    DevBuf* bufs[] = {&h->text, &h->zearly, &h->zids, &h->zrows, &h->defer, &h->edge_slots, &h->edge_w, &h->longs, &h->tile_info, &h->tile_base, &h->wprefix,
+                      &h->slot_id, &h->id2slot, &h->name_len, &h->name_off, &h->names, &h->rowptr, &h->cursor, &h->entries, &h->w_emit, &h->biglist, &h->ucnt, &h->indptr, &h->indices, &h->data, &h->row, &h->col,
+                      &h->scan_state, &h->up_row, &h->up_col, &h->up_data, &h->gtable, &h->gfirst, &h->gslot_id, &h->dest_cnt};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(h->ev[i]);
     for (KTimer& t : h->ktimers) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
-    if (h->h_cnt) cudaFreeHost(h->h_cnt);
+    if (h->h_ctl) cudaFreeHost(h->h_ctl);
     if (h->h_tail) cudaFreeHost(h->h_tail);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -413,6 +482,13 @@ void* g2n_host_alloc(uint64_t nbytes)
 void g2n_host_free(void* p)
 {
     if (p) cudaFreeHost(p);
+}
+
+int g2n_set_speculation(g2n_handle* h, int on)
+{
+    if (!h) return G2N_ERR_INVALID;
+    h->speculate = on != 0;
+    return G2N_OK;
 }
 
 int g2n_set_profile(g2n_handle* h, int on)
@@ -457,8 +533,63 @@ int g2n_status(g2n_handle* h, g2n_diag* out)
     return G2N_OK;
 }
 
-// Phase 1 of every build: text -> hash table (min order per key), tile_info / tile_base, edge_slots.
-static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n_params* p)
+// zearly arena: keys | first | rep | counters + DevSizes | look-back state of the tile scan
+static int layout_zearly(g2n_handle* h, u32 cap, u32 n_tiles, size_t* bytes)
+{
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t a = up((size_t)cap * sizeof(TKey)), b = up((size_t)cap * sizeof(u64)), c = up((size_t)cap * sizeof(u32));
+    const size_t d = up(sizeof(Ctl)), e = up(scan_state_bytes(n_tiles));
+    CK(h->zearly.ensure(a + b + c + d + e));
+    uint8_t* base = h->zearly.as<uint8_t>();
+    h->d_tkeys = (TKey*)base;
+    h->d_tfirst = (u64*)(base + a);
+    h->d_trep = (u32*)(base + a + b);
+    h->d_ctl = (Ctl*)(base + a + b + c);
+    h->d_cnt = &h->d_ctl->c;
+    h->d_ds = &h->d_ctl->s;
+    h->d_scan_tiles = (u64*)(base + a + b + c + d);
+    *bytes = a + b + c + d + e;
+    return G2N_OK;
+}
+
+// zids arena: first-appearance bitmap | look-back state of its popcount scan
+static int layout_zids(g2n_handle* h, u64 R_cap)
+{
+    const u64 words = (4 * R_cap + 31) / 32 + 1;
+    const size_t a = (words * sizeof(u32) + 255) & ~(size_t)255;
+    const size_t b = (scan_state_bytes(words) + 255) & ~(size_t)255;
+    CK(h->zids.ensure(a + b));
+    h->d_bitmap = h->zids.as<u32>();
+    h->d_scan_words = (u64*)(h->zids.as<uint8_t>() + a);
+    h->zids_bytes = a + b;
+    return G2N_OK;
+}
+
+// Everything downstream of the tokenizer that can be sized from (cap_n, cap_R): allocate and clear.
+static int prepare_late(g2n_handle* h, bool want_rows)
+{
+    int rc = layout_zids(h, h->cap_R);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(h->zids.p, 0, h->zids_bytes, h->stream));
+    if (want_rows) {
+        rc = layout_zrows(h, h->cap_n);
+        if (rc) return rc;
+        CK(cudaMemsetAsync(h->zrows.p, 0, h->zrows_bytes, h->stream));
+    }
+    return G2N_OK;
+}
+
+static u64 shape_signature(const g2n_params* p, u64 nbytes, int wt_len)
+{
+    u64 s = nbytes * 0x9e3779b97f4a7c15ull;
+    s ^= (u64)(p->directed != 0) | (u64)(p->bidirected != 0) << 1 | (u64)(p->keep_directed_bidir != 0) << 2 | (u64)(p->asymmetric != 0) << 3 |
+         (u64)(p->strip_orientation != 0) << 4 | (u64)(wt_len > 0) << 5 | (u64)(p->want_format & 7) << 6;
+    return s | 1;
+}
+
+// Phase 1 of every build: text -> hash table (min order per key), tile_info / tile_base, edge_slots,
+// DevSizes.  spec: no host round trip -- buffers come from the hints of the previous build of this shape.
+static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n_params* p, bool spec, bool late_rows)
 {
     if (!h || !p || (!text && nbytes)) return G2N_ERR_INVALID;
     h->err.clear();
@@ -466,6 +597,7 @@ static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, c
     h->have_edges = false;
     h->names_ready = false;
     h->edges_are_ids = false;
+    h->spec = spec;
     if (p->dtype < G2N_DTYPE_F64 || p->dtype > G2N_DTYPE_BOOL) { h->err = "unknown dtype"; return G2N_ERR_INVALID; }
     if (p->want_format < G2N_FMT_NATIVE || p->want_format > G2N_FMT_CSC) { h->err = "unknown want_format"; return G2N_ERR_INVALID; }
     if (p->weight_tag_len > 64) { h->err = "weight tag longer than 64 bytes"; return G2N_ERR_UNSUPPORTED; }
@@ -506,6 +638,7 @@ static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, c
     u64 edge_cap = h->hint_edges ? h->hint_edges + 64 : nbytes / 20 + 1024;
     u64 long_cap = h->hint_long ? h->hint_long + h->hint_long / 4 + 1024 : 65536;
     u64 defer_cap = h->hint_defer ? h->hint_defer + h->hint_defer / 4 + 1024 : (nbytes / 2048 > 65536 ? nbytes / 2048 : 65536);
+    if (spec) edge_cap += edge_cap / 16;
     u64 seed = 0x51ed270b7a2d4c1full;
     Counters& hc = *h->h_cnt;
     for (u32 attempt = 0;; attempt++) {
@@ -517,31 +650,35 @@ static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, c
         const u32 cap = next_pow2(want_slots < 1024 ? 1024 : want_slots);
         if (want_slots > (1ull << 31)) { h->err = "more than 2^30 distinct node keys"; return G2N_ERR_UNSUPPORTED; }
         h->table_cap = cap;
-        CK(h->table.ensure((size_t)cap * sizeof(TKey)));
-        CK(h->tfirst.ensure((size_t)cap * sizeof(u64)));
-        CK(h->trep.ensure((size_t)cap * sizeof(u32)));
-        CK(cudaMemsetAsync(h->table.p, 0, (size_t)cap * sizeof(TKey), h->stream));
-        CK(cudaMemsetAsync(h->tfirst.p, 0, (size_t)cap * sizeof(u64), h->stream));
-        CK(cudaMemsetAsync(h->trep.p, 0, (size_t)cap * sizeof(u32), h->stream));
+        size_t zbytes = 0;
+        {
+            int rc = layout_zearly(h, cap, n_tiles, &zbytes);
+            if (rc) return rc;
+        }
+        CK(cudaMemsetAsync(h->zearly.p, 0, zbytes, h->stream));
         CK(h->edge_slots.ensure((edge_cap + 1) * h->spe * sizeof(u32)));
         if (weighted) CK(h->edge_w.ensure((edge_cap + 1) * sizeof(double)));
         CK(h->longs.ensure((long_cap + 1) * sizeof(LongDesc)));
         CK(h->defer.ensure((defer_cap + 1) * sizeof(DeferEnt)));
         CK(h->tile_info.ensure(((size_t)n_tiles + 1) * sizeof(TileInfo)));
         CK(h->tile_base.ensure(((size_t)n_tiles + 2) * sizeof(u64)));
-        CK(h->cnt.ensure(sizeof(Counters)));
-        memset(&hc, 0, sizeof(hc));
-        hc.first_error = ~0ull;
-        hc.first_unknown = ~0ull;
-        CK(cudaMemcpyAsync(h->cnt.p, &hc, sizeof(Counters), cudaMemcpyHostToDevice, h->stream));
+        if (spec) {
+            // everything downstream is sized now, so that the kernels run back to back
+            h->cap_n = cap / 2 + cap / 4;  // the table refuses more keys than this
+            h->cap_E = edge_cap;
+            h->cap_R = h->hint_records + h->hint_records / 16 + 1024;
+            int rc = prepare_late(h, late_rows);
+            if (rc) return rc;
+        }
         ScanParams P;
         memset(&P, 0, sizeof(P));
+        h->slow_ran = false;
         if (n_tiles > 0) {
             P.text = h->d_text;
             P.nbytes = nbytes;
-            P.tkeys = h->table.as<TKey>();
-            P.tfirst = h->tfirst.as<u64>();
-            P.trep = h->trep.as<u32>();
+            P.tkeys = h->d_tkeys;
+            P.tfirst = h->d_tfirst;
+            P.trep = h->d_trep;
             P.table_mask = cap - 1;
             P.table_max_keys = (u32)(cap / 2 + cap / 4);
             P.n_tiles = n_tiles;
@@ -553,7 +690,7 @@ static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, c
             P.defer = h->defer.as<DeferEnt>();
             P.defer_cap = (u32)defer_cap;
             P.tile_info = h->tile_info.as<TileInfo>();
-            P.cnt = h->cnt.as<Counters>();
+            P.cnt = h->d_cnt;
             P.n_tiles = n_tiles;
             P.bidirected = p->bidirected ? 1 : 0;
             P.slots_per_edge = h->spe;
@@ -578,22 +715,33 @@ static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, c
             CK(cudaGetLastError());
             // (records, edge records) before every tile; the grand totals come back with the counters
             LoadTileCounts ltc{h->tile_info.as<TileInfo>()};
-            int rc = launch_scan<u64>(h, ltc, h->tile_base.as<u64>(), n_tiles);
+            int rc = launch_scan<u64>(h, ltc, h->tile_base.as<u64>(), nullptr, n_tiles, nullptr, h->d_scan_tiles);
             if (rc) return rc;
+            if (spec) {
+                if (h->hint_defer > 0) {
+                    // the previous build of this shape deferred lines: same launch, the count is read on the device
+                    { KScope ks(h, "k_tokenize_slow"); k_tokenize_slow<<<grid_for(h->hint_defer + h->hint_defer / 4 + 1024, 128), 128, 0, h->stream>>>(P); }
+                    CK(cudaGetLastError());
+                    h->slow_ran = true;
+                }
+                break;
+            }
             CK(cudaMemcpyAsync(&h->h_tail[2], h->tile_base.as<u64>() + n_tiles, sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
         } else {
+            if (spec) break;
             h->h_tail[2] = 0;
         }
         CK(cudaEventRecord(h->ev[EV_TOKENIZE], h->stream));
-        CK(cudaMemcpyAsync(&hc, h->cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(&hc, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         const u32 fatal = CF_TABLE_FULL | CF_EDGE_FULL | CF_LONG_FULL | CF_DEFER_FULL;
         if (!(hc.flags & fatal) && hc.n_defer > 0) {
             // lines the hot kernel handed over: generic byte-wise parser, one line per thread
-            { KScope ks(h, "k_tokenize_slow"); k_tokenize_slow<<<grid_for(hc.n_defer, 128), 128, 0, h->stream>>>(P, hc.n_defer); }
+            { KScope ks(h, "k_tokenize_slow"); k_tokenize_slow<<<grid_for(hc.n_defer, 128), 128, 0, h->stream>>>(P); }
             CK(cudaGetLastError());
+            h->slow_ran = true;
             CK(cudaEventRecord(h->ev[EV_TOKENIZE], h->stream));
-            CK(cudaMemcpyAsync(&hc, h->cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaMemcpyAsync(&hc, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
         }
         bool retry = false;
@@ -606,24 +754,25 @@ static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, c
         if (!retry && hc.collision) { seed = seed * 6364136223846793005ull + 1442695040888963407ull; retry = true; }
         if (!retry) break;
     }
+    SizeCaps caps;
+    caps.n_tiles = n_tiles;
+    caps.tpe = h->tpe;
+    caps.sym = h->symmax ? 1 : 0;
+    caps.slow_ran = h->slow_ran ? 1 : 0;
+    if (spec) {
+        caps.n_cap = (u32)h->cap_n; caps.E_cap = (u32)h->cap_E; caps.R_cap = (u32)h->cap_R;
+        k_sizes<<<1, 32, 0, h->stream>>>(h->d_cnt, h->tile_base.as<u64>(), caps, h->d_ds);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(h->ev[EV_TOKENIZE], h->stream));
+        return G2N_OK;
+    }
     h->hint_keys = hc.n_keys;
     h->hint_edges = hc.edge_alloc;
     h->hint_long = hc.n_long;
     h->hint_defer = hc.n_defer;
-    // ---- diagnostics: first error / first unknown record in file order
     const u64 R = h->h_tail[2] >> 32;
-    h->diag.n_records = R;
-    h->diag.n_edge_records = hc.edge_alloc;
-    h->diag.n_long_keys = hc.n_long;
-    if (hc.flags & CF_CAST_OVERFLOW) h->diag.warn_flags |= G2N_WARN_CAST_OVERFLOW;
-    if (hc.first_error != ~0ull) {
-        h->diag.err_kind = (int32_t)(hc.first_error & 0xFF);
-        h->diag.err_offset = hc.first_error >> 8;
-    }
-    if (hc.first_unknown != ~0ull && (hc.first_error == ~0ull || (hc.first_unknown >> 8) < (hc.first_error >> 8))) {
-        h->diag.unknown_byte = (int32_t)(hc.first_unknown & 0xFF);
-        h->diag.unknown_offset = hc.first_unknown >> 8;
-    }
+    h->hint_records = R;
+    collect_diag(h, hc, R);
     if (h->diag.err_kind) {
         h->diag.gpu_launches = h->launches;
         h->err = "input holds a record the reference raises on";
@@ -633,33 +782,40 @@ static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, c
     const u64 n = hc.n_keys;
     const u64 E = hc.edge_alloc;
     if (n > 0x7FFFFFFFull) { h->err = "more than 2^31-1 nodes (int64 indices) is out of scope"; return G2N_ERR_UNSUPPORTED; }
+    if (E * (u64)h->tpe * (h->symmax ? 2 : 1) >= 0xFFFFFFF0ull) { h->err = "more than 2^32 triplets in one build"; return G2N_ERR_UNSUPPORTED; }
     h->n_nodes = n;
     h->n_edges = E;
     h->n_records = R;
     h->n_long = hc.n_long;
+    h->cap_n = n;
+    h->cap_E = E;
+    h->cap_R = R;
+    caps.n_cap = (u32)n; caps.E_cap = (u32)(E > edge_cap ? E : edge_cap); caps.R_cap = (u32)R;
+    k_sizes<<<1, 32, 0, h->stream>>>(h->d_cnt, h->tile_base.as<u64>(), caps, h->d_ds);
+    CK(cudaGetLastError());
+    int rc = prepare_late(h, late_rows);
+    if (rc) return rc;
     return G2N_OK;
 }
 
-// Phase 2 on one GPU: first-appearance ranking -> node IDs (slot_id, id2slot, name lengths / offsets).
+// Phase 2 on one GPU: first-appearance ranking -> node IDs (slot_id, id2slot, name lengths).
 static int ids_phase(g2n_handle* h)
 {
-    const u64 n = h->n_nodes, R = h->n_records;
+    const u64 n = h->cap_n, R = h->cap_R;
     const u32 cap = h->table_cap;
     const u64 words = (4 * R + 31) / 32 + 1;
-    CK(h->bitmap.ensure(words * sizeof(u32)));
     CK(h->wprefix.ensure((words + 2) * sizeof(u32)));
     CK(h->slot_id.ensure((size_t)cap * sizeof(u32)));
     CK(h->id2slot.ensure((n + 1) * sizeof(u32)));
     CK(h->name_len.ensure((n + 1) * sizeof(u32)));
     CK(h->name_off.ensure((n + 2) * sizeof(u64)));
     if (n > 0) {
-        CK(cudaMemsetAsync(h->bitmap.p, 0, words * sizeof(u32), h->stream));
-        { KScope ks(h, "k_mark_first"); k_mark_first<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->table.as<TKey>(), h->tfirst.as<u64>(), cap, h->tile_base.as<u64>(), h->bitmap.as<u32>()); }
-        LoadPopc lp{h->bitmap.as<u32>()};
-        int rc = launch_scan<u32>(h, lp, h->wprefix.as<u32>(), words);
+        { KScope ks(h, "k_mark_first"); k_mark_first<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->d_tkeys, h->d_tfirst, cap, h->tile_base.as<u64>(), h->d_bitmap, h->d_ds); }
+        LoadPopc lp{h->d_bitmap};
+        int rc = launch_scan<u32>(h, lp, h->wprefix.as<u32>(), nullptr, words, &h->d_ds->words, h->d_scan_words);
         if (rc) return rc;
-        { KScope ks(h, "k_assign_ids"); k_assign_ids<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->table.as<TKey>(), h->tfirst.as<u64>(), cap, h->tile_base.as<u64>(), h->bitmap.as<u32>(), h->wprefix.as<u32>(),
-                                                                 h->slot_id.as<u32>(), h->id2slot.as<u32>(), h->name_len.as<u32>()); }
+        { KScope ks(h, "k_assign_ids"); k_assign_ids<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->d_tkeys, h->d_tfirst, cap, h->tile_base.as<u64>(), h->d_bitmap, h->wprefix.as<u32>(),
+                                                                 h->slot_id.as<u32>(), h->id2slot.as<u32>(), h->name_len.as<u32>(), h->d_ds); }
         CK(cudaGetLastError());
     }
     h->names_sized = false;  // name offsets are scanned on demand (g2n_names_bytes / g2n_fetch_names)
@@ -675,7 +831,7 @@ static int size_names(g2n_handle* h)
     const u64 n = h->n_nodes;
     if (n > 0) {
         LoadArray<u32> ln{h->name_len.as<u32>()};
-        int rc = launch_scan<u64>(h, ln, (u64*)h->name_off.as<u64>(), n);
+        int rc = launch_scan<u64>(h, ln, (u64*)h->name_off.as<u64>(), nullptr, n, nullptr, nullptr);
         if (rc) return rc;
         CK(cudaMemcpyAsync(&h->h_tail[1], h->name_off.as<u64>() + n, sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
     } else {
@@ -688,20 +844,38 @@ static int size_names(g2n_handle* h)
     return G2N_OK;
 }
 
-int g2n_build(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n_params* p)
+static int build_once(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n_params* p, bool spec)
 {
-    int rc = tokenize_phase(h, text, nbytes, p);
+    const bool graph_directed = p->keep_directed_bidir || (!p->bidirected && p->directed);
+    const bool rows = (graph_directed && !p->asymmetric) || p->want_format != G2N_FMT_NATIVE;
+    int rc = tokenize_phase(h, text, nbytes, p, spec, rows);
     if (rc) return rc;
     h->slab_mode = false;
     rc = ids_phase(h);
     if (rc) return rc;
     // ---- K3 + K4
-    if (h->symmax) rc = build_compressed(h, p->want_format == G2N_FMT_CSC ? G2N_FMT_CSC : G2N_FMT_CSR);
+    if (h->symmax) rc = build_compressed(h, p->want_format == G2N_FMT_CSC ? G2N_FMT_CSC : G2N_FMT_CSR, true);
     else if (p->want_format == G2N_FMT_NATIVE) rc = build_coo(h);
-    else rc = build_compressed(h, p->want_format);
+    else rc = build_compressed(h, p->want_format, true);
     if (rc) return rc;
-    rc = finish_result(h);
+    return finish_result(h);
+}
+
+int g2n_build(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n_params* p)
+{
+    if (!h || !p) return G2N_ERR_INVALID;
+    const int wt_len = (p->weight_tag && p->weight_tag_len > 0) ? p->weight_tag_len : 0;
+    const u64 sig = shape_signature(p, nbytes, wt_len);
+    int rc = G2N_SPEC_MISS;
+    if (h->speculate && h->hint_valid && h->hint_sig == sig && h->hint_keys > 0 && h->hint_edges > 0)
+        rc = build_once(h, text, nbytes, p, true);
+    if (rc == G2N_SPEC_MISS) {
+        h->hint_valid = false;
+        rc = build_once(h, text, nbytes, p, false);
+    }
     if (rc) return rc;
+    h->hint_sig = sig;
+    h->hint_valid = true;
     h->built = true;
     return G2N_OK;
 }
@@ -717,7 +891,10 @@ int g2n_convert(g2n_handle* h, int32_t want_format)
     CK(cudaEventRecord(h->ev[EV_H2D], h->stream));
     CK(cudaEventRecord(h->ev[EV_TOKENIZE], h->stream));
     CK(cudaEventRecord(h->ev[EV_IDS], h->stream));
-    int rc = build_compressed(h, want_format);
+    h->spec = false;
+    h->cap_n = h->n_nodes;
+    h->cap_E = h->n_edges;
+    int rc = build_compressed(h, want_format, false);
     if (rc) return rc;
     return finish_result(h);
 }
@@ -790,7 +967,7 @@ int g2n_fetch_names(g2n_handle* h, uint8_t* names, uint64_t* offsets)
     if (!h->names_ready) {
         CK(h->names.ensure(h->names_bytes + 16));
         if (h->n_nodes > 0) {
-            { KScope ks(h, "k_gather_names"); k_gather_names<<<grid_for(h->n_nodes, 256), 256, 0, h->stream>>>(h->slab_mode ? h->gtable.as<TKey>() : h->table.as<TKey>(), h->trep.as<u32>(), h->id2slot.as<u32>(), h->name_off.as<u64>(),
+            { KScope ks(h, "k_gather_names"); k_gather_names<<<grid_for(h->n_nodes, 256), 256, 0, h->stream>>>(h->slab_mode ? h->gtable.as<TKey>() : h->d_tkeys, h->d_trep, h->id2slot.as<u32>(), h->name_off.as<u64>(),
                                                                               (u32)h->n_nodes, h->d_text, h->longs.as<LongDesc>(),
                                                                               h->names.as<uint8_t>()); }
             CK(cudaGetLastError());
@@ -825,25 +1002,32 @@ int g2n_coo_to_compressed(g2n_handle* h, const int32_t* row, const int32_t* col,
     CK(cudaMemcpyAsync(h->up_row.p, row, nnz_in * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->up_col.p, col, nnz_in * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->up_data.p, data, nnz_in * ds, cudaMemcpyHostToDevice, h->stream));
-    CK(h->rowcnt.ensure((n + 2) * sizeof(u32)));
     CK(h->rowptr.ensure((n + 2) * sizeof(u32)));
+    CK(h->cursor.ensure((n + 2) * sizeof(u32)));
     CK(h->entries.ensure((nnz_in + 1) * sizeof(u64)));
-    CK(h->cnt.ensure(sizeof(Counters)));
-    CK(cudaMemsetAsync(h->rowcnt.p, 0, (n + 2) * sizeof(u32), h->stream));
+    {
+        size_t zb = 0;
+        int rc0 = layout_zearly(h, 1024, 0, &zb);  // only the control block is used here
+        if (rc0) return rc0;
+        rc0 = layout_zrows(h, n);
+        if (rc0) return rc0;
+    }
+    h->spec = false;
+    CK(cudaMemsetAsync(h->zrows.p, 0, h->zrows_bytes, h->stream));
+    k_set_sizes<<<1, 32, 0, h->stream>>>(h->d_ds, (u32)n, (u32)nnz_in);
     const int csc = want_format == G2N_FMT_CSC ? 1 : 0;
-    { KScope ks(h, "k_coo_count"); k_coo_count<<<grid_for(nnz_in, 256), 256, 0, h->stream>>>(h->up_row.as<int32_t>(), h->up_col.as<int32_t>(), nnz_in, csc, h->rowcnt.as<u32>()); }
+    { KScope ks(h, "k_coo_count"); k_coo_count<<<grid_for(nnz_in, 256), 256, 0, h->stream>>>(h->up_row.as<int32_t>(), h->up_col.as<int32_t>(), nnz_in, csc, h->d_rowcnt); }
     CK(cudaGetLastError());
-    LoadArray<u32> ldc{h->rowcnt.as<u32>()};
-    int rc = launch_scan<u32>(h, ldc, h->rowptr.as<u32>(), n);
+    LoadArray<u32> ldc{h->d_rowcnt};
+    int rc = launch_scan<u32>(h, ldc, h->rowptr.as<u32>(), h->cursor.as<u32>(), n, nullptr, h->d_scan_rows[0]);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(h->rowcnt.p, h->rowptr.p, (n + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, h->stream));  // cursors
-    { KScope ks(h, "k_coo_scatter"); k_coo_scatter<<<grid_for(nnz_in, 256), 256, 0, h->stream>>>(h->up_row.as<int32_t>(), h->up_col.as<int32_t>(), nnz_in, csc, h->rowcnt.as<u32>(), h->entries.as<u64>()); }
+    { KScope ks(h, "k_coo_scatter"); k_coo_scatter<<<grid_for(nnz_in, 256), 256, 0, h->stream>>>(h->up_row.as<int32_t>(), h->up_col.as<int32_t>(), nnz_in, csc, h->cursor.as<u32>(), h->entries.as<u64>()); }
     CK(cudaGetLastError());
     rc = rows_finalize(h, dtype, nnz_in, n, 0, nullptr, h->up_data.p);
     if (rc) return rc;
+    CK(cudaMemcpyAsync(&h->h_ctl->s, h->d_ds, sizeof(DevSizes), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    const u64 nnz = (u64)(u32)h->h_tail[3];
-    h->nnz_in_tail3 = false;
+    const u64 nnz = h->h_ctl->s.nnz;
     *nnz_out = nnz;
     CK(cudaMemcpyAsync(indptr, h->indptr.p, (n + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     if (nnz) {
@@ -861,7 +1045,7 @@ int g2n_dist_scan(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n
 {
     if (!out) return G2N_ERR_INVALID;
     if (p && p->weight_tag && p->weight_tag_len > 0) { if (h) h->err = "multi-GPU builds are unweighted in this version"; return G2N_ERR_UNSUPPORTED; }
-    int rc = tokenize_phase(h, text, nbytes, p);
+    int rc = tokenize_phase(h, text, nbytes, p, false, false);
     if (rc) return rc;
     if (h->n_long) { h->err = "multi-GPU builds need node names of <= 15 bytes (13 with --bidirected) in this version"; return G2N_ERR_UNSUPPORTED; }
     out->n_keys = h->n_nodes;
@@ -881,7 +1065,7 @@ int g2n_dist_export(g2n_handle* h, void* dev_keys, void* dev_tile_base)
     CK(cudaMemsetAsync(h->dest_cnt.p, 0, 64 * sizeof(u32), h->stream));
     if (h->n_nodes) {
         KScope ks(h, "k_dist_export");
-        k_dist_export<<<grid_for(h->table_cap, 256), 256, 0, h->stream>>>(h->table.as<TKey>(), h->tfirst.as<u64>(), h->table_cap, (DistKey*)dev_keys, h->dest_cnt.as<u32>());
+        k_dist_export<<<grid_for(h->table_cap, 256), 256, 0, h->stream>>>(h->d_tkeys, h->d_tfirst, h->table_cap, (DistKey*)dev_keys, h->dest_cnt.as<u32>());
     }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(dev_tile_base, h->tile_base.p, ((size_t)h->n_tiles + 1) * sizeof(u64), cudaMemcpyDeviceToDevice, h->stream));
@@ -905,16 +1089,13 @@ int g2n_dist_merge(g2n_handle* h, const void* dev_keys_all, uint64_t key_stride,
     CK(cudaMemsetAsync(h->gtable.p, 0, (size_t)gcap * sizeof(TKey), h->stream));
     CK(cudaMemsetAsync(h->gfirst.p, 0, (size_t)gcap * sizeof(u64), h->stream));
     Counters& hc = *h->h_cnt;
-    memset(&hc, 0, sizeof(hc));
-    hc.first_error = ~0ull;
-    hc.first_unknown = ~0ull;
-    CK(cudaMemcpyAsync(h->cnt.p, &hc, sizeof(Counters), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
     ScanParams P;
     memset(&P, 0, sizeof(P));
     P.tkeys = h->gtable.as<TKey>();
     P.tfirst = h->gfirst.as<u64>();
     P.table_mask = gcap - 1;
-    P.cnt = h->cnt.as<Counters>();
+    P.cnt = h->d_cnt;
     DistMergeParams D;
     memset(&D, 0, sizeof(D));
     D.keys = (const DistKey*)dev_keys_all;
@@ -928,7 +1109,7 @@ int g2n_dist_merge(g2n_handle* h, const void* dev_keys_all, uint64_t key_stride,
         k_dist_insert<<<grid_for(total_keys / world + 1, 256), 256, 0, h->stream>>>(P, D);
     }
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(&hc, h->cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&hc, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (hc.flags & CF_TABLE_FULL) { h->err = "global table overflow"; return G2N_ERR_INTERNAL; }
     const u64 n = hc.n_keys;
@@ -937,24 +1118,27 @@ int g2n_dist_merge(g2n_handle* h, const void* dev_keys_all, uint64_t key_stride,
     *n_global_out = n;
     // global IDs: same bitmap ranking, the order already is the bit index
     const u64 words = (4 * total_records + 31) / 32 + 1;
-    CK(h->bitmap.ensure(words * sizeof(u32)));
+    {
+        int rc0 = layout_zids(h, total_records);
+        if (rc0) return rc0;
+    }
     CK(h->wprefix.ensure((words + 2) * sizeof(u32)));
     CK(h->id2slot.ensure((n + 1) * sizeof(u32)));
     CK(h->name_len.ensure((n + 1) * sizeof(u32)));
     CK(h->name_off.ensure((n + 2) * sizeof(u64)));
     CK(h->slot_id.ensure((size_t)h->table_cap * sizeof(u32)));
     if (n > 0) {
-        CK(cudaMemsetAsync(h->bitmap.p, 0, words * sizeof(u32), h->stream));
-        { KScope ks(h, "k_dist_mark"); k_dist_mark<<<grid_for(gcap, 256), 256, 0, h->stream>>>(h->gtable.as<TKey>(), h->gfirst.as<u64>(), gcap, h->bitmap.as<u32>()); }
-        LoadPopc lp{h->bitmap.as<u32>()};
-        int rc = launch_scan<u32>(h, lp, h->wprefix.as<u32>(), words);
+        CK(cudaMemsetAsync(h->zids.p, 0, h->zids_bytes, h->stream));
+        { KScope ks(h, "k_dist_mark"); k_dist_mark<<<grid_for(gcap, 256), 256, 0, h->stream>>>(h->gtable.as<TKey>(), h->gfirst.as<u64>(), gcap, h->d_bitmap); }
+        LoadPopc lp{h->d_bitmap};
+        int rc = launch_scan<u32>(h, lp, h->wprefix.as<u32>(), nullptr, words, nullptr, h->d_scan_words);
         if (rc) return rc;
-        { KScope ks(h, "k_dist_assign"); k_dist_assign<<<grid_for(gcap, 256), 256, 0, h->stream>>>(h->gtable.as<TKey>(), h->gfirst.as<u64>(), gcap, h->bitmap.as<u32>(), h->wprefix.as<u32>(), h->gslot_id.as<u32>(), h->id2slot.as<u32>(), h->name_len.as<u32>()); }
+        { KScope ks(h, "k_dist_assign"); k_dist_assign<<<grid_for(gcap, 256), 256, 0, h->stream>>>(h->gtable.as<TKey>(), h->gfirst.as<u64>(), gcap, h->d_bitmap, h->wprefix.as<u32>(), h->gslot_id.as<u32>(), h->id2slot.as<u32>(), h->name_len.as<u32>()); }
         LoadArray<u32> ln{h->name_len.as<u32>()};
-        rc = launch_scan<u64>(h, ln, (u64*)h->name_off.as<u64>(), n);
+        rc = launch_scan<u64>(h, ln, (u64*)h->name_off.as<u64>(), nullptr, n, nullptr, nullptr);
         if (rc) return rc;
         CK(cudaMemcpyAsync(&h->h_tail[1], h->name_off.as<u64>() + n, sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
-        { KScope ks(h, "k_dist_localmap"); k_dist_localmap<<<grid_for(h->table_cap, 256), 256, 0, h->stream>>>(h->table.as<TKey>(), h->table_cap, h->gtable.as<TKey>(), gcap - 1, h->gslot_id.as<u32>(), h->slot_id.as<u32>()); }
+        { KScope ks(h, "k_dist_localmap"); k_dist_localmap<<<grid_for(h->table_cap, 256), 256, 0, h->stream>>>(h->d_tkeys, h->table_cap, h->gtable.as<TKey>(), gcap - 1, h->gslot_id.as<u32>(), h->slot_id.as<u32>()); }
         CK(cudaGetLastError());
     } else {
         CK(cudaMemsetAsync(h->name_off.p, 0, 2 * sizeof(u64), h->stream));
@@ -1019,29 +1203,34 @@ int g2n_dist_slab(g2n_handle* h, const void* dev_pairs, uint64_t n_pairs, uint64
     h->n_nodes = h->n_global;
     h->result_format = (!sym && h->params.want_format == G2N_FMT_CSC) ? G2N_FMT_CSC : G2N_FMT_CSR;
     if (n_pairs >= 0xFFFFFFF0ull) { h->err = "more than 2^32 entries in one slab"; return G2N_ERR_UNSUPPORTED; }
-    CK(h->rowcnt.ensure((n_rows + 2) * sizeof(u32)));
     CK(h->rowptr.ensure((n_rows + 2) * sizeof(u32)));
+    CK(h->cursor.ensure((n_rows + 2) * sizeof(u32)));
     CK(h->entries.ensure((n_pairs + 1) * sizeof(u64)));
-    CK(cudaMemsetAsync(h->rowcnt.p, 0, (n_rows + 2) * sizeof(u32), h->stream));
+    {
+        int rc0 = layout_zrows(h, n_rows);
+        if (rc0) return rc0;
+    }
+    h->spec = false;
+    CK(cudaMemsetAsync(h->zrows.p, 0, h->zrows_bytes, h->stream));
+    k_set_sizes<<<1, 32, 0, h->stream>>>(h->d_ds, (u32)n_rows, (u32)n_pairs);
     if (n_pairs) {
         KScope ks(h, "k_pairs_count");
-        k_pairs_count<<<grid_for(n_pairs, 256), 256, 0, h->stream>>>((const DistPair*)dev_pairs, n_pairs, (u32)row0, h->rowcnt.as<u32>());
+        k_pairs_count<<<grid_for(n_pairs, 256), 256, 0, h->stream>>>((const DistPair*)dev_pairs, n_pairs, (u32)row0, h->d_rowcnt);
     }
     CK(cudaGetLastError());
-    LoadArray<u32> ldc{h->rowcnt.as<u32>()};
-    int rc = launch_scan<u32>(h, ldc, h->rowptr.as<u32>(), n_rows);
+    LoadArray<u32> ldc{h->d_rowcnt};
+    int rc = launch_scan<u32>(h, ldc, h->rowptr.as<u32>(), h->cursor.as<u32>(), n_rows, nullptr, h->d_scan_rows[0]);
     if (rc) return rc;
     if (n_pairs) {
         KScope ks(h, "k_pairs_scatter");
-        CK(cudaMemcpyAsync(h->rowcnt.p, h->rowptr.p, (n_rows + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, h->stream));  // cursors
-        k_pairs_scatter<<<grid_for(n_pairs, 256), 256, 0, h->stream>>>((const DistPair*)dev_pairs, n_pairs, (u32)row0, h->rowcnt.as<u32>(), h->entries.as<u64>());
+        k_pairs_scatter<<<grid_for(n_pairs, 256), 256, 0, h->stream>>>((const DistPair*)dev_pairs, n_pairs, (u32)row0, h->cursor.as<u32>(), h->entries.as<u64>());
     }
     CK(cudaGetLastError());
     rc = rows_finalize(h, h->params.dtype, n_pairs, n_rows, sym, nullptr, nullptr);
     if (rc) return rc;
+    CK(cudaMemcpyAsync(&h->h_ctl->s, h->d_ds, sizeof(DevSizes), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    h->nnz = (u64)(u32)h->h_tail[3];
-    h->nnz_in_tail3 = false;
+    h->nnz = h->h_ctl->s.nnz;
     h->built = true;
     return G2N_OK;
 }

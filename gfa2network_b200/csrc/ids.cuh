@@ -19,10 +19,51 @@ __device__ __forceinline__ u32 order_bit(const u64* __restrict__ tile_base, u64 
     return (rec << 2) | (u32)(order & 3u);
 }
 
+// Capacities the host sized this build's buffers for (exact after a host round trip, learnt from the
+// previous build of the same shape otherwise).
+struct SizeCaps {
+    u32 n_cap, E_cap, R_cap;
+    u32 n_tiles;
+    int tpe, sym;
+    int slow_ran;  // k_tokenize_slow was launched (deferred lines are only legal if it was)
+};
+
+// One thread: counters -> DevSizes.  ok = 0 (and every size 0) if anything needs the host: an error
+// record, a full table / list, a hash collision, or more nodes / edges / records than the buffers hold.
+__global__ void k_sizes(const Counters* __restrict__ cnt, const u64* __restrict__ tile_base, const SizeCaps c, DevSizes* __restrict__ ds)
+{
+    if (blockIdx.x || threadIdx.x) return;
+    const u64 tot = c.n_tiles ? tile_base[c.n_tiles] : 0ull;  // records << 32 | edge records
+    const u64 R = tot >> 32, E = tot & 0xFFFFFFFFull, n = cnt->n_keys;
+    const u64 T = E * (u64)c.tpe, M = c.sym ? 2 * T : T;
+    const u32 fatal = CF_TABLE_FULL | CF_EDGE_FULL | CF_LONG_FULL | CF_DEFER_FULL;
+    bool ok = !(cnt->flags & fatal) && !cnt->collision && cnt->first_error_inv == 0;
+    ok = ok && (cnt->n_defer == 0 || c.slow_ran) && cnt->edge_alloc <= c.E_cap;
+    ok = ok && n <= c.n_cap && E <= c.E_cap && R <= c.R_cap && n <= 0x7FFFFFFFull && R < (1ull << 30) - 1 && M < 0xFFFFFFF0ull;
+    DevSizes s;
+    memset(&s, 0, sizeof(s));
+    if (ok) {
+        s.n = (u32)n; s.E = (u32)E; s.R = (u32)R; s.words = (u32)((4 * R + 31) / 32 + 1);
+        s.T = (u32)T; s.M = (u32)M; s.ok = 1; s.nnz = (u32)T; s.rows = (u32)n;
+    }
+    *ds = s;
+}
+
+// host-known sizes (slab builds, caller-provided COO): rows and entries only
+__global__ void k_set_sizes(DevSizes* __restrict__ ds, u32 rows, u32 M)
+{
+    if (blockIdx.x || threadIdx.x) return;
+    DevSizes s;
+    memset(&s, 0, sizeof(s));
+    s.n = rows; s.rows = rows; s.M = M; s.T = M; s.ok = 1;
+    *ds = s;
+}
+
 // bit (global record ordinal << 2 | sub-rank) of `bitmap` set for every occupied slot
 __global__ void __launch_bounds__(256) k_mark_first(const TKey* __restrict__ tkeys, const u64* __restrict__ tfirst, u32 cap,
-                                                     const u64* __restrict__ tile_base, u32* __restrict__ bitmap)
+                                                     const u64* __restrict__ tile_base, u32* __restrict__ bitmap, const DevSizes* __restrict__ ds)
 {
+    if (!ds->ok) return;
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
         const TKey k = tkeys[i];
         if (k.x == 0 && k.y == 0) continue;
@@ -41,8 +82,9 @@ __device__ __forceinline__ u32 slot_key_len(u64 k1)
 __global__ void __launch_bounds__(256) k_assign_ids(const TKey* __restrict__ tkeys, const u64* __restrict__ tfirst, u32 cap,
                                                      const u64* __restrict__ tile_base, const u32* __restrict__ bitmap,
                                                      const u32* __restrict__ wprefix, u32* __restrict__ slot_id,
-                                                     u32* __restrict__ id2slot, u32* __restrict__ name_len)
+                                                     u32* __restrict__ id2slot, u32* __restrict__ name_len, const DevSizes* __restrict__ ds)
 {
+    if (!ds->ok) return;
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
         const TKey k = tkeys[i];
         if (k.x == 0 && k.y == 0) continue;
@@ -111,6 +153,7 @@ struct EmitParams {
     int tpe;               // triplets per edge record: 1 (graph_directed) | 2 | 4
     int ids_ready;         // edge_slots already hold node IDs (translated in place by an earlier pass)
     int write_ids;         // translate in place during this pass
+    const DevSizes* ds;    // ds->ok == 0: the build was abandoned on the device, touch nothing
 };
 
 #define EM_UNROLL 4
@@ -124,6 +167,7 @@ __device__ __forceinline__ void for_each_edge(const EmitParams& E, F f)
 {
     const u32 lane = threadIdx.x & 31;
     const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    if (!E.ds->ok) return;
     for (u32 tile = warp; tile < E.n_tiles; tile += n_warps) {
         const TileInfo ti = E.tile_info[tile];
         if (ti.n_edge == 0) continue;

@@ -87,8 +87,9 @@ __global__ void __launch_bounds__(256) k_coo_scatter(const int32_t* __restrict__
 }
 
 // ---------------------------------------------------------------- long rows (rare)
-__global__ void __launch_bounds__(256) k_rows_find_big(const u32* __restrict__ rowptr, u32 n, u32* __restrict__ biglist, u32* __restrict__ bigcount)
+__global__ void __launch_bounds__(256) k_rows_find_big(const u32* __restrict__ rowptr, const u32* __restrict__ n_dev, u32* __restrict__ biglist, u32* __restrict__ bigcount)
 {
+    const u32 n = *n_dev;
     for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x)
         if (rowptr[r + 1] - rowptr[r] > RS_SMALL) biglist[atomicAdd(bigcount, 1u)] = r;
 }
@@ -195,11 +196,12 @@ __device__ __forceinline__ void insertion_sort(u64* a, u32 len)
 // Pass A: one warp per group of 32 consecutive rows, one lane per row: sort the row (staged in shared
 // memory when the group fits), write it back, count the entries it will store.
 template <typename T>
-__global__ void __launch_bounds__(RS_WARPS * 32) k_rows_sort(const u32* __restrict__ rowptr, u64* __restrict__ entries, u32 n, int sym,
+__global__ void __launch_bounds__(RS_WARPS * 32) k_rows_sort(const u32* __restrict__ rowptr, u64* __restrict__ entries, const u32* __restrict__ n_dev, int sym,
                                                               const double* __restrict__ w_emit, const T* __restrict__ w_typed,
                                                               u32* __restrict__ ucnt)
 {
     __shared__ u64 s_ent[RS_WARPS][RS_GROUP_CAP];
+    const u32 n = *n_dev;
     const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     u64* sm = s_ent[wid];
     const u32 n_groups = (n + 31) / 32;
@@ -235,10 +237,13 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_rows_sort(const u32* __restri
 
 // Pass B: indptr is known; one lane per row walks its sorted entries and writes indices / data.
 template <typename T>
-__global__ void __launch_bounds__(256) k_rows_write(const u32* __restrict__ rowptr, const u64* __restrict__ entries, u32 n, int sym,
+__global__ void __launch_bounds__(256) k_rows_write(const u32* __restrict__ rowptr, const u64* __restrict__ entries, const u32* __restrict__ n_dev, int sym,
                                                      const double* __restrict__ w_emit, const T* __restrict__ w_typed,
-                                                     const int32_t* __restrict__ indptr, int32_t* __restrict__ indices, T* __restrict__ data)
+                                                     const int32_t* __restrict__ indptr, int32_t* __restrict__ indices, T* __restrict__ data,
+                                                     u32* __restrict__ nnz_out)
 {
+    const u32 n = *n_dev;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *nnz_out = (u32)indptr[n];
     for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
         const u32 lo = rowptr[r], len = rowptr[r + 1] - lo;
         const u32 out0 = (u32)indptr[r];

@@ -60,9 +60,9 @@ struct LongDesc {
     u32 has_ori;   // 1: key is base + ':' + ori
 };
 
-struct Counters {
-    u64 first_error;    // min (line_offset << 8 | kind); ~0 if none
-    u64 first_unknown;  // min (line_offset << 8 | first byte); ~0 if none
+struct Counters {  // all-zero at the start of a build (one memset)
+    u64 first_error_inv;    // max ~(line_offset << 8 | kind): the FIRST offending line; 0 if none
+    u64 first_unknown_inv;  // max ~(line_offset << 8 | first byte); 0 if none
     u32 n_records;
     u32 n_edges;
     u32 n_keys;
@@ -77,6 +77,25 @@ struct Counters {
     u64 aux[4];
     u64 phase[8];  // -DTK_TIMING: clock64() cycles per kernel phase, summed over CTAs (thread 0 view)
 };
+// Sizes of the current build, resident in device memory so that no kernel after the tokenizer needs a
+// host round trip: k_sizes (ids.cuh) derives them from the counters, later kernels read what they need.
+struct DevSizes {
+    u32 n;      // nodes
+    u32 E;      // edge records
+    u32 R;      // records (S L E C P O)
+    u32 words;  // 32-bit words of the first-appearance bitmap (4 bits per record)
+    u32 T;      // triplets
+    u32 M;      // row entries (T, or 2T for max(S, S^T))
+    u32 ok;     // 0: a capacity was exceeded or the host has to look at the input: later kernels do nothing
+    u32 nnz;    // stored entries of the result (written by the last kernel of the build)
+    u32 rows;   // rows of the matrix this GPU builds (n, or the rows of its slab)
+    u32 pad[7];
+};
+struct Ctl {
+    Counters c;
+    DevSizes s;
+};
+
 #define CF_TABLE_FULL 1u
 #define CF_EDGE_FULL 2u
 #define CF_LONG_FULL 4u

@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, TK_MIN_BLOCKS) k_tokenize(const
                 if (c0 == 'L' || c0 == 'E' || c0 == 'C') edg |= 1ull << bit;
             } else if (!known && c0 != 'H' && c0 != 'F') {
                 const u64 val = ((wbase + off) << 8) | c0;
-                if (val < ld_volatile_u64(&P.cnt->first_unknown)) atomicMin(&P.cnt->first_unknown, val);
+                if (~val > ld_volatile_u64(&P.cnt->first_unknown_inv)) atomicMax(&P.cnt->first_unknown_inv, ~val);
             }
         }
         // ---- warp scan of (records, edges): index of my first record / edge inside the tile

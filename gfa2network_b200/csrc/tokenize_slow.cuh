@@ -120,7 +120,7 @@ __device__ __noinline__ bool int_probe(const Win w, const Span f)
 __device__ __forceinline__ void report_error(Counters* cnt, u64 line_off, int kind)
 {
     const u64 v = (line_off << 8) | (u64)kind;
-    if (v < ld_volatile_u64(&cnt->first_error)) atomicMin(&cnt->first_error, v);
+    if (~v > ld_volatile_u64(&cnt->first_error_inv)) atomicMax(&cnt->first_error_inv, ~v);
 }
 
 struct EdgeParse {
@@ -271,8 +271,9 @@ __device__ __forceinline__ void parse_line_body(const ScanParams& P, const Win& 
 }
 
 // One deferred line per thread.
-__global__ void __launch_bounds__(128) k_tokenize_slow(const __grid_constant__ ScanParams P, u32 n_defer)
+__global__ void __launch_bounds__(128) k_tokenize_slow(const __grid_constant__ ScanParams P)
 {
+    const u32 n_defer = min(P.cnt->n_defer, P.defer_cap);  // nobody appends while this kernel runs
     u32 claimed = 0;
     Win w{nullptr, P.text, 0, P.nbytes, 0};
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_defer; i += gridDim.x * blockDim.x) {

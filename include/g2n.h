@@ -106,7 +106,8 @@ typedef struct g2n_diag {
     float ms_h2d;            /* host->device copy of the text (0 when text_on_device) */
     float ms_stage[8];       /* scan+hash, ids, names, emit, sort, reduce, (spare) */
     uint32_t warn_flags;     /* G2N_WARN_* */
-    uint32_t reserved;
+    uint32_t speculative;    /* 1: the build ran without a host round trip after the tokenizer (buffers
+                                sized from the previous build of the same input size and mode) */
 } g2n_diag;
 
 #define G2N_WARN_CAST_OVERFLOW 1u /* a finite float64 weight became inf in the float32 cast: NumPy's
@@ -161,6 +162,13 @@ typedef struct g2n_ktime {
     uint32_t launches;
 } g2n_ktime;
 int g2n_set_profile(g2n_handle *h, int on);
+
+/* A handle remembers the sizes (nodes, records, edge records) of its last build.  A build of the same
+ * input size and mode then runs speculatively: every buffer is sized up front, size-dependent kernels
+ * read the actual sizes from device memory, and the host synchronises once, at the end; if the sizes
+ * do not fit the build is repeated with the usual host round trip after the tokenizer.  The result
+ * is identical either way.  On by default; g2n_set_speculation(h, 0) turns it off. */
+int g2n_set_speculation(g2n_handle *h, int on);
 int g2n_kernel_times(g2n_handle *h, g2n_ktime *out, int cap);
 
 int g2n_status(g2n_handle *h, g2n_diag *out);

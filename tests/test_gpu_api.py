@@ -152,3 +152,46 @@ def test_inexact_float_weights_within_stated_tolerance():
             short = raw_per_row[rows] <= 16
             assert short.sum() > 0.9 * len(rows)
             assert np.array_equal(A.data[short], B.data[short])
+
+
+def test_speculative_builds_hit_and_miss():
+    """A repeat build of the same input size and mode skips the host round trip after the tokenizer
+    (g2n_set_speculation); a same-sized input that does not fit the learnt sizes, or that holds an
+    error record, falls back to the host-checked path.  Results are identical either way."""
+    from gfa2network_b200 import _capi, parse_gfa
+    from gfa2network_b200.synth import synth_gfa
+    from oracle.oracle import oracle_parse_gfa
+
+    h = _capi.default_handle(0)
+    a = bytes(synth_gfa(20_000, 60_000, seed=31, kind=1, n_paths=1, n_walks=1))
+    line = b"L\ta\t+\tb\t+\n"
+    b = (line * (len(a) // len(line) + 1))[: len(a) - len(a) % len(line)]
+    b = b + b"#" * (len(a) - len(b) - 1) + b"\n" if len(a) - len(b) >= 1 else b  # same size, 3x the edge records
+    assert len(b) == len(a)
+    bad = bytearray(a)
+    pos = a.index(b"\nL\t", len(a) // 2)  # a link in the middle of the file loses its fields
+    end = a.index(b"\n", pos + 1)
+    bad[pos + 1:end] = b"L\tx" + b" " * (end - pos - 4)
+    bad = bytes(bad)
+    for mode in (dict(), dict(directed=False), dict(bidirected=True)):
+        want, wnodes = oracle_parse_gfa(a, return_node_list=True, **mode)
+        wantb = oracle_parse_gfa(b, **mode)
+        flags = []
+        for text, exp in ((a, want), (a, want), (a, want), (b, wantb), (b, wantb), (a, want), (a, want)):
+            A, nodes = parse_gfa(text, build_graph=False, build_matrix=True, return_node_list=True, **mode)
+            flags.append(int(h.status().speculative))
+            _same(A, exp, str(mode))
+            if text is a:
+                assert nodes == wnodes
+        assert flags[1:3] == [1, 1] and flags[3] == 0 and flags[4] == 1 and flags[5] == 0 and flags[6] == 1, flags
+        with pytest.raises(ValueError, match="Malformed L record"):
+            parse_gfa(bad, build_graph=False, build_matrix=True, **mode)
+        A = parse_gfa(a, build_graph=False, build_matrix=True, **mode)
+        _same(A, want, str(mode))
+    h.set_speculation(False)
+    try:
+        for _ in range(2):
+            _same(parse_gfa(a, build_graph=False, build_matrix=True), oracle_parse_gfa(a))
+            assert h.status().speculative == 0
+    finally:
+        h.set_speculation(True)
