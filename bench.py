@@ -158,14 +158,14 @@ def workload_name(cfg_name, scale, n_seg, n_link, cfg):
 # algorithmic bytes per launch of each kernel: compulsory reads + writes only
 def algo_bytes(name, st):
     N, E, spe, M, n, nnz, weighted, world = (st[k] for k in ("N", "E", "spe", "M", "n", "nnz", "weighted", "world"))
+    ent = 8 if weighted else 4  # bytes per row entry (rowsort.cuh: Ent64 / Ent32)
     table = {
         "k_tokenize": N + 4 * spe * E + (8 * E if weighted else 0),
         "k_mark_first": 24 * 2 * n,
         "k_assign_ids": 24 * 2 * n + 12 * n,
         "k_rows_count": 2 * 4 * spe * E + 4 * M + (16 * E if weighted else 0),
-        "k_rows_scatter": 4 * spe * E + 12 * M,
-        "k_rows_sort": 16 * M + 4 * n,
-        "k_rows_write": 8 * M + 12 * nnz + 8 * n,
+        "k_rows_scatter": 4 * spe * E + 4 * M + ent * M,           # ids in, cursors, entries out
+        "k_rows_finish": ent * M + 8 * n + 12 * nnz,               # entries in, rowptr in, indptr/indices/data out
         "k_emit_coo": 4 * spe * E + 16 * M,
         "k_dist_insert": 32 * n,            # n = global nodes: every rank inserts every rank's distinct keys
         "k_dist_dest_count": 2 * 4 * spe * E,

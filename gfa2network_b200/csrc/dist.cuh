@@ -178,12 +178,13 @@ __global__ void __launch_bounds__(256) k_pairs_count(const DistPair* __restrict_
         atomicAdd(&cnt[(u32)pairs[i].major - row0], 1u);
 }
 
+// multi-GPU builds are unweighted: the slab keeps 32-bit entries (minor << 1 | dir), see Ent32
 __global__ void __launch_bounds__(256) k_pairs_scatter(const DistPair* __restrict__ pairs, u64 n, u32 row0, u32* __restrict__ cursor,
-                                                        u64* __restrict__ entries)
+                                                        u32* __restrict__ entries)
 {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
         const DistPair p = pairs[i];
-        entries[atomicAdd(&cursor[(u32)p.major - row0], 1u)] = p.entry;
+        entries[atomicAdd(&cursor[(u32)p.major - row0], 1u)] = (u32)(p.entry >> 32);
     }
 }
 

@@ -3,7 +3,7 @@
 //   K1  k_tokenize        line scan + field split + node-key hashing + edge-record emission (tokenize.cuh)
 //   K2  k_mark_first / k_assign_ids / k_gather_names   first-appearance ranking -> node IDs   (ids.cuh)
 //   K3  k_emit_coo | k_emit_keys                        COO triplets / sort keys               (ids.cuh)
-//   K4  k_rows_count / k_rows_scatter / k_rows_big / k_rows_sort / k_rows_write   row bucketing + dedup/sum (+max) (rowsort.cuh)
+//   K4  k_rows_count / k_rows_scatter / k_rows_big / k_rows_finish   row bucketing + in-row sort + dedup/sum (+max) (rowsort.cuh)
 // No CPU fallback exists: every entry point needs a CUDA device.
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -60,7 +60,7 @@ struct g2n_handle {
     cudaEvent_t ev[EV_COUNT];
     // device buffers (kept between builds: a warm handle allocates nothing)
     DevBuf text, defer, edge_slots, edge_w, longs, tile_info, tile_base, wprefix, slot_id, id2slot, name_len, name_off, names;
-    DevBuf rowptr, cursor, entries, w_emit, biglist, ucnt, indptr, indices, data, row, col, scan_state;
+    DevBuf rowptr, cursor, entries, w_emit, biglist, indptr, indices, data, row, col, scan_state;
     DevBuf up_row, up_col, up_data;
     // zero-initialised state, one memset per arena and build:
     //   zearly  hash table (keys | first | rep), counters + DevSizes, look-back state of the tile scan
@@ -206,13 +206,14 @@ int layout_zrows(g2n_handle* h, u64 n_cap)
     const size_t a = ((n_cap + 2) * sizeof(u32) + 255) & ~(size_t)255;
     const size_t b = 256;
     const size_t c = (scan_state_bytes(n_cap) + 255) & ~(size_t)255;
-    CK(h->zrows.ensure(a + b + 2 * c));
+    const size_t d = (((n_cap + RF_ROWS - 1) / RF_ROWS + 3) * sizeof(u64) + 255) & ~(size_t)255;  // one word per k_rows_finish chunk
+    CK(h->zrows.ensure(a + b + c + d));
     uint8_t* base = h->zrows.as<uint8_t>();
     h->d_rowcnt = (u32*)base;
     h->d_bigcount = (u32*)(base + a);
     h->d_scan_rows[0] = (u64*)(base + a + b);
     h->d_scan_rows[1] = (u64*)(base + a + b + c);
-    h->zrows_bytes = a + b + 2 * c;
+    h->zrows_bytes = a + b + c + d;
     return G2N_OK;
 }
 
@@ -226,41 +227,49 @@ size_t dtype_size(int dt)
     }
 }
 
-// rowptr (u32, rows+1) and entries (u64, M) are ready: sort every row, sum duplicates, write the result.
-// M and n are host-side bounds (exact or capacities); the kernels read the actual row count from DevSizes.
-template <typename T>
+// rowptr (u32, rows+1) and entries (ENT, M) are ready, long rows are listed: sort every row, sum
+// duplicates, write the result.  M and n are host-side bounds (exact or capacities); the kernels read the
+// actual row count from DevSizes.
+template <typename T, class ENT>
 int rows_finalize_typed(g2n_handle* h, u64 M, u64 n, int sym, const double* w_emit, const T* w_typed)
 {
+    typedef typename ENT::type E;
     const u32* n_dev = &h->d_ds->rows;
     CK(h->indptr.ensure((n + 2) * sizeof(int32_t)));
     CK(h->indices.ensure((M + 1) * sizeof(int32_t)));
     CK(h->data.ensure((M + 1) * sizeof(T)));
-    CK(h->biglist.ensure((n + 2) * sizeof(u32)));
-    { KScope ks(h, "k_rows_find_big"); k_rows_find_big<<<grid_for(n, 256), 256, 0, h->stream>>>(h->rowptr.as<u32>(), n_dev, h->biglist.as<u32>(), h->d_bigcount); }
-    { KScope ks(h, "k_rows_big"); k_rows_big<<<G2N_SM_COUNT, 256, 0, h->stream>>>(h->rowptr.as<u32>(), h->biglist.as<u32>(), h->d_bigcount, h->entries.as<u64>()); }
-    const u64 n_groups = (n + 31) / 32;
-    CK(h->ucnt.ensure((n + 2) * sizeof(u32)));
-    { KScope ks(h, "k_rows_sort"); k_rows_sort<T><<<grid_for(n_groups, RS_WARPS, 12), RS_WARPS * 32, 0, h->stream>>>(h->rowptr.as<u32>(), h->entries.as<u64>(), n_dev, sym, w_emit, w_typed, h->ucnt.as<u32>()); }
-    CK(cudaGetLastError());
-    LoadArray<u32> ldu{h->ucnt.as<u32>()};
-    int rc = launch_scan<int32_t>(h, ldu, h->indptr.as<int32_t>(), nullptr, n, n_dev, h->d_scan_rows[1]);
-    if (rc) return rc;
-    { KScope ks(h, "k_rows_write"); k_rows_write<T><<<grid_for(n, 256), 256, 0, h->stream>>>(h->rowptr.as<u32>(), h->entries.as<u64>(), n_dev, sym, w_emit, w_typed, h->indptr.as<int32_t>(), h->indices.as<int32_t>(), h->data.as<T>(), &h->d_ds->nnz); }
+    { KScope ks(h, "k_rows_big"); k_rows_big<ENT><<<G2N_SM_COUNT, 256, 0, h->stream>>>(h->rowptr.as<u32>(), h->biglist.as<u32>(), h->d_bigcount, h->entries.as<E>()); }
+    const u64 n_chunks = (n + RF_ROWS - 1) / RF_ROWS;
+    u64* state = h->d_scan_rows[1];
+    { KScope ks(h, "k_rows_finish"); k_rows_finish<T, ENT><<<grid_for(n_chunks, 1, 6), RF_ROWS, 0, h->stream>>>(h->rowptr.as<u32>(), h->entries.as<E>(), n_dev, sym, w_emit, w_typed, h->indptr.as<int32_t>(), h->indices.as<int32_t>(), h->data.as<T>(), state + 1, (u32*)state, &h->d_ds->nnz); }
     CK(cudaGetLastError());
     return G2N_OK;
 }
 
-int rows_finalize(g2n_handle* h, int dtype, u64 M, u64 n, int sym, const double* w_emit, const void* w_typed)
+// weighted: 64-bit entries that carry the emission index; unweighted: 32-bit entries
+int rows_finalize(g2n_handle* h, int dtype, bool weighted, u64 M, u64 n, int sym, const double* w_emit, const void* w_typed)
 {
+#define G2N_FIN(T) (weighted ? rows_finalize_typed<T, Ent64>(h, M, n, sym, w_emit, (const T*)w_typed) : rows_finalize_typed<T, Ent32>(h, M, n, sym, nullptr, nullptr))
     switch (dtype) {
-        case G2N_DTYPE_F64: return rows_finalize_typed<double>(h, M, n, sym, w_emit, (const double*)w_typed);
-        case G2N_DTYPE_F32: return rows_finalize_typed<float>(h, M, n, sym, w_emit, (const float*)w_typed);
-        case G2N_DTYPE_I32: return rows_finalize_typed<int32_t>(h, M, n, sym, w_emit, (const int32_t*)w_typed);
-        case G2N_DTYPE_I8: return rows_finalize_typed<int8_t>(h, M, n, sym, w_emit, (const int8_t*)w_typed);
-        case G2N_DTYPE_BOOL: return rows_finalize_typed<BoolT>(h, M, n, sym, w_emit, (const BoolT*)w_typed);
+        case G2N_DTYPE_F64: return G2N_FIN(double);
+        case G2N_DTYPE_F32: return G2N_FIN(float);
+        case G2N_DTYPE_I32: return G2N_FIN(int32_t);
+        case G2N_DTYPE_I8: return G2N_FIN(int8_t);
+        case G2N_DTYPE_BOOL: return G2N_FIN(BoolT);
     }
+#undef G2N_FIN
     h->err = "unknown dtype";
     return G2N_ERR_INVALID;
+}
+
+// rowcnt -> rowptr + cursors; rows longer than RS_SMALL are listed on the way
+int rows_scan(g2n_handle* h, u64 n_cap, const u32* n_dev)
+{
+    CK(h->rowptr.ensure((n_cap + 2) * sizeof(u32)));
+    CK(h->cursor.ensure((n_cap + 2) * sizeof(u32)));
+    CK(h->biglist.ensure((n_cap + 2) * sizeof(u32)));
+    LoadRowCounts ldc{h->d_rowcnt, h->biglist.as<u32>(), h->d_bigcount};
+    return launch_scan<u32>(h, ldc, h->rowptr.as<u32>(), h->cursor.as<u32>(), n_cap, n_dev, h->d_scan_rows[0]);
 }
 
 struct LoadTileCounts {
@@ -305,9 +314,7 @@ int build_compressed(g2n_handle* h, int fmt, bool zeroed)
         if (rc) return rc;
         CK(cudaMemsetAsync(h->zrows.p, 0, h->zrows_bytes, h->stream));
     }
-    CK(h->rowptr.ensure((n + 2) * sizeof(u32)));
-    CK(h->cursor.ensure((n + 2) * sizeof(u32)));
-    CK(h->entries.ensure((M + 1) * sizeof(u64)));
+    CK(h->entries.ensure((M + 1) * (weighted ? sizeof(u64) : sizeof(u32))));
     if (weighted) CK(h->w_emit.ensure((T + 1) * sizeof(double)));
     EmitParams E = emit_params(h);
     E.write_ids = 1;  // the count pass leaves node IDs in edge_slots for the scatter pass (and later converts)
@@ -317,14 +324,17 @@ int build_compressed(g2n_handle* h, int fmt, bool zeroed)
     h->edges_are_ids = true;
     E.ids_ready = 1;
     E.write_ids = 0;
-    LoadArray<u32> ldc{h->d_rowcnt};
-    int rc = launch_scan<u32>(h, ldc, h->rowptr.as<u32>(), h->cursor.as<u32>(), n, &h->d_ds->rows, h->d_scan_rows[0]);  // rowptr + cursors
+    int rc = rows_scan(h, n, &h->d_ds->rows);
     if (rc) return rc;
     CK(cudaEventRecord(h->ev[EV_EMIT], h->stream));
-    { KScope ks(h, "k_rows_scatter"); k_rows_scatter<<<egrid, 256, 0, h->stream>>>(E, sym, csc, h->cursor.as<u32>(), h->entries.as<u64>()); }
+    {
+        KScope ks(h, "k_rows_scatter");
+        if (weighted) k_rows_scatter<Ent64><<<egrid, 256, 0, h->stream>>>(E, sym, csc, h->cursor.as<u32>(), h->entries.as<u64>());
+        else k_rows_scatter<Ent32><<<egrid, 256, 0, h->stream>>>(E, sym, csc, h->cursor.as<u32>(), h->entries.as<u32>());
+    }
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev[EV_SORT], h->stream));
-    rc = rows_finalize(h, h->params.dtype, M, n, sym, weighted ? h->w_emit.as<double>() : nullptr, nullptr);
+    rc = rows_finalize(h, h->params.dtype, weighted, M, n, sym, weighted ? h->w_emit.as<double>() : nullptr, nullptr);
     if (rc) return rc;
     CK(cudaEventRecord(h->ev[EV_REDUCE], h->stream));
     return G2N_OK;
@@ -452,7 +462,7 @@ void g2n_destroy(g2n_handle* h)
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->text, &h->zearly, &h->zids, &h->zrows, &h->defer, &h->edge_slots, &h->edge_w, &h->longs, &h->tile_info, &h->tile_base, &h->wprefix,
-                      &h->slot_id, &h->id2slot, &h->name_len, &h->name_off, &h->names, &h->rowptr, &h->cursor, &h->entries, &h->w_emit, &h->biglist, &h->ucnt, &h->indptr, &h->indices, &h->data, &h->row, &h->col,
+                      &h->slot_id, &h->id2slot, &h->name_len, &h->name_off, &h->names, &h->rowptr, &h->cursor, &h->entries, &h->w_emit, &h->biglist, &h->indptr, &h->indices, &h->data, &h->row, &h->col,
                       &h->scan_state, &h->up_row, &h->up_col, &h->up_data, &h->gtable, &h->gfirst, &h->gslot_id, &h->dest_cnt};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(h->ev[i]);
@@ -1002,8 +1012,6 @@ int g2n_coo_to_compressed(g2n_handle* h, const int32_t* row, const int32_t* col,
     CK(cudaMemcpyAsync(h->up_row.p, row, nnz_in * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->up_col.p, col, nnz_in * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->up_data.p, data, nnz_in * ds, cudaMemcpyHostToDevice, h->stream));
-    CK(h->rowptr.ensure((n + 2) * sizeof(u32)));
-    CK(h->cursor.ensure((n + 2) * sizeof(u32)));
     CK(h->entries.ensure((nnz_in + 1) * sizeof(u64)));
     {
         size_t zb = 0;
@@ -1018,12 +1026,11 @@ int g2n_coo_to_compressed(g2n_handle* h, const int32_t* row, const int32_t* col,
     const int csc = want_format == G2N_FMT_CSC ? 1 : 0;
     { KScope ks(h, "k_coo_count"); k_coo_count<<<grid_for(nnz_in, 256), 256, 0, h->stream>>>(h->up_row.as<int32_t>(), h->up_col.as<int32_t>(), nnz_in, csc, h->d_rowcnt); }
     CK(cudaGetLastError());
-    LoadArray<u32> ldc{h->d_rowcnt};
-    int rc = launch_scan<u32>(h, ldc, h->rowptr.as<u32>(), h->cursor.as<u32>(), n, nullptr, h->d_scan_rows[0]);
+    int rc = rows_scan(h, n, nullptr);
     if (rc) return rc;
     { KScope ks(h, "k_coo_scatter"); k_coo_scatter<<<grid_for(nnz_in, 256), 256, 0, h->stream>>>(h->up_row.as<int32_t>(), h->up_col.as<int32_t>(), nnz_in, csc, h->cursor.as<u32>(), h->entries.as<u64>()); }
     CK(cudaGetLastError());
-    rc = rows_finalize(h, dtype, nnz_in, n, 0, nullptr, h->up_data.p);
+    rc = rows_finalize(h, dtype, true, nnz_in, n, 0, nullptr, h->up_data.p);
     if (rc) return rc;
     CK(cudaMemcpyAsync(&h->h_ctl->s, h->d_ds, sizeof(DevSizes), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -1203,9 +1210,7 @@ int g2n_dist_slab(g2n_handle* h, const void* dev_pairs, uint64_t n_pairs, uint64
     h->n_nodes = h->n_global;
     h->result_format = (!sym && h->params.want_format == G2N_FMT_CSC) ? G2N_FMT_CSC : G2N_FMT_CSR;
     if (n_pairs >= 0xFFFFFFF0ull) { h->err = "more than 2^32 entries in one slab"; return G2N_ERR_UNSUPPORTED; }
-    CK(h->rowptr.ensure((n_rows + 2) * sizeof(u32)));
-    CK(h->cursor.ensure((n_rows + 2) * sizeof(u32)));
-    CK(h->entries.ensure((n_pairs + 1) * sizeof(u64)));
+    CK(h->entries.ensure((n_pairs + 1) * sizeof(u32)));
     {
         int rc0 = layout_zrows(h, n_rows);
         if (rc0) return rc0;
@@ -1218,15 +1223,14 @@ int g2n_dist_slab(g2n_handle* h, const void* dev_pairs, uint64_t n_pairs, uint64
         k_pairs_count<<<grid_for(n_pairs, 256), 256, 0, h->stream>>>((const DistPair*)dev_pairs, n_pairs, (u32)row0, h->d_rowcnt);
     }
     CK(cudaGetLastError());
-    LoadArray<u32> ldc{h->d_rowcnt};
-    int rc = launch_scan<u32>(h, ldc, h->rowptr.as<u32>(), h->cursor.as<u32>(), n_rows, nullptr, h->d_scan_rows[0]);
+    int rc = rows_scan(h, n_rows, nullptr);
     if (rc) return rc;
     if (n_pairs) {
         KScope ks(h, "k_pairs_scatter");
-        k_pairs_scatter<<<grid_for(n_pairs, 256), 256, 0, h->stream>>>((const DistPair*)dev_pairs, n_pairs, (u32)row0, h->cursor.as<u32>(), h->entries.as<u64>());
+        k_pairs_scatter<<<grid_for(n_pairs, 256), 256, 0, h->stream>>>((const DistPair*)dev_pairs, n_pairs, (u32)row0, h->cursor.as<u32>(), h->entries.as<u32>());
     }
     CK(cudaGetLastError());
-    rc = rows_finalize(h, h->params.dtype, n_pairs, n_rows, sym, nullptr, nullptr);
+    rc = rows_finalize(h, h->params.dtype, false, n_pairs, n_rows, sym, nullptr, nullptr);
     if (rc) return rc;
     CK(cudaMemcpyAsync(&h->h_ctl->s, h->d_ds, sizeof(DevSizes), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));

@@ -3,16 +3,18 @@
 // Adjacency rows of sequence graphs are tiny (a handful of links per segment), so instead of a global
 // radix sort of (row, col) keys the build is a counting sort by row followed by an in-row sort:
 //   k_rows_count     one atomic per triplet into cnt[major]                       (histogram)
-//   exclusive scan   cnt -> rowptr                                                (common.cuh)
-//   k_rows_scatter   entry (minor, dir, emission index) -> atomicAdd(cursor[major]) (any order inside a row)
+//   exclusive scan   cnt -> rowptr + cursors; rows longer than RS_SMALL are listed on the way (common.cuh)
+//   k_rows_scatter   entry (minor, dir[, emission index]) -> atomicAdd(cursor[major]) (any order inside a row)
 //   k_rows_big       rows longer than RS_SMALL are sorted in place by a whole CTA (bitonic; rare)
-//   k_rows_sort      one lane per row: insertion sort by (minor, dir, emission index) in shared memory,
-//                    count of the entries the row will store (duplicates summed, zeros of max() dropped)
-//   exclusive scan   counts -> indptr
-//   k_rows_write     one lane per row: left-to-right duplicate sum, optional max(S, S^T), output
-// No kernel waits on another CTA; the sorted order inside a row is total (the emission
-// index breaks ties), so the result is deterministic and duplicate weights are summed in emission
-// order exactly like SciPy does for rows of <= 16 stored entries.
+//   k_rows_finish    one CTA per chunk of RF_ROWS consecutive rows, one lane per row: the chunk's entries
+//                    are staged in shared memory (one coalesced read), every row is insertion-sorted and
+//                    walked (duplicates summed left to right, max(S, S^T), zeros dropped), the chunk's
+//                    output offset comes from a decoupled look-back over the chunk totals, and indptr /
+//                    indices / data are written -- sort, count, scan and write in ONE pass over the entries
+// An entry is 64 bits (minor << 33 | dir << 32 | emission index) when weights exist -- the emission
+// index finds the weight and makes the order inside a row total, so duplicate weights are summed in
+// emission order exactly like SciPy does for rows of <= 16 stored entries -- and 32
+// bits (minor << 1 | dir) for unweighted builds, where every weight is 1 and only counts matter.
 //
 // Replaces the SciPy C++ the reference reaches through
 //   builders.py:283   out_mat.maximum(out_mat.T)  -> coo_tocsr, csr_sort_indices, csr_sum_duplicates, csr_maximum_csr
@@ -31,6 +33,23 @@ __device__ __forceinline__ u64 rs_entry(u32 minor, u32 dir, u32 t) { return ((u6
 __device__ __forceinline__ u32 rs_minor(u64 e) { return (u32)(e >> 33); }
 __device__ __forceinline__ u32 rs_dir(u64 e) { return (u32)(e >> 32) & 1u; }
 __device__ __forceinline__ u32 rs_t(u64 e) { return (u32)e; }
+
+struct Ent64 {  // weighted builds
+    typedef u64 type;
+    static constexpr bool kWeighted = true;
+    static __device__ __forceinline__ u64 make(u32 minor, u32 dir, u32 t) { return rs_entry(minor, dir, t); }
+    static __device__ __forceinline__ u32 minor(u64 e) { return rs_minor(e); }
+    static __device__ __forceinline__ u32 dir(u64 e) { return rs_dir(e); }
+    static __device__ __forceinline__ u32 t(u64 e) { return rs_t(e); }
+};
+struct Ent32 {  // unweighted builds: every weight is 1.0, node IDs are below 2^31
+    typedef u32 type;
+    static constexpr bool kWeighted = false;
+    static __device__ __forceinline__ u32 make(u32 minor, u32 dir, u32) { return (minor << 1) | dir; }
+    static __device__ __forceinline__ u32 minor(u32 e) { return e >> 1; }
+    static __device__ __forceinline__ u32 dir(u32 e) { return e & 1u; }
+    static __device__ __forceinline__ u32 t(u32) { return 0; }
+};
 
 // Entries of one edge record:  g(major, minor, dir, t)
 //   sym == 0: one entry per triplet, major = row (CSR) or col (CSC)
@@ -62,11 +81,12 @@ __global__ void __launch_bounds__(256) k_rows_count(const EmitParams E, int sym,
 
 // cursor[major] starts at rowptr[major]; one atomicAdd hands out the entry's position inside the row's
 // range (order inside the range is arbitrary; the in-row sort restores a total order)
-__global__ void __launch_bounds__(256) k_rows_scatter(const EmitParams E, int sym, int csc, u32* __restrict__ cursor, u64* __restrict__ entries)
+template <class ENT>
+__global__ void __launch_bounds__(256) k_rows_scatter(const EmitParams E, int sym, int csc, u32* __restrict__ cursor, typename ENT::type* __restrict__ entries)
 {
     for_each_edge(E, [&](u32, u32 t0, const u32 (&id)[4]) {
         record_entries(id, E.tpe, t0, sym, csc, [&](u32 major, u32 minor, u32 dir, u32 t) {
-            entries[atomicAdd(&cursor[major], 1u)] = rs_entry(minor, dir, t);
+            entries[atomicAdd(&cursor[major], 1u)] = ENT::make(minor, dir, t);
         });
     });
 }
@@ -87,26 +107,34 @@ __global__ void __launch_bounds__(256) k_coo_scatter(const int32_t* __restrict__
 }
 
 // ---------------------------------------------------------------- long rows (rare)
-__global__ void __launch_bounds__(256) k_rows_find_big(const u32* __restrict__ rowptr, const u32* __restrict__ n_dev, u32* __restrict__ biglist, u32* __restrict__ bigcount)
-{
-    const u32 n = *n_dev;
-    for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x)
-        if (rowptr[r + 1] - rowptr[r] > RS_SMALL) biglist[atomicAdd(bigcount, 1u)] = r;
-}
+// Load functor of the rowptr scan: lists the rows longer than RS_SMALL while the counts stream by.
+struct LoadRowCounts {
+    const u32* cnt;
+    u32* biglist;
+    u32* bigcount;
+    __device__ __forceinline__ u64 operator()(u64 i) const
+    {
+        const u32 c = cnt[i];
+        if (c > RS_SMALL) biglist[atomicAdd(bigcount, 1u)] = (u32)i;
+        return (u64)c;
+    }
+};
 
 #define RS_BIG_SMEM 4096
 // One CTA sorts one long row with a normalized bitonic network (every comparison ascending) over the
 // next power of two; indices past the end act as +infinity and are never touched.  Rows that fit are
 // sorted in shared memory, longer ones in place in global memory.
+template <class ENT>
 __global__ void __launch_bounds__(256) k_rows_big(const u32* __restrict__ rowptr, const u32* __restrict__ biglist,
-                                                   const u32* __restrict__ bigcount, u64* __restrict__ entries)
+                                                   const u32* __restrict__ bigcount, typename ENT::type* __restrict__ entries)
 {
-    __shared__ u64 s_big[RS_BIG_SMEM];
+    typedef typename ENT::type E;
+    __shared__ E s_big[RS_BIG_SMEM];
     const u32 nbig = *bigcount;
     for (u32 b = blockIdx.x; b < nbig; b += gridDim.x) {
         const u32 r = biglist[b];
         const u32 lo = rowptr[r], len = rowptr[r + 1] - lo;
-        u64* a = entries + lo;
+        E* a = entries + lo;
         const bool in_smem = len <= RS_BIG_SMEM;
         if (in_smem) {
             for (u32 i = threadIdx.x; i < len; i += blockDim.x) s_big[i] = a[i];
@@ -121,7 +149,7 @@ __global__ void __launch_bounds__(256) k_rows_big(const u32* __restrict__ rowptr
                 for (u32 i = threadIdx.x; i < p2; i += blockDim.x) {
                     const u32 l = mirror ? (i ^ (k - 1)) : (i ^ j);
                     if (l > i && l < len) {
-                        const u64 x = a[i], y = a[l];
+                        const E x = a[i], y = a[l];
                         if (x > y) { a[i] = y; a[l] = x; }
                     }
                 }
@@ -155,26 +183,28 @@ struct RowAcc {
     }
 };
 
-template <typename T>
-__device__ __forceinline__ T entry_weight(u64 e, const double* __restrict__ w_emit, const T* __restrict__ w_typed)
+template <typename T, class ENT>
+__device__ __forceinline__ T entry_weight(typename ENT::type e, const double* __restrict__ w_emit, const T* __restrict__ w_typed)
 {
-    if (w_typed) return w_typed[rs_t(e)];
-    if (w_emit) return cast_weight<T>(w_emit[rs_t(e)]);
+    if (ENT::kWeighted) {
+        if (w_typed) return w_typed[ENT::t(e)];
+        if (w_emit) return cast_weight<T>(w_emit[ENT::t(e)]);
+    }
     return cast_weight<T>(1.0);
 }
 
-// Walks one sorted row; emit(minor, value) is called for every stored result.  Returns their count.
-template <typename T, class Emit>
-__device__ __forceinline__ u32 walk_row(const u64* a, u32 len, int sym, const double* w_emit, const T* w_typed, Emit emit)
+// Walks one sorted row; emit(k, minor, value) is called for every stored result.  Returns their count.
+template <typename T, class ENT, class Emit>
+__device__ __forceinline__ u32 walk_row(const typename ENT::type* a, u32 len, int sym, const double* w_emit, const T* w_typed, Emit emit)
 {
     u32 out = 0;
     u32 i = 0;
     while (i < len) {
-        const u32 minor = rs_minor(a[i]);
+        const u32 minor = ENT::minor(a[i]);
         RowAcc<T> acc;
         acc.reset();
-        while (i < len && rs_minor(a[i]) == minor) {
-            acc.add(rs_dir(a[i]), entry_weight<T>(a[i], w_emit, w_typed));
+        while (i < len && ENT::minor(a[i]) == minor) {
+            acc.add(ENT::dir(a[i]), entry_weight<T, ENT>(a[i], w_emit, w_typed));
             i++;
         }
         T v;
@@ -183,74 +213,78 @@ __device__ __forceinline__ u32 walk_row(const u64* a, u32 len, int sym, const do
     return out;
 }
 
-__device__ __forceinline__ void insertion_sort(u64* a, u32 len)
+template <typename E>
+__device__ __forceinline__ void insertion_sort(E* a, u32 len)
 {
     for (u32 i = 1; i < len; i++) {
-        const u64 x = a[i];
+        const E x = a[i];
         u32 j = i;
         while (j > 0 && a[j - 1] > x) { a[j] = a[j - 1]; j--; }
         a[j] = x;
     }
 }
 
-// Pass A: one warp per group of 32 consecutive rows, one lane per row: sort the row (staged in shared
-// memory when the group fits), write it back, count the entries it will store.
-template <typename T>
-__global__ void __launch_bounds__(RS_WARPS * 32) k_rows_sort(const u32* __restrict__ rowptr, u64* __restrict__ entries, const u32* __restrict__ n_dev, int sym,
-                                                              const double* __restrict__ w_emit, const T* __restrict__ w_typed,
-                                                              u32* __restrict__ ucnt)
+#define RF_ROWS 256       // rows per chunk = threads per CTA
+#define RF_SMEM_ENT 4096  // entries of a chunk staged in shared memory (else: in place in global memory)
+
+// Sort + count + scan + write in one pass.  Chunks are handed out by an atomic ticket, so every
+// predecessor of a chunk is already running and the look-back cannot starve.
+// `state` (one word per chunk) and `ticket` must be zero at launch.
+template <typename T, class ENT>
+__global__ void __launch_bounds__(RF_ROWS) k_rows_finish(const u32* __restrict__ rowptr, typename ENT::type* __restrict__ entries,
+                                                          const u32* __restrict__ n_dev, int sym, const double* __restrict__ w_emit,
+                                                          const T* __restrict__ w_typed, int32_t* __restrict__ indptr,
+                                                          int32_t* __restrict__ indices, T* __restrict__ data, u64* __restrict__ state,
+                                                          u32* __restrict__ ticket, u32* __restrict__ nnz_out)
 {
-    __shared__ u64 s_ent[RS_WARPS][RS_GROUP_CAP];
+    typedef typename ENT::type E;
+    __shared__ E s_ent[RF_SMEM_ENT];
+    __shared__ u64 sm[RF_ROWS / 32 + 2];
+    __shared__ u32 s_chunk;
+    __shared__ u64 s_base;
     const u32 n = *n_dev;
-    const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    u64* sm = s_ent[wid];
-    const u32 n_groups = (n + 31) / 32;
-    const u32 warp = blockIdx.x * RS_WARPS + wid, n_warps = gridDim.x * RS_WARPS;
-    for (u32 g = warp; g < n_groups; g += n_warps) {
-        const u32 r = g * 32 + lane;
+    const u32 n_chunks = (n + RF_ROWS - 1) / RF_ROWS;
+    if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) { indptr[0] = 0; *nnz_out = 0; }
+    while (true) {
+        if (threadIdx.x == 0) s_chunk = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const u32 chunk = s_chunk;
+        if (chunk >= n_chunks) break;
+        const u32 r0 = chunk * RF_ROWS, r = r0 + threadIdx.x;
+        const u32 r_end = min(r0 + RF_ROWS, n);
         const bool live = r < n;
-        const u32 lo = live ? rowptr[r] : 0, hi = live ? rowptr[r + 1] : 0;
+        const u32 lo = rowptr[live ? r : r_end], hi = rowptr[live ? r + 1 : r_end];
         const u32 len = hi - lo;
-        const u32 g_lo = __shfl_sync(0xffffffffu, lo, 0);
-        const u32 g_hi = rowptr[min(g * 32 + 32, n)];
-        const u32 g_len = g_hi - g_lo;
-        const bool all_small = __all_sync(0xffffffffu, len <= RS_SMALL);
-        const bool staged = all_small && g_len <= RS_GROUP_CAP;
-        __syncwarp();
-        u64* a;
+        const u32 c_lo = rowptr[r0], c_len = rowptr[r_end] - c_lo;
+        const bool staged = c_len <= RF_SMEM_ENT;
+        E* a;
         if (staged) {
-            for (u32 i = lane; i < g_len; i += 32) sm[i] = entries[g_lo + i];
-            __syncwarp();
-            a = sm + (lo - g_lo);
+            for (u32 i = threadIdx.x; i < c_len; i += RF_ROWS) s_ent[i] = entries[c_lo + i];
+            __syncthreads();
+            a = s_ent + (lo - c_lo);
         } else {
             a = entries + lo;  // in place in global memory (rows > RS_SMALL were sorted by k_rows_big)
         }
-        if (len > 1 && len <= RS_SMALL) insertion_sort(a, len);
-        const u32 mine = walk_row<T>(a, len, sym, w_emit, w_typed, [](u32, u32, T) {});
-        if (live) ucnt[r] = mine;
-        if (staged) {
-            __syncwarp();
-            for (u32 i = lane; i < g_len; i += 32) entries[g_lo + i] = sm[i];
+        if (len > 1 && len <= RS_SMALL) insertion_sort<E>(a, len);
+        const u32 mine = walk_row<T, ENT>(a, len, sym, w_emit, w_typed, [](u32, u32, T) {});
+        u64 total;
+        const u64 excl = block_excl_scan64((u64)mine, sm, &total);
+        if (threadIdx.x < 32) {
+            const u64 e = lookback_exclusive(state, chunk, total);
+            if (threadIdx.x == 0) s_base = e;
         }
-    }
-}
-
-// Pass B: indptr is known; one lane per row walks its sorted entries and writes indices / data.
-template <typename T>
-__global__ void __launch_bounds__(256) k_rows_write(const u32* __restrict__ rowptr, const u64* __restrict__ entries, const u32* __restrict__ n_dev, int sym,
-                                                     const double* __restrict__ w_emit, const T* __restrict__ w_typed,
-                                                     const int32_t* __restrict__ indptr, int32_t* __restrict__ indices, T* __restrict__ data,
-                                                     u32* __restrict__ nnz_out)
-{
-    const u32 n = *n_dev;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *nnz_out = (u32)indptr[n];
-    for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
-        const u32 lo = rowptr[r], len = rowptr[r + 1] - lo;
-        const u32 out0 = (u32)indptr[r];
-        walk_row<T>(entries + lo, len, sym, w_emit, w_typed, [&](u32 k, u32 minor, T v) {
+        __syncthreads();
+        const u32 out0 = (u32)(s_base + excl);
+        if (live) indptr[r] = (int32_t)out0;
+        if (r + 1 == n) {
+            indptr[n] = (int32_t)(out0 + mine);
+            *nnz_out = out0 + mine;
+        }
+        walk_row<T, ENT>(a, len, sym, w_emit, w_typed, [&](u32 k, u32 minor, T v) {
             indices[out0 + k] = (int32_t)minor;
             data[out0 + k] = v;
         });
+        __syncthreads();  // s_ent and s_chunk are reused by the next chunk
     }
 }
 
