@@ -165,6 +165,8 @@ def algo_bytes(name, st):
         "k_assign_ids": 24 * 2 * n + 12 * n,
         "k_rows_count": 2 * 4 * spe * E + 4 * M + (16 * E if weighted else 0),
         "k_rows_scatter": 4 * spe * E + 4 * M + ent * M,           # ids in, cursors, entries out
+        "k_edges_count_flat": 2 * 4 * spe * E + 4 * M,             # slots in, ids out, one histogram update per entry
+        "k_edges_scatter_flat": 4 * spe * E + 4 * M + 4 * M,       # ids in, cursors, 32-bit entries out
         "k_rows_finish": ent * M + 8 * n + 12 * nnz,               # entries in, rowptr in, indptr/indices/data out
         "k_emit_coo": 4 * spe * E + 16 * M,
         "k_dist_insert": 32 * n,            # n = global nodes: every rank inserts every rank's distinct keys

@@ -317,22 +317,52 @@ int build_compressed(g2n_handle* h, int fmt, bool zeroed)
     CK(h->entries.ensure((M + 1) * (weighted ? sizeof(u64) : sizeof(u32))));
     if (weighted) CK(h->w_emit.ensure((T + 1) * sizeof(double)));
     EmitParams E = emit_params(h);
-    E.write_ids = 1;  // the count pass leaves node IDs in edge_slots for the scatter pass (and later converts)
-    const u32 egrid = grid_for((u64)h->n_tiles * 32, 256);
-    { KScope ks(h, "k_rows_count"); k_rows_count<<<egrid, 256, 0, h->stream>>>(E, sym, csc, h->d_rowcnt, weighted ? h->w_emit.as<double>() : nullptr); }
-    CK(cudaGetLastError());
-    h->edges_are_ids = true;
-    E.ids_ready = 1;
-    E.write_ids = 0;
-    int rc = rows_scan(h, n, &h->d_ds->rows);
-    if (rc) return rc;
-    CK(cudaEventRecord(h->ev[EV_EMIT], h->stream));
-    {
-        KScope ks(h, "k_rows_scatter");
-        if (weighted) k_rows_scatter<Ent64><<<egrid, 256, 0, h->stream>>>(E, sym, csc, h->cursor.as<u32>(), h->entries.as<u64>());
-        else k_rows_scatter<Ent32><<<egrid, 256, 0, h->stream>>>(E, sym, csc, h->cursor.as<u32>(), h->entries.as<u32>());
+    int rc;
+    if (!weighted) {
+        // flat passes over the stored edge records (rowsort.cuh): the emission index is not needed
+        const u32 fgrid = grid_for((h->cap_E + EF_BATCH - 1) / EF_BATCH, 256);
+        u32* es = h->edge_slots.as<u32>();
+        if (!h->edges_are_ids) {
+            KScope ks(h, "k_edges_count_flat");
+            switch (h->tpe) {
+                case 1: k_edges_count_flat<1><<<fgrid, 256, 0, h->stream>>>(es, h->slot_id.as<u32>(), h->d_ds, sym, csc, h->d_rowcnt); break;
+                case 2: k_edges_count_flat<2><<<fgrid, 256, 0, h->stream>>>(es, h->slot_id.as<u32>(), h->d_ds, sym, csc, h->d_rowcnt); break;
+                default: k_edges_count_flat<4><<<fgrid, 256, 0, h->stream>>>(es, h->slot_id.as<u32>(), h->d_ds, sym, csc, h->d_rowcnt); break;
+            }
+        } else {
+            // a later convert of the same build: IDs are in place already, only the histogram is needed
+            E.ids_ready = 1;
+            KScope ks(h, "k_rows_count");
+            k_rows_count<<<grid_for((u64)h->n_tiles * 32, 256), 256, 0, h->stream>>>(E, sym, csc, h->d_rowcnt, nullptr);
+        }
+        CK(cudaGetLastError());
+        h->edges_are_ids = true;
+        rc = rows_scan(h, n, &h->d_ds->rows);
+        if (rc) return rc;
+        CK(cudaEventRecord(h->ev[EV_EMIT], h->stream));
+        {
+            KScope ks(h, "k_edges_scatter_flat");
+            switch (h->tpe) {
+                case 1: k_edges_scatter_flat<1><<<fgrid, 256, 0, h->stream>>>(es, h->d_ds, sym, csc, h->cursor.as<u32>(), h->entries.as<u32>()); break;
+                case 2: k_edges_scatter_flat<2><<<fgrid, 256, 0, h->stream>>>(es, h->d_ds, sym, csc, h->cursor.as<u32>(), h->entries.as<u32>()); break;
+                default: k_edges_scatter_flat<4><<<fgrid, 256, 0, h->stream>>>(es, h->d_ds, sym, csc, h->cursor.as<u32>(), h->entries.as<u32>()); break;
+            }
+        }
+        CK(cudaGetLastError());
+    } else {
+        E.write_ids = 1;  // the count pass leaves node IDs in edge_slots for the scatter pass (and later converts)
+        const u32 egrid = grid_for((u64)h->n_tiles * 32, 256);
+        { KScope ks(h, "k_rows_count"); k_rows_count<<<egrid, 256, 0, h->stream>>>(E, sym, csc, h->d_rowcnt, h->w_emit.as<double>()); }
+        CK(cudaGetLastError());
+        h->edges_are_ids = true;
+        E.ids_ready = 1;
+        E.write_ids = 0;
+        rc = rows_scan(h, n, &h->d_ds->rows);
+        if (rc) return rc;
+        CK(cudaEventRecord(h->ev[EV_EMIT], h->stream));
+        { KScope ks(h, "k_rows_scatter"); k_rows_scatter<Ent64><<<egrid, 256, 0, h->stream>>>(E, sym, csc, h->cursor.as<u32>(), h->entries.as<u64>()); }
+        CK(cudaGetLastError());
     }
-    CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev[EV_SORT], h->stream));
     rc = rows_finalize(h, h->params.dtype, weighted, M, n, sym, weighted ? h->w_emit.as<double>() : nullptr, nullptr);
     if (rc) return rc;

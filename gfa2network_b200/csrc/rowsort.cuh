@@ -66,6 +66,102 @@ __device__ __forceinline__ void record_entries(const u32 (&id)[4], int tpe, u32 
     }
 }
 
+// compile-time triplet count: the record's IDs stay in registers (no dynamic indexing)
+template <int TPE, class G>
+__device__ __forceinline__ void record_entries_t(const u32 (&id)[4], u32 t0, int sym, int csc, G g)
+{
+#pragma unroll
+    for (int k = 0; k < TPE; k++) {
+        const u32 a = id[k & 2], b = id[(k & 2) + 1];
+        const u32 r = (k & 1) ? b : a, c = (k & 1) ? a : b;
+        if (sym) { g(r, c, 0u, t0 + k); g(c, r, 1u, t0 + k); }
+        else if (csc) g(c, r, 0u, t0 + k);
+        else g(r, c, 0u, t0 + k);
+    }
+}
+
+// ---------------------------------------------------------------- unweighted builds: flat passes
+// Without weights nothing depends on the emission index, so the two bucketing passes run over the
+// stored edge records [0, E) directly -- coalesced, no per-tile bookkeeping.  TPE = triplets per edge
+// record (1 | 2 | 4); records hold 4 slots iff TPE == 4.
+#define EF_BATCH 4
+template <int TPE>
+__global__ void __launch_bounds__(256) k_edges_count_flat(u32* __restrict__ edge_slots, const u32* __restrict__ slot_id,
+                                                           const DevSizes* __restrict__ ds, int sym, int csc, u32* __restrict__ cnt)
+{
+    constexpr int SPE = TPE == 4 ? 4 : 2;
+    if (!ds->ok) return;
+    const u32 E = ds->E;
+    const u32 stride = gridDim.x * blockDim.x;
+    for (u32 e0 = blockIdx.x * blockDim.x + threadIdx.x; e0 < E; e0 += stride * EF_BATCH) {
+        u32 id[EF_BATCH][4];
+#pragma unroll
+        for (int u = 0; u < EF_BATCH; u++) {
+            const u32 e = e0 + u * stride;
+            id[u][0] = id[u][1] = id[u][2] = id[u][3] = 0;
+            if (e < E) {
+                if (SPE == 4) {
+                    const uint4 q = reinterpret_cast<const uint4*>(edge_slots)[e];
+                    id[u][0] = q.x; id[u][1] = q.y; id[u][2] = q.z; id[u][3] = q.w;
+                } else {
+                    const uint2 q = reinterpret_cast<const uint2*>(edge_slots)[e];
+                    id[u][0] = q.x; id[u][1] = q.y;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < EF_BATCH; u++) {
+            if (e0 + u * stride < E) {
+#pragma unroll
+                for (int k = 0; k < SPE; k++) id[u][k] = slot_id[id[u][k]];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < EF_BATCH; u++) {
+            const u32 e = e0 + u * stride;
+            if (e < E) {
+                if (SPE == 4) reinterpret_cast<uint4*>(edge_slots)[e] = make_uint4(id[u][0], id[u][1], id[u][2], id[u][3]);
+                else reinterpret_cast<uint2*>(edge_slots)[e] = make_uint2(id[u][0], id[u][1]);
+                record_entries_t<TPE>(id[u], 0u, sym, csc, [&](u32 major, u32, u32, u32) { atomicAdd(&cnt[major], 1u); });
+            }
+        }
+    }
+}
+
+template <int TPE>
+__global__ void __launch_bounds__(256) k_edges_scatter_flat(const u32* __restrict__ edge_ids, const DevSizes* __restrict__ ds, int sym, int csc,
+                                                             u32* __restrict__ cursor, u32* __restrict__ entries)
+{
+    constexpr int SPE = TPE == 4 ? 4 : 2;
+    if (!ds->ok) return;
+    const u32 E = ds->E;
+    const u32 stride = gridDim.x * blockDim.x;
+    for (u32 e0 = blockIdx.x * blockDim.x + threadIdx.x; e0 < E; e0 += stride * EF_BATCH) {
+        u32 id[EF_BATCH][4];
+#pragma unroll
+        for (int u = 0; u < EF_BATCH; u++) {
+            const u32 e = e0 + u * stride;
+            id[u][0] = id[u][1] = id[u][2] = id[u][3] = 0;
+            if (e < E) {
+                if (SPE == 4) {
+                    const uint4 q = reinterpret_cast<const uint4*>(edge_ids)[e];
+                    id[u][0] = q.x; id[u][1] = q.y; id[u][2] = q.z; id[u][3] = q.w;
+                } else {
+                    const uint2 q = reinterpret_cast<const uint2*>(edge_ids)[e];
+                    id[u][0] = q.x; id[u][1] = q.y;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < EF_BATCH; u++) {
+            if (e0 + u * stride < E)
+                record_entries_t<TPE>(id[u], 0u, sym, csc, [&](u32 major, u32 minor, u32 dir, u32) {
+                    entries[atomicAdd(&cursor[major], 1u)] = Ent32::make(minor, dir, 0u);
+                });
+        }
+    }
+}
+
 // histogram of majors; translates edge_slots to node IDs in place and lays the weights out in emission
 // order (w_emit[t]) when there are any
 __global__ void __launch_bounds__(256) k_rows_count(const EmitParams E, int sym, int csc, u32* __restrict__ cnt, double* __restrict__ w_emit)
