@@ -320,11 +320,104 @@ __device__ __forceinline__ void insertion_sort(E* a, u32 len)
     }
 }
 
+// ---- rows of <= 16 entries live in registers: Batcher's odd-even merge sort network (19 / 63
+// comparators for 8 / 16 inputs, every lane runs the same instructions) and an unrolled walk
+template <typename E>
+__device__ __forceinline__ void cmp_swap(E& x, E& y)
+{
+    const E lo = x < y ? x : y, hi = x < y ? y : x;
+    x = lo;
+    y = hi;
+}
+
+// comparator lists generated from Batcher's construction (checked with the 0-1 principle); written out
+// so that every register index is a literal
+#define CS(a, b) cmp_swap(v[a], v[b]);
+template <typename E>
+__device__ __forceinline__ void sort_network(E (&v)[8])
+{
+    CS(0, 1) CS(2, 3) CS(4, 5) CS(6, 7) CS(0, 2) CS(1, 3) CS(4, 6) CS(5, 7) CS(1, 2) CS(5, 6) CS(0, 4) CS(1, 5)
+    CS(2, 6) CS(3, 7) CS(2, 4) CS(3, 5) CS(1, 2) CS(3, 4) CS(5, 6)
+}
+template <typename E>
+__device__ __forceinline__ void sort_network(E (&v)[16])
+{
+    CS(0, 1) CS(2, 3) CS(4, 5) CS(6, 7) CS(8, 9) CS(10, 11) CS(12, 13) CS(14, 15) CS(0, 2) CS(1, 3) CS(4, 6) CS(5, 7)
+    CS(8, 10) CS(9, 11) CS(12, 14) CS(13, 15) CS(1, 2) CS(5, 6) CS(9, 10) CS(13, 14) CS(0, 4) CS(1, 5) CS(2, 6)
+    CS(3, 7) CS(8, 12) CS(9, 13) CS(10, 14) CS(11, 15) CS(2, 4) CS(3, 5) CS(10, 12) CS(11, 13) CS(1, 2) CS(3, 4)
+    CS(5, 6) CS(9, 10) CS(11, 12) CS(13, 14) CS(0, 8) CS(1, 9) CS(2, 10) CS(3, 11) CS(4, 12) CS(5, 13) CS(6, 14)
+    CS(7, 15) CS(4, 8) CS(5, 9) CS(6, 10) CS(7, 11) CS(2, 4) CS(3, 5) CS(6, 8) CS(7, 9) CS(10, 12) CS(11, 13)
+    CS(1, 2) CS(3, 4) CS(5, 6) CS(7, 8) CS(9, 10) CS(11, 12) CS(13, 14)
+}
+#undef CS
+
+// the sorted row in registers (entries past `len` are all-ones); same contract as walk_row
+template <int N, typename T, class ENT, class Emit>
+__device__ __forceinline__ u32 walk_regs(const typename ENT::type (&v)[N], u32 len, int sym, const double* w_emit, const T* w_typed, Emit emit)
+{
+    u32 out = 0;
+    RowAcc<T> acc;
+    acc.reset();
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        if ((u32)k < len) {
+            const u32 minor = ENT::minor(v[k]);
+            acc.add(ENT::dir(v[k]), entry_weight<T, ENT>(v[k], w_emit, w_typed));
+            bool last = (u32)(k + 1) == len;
+            if (k + 1 < N) last = last || ENT::minor(v[k + 1 < N ? k + 1 : k]) != minor;
+            if (last) {
+                T val;
+                if (acc.result(sym, val)) { emit(out, minor, val); out++; }
+                acc.reset();
+            }
+        }
+    }
+    return out;
+}
+
+template <int N, class ENT>
+__device__ __forceinline__ void load_row(typename ENT::type (&v)[N], const typename ENT::type* a, u32 len)
+{
+#pragma unroll
+    for (int k = 0; k < N; k++) v[k] = (u32)k < len ? a[k] : ~(typename ENT::type)0;
+}
+
+// phase 1: sort the row (written back in place) and count the entries it will store
+template <int N, typename T, class ENT>
+__device__ __forceinline__ u32 row_sort_count(typename ENT::type* a, u32 len, int sym, const double* w_emit, const T* w_typed)
+{
+    typename ENT::type v[N];
+    load_row<N, ENT>(v, a, len);
+    sort_network(v);
+#pragma unroll
+    for (int k = 0; k < N; k++)
+        if ((u32)k < len) a[k] = v[k];
+    if (ENT::kWeighted && sym) return walk_regs<N, T, ENT>(v, len, sym, w_emit, w_typed, [](u32, u32, T) {});  // zeros of max() are dropped
+    u32 heads = 0;  // every distinct minor is stored (explicit zeros are kept, counts are never zero)
+#pragma unroll
+    for (int k = 0; k < N; k++) heads += ((u32)k < len && (k == 0 || ENT::minor(v[k]) != ENT::minor(v[k > 0 ? k - 1 : 0]))) ? 1u : 0u;
+    return heads;
+}
+
+// phase 2: walk the sorted row and write its results
+template <int N, typename T, class ENT>
+__device__ __forceinline__ void row_emit(const typename ENT::type* a, u32 len, int sym, const double* w_emit, const T* w_typed, u32 out0,
+                                         int32_t* __restrict__ indices, T* __restrict__ data)
+{
+    typename ENT::type v[N];
+    load_row<N, ENT>(v, a, len);
+    walk_regs<N, T, ENT>(v, len, sym, w_emit, w_typed, [&](u32 k, u32 minor, T val) {
+        indices[out0 + k] = (int32_t)minor;
+        data[out0 + k] = val;
+    });
+}
+
 #define RF_ROWS 256       // rows per chunk = threads per CTA
 #define RF_SMEM_ENT 4096  // entries of a chunk staged in shared memory (else: in place in global memory)
 
 // Sort + count + scan + write in one pass.  Chunks are handed out by an atomic ticket, so every
-// predecessor of a chunk is already running and the look-back cannot starve.
+// predecessor of a chunk is already running and the look-back cannot starve.  Per warp the longest of
+// its 32 rows picks the path: 8- or 16-input sorting network in registers, else insertion sort.
 // `state` (one word per chunk) and `ticket` must be zero at launch.
 template <typename T, class ENT>
 __global__ void __launch_bounds__(RF_ROWS) k_rows_finish(const u32* __restrict__ rowptr, typename ENT::type* __restrict__ entries,
@@ -361,8 +454,16 @@ __global__ void __launch_bounds__(RF_ROWS) k_rows_finish(const u32* __restrict__
         } else {
             a = entries + lo;  // in place in global memory (rows > RS_SMALL were sorted by k_rows_big)
         }
-        if (len > 1 && len <= RS_SMALL) insertion_sort<E>(a, len);
-        const u32 mine = walk_row<T, ENT>(a, len, sym, w_emit, w_typed, [](u32, u32, T) {});
+        const u32 wmax = __reduce_max_sync(0xffffffffu, len);  // warp-uniform path
+        u32 mine;
+        if (wmax <= 8) {
+            mine = row_sort_count<8, T, ENT>(a, len, sym, w_emit, w_typed);
+        } else if (wmax <= 16) {
+            mine = row_sort_count<16, T, ENT>(a, len, sym, w_emit, w_typed);
+        } else {
+            if (len > 1 && len <= RS_SMALL) insertion_sort<E>(a, len);
+            mine = walk_row<T, ENT>(a, len, sym, w_emit, w_typed, [](u32, u32, T) {});
+        }
         u64 total;
         const u64 excl = block_excl_scan64((u64)mine, sm, &total);
         if (threadIdx.x < 32) {
@@ -376,10 +477,16 @@ __global__ void __launch_bounds__(RF_ROWS) k_rows_finish(const u32* __restrict__
             indptr[n] = (int32_t)(out0 + mine);
             *nnz_out = out0 + mine;
         }
-        walk_row<T, ENT>(a, len, sym, w_emit, w_typed, [&](u32 k, u32 minor, T v) {
-            indices[out0 + k] = (int32_t)minor;
-            data[out0 + k] = v;
-        });
+        if (wmax <= 8) {
+            row_emit<8, T, ENT>(a, len, sym, w_emit, w_typed, out0, indices, data);
+        } else if (wmax <= 16) {
+            row_emit<16, T, ENT>(a, len, sym, w_emit, w_typed, out0, indices, data);
+        } else {
+            walk_row<T, ENT>(a, len, sym, w_emit, w_typed, [&](u32 k, u32 minor, T v) {
+                indices[out0 + k] = (int32_t)minor;
+                data[out0 + k] = v;
+            });
+        }
         __syncthreads();  // s_ent and s_chunk are reused by the next chunk
     }
 }

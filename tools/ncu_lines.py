@@ -2,7 +2,8 @@
 """Attribute an ncu --set full report's warp-stall samples of one kernel to CUDA source lines.
 ncu's CSV source page is SASS-only; nvdisasm -g supplies the SASS -> file:line map (same order).
 
-    python tools/ncu_lines.py <report.ncu-rep> <lib.so> <kernel-mangled-substring> [top]
+    python tools/ncu_lines.py <report.ncu-rep> <lib.so> <kernel-mangled-substring> [top] [ncu-kernel-regex]
+(the last argument selects one kernel of a multi-kernel report, e.g. k_rows_finish)
 """
 import csv
 import re
@@ -12,8 +13,9 @@ import tempfile
 from pathlib import Path
 
 
-def main(rep, lib, kern, top=40):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+def main(rep, lib, kern, top=40, kregex=None):
+    sel = ["-k", "regex:" + kregex, "-c", "1"] if kregex else []
+    raw = subprocess.run(["ncu", "-i", rep, *sel, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
     hdr, data = rows[hi], [r for r in rows[hi + 1:] if len(r) == len(rows[hi])]
@@ -69,4 +71,4 @@ def main(rep, lib, kern, top=40):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 40)
+    main(sys.argv[1], sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 40, sys.argv[5] if len(sys.argv) > 5 else None)
