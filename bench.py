@@ -167,7 +167,8 @@ def algo_bytes(name, st):
         "k_rows_scatter": 4 * spe * E + 4 * M + ent * M,           # ids in, cursors, entries out
         "k_edges_count_flat": 2 * 4 * spe * E + 4 * M,             # slots in, ids out, one histogram update per entry
         "k_edges_scatter_flat": 4 * spe * E + 4 * M + 4 * M,       # ids in, cursors, 32-bit entries out
-        "k_rows_finish": ent * M + 8 * n + 12 * nnz,               # entries in, rowptr in, indptr/indices/data out
+        "k_rows_sort": 2 * ent * M + 8 * n,                        # entries in and (sorted) out, rowptr in, counts out
+        "k_rows_write": ent * M + 8 * n + 12 * nnz,                # entries in, rowptr + indptr in, indices/data out
         "k_emit_coo": 4 * spe * E + 16 * M,
         "k_dist_insert": 32 * n,            # n = global nodes: every rank inserts every rank's distinct keys
         "k_dist_dest_count": 2 * 4 * spe * E,

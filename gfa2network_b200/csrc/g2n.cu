@@ -3,7 +3,7 @@
 //   K1  k_tokenize        line scan + field split + node-key hashing + edge-record emission (tokenize.cuh)
 //   K2  k_mark_first / k_assign_ids / k_gather_names   first-appearance ranking -> node IDs   (ids.cuh)
 //   K3  k_emit_coo | k_emit_keys                        COO triplets / sort keys               (ids.cuh)
-//   K4  k_rows_count / k_rows_scatter / k_rows_big / k_rows_finish   row bucketing + in-row sort + dedup/sum (+max) (rowsort.cuh)
+//   K4  k_rows_count / k_rows_scatter / k_rows_big / k_rows_sort / k_rows_write   row bucketing + in-row sort + dedup/sum (+max) (rowsort.cuh)
 // No CPU fallback exists: every entry point needs a CUDA device.
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -60,7 +60,7 @@ struct g2n_handle {
     cudaEvent_t ev[EV_COUNT];
     // device buffers (kept between builds: a warm handle allocates nothing)
     DevBuf text, defer, edge_slots, edge_w, longs, tile_info, tile_base, wprefix, slot_id, id2slot, name_len, name_off, names;
-    DevBuf rowptr, cursor, entries, w_emit, biglist, indptr, indices, data, row, col, scan_state;
+    DevBuf rowptr, cursor, entries, w_emit, biglist, ucnt, indptr, indices, data, row, col, scan_state;
     DevBuf up_row, up_col, up_data;
     // zero-initialised state, one memset per arena and build:
     //   zearly  hash table (keys | first | rep), counters + DevSizes, look-back state of the tile scan
@@ -206,7 +206,7 @@ int layout_zrows(g2n_handle* h, u64 n_cap)
     const size_t a = ((n_cap + 2) * sizeof(u32) + 255) & ~(size_t)255;
     const size_t b = 256;
     const size_t c = (scan_state_bytes(n_cap) + 255) & ~(size_t)255;
-    const size_t d = (((n_cap + RF_ROWS - 1) / RF_ROWS + 3) * sizeof(u64) + 255) & ~(size_t)255;  // one word per k_rows_finish chunk
+    const size_t d = c;  // look-back state of the indptr scan
     CK(h->zrows.ensure(a + b + c + d));
     uint8_t* base = h->zrows.as<uint8_t>();
     h->d_rowcnt = (u32*)base;
@@ -240,8 +240,13 @@ int rows_finalize_typed(g2n_handle* h, u64 M, u64 n, int sym, const double* w_em
     CK(h->data.ensure((M + 1) * sizeof(T)));
     { KScope ks(h, "k_rows_big"); k_rows_big<ENT><<<G2N_SM_COUNT, 256, 0, h->stream>>>(h->rowptr.as<u32>(), h->biglist.as<u32>(), h->d_bigcount, h->entries.as<E>()); }
     const u64 n_chunks = (n + RF_ROWS - 1) / RF_ROWS;
-    u64* state = h->d_scan_rows[1];
-    { KScope ks(h, "k_rows_finish"); k_rows_finish<T, ENT><<<grid_for(n_chunks, 1, 6), RF_ROWS, 0, h->stream>>>(h->rowptr.as<u32>(), h->entries.as<E>(), n_dev, sym, w_emit, w_typed, h->indptr.as<int32_t>(), h->indices.as<int32_t>(), h->data.as<T>(), state + 1, (u32*)state, &h->d_ds->nnz); }
+    CK(h->ucnt.ensure((n + 2) * sizeof(u32)));
+    { KScope ks(h, "k_rows_sort"); k_rows_sort<T, ENT><<<grid_for(n_chunks, 1, 8), RF_ROWS, 0, h->stream>>>(h->rowptr.as<u32>(), h->entries.as<E>(), n_dev, sym, w_emit, w_typed, h->ucnt.as<u32>()); }
+    CK(cudaGetLastError());
+    LoadArray<u32> ldu{h->ucnt.as<u32>()};
+    int rc = launch_scan<int32_t>(h, ldu, h->indptr.as<int32_t>(), nullptr, n, n_dev, h->d_scan_rows[1]);
+    if (rc) return rc;
+    { KScope ks(h, "k_rows_write"); k_rows_write<T, ENT><<<grid_for(n_chunks, 1, 8), RF_ROWS, 0, h->stream>>>(h->rowptr.as<u32>(), h->entries.as<E>(), n_dev, sym, w_emit, w_typed, h->indptr.as<int32_t>(), h->indices.as<int32_t>(), h->data.as<T>(), &h->d_ds->nnz); }
     CK(cudaGetLastError());
     return G2N_OK;
 }
@@ -492,7 +497,7 @@ void g2n_destroy(g2n_handle* h)
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->text, &h->zearly, &h->zids, &h->zrows, &h->defer, &h->edge_slots, &h->edge_w, &h->longs, &h->tile_info, &h->tile_base, &h->wprefix,
-                      &h->slot_id, &h->id2slot, &h->name_len, &h->name_off, &h->names, &h->rowptr, &h->cursor, &h->entries, &h->w_emit, &h->biglist, &h->indptr, &h->indices, &h->data, &h->row, &h->col,
+                      &h->slot_id, &h->id2slot, &h->name_len, &h->name_off, &h->names, &h->rowptr, &h->cursor, &h->entries, &h->w_emit, &h->biglist, &h->ucnt, &h->indptr, &h->indices, &h->data, &h->row, &h->col,
                       &h->scan_state, &h->up_row, &h->up_col, &h->up_data, &h->gtable, &h->gfirst, &h->gslot_id, &h->dest_cnt};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(h->ev[i]);

@@ -6,11 +6,15 @@
 //   exclusive scan   cnt -> rowptr + cursors; rows longer than RS_SMALL are listed on the way (common.cuh)
 //   k_rows_scatter   entry (minor, dir[, emission index]) -> atomicAdd(cursor[major]) (any order inside a row)
 //   k_rows_big       rows longer than RS_SMALL are sorted in place by a whole CTA (bitonic; rare)
-//   k_rows_finish    one CTA per chunk of RF_ROWS consecutive rows, one lane per row: the chunk's entries
-//                    are staged in shared memory (one coalesced read), every row is insertion-sorted and
-//                    walked (duplicates summed left to right, max(S, S^T), zeros dropped), the chunk's
-//                    output offset comes from a decoupled look-back over the chunk totals, and indptr /
-//                    indices / data are written -- sort, count, scan and write in ONE pass over the entries
+//   k_rows_sort      one CTA per chunk of RF_ROWS consecutive rows, one lane per row: the chunk's entries
+//                    are staged in shared memory (coalesced), every row is sorted -- rows of <= 16
+//                    entries by a sorting network in registers -- and the number of entries each row
+//                    will store (duplicates summed, zeros of max() dropped) is counted
+//   exclusive scan   counts -> indptr
+//   k_rows_write     same chunking: walk the sorted rows (duplicates summed left to right, max(S, S^T)),
+//                    write indices / data
+//   (a single-pass variant with a decoupled look-back over chunk totals was measured and dropped: with
+//   ~1.5 K entries per chunk the look-back latency, not the work, set the pace -- 119 us vs 90 us on C2)
 // An entry is 64 bits (minor << 33 | dir << 32 | emission index) when weights exist -- the emission
 // index finds the weight and makes the order inside a row total, so duplicate weights are summed in
 // emission order exactly like SciPy does for rows of <= 16 stored entries -- and 32
@@ -415,30 +419,39 @@ __device__ __forceinline__ void row_emit(const typename ENT::type* a, u32 len, i
 #define RF_ROWS 256       // rows per chunk = threads per CTA
 #define RF_SMEM_ENT 4096  // entries of a chunk staged in shared memory (else: in place in global memory)
 
-// Sort + count + scan + write in one pass.  Chunks are handed out by an atomic ticket, so every
-// predecessor of a chunk is already running and the look-back cannot starve.  Per warp the longest of
-// its 32 rows picks the path: 8- or 16-input sorting network in registers, else insertion sort.
-// `state` (one word per chunk) and `ticket` must be zero at launch.
+// one coalesced copy of the chunk's entries into shared memory, eight loads in flight per thread
+template <typename E>
+__device__ __forceinline__ void stage_chunk(E* s_ent, const E* __restrict__ src, u32 c_len)
+{
+    for (u32 i0 = threadIdx.x; i0 < c_len; i0 += 8 * RF_ROWS) {
+        E tmp[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const u32 i = i0 + u * RF_ROWS;
+            if (i < c_len) tmp[u] = src[i];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const u32 i = i0 + u * RF_ROWS;
+            if (i < c_len) s_ent[i] = tmp[u];
+        }
+    }
+}
+
+// Pass A: one CTA per chunk of RF_ROWS consecutive rows, one lane per row.  The chunk's entries are
+// staged in shared memory, every row is sorted (per warp the longest of its 32 rows picks the path: 8- or
+// 16-input sorting network in registers, else insertion sort) and written back, and the number of
+// entries each row will store goes to ucnt.  No CTA depends on another one.
 template <typename T, class ENT>
-__global__ void __launch_bounds__(RF_ROWS) k_rows_finish(const u32* __restrict__ rowptr, typename ENT::type* __restrict__ entries,
-                                                          const u32* __restrict__ n_dev, int sym, const double* __restrict__ w_emit,
-                                                          const T* __restrict__ w_typed, int32_t* __restrict__ indptr,
-                                                          int32_t* __restrict__ indices, T* __restrict__ data, u64* __restrict__ state,
-                                                          u32* __restrict__ ticket, u32* __restrict__ nnz_out)
+__global__ void __launch_bounds__(RF_ROWS) k_rows_sort(const u32* __restrict__ rowptr, typename ENT::type* __restrict__ entries,
+                                                        const u32* __restrict__ n_dev, int sym, const double* __restrict__ w_emit,
+                                                        const T* __restrict__ w_typed, u32* __restrict__ ucnt)
 {
     typedef typename ENT::type E;
     __shared__ E s_ent[RF_SMEM_ENT];
-    __shared__ u64 sm[RF_ROWS / 32 + 2];
-    __shared__ u32 s_chunk;
-    __shared__ u64 s_base;
     const u32 n = *n_dev;
     const u32 n_chunks = (n + RF_ROWS - 1) / RF_ROWS;
-    if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) { indptr[0] = 0; *nnz_out = 0; }
-    while (true) {
-        if (threadIdx.x == 0) s_chunk = atomicAdd(ticket, 1u);
-        __syncthreads();
-        const u32 chunk = s_chunk;
-        if (chunk >= n_chunks) break;
+    for (u32 chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
         const u32 r0 = chunk * RF_ROWS, r = r0 + threadIdx.x;
         const u32 r_end = min(r0 + RF_ROWS, n);
         const bool live = r < n;
@@ -448,7 +461,7 @@ __global__ void __launch_bounds__(RF_ROWS) k_rows_finish(const u32* __restrict__
         const bool staged = c_len <= RF_SMEM_ENT;
         E* a;
         if (staged) {
-            for (u32 i = threadIdx.x; i < c_len; i += RF_ROWS) s_ent[i] = entries[c_lo + i];
+            stage_chunk<E>(s_ent, entries + c_lo, c_len);
             __syncthreads();
             a = s_ent + (lo - c_lo);
         } else {
@@ -464,19 +477,46 @@ __global__ void __launch_bounds__(RF_ROWS) k_rows_finish(const u32* __restrict__
             if (len > 1 && len <= RS_SMALL) insertion_sort<E>(a, len);
             mine = walk_row<T, ENT>(a, len, sym, w_emit, w_typed, [](u32, u32, T) {});
         }
-        u64 total;
-        const u64 excl = block_excl_scan64((u64)mine, sm, &total);
-        if (threadIdx.x < 32) {
-            const u64 e = lookback_exclusive(state, chunk, total);
-            if (threadIdx.x == 0) s_base = e;
+        if (live) ucnt[r] = mine;
+        if (staged) {
+            __syncthreads();
+            for (u32 i = threadIdx.x; i < c_len; i += RF_ROWS) entries[c_lo + i] = s_ent[i];
+            __syncthreads();  // s_ent is reused by the next chunk
         }
-        __syncthreads();
-        const u32 out0 = (u32)(s_base + excl);
-        if (live) indptr[r] = (int32_t)out0;
-        if (r + 1 == n) {
-            indptr[n] = (int32_t)(out0 + mine);
-            *nnz_out = out0 + mine;
+    }
+}
+
+// Pass B: indptr (exclusive scan of ucnt) is known.  Same chunking: stage the sorted entries, walk every
+// row, write indices / data.
+template <typename T, class ENT>
+__global__ void __launch_bounds__(RF_ROWS) k_rows_write(const u32* __restrict__ rowptr, const typename ENT::type* __restrict__ entries,
+                                                         const u32* __restrict__ n_dev, int sym, const double* __restrict__ w_emit,
+                                                         const T* __restrict__ w_typed, const int32_t* __restrict__ indptr,
+                                                         int32_t* __restrict__ indices, T* __restrict__ data, u32* __restrict__ nnz_out)
+{
+    typedef typename ENT::type E;
+    __shared__ E s_ent[RF_SMEM_ENT];
+    const u32 n = *n_dev;
+    const u32 n_chunks = (n + RF_ROWS - 1) / RF_ROWS;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *nnz_out = (u32)indptr[n];
+    for (u32 chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const u32 r0 = chunk * RF_ROWS, r = r0 + threadIdx.x;
+        const u32 r_end = min(r0 + RF_ROWS, n);
+        const bool live = r < n;
+        const u32 lo = rowptr[live ? r : r_end], hi = rowptr[live ? r + 1 : r_end];
+        const u32 len = hi - lo;
+        const u32 c_lo = rowptr[r0], c_len = rowptr[r_end] - c_lo;
+        const u32 out0 = (u32)indptr[live ? r : r_end];
+        const bool staged = c_len <= RF_SMEM_ENT;
+        const E* a;
+        if (staged) {
+            stage_chunk<E>(s_ent, entries + c_lo, c_len);
+            __syncthreads();
+            a = s_ent + (lo - c_lo);
+        } else {
+            a = entries + lo;
         }
+        const u32 wmax = __reduce_max_sync(0xffffffffu, len);
         if (wmax <= 8) {
             row_emit<8, T, ENT>(a, len, sym, w_emit, w_typed, out0, indices, data);
         } else if (wmax <= 16) {
@@ -487,7 +527,7 @@ __global__ void __launch_bounds__(RF_ROWS) k_rows_finish(const u32* __restrict__
                 data[out0 + k] = v;
             });
         }
-        __syncthreads();  // s_ent and s_chunk are reused by the next chunk
+        __syncthreads();  // s_ent is reused by the next chunk
     }
 }
 
