@@ -74,7 +74,9 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.build()
+    import os
+
+    path = os.environ.get("G2N_LIB") or _build.build()  # G2N_LIB: a specific build of the same sources (kernel-variant experiments)
     lib = C.CDLL(str(path))
     vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int32
     lib.g2n_abi_version.restype = C.c_int

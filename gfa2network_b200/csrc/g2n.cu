@@ -684,6 +684,7 @@ static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, c
     u64 long_cap = h->hint_long ? h->hint_long + h->hint_long / 4 + 1024 : 65536;
     u64 defer_cap = h->hint_defer ? h->hint_defer + h->hint_defer / 4 + 1024 : (nbytes / 2048 > 65536 ? nbytes / 2048 : 65536);
     if (spec) edge_cap += edge_cap / 16;
+    if (const char* kc = getenv("G2N_DBG_KEYS")) keys_cap = (u64)atoll(kc);  // timing experiments: table size of a warm handle
     u64 seed = 0x51ed270b7a2d4c1full;
     Counters& hc = *h->h_cnt;
     for (u32 attempt = 0;; attempt++) {
@@ -747,17 +748,39 @@ static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, c
             {
                 KScope ks(h, "k_tokenize");
                 const dim3 grid(grid_for(n_tiles, WT_WARPS, TK_MIN_BLOCKS)), block(WT_WARPS * 32);
-                const int tm = (P.bidirected ? TM_BIDIR : 0) | (P.slots_per_edge == 4 ? TM_FOUR : 0) | (P.wt_len > 0 ? TM_WEIGHT : 0);
-                switch (tm) {  // bidirected keys x four slots x weights: the combinations parse_gfa can ask for
-                    case 0: k_tokenize<0><<<grid, block, 0, h->stream>>>(P); break;
-                    case TM_WEIGHT: k_tokenize<TM_WEIGHT><<<grid, block, 0, h->stream>>>(P); break;
-                    case TM_BIDIR: k_tokenize<TM_BIDIR><<<grid, block, 0, h->stream>>>(P); break;
-                    case TM_BIDIR | TM_WEIGHT: k_tokenize<TM_BIDIR | TM_WEIGHT><<<grid, block, 0, h->stream>>>(P); break;
-                    case TM_BIDIR | TM_FOUR: k_tokenize<TM_BIDIR | TM_FOUR><<<grid, block, 0, h->stream>>>(P); break;
-                    default: k_tokenize<TM_BIDIR | TM_FOUR | TM_WEIGHT><<<grid, block, 0, h->stream>>>(P); break;
+                int tm = (P.bidirected ? TM_BIDIR : 0) | (P.slots_per_edge == 4 ? TM_FOUR : 0) | (P.wt_len > 0 ? TM_WEIGHT : 0);
+                // keys + first words far beyond the 126 MB L2: skip the first-appearance atomic when the loaded value says so
+                if ((size_t)cap * (sizeof(TKey) + sizeof(u64)) > ((size_t)96 << 20)) tm |= TM_COND;
+                if (const char* fc = getenv("G2N_DBG_COND")) tm = (tm & ~TM_COND) | (atoi(fc) ? TM_COND : 0);
+#define G2N_TK(M) case M: k_tokenize<M><<<grid, block, 0, h->stream>>>(P); break;
+                switch (tm) {  // bidirected keys x four slots x weights (the combinations parse_gfa can ask for) x table regime
+                    G2N_TK(0) G2N_TK(TM_WEIGHT) G2N_TK(TM_BIDIR) G2N_TK(TM_BIDIR | TM_WEIGHT) G2N_TK(TM_BIDIR | TM_FOUR) G2N_TK(TM_BIDIR | TM_FOUR | TM_WEIGHT)
+                    G2N_TK(TM_COND) G2N_TK(TM_COND | TM_WEIGHT) G2N_TK(TM_COND | TM_BIDIR) G2N_TK(TM_COND | TM_BIDIR | TM_WEIGHT)
+                    G2N_TK(TM_COND | TM_BIDIR | TM_FOUR) G2N_TK(TM_COND | TM_BIDIR | TM_FOUR | TM_WEIGHT)
+                    default: h->err = "no tokenizer specialisation for this mode"; return G2N_ERR_INTERNAL;
                 }
+#undef G2N_TK
             }
             CK(cudaGetLastError());
+            if (getenv("G2N_DBG_TOKENIZE_ONLY")) {  // kernel-variant timing experiments: stop after the hot kernel
+                cudaEvent_t e0, e1;
+                cudaEventCreate(&e0); cudaEventCreate(&e1);
+                CK(cudaStreamSynchronize(h->stream));
+                float best = 1e9f;
+                for (int rep = 0; rep < 5; rep++) {
+                    CK(cudaMemsetAsync(h->zearly.p, 0, zbytes, h->stream));
+                    cudaEventRecord(e0, h->stream);
+                    if (getenv("G2N_DBG_COND") && atoi(getenv("G2N_DBG_COND"))) k_tokenize<TM_COND><<<grid_for(n_tiles, WT_WARPS, TK_MIN_BLOCKS), WT_WARPS * 32, 0, h->stream>>>(P);
+                    else k_tokenize<0><<<grid_for(n_tiles, WT_WARPS, TK_MIN_BLOCKS), WT_WARPS * 32, 0, h->stream>>>(P);
+                    cudaEventRecord(e1, h->stream);
+                    CK(cudaStreamSynchronize(h->stream));
+                    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+                    if (ms < best) best = ms;
+                }
+                fprintf(stderr, "DBG k_tokenize<0> best of 5: %.4f ms (L2 warm)\n", best);
+                h->err = "G2N_DBG_TOKENIZE_ONLY";
+                return G2N_ERR_INTERNAL;
+            }
             // (records, edge records) before every tile; the grand totals come back with the counters
             LoadTileCounts ltc{h->tile_info.as<TileInfo>()};
             int rc = launch_scan<u64>(h, ltc, h->tile_base.as<u64>(), nullptr, n_tiles, nullptr, h->d_scan_tiles);

@@ -256,16 +256,29 @@ __device__ __forceinline__ uint8_t long_byte(const uint8_t* text, const LongDesc
 struct Probe {
     u64 k0, k1;
     u64 b[4];  // the two keys of the current bucket
+    u64 f[2];  // ~min(order) of the two slots of the HOME bucket, loaded together with its keys
     u32 i;     // first slot of the current bucket
     u32 step;  // bucket stride of the probe sequence (double hashing: odd number of buckets)
 };
 
+__device__ __forceinline__ void ld_first2(const u64* p, u64 (&f)[2], u64 pol)
+{
+    asm volatile("ld.global.cg.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(f[0]), "=l"(f[1]) : "l"(p), "l"(pol) : "memory");
+}
+
+// COND: also load the home bucket's `first` words, so that probe_finish can skip the atomic (worth it
+// when the table is much larger than L2: the atomic dirties a DRAM line per mention; measured slower
+// when the table is L2-resident)
+template <bool COND>
 __device__ __forceinline__ void probe_issue(const ScanParams& P, Probe& pr, u64 pol)
 {
     const u64 h = mix64(pr.k0 ^ (pr.k1 * 0x9e3779b97f4a7c15ULL));
     pr.i = ((u32)h & P.table_mask) & ~(u32)(TB_SLOTS - 1);
     pr.step = (((u32)(h >> 40) << 1) | 1u) * TB_SLOTS;  // odd multiple of the bucket size: visits every bucket
+#ifndef TK_DBG_NOPROBE
     ld_key2(&P.tkeys[pr.i], pr.b, pol);
+    if (COND) ld_first2(&P.tfirst[pr.i], pr.f, pol);
+#endif
 }
 
 // Examines one slot whose key was loaded as (s0, s1): claims it if empty.  Returns true if the slot
@@ -281,10 +294,15 @@ __device__ __forceinline__ bool probe_slot(const ScanParams& P, u32 slot, u64 k0
 
 // Returns the slot index (0xFFFFFFFF if the table is full).  `claimed` is incremented when this call
 // created the key.  Records min(order) as atomicMax(~order) -- fire and forget.
+template <bool COND>
 __device__ __forceinline__ u32 probe_finish(const ScanParams& P, Probe& pr, u64 order, u32& claimed, u64 pol)
 {
     const u64 k0 = pr.k0, k1 = pr.k1;
     u32 i = pr.i, probes = 0, slot;
+    const u32 home = pr.i;
+#ifdef TK_DBG_NOPROBE
+    return i + (u32)(order & 1);  // timing experiment: no table access at all
+#endif
     while (true) {
         // slots are examined in order; an empty slot ends the probe sequence (it is claimed)
         if (probe_slot(P, i, k0, k1, pr.b[0], pr.b[1], claimed)) { slot = i; break; }
@@ -293,7 +311,17 @@ __device__ __forceinline__ u32 probe_finish(const ScanParams& P, Probe& pr, u64 
         if (++probes > 4096u || TB_SLOTS * probes > P.table_mask) { atomicOr(&P.cnt->flags, CF_TABLE_FULL); return 0xFFFFFFFFu; }
         ld_key2(&P.tkeys[i], pr.b, pol);
     }
-    atomicMax(&P.tfirst[slot], ~order);
+#ifndef TK_DBG_NOMAX
+    // tfirst only ever grows, so a mention that is not earlier than the value loaded with the home bucket
+    // needs no atomic (a stale value can only cause a redundant one).  Files are read roughly in order:
+    // all but the first mention of a key take this exit, and the slot's line is never dirtied again.
+    if (COND) {
+        const u64 seen = slot == home ? pr.f[0] : (slot == home + 1 ? pr.f[1] : 0ull);
+        if (~order > seen) atomicMax(&P.tfirst[slot], ~order);
+    } else {
+        atomicMax(&P.tfirst[slot], ~order);
+    }
+#endif
     return slot;
 }
 
@@ -302,8 +330,8 @@ __device__ __forceinline__ u32 table_probe(const ScanParams& P, u64 k0, u64 k1, 
     const u64 pol = table_policy();
     Probe pr;
     pr.k0 = k0; pr.k1 = k1;
-    probe_issue(P, pr, pol);
-    return probe_finish(P, pr, order, claimed, pol);
+    probe_issue<false>(P, pr, pol);
+    return probe_finish<false>(P, pr, order, claimed, pol);
 }
 
 // Generic lookup-or-insert from a key descriptor (any length, any orientation string).

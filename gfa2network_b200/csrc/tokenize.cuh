@@ -148,12 +148,13 @@ __device__ __forceinline__ bool fast_weight(const ScanParams& P, const Tile& t, 
 #define TM_BIDIR 1
 #define TM_FOUR 2
 #define TM_WEIGHT 4
+#define TM_COND 8  // conditional first-appearance atomic (table much larger than L2), see probe_issue
 
 template <int MODE>
 __device__ __forceinline__ void node_issue(const ScanParams& P, const Tile& t, Probe& pr, u32 off, u32 len, u32 ori)
 {
     key_inline(t, off, len, (MODE & TM_BIDIR) != 0, ori, pr.k0, pr.k1);
-    probe_issue(P, pr, t.pol);
+    probe_issue<(MODE & TM_COND) != 0>(P, pr, t.pol);
 }
 
 // the first separators of a short line from one 64-bit slice of the separator mask starting at `pos`
@@ -198,8 +199,8 @@ __device__ __forceinline__ bool parse_line_fast(const ScanParams& P, const Tile&
         Probe a, b;
         node_issue<MODE>(P, t, a, p1, len, '+');
         if (BIDIR) node_issue<MODE>(P, t, b, p1, len, '-');
-        probe_finish(P, a, order0, claimed, t.pol);
-        if (BIDIR) probe_finish(P, b, order0 | 1, claimed, t.pol);
+        probe_finish<(MODE & TM_COND) != 0>(P, a, order0, claimed, t.pol);
+        if (BIDIR) probe_finish<(MODE & TM_COND) != 0>(P, b, order0 | 1, claimed, t.pol);
         return true;
     }
     if (c0 == 'P' || c0 == 'O') return t.win[e1] == '\t';  // >= 3 fields; otherwise the generic parser raises
@@ -262,13 +263,13 @@ __device__ __forceinline__ bool parse_line_fast(const ScanParams& P, const Tile&
     Probe na, nb;
     node_issue<MODE>(P, t, na, uo, ul, oc_u);
     node_issue<MODE>(P, t, nb, vo, vl, oc_v);
-    const u32 su = probe_finish(P, na, order0, claimed, t.pol);
-    const u32 sv = probe_finish(P, nb, order0 | 1, claimed, t.pol);
+    const u32 su = probe_finish<(MODE & TM_COND) != 0>(P, na, order0, claimed, t.pol);
+    const u32 sv = probe_finish<(MODE & TM_COND) != 0>(P, nb, order0 | 1, claimed, t.pol);
     if (FOUR) {
         node_issue<MODE>(P, t, na, vo, vl, oc_v == '+' ? '-' : '+');
         node_issue<MODE>(P, t, nb, uo, ul, oc_u == '+' ? '-' : '+');
-        const u32 sv2 = probe_finish(P, na, order0 | 2, claimed, t.pol);
-        const u32 su2 = probe_finish(P, nb, order0 | 3, claimed, t.pol);
+        const u32 sv2 = probe_finish<(MODE & TM_COND) != 0>(P, na, order0 | 2, claimed, t.pol);
+        const u32 su2 = probe_finish<(MODE & TM_COND) != 0>(P, nb, order0 | 3, claimed, t.pol);
         if (edge_ord < P.edge_cap) reinterpret_cast<uint4*>(P.edge_slots)[edge_ord] = make_uint4(su, sv, sv2, su2);
     } else if (edge_ord < P.edge_cap) {
         reinterpret_cast<uint2*>(P.edge_slots)[edge_ord] = make_uint2(su, sv);
