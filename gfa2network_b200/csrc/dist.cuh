@@ -94,16 +94,15 @@ __global__ void __launch_bounds__(256) k_dist_localmap(const TKey* __restrict__ 
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < lcap; i += gridDim.x * blockDim.x) {
         const TKey k = ltkeys[i];
         if (k.x == 0 && k.y == 0) continue;
-        const u64 hh = mix64(k.x ^ (k.y * 0x9e3779b97f4a7c15ULL));
-        u32 j = ((u32)hh & gmask) & ~(u32)(TB_SLOTS - 1);
-        const u32 step = (((u32)(hh >> 40) << 1) | 1u) * TB_SLOTS;  // same sequence as probe_issue / probe_finish
-        u32 found = 0xFFFFFFFFu;
-        for (u32 probes = 0; probes <= gmask; probes += TB_SLOTS) {
+        ProbeSeq q = probe_seq(k.x, k.y, gmask);  // the sequence probe_issue / probe_finish walk
+        u32 found = 0xFFFFFFFFu, visited = 0;
+        while (true) {
+            const u32 j = q.slot();
             const TKey a = gtkeys[j], b = gtkeys[j + 1];
             if (a.x == k.x && a.y == k.y) { found = j; break; }
             if (b.x == k.x && b.y == k.y) { found = j + 1; break; }
             if ((a.x == 0 && a.y == 0) || (b.x == 0 && b.y == 0)) break;
-            j = (j + step) & gmask;
+            if (!q.next(gmask, visited)) break;
         }
         lslot_id[i] = found == 0xFFFFFFFFu ? 0xFFFFFFFFu : gslot_id[found];
     }

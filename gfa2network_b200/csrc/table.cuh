@@ -253,12 +253,61 @@ __device__ __forceinline__ uint8_t long_byte(const uint8_t* text, const LongDesc
 
 // Lookup-or-insert of a ready 128-bit key, split in two so that several probes can be in flight:
 // probe_issue() starts the loads of the home slot, probe_finish() walks the probe sequence.
+// Probe sequence.  Sequence graphs name their segments in runs (s1041, s1042, ... / 1041+, 1041-), and
+// links join neighbours, so keys that differ only in their last character are used together.  The
+// table therefore hashes the key WITHOUT its last name character to a group of TG_SLOTS consecutive
+// slots (512 B of keys: a few DRAM bursts / L2 sectors) and lets that character (and the orientation of a
+// bidirected key) pick the bucket inside the group; the sequence continues with the same bucket of
+// other groups (double hashing over groups).  Any key set works -- clustering only shortens the
+// distance between keys that are likely to be touched together; per-bucket load is that of plain
+// bucketed hashing because the bucket offset is rotated by the hash.
+#define TG_SLOTS 32                      // slots per group
+#define TG_BUCKETS (TG_SLOTS / TB_SLOTS)  // 16 buckets per group
+struct ProbeSeq {
+    u32 g;     // first slot of the current group
+    u32 boff;  // slot offset of the key's bucket inside every group
+    u32 step;  // group stride in slots: an odd number of groups
+    __device__ __forceinline__ u32 slot() const { return g + boff; }
+    // moves to the next bucket; false when every group has been visited
+    __device__ __forceinline__ bool next(u32 mask, u32& visited)
+    {
+        visited += TG_SLOTS;
+        if (visited > mask) return false;
+        g = (g + step) & mask;
+        return true;
+    }
+};
+
+__device__ __forceinline__ ProbeSeq probe_seq(u64 k0, u64 k1, u32 mask)
+{
+    // position of the last name character: the key's last byte, or the byte before a ":+" / ":-" suffix
+    const u32 top = (u32)(k1 >> 56);
+    u32 c = 0, ori = 0;
+    u64 h0 = k0, h1 = k1;
+    if (top != 0xFF && top >= 2) {  // inline key of >= 1 byte (0xFF: hashed long key -- no structure to exploit)
+        const u32 L = top - 1;
+        auto byte_at = [&](u32 p) { return (u32)((p < 8 ? k0 >> (8 * p) : k1 >> (8 * (p - 8))) & 0xFF); };
+        u32 pos = L - 1;
+        const u32 last = byte_at(pos);
+        if (L >= 3 && (last == '+' || last == '-') && byte_at(L - 2) == ':') { pos = L - 3; ori = last == '-'; }
+        c = byte_at(pos);
+        if (pos < 8) h0 &= ~(0xFFull << (8 * pos)); else h1 &= ~(0xFFull << (8 * (pos - 8)));
+    }
+    const u64 h = mix64(h0 ^ (h1 * 0x9e3779b97f4a7c15ULL));
+    ProbeSeq q;
+    const u32 gmask = mask & ~(u32)(TG_SLOTS - 1);  // tables are at least TG_SLOTS slots
+    q.g = (u32)h & gmask;
+    // ten digits -> ten of the sixteen buckets, rotated per group of keys; the '-' twin sits ten further
+    q.boff = ((c + (u32)(h >> 32) + 10u * ori) & (TG_BUCKETS - 1)) * TB_SLOTS;
+    q.step = ((((u32)(h >> 40) << 1) | 1u) * TG_SLOTS) & mask;
+    return q;
+}
+
 struct Probe {
     u64 k0, k1;
     u64 b[4];  // the two keys of the current bucket
     u64 f[2];  // ~min(order) of the two slots of the HOME bucket, loaded together with its keys
-    u32 i;     // first slot of the current bucket
-    u32 step;  // bucket stride of the probe sequence (double hashing: odd number of buckets)
+    ProbeSeq q;
 };
 
 __device__ __forceinline__ void ld_first2(const u64* p, u64 (&f)[2], u64 pol)
@@ -272,12 +321,11 @@ __device__ __forceinline__ void ld_first2(const u64* p, u64 (&f)[2], u64 pol)
 template <bool COND>
 __device__ __forceinline__ void probe_issue(const ScanParams& P, Probe& pr, u64 pol)
 {
-    const u64 h = mix64(pr.k0 ^ (pr.k1 * 0x9e3779b97f4a7c15ULL));
-    pr.i = ((u32)h & P.table_mask) & ~(u32)(TB_SLOTS - 1);
-    pr.step = (((u32)(h >> 40) << 1) | 1u) * TB_SLOTS;  // odd multiple of the bucket size: visits every bucket
+    pr.q = probe_seq(pr.k0, pr.k1, P.table_mask);
 #ifndef TK_DBG_NOPROBE
-    ld_key2(&P.tkeys[pr.i], pr.b, pol);
-    if (COND) ld_first2(&P.tfirst[pr.i], pr.f, pol);
+    const u32 i = pr.q.slot();
+    ld_key2(&P.tkeys[i], pr.b, pol);
+    if (COND) ld_first2(&P.tfirst[i], pr.f, pol);
 #endif
 }
 
@@ -298,8 +346,8 @@ template <bool COND>
 __device__ __forceinline__ u32 probe_finish(const ScanParams& P, Probe& pr, u64 order, u32& claimed, u64 pol)
 {
     const u64 k0 = pr.k0, k1 = pr.k1;
-    u32 i = pr.i, probes = 0, slot;
-    const u32 home = pr.i;
+    u32 i = pr.q.slot(), visited = 0, slot;
+    const u32 home = i;
 #ifdef TK_DBG_NOPROBE
     return i + (u32)(order & 1);  // timing experiment: no table access at all
 #endif
@@ -307,8 +355,8 @@ __device__ __forceinline__ u32 probe_finish(const ScanParams& P, Probe& pr, u64 
         // slots are examined in order; an empty slot ends the probe sequence (it is claimed)
         if (probe_slot(P, i, k0, k1, pr.b[0], pr.b[1], claimed)) { slot = i; break; }
         if (probe_slot(P, i + 1, k0, k1, pr.b[2], pr.b[3], claimed)) { slot = i + 1; break; }
-        i = (i + pr.step) & P.table_mask;
-        if (++probes > 4096u || TB_SLOTS * probes > P.table_mask) { atomicOr(&P.cnt->flags, CF_TABLE_FULL); return 0xFFFFFFFFu; }
+        if (!pr.q.next(P.table_mask, visited) || visited > 4096u * TG_SLOTS) { atomicOr(&P.cnt->flags, CF_TABLE_FULL); return 0xFFFFFFFFu; }
+        i = pr.q.slot();
         ld_key2(&P.tkeys[i], pr.b, pol);
     }
 #ifndef TK_DBG_NOMAX
