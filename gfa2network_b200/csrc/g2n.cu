@@ -660,8 +660,13 @@ static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, c
     h->diag.unknown_byte = -1;
 
     CK(cudaEventRecord(h->ev[EV_START], h->stream));
-    if (p->text_on_device) {
+    if (p->text_on_device && ((uintptr_t)text & 15) == 0) {
         h->d_text = text;
+    } else if (p->text_on_device) {
+        // the tokenizer reads 16-byte pieces (TMA windows): an unaligned device range is copied once
+        CK(h->text.ensure(nbytes + 64));
+        if (nbytes) CK(cudaMemcpyAsync(h->text.p, text, nbytes, cudaMemcpyDeviceToDevice, h->stream));
+        h->d_text = h->text.as<uint8_t>();
     } else {
         CK(h->text.ensure(nbytes + 64));
         if (nbytes) CK(cudaMemcpyAsync(h->text.p, text, nbytes, cudaMemcpyHostToDevice, h->stream));
@@ -752,7 +757,12 @@ static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, c
                 // keys + first words far beyond the 126 MB L2: skip the first-appearance atomic when the loaded value says so
                 if ((size_t)cap * (sizeof(TKey) + sizeof(u64)) > ((size_t)96 << 20)) tm |= TM_COND;
                 if (const char* fc = getenv("G2N_DBG_COND")) tm = (tm & ~TM_COND) | (atoi(fc) ? TM_COND : 0);
-#define G2N_TK(M) case M: k_tokenize<M><<<grid, block, 0, h->stream>>>(P); break;
+#define G2N_TK(M)                                                                                                         \
+    case M: {                                                                                                             \
+        static bool attr = false;                                                                                         \
+        if (!attr) { CK(cudaFuncSetAttribute(k_tokenize<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TK_SMEM_BYTES)); attr = true; } \
+        k_tokenize<M><<<grid, block, TK_SMEM_BYTES, h->stream>>>(P);                                                      \
+    } break;
                 switch (tm) {  // bidirected keys x four slots x weights (the combinations parse_gfa can ask for) x table regime
                     G2N_TK(0) G2N_TK(TM_WEIGHT) G2N_TK(TM_BIDIR) G2N_TK(TM_BIDIR | TM_WEIGHT) G2N_TK(TM_BIDIR | TM_FOUR) G2N_TK(TM_BIDIR | TM_FOUR | TM_WEIGHT)
                     G2N_TK(TM_COND) G2N_TK(TM_COND | TM_WEIGHT) G2N_TK(TM_COND | TM_BIDIR) G2N_TK(TM_COND | TM_BIDIR | TM_WEIGHT)
@@ -770,8 +780,8 @@ static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, c
                 for (int rep = 0; rep < 5; rep++) {
                     CK(cudaMemsetAsync(h->zearly.p, 0, zbytes, h->stream));
                     cudaEventRecord(e0, h->stream);
-                    if (getenv("G2N_DBG_COND") && atoi(getenv("G2N_DBG_COND"))) k_tokenize<TM_COND><<<grid_for(n_tiles, WT_WARPS, TK_MIN_BLOCKS), WT_WARPS * 32, 0, h->stream>>>(P);
-                    else k_tokenize<0><<<grid_for(n_tiles, WT_WARPS, TK_MIN_BLOCKS), WT_WARPS * 32, 0, h->stream>>>(P);
+                    if (getenv("G2N_DBG_COND") && atoi(getenv("G2N_DBG_COND"))) k_tokenize<TM_COND><<<grid_for(n_tiles, WT_WARPS, TK_MIN_BLOCKS), WT_WARPS * 32, TK_SMEM_BYTES, h->stream>>>(P);
+                    else k_tokenize<0><<<grid_for(n_tiles, WT_WARPS, TK_MIN_BLOCKS), WT_WARPS * 32, TK_SMEM_BYTES, h->stream>>>(P);
                     cudaEventRecord(e1, h->stream);
                     CK(cudaStreamSynchronize(h->stream));
                     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);

@@ -2,8 +2,9 @@
 // emission for the record shapes real GFA files are made of.
 //
 // One pass over the text, no dependency between tiles.  Each WARP owns 2 KiB tiles (64 bytes per
-// lane): it stages the tile plus a look-ahead window in shared memory, classifies '\n' and '\t' 16
-// bytes at a time into bitmasks, compacts the starts of its record lines with warp shuffles, and
+// lane): the tile plus a look-ahead window is fetched into shared memory by the TMA unit (one bulk copy
+// per window, double-buffered: the next window arrives while this one is parsed), the warp classifies
+// '\n' and '\t' 16 bytes at a time into bitmasks, compacts the starts of its record lines with warp shuffles, and
 // parses one line per lane per round from the separator bitmask (no byte loops, no block barriers).
 // Node keys of <= 15 bytes are packed inline into a 128-bit table key and inserted with a 128-bit CAS;
 // the table keeps, per key, the minimum `order` = (tile, record index in tile, sub-rank) -- file
@@ -180,8 +181,16 @@ __device__ __forceinline__ void defer_line(const ScanParams& P, u64 off, u32 til
 
 // Common record shapes, parsed from the separator bitmask.  Returns false when the line must go to the
 // generic parser (rare shapes, errors, long keys, fields running past the window).
+// what an edge record leaves behind: the table slots of its endpoints (and the weight); stored by the
+// caller once the tile's range of edge_slots is known
+struct EdgeOut {
+    u32 s0, s1, s2, s3;
+    double w;
+    bool has;
+};
+
 template <int MODE>
-__device__ __forceinline__ bool parse_line_fast(const ScanParams& P, const Tile& t, u32 s, u64 order0, u32 edge_ord, u32& claimed)
+__device__ __forceinline__ bool parse_line_fast(const ScanParams& P, const Tile& t, u32 s, u64 order0, EdgeOut& eo, u32& claimed)
 {
     constexpr bool BIDIR = (MODE & TM_BIDIR) != 0;
     constexpr bool FOUR = (MODE & TM_FOUR) != 0;
@@ -268,17 +277,23 @@ __device__ __forceinline__ bool parse_line_fast(const ScanParams& P, const Tile&
     if (FOUR) {
         node_issue<MODE>(P, t, na, vo, vl, oc_v == '+' ? '-' : '+');
         node_issue<MODE>(P, t, nb, uo, ul, oc_u == '+' ? '-' : '+');
-        const u32 sv2 = probe_finish<(MODE & TM_COND) != 0>(P, na, order0 | 2, claimed, t.pol);
-        const u32 su2 = probe_finish<(MODE & TM_COND) != 0>(P, nb, order0 | 3, claimed, t.pol);
-        if (edge_ord < P.edge_cap) reinterpret_cast<uint4*>(P.edge_slots)[edge_ord] = make_uint4(su, sv, sv2, su2);
-    } else if (edge_ord < P.edge_cap) {
-        reinterpret_cast<uint2*>(P.edge_slots)[edge_ord] = make_uint2(su, sv);
+        eo.s2 = probe_finish<(MODE & TM_COND) != 0>(P, na, order0 | 2, claimed, t.pol);
+        eo.s3 = probe_finish<(MODE & TM_COND) != 0>(P, nb, order0 | 3, claimed, t.pol);
     }
-    if (want_w && edge_ord < P.edge_cap) {
-        P.edge_w[edge_ord] = wv;
-        if (P.dtype == G2N_DTYPE_F32 && isfinite(wv) && isinf((float)wv)) atomicOr(&P.cnt->flags, CF_CAST_OVERFLOW);
-    }
+    eo.s0 = su; eo.s1 = sv; eo.w = wv; eo.has = true;
     return true;
+}
+
+template <int MODE>
+__device__ __forceinline__ void store_edge(const ScanParams& P, const EdgeOut& eo, u32 edge_ord)
+{
+    if (edge_ord >= P.edge_cap) return;  // the host sees edge_alloc > edge_cap and retries with room
+    if (MODE & TM_FOUR) reinterpret_cast<uint4*>(P.edge_slots)[edge_ord] = make_uint4(eo.s0, eo.s1, eo.s2, eo.s3);
+    else reinterpret_cast<uint2*>(P.edge_slots)[edge_ord] = make_uint2(eo.s0, eo.s1);
+    if (MODE & TM_WEIGHT) {
+        P.edge_w[edge_ord] = eo.w;
+        if (P.dtype == G2N_DTYPE_F32 && isfinite(eo.w) && isinf((float)eo.w)) atomicOr(&P.cnt->flags, CF_CAST_OVERFLOW);
+    }
 }
 
 // ---------------------------------------------------------------- the kernel
@@ -286,57 +301,128 @@ __device__ __forceinline__ bool parse_line_fast(const ScanParams& P, const Tile&
 #define TK_MIN_BLOCKS 3
 #endif
 
+// per-warp shared memory: two text windows (the next tile's window is fetched by the TMA unit while
+// this one is parsed), the two bitmasks, the compacted line list, two mbarriers
+struct alignas(128) WarpSmem {
+    uint8_t win[2][WT_WIN + 32];  // + 32 bytes of '\n' slack read by key_inline
+    u32 nl[WT_WORDS];
+    u32 sp[WT_WORDS + 2];  // + 2 words of slack for sep_slice
+    u32 list[WT_LIST];     // [15:0] window offset of the line, [31:16] edge index within the tile
+    u64 bar[2];
+};
+#define TK_SMEM_BYTES (WT_WARPS * sizeof(WarpSmem))
+
+__device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+
+// TMA bulk copy global -> shared, completion counted on an mbarrier (bytes and addresses: multiples of 16)
+__device__ __forceinline__ void tma_load(void* dst, const void* src, u32 bytes, u64* bar, u64 pol)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_addr(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_addr(bar)), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "TK_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra TK_WAIT_%=;\n\t"
+        "}" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// 0x80 in every byte of w that equals the byte replicated in c (exact, no cross-byte carries)
+__device__ __forceinline__ u32 eq_bytes(u32 w, u32 c)
+{
+    const u32 x = w ^ c;
+    const u32 t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+    return ~(t | x | 0x7F7F7F7Fu);
+}
+// the four 0x80 flags of a word -> bits 0..3
+__device__ __forceinline__ u32 flags4(u32 f) { return (f * 0x00204081u) >> 28; }
+
 template <int MODE>
 __global__ void __launch_bounds__(WT_WARPS * 32, TK_MIN_BLOCKS) k_tokenize(const __grid_constant__ ScanParams P)
 {
-    __shared__ __align__(16) uint8_t s_win[WT_WARPS][WT_WIN + 32];
-    __shared__ u32 s_nl[WT_WARPS][WT_WORDS];
-    __shared__ u32 s_sp[WT_WARPS][WT_WORDS + 2];  // + 2 words of slack for sep_slice
-    __shared__ u32 s_list[WT_WARPS][WT_LIST];  // [15:0] window offset of the line, [31:16] edge index within the tile
-
+    extern __shared__ __align__(128) uint8_t s_raw[];
     const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint8_t* win = s_win[wid];
-    u32* nlm = s_nl[wid];
-    u32* spm = s_sp[wid];
-    u32* list = s_list[wid];
+    WarpSmem& S = reinterpret_cast<WarpSmem*>(s_raw)[wid];
+    u32* nlm = S.nl;
+    u32* spm = S.sp;
+    u32* list = S.list;
     const u64 pol_text = policy_evict_first();
     const u64 pol_table = table_policy();
-    if (lane < 8) reinterpret_cast<u32*>(win + WT_WIN)[lane] = 0x0A0A0A0Au;  // slack read by key_inline
-    if (lane < 2) spm[WT_WORDS + lane] = 0;
+    if (lane < 8) {
+        reinterpret_cast<u32*>(S.win[0] + WT_WIN)[lane] = 0x0A0A0A0Au;
+        reinterpret_cast<u32*>(S.win[1] + WT_WIN)[lane] = 0x0A0A0A0Au;
+    }
+    if (lane < 2) {
+        spm[WT_WORDS + lane] = 0;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&S.bar[lane])) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
     const u32 n_warps = gridDim.x * WT_WARPS;
-    for (u32 tile = blockIdx.x * WT_WARPS + wid; tile < P.n_tiles; tile += n_warps) {
+    // a window the TMA unit can fetch in one piece: inside the text, 16-byte granular (text is 16-byte aligned)
+    const u64 n16 = P.nbytes & ~15ull;
+    auto tma_ok = [&](u32 tile) { return tile > 0 && (u64)tile * WT_TILE - WT_PRE + WT_WIN <= n16; };
+    u32 tile = blockIdx.x * WT_WARPS + wid;
+    u32 buf = 0, parity = 0;  // bit b of parity: phase the next wait on bar[b] expects
+    if (lane == 0 && tile < P.n_tiles && tma_ok(tile)) tma_load(S.win[0], P.text + ((u64)tile * WT_TILE - WT_PRE), WT_WIN, &S.bar[0], pol_text);
+    u32 aborted = 0;
+    bool pending = false;  // a window fetch for the NEXT tile is in flight
+    for (; tile < P.n_tiles && !aborted; tile += n_warps, buf ^= 1) {
         const u64 t0 = (u64)tile * WT_TILE;
         const u64 wbase = t0 - WT_PRE;  // wraps for tile 0: only ever used as wbase + offset
-        __syncwarp();                   // every lane is done with the previous tile's window
-        // ---- stage [t0 - 32, t0 + TILE + LOOK) in shared memory; classify '\n' and '\t' 16 bytes at a time
-        uint4 v[WT_WIN / 16 / 32];
-#pragma unroll
-        for (int k = 0; k < WT_WIN / 16 / 32; k++) {
-            const u32 piece = lane + 32 * k;
-            const u64 g = wbase + (u64)piece * 16;  // global offset of this 16-byte piece
-            if (tile == 0 && piece < WT_PRE / 16) {
-                v[k] = make_uint4(0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au);  // virtual '\n' before byte 0
-            } else if (g + 16 <= P.nbytes) {
-                v[k] = ld_stream_v4(P.text + g, pol_text);
-            } else {
-                uint8_t tmp[16];
-#pragma unroll
-                for (int b = 0; b < 16; b++) tmp[b] = (g + b < P.nbytes) ? P.text[g + b] : (uint8_t)'\n';
-                v[k] = *reinterpret_cast<uint4*>(tmp);
+        uint8_t* win = S.win[buf];
+        // ---- the other buffer is free (every lane passed the barrier that ends the previous tile): fetch the next window
+        {
+            const u32 nxt = tile + n_warps;
+            pending = nxt < P.n_tiles && tma_ok(nxt);
+            if (lane == 0 && pending) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of that buffer vs the async write
+                tma_load(S.win[buf ^ 1], P.text + ((u64)nxt * WT_TILE - WT_PRE), WT_WIN, &S.bar[buf ^ 1], pol_text);
             }
         }
+        if (tma_ok(tile)) {
+            mbar_wait(&S.bar[buf], (parity >> buf) & 1u);
+            parity ^= 1u << buf;
+        } else {
+            // first and last windows: virtual '\n' before byte 0 and after the last byte
+#pragma unroll
+            for (int k = 0; k < WT_WIN / 16 / 32; k++) {
+                const u32 piece = lane + 32 * k;
+                const u64 g = wbase + (u64)piece * 16;  // global offset of this 16-byte piece
+                uint4 v;
+                if (tile == 0 && piece < WT_PRE / 16) {
+                    v = make_uint4(0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au);
+                } else if (g + 16 <= P.nbytes) {
+                    v = ld_stream_v4(P.text + g, pol_text);
+                } else {
+                    uint8_t tmp[16];
+#pragma unroll
+                    for (int b = 0; b < 16; b++) tmp[b] = (g + b < P.nbytes) ? P.text[g + b] : (uint8_t)'\n';
+                    v = *reinterpret_cast<uint4*>(tmp);
+                }
+                reinterpret_cast<uint4*>(win)[piece] = v;
+            }
+            __syncwarp();
+        }
+        // ---- classify '\n' and '\t' 16 bytes at a time into the two bitmasks
 #pragma unroll
         for (int k = 0; k < WT_WIN / 16 / 32; k++) {
             const u32 piece = lane + 32 * k;
-            reinterpret_cast<uint4*>(win)[piece] = v[k];
+            const uint4 v = reinterpret_cast<const uint4*>(win)[piece];
+            const u32 ww[4] = {v.x, v.y, v.z, v.w};
             u32 mn = 0, mt = 0;
-            const u32 ww[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
 #pragma unroll
             for (int b = 0; b < 4; b++) {
-                const u32 eqn = __vcmpeq4(ww[b], 0x0A0A0A0Au) & 0x01010101u;  // 1 per matching byte
-                const u32 eqt = __vcmpeq4(ww[b], 0x09090909u) & 0x01010101u;
-                mn |= (((eqn * 0x01020408u) >> 24) & 0xF) << (4 * b);  // byte b -> bit b
-                mt |= (((eqt * 0x01020408u) >> 24) & 0xF) << (4 * b);
+                mn |= flags4(eq_bytes(ww[b], 0x0A0A0A0Au)) << (4 * b);
+                mt |= flags4(eq_bytes(ww[b], 0x09090909u)) << (4 * b);
             }
             reinterpret_cast<unsigned short*>(nlm)[piece] = (unsigned short)mn;
             reinterpret_cast<unsigned short*>(spm)[piece] = (unsigned short)(mn | mt);
@@ -372,22 +458,20 @@ __global__ void __launch_bounds__(WT_WARPS * 32, TK_MIN_BLOCKS) k_tokenize(const
         const u32 tot = __shfl_sync(0xffffffffu, inc, 31);
         const u32 n_rec_tile = tot >> 16, n_edge_tile = tot & 0xFFFFu;
         const u32 my_rec0 = (inc - packed) >> 16, my_edge0 = (inc - packed) & 0xFFFFu;
-        // one atomicAdd claims this tile's range of edge_slots; the abort flag rides along
-        u32 alloc = 0, aborted = 0;
+        // one atomicAdd claims this tile's range of edge_slots; the abort flag rides along.  Both results are
+        // consumed only after the first round of lines has been parsed and probed, so their latency is hidden.
+        u32 alloc_l0 = 0, flags_l0 = 0;
         if (lane == 0) {
-            if (n_edge_tile) alloc = atomicAdd(&P.cnt->edge_alloc, n_edge_tile);
-            aborted = ld_volatile_u32(&P.cnt->flags) & (CF_TABLE_FULL | CF_DEFER_FULL);
-            TileInfo ti;
-            ti.n_rec = n_rec_tile; ti.n_edge = n_edge_tile; ti.edge_alloc = alloc; ti.pad = 0;
-            P.tile_info[tile] = ti;
+            if (n_edge_tile) alloc_l0 = atomicAdd(&P.cnt->edge_alloc, n_edge_tile);
+            flags_l0 = ld_volatile_u32(&P.cnt->flags);
         }
-        alloc = __shfl_sync(0xffffffffu, alloc, 0);
-        aborted = __shfl_sync(0xffffffffu, aborted, 0);
+        u32 alloc = 0;
+        bool alloc_ready = false;
         u32 claimed = 0;
         // ---- parse, hash, emit.  Record lines are compacted into `list` (WT_LIST per batch; one batch
         // unless the tile holds very short lines) and handed out one line per lane per round, so
         // neighbouring lanes parse neighbouring lines.
-        for (u32 lo = 0; lo < n_rec_tile && !aborted; lo += WT_LIST) {
+        for (u32 lo = 0; lo < n_rec_tile; lo += WT_LIST) {
             {
                 u32 ri = my_rec0, ei = my_edge0;
                 for (u64 m = rec; m; m &= m - 1) {
@@ -399,19 +483,43 @@ __global__ void __launch_bounds__(WT_WARPS * 32, TK_MIN_BLOCKS) k_tokenize(const
             }
             __syncwarp();
             const u32 nb = min(n_rec_tile - lo, (u32)WT_LIST);
-            for (u32 i = lane; i < nb; i += 32) {
-                const u32 ent = list[i];
-                const u32 off = ent & 0xFFFFu, eidx = ent >> 16;
-                if (!parse_line_fast<MODE>(P, t, off, make_order(tile, lo + i, 0), alloc + eidx, claimed))
-                    defer_line(P, wbase + off, tile, lo + i, eidx);
+            for (u32 i0 = 0; i0 < nb; i0 += 32) {  // uniform trip count: the shuffle below needs every lane
+                const u32 i = i0 + lane;
+                EdgeOut eo;
+                eo.has = false;
+                bool ok = true;
+                u32 off = 0, eidx = 0;
+                if (i < nb) {
+                    const u32 ent = list[i];
+                    off = ent & 0xFFFFu;
+                    eidx = ent >> 16;
+                    ok = parse_line_fast<MODE>(P, t, off, make_order(tile, lo + i, 0), eo, claimed);
+                }
+                if (!alloc_ready) {
+                    alloc = __shfl_sync(0xffffffffu, alloc_l0, 0);
+                    alloc_ready = true;
+                }
+                if (i < nb) {
+                    if (!ok) defer_line(P, wbase + off, tile, lo + i, eidx);
+                    else if (eo.has) store_edge<MODE>(P, eo, alloc + eidx);
+                }
             }
             __syncwarp();
         }
+        if (lane == 0) {
+            TileInfo ti;
+            ti.n_rec = n_rec_tile; ti.n_edge = n_edge_tile; ti.edge_alloc = alloc_l0; ti.pad = 0;
+            P.tile_info[tile] = ti;
+        }
+        aborted = __shfl_sync(0xffffffffu, flags_l0, 0) & (CF_TABLE_FULL | CF_DEFER_FULL);
         // new keys of this tile: one fire-and-forget atomic per warp (the host checks the load factor)
 #pragma unroll
         for (int d = 16; d; d >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, d);
         if (lane == 0 && claimed) atomicAdd(&P.cnt->n_keys, claimed);
+        __syncwarp();  // every lane is done with this tile's window, masks and list
     }
+    // an aborted pass (table / defer list full) must not leave a bulk copy in flight towards its shared memory
+    if (aborted && pending) mbar_wait(&S.bar[buf], (parity >> buf) & 1u);
 }
 
 }  // namespace g2n
