@@ -209,14 +209,86 @@ __global__ void __launch_bounds__(256) k_scan_exclusive(LoadOp load, Tout* __res
     }
 }
 
+// ---------------------------------------------------------------- gang scan
+// Same contract as k_scan_exclusive, for launches whose CTAs are all co-resident (cooperative launch,
+// grid <= a few CTAs per SM): every CTA owns one contiguous range, reduces it, publishes the sum, meets
+// the others at a grid-wide barrier, adds up its predecessors' sums and scans its range.  Three memory
+// round trips in a row instead of a look-back chain: about half the latency for the 10^4 .. 10^7 element
+// scans of this pipeline.  load.peek(i) must be free of side effects; load(i) runs once per element.
+// `state`: gridDim.x + 2 words, zero at launch ([0] arrival counter, [1 + b] sum of CTA b).
+template <typename Tout, class LoadOp>
+__global__ void __launch_bounds__(256) k_scan_gang(LoadOp load, Tout* __restrict__ out, Tout* __restrict__ out2, u64 n_host,
+                                                    const u32* __restrict__ n_dev, u64* __restrict__ state)
+{
+    __shared__ u64 sm[10];
+    const u64 n = n_dev ? (u64)*n_dev : n_host;
+    const u32 G = gridDim.x, b = blockIdx.x;
+    u64 chunk = (n + G - 1) / G;
+    chunk = (chunk + SCAN_TILE - 1) / SCAN_TILE * SCAN_TILE;
+    const u64 lo = min(n, (u64)b * chunk), hi = min(n, lo + chunk);
+    // pass 1: my range's sum (coalesced, four loads in flight)
+    u64 s = 0;
+    for (u64 i = lo + threadIdx.x; i < hi; i += 4 * 256) {
+        u64 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = (i + k * 256 < hi) ? (u64)load.peek(i + k * 256) : 0ull;
+        s += v[0] + v[1] + v[2] + v[3];
+    }
+    u64 total;
+    block_excl_scan64(s, sm, &total);
+    if (threadIdx.x == 0) {
+        st_volatile_u64(&state[1 + b], total);
+        __threadfence();
+        atomicAdd((unsigned long long*)&state[0], 1ull);
+        while (ld_volatile_u64(&state[0]) < (u64)G) {}
+        __threadfence();
+    }
+    __syncthreads();
+    // sums of my predecessors
+    u64 p = 0;
+    for (u32 j = threadIdx.x; j < b; j += 256) p += ld_volatile_u64(&state[1 + j]);
+    u64 base;
+    block_excl_scan64(p, sm, &base);
+    // pass 2: scan my range tile by tile
+    for (u64 t0 = lo; t0 < hi; t0 += SCAN_TILE) {
+        const u64 i0 = t0 + (u64)threadIdx.x * SCAN_ITEMS;
+        u64 v[SCAN_ITEMS];
+        u64 sum = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            v[k] = (i0 + k < hi) ? (u64)load(i0 + k) : 0ull;
+            sum += v[k];
+        }
+        u64 tile_total;
+        const u64 excl = block_excl_scan64(sum, sm, &tile_total);
+        u64 run = base + excl;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            if (i0 + k < hi) {
+                out[i0 + k] = (Tout)run;
+                if (out2) out2[i0 + k] = (Tout)run;
+            }
+            run += v[k];
+        }
+        base += tile_total;
+    }
+    // whoever owns the end of the input writes the total (CTA 0 when the input is empty)
+    if (threadIdx.x == 0 && ((hi == n && lo < n) || (n == 0 && b == 0))) {
+        out[n] = (Tout)base;
+        if (out2) out2[n] = (Tout)base;
+    }
+}
+
 template <typename T>
 struct LoadArray {
     const T* p;
     __device__ __forceinline__ u64 operator()(u64 i) const { return (u64)p[i]; }
+    __device__ __forceinline__ u64 peek(u64 i) const { return (u64)p[i]; }
 };
 struct LoadPopc {
     const u32* p;
     __device__ __forceinline__ u64 operator()(u64 i) const { return (u64)__popc(p[i]); }
+    __device__ __forceinline__ u64 peek(u64 i) const { return (u64)__popc(p[i]); }
 };
 
 }  // namespace g2n

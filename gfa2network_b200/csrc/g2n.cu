@@ -94,6 +94,7 @@ struct g2n_handle {
     bool speculate = true;  // g2n_set_option("speculate", 0) turns it off
     bool spec = false;      // the current build is speculative
     bool slow_ran = false;
+    bool gang_scan = true;  // scans run as one co-resident gang (cooperative launch); cleared if the launch is refused
     u64 cap_n = 0, cap_E = 0, cap_R = 0;  // what this build's buffers were sized for
     // state of the last build
     g2n_params params;
@@ -193,9 +194,20 @@ int launch_scan(g2n_handle* h, LoadOp load, Tout* out, Tout* out2, u64 n_cap, co
         CK(cudaMemsetAsync(h->scan_state.p, 0, scan_state_bytes(n_cap), h->stream));
         state_region = h->scan_state.as<u64>();
     }
+    const u32 grid = grid_for(n_tiles, 1, 4);
+    if (h->gang_scan) {
+        // all CTAs co-resident (cooperative launch): reduce, grid barrier, scan -- no look-back chain
+        KScope ks(h, "k_scan_gang");
+        u64 n_host = n_cap;
+        void* args[] = {(void*)&load, (void*)&out, (void*)&out2, (void*)&n_host, (void*)&n_dev, (void*)&state_region};
+        cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_scan_gang<Tout, LoadOp>, dim3(grid), dim3(256), args, 0, h->stream);
+        if (e == cudaSuccess) return G2N_OK;
+        (void)cudaGetLastError();
+        h->gang_scan = false;  // not launchable as a gang on this device / context: use the look-back scan from now on
+    }
     u64* state = state_region + 1;
     u32* ticket = (u32*)state_region;
-    { KScope ks(h, "k_scan_exclusive"); k_scan_exclusive<Tout, LoadOp><<<grid_for(n_tiles, 1, 4), 256, 0, h->stream>>>(load, out, out2, n_cap, n_dev, state, ticket); }
+    { KScope ks(h, "k_scan_exclusive"); k_scan_exclusive<Tout, LoadOp><<<grid, 256, 0, h->stream>>>(load, out, out2, n_cap, n_dev, state, ticket); }
     CK(cudaGetLastError());
     return G2N_OK;
 }
@@ -280,6 +292,7 @@ int rows_scan(g2n_handle* h, u64 n_cap, const u32* n_dev)
 struct LoadTileCounts {
     const TileInfo* p;
     __device__ __forceinline__ u64 operator()(u64 i) const { return ((u64)p[i].n_rec << 32) | (u64)p[i].n_edge; }
+    __device__ __forceinline__ u64 peek(u64 i) const { return (*this)(i); }
 };
 
 EmitParams emit_params(g2n_handle* h)

@@ -218,6 +218,7 @@ struct LoadRowCounts {
         if (c > RS_SMALL) biglist[atomicAdd(bigcount, 1u)] = (u32)i;
         return (u64)c;
     }
+    __device__ __forceinline__ u64 peek(u64 i) const { return (u64)cnt[i]; }
 };
 
 #define RS_BIG_SMEM 4096
