@@ -187,3 +187,58 @@ def test_standalone_coo_to_compressed():
     for fmt in ("csr", "csc"):
         got, want = convert_format(A, fmt), A.asformat(fmt)
         _same(got, want, fmt)
+
+
+def test_c5_shaped_shard_vs_oracle():
+    """BASELINE.json configs[4] shape (segments with sequences, mean 270 B; 4 links per segment; directed
+    default = max(S, S^T) CSR) at a size the oracle finishes in seconds: full comparison + properties."""
+    from gfa2network_b200 import parse_gfa
+    from gfa2network_b200.synth import CONFIGS, synth_gfa
+    from oracle.oracle import oracle_convert_format, oracle_parse_gfa
+
+    cfg = CONFIGS["C5"]
+    n_seg, n_link = 400_000, 1_600_000
+    text = synth_gfa(n_seg, n_link, seed=cfg["seed"], kind=cfg["kind"], seq_mean=cfg["seq_mean"])
+    assert text.size > 100_000_000
+    A, nodes = parse_gfa(text, build_graph=False, build_matrix=True, return_node_list=True, **cfg["mode"])
+    B, onodes = oracle_parse_gfa(text, return_node_list=True, **cfg["mode"])
+    _same(A, B, "C5 shard")
+    assert nodes == onodes
+    assert A.format == "csr" and (A != A.T).nnz == 0 and A.data.min() == 1.0
+    from gfa2network_b200 import convert_format
+
+    _same(convert_format(A, "csc"), oracle_convert_format(B, "csc"), "C5 shard csc")
+
+
+def test_conditional_first_appearance_variant(monkeypatch):
+    """The tokenizer specialisation used when the table is far larger than L2 (TM_COND), forced on small
+    inputs: same results in every mode."""
+    from gfa2network_b200 import parse_gfa
+    from gfa2network_b200.synth import synth_gfa
+    from oracle.oracle import oracle_parse_gfa
+
+    monkeypatch.setenv("G2N_DBG_COND", "1")
+    plain = synth_gfa(30_000, 90_000, seed=41, kind=1, n_paths=1, n_walks=1, interleave=1)
+    wtd = synth_gfa(10_000, 30_000, seed=42, kind=2)
+    for text, mode in ((plain, dict()), (plain, dict(directed=False)), (plain, dict(bidirected=True)),
+                       (wtd, dict(bidirected=True, weight_tag="RC")), (wtd, dict(weight_tag="RC", asymmetric=True))):
+        A, nodes = parse_gfa(text, build_graph=False, build_matrix=True, return_node_list=True, **mode)
+        B, onodes = oracle_parse_gfa(text, return_node_list=True, **mode)
+        _same(A, B, f"cond {mode}")
+        assert nodes == onodes
+
+
+def test_unaligned_device_text():
+    """A device pointer that is not 16-byte aligned (a slice of a larger tensor) is accepted."""
+    import torch
+
+    from gfa2network_b200 import parse_gfa
+    from gfa2network_b200.synth import synth_gfa
+    from oracle.oracle import oracle_parse_gfa
+
+    text = synth_gfa(5_000, 15_000, seed=43)
+    want = oracle_parse_gfa(text)
+    big = torch.zeros(text.size + 64, dtype=torch.uint8, device="cuda")
+    for shift in (1, 7, 16, 33):
+        big[shift:shift + text.size] = torch.from_numpy(text).cuda()
+        _same(parse_gfa(big[shift:shift + text.size], build_graph=False, build_matrix=True), want, f"shift {shift}")
