@@ -56,6 +56,8 @@ struct g2n_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // host -> device copy of the text in pieces, overlapped with the tokenizer
+    std::vector<cudaEvent_t> copy_ev;
     std::string err;
     cudaEvent_t ev[EV_COUNT];
     // device buffers (kept between builds: a warm handle allocates nothing)
@@ -94,6 +96,8 @@ struct g2n_handle {
     bool speculate = true;  // g2n_set_option("speculate", 0) turns it off
     bool spec = false;      // the current build is speculative
     bool slow_ran = false;
+    u32 n_pieces = 0;    // host text of the current build: copy pieces still to be waited for (0: text is on the device)
+    u64 piece_bytes = 0;
     bool gang_scan = true;  // scans run as one co-resident gang (cooperative launch); cleared if the launch is refused
     u64 cap_n = 0, cap_E = 0, cap_R = 0;  // what this build's buffers were sized for
     // state of the last build
@@ -436,6 +440,7 @@ void collect_diag(g2n_handle* h, const Counters& hc, u64 n_records)
     }
 }
 
+#define G2N_H2D_PIECE ((u64)8 << 20)  // bytes per host -> device copy piece
 #define G2N_SPEC_MISS 1000  // internal: the speculative build has to be repeated with a host round trip
 
 // The one host round trip of a build: counters + device-side sizes come back, timings are read.
@@ -490,6 +495,7 @@ int g2n_create(int device, g2n_handle** out)
     g2n_handle* h = new g2n_handle();
     h->device = device;
     if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return G2N_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return G2N_ERR_CUDA; }
     h->stream = h->own_stream;
     for (int i = 0; i < EV_COUNT; i++) cudaEventCreate(&h->ev[i]);
     if (cudaHostAlloc((void**)&h->h_ctl, sizeof(Ctl), cudaHostAllocDefault) != cudaSuccess ||
@@ -517,6 +523,8 @@ void g2n_destroy(g2n_handle* h)
     for (KTimer& t : h->ktimers) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     if (h->h_ctl) cudaFreeHost(h->h_ctl);
     if (h->h_tail) cudaFreeHost(h->h_tail);
+    for (cudaEvent_t e : h->copy_ev) cudaEventDestroy(e);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -681,9 +689,28 @@ static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, c
         if (nbytes) CK(cudaMemcpyAsync(h->text.p, text, nbytes, cudaMemcpyDeviceToDevice, h->stream));
         h->d_text = h->text.as<uint8_t>();
     } else {
+        // host text: copied in pieces on a second stream; the tokenizer is launched piece by piece behind it
         CK(h->text.ensure(nbytes + 64));
-        if (nbytes) CK(cudaMemcpyAsync(h->text.p, text, nbytes, cudaMemcpyHostToDevice, h->stream));
         h->d_text = h->text.as<uint8_t>();
+        h->n_pieces = 0;
+        if (nbytes) {
+            const u64 piece = nbytes <= G2N_H2D_PIECE * 2 ? nbytes : G2N_H2D_PIECE;
+            const u32 np = (u32)((nbytes + piece - 1) / piece);
+            while (h->copy_ev.size() < np + 1) {
+                cudaEvent_t e;
+                CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                h->copy_ev.push_back(e);
+            }
+            CK(cudaEventRecord(h->copy_ev[np], h->stream));  // the copies start after whatever the caller queued before
+            CK(cudaStreamWaitEvent(h->copy_stream, h->copy_ev[np], 0));
+            for (u32 k = 0; k < np; k++) {
+                const u64 a = (u64)k * piece, b = a + piece < nbytes ? a + piece : nbytes;
+                CK(cudaMemcpyAsync(h->text.as<uint8_t>() + a, text + a, b - a, cudaMemcpyHostToDevice, h->copy_stream));
+                CK(cudaEventRecord(h->copy_ev[k], h->copy_stream));
+            }
+            h->n_pieces = np;
+            h->piece_bytes = piece;
+        }
     }
     h->nbytes = nbytes;
     CK(cudaEventRecord(h->ev[EV_H2D], h->stream));
@@ -763,13 +790,27 @@ static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, c
             P.dtype = p->dtype;
             P.seed = seed;
             memcpy(P.wt, h->weight_tag, sizeof(P.wt));
-            {
+            P.tile_begin = 0;
+            P.tile_end = n_tiles;
+            int tm = (P.bidirected ? TM_BIDIR : 0) | (P.slots_per_edge == 4 ? TM_FOUR : 0) | (P.wt_len > 0 ? TM_WEIGHT : 0);
+            // keys + first words far beyond the 126 MB L2: skip the first-appearance atomic when the loaded value says so
+            if ((size_t)cap * (sizeof(TKey) + sizeof(u64)) > ((size_t)96 << 20)) tm |= TM_COND;
+            if (const char* fc = getenv("G2N_DBG_COND")) tm = (tm & ~TM_COND) | (atoi(fc) ? TM_COND : 0);
+            // one launch per arrived piece of a host text (the copy of the next piece overlaps this launch)
+            const u32 n_launch = h->n_pieces > 1 ? h->n_pieces : 1;
+            u32 t_begin = 0;
+            for (u32 k = 0; k < n_launch; k++) {
+                if (h->n_pieces) CK(cudaStreamWaitEvent(h->stream, h->copy_ev[k], 0));
+                u32 t_end = n_tiles;
+                if (k + 1 < n_launch) {
+                    const u64 copied = (u64)(k + 1) * h->piece_bytes;  // windows of these tiles end inside the copied prefix
+                    t_end = (u32)((copied - WT_LOOK) / WT_TILE);
+                }
+                if (t_end <= t_begin) continue;
+                P.tile_begin = t_begin;
+                P.tile_end = t_end;
                 KScope ks(h, "k_tokenize");
-                const dim3 grid(grid_for(n_tiles, WT_WARPS, TK_MIN_BLOCKS)), block(WT_WARPS * 32);
-                int tm = (P.bidirected ? TM_BIDIR : 0) | (P.slots_per_edge == 4 ? TM_FOUR : 0) | (P.wt_len > 0 ? TM_WEIGHT : 0);
-                // keys + first words far beyond the 126 MB L2: skip the first-appearance atomic when the loaded value says so
-                if ((size_t)cap * (sizeof(TKey) + sizeof(u64)) > ((size_t)96 << 20)) tm |= TM_COND;
-                if (const char* fc = getenv("G2N_DBG_COND")) tm = (tm & ~TM_COND) | (atoi(fc) ? TM_COND : 0);
+                const dim3 grid(grid_for(t_end - t_begin, WT_WARPS, TK_MIN_BLOCKS)), block(WT_WARPS * 32);
 #define G2N_TK(M)                                                                                                         \
     case M: {                                                                                                             \
         static bool attr = false;                                                                                         \
@@ -783,7 +824,11 @@ static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, c
                     default: h->err = "no tokenizer specialisation for this mode"; return G2N_ERR_INTERNAL;
                 }
 #undef G2N_TK
+                t_begin = t_end;
             }
+            h->n_pieces = 0;  // a capacity retry finds the whole text on the device
+            P.tile_begin = 0;
+            P.tile_end = n_tiles;
             CK(cudaGetLastError());
             if (getenv("G2N_DBG_TOKENIZE_ONLY")) {  // kernel-variant timing experiments: stop after the hot kernel
                 cudaEvent_t e0, e1;

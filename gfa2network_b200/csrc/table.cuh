@@ -119,7 +119,9 @@ struct ScanParams {
     u32 defer_cap;
     TileInfo* tile_info;
     Counters* cnt;
-    u32 n_tiles;
+    u32 n_tiles;     // tiles of the whole text
+    u32 tile_begin;  // this launch handles tiles [tile_begin, tile_end): the text may still be arriving
+    u32 tile_end;    // (host -> device copy in pieces, one launch per piece)
     int bidirected;
     int slots_per_edge;  // 2, or 4 for bidirected without keep_directed_bidir
     int strip_orientation;

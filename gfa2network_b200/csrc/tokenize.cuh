@@ -370,19 +370,19 @@ __global__ void __launch_bounds__(WT_WARPS * 32, TK_MIN_BLOCKS) k_tokenize(const
     // a window the TMA unit can fetch in one piece: inside the text, 16-byte granular (text is 16-byte aligned)
     const u64 n16 = P.nbytes & ~15ull;
     auto tma_ok = [&](u32 tile) { return tile > 0 && (u64)tile * WT_TILE - WT_PRE + WT_WIN <= n16; };
-    u32 tile = blockIdx.x * WT_WARPS + wid;
+    u32 tile = P.tile_begin + blockIdx.x * WT_WARPS + wid;
     u32 buf = 0, parity = 0;  // bit b of parity: phase the next wait on bar[b] expects
-    if (lane == 0 && tile < P.n_tiles && tma_ok(tile)) tma_load(S.win[0], P.text + ((u64)tile * WT_TILE - WT_PRE), WT_WIN, &S.bar[0], pol_text);
+    if (lane == 0 && tile < P.tile_end && tma_ok(tile)) tma_load(S.win[0], P.text + ((u64)tile * WT_TILE - WT_PRE), WT_WIN, &S.bar[0], pol_text);
     u32 aborted = 0;
     bool pending = false;  // a window fetch for the NEXT tile is in flight
-    for (; tile < P.n_tiles && !aborted; tile += n_warps, buf ^= 1) {
+    for (; tile < P.tile_end && !aborted; tile += n_warps, buf ^= 1) {
         const u64 t0 = (u64)tile * WT_TILE;
         const u64 wbase = t0 - WT_PRE;  // wraps for tile 0: only ever used as wbase + offset
         uint8_t* win = S.win[buf];
         // ---- the other buffer is free (every lane passed the barrier that ends the previous tile): fetch the next window
         {
             const u32 nxt = tile + n_warps;
-            pending = nxt < P.n_tiles && tma_ok(nxt);
+            pending = nxt < P.tile_end && tma_ok(nxt);
             if (lane == 0 && pending) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of that buffer vs the async write
                 tma_load(S.win[buf ^ 1], P.text + ((u64)nxt * WT_TILE - WT_PRE), WT_WIN, &S.bar[buf ^ 1], pol_text);
