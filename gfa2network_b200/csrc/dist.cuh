@@ -35,8 +35,8 @@ __global__ void __launch_bounds__(256) k_dist_export(const TKey* __restrict__ tk
 }
 
 struct DistMergeParams {
-    const DistKey* keys;     // world * key_stride entries
-    const u64* tile_base;    // world * tile_stride entries: per-rank exclusive scan of (n_rec << 32 | n_edge)
+    const uint8_t* keys;       // rank s: DistKey[n_keys[s]] at keys + s * key_stride (bytes)
+    const uint8_t* tile_base;  // rank s: u64[n_tiles + 1] at tile_base + s * tile_stride (bytes): exclusive scan of (n_rec << 32 | n_edge)
     u64 key_stride, tile_stride;
     u64 n_keys[8];
     u64 rec_base[8];         // records before each rank
@@ -48,8 +48,8 @@ __global__ void __launch_bounds__(256) k_dist_insert(const ScanParams P, const D
 {
     u32 claimed = 0;
     for (int s = 0; s < D.world; s++) {
-        const DistKey* keys = D.keys + (u64)s * D.key_stride;
-        const u64* tb = D.tile_base + (u64)s * D.tile_stride;
+        const DistKey* keys = reinterpret_cast<const DistKey*>(D.keys + (u64)s * D.key_stride);
+        const u64* tb = reinterpret_cast<const u64*>(D.tile_base + (u64)s * D.tile_stride);
         for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < D.n_keys[s]; i += (u64)gridDim.x * blockDim.x) {
             const DistKey d = keys[i];
             const u64 tile = d.order >> 12;
@@ -109,9 +109,9 @@ __global__ void __launch_bounds__(256) k_dist_localmap(const TKey* __restrict__ 
 }
 
 // ---------------------------------------------------------------- phase 3
-struct DistPair {
-    u64 entry;  // minor << 33 | dir << 32 | global emission index of the triplet
-    u64 major;
+struct DistPair {  // multi-GPU builds are unweighted: no emission index travels (rowsort.cuh: Ent32)
+    u32 entry;  // minor << 1 | dir
+    u32 major;
 };
 
 __global__ void __launch_bounds__(256) k_dist_dest_count(const EmitParams E, int sym, int csc, u32 rows_per, u32* __restrict__ dest_cnt)
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) k_dist_dest_count(const EmitParams E, int
 // dest_off[d] = first send-buffer index of destination d; dest_cur[d] = entries reserved so far.
 // One warp per tile: count the tile's entries per destination in shared memory, reserve the ranges
 // with one global atomic per destination, then write (requires edge_slots to hold node IDs already).
-__global__ void __launch_bounds__(256) k_dist_dest_scatter(const EmitParams E, int sym, int csc, u32 rows_per, u32 t_base, int world,
+__global__ void __launch_bounds__(256) k_dist_dest_scatter(const EmitParams E, int sym, int csc, u32 rows_per, int world,
                                                             const u32* __restrict__ dest_off, u32* __restrict__ dest_cur,
                                                             DistPair* __restrict__ send)
 {
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(256) k_dist_dest_scatter(const EmitParams E, i
                     const u32 k = atomicAdd(&s_cnt[wid][d], 1u);
                     if (pass) {
                         DistPair p;
-                        p.entry = rs_entry(minor, dir, t_base + t);
+                        p.entry = Ent32::make(minor, dir, 0u);
                         p.major = major;
                         send[s_base[wid][d] + k] = p;
                     }
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(256) k_dist_dest_scatter(const EmitParams E, i
 __global__ void __launch_bounds__(256) k_pairs_count(const DistPair* __restrict__ pairs, u64 n, u32 row0, u32* __restrict__ cnt)
 {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
-        atomicAdd(&cnt[(u32)pairs[i].major - row0], 1u);
+        atomicAdd(&cnt[pairs[i].major - row0], 1u);
 }
 
 // multi-GPU builds are unweighted: the slab keeps 32-bit entries (minor << 1 | dir), see Ent32
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(256) k_pairs_scatter(const DistPair* __restric
 {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
         const DistPair p = pairs[i];
-        entries[atomicAdd(&cursor[(u32)p.major - row0], 1u)] = (u32)(p.entry >> 32);
+        entries[atomicAdd(&cursor[p.major - row0], 1u)] = p.entry;
     }
 }
 

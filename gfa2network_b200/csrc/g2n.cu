@@ -1231,8 +1231,8 @@ int g2n_dist_merge(g2n_handle* h, const void* dev_keys_all, uint64_t key_stride,
     P.cnt = h->d_cnt;
     DistMergeParams D;
     memset(&D, 0, sizeof(D));
-    D.keys = (const DistKey*)dev_keys_all;
-    D.tile_base = (const u64*)dev_tile_base_all;
+    D.keys = (const uint8_t*)dev_keys_all;
+    D.tile_base = (const uint8_t*)dev_tile_base_all;
     D.key_stride = key_stride;
     D.tile_stride = tile_stride;
     D.world = world;
@@ -1291,10 +1291,9 @@ int g2n_dist_entries(g2n_handle* h, int world, uint64_t rows_per_rank, uint64_t 
     if (!h || !dest_counts || world < 1 || world > 8 || rows_per_rank == 0) return G2N_ERR_INVALID;
     CK(cudaSetDevice(h->device));
     const int sym = h->symmax ? 1 : 0;
-    const u64 triplet_base = edge_base * (u64)h->tpe;  // emission index of this rank's first triplet
+    (void)edge_base;  // unweighted entries carry no emission index
     const u64 M = h->n_edges * (u64)h->tpe * (sym ? 2 : 1);
     if (M > send_cap) { h->err = "send buffer too small"; return G2N_ERR_INVALID; }
-    if (triplet_base + h->n_edges * (u64)h->tpe >= 0xFFFFFFF0ull) { h->err = "more than 2^32 triplets across all ranks"; return G2N_ERR_UNSUPPORTED; }
     const int csc = (!sym && h->params.want_format == G2N_FMT_CSC) ? 1 : 0;
     CK(h->dest_cnt.ensure(64 * sizeof(u32)));
     u32* cnt = h->dest_cnt.as<u32>();
@@ -1319,9 +1318,8 @@ int g2n_dist_entries(g2n_handle* h, int world, uint64_t rows_per_rank, uint64_t 
     if (M) {
         CK(cudaMemcpyAsync(cnt + 16, off, 8 * sizeof(u32), cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemsetAsync(cnt + 32, 0, 8 * sizeof(u32), h->stream));
-        { KScope ks(h, "k_dist_dest_scatter"); k_dist_dest_scatter<<<egrid, 256, 0, h->stream>>>(E, sym, csc, (u32)rows_per_rank, (u32)triplet_base, world, cnt + 16, cnt + 32, (DistPair*)dev_send); }
-        CK(cudaGetLastError());
-        CK(cudaStreamSynchronize(h->stream));
+        { KScope ks(h, "k_dist_dest_scatter"); k_dist_dest_scatter<<<egrid, 256, 0, h->stream>>>(E, sym, csc, (u32)rows_per_rank, world, cnt + 16, cnt + 32, (DistPair*)dev_send); }
+        CK(cudaGetLastError());  // no synchronisation: the exchange that follows is ordered on the same stream
     }
     return G2N_OK;
 }

@@ -24,9 +24,17 @@ import scipy.sparse as sp
 
 from . import _capi
 
-PAIR_WORDS = 2  # int64 words per exchanged row entry {entry, row}
+PAIR_WORDS = 1  # int64 words per exchanged row entry {entry u32 = col << 1 | dir, row u32}
 KEY_WORDS = 4   # int64 words per exchanged key {k0, k1, order, pad}
+META_WORDS = 8  # int64 words of per-rank counts at the head of an exchanged block
 MAX_WORLD = 8
+
+
+def block_layout(key_stride: int, tile_stride: int) -> tuple[int, int, int]:
+    """One all-gathered block per rank: [meta | keys | tile prefix]; returns (block words, key offset, tile offset)."""
+    key_off = META_WORDS
+    tile_off = key_off + key_stride * KEY_WORDS
+    return tile_off + tile_stride, key_off, tile_off
 
 
 # ------------------------------------------------------------------ host logic (pure, CPU-testable)
@@ -108,21 +116,29 @@ class LocalRank:
         self.info = info
         return [int(info.n_keys), int(info.n_tiles), int(info.n_records), int(info.n_edge_records), int(info.n_entries)]
 
-    def export(self, key_stride: int, tile_stride: int):
+    def export_block(self, mine: list[int], key_stride: int, tile_stride: int):
+        """This rank's block [meta | keys | tile prefix] for the all-gather.  If the shard holds more keys or
+        tiles than the strides allow, only the meta words are valid (every rank sees that and re-plans)."""
         t = self.torch
-        keys = t.zeros(key_stride * KEY_WORDS, dtype=t.int64, device=self.dev)
-        tb = t.zeros(tile_stride, dtype=t.int64, device=self.dev)
-        self.h.check(self.h.lib.g2n_dist_export(self.h.h, C.c_void_p(keys.data_ptr()), C.c_void_p(tb.data_ptr())))
-        return keys, tb
+        words, key_off, tile_off = block_layout(key_stride, tile_stride)
+        block = t.empty(words, dtype=t.int64, device=self.dev)
+        meta = list(mine) + [key_stride, tile_stride] + [0] * (META_WORDS - len(mine) - 2)
+        block[:META_WORDS] = t.tensor(meta, dtype=t.int64)  # one small H2D copy, ordered on the stream
+        if mine[0] <= key_stride and mine[1] + 1 <= tile_stride:
+            self.h.check(self.h.lib.g2n_dist_export(self.h.h, C.c_void_p(block.data_ptr() + 8 * key_off), C.c_void_p(block.data_ptr() + 8 * tile_off)))
+        return block
 
-    def merge(self, keys_all, tb_all, key_stride, tile_stride, meta) -> int:
+    def merge(self, blocks_all, key_stride, tile_stride, meta) -> int:
+        """blocks_all: the `world` blocks of export_block(), rank order, one buffer."""
         W = self.world
+        words, key_off, tile_off = block_layout(key_stride, tile_stride)
         u64a = C.c_uint64 * MAX_WORLD
         n_keys = [m[0] for m in meta] + [0] * (MAX_WORLD - W)
         rec_base = exclusive_prefix([m[2] for m in meta]) + [0] * (MAX_WORLD - W)
         n_global = C.c_uint64()
-        self.h.check(self.h.lib.g2n_dist_merge(self.h.h, C.c_void_p(keys_all.data_ptr()), key_stride, u64a(*n_keys),
-                                               C.c_void_p(tb_all.data_ptr()), tile_stride, u64a(*rec_base), sum(m[2] for m in meta), W,
+        base = blocks_all.data_ptr()
+        self.h.check(self.h.lib.g2n_dist_merge(self.h.h, C.c_void_p(base + 8 * key_off), 8 * words, u64a(*n_keys),
+                                               C.c_void_p(base + 8 * tile_off), 8 * words, u64a(*rec_base), sum(m[2] for m in meta), W,
                                                C.byref(n_global)))
         self.n_global = int(n_global.value)
         return self.n_global
@@ -175,31 +191,57 @@ class DistBuilder:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.local = LocalRank(device_index, self.rank, self.world)
         self.dev = self.local.dev
+        self.strides = None  # (key_stride, tile_stride) of the exchanged blocks, remembered between builds
 
     def build(self, text_dev, **mode) -> DistResult:
         torch, dist, W, L = self.torch, self.dist, self.world, self.local
+        import os
+        import time
+        dbg = os.environ.get("G2N_DIST_DEBUG")
+        marks = []
+
+        def mark(name):
+            if dbg:
+                torch.cuda.synchronize()
+                marks.append((name, time.perf_counter()))
+
+        mark("start")
         mine = L.scan(text_dev, **mode)
-        # ---- phase 2: dictionary merge
-        if W > 1:
-            t = torch.tensor(mine, dtype=torch.int64, device=self.dev)
-            out = torch.empty(W * len(mine), dtype=torch.int64, device=self.dev)
-            dist.all_gather_into_tensor(out, t, group=self.group)
-            meta = out.view(W, len(mine)).tolist()
-        else:
-            meta = [mine]
-        key_stride = max(max(m[0] for m in meta), 1)
-        tile_stride = max(m[1] for m in meta) + 1
-        keys, tb = L.export(key_stride, tile_stride)
-        if W > 1:
-            keys_all = torch.empty(W * key_stride * KEY_WORDS, dtype=torch.int64, device=self.dev)
-            tb_all = torch.empty(W * tile_stride, dtype=torch.int64, device=self.dev)
-            dist.all_gather_into_tensor(keys_all, keys, group=self.group)
-            dist.all_gather_into_tensor(tb_all, tb, group=self.group)
-        else:
-            keys_all, tb_all = keys, tb
-        ng = L.merge(keys_all, tb_all, key_stride, tile_stride, meta)
+        mark("scan")
+        # ---- phase 2: dictionary merge.  ONE all-gather of [meta | keys | tile prefix] blocks; the block
+        # strides are those of the previous build of this builder (+ slack) -- if any rank's shard does not
+        # fit, every rank sees it in the gathered meta words and the exchange is repeated with exact strides.
+        meta = None
+        for attempt in range(2):
+            if self.strides is None:
+                if W > 1:
+                    t = torch.tensor(mine, dtype=torch.int64, device=self.dev)
+                    out = torch.empty(W * len(mine), dtype=torch.int64, device=self.dev)
+                    dist.all_gather_into_tensor(out, t, group=self.group)
+                    meta = out.view(W, len(mine)).tolist()
+                else:
+                    meta = [mine]
+                ks, ts = max(max(m[0] for m in meta), 1), max(m[1] for m in meta) + 1
+                self.strides = (ks + ks // 16 + 64, ts + ts // 16 + 8)
+            key_stride, tile_stride = self.strides
+            block = L.export_block(mine, key_stride, tile_stride)
+            mark("export")
+            if W > 1:
+                blocks_all = torch.empty(W * block.numel(), dtype=torch.int64, device=self.dev)
+                dist.all_gather_into_tensor(blocks_all, block, group=self.group)
+            else:
+                blocks_all = block
+            got = blocks_all.view(W, -1)[:, :META_WORDS].tolist()
+            meta = [g[:len(mine)] for g in got]
+            if all(m[0] <= key_stride and m[1] + 1 <= tile_stride for m in meta):
+                break
+            self.strides = None  # some shard outgrew the remembered strides: plan again (same decision on every rank)
+        mark("allgather")
+        ng = L.merge(blocks_all, key_stride, tile_stride, meta)
+        mark("merge")
         # ---- phase 3: edge exchange by owner row block
         send, send_counts = L.entries(meta)
+        mark("entries")
         if W > 1:
             sc = torch.tensor(send_counts, dtype=torch.int64, device=self.dev)
             rcnt = torch.empty(W, dtype=torch.int64, device=self.dev)
@@ -211,7 +253,12 @@ class DistBuilder:
                                    [c * PAIR_WORDS for c in recv_counts], [c * PAIR_WORDS for c in send_counts], group=self.group)
         else:
             recv, n_recv = send, send_counts[0]
+        mark("alltoall")
         row0, n_rows = L.slab(recv, n_recv)
+        mark("slab")
+        if dbg and self.rank == 0:
+            import sys
+            print("dist phases (ms): " + ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.3f}" for a, b in zip(marks, marks[1:])), file=sys.stderr)
         s = L.h.sizes()
         return DistResult(ng, row0, n_rows, int(s.nnz), dict(meta=meta, send_counts=send_counts, n_recv=n_recv,
                                                             key_bytes=W * key_stride * KEY_WORDS * 8,

@@ -207,12 +207,14 @@ typedef struct g2n_dist_info {
 int g2n_dist_scan(g2n_handle *h, const uint8_t *text, uint64_t nbytes, const g2n_params *p, g2n_dist_info *out);
 /* dev_keys: n_keys x 32 bytes {key[16], order u64, pad u64}; dev_tile_base: (n_tiles + 1) x u64 */
 int g2n_dist_export(g2n_handle *h, void *dev_keys, void *dev_tile_base);
-/* dev_keys_all / dev_tile_base_all: `world` blocks of key_stride / tile_stride elements (rank order) */
+/* dev_keys_all / dev_tile_base_all: rank s's exported keys / tile prefix start at base + s * stride,
+ * strides in BYTES (so both may point into one all-gathered buffer of per-rank blocks) */
 int g2n_dist_merge(g2n_handle *h, const void *dev_keys_all, uint64_t key_stride, const uint64_t *n_keys,
                    const void *dev_tile_base_all, uint64_t tile_stride, const uint64_t *rec_base,
                    uint64_t total_records, int world, uint64_t *n_global_out);
-/* edge_base: edge records of all lower ranks (keeps emission order global);
- * dev_send: n_entries x 16 bytes {entry u64, row u64}, grouped by destination; dest_counts[world] out */
+/* edge_base: edge records of all lower ranks (unused by unweighted builds, kept for weighted ones);
+ * dev_send: n_entries x 8 bytes {entry u32 = col << 1 | dir, row u32}, grouped by destination;
+ * dest_counts[world] out */
 int g2n_dist_entries(g2n_handle *h, int world, uint64_t rows_per_rank, uint64_t edge_base, void *dev_send,
                      uint64_t send_cap, uint64_t *dest_counts);
 int g2n_dist_slab(g2n_handle *h, const void *dev_pairs, uint64_t n_pairs, uint64_t row0, uint64_t n_rows);

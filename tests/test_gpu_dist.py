@@ -22,10 +22,8 @@ def _run_logical(text: np.ndarray, G: int, **mode):
     meta = [ranks[r].scan(shards[r], **mode) for r in range(G)]
     key_stride = max(max(m[0] for m in meta), 1)
     tile_stride = max(m[1] for m in meta) + 1
-    exp = [ranks[r].export(key_stride, tile_stride) for r in range(G)]
-    keys_all = torch.cat([e[0] for e in exp])
-    tb_all = torch.cat([e[1] for e in exp])
-    ng = {ranks[r].merge(keys_all, tb_all, key_stride, tile_stride, meta) for r in range(G)}
+    blocks_all = torch.cat([ranks[r].export_block(meta[r], key_stride, tile_stride) for r in range(G)])
+    ng = {ranks[r].merge(blocks_all, key_stride, tile_stride, meta) for r in range(G)}
     assert len(ng) == 1
     ng = ng.pop()
     sends = [ranks[r].entries(meta) for r in range(G)]
