@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) k_dist_localmap(const TKey* __restrict__ 
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < lcap; i += gridDim.x * blockDim.x) {
         const TKey k = ltkeys[i];
         if (k.x == 0 && k.y == 0) continue;
-        ProbeSeq q = probe_seq(k.x, k.y, gmask);  // the sequence probe_issue / probe_finish walk
+        ProbeSeq q = probe_seq(k.x, k.y, gmask, 0);  // the sequence probe_issue / probe_finish walk (the merge inserts with bidirected = 0)
         u32 found = 0xFFFFFFFFu, visited = 0;
         while (true) {
             const u32 j = q.slot();

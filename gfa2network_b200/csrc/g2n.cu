@@ -96,6 +96,7 @@ struct g2n_handle {
     bool speculate = true;  // g2n_set_option("speculate", 0) turns it off
     bool spec = false;      // the current build is speculative
     bool slow_ran = false;
+    u32 tk_attr = 0;     // tokenizer specialisations whose dynamic shared memory opt-in was set on this device
     u32 n_pieces = 0;    // host text of the current build: copy pieces still to be waited for (0: text is on the device)
     u64 piece_bytes = 0;
     bool gang_scan = true;  // scans run as one co-resident gang (cooperative launch); cleared if the launch is refused
@@ -813,8 +814,10 @@ static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, c
                 const dim3 grid(grid_for(t_end - t_begin, WT_WARPS, TK_MIN_BLOCKS)), block(WT_WARPS * 32);
 #define G2N_TK(M)                                                                                                         \
     case M: {                                                                                                             \
-        static bool attr = false;                                                                                         \
-        if (!attr) { CK(cudaFuncSetAttribute(k_tokenize<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TK_SMEM_BYTES)); attr = true; } \
+        if (!(h->tk_attr & (1u << (M)))) { /* per handle = per device: the opt-in is a per-device function attribute */ \
+            CK(cudaFuncSetAttribute(k_tokenize<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TK_SMEM_BYTES));    \
+            h->tk_attr |= 1u << (M);                                                                                      \
+        }                                                                                                                 \
         k_tokenize<M><<<grid, block, TK_SMEM_BYTES, h->stream>>>(P);                                                      \
     } break;
                 switch (tm) {  // bidirected keys x four slots x weights (the combinations parse_gfa can ask for) x table regime

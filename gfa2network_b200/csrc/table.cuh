@@ -280,9 +280,27 @@ struct ProbeSeq {
     }
 };
 
-__device__ __forceinline__ ProbeSeq probe_seq(u64 k0, u64 k1, u32 mask)
+// (h0, h1): the key with its cluster byte zeroed; c: that byte; ori: 1 for the '-' twin of a bidirected key
+__device__ __forceinline__ ProbeSeq probe_seq_core(u64 h0, u64 h1, u32 c, u32 ori, u32 mask)
 {
-    // position of the last name character: the key's last byte, or the byte before a ":+" / ":-" suffix
+    // 32-bit multiply-xorshift mix of the four key words (the quality only matters for speed)
+    u32 a = (u32)h0 ^ ((u32)(h0 >> 32) * 0x9E3779B1u) ^ ((u32)h1 * 0x85EBCA77u) ^ ((u32)(h1 >> 32) * 0xC2B2AE3Du);
+    a ^= a >> 16; a *= 0x21F0AAADu; a ^= a >> 15; a *= 0x735A2D97u; a ^= a >> 15;
+    const u32 b = (a ^ (u32)(h0 >> 32) ^ (u32)h1) * 0x9E3779B1u;  // further bits: bucket rotation and group stride
+    ProbeSeq q;
+    const u32 gmask = mask & ~(u32)(TG_SLOTS - 1);  // tables are at least TG_SLOTS slots
+    q.g = a & gmask;
+    // ten digits -> ten of the sixteen buckets, rotated per group of keys; the '-' twin sits ten further
+    q.boff = ((c + (b >> 28) + 10u * ori) & (TG_BUCKETS - 1)) * TB_SLOTS;
+    q.step = (((b << 1) | 1u) * TG_SLOTS) & mask;
+    return q;
+}
+
+// The cluster byte of a key is positional: the last byte, or -- for the keys of a bidirected build, which
+// end in ':' + orientation -- the third byte from the end (the last character of the segment name when
+// the orientation is one character, as it is in every well-formed file).
+__device__ __forceinline__ ProbeSeq probe_seq(u64 k0, u64 k1, u32 mask, int bidir)
+{
     const u32 top = (u32)(k1 >> 56);
     u32 c = 0, ori = 0;
     u64 h0 = k0, h1 = k1;
@@ -290,19 +308,14 @@ __device__ __forceinline__ ProbeSeq probe_seq(u64 k0, u64 k1, u32 mask)
         const u32 L = top - 1;
         auto byte_at = [&](u32 p) { return (u32)((p < 8 ? k0 >> (8 * p) : k1 >> (8 * (p - 8))) & 0xFF); };
         u32 pos = L - 1;
-        const u32 last = byte_at(pos);
-        if (L >= 3 && (last == '+' || last == '-') && byte_at(L - 2) == ':') { pos = L - 3; ori = last == '-'; }
+        if (bidir) {
+            ori = byte_at(L - 1) == '-';
+            if (L >= 3) pos = L - 3;
+        }
         c = byte_at(pos);
         if (pos < 8) h0 &= ~(0xFFull << (8 * pos)); else h1 &= ~(0xFFull << (8 * (pos - 8)));
     }
-    const u64 h = mix64(h0 ^ (h1 * 0x9e3779b97f4a7c15ULL));
-    ProbeSeq q;
-    const u32 gmask = mask & ~(u32)(TG_SLOTS - 1);  // tables are at least TG_SLOTS slots
-    q.g = (u32)h & gmask;
-    // ten digits -> ten of the sixteen buckets, rotated per group of keys; the '-' twin sits ten further
-    q.boff = ((c + (u32)(h >> 32) + 10u * ori) & (TG_BUCKETS - 1)) * TB_SLOTS;
-    q.step = ((((u32)(h >> 40) << 1) | 1u) * TG_SLOTS) & mask;
-    return q;
+    return probe_seq_core(h0, h1, c, ori, mask);
 }
 
 struct Probe {
@@ -317,18 +330,25 @@ __device__ __forceinline__ void ld_first2(const u64* p, u64 (&f)[2], u64 pol)
     asm volatile("ld.global.cg.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(f[0]), "=l"(f[1]) : "l"(p), "l"(pol) : "memory");
 }
 
+// the loads of the home bucket, for a probe whose sequence (pr.q) is set
+template <bool COND>
+__device__ __forceinline__ void probe_load(const ScanParams& P, Probe& pr, u64 pol)
+{
+#ifndef TK_DBG_NOPROBE
+    const u32 i = pr.q.slot();
+    ld_key2(&P.tkeys[i], pr.b, pol);
+    if (COND) ld_first2(&P.tfirst[i], pr.f, pol);
+#endif
+}
+
 // COND: also load the home bucket's `first` words, so that probe_finish can skip the atomic (worth it
 // when the table is much larger than L2: the atomic dirties a DRAM line per mention; measured slower
 // when the table is L2-resident)
 template <bool COND>
 __device__ __forceinline__ void probe_issue(const ScanParams& P, Probe& pr, u64 pol)
 {
-    pr.q = probe_seq(pr.k0, pr.k1, P.table_mask);
-#ifndef TK_DBG_NOPROBE
-    const u32 i = pr.q.slot();
-    ld_key2(&P.tkeys[i], pr.b, pol);
-    if (COND) ld_first2(&P.tfirst[i], pr.f, pol);
-#endif
+    pr.q = probe_seq(pr.k0, pr.k1, P.table_mask, P.bidirected);
+    probe_load<COND>(P, pr, pol);
 }
 
 // Examines one slot whose key was loaded as (s0, s1): claims it if empty.  Returns true if the slot

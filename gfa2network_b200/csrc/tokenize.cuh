@@ -155,7 +155,17 @@ template <int MODE>
 __device__ __forceinline__ void node_issue(const ScanParams& P, const Tile& t, Probe& pr, u32 off, u32 len, u32 ori)
 {
     key_inline(t, off, len, (MODE & TM_BIDIR) != 0, ori, pr.k0, pr.k1);
-    probe_issue<(MODE & TM_COND) != 0>(P, pr, t.pol);
+    if (len == 0) {
+        probe_issue<(MODE & TM_COND) != 0>(P, pr, t.pol);
+        return;
+    }
+    // the probe sequence from what the parser already knows (same result as probe_seq on the packed key):
+    // the cluster byte is the last character of the name, at key position len - 1
+    const u32 pos = len - 1;
+    u64 h0 = pr.k0, h1 = pr.k1;
+    if (pos < 8) h0 &= ~(0xFFull << (8 * pos)); else h1 &= ~(0xFFull << (8 * (pos - 8)));
+    pr.q = probe_seq_core(h0, h1, t.win[off + pos], ((MODE & TM_BIDIR) && ori == '-') ? 1u : 0u, P.table_mask);
+    probe_load<(MODE & TM_COND) != 0>(P, pr, t.pol);
 }
 
 // the first separators of a short line from one 64-bit slice of the separator mask starting at `pos`
