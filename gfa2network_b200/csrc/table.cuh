@@ -323,6 +323,7 @@ struct Probe {
     u64 b[4];  // the two keys of the current bucket
     u64 f[2];  // ~min(order) of the two slots of the HOME bucket, loaded together with its keys
     ProbeSeq q;
+    u32 visited;  // slots' worth of groups left behind (0: still at the home bucket)
 };
 
 __device__ __forceinline__ void ld_first2(const u64* p, u64 (&f)[2], u64 pol)
@@ -334,6 +335,7 @@ __device__ __forceinline__ void ld_first2(const u64* p, u64 (&f)[2], u64 pol)
 template <bool COND>
 __device__ __forceinline__ void probe_load(const ScanParams& P, Probe& pr, u64 pol)
 {
+    pr.visited = 0;
 #ifndef TK_DBG_NOPROBE
     const u32 i = pr.q.slot();
     ld_key2(&P.tkeys[i], pr.b, pol);
@@ -362,37 +364,62 @@ __device__ __forceinline__ bool probe_slot(const ScanParams& P, u32 slot, u64 k0
     return s0 == k0 && s1 == k1;
 }
 
-// Returns the slot index (0xFFFFFFFF if the table is full).  `claimed` is incremented when this call
-// created the key.  Records min(order) as atomicMax(~order) -- fire and forget.
+// One step of a probe whose current bucket is loaded.  True: resolved, `slot` holds the key's slot
+// (0xFFFFFFFF if the table is full; `claimed` is incremented if this call created the key; min(order) is
+// recorded as atomicMax(~order), fire and forget).  False: the next bucket's load is in flight.
+template <bool COND>
+__device__ __forceinline__ bool probe_step(const ScanParams& P, Probe& pr, u64 order, u32& claimed, u64 pol, u32& slot)
+{
+    const u32 i = pr.q.slot();
+#ifdef TK_DBG_NOPROBE
+    slot = i + (u32)(order & 1);  // timing experiment: no table access at all
+    return true;
+#endif
+    // slots are examined in order; an empty slot ends the probe sequence (it is claimed)
+    bool hit = false;
+    if (probe_slot(P, i, pr.k0, pr.k1, pr.b[0], pr.b[1], claimed)) { slot = i; hit = true; }
+    else if (probe_slot(P, i + 1, pr.k0, pr.k1, pr.b[2], pr.b[3], claimed)) { slot = i + 1; hit = true; }
+    if (hit) {
+#ifndef TK_DBG_NOMAX
+        // tfirst only ever grows, so a mention that is not earlier than the value loaded with the home bucket
+        // needs no atomic (a stale value can only cause a redundant one).  Files are read roughly in order:
+        // all but the first mention of a key take this exit, and the slot's line is never dirtied again.
+        if (COND) {
+            const u64 seen = pr.visited ? 0ull : (slot == i ? pr.f[0] : pr.f[1]);
+            if (~order > seen) atomicMax(&P.tfirst[slot], ~order);
+        } else {
+            atomicMax(&P.tfirst[slot], ~order);
+        }
+#endif
+        return true;
+    }
+    if (!pr.q.next(P.table_mask, pr.visited) || pr.visited > 4096u * TG_SLOTS) {
+        atomicOr(&P.cnt->flags, CF_TABLE_FULL);
+        slot = 0xFFFFFFFFu;
+        return true;
+    }
+    ld_key2(&P.tkeys[pr.q.slot()], pr.b, pol);
+    return false;
+}
+
 template <bool COND>
 __device__ __forceinline__ u32 probe_finish(const ScanParams& P, Probe& pr, u64 order, u32& claimed, u64 pol)
 {
-    const u64 k0 = pr.k0, k1 = pr.k1;
-    u32 i = pr.q.slot(), visited = 0, slot;
-    const u32 home = i;
-#ifdef TK_DBG_NOPROBE
-    return i + (u32)(order & 1);  // timing experiment: no table access at all
-#endif
-    while (true) {
-        // slots are examined in order; an empty slot ends the probe sequence (it is claimed)
-        if (probe_slot(P, i, k0, k1, pr.b[0], pr.b[1], claimed)) { slot = i; break; }
-        if (probe_slot(P, i + 1, k0, k1, pr.b[2], pr.b[3], claimed)) { slot = i + 1; break; }
-        if (!pr.q.next(P.table_mask, visited) || visited > 4096u * TG_SLOTS) { atomicOr(&P.cnt->flags, CF_TABLE_FULL); return 0xFFFFFFFFu; }
-        i = pr.q.slot();
-        ld_key2(&P.tkeys[i], pr.b, pol);
-    }
-#ifndef TK_DBG_NOMAX
-    // tfirst only ever grows, so a mention that is not earlier than the value loaded with the home bucket
-    // needs no atomic (a stale value can only cause a redundant one).  Files are read roughly in order:
-    // all but the first mention of a key take this exit, and the slot's line is never dirtied again.
-    if (COND) {
-        const u64 seen = slot == home ? pr.f[0] : (slot == home + 1 ? pr.f[1] : 0ull);
-        if (~order > seen) atomicMax(&P.tfirst[slot], ~order);
-    } else {
-        atomicMax(&P.tfirst[slot], ~order);
-    }
-#endif
+    u32 slot;
+    while (!probe_step<COND>(P, pr, order, claimed, pol, slot)) {}
     return slot;
+}
+
+// Two probes side by side: when both need another bucket, both loads are in flight before either is
+// waited for (the slower chain of the two sets the pace, not their sum).
+template <bool COND>
+__device__ __forceinline__ void probe_finish2(const ScanParams& P, Probe& a, u64 order_a, Probe& b, u64 order_b, u32& claimed, u64 pol, u32& slot_a, u32& slot_b)
+{
+    bool da = false, db = false;
+    do {
+        if (!da) da = probe_step<COND>(P, a, order_a, claimed, pol, slot_a);
+        if (!db) db = probe_step<COND>(P, b, order_b, claimed, pol, slot_b);
+    } while (!(da && db));
 }
 
 __device__ __forceinline__ u32 table_probe(const ScanParams& P, u64 k0, u64 k1, u64 order, u32& claimed)

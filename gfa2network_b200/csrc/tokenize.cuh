@@ -218,8 +218,9 @@ __device__ __forceinline__ bool parse_line_fast(const ScanParams& P, const Tile&
         Probe a, b;
         node_issue<MODE>(P, t, a, p1, len, '+');
         if (BIDIR) node_issue<MODE>(P, t, b, p1, len, '-');
-        probe_finish<(MODE & TM_COND) != 0>(P, a, order0, claimed, t.pol);
-        if (BIDIR) probe_finish<(MODE & TM_COND) != 0>(P, b, order0 | 1, claimed, t.pol);
+        u32 sa, sb;
+        if (BIDIR) probe_finish2<(MODE & TM_COND) != 0>(P, a, order0, b, order0 | 1, claimed, t.pol, sa, sb);
+        else probe_finish<(MODE & TM_COND) != 0>(P, a, order0, claimed, t.pol);
         return true;
     }
     if (c0 == 'P' || c0 == 'O') return t.win[e1] == '\t';  // >= 3 fields; otherwise the generic parser raises
@@ -282,13 +283,12 @@ __device__ __forceinline__ bool parse_line_fast(const ScanParams& P, const Tile&
     Probe na, nb;
     node_issue<MODE>(P, t, na, uo, ul, oc_u);
     node_issue<MODE>(P, t, nb, vo, vl, oc_v);
-    const u32 su = probe_finish<(MODE & TM_COND) != 0>(P, na, order0, claimed, t.pol);
-    const u32 sv = probe_finish<(MODE & TM_COND) != 0>(P, nb, order0 | 1, claimed, t.pol);
+    u32 su, sv;
+    probe_finish2<(MODE & TM_COND) != 0>(P, na, order0, nb, order0 | 1, claimed, t.pol, su, sv);
     if (FOUR) {
         node_issue<MODE>(P, t, na, vo, vl, oc_v == '+' ? '-' : '+');
         node_issue<MODE>(P, t, nb, uo, ul, oc_u == '+' ? '-' : '+');
-        eo.s2 = probe_finish<(MODE & TM_COND) != 0>(P, na, order0 | 2, claimed, t.pol);
-        eo.s3 = probe_finish<(MODE & TM_COND) != 0>(P, nb, order0 | 3, claimed, t.pol);
+        probe_finish2<(MODE & TM_COND) != 0>(P, na, order0 | 2, nb, order0 | 3, claimed, t.pol, eo.s2, eo.s3);
     }
     eo.s0 = su; eo.s1 = sv; eo.w = wv; eo.has = true;
     return true;
