@@ -20,7 +20,7 @@ DTYPE_NP = {0: np.float64, 1: np.float32, 2: np.int32, 3: np.int8, 4: np.bool_}
 EXPORTS = [
     "g2n_abi_version", "g2n_create", "g2n_destroy", "g2n_set_stream", "g2n_host_alloc", "g2n_host_free",
     "g2n_build", "g2n_convert", "g2n_sizes", "g2n_fetch_matrix", "g2n_names_bytes", "g2n_fetch_names", "g2n_device_result",
-    "g2n_status", "g2n_last_error", "g2n_coo_to_compressed", "g2n_set_profile", "g2n_set_speculation", "g2n_kernel_times",
+    "g2n_status", "g2n_last_error", "g2n_coo_to_compressed", "g2n_set_profile", "g2n_set_speculation", "g2n_kernel_times", "g2n_nodes_tsv_bytes", "g2n_fetch_nodes_tsv",
     "g2n_dist_scan", "g2n_dist_export", "g2n_dist_merge", "g2n_dist_entries", "g2n_dist_slab",
 ]
 
@@ -107,6 +107,8 @@ def load():
     lib.g2n_dist_slab.argtypes = [vp, vp, u64, u64, u64]
     lib.g2n_set_profile.argtypes = [vp, C.c_int]
     lib.g2n_set_speculation.argtypes = [vp, C.c_int]
+    lib.g2n_nodes_tsv_bytes.argtypes = [vp, C.POINTER(u64)]
+    lib.g2n_fetch_nodes_tsv.argtypes = [vp, vp]
     lib.g2n_kernel_times.argtypes = [vp, C.POINTER(KTime), C.c_int]
     _lib = lib
     return lib
@@ -159,6 +161,14 @@ class Handle:
 
     def set_profile(self, on: bool):
         self.check(self.lib.g2n_set_profile(self.h, int(on)))
+
+    def fetch_nodes_tsv(self) -> np.ndarray:
+        """The node map file of the last build as bytes: "<index>\\t<name>\\n" per node (utils.py:108-114)."""
+        nb = C.c_uint64()
+        self.check(self.lib.g2n_nodes_tsv_bytes(self.h, C.byref(nb)))
+        out = np.empty(nb.value, dtype=np.uint8)
+        self.check(self.lib.g2n_fetch_nodes_tsv(self.h, C.c_void_p(out.ctypes.data)))
+        return out
 
     def set_speculation(self, on: bool):
         """Repeat builds of the same input size and mode skip the host round trip after the tokenizer

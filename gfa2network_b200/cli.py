@@ -56,13 +56,26 @@ def main(argv: list[str] | None = None) -> None:
         weight_tag=args.weight_tag, store_seq=args.store_seq, store_tags=args.store_tags,
         strip_orientation=args.strip_orientation, verbose=args.verbose, bidirected=args.bidirected,
         keep_directed_bidir=args.keep_directed_bidir, backend=args.backend, dtype=args.dtype,
-        asymmetric=args.asymmetric, raw_bytes_id=args.raw_bytes_id, return_node_list=want_nodes,
+        asymmetric=args.asymmetric, raw_bytes_id=args.raw_bytes_id, return_node_list=False,
         max_tag_mb=args.max_tag_mb, split_on_alignment=args.split_on_alignment)
-    A, nodes = result if want_nodes else (result, None)
+    A = result
+    tsv = None
+    if want_nodes:
+        # the node map file is made on the GPU ("<index>\t<name>\n", utils.py:108-114) instead of building a
+        # Python list of names first; names are validated as UTF-8 where the reference decodes them
+        sess = getattr(A, "_g2n_session", None)
+        if sess is None or not sess.live():
+            raise RuntimeError("the matrix is not backed by a live device build")
+        tsv = sess.handle.fetch_nodes_tsv()
+        if not args.raw_bytes_id:
+            tsv.tobytes().decode()  # builders.py:287 node.decode() raises UnicodeDecodeError here
     A = convert_format(A, args.matrix_format, verbose=args.verbose)  # cli.py:239
     try:
         save_matrix(A, Path(args.matrix), verbose=args.verbose, max_dense_gb=args.max_dense_gb)
     except MemoryError as exc:  # cli.py:247-248
         raise SystemExit(str(exc)) from exc
     if want_nodes:
-        save_node_map(nodes, Path(str(args.matrix) + ".nodes.tsv"))  # cli.py:249-250
+        if args.raw_bytes_id:
+            tsv.tobytes().decode()  # utils.py:112 node.decode() raises here
+        with open(str(args.matrix) + ".nodes.tsv", "wb") as fh:  # cli.py:249-250
+            fh.write(memoryview(tsv))

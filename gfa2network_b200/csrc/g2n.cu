@@ -63,7 +63,9 @@ struct g2n_handle {
     // device buffers (kept between builds: a warm handle allocates nothing)
     DevBuf text, defer, edge_slots, edge_w, longs, tile_info, tile_base, wprefix, slot_id, id2slot, name_len, name_off, names;
     DevBuf rowptr, cursor, entries, w_emit, biglist, ucnt, indptr, indices, data, row, col, scan_state;
-    DevBuf up_row, up_col, up_data;
+    DevBuf up_row, up_col, up_data, tsv, tsv_off;
+    bool tsv_ready = false;
+    u64 tsv_bytes = 0;
     // zero-initialised state, one memset per arena and build:
     //   zearly  hash table (keys | first | rep), counters + DevSizes, look-back state of the tile scan
     //   zids    first-appearance bitmap, look-back state of its scan
@@ -518,7 +520,7 @@ void g2n_destroy(g2n_handle* h)
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->text, &h->zearly, &h->zids, &h->zrows, &h->defer, &h->edge_slots, &h->edge_w, &h->longs, &h->tile_info, &h->tile_base, &h->wprefix,
                       &h->slot_id, &h->id2slot, &h->name_len, &h->name_off, &h->names, &h->rowptr, &h->cursor, &h->entries, &h->w_emit, &h->biglist, &h->ucnt, &h->indptr, &h->indices, &h->data, &h->row, &h->col,
-                      &h->scan_state, &h->up_row, &h->up_col, &h->up_data, &h->gtable, &h->gfirst, &h->gslot_id, &h->dest_cnt};
+                      &h->scan_state, &h->up_row, &h->up_col, &h->up_data, &h->tsv, &h->tsv_off, &h->gtable, &h->gfirst, &h->gslot_id, &h->dest_cnt};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(h->ev[i]);
     for (KTimer& t : h->ktimers) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
@@ -663,6 +665,7 @@ static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, c
     h->built = false;
     h->have_edges = false;
     h->names_ready = false;
+    h->tsv_ready = false;
     h->edges_are_ids = false;
     h->spec = spec;
     if (p->dtype < G2N_DTYPE_F64 || p->dtype > G2N_DTYPE_BOOL) { h->err = "unknown dtype"; return G2N_ERR_INVALID; }
@@ -1115,6 +1118,54 @@ int g2n_fetch_names(g2n_handle* h, uint8_t* names, uint64_t* offsets)
     }
     CK(cudaMemcpyAsync(offsets, h->name_off.p, (h->n_nodes + 1) * sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
     if (h->names_bytes) CK(cudaMemcpyAsync(names, h->names.p, h->names_bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return G2N_OK;
+}
+
+// "<index>\t<name>\n" per node (utils.py:108-114), made on the device
+static int build_tsv(g2n_handle* h)
+{
+    if (h->tsv_ready) return G2N_OK;
+    const u64 n = h->n_nodes;
+    CK(h->tsv_off.ensure((n + 2) * sizeof(u64)));
+    if (n > 0) {
+        LoadTsvLen ll{h->name_len.as<u32>()};
+        int rc = launch_scan<u64>(h, ll, h->tsv_off.as<u64>(), nullptr, n, nullptr, nullptr);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(&h->h_tail[4], h->tsv_off.as<u64>() + n, sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    } else {
+        h->h_tail[4] = 0;
+    }
+    h->tsv_bytes = h->h_tail[4];
+    CK(h->tsv.ensure(h->tsv_bytes + 16));
+    if (n > 0) {
+        KScope ks(h, "k_tsv_write");
+        k_tsv_write<<<grid_for(n, 256), 256, 0, h->stream>>>(h->slab_mode ? h->gtable.as<TKey>() : h->d_tkeys, h->d_trep, h->id2slot.as<u32>(), h->tsv_off.as<u64>(), (u32)n, h->d_text,
+                                                              h->longs.as<LongDesc>(), h->tsv.as<uint8_t>());
+        CK(cudaGetLastError());
+    }
+    h->tsv_ready = true;
+    return G2N_OK;
+}
+
+int g2n_nodes_tsv_bytes(g2n_handle* h, uint64_t* out)
+{
+    if (!h || !out || !h->built) return G2N_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    int rc = build_tsv(h);
+    if (rc) return rc;
+    *out = h->tsv_bytes;
+    return G2N_OK;
+}
+
+int g2n_fetch_nodes_tsv(g2n_handle* h, uint8_t* out)
+{
+    if (!h || !h->built) return G2N_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    int rc = build_tsv(h);
+    if (rc) return rc;
+    if (h->tsv_bytes) CK(cudaMemcpyAsync(out, h->tsv.p, h->tsv_bytes, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return G2N_OK;
 }

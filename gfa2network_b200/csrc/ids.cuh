@@ -119,6 +119,47 @@ __global__ void __launch_bounds__(256) k_gather_names(const TKey* __restrict__ t
     }
 }
 
+// ---------------------------------------------------------------- node map as text (utils.py:108-114)
+// "<index>\t<name>\n" per node, in ID order: the file save_node_map writes next to the matrix.
+__device__ __forceinline__ u32 dec_digits(u32 v)
+{
+    u32 d = 1;
+    while (v >= 10) { v /= 10; d++; }
+    return d;
+}
+struct LoadTsvLen {  // bytes of node i's line
+    const u32* name_len;
+    __device__ __forceinline__ u64 operator()(u64 i) const { return (u64)dec_digits((u32)i) + name_len[i] + 2; }
+    __device__ __forceinline__ u64 peek(u64 i) const { return (*this)(i); }
+};
+__global__ void __launch_bounds__(256) k_tsv_write(const TKey* __restrict__ tkeys, const u32* __restrict__ trep,
+                                                    const u32* __restrict__ id2slot, const u64* __restrict__ line_off, u32 n,
+                                                    const uint8_t* __restrict__ text, const LongDesc* __restrict__ longs,
+                                                    uint8_t* __restrict__ out)
+{
+    for (u32 id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
+        uint8_t* dst = out + line_off[id];
+        const u32 nd = dec_digits(id);
+        u32 v = id;
+        for (u32 k = nd; k-- > 0;) { dst[k] = (uint8_t)('0' + v % 10); v /= 10; }
+        dst += nd;
+        *dst++ = '\t';
+        const u32 slot = id2slot[id];
+        const TKey k = tkeys[slot];
+        const u32 top = (u32)(k.y >> 56);
+        u32 L;
+        if (top != 0xFF) {
+            L = top - 1;
+            for (u32 j = 0; j < L; j++) dst[j] = (uint8_t)((j < 8 ? k.x >> (8 * j) : k.y >> (8 * (j - 8))) & 0xFF);
+        } else {
+            const LongDesc d = longs[trep[slot] - 1];
+            L = d.base_len + (d.has_ori ? 1 + d.ori_len : 0);
+            for (u32 j = 0; j < L; j++) dst[j] = long_byte(text, d, j);
+        }
+        dst[L] = '\n';
+    }
+}
+
 // ---------------------------------------------------------------- dtype helpers
 // The reference casts the float64 weight list to `dtype` when the COO matrix is built
 // (builders.py:281 -> scipy/_coo.py), i.e. BEFORE duplicates are summed.

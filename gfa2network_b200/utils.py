@@ -1,6 +1,7 @@
 """Host-side mirror of ``gfa2network/utils.py``: ``convert_format`` (``:40-63``) finishes
-COO -> CSR/CSC on the GPU (stage K4); ``save_matrix`` / ``save_node_map`` (``:66-114``) are the
-reference's plain host writers."""
+COO -> CSR/CSC on the GPU (stage K4); ``save_matrix`` (``:66-105``) writes the same ``.npz`` members with a
+multi-threaded deflate (``writers.py``); ``save_node_map`` (``:108-114``) is the reference's host writer for
+arbitrary node lists -- the CLI writes the node map of a device build from GPU-made bytes instead."""
 from __future__ import annotations
 
 import ctypes as C
@@ -87,7 +88,9 @@ def save_matrix(A, dest: Path, *, verbose: bool = False, max_dense_gb: float = 5
         start = time.perf_counter()
         print(f"[save] {dest.suffix[1:]} → {dest}", "...", end="", file=sys.stderr, flush=True)
     if dest.suffix == ".npz":
-        sp.save_npz(dest, A)
+        from .writers import save_npz_parallel
+
+        save_npz_parallel(dest, A)  # same members as sp.save_npz(dest, A) (utils.py:86), deflated on all host cores
     elif dest.suffix == ".npy":
         np.save(dest, A.toarray() if sp.issparse(A) else A)
     elif dest.suffix == ".csv":

@@ -150,6 +150,11 @@ int g2n_names_bytes(g2n_handle *h, uint64_t *out);
  * `offsets` = n_nodes+1 uint64 offsets into it. */
 int g2n_fetch_names(g2n_handle *h, uint8_t *names, uint64_t *offsets);
 
+/* The node map as text, "<index>\t<name>\n" per node in ID order -- the bytes save_node_map writes
+ * (utils.py:108-114) -- produced on the device.  g2n_nodes_tsv_bytes sizes it, g2n_fetch_nodes_tsv copies it. */
+int g2n_nodes_tsv_bytes(g2n_handle *h, uint64_t *out);
+int g2n_fetch_nodes_tsv(g2n_handle *h, uint8_t *out);
+
 /* Device pointers of the resident result (for device-side consumers / benchmarks). */
 int g2n_device_result(g2n_handle *h, void **a0, void **a1, void **data);
 
