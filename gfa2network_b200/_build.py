@@ -12,7 +12,7 @@ LIB = PKG / "libg2n.so"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
+    "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC,-pthread",
 ]
 
 

@@ -5,6 +5,7 @@ every entry point raises -- there is no CPU fallback."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
@@ -19,7 +20,7 @@ DTYPE_NP = {0: np.float64, 1: np.float32, 2: np.int32, 3: np.int8, 4: np.bool_}
 
 EXPORTS = [
     "g2n_abi_version", "g2n_create", "g2n_destroy", "g2n_set_stream", "g2n_host_alloc", "g2n_host_free",
-    "g2n_build", "g2n_convert", "g2n_sizes", "g2n_fetch_matrix", "g2n_names_bytes", "g2n_fetch_names", "g2n_device_result",
+    "g2n_build", "g2n_build_file", "g2n_convert", "g2n_sizes", "g2n_fetch_matrix", "g2n_names_bytes", "g2n_fetch_names", "g2n_device_result",
     "g2n_status", "g2n_last_error", "g2n_coo_to_compressed", "g2n_set_profile", "g2n_set_speculation", "g2n_kernel_times", "g2n_nodes_tsv_bytes", "g2n_fetch_nodes_tsv",
     "g2n_dist_scan", "g2n_dist_export", "g2n_dist_merge", "g2n_dist_entries", "g2n_dist_slab",
 ]
@@ -89,6 +90,7 @@ def load():
     lib.g2n_host_free.argtypes = [vp]
     lib.g2n_host_free.restype = None
     lib.g2n_build.argtypes = [vp, vp, u64, C.POINTER(Params)]
+    lib.g2n_build_file.argtypes = [vp, C.c_char_p, C.POINTER(Params)]
     lib.g2n_convert.argtypes = [vp, i32]
     lib.g2n_sizes.argtypes = [vp, C.POINTER(Sizes)]
     lib.g2n_fetch_matrix.argtypes = [vp, vp, vp, vp]
@@ -192,6 +194,9 @@ class Handle:
 
     def build(self, text_ptr: int, nbytes: int, params: Params) -> int:
         return self.lib.g2n_build(self.h, C.c_void_p(text_ptr), nbytes, C.byref(params))
+
+    def build_file(self, path: str, params: Params) -> int:
+        return self.lib.g2n_build_file(self.h, os.fsencode(path), C.byref(params))
 
     def convert(self, fmt: int):
         self.check(self.lib.g2n_convert(self.h, fmt))

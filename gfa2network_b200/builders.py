@@ -58,6 +58,16 @@ class _Session:
         return self.handle.h is not None and getattr(self.handle, "_current_token", None) == self.token
 
 
+class _FileSource:
+    def __init__(self, path: str):
+        self.path = path
+
+    def read_at(self, off: int, n: int) -> bytes:
+        with open(self.path, "rb") as fh:
+            fh.seek(off)
+            return fh.read(n)
+
+
 def _read_source(path):
     """Returns (host uint8 array | None, device pointer | None, nbytes, keepalive)."""
     if hasattr(path, "is_cuda") and hasattr(path, "data_ptr"):  # torch tensor (extension)
@@ -82,8 +92,11 @@ def _read_source(path):
             with gzip.open(p, "rb") as fh:  # parser.py:108-109
                 raw = fh.read()
         else:
-            arr = np.fromfile(p, dtype=np.uint8)  # parser.py:111
-            return arr, None, arr.size, arr
+            # parser.py:111 open(path, "rb"): the library reads the file itself (g2n_build_file: reader threads ->
+            # pinned staging buffers -> device, tokenized piece by piece behind the copy)
+            with open(p, "rb"):  # same FileNotFoundError / PermissionError / IsADirectoryError as the reference
+                pass
+            return None, None, os.path.getsize(p), _FileSource(p)
         arr = np.frombuffer(raw, dtype=np.uint8)
         return arr, None, arr.size, raw
     if hasattr(path, "read"):  # binary file object, parser.py:90-92
@@ -100,7 +113,7 @@ def _raise_parse_error(diag, host):
         # host to raise the identical exception (parser.py:214, 291-293, 337-339)
         if host is not None:
             off = int(diag.err_offset)
-            tail = host[off:off + (1 << 20)].tobytes()
+            tail = host.read_at(off, 1 << 20) if isinstance(host, _FileSource) else host[off:off + (1 << 20)].tobytes()
             line = tail.split(b"\n", 1)[0]
             f = line.split(b"\t")
             cand = {b"L": (4,), b"E": (3, 5), b"C": (2, 4)}.get(f[0], ())
@@ -204,8 +217,12 @@ def parse_gfa(
         int(bool(directed)), int(bool(bidirected)), int(bool(keep_directed_bidir)), int(bool(asymmetric)),
         int(bool(strip_orientation)), _capi.DTYPES[dt.name], want, 0 if dev_ptr is None else 1,
         wt, len(wt) if wt else 0, 0)
-    ptr = dev_ptr if dev_ptr is not None else (host.ctypes.data if nbytes else 0)
-    rc = handle.build(ptr, nbytes, params)
+    if isinstance(keep, _FileSource):
+        host = keep
+        rc = handle.build_file(keep.path, params)
+    else:
+        ptr = dev_ptr if dev_ptr is not None else (host.ctypes.data if nbytes else 0)
+        rc = handle.build(ptr, nbytes, params)
     diag = handle.status()
     if rc in (_capi.G2N_OK, _capi.G2N_ERR_PARSE):
         if diag.unknown_byte >= 0:

@@ -9,7 +9,14 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/g2n.h"
@@ -101,6 +108,14 @@ struct g2n_handle {
     u32 tk_attr = 0;     // tokenizer specialisations whose dynamic shared memory opt-in was set on this device
     u32 n_pieces = 0;    // host text of the current build: copy pieces still to be waited for (0: text is on the device)
     u64 piece_bytes = 0;
+    // file source (g2n_build_file): reader threads pread() pieces into pinned staging buffers and queue the copies
+    int src_fd = -1;
+    bool src_resident = false;  // the file is already in h->text (second pass of the same g2n_build_file call)
+    std::vector<void*> stage;
+    std::vector<cudaEvent_t> stage_ev;
+    std::vector<std::thread> readers;
+    std::unique_ptr<std::atomic<int>[]> piece_issued;
+    std::atomic<int> reader_err{0};
     bool gang_scan = true;  // scans run as one co-resident gang (cooperative launch); cleared if the launch is refused
     u64 cap_n = 0, cap_E = 0, cap_R = 0;  // what this build's buffers were sized for
     // state of the last build
@@ -444,6 +459,7 @@ void collect_diag(g2n_handle* h, const Counters& hc, u64 n_records)
 }
 
 #define G2N_H2D_PIECE ((u64)8 << 20)  // bytes per host -> device copy piece
+#define G2N_READERS 4                  // file reader threads (g2n_build_file)
 #define G2N_SPEC_MISS 1000  // internal: the speculative build has to be repeated with a host round trip
 
 // The one host round trip of a build: counters + device-side sizes come back, timings are read.
@@ -527,6 +543,8 @@ void g2n_destroy(g2n_handle* h)
     if (h->h_ctl) cudaFreeHost(h->h_ctl);
     if (h->h_tail) cudaFreeHost(h->h_tail);
     for (cudaEvent_t e : h->copy_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->stage_ev) cudaEventDestroy(e);
+    for (void* b : h->stage) cudaFreeHost(b);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -692,6 +710,64 @@ static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, c
         CK(h->text.ensure(nbytes + 64));
         if (nbytes) CK(cudaMemcpyAsync(h->text.p, text, nbytes, cudaMemcpyDeviceToDevice, h->stream));
         h->d_text = h->text.as<uint8_t>();
+    } else if (h->src_fd >= 0 && h->src_resident) {
+        h->d_text = h->text.as<uint8_t>();
+        h->n_pieces = 0;
+    } else if (h->src_fd >= 0) {
+        // file source: G2N_READERS threads pread() 8 MiB pieces into pinned staging buffers (two per thread) and queue
+        // their copies on the copy stream; the tokenizer is launched piece by piece behind them (as for a host text)
+        CK(h->text.ensure(nbytes + 64));
+        h->d_text = h->text.as<uint8_t>();
+        h->n_pieces = 0;
+        if (nbytes) {
+            const u64 piece = G2N_H2D_PIECE;
+            const u32 np = (u32)((nbytes + piece - 1) / piece);
+            const u32 R = np < G2N_READERS ? np : G2N_READERS;
+            while (h->copy_ev.size() < np + 1) {
+                cudaEvent_t e;
+                CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                h->copy_ev.push_back(e);
+            }
+            while (h->stage.size() < 2 * G2N_READERS) {
+                void* b = nullptr;
+                CK(cudaHostAlloc(&b, piece, cudaHostAllocDefault));
+                h->stage.push_back(b);
+                cudaEvent_t e;
+                CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                h->stage_ev.push_back(e);
+            }
+            h->piece_issued.reset(new std::atomic<int>[np]);
+            for (u32 k = 0; k < np; k++) h->piece_issued[k].store(0);
+            h->reader_err.store(0);
+            CK(cudaEventRecord(h->copy_ev[np], h->stream));
+            CK(cudaStreamWaitEvent(h->copy_stream, h->copy_ev[np], 0));
+            uint8_t* dtext = h->text.as<uint8_t>();
+            for (u32 r = 0; r < R; r++) {
+                h->readers.emplace_back([h, r, R, np, piece, nbytes, dtext]() {
+                    cudaSetDevice(h->device);
+                    for (u32 k = r, turn = 0; k < np; k += R, turn++) {
+                        const u32 sb = 2 * r + (turn & 1);
+                        cudaEventSynchronize(h->stage_ev[sb]);  // the previous copy out of this staging buffer is done
+                        const u64 a = (u64)k * piece, len = (a + piece < nbytes ? a + piece : nbytes) - a;
+                        u64 got = 0;
+                        while (got < len) {
+                            const ssize_t n = pread(h->src_fd, (uint8_t*)h->stage[sb] + got, len - got, (off_t)(a + got));
+                            if (n <= 0) { h->reader_err.store(1); break; }
+                            got += (u64)n;
+                        }
+                        if (got == len) {
+                            if (cudaMemcpyAsync(dtext + a, h->stage[sb], len, cudaMemcpyHostToDevice, h->copy_stream) != cudaSuccess ||
+                                cudaEventRecord(h->copy_ev[k], h->copy_stream) != cudaSuccess ||
+                                cudaEventRecord(h->stage_ev[sb], h->copy_stream) != cudaSuccess)
+                                h->reader_err.store(2);
+                        }
+                        h->piece_issued[k].store(1, std::memory_order_release);
+                    }
+                });
+            }
+            h->n_pieces = np;
+            h->piece_bytes = piece;
+        }
     } else {
         // host text: copied in pieces on a second stream; the tokenizer is launched piece by piece behind it
         CK(h->text.ensure(nbytes + 64));
@@ -804,6 +880,9 @@ static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, c
             const u32 n_launch = h->n_pieces > 1 ? h->n_pieces : 1;
             u32 t_begin = 0;
             for (u32 k = 0; k < n_launch; k++) {
+                if (h->n_pieces && !h->readers.empty()) {
+                    while (!h->piece_issued[k].load(std::memory_order_acquire)) std::this_thread::yield();  // its copy is queued
+                }
                 if (h->n_pieces) CK(cudaStreamWaitEvent(h->stream, h->copy_ev[k], 0));
                 u32 t_end = n_tiles;
                 if (k + 1 < n_launch) {
@@ -832,6 +911,10 @@ static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, c
 #undef G2N_TK
                 t_begin = t_end;
             }
+            for (std::thread& t : h->readers) t.join();
+            h->readers.clear();
+            if (h->reader_err.load()) { h->err = h->reader_err.load() == 1 ? "reading the input file failed" : "queueing a copy of the input file failed"; return G2N_ERR_CUDA; }
+            if (h->src_fd >= 0) h->src_resident = true;
             h->n_pieces = 0;  // a capacity retry finds the whole text on the device
             P.tile_begin = 0;
             P.tile_end = n_tiles;
@@ -1020,6 +1103,27 @@ int g2n_build(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n_par
     h->hint_valid = true;
     h->built = true;
     return G2N_OK;
+}
+
+int g2n_build_file(g2n_handle* h, const char* path, const g2n_params* p)
+{
+    if (!h || !path || !p) return G2N_ERR_INVALID;
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) { h->err = std::string("cannot open ") + path; return G2N_ERR_INVALID; }
+    struct stat st;
+    if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) { close(fd); h->err = "not a regular file"; return G2N_ERR_INVALID; }
+    g2n_params q = *p;
+    q.text_on_device = 0;
+    h->src_fd = fd;
+    h->src_resident = false;
+    // any non-null pointer: the bytes come from the file, never from this address
+    const int rc = g2n_build(h, (const uint8_t*)h, (uint64_t)st.st_size, &q);
+    for (std::thread& t : h->readers) t.join();  // (only after an early error return)
+    h->readers.clear();
+    h->src_fd = -1;
+    h->src_resident = false;
+    close(fd);
+    return rc;
 }
 
 int g2n_convert(g2n_handle* h, int32_t want_format)

@@ -132,6 +132,12 @@ void g2n_host_free(void *p);
  * until the next build or g2n_destroy.  On G2N_ERR_PARSE consult g2n_status(). */
 int g2n_build(g2n_handle *h, const uint8_t *text, uint64_t nbytes, const g2n_params *p);
 
+/* Same build with the text read from a regular file (the reference opens the path itself,
+ * parser.py:100-112): reader threads pread() 8 MiB pieces into pinned staging buffers, the pieces are
+ * copied to the device as they arrive and tokenized behind the copy.  `p->text_on_device` is ignored.
+ * stdin and .gz sources stay with the caller (read / inflate on the host, then g2n_build). */
+int g2n_build_file(g2n_handle *h, const char *path, const g2n_params *p);
+
 /* Convert the device-resident raw COO of the last build to CSR/CSC in place of calling
  * convert_format(A, fmt) on the host (utils.py:55).  No-op if already in that format. */
 int g2n_convert(g2n_handle *h, int32_t want_format);

@@ -195,3 +195,37 @@ def test_speculative_builds_hit_and_miss():
             assert h.status().speculative == 0
     finally:
         h.set_speculation(True)
+
+
+def test_file_source_streams_in_pieces(tmp_path):
+    """A path is read by the library itself (g2n_build_file: reader threads -> pinned staging -> device, the
+    tokenizer launched behind every 8 MiB piece): same result as the bytes, also for an error in a late
+    piece, an empty file, and when the same handle repeats the build (speculative path)."""
+    from gfa2network_b200 import parse_gfa
+    from gfa2network_b200.synth import synth_gfa
+    from oracle.oracle import oracle_parse_gfa
+
+    text = synth_gfa(400_000, 1_200_000, seed=61, kind=1, n_paths=1, n_walks=1)
+    assert text.size > 4 * (8 << 20)  # several pieces, every reader thread gets work
+    p = tmp_path / "big.gfa"
+    p.write_bytes(text.tobytes())
+    want, wnodes = oracle_parse_gfa(text, return_node_list=True)
+    for _ in range(3):
+        A, nodes = parse_gfa(p, build_graph=False, build_matrix=True, return_node_list=True)
+        _same(A, want, "file")
+        assert nodes == wnodes
+    _same(parse_gfa(str(p), build_graph=False, build_matrix=True, directed=False), oracle_parse_gfa(text, directed=False), "file undirected")
+    bad = bytearray(text.tobytes())
+    pos = bytes(bad).rindex(b"\nL\t")  # the last link: several pieces into the file
+    assert pos > 3 * (8 << 20)
+    end = bytes(bad).index(b"\n", pos + 1)
+    bad[pos + 1:end] = b"L\tx" + b" " * (end - pos - 4)
+    q = tmp_path / "bad.gfa"
+    q.write_bytes(bytes(bad))
+    with pytest.raises(ValueError, match="Malformed L record"):
+        parse_gfa(q, build_graph=False, build_matrix=True)
+    e = tmp_path / "empty.gfa"
+    e.write_bytes(b"")
+    _same(parse_gfa(e, build_graph=False, build_matrix=True), oracle_parse_gfa(b""), "empty file")
+    with pytest.raises(FileNotFoundError):
+        parse_gfa(tmp_path / "missing.gfa", build_graph=False, build_matrix=True)
