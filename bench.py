@@ -170,11 +170,12 @@ def algo_bytes(name, st):
         "k_rows_sort": 2 * ent * M + 8 * n,                        # entries in and (sorted) out, rowptr in, counts out
         "k_rows_write": ent * M + 8 * n + 12 * nnz,                # entries in, rowptr + indptr in, indices/data out
         "k_emit_coo": 4 * spe * E + 16 * M,
-        "k_dist_insert": 32 * n,            # n = global nodes: every rank inserts every rank's distinct keys
-        "k_dist_dest_count": 2 * 4 * spe * E,
-        "k_dist_dest_scatter": 4 * spe * E + 16 * M,
-        "k_pairs_count": 16 * M,
-        "k_pairs_scatter": 24 * M,
+        # multi-GPU (dist.cuh); n = keys of this shard, M = row entries of this shard / slab
+        "k_dx_export": 24 * 2 * n + 24 * n,   # local table in (keys + first at load <= 0.5), key + order + position out
+        "k_dx_insert": 20 * n + 24 * n + 4 * n,
+        "k_dx_entries": 2 * 4 * spe * E + 8 * M,
+        "k_pairs_count": 8 * M + 4 * M,
+        "k_pairs_scatter": 8 * M + 4 * M + 4 * M,
     }
     return table.get(name)
 
@@ -375,8 +376,9 @@ def run_ours(args):
         "dtype": "u8/int32/f64", "data": "synthetic",
         "config": {"workload": workload_name(args.config, args.scale, n_seg, n_link, cfg), "text_bytes_per_gpu": nbytes,
                    "l2": "flushed between steps (512 MiB write)", "nodes": int(sz.n_nodes), "nnz": int(sz.nnz),
-                   "sharding": ("one shard of this shape per GPU; NCCL all-gather of the node dictionary, all-to-all of row entries "
-                                "by owner row block, per-GPU CSR slab") if world > 1 else "single GPU"},
+                   "sharding": ("one shard of this shape per GPU, ONE graph; hash-partitioned node dictionary and row entries by owner row "
+                                "block, both written straight into peer memory over NVLink by the kernels (no collective library, no "
+                                "host round trip inside a step); per-GPU CSR slab") if world > 1 else "single GPU"},
         "edges_per_s": world * n_link / (ms_step / 1e3),
         "path_roofline": {"algorithmic_bytes": int(nbytes + out_bytes), "achieved": path_ach, "peak": peak, "frac": path_ach / peak, "unit": "GB/s"},
         "roofline": roof,

@@ -12,7 +12,8 @@ import numpy as np
 
 from . import _build
 
-G2N_OK, G2N_ERR_CUDA, G2N_ERR_INVALID, G2N_ERR_PARSE, G2N_ERR_UNSUPPORTED, G2N_ERR_INTERNAL = range(6)
+G2N_OK, G2N_ERR_CUDA, G2N_ERR_INVALID, G2N_ERR_PARSE, G2N_ERR_UNSUPPORTED, G2N_ERR_INTERNAL, G2N_ERR_RETRY = range(7)
+ABI_VERSION = 2
 FMT_NATIVE, FMT_CSR, FMT_CSC, FMT_COO = 0, 1, 2, 3
 FMT_NAMES = {FMT_CSR: "csr", FMT_CSC: "csc", FMT_COO: "coo"}
 DTYPES = {"float64": 0, "float32": 1, "int32": 2, "int8": 3, "bool": 4}
@@ -22,7 +23,8 @@ EXPORTS = [
     "g2n_abi_version", "g2n_create", "g2n_destroy", "g2n_set_stream", "g2n_host_alloc", "g2n_host_free",
     "g2n_build", "g2n_build_file", "g2n_convert", "g2n_sizes", "g2n_fetch_matrix", "g2n_names_bytes", "g2n_fetch_names", "g2n_device_result",
     "g2n_status", "g2n_last_error", "g2n_coo_to_compressed", "g2n_set_profile", "g2n_set_speculation", "g2n_kernel_times", "g2n_nodes_tsv_bytes", "g2n_fetch_nodes_tsv",
-    "g2n_dist_scan", "g2n_dist_export", "g2n_dist_merge", "g2n_dist_entries", "g2n_dist_slab",
+    "g2n_dist_init", "g2n_dist_probe", "g2n_dist_plan", "g2n_dist_local_mem", "g2n_dist_set_peers", "g2n_dist_open_peers",
+    "g2n_dist_close_peers", "g2n_dist_stage", "g2n_dist_finish",
 ]
 
 
@@ -39,13 +41,19 @@ class Sizes(C.Structure):
     _fields_ = [
         ("n_nodes", C.c_uint64), ("nnz", C.c_uint64), ("names_bytes", C.c_uint64),
         ("format", C.c_int32), ("index_bytes", C.c_int32), ("dtype", C.c_int32), ("reserved", C.c_int32),
-        ("slab_rows", C.c_uint64),
+        ("slab_rows", C.c_uint64), ("names_count", C.c_uint64), ("names_id0", C.c_uint64),
     ]
 
 
 class DistInfo(C.Structure):
     _fields_ = [("n_keys", C.c_uint64), ("n_tiles", C.c_uint64), ("n_records", C.c_uint64),
                 ("n_edge_records", C.c_uint64), ("n_entries", C.c_uint64), ("reserved", C.c_uint64)]
+
+
+class DistResult(C.Structure):
+    _fields_ = [("bad", C.c_uint64), ("n_global", C.c_uint64), ("row0", C.c_uint64), ("n_rows", C.c_uint64), ("nnz", C.c_uint64),
+                ("n_recv", C.c_uint64), ("n_first", C.c_uint64), ("id0", C.c_uint64), ("n_keys", C.c_uint64), ("n_records", C.c_uint64),
+                ("n_edge_records", C.c_uint64), ("keys_to", C.c_uint64 * 8), ("pairs_to", C.c_uint64 * 8)]
 
 
 class Diag(C.Structure):
@@ -102,11 +110,15 @@ def load():
     lib.g2n_last_error.restype = C.c_char_p
     lib.g2n_coo_to_compressed.argtypes = [vp, vp, vp, vp, u64, u64, i32, i32, vp, vp, vp, C.POINTER(u64)]
     pu64 = C.POINTER(u64)
-    lib.g2n_dist_scan.argtypes = [vp, vp, u64, C.POINTER(Params), C.POINTER(DistInfo)]
-    lib.g2n_dist_export.argtypes = [vp, vp, vp]
-    lib.g2n_dist_merge.argtypes = [vp, vp, u64, pu64, vp, u64, pu64, u64, C.c_int, pu64]
-    lib.g2n_dist_entries.argtypes = [vp, C.c_int, u64, u64, vp, u64, pu64]
-    lib.g2n_dist_slab.argtypes = [vp, vp, u64, u64, u64]
+    lib.g2n_dist_init.argtypes = [vp, C.c_int, C.c_int]
+    lib.g2n_dist_probe.argtypes = [vp, vp, u64, C.POINTER(Params), C.POINTER(DistInfo)]
+    lib.g2n_dist_plan.argtypes = [vp, u64, u64, u64, u64, C.c_int, C.POINTER(C.c_int)]
+    lib.g2n_dist_local_mem.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), vp]
+    lib.g2n_dist_set_peers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    lib.g2n_dist_open_peers.argtypes = [vp, C.c_char_p]
+    lib.g2n_dist_close_peers.argtypes = [vp]
+    lib.g2n_dist_stage.argtypes = [vp, C.c_int, vp, u64, C.POINTER(Params), C.c_int]
+    lib.g2n_dist_finish.argtypes = [vp, C.POINTER(DistResult)]
     lib.g2n_set_profile.argtypes = [vp, C.c_int]
     lib.g2n_set_speculation.argtypes = [vp, C.c_int]
     lib.g2n_nodes_tsv_bytes.argtypes = [vp, C.POINTER(u64)]
@@ -217,7 +229,7 @@ class Handle:
         self.check(self.lib.g2n_names_bytes(self.h, C.byref(nb)))
         s = self.sizes()
         names = np.empty(max(1, nb.value), dtype=np.uint8)
-        offs = np.empty(s.n_nodes + 1, dtype=np.uint64)
+        offs = np.empty(s.names_count + 1, dtype=np.uint64)
         self.check(self.lib.g2n_fetch_names(self.h, names.ctypes.data, offs.ctypes.data))
         return names[: nb.value], offs
 

@@ -1,190 +1,518 @@
-// dist.cuh -- device side of the multi-GPU build (one process per GPU; the host moves the exchange
-// buffers between ranks with NCCL, see gfa2network_b200/dist.py and SURVEY.md 8(e)).
+// dist.cuh -- device side of the multi-GPU build: one process and one handle per GPU.
 //
-//   phase 1  every rank tokenizes its own byte range (k_tokenize, local table, local `order`)
-//   phase 2  k_dist_export: local distinct keys + their first local order  -> all-gather ->
-//            k_dist_insert: every rank builds the same global table keyed by the same bytes, keeping the
-//            global first appearance (records before the rank + records before the tile + index in tile);
-//            IDs by the same bitmap ranking as on one GPU; k_dist_localmap: local slot -> global ID
-//   phase 3  k_dist_dest_count / k_dist_dest_scatter: row entries bucketed by owner(row) -> all-to-all ->
-//            k_pairs_count / k_pairs_scatter + the single-GPU row sort: each rank builds its CSR slab
+// Nothing here goes through the host or through a collective library: every exchange is a kernel that
+// WRITES STRAIGHT INTO THE PEER'S MEMORY over NVLink (peer pointers from CUDA IPC, or plain pointers when
+// several logical ranks share one device) followed by a one-warp signal kernel that publishes per-source
+// headers and an epoch flag in the peer's control block; the consuming kernel of the peer spins on those
+// flags (acquire, system scope) before it touches the data.  A whole build is queued on the stream
+// without a host round trip; the host synchronises once, at the end.
+//
+//   stage 0  k_tokenize (this rank's byte range: local table, local first-appearance order)
+//            k_dx_export     distinct local keys + first local order  --> owner = hash(key) % world     [x1]
+//   stage 1  k_dx_insert     owner table: min over (source rank, local order) = global first appearance
+//            k_dx_reply_first  owner -> every source: "your mention is the global first"               [x2]
+//   stage 2  k_dx_mark + scan  bitmap of this shard's global firsts -> rank among them (builders.py:194-198:
+//                            ID = number of earlier first appearances)
+//            k_dx_send_rank  first source -> owner: rank inside the shard; count of firsts in the header [x3]
+//   stage 3  k_dx_reply_ids  owner -> every source: ID = (firsts of lower shards) + rank               [x4]
+//   stage 4  k_dx_localmap   local slot -> global node ID
+//            k_dx_entries    row entries --> owner(row) = row / ceil(n / world)                         [x5]
+//   stage 5  k_dx_slab_sizes, k_pairs_count / scan / k_pairs_scatter + the single-GPU row kernels:
+//            duplicate sum / max(S, S^T) -> this rank's CSR slab (builders.py:279-283, utils.py:55)
+//            status word to every rank                                                                  [x6]
+//   stage 6  k_dx_final      the build's verdict, the same on every rank: a capacity miss anywhere repeats the
+//                            build everywhere
+// Per-rank work is proportional to the rank's own shard (keys are hash-partitioned, nobody holds the
+// whole dictionary).  Node names stay with the shard of their first appearance: shard s names the
+// consecutive IDs [idbase[s], idbase[s] + firsts[s]).
 // Restricted to inline (<= 15 byte) keys and unweighted builds; the host mirror refuses anything else.
 #pragma once
 #include "rowsort.cuh"
 
 namespace g2n {
 
-struct DistKey {
-    u64 k0, k1;
-    u64 order;  // local order (export) -- rewritten to the global order by the receiver
+#define DX_MAXW 8
+#define DX_NEX 6  // exchanges per build
+
+// `bad` bits: anything set on any rank repeats the build with a host-planned (non-speculative) pass
+#define DXB_TOK 1u       // the speculative tokenizer pass did not fit its buffers / needs the host
+#define DXB_KEYS 2u      // a (source, owner) key segment overflowed
+#define DXB_PAIRS 4u     // a (source, owner) entry segment overflowed
+#define DXB_RECV 8u      // more entries received than the slab buffers hold
+#define DXB_ROWS 16u     // more rows than the slab buffers hold
+#define DXB_GTABLE 32u   // owner table full
+#define DXB_TIMEOUT 64u  // a peer's signal did not arrive
+#define DXB_RANGE 128u   // an entry for a row outside this slab (only after another failure)
+#define DXB_SHAPE 256u   // host: this rank's input does not match the remembered plan
+
+struct DxHdr {  // written by the source into the receiver's control block, before the epoch flag
+    u64 count;  // x1: keys in the segment; x5: entries in the segment
+    u64 bad;    // everything bad the source knew when it signalled
+    u64 aux;    // x3: global firsts of the source's shard
     u64 pad;
 };
 
-// local distinct keys (any order)
-__global__ void __launch_bounds__(256) k_dist_export(const TKey* __restrict__ tkeys, const u64* __restrict__ tfirst, u32 cap,
-                                                      DistKey* __restrict__ out, u32* __restrict__ counter)
-{
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
-        const TKey k = tkeys[i];
-        if (k.x == 0 && k.y == 0) continue;
-        const u32 j = atomicAdd(counter, 1u);
-        DistKey d;
-        d.k0 = k.x; d.k1 = k.y; d.order = ~tfirst[i]; d.pad = 0;
-        out[j] = d;
-    }
-}
-
-struct DistMergeParams {
-    const uint8_t* keys;       // rank s: DistKey[n_keys[s]] at keys + s * key_stride (bytes)
-    const uint8_t* tile_base;  // rank s: u64[n_tiles + 1] at tile_base + s * tile_stride (bytes): exclusive scan of (n_rec << 32 | n_edge)
-    u64 key_stride, tile_stride;
-    u64 n_keys[8];
-    u64 rec_base[8];         // records before each rank
-    int world;
+struct DxCtl {  // device memory of one rank, written by its peers
+    u32 sig[DX_NEX][DX_MAXW];  // epoch of the latest signal of exchange e from source s (monotone)
+    DxHdr hdr[DX_NEX][DX_MAXW];
 };
 
-// insert every rank's keys with their GLOBAL order = global record ordinal << 2 | sub-rank
-__global__ void __launch_bounds__(256) k_dist_insert(const ScanParams P, const DistMergeParams D)
-{
-    u32 claimed = 0;
-    for (int s = 0; s < D.world; s++) {
-        const DistKey* keys = reinterpret_cast<const DistKey*>(D.keys + (u64)s * D.key_stride);
-        const u64* tb = reinterpret_cast<const u64*>(D.tile_base + (u64)s * D.tile_stride);
-        for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < D.n_keys[s]; i += (u64)gridDim.x * blockDim.x) {
-            const DistKey d = keys[i];
-            const u64 tile = d.order >> 12;
-            const u64 rec = D.rec_base[s] + (tb[tile] >> 32) + ((d.order >> 2) & 1023u);
-            table_probe(P, d.k0, d.k1, (rec << 2) | (d.order & 3u), claimed);
-        }
-    }
-    if (claimed) atomicAdd(&P.cnt->n_keys, claimed);
-}
+struct DxLocal {  // zeroed at the start of every build; never written by peers
+    u32 bad;
+    u32 cur_keys[DX_MAXW];   // keys sent to each owner so far
+    u32 cur_pairs[DX_MAXW];  // entries sent to each row owner so far
+    u32 idbase[DX_MAXW + 1];
+    u32 n_first, n_global, rows_per, row0, n_rows, n_recv;
+    u32 seg_off[DX_MAXW + 1];  // received entries: exclusive prefix over sources
+    u32 n_keys, n_records, n_edges;  // this shard (copied from DevSizes before the slab overwrites it)
+    u32 final_bad;
+    u32 pad[8];
+};
 
-// global table: order already is the bit index
-__global__ void __launch_bounds__(256) k_dist_mark(const TKey* __restrict__ tkeys, const u64* __restrict__ tfirst, u32 cap, u32* __restrict__ bitmap)
-{
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
-        const TKey k = tkeys[i];
-        if (k.x == 0 && k.y == 0) continue;
-        const u64 bit = ~tfirst[i];
-        atomicOr(&bitmap[bit >> 5], 1u << (bit & 31));
-    }
-}
+struct DxLayout {  // the exchange arena of one rank (same layout on every rank)
+    u64 kcap, pcap;  // elements per (source, destination) segment
+    u64 off_key, off_ord, off_first, off_rank, off_id, off_pair, bytes;
+};
 
-__global__ void __launch_bounds__(256) k_dist_assign(const TKey* __restrict__ tkeys, const u64* __restrict__ tfirst, u32 cap,
-                                                      const u32* __restrict__ bitmap, const u32* __restrict__ wprefix,
-                                                      u32* __restrict__ slot_id, u32* __restrict__ id2slot, u32* __restrict__ name_len)
-{
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
-        const TKey k = tkeys[i];
-        if (k.x == 0 && k.y == 0) continue;
-        const u64 ob = ~tfirst[i];
-        const u32 wd = (u32)(ob >> 5), bit = (u32)(ob & 31);
-        const u32 id = wprefix[wd] + __popc(bitmap[wd] & ((1u << bit) - 1u));
-        slot_id[i] = id;
-        id2slot[id] = i;
-        name_len[id] = slot_key_len(k.y);
-    }
-}
+struct DxPeers {
+    uint8_t* arena[DX_MAXW];
+    DxCtl* ctl[DX_MAXW];
+    int rank, world;
+    u32 epoch;
+};
 
-// local slot -> global node ID (lookup of the local key in the global table; it is always present)
-__global__ void __launch_bounds__(256) k_dist_localmap(const TKey* __restrict__ ltkeys, u32 lcap, const TKey* __restrict__ gtkeys, u32 gmask,
-                                                        const u32* __restrict__ gslot_id, u32* __restrict__ lslot_id)
-{
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < lcap; i += gridDim.x * blockDim.x) {
-        const TKey k = ltkeys[i];
-        if (k.x == 0 && k.y == 0) continue;
-        ProbeSeq q = probe_seq(k.x, k.y, gmask, 0);  // the sequence probe_issue / probe_finish walk (the merge inserts with bidirected = 0)
-        u32 found = 0xFFFFFFFFu, visited = 0;
-        while (true) {
-            const u32 j = q.slot();
-            const TKey a = gtkeys[j], b = gtkeys[j + 1];
-            if (a.x == k.x && a.y == k.y) { found = j; break; }
-            if (b.x == k.x && b.y == k.y) { found = j + 1; break; }
-            if ((a.x == 0 && a.y == 0) || (b.x == 0 && b.y == 0)) break;
-            if (!q.next(gmask, visited)) break;
-        }
-        lslot_id[i] = found == 0xFFFFFFFFu ? 0xFFFFFFFFu : gslot_id[found];
-    }
-}
-
-// ---------------------------------------------------------------- phase 3
 struct DistPair {  // multi-GPU builds are unweighted: no emission index travels (rowsort.cuh: Ent32)
     u32 entry;  // minor << 1 | dir
     u32 major;
 };
 
-__global__ void __launch_bounds__(256) k_dist_dest_count(const EmitParams E, int sym, int csc, u32 rows_per, u32* __restrict__ dest_cnt)
+__device__ __forceinline__ u32 ld_acquire_sys_u32(const u32* p)
 {
-    __shared__ u32 s_cnt[8];
-    if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
-    __syncthreads();
-    for_each_edge(E, [&](u32, u32 t0, const u32 (&id)[4]) {
-        record_entries(id, E.tpe, t0, sym, csc, [&](u32 major, u32, u32, u32) { atomicAdd(&s_cnt[major / rows_per], 1u); });
-    });
-    __syncthreads();
-    if (threadIdx.x < 8 && s_cnt[threadIdx.x]) atomicAdd(&dest_cnt[threadIdx.x], s_cnt[threadIdx.x]);
+    u32 v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(u32* p, u32 v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// dest_off[d] = first send-buffer index of destination d; dest_cur[d] = entries reserved so far.
-// One warp per tile: count the tile's entries per destination in shared memory, reserve the ranges
-// with one global atomic per destination, then write (requires edge_slots to hold node IDs already).
-__global__ void __launch_bounds__(256) k_dist_dest_scatter(const EmitParams E, int sym, int csc, u32 rows_per, int world,
-                                                            const u32* __restrict__ dest_off, u32* __restrict__ dest_cur,
-                                                            DistPair* __restrict__ send)
+__device__ __forceinline__ u32 dx_owner(u64 k0, u64 k1, int world)
 {
-    __shared__ u32 s_cnt[8][8];
-    __shared__ u32 s_base[8][8];
-    const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    if (!E.ds->ok) return;
-    for (u32 tile = warp; tile < E.n_tiles; tile += n_warps) {
-        const TileInfo ti = E.tile_info[tile];
-        if (ti.n_edge == 0) continue;
-        const u32 e0 = (u32)E.tile_base[tile];
-        if (lane < 8) s_cnt[wid][lane] = 0;
-        __syncwarp();
-        for (int pass = 0; pass < 2; pass++) {
-            for (u32 j = lane; j < ti.n_edge; j += 32) {
-                const u32* sl = E.edge_slots + (u64)(ti.edge_alloc + j) * E.slots_per_edge;
-                u32 id[4] = {sl[0], sl[1], 0, 0};
-                if (E.slots_per_edge == 4) { id[2] = sl[2]; id[3] = sl[3]; }
-                record_entries(id, E.tpe, (e0 + j) * (u32)E.tpe, sym, csc, [&](u32 major, u32 minor, u32 dir, u32 t) {
-                    const u32 d = major / rows_per;
-                    const u32 k = atomicAdd(&s_cnt[wid][d], 1u);
-                    if (pass) {
-                        DistPair p;
-                        p.entry = Ent32::make(minor, dir, 0u);
-                        p.major = major;
-                        send[s_base[wid][d] + k] = p;
-                    }
-                });
-            }
-            __syncwarp();
-            if (pass == 0 && lane < (u32)world) {
-                const u32 c = s_cnt[wid][lane];
-                s_base[wid][lane] = dest_off[lane] + (c ? atomicAdd(&dest_cur[lane], c) : 0u);
-                s_cnt[wid][lane] = 0;
-            }
-            __syncwarp();
+    return (u32)((mix64(k0 ^ mix64(k1 + 0x9e3779b97f4a7c15ULL)) >> 33) % (u32)world);
+}
+
+// Every CTA of a consuming kernel: wait until all sources have signalled exchange `e` of this epoch.
+// Bounded: a peer that never signals raises DXB_TIMEOUT instead of hanging the device.
+__device__ __forceinline__ void dx_wait(const DxCtl* my, int e, const DxPeers& X, DxLocal* loc)
+{
+    if (threadIdx.x < (u32)X.world) {
+        const u32* f = &my->sig[e][threadIdx.x];
+        u32 spins = 0;
+        while ((int)(ld_acquire_sys_u32(f) - X.epoch) < 0) {
+            __nanosleep(200);
+            if (++spins > 8000000u) { atomicOr(&loc->bad, DXB_TIMEOUT); break; }
+        }
+    }
+    __syncthreads();
+}
+
+// One warp: headers, then the epoch flag, into every peer's control block.
+// `aux_words`: the popcount prefix of the first-appearance bitmap -- its total is this shard's number of firsts (x3)
+__global__ void k_dx_signal(const DxPeers X, int e, DxLocal* loc, const u32* counts, u64 cap, const u32* aux_words, const DevSizes* ds)
+{
+    const u32 d = threadIdx.x;
+    if (d >= (u32)X.world) return;
+    DxHdr h;
+    u64 c = counts ? counts[d] : 0u;
+    if (c > cap) c = cap;
+    h.count = c;
+    h.bad = loc->bad;
+    h.aux = (aux_words && ds->ok) ? aux_words[ds->words] : 0ull;
+    h.pad = 0;
+    DxCtl* pc = X.ctl[d];
+    pc->hdr[e][X.rank] = h;
+    __threadfence_system();
+    st_release_sys_u32(&pc->sig[e][X.rank], X.epoch);
+}
+
+// ---------------------------------------------------------------- x1: local keys -> owners
+// sent[slot] = owner << 29 | position in the owner's segment of this rank
+__global__ void __launch_bounds__(256) k_dx_export(const TKey* __restrict__ tkeys, const u64* __restrict__ tfirst, u32 cap,
+                                                    const u64* __restrict__ tile_base, const DevSizes* __restrict__ ds,
+                                                    const DxPeers X, const DxLayout L, DxLocal* __restrict__ loc, u32* __restrict__ sent)
+{
+    if (!ds->ok) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&loc->bad, DXB_TOK);
+        return;
+    }
+    const u32 lane = threadIdx.x & 31;
+    for (u32 i0 = blockIdx.x * blockDim.x; i0 < cap; i0 += gridDim.x * blockDim.x) {  // cap is a multiple of 256
+        const u32 i = i0 + threadIdx.x;
+        const TKey k = tkeys[i];
+        const bool occ = !(k.x == 0 && k.y == 0);
+        const u32 d = occ ? dx_owner(k.x, k.y, X.world) : 0xFFu;
+        const u32 m = __match_any_sync(0xffffffffu, d);
+        if (!occ) continue;
+        const int leader = __ffs(m) - 1;
+        u32 base = 0;
+        if ((int)lane == leader) base = atomicAdd(&loc->cur_keys[d], (u32)__popc(m));
+        base = __shfl_sync(m, base, leader);
+        const u32 pos = base + __popc(m & ((1u << lane) - 1u));
+        if (pos >= L.kcap) { atomicOr(&loc->bad, DXB_KEYS); sent[i] = 0xFFFFFFFFu; continue; }
+        uint8_t* a = X.arena[d];
+        const u64 j = (u64)X.rank * L.kcap + pos;
+        reinterpret_cast<TKey*>(a + L.off_key)[j] = k;
+        reinterpret_cast<u32*>(a + L.off_ord)[j] = order_bit(tile_base, ~tfirst[i]);
+        sent[i] = (d << 29) | pos;
+    }
+}
+
+struct DxOwner {  // the owner's table over the keys it is responsible for
+    TKey* gkeys;
+    u64* gfirst;  // ~min(source rank << 32 | local order)
+    u32 gmask;
+    u32* gslot;   // [source][position]: table slot of the received key
+    u32* gpos;    // [table slot]: position of the key in the segment of its FIRST source
+};
+
+// headers are read after dx_wait(); volatile: never through the read-only path
+__device__ __forceinline__ u32 dx_count(const DxCtl* my, int e, u32 s, u64 cap)
+{
+    const u64 c = *(const volatile u64*)&my->hdr[e][s].count;
+    return (u32)(c < cap ? c : cap);
+}
+__device__ __forceinline__ u32 dx_bad(const DxCtl* my, int e, u32 s) { return (u32) * (const volatile u64*)&my->hdr[e][s].bad; }
+__device__ __forceinline__ u32 dx_aux(const DxCtl* my, int e, u32 s) { return (u32) * (const volatile u64*)&my->hdr[e][s].aux; }
+
+// ---------------------------------------------------------------- x1 consumer: owner table
+__global__ void __launch_bounds__(256) k_dx_insert(const DxPeers X, const DxLayout L, const DxCtl* my, DxLocal* __restrict__ loc,
+                                                    const DxOwner G, Counters* __restrict__ cnt)
+{
+    dx_wait(my, 0, X, loc);
+    if (blockIdx.x == 0 && threadIdx.x < (u32)X.world) {
+        const u32 b = dx_bad(my, 0, threadIdx.x);
+        if (b) atomicOr(&loc->bad, b);
+    }
+    ScanParams P;
+    P.tkeys = G.gkeys;
+    P.tfirst = G.gfirst;
+    P.table_mask = G.gmask;
+    P.cnt = cnt;
+    P.bidirected = 0;
+    const uint8_t* a = X.arena[X.rank];
+    u32 claimed = 0;
+    for (u32 s = 0; s < (u32)X.world; s++) {
+        const u32 n = dx_count(my, 0, s, L.kcap);
+        const TKey* keys = reinterpret_cast<const TKey*>(a + L.off_key) + (u64)s * L.kcap;
+        const u32* ord = reinterpret_cast<const u32*>(a + L.off_ord) + (u64)s * L.kcap;
+        for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+            const TKey k = keys[j];
+            const u32 slot = table_probe(P, k.x, k.y, ((u64)s << 32) | ord[j], claimed);
+            if (slot == 0xFFFFFFFFu) atomicOr(&loc->bad, DXB_GTABLE);
+            G.gslot[(u64)s * L.kcap + j] = slot;
         }
     }
 }
 
-__global__ void __launch_bounds__(256) k_pairs_count(const DistPair* __restrict__ pairs, u64 n, u32 row0, u32* __restrict__ cnt)
+// ---------------------------------------------------------------- x2: owner -> sources, one byte per key
+// four keys per thread: one 32-bit store into the peer's memory
+__global__ void __launch_bounds__(256) k_dx_reply_first(const DxPeers X, const DxLayout L, const DxCtl* my, const DxOwner G)
 {
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
-        atomicAdd(&cnt[pairs[i].major - row0], 1u);
+    for (u32 s = 0; s < (u32)X.world; s++) {
+        const u32 n = dx_count(my, 0, s, L.kcap);
+        const u32* gs = G.gslot + (u64)s * L.kcap;
+        u32* out = reinterpret_cast<u32*>(X.arena[s] + L.off_first + (u64)X.rank * L.kcap);  // kcap is a multiple of 4
+        for (u32 q = blockIdx.x * blockDim.x + threadIdx.x; q * 4 < n; q += gridDim.x * blockDim.x) {
+            u32 word = 0;
+#pragma unroll
+            for (u32 t = 0; t < 4; t++) {
+                const u32 j = q * 4 + t;
+                if (j >= n) break;
+                const u32 g = gs[j];
+                if (g == 0xFFFFFFFFu) continue;
+                const u64 f = ~G.gfirst[g];
+                if ((u32)(f >> 32) == s) {
+                    word |= 1u << (8 * t);
+                    G.gpos[g] = j;
+                }
+            }
+            out[q] = word;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- x2 consumer: bitmap of this shard's global firsts
+__global__ void __launch_bounds__(256) k_dx_mark(const TKey* __restrict__ tkeys, const u64* __restrict__ tfirst, u32 cap,
+                                                  const u64* __restrict__ tile_base, const DevSizes* __restrict__ ds, const DxPeers X,
+                                                  const DxLayout L, const DxCtl* my, DxLocal* __restrict__ loc,
+                                                  const u32* __restrict__ sent, u32* __restrict__ bitmap)
+{
+    dx_wait(my, 1, X, loc);
+    if (blockIdx.x == 0 && threadIdx.x < (u32)X.world) {
+        const u32 b = dx_bad(my, 1, threadIdx.x);
+        if (b) atomicOr(&loc->bad, b);
+    }
+    if (!ds->ok) return;
+    const uint8_t* first = X.arena[X.rank] + L.off_first;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+        const TKey k = tkeys[i];
+        if (k.x == 0 && k.y == 0) continue;
+        const u32 sv = sent[i];
+        if (sv == 0xFFFFFFFFu) continue;
+        if (!first[(u64)(sv >> 29) * L.kcap + (sv & 0x1FFFFFFFu)]) continue;
+        const u32 bit = order_bit(tile_base, ~tfirst[i]);
+        atomicOr(&bitmap[bit >> 5], 1u << (bit & 31));
+    }
+}
+
+// ---------------------------------------------------------------- x3: first source -> owner, rank inside the shard
+// also this shard's name table: id2slot / name_len are indexed by that rank
+__global__ void __launch_bounds__(256) k_dx_send_rank(const TKey* __restrict__ tkeys, const u64* __restrict__ tfirst, u32 cap,
+                                                       const u64* __restrict__ tile_base, const DevSizes* __restrict__ ds, const DxPeers X,
+                                                       const DxLayout L, const u32* __restrict__ sent, const u32* __restrict__ bitmap,
+                                                       const u32* __restrict__ wprefix, u32* __restrict__ id2slot, u32* __restrict__ name_len)
+{
+    if (!ds->ok) return;
+    const uint8_t* first = X.arena[X.rank] + L.off_first;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+        const TKey k = tkeys[i];
+        if (k.x == 0 && k.y == 0) continue;
+        const u32 sv = sent[i];
+        if (sv == 0xFFFFFFFFu) continue;
+        const u32 d = sv >> 29, pos = sv & 0x1FFFFFFFu;
+        if (!first[(u64)d * L.kcap + pos]) continue;
+        const u32 ob = order_bit(tile_base, ~tfirst[i]);
+        const u32 wd = ob >> 5, bit = ob & 31;
+        const u32 r = wprefix[wd] + __popc(bitmap[wd] & ((1u << bit) - 1u));
+        reinterpret_cast<u32*>(X.arena[d] + L.off_rank)[(u64)X.rank * L.kcap + pos] = r;
+        id2slot[r] = i;
+        name_len[r] = slot_key_len(k.y);
+    }
+}
+
+// ---------------------------------------------------------------- x4: owner -> sources, the node ID of every key
+__global__ void __launch_bounds__(256) k_dx_reply_ids(const DxPeers X, const DxLayout L, const DxCtl* my, DxLocal* __restrict__ loc,
+                                                       const DxOwner G)
+{
+    __shared__ u32 s_base[DX_MAXW + 1];
+    dx_wait(my, 2, X, loc);
+    if (threadIdx.x == 0) {
+        u32 run = 0, bad = 0;
+        for (int s = 0; s < X.world; s++) {
+            s_base[s] = run;
+            run += dx_aux(my, 2, (u32)s);
+            bad |= dx_bad(my, 2, (u32)s);
+        }
+        s_base[X.world] = run;
+        if (blockIdx.x == 0) {
+            if (bad) atomicOr(&loc->bad, bad);
+            for (int s = 0; s <= X.world; s++) loc->idbase[s] = s_base[s];
+            const u32 n = run, rpr = n ? (n + (u32)X.world - 1) / (u32)X.world : 1u;
+            const u32 r0 = min(n, (u32)X.rank * rpr);
+            loc->n_first = s_base[X.rank + 1] - s_base[X.rank];
+            loc->n_global = n;
+            loc->rows_per = rpr;
+            loc->row0 = r0;
+            loc->n_rows = min(n, r0 + rpr) - r0;
+        }
+    }
+    __syncthreads();
+    const u32* ranks = reinterpret_cast<const u32*>(X.arena[X.rank] + L.off_rank);
+    for (u32 s = 0; s < (u32)X.world; s++) {
+        const u32 n = dx_count(my, 0, s, L.kcap);
+        const u32* gs = G.gslot + (u64)s * L.kcap;
+        u32* out = reinterpret_cast<u32*>(X.arena[s] + L.off_id) + (u64)X.rank * L.kcap;
+        for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+            const u32 g = gs[j];
+            u32 id = 0;
+            if (g != 0xFFFFFFFFu) {
+                const u32 fs = (u32)((~G.gfirst[g]) >> 32);
+                if (fs < (u32)X.world) {
+                    const u32 p = G.gpos[g];
+                    if (p < L.kcap) id = s_base[fs] + ranks[(u64)fs * L.kcap + p];
+                }
+            }
+            out[j] = id;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- x4 consumer: local slot -> global node ID
+__global__ void __launch_bounds__(256) k_dx_localmap(const TKey* __restrict__ tkeys, u32 cap, const DevSizes* __restrict__ ds, const DxPeers X,
+                                                      const DxLayout L, const DxCtl* my, DxLocal* __restrict__ loc,
+                                                      const u32* __restrict__ sent, u32* __restrict__ slot_id, u32 rows_cap)
+{
+    dx_wait(my, 3, X, loc);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        u32 bad = 0;
+        for (int s = 0; s < X.world; s++) bad |= dx_bad(my, 3, (u32)s);
+        if (loc->n_rows > rows_cap) bad |= DXB_ROWS;
+        if (bad) atomicOr(&loc->bad, bad);
+        loc->n_keys = ds->n; loc->n_records = ds->R; loc->n_edges = ds->E;
+    }
+    if (!ds->ok) return;
+    const u32* ids = reinterpret_cast<const u32*>(X.arena[X.rank] + L.off_id);
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+        const TKey k = tkeys[i];
+        if (k.x == 0 && k.y == 0) continue;
+        const u32 sv = sent[i];
+        slot_id[i] = sv == 0xFFFFFFFFu ? 0u : ids[(u64)(sv >> 29) * L.kcap + (sv & 0x1FFFFFFFu)];
+    }
+}
+
+// ---------------------------------------------------------------- x5: row entries -> owner of their row block
+// Flat over the stored edge records (unweighted: nothing depends on the emission index).  A CTA handles
+// 256 x DXE_BATCH records per round: count per destination in shared memory, reserve the CTA's range in
+// every destination segment with ONE global atomic per destination, then write the entries straight
+// into the destination rank's memory.
+#define DXE_BATCH 4
+template <int TPE>
+__global__ void __launch_bounds__(256) k_dx_entries(u32* __restrict__ edge_slots, const u32* __restrict__ slot_id, const DevSizes* __restrict__ ds,
+                                                     int sym, int csc, const DxPeers X, const DxLayout L, DxLocal* __restrict__ loc)
+{
+    constexpr int SPE = TPE == 4 ? 4 : 2;
+    __shared__ u32 s_cnt[DX_MAXW], s_base[DX_MAXW], s_go;
+    if (threadIdx.x == 0) s_go = ds->ok && !loc->bad;  // one decision per CTA (another CTA may raise `bad` meanwhile)
+    __syncthreads();
+    if (!s_go) return;
+    const u32 E = ds->E;
+    const u32 rpr = loc->rows_per;
+    const u32 lane = threadIdx.x & 31;
+    const u32 per_round = 256 * DXE_BATCH;
+    for (u32 r0 = blockIdx.x * per_round; r0 < E; r0 += gridDim.x * per_round) {  // uniform per CTA
+        if (threadIdx.x < DX_MAXW) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        u32 id[DXE_BATCH][4];
+#pragma unroll
+        for (int u = 0; u < DXE_BATCH; u++) {
+            const u32 e = r0 + u * 256 + threadIdx.x;
+            id[u][0] = id[u][1] = id[u][2] = id[u][3] = 0;
+            if (e < E) {
+                if (SPE == 4) {
+                    const uint4 q = reinterpret_cast<const uint4*>(edge_slots)[e];
+                    id[u][0] = q.x; id[u][1] = q.y; id[u][2] = q.z; id[u][3] = q.w;
+                } else {
+                    const uint2 q = reinterpret_cast<const uint2*>(edge_slots)[e];
+                    id[u][0] = q.x; id[u][1] = q.y;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < DXE_BATCH; u++) {
+            if (r0 + u * 256 + threadIdx.x < E) {
+#pragma unroll
+                for (int k = 0; k < SPE; k++) id[u][k] = slot_id[id[u][k]];
+            }
+        }
+        // the in-segment position of an entry: (entries of the same destination in earlier (u, k, half) steps of this
+        // CTA) + rank among the lanes of the same step; pass 0 counts, pass 1 writes
+        for (int pass = 0; pass < 2; pass++) {
+#pragma unroll
+            for (int u = 0; u < DXE_BATCH; u++) {
+                const bool valid = r0 + u * 256 + threadIdx.x < E;
+                record_entries_t<TPE>(id[u], 0u, sym, csc, [&](u32 major, u32 minor, u32 dir, u32) {
+                    u32 d = valid ? major / rpr : 0xFFu;
+                    if (valid && d >= (u32)X.world) d = (u32)X.world - 1;  // never: IDs are below n
+                    const u32 m = __match_any_sync(0xffffffffu, d);
+                    if (!valid) return;
+                    const int leader = __ffs(m) - 1;
+                    u32 base = 0;
+                    if ((int)lane == leader) base = atomicAdd(&s_cnt[d], (u32)__popc(m));
+                    base = __shfl_sync(m, base, leader);
+                    if (pass) {
+                        const u32 pos = s_base[d] + base + __popc(m & ((1u << lane) - 1u));
+                        if (pos < L.pcap) {
+                            DistPair p;
+                            p.entry = Ent32::make(minor, dir, 0u);
+                            p.major = major;
+                            reinterpret_cast<DistPair*>(X.arena[d] + L.off_pair)[(u64)X.rank * L.pcap + pos] = p;
+                        }
+                    }
+                });
+            }
+            __syncthreads();
+            if (pass == 0) {
+                if (threadIdx.x < (u32)X.world) {
+                    const u32 c = s_cnt[threadIdx.x];
+                    const u32 b = c ? atomicAdd(&loc->cur_pairs[threadIdx.x], c) : 0u;
+                    if ((u64)b + c > L.pcap) atomicOr(&loc->bad, DXB_PAIRS);
+                    s_base[threadIdx.x] = b;
+                    s_cnt[threadIdx.x] = 0;
+                }
+                __syncthreads();
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- x5 consumer: this rank's slab
+// one warp: received counts -> DevSizes of the slab build (rows, entries)
+__global__ void k_dx_slab_sizes(const DxPeers X, const DxLayout L, const DxCtl* my, DxLocal* __restrict__ loc,
+                                DevSizes* __restrict__ ds, u32 recv_cap, u32 rows_cap)
+{
+    dx_wait(my, 4, X, loc);
+    if (threadIdx.x) return;
+    u32 bad = loc->bad, run = 0;
+    for (int s = 0; s < X.world; s++) {
+        bad |= dx_bad(my, 4, (u32)s);
+        loc->seg_off[s] = run;
+        run += dx_count(my, 4, (u32)s, L.pcap);
+    }
+    loc->seg_off[X.world] = run;
+    loc->n_recv = run;
+    if (run > recv_cap) bad |= DXB_RECV;
+    if (loc->n_rows > rows_cap) bad |= DXB_ROWS;
+    loc->bad = bad;
+    DevSizes s;
+    memset(&s, 0, sizeof(s));
+    if (!bad) { s.n = loc->n_rows; s.rows = loc->n_rows; s.M = run; s.T = run; s.ok = 1; }
+    *ds = s;
+}
+
+__global__ void __launch_bounds__(256) k_pairs_count(const DxPeers X, const DxLayout L, const DxLocal* __restrict__ loc, const DevSizes* __restrict__ ds,
+                                                      u32* __restrict__ cnt, u32* __restrict__ bad_out)
+{
+    if (!ds->ok) return;
+    const u32 row0 = loc->row0, n_rows = loc->n_rows;
+    const DistPair* base = reinterpret_cast<const DistPair*>(X.arena[X.rank] + L.off_pair);
+    for (u32 s = 0; s < (u32)X.world; s++) {
+        const u32 n = loc->seg_off[s + 1] - loc->seg_off[s];
+        const DistPair* pairs = base + (u64)s * L.pcap;
+        for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const u32 r = pairs[i].major - row0;
+            if (r < n_rows) atomicAdd(&cnt[r], 1u);
+            else atomicOr(bad_out, DXB_RANGE);
+        }
+    }
 }
 
 // multi-GPU builds are unweighted: the slab keeps 32-bit entries (minor << 1 | dir), see Ent32
-__global__ void __launch_bounds__(256) k_pairs_scatter(const DistPair* __restrict__ pairs, u64 n, u32 row0, u32* __restrict__ cursor,
-                                                        u32* __restrict__ entries)
+__global__ void __launch_bounds__(256) k_pairs_scatter(const DxPeers X, const DxLayout L, const DxLocal* __restrict__ loc, const DevSizes* __restrict__ ds,
+                                                        u32* __restrict__ cursor, u32* __restrict__ entries)
 {
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
-        const DistPair p = pairs[i];
-        entries[atomicAdd(&cursor[p.major - row0], 1u)] = p.entry;
+    if (!ds->ok) return;
+    const u32 row0 = loc->row0, n_rows = loc->n_rows;
+    const DistPair* base = reinterpret_cast<const DistPair*>(X.arena[X.rank] + L.off_pair);
+    for (u32 s = 0; s < (u32)X.world; s++) {
+        const u32 n = loc->seg_off[s + 1] - loc->seg_off[s];
+        const DistPair* pairs = base + (u64)s * L.pcap;
+        for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const DistPair p = pairs[i];
+            const u32 r = p.major - row0;
+            if (r < n_rows) entries[atomicAdd(&cursor[r], 1u)] = p.entry;
+        }
     }
+}
+
+// ---------------------------------------------------------------- x6 consumer: the build's verdict, same on every rank
+__global__ void k_dx_final(const DxPeers X, const DxCtl* my, DxLocal* __restrict__ loc)
+{
+    dx_wait(my, 5, X, loc);
+    if (threadIdx.x) return;
+    u32 bad = loc->bad;
+    for (int s = 0; s < X.world; s++) bad |= dx_bad(my, 5, (u32)s);
+    loc->final_bad = bad;
 }
 
 }  // namespace g2n

@@ -129,8 +129,15 @@ struct g2n_handle {
     // multi-GPU state
     bool slab_mode = false;
     u64 slab_rows = 0, n_global = 0;
-    u32 gcap = 0;
-    DevBuf gtable, gfirst, gslot_id, dest_cnt;
+    u64 names_n = 0, names_id0 = 0;  // slab mode: this rank names the IDs [names_id0, names_id0 + names_n)
+    bool dx_inited = false, dx_probed = false, dx_spec = false;
+    DxPeers dxp;   // rank, world, epoch, peer arenas / control blocks
+    DxLayout dxl;  // layout of every rank's exchange arena
+    DevBuf dx_arena, dx_ctl, dx_loc, dx_zg, dx_gslot, dx_gpos, dx_sent;
+    DxLocal* h_loc = nullptr;  // pinned copy of the build's local status
+    bool dx_peer_open[DX_MAXW] = {false, false, false, false, false, false, false, false};
+    u32 dx_gcap = 0;
+    u64 dx_rows_cap = 0, dx_recv_cap = 0;
     u32 table_cap = 0;
     u32 n_tiles = 0;
     int tpe = 1, spe = 2;
@@ -503,6 +510,7 @@ int finish_result(g2n_handle* h)
 extern "C" {
 
 int g2n_abi_version(void) { return G2N_ABI_VERSION; }
+int g2n_dist_close_peers(g2n_handle* h);
 
 int g2n_create(int device, g2n_handle** out)
 {
@@ -536,8 +544,10 @@ void g2n_destroy(g2n_handle* h)
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->text, &h->zearly, &h->zids, &h->zrows, &h->defer, &h->edge_slots, &h->edge_w, &h->longs, &h->tile_info, &h->tile_base, &h->wprefix,
                       &h->slot_id, &h->id2slot, &h->name_len, &h->name_off, &h->names, &h->rowptr, &h->cursor, &h->entries, &h->w_emit, &h->biglist, &h->ucnt, &h->indptr, &h->indices, &h->data, &h->row, &h->col,
-                      &h->scan_state, &h->up_row, &h->up_col, &h->up_data, &h->tsv, &h->tsv_off, &h->gtable, &h->gfirst, &h->gslot_id, &h->dest_cnt};
+                      &h->scan_state, &h->up_row, &h->up_col, &h->up_data, &h->tsv, &h->tsv_off, &h->dx_arena, &h->dx_ctl, &h->dx_loc, &h->dx_zg, &h->dx_gslot, &h->dx_gpos, &h->dx_sent};
+    if (h->dx_inited) g2n_dist_close_peers(h);
     for (DevBuf* b : bufs) b->release();
+    if (h->h_loc) cudaFreeHost(h->h_loc);
     for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(h->ev[i]);
     for (KTimer& t : h->ktimers) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     if (h->h_ctl) cudaFreeHost(h->h_ctl);
@@ -1049,11 +1059,14 @@ static int ids_phase(g2n_handle* h)
     return G2N_OK;
 }
 
+// names held by this handle: all nodes, or -- multi-GPU slab -- the nodes that first appear in this rank's shard
+static u64 names_count(const g2n_handle* h) { return h->slab_mode ? h->names_n : h->n_nodes; }
+
 // name_len -> name_off (exclusive scan) and the total; only when somebody asks for the node names
 static int size_names(g2n_handle* h)
 {
     if (h->names_sized) return G2N_OK;
-    const u64 n = h->n_nodes;
+    const u64 n = names_count(h);
     if (n > 0) {
         LoadArray<u32> ln{h->name_len.as<u32>()};
         int rc = launch_scan<u64>(h, ln, (u64*)h->name_off.as<u64>(), nullptr, n, nullptr, nullptr);
@@ -1156,6 +1169,8 @@ int g2n_sizes(g2n_handle* h, g2n_sizes_t* out)
     out->dtype = h->params.dtype;
     out->reserved = 0;
     out->slab_rows = h->slab_mode ? h->slab_rows : h->n_nodes;
+    out->names_count = names_count(h);
+    out->names_id0 = h->slab_mode ? h->names_id0 : 0;
     return G2N_OK;
 }
 
@@ -1212,15 +1227,16 @@ int g2n_fetch_names(g2n_handle* h, uint8_t* names, uint64_t* offsets)
     }
     if (!h->names_ready) {
         CK(h->names.ensure(h->names_bytes + 16));
-        if (h->n_nodes > 0) {
-            { KScope ks(h, "k_gather_names"); k_gather_names<<<grid_for(h->n_nodes, 256), 256, 0, h->stream>>>(h->slab_mode ? h->gtable.as<TKey>() : h->d_tkeys, h->d_trep, h->id2slot.as<u32>(), h->name_off.as<u64>(),
-                                                                              (u32)h->n_nodes, h->d_text, h->longs.as<LongDesc>(),
+        const u64 nn = names_count(h);
+        if (nn > 0) {
+            { KScope ks(h, "k_gather_names"); k_gather_names<<<grid_for(nn, 256), 256, 0, h->stream>>>(h->d_tkeys, h->d_trep, h->id2slot.as<u32>(), h->name_off.as<u64>(),
+                                                                              (u32)nn, h->d_text, h->longs.as<LongDesc>(),
                                                                               h->names.as<uint8_t>()); }
             CK(cudaGetLastError());
         }
         h->names_ready = true;
     }
-    CK(cudaMemcpyAsync(offsets, h->name_off.p, (h->n_nodes + 1) * sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(offsets, h->name_off.p, (names_count(h) + 1) * sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
     if (h->names_bytes) CK(cudaMemcpyAsync(names, h->names.p, h->names_bytes, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return G2N_OK;
@@ -1230,6 +1246,7 @@ int g2n_fetch_names(g2n_handle* h, uint8_t* names, uint64_t* offsets)
 static int build_tsv(g2n_handle* h)
 {
     if (h->tsv_ready) return G2N_OK;
+    if (h->slab_mode) { h->err = "the node map of a multi-GPU slab is assembled by the caller (g2n_fetch_names per rank)"; return G2N_ERR_INVALID; }
     const u64 n = h->n_nodes;
     CK(h->tsv_off.ensure((n + 2) * sizeof(u64)));
     if (n > 0) {
@@ -1245,7 +1262,7 @@ static int build_tsv(g2n_handle* h)
     CK(h->tsv.ensure(h->tsv_bytes + 16));
     if (n > 0) {
         KScope ks(h, "k_tsv_write");
-        k_tsv_write<<<grid_for(n, 256), 256, 0, h->stream>>>(h->slab_mode ? h->gtable.as<TKey>() : h->d_tkeys, h->d_trep, h->id2slot.as<u32>(), h->tsv_off.as<u64>(), (u32)n, h->d_text,
+        k_tsv_write<<<grid_for(n, 256), 256, 0, h->stream>>>(h->d_tkeys, h->d_trep, h->id2slot.as<u32>(), h->tsv_off.as<u64>(), (u32)n, h->d_text,
                                                               h->longs.as<LongDesc>(), h->tsv.as<uint8_t>());
         CK(cudaGetLastError());
     }
@@ -1330,12 +1347,147 @@ int g2n_coo_to_compressed(g2n_handle* h, const int32_t* row, const int32_t* col,
 }
 
 // =====================================================================================
-// multi-GPU phases.  One handle per rank; the caller moves the buffers between ranks.
+// multi-GPU build (device side and protocol: dist.cuh).  One handle per rank.  The caller
+// (gfa2network_b200/dist.py) only bootstraps: it agrees on capacities, exchanges the CUDA IPC handles of
+// the exchange arenas and queues the six stages; data moves between GPUs inside the kernels.
 
-int g2n_dist_scan(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n_params* p, g2n_dist_info* out)
+static size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static void dx_make_layout(DxLayout& L, int world, u64 kcap, u64 pcap)
 {
-    if (!out) return G2N_ERR_INVALID;
-    if (p && p->weight_tag && p->weight_tag_len > 0) { if (h) h->err = "multi-GPU builds are unweighted in this version"; return G2N_ERR_UNSUPPORTED; }
+    L.kcap = kcap;
+    L.pcap = pcap;
+    size_t o = 0;
+    L.off_key = o;   o += up256((size_t)world * kcap * sizeof(TKey));
+    L.off_ord = o;   o += up256((size_t)world * kcap * sizeof(u32));
+    L.off_first = o; o += up256((size_t)world * kcap);
+    L.off_rank = o;  o += up256((size_t)world * kcap * sizeof(u32));
+    L.off_id = o;    o += up256((size_t)world * kcap * sizeof(u32));
+    L.off_pair = o;  o += up256((size_t)world * pcap * sizeof(DistPair));
+    L.bytes = o;
+}
+
+int g2n_dist_init(g2n_handle* h, int rank, int world)
+{
+    if (!h || world < 1 || world > DX_MAXW || rank < 0 || rank >= world) return G2N_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (!h->dx_ctl.p) {
+        CK(h->dx_ctl.ensure(sizeof(DxCtl)));
+        CK(cudaMemset(h->dx_ctl.p, 0, sizeof(DxCtl)));
+        CK(h->dx_loc.ensure(sizeof(DxLocal)));
+        CK(cudaHostAlloc((void**)&h->h_loc, sizeof(DxLocal), cudaHostAllocDefault));
+    }
+    memset(&h->dxp, 0, sizeof(h->dxp));
+    memset(&h->dxl, 0, sizeof(h->dxl));
+    h->dxp.rank = rank;
+    h->dxp.world = world;
+    h->dxp.ctl[rank] = h->dx_ctl.as<DxCtl>();
+    h->dx_inited = true;
+    h->dx_probed = false;
+    return G2N_OK;
+}
+
+int g2n_dist_plan(g2n_handle* h, uint64_t key_cap, uint64_t pair_cap, uint64_t rows_cap, uint64_t recv_cap, int dry_run, int* will_realloc)
+{
+    if (!h || !h->dx_inited) return G2N_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    const u64 kcap = (key_cap + 255) & ~255ull, pcap = (pair_cap + 255) & ~255ull;
+    if (kcap >= (1ull << 29) || pcap >= 0xFFFFFF00ull) { h->err = "multi-GPU exchange segment too large"; return G2N_ERR_UNSUPPORTED; }
+    DxLayout L;
+    dx_make_layout(L, h->dxp.world, kcap, pcap);
+    const bool re = L.bytes > h->dx_arena.cap;
+    if (will_realloc) *will_realloc = re ? 1 : 0;
+    if (dry_run) return G2N_OK;
+    if (re) {
+        for (int s = 0; s < h->dxp.world; s++)
+            if (h->dx_peer_open[s]) { h->err = "close the peer mappings before the exchange arena grows"; return G2N_ERR_INVALID; }
+        CK(cudaStreamSynchronize(h->stream));
+        CK(h->dx_arena.ensure(L.bytes));
+    }
+    h->dxl = L;
+    h->dxp.arena[h->dxp.rank] = h->dx_arena.as<uint8_t>();
+    h->dx_rows_cap = rows_cap;
+    h->dx_recv_cap = recv_cap;
+    const u64 want = (u64)h->dxp.world * kcap;
+    h->dx_gcap = next_pow2(want + want / 2 < 1024 ? 1024 : want + want / 2);
+    CK(h->dx_zg.ensure((size_t)h->dx_gcap * (sizeof(TKey) + sizeof(u64))));
+    CK(h->dx_gslot.ensure((size_t)want * sizeof(u32) + 256));
+    CK(h->dx_gpos.ensure((size_t)h->dx_gcap * sizeof(u32)));
+    return G2N_OK;
+}
+
+int g2n_dist_local_mem(g2n_handle* h, void** arena, void** ctl, uint8_t* ipc128)
+{
+    if (!h || !h->dx_inited || !h->dx_arena.p) return G2N_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (arena) *arena = h->dx_arena.p;
+    if (ctl) *ctl = h->dx_ctl.p;
+    if (ipc128) {
+        cudaIpcMemHandle_t a, c;
+        CK(cudaIpcGetMemHandle(&a, h->dx_arena.p));
+        CK(cudaIpcGetMemHandle(&c, h->dx_ctl.p));
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+        memcpy(ipc128, &a, 64);
+        memcpy(ipc128 + 64, &c, 64);
+    }
+    return G2N_OK;
+}
+
+int g2n_dist_set_peers(g2n_handle* h, void* const* arenas, void* const* ctls)
+{
+    if (!h || !h->dx_inited || !arenas || !ctls) return G2N_ERR_INVALID;
+    for (int s = 0; s < h->dxp.world; s++) {
+        if (s == h->dxp.rank) continue;
+        h->dxp.arena[s] = (uint8_t*)arenas[s];
+        h->dxp.ctl[s] = (DxCtl*)ctls[s];
+    }
+    return G2N_OK;
+}
+
+int g2n_dist_close_peers(g2n_handle* h)
+{
+    if (!h || !h->dx_inited) return G2N_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int s = 0; s < h->dxp.world; s++) {
+        if (!h->dx_peer_open[s]) continue;
+        cudaIpcCloseMemHandle(h->dxp.arena[s]);
+        cudaIpcCloseMemHandle(h->dxp.ctl[s]);
+        h->dxp.arena[s] = nullptr;
+        h->dxp.ctl[s] = nullptr;
+        h->dx_peer_open[s] = false;
+    }
+    return G2N_OK;
+}
+
+int g2n_dist_open_peers(g2n_handle* h, const uint8_t* ipc_all)
+{
+    if (!h || !h->dx_inited || !ipc_all) return G2N_ERR_INVALID;
+    int rc = g2n_dist_close_peers(h);
+    if (rc) return rc;
+    for (int s = 0; s < h->dxp.world; s++) {
+        if (s == h->dxp.rank) continue;
+        cudaIpcMemHandle_t a, c;
+        memcpy(&a, ipc_all + (size_t)s * 128, 64);
+        memcpy(&c, ipc_all + (size_t)s * 128 + 64, 64);
+        void *pa = nullptr, *pc = nullptr;
+        CK(cudaIpcOpenMemHandle(&pa, a, cudaIpcMemLazyEnablePeerAccess));
+        CK(cudaIpcOpenMemHandle(&pc, c, cudaIpcMemLazyEnablePeerAccess));
+        h->dxp.arena[s] = (uint8_t*)pa;
+        h->dxp.ctl[s] = (DxCtl*)pc;
+        h->dx_peer_open[s] = true;
+    }
+    return G2N_OK;
+}
+
+// Host-planned pass: tokenize this rank's byte range with the usual host round trip and report the shard's
+// counts (or its first parse error -- g2n_status -- so that every rank can raise the same exception).
+int g2n_dist_probe(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n_params* p, g2n_dist_info* out)
+{
+    if (!h || !out || !h->dx_inited) return G2N_ERR_INVALID;
+    memset(out, 0, sizeof(*out));
+    h->dx_probed = false;
+    if (p && p->weight_tag && p->weight_tag_len > 0) { h->err = "multi-GPU builds are unweighted in this version"; return G2N_ERR_UNSUPPORTED; }
     int rc = tokenize_phase(h, text, nbytes, p, false, false);
     if (rc) return rc;
     if (h->n_long) { h->err = "multi-GPU builds need node names of <= 15 bytes (13 with --bidirected) in this version"; return G2N_ERR_UNSUPPORTED; }
@@ -1344,179 +1496,202 @@ int g2n_dist_scan(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2n
     out->n_records = h->n_records;
     out->n_edge_records = h->n_edges;
     out->n_entries = h->n_edges * (u64)h->tpe * (h->symmax ? 2 : 1);
-    out->reserved = 0;
+    h->hint_sig = shape_signature(p, nbytes, 0);
+    h->hint_valid = true;
+    h->dx_probed = true;
     return G2N_OK;
 }
 
-int g2n_dist_export(g2n_handle* h, void* dev_keys, void* dev_tile_base)
-{
-    if (!h || !dev_tile_base || (!dev_keys && h->n_nodes)) return G2N_ERR_INVALID;
-    CK(cudaSetDevice(h->device));
-    CK(h->dest_cnt.ensure(64 * sizeof(u32)));
-    CK(cudaMemsetAsync(h->dest_cnt.p, 0, 64 * sizeof(u32), h->stream));
-    if (h->n_nodes) {
-        KScope ks(h, "k_dist_export");
-        k_dist_export<<<grid_for(h->table_cap, 256), 256, 0, h->stream>>>(h->d_tkeys, h->d_tfirst, h->table_cap, (DistKey*)dev_keys, h->dest_cnt.as<u32>());
-    }
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(dev_tile_base, h->tile_base.p, ((size_t)h->n_tiles + 1) * sizeof(u64), cudaMemcpyDeviceToDevice, h->stream));
-    return G2N_OK;
-}
+#define DX_SIGNAL(E, COUNTS, CAP, AUX)                                                                                                   \
+    do {                                                                                                                                 \
+        KScope ks(h, "k_dx_signal");                                                                                                     \
+        k_dx_signal<<<1, 32, 0, h->stream>>>(X, (E), loc, (COUNTS), (u64)(CAP), (AUX), h->d_ds);                                         \
+    } while (0)
 
-int g2n_dist_merge(g2n_handle* h, const void* dev_keys_all, uint64_t key_stride, const uint64_t* n_keys, const void* dev_tile_base_all,
-                   uint64_t tile_stride, const uint64_t* rec_base, uint64_t total_records, int world, uint64_t* n_global_out)
+int g2n_dist_stage(g2n_handle* h, int stage, const uint8_t* text, uint64_t nbytes, const g2n_params* p, int speculative)
 {
-    if (!h || !n_keys || !rec_base || !n_global_out || world < 1 || world > 8) return G2N_ERR_INVALID;
+    if (!h || !h->dx_inited || stage < 0 || stage > 6) return G2N_ERR_INVALID;
     CK(cudaSetDevice(h->device));
-    u64 total_keys = 0;
-    for (int s = 0; s < world; s++) total_keys += n_keys[s];
-    if (total_records >= (1ull << 30) - 1) { h->err = "more than 2^30 records across all ranks"; return G2N_ERR_UNSUPPORTED; }
-    const u64 want_slots = total_keys + total_keys / 2 + 64;
-    const u32 gcap = next_pow2(want_slots < 1024 ? 1024 : want_slots);
-    h->gcap = gcap;
-    CK(h->gtable.ensure((size_t)gcap * sizeof(TKey)));
-    CK(h->gfirst.ensure((size_t)gcap * sizeof(u64)));
-    CK(h->gslot_id.ensure((size_t)gcap * sizeof(u32)));
-    CK(cudaMemsetAsync(h->gtable.p, 0, (size_t)gcap * sizeof(TKey), h->stream));
-    CK(cudaMemsetAsync(h->gfirst.p, 0, (size_t)gcap * sizeof(u64), h->stream));
-    Counters& hc = *h->h_cnt;
-    CK(cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
-    ScanParams P;
-    memset(&P, 0, sizeof(P));
-    P.tkeys = h->gtable.as<TKey>();
-    P.tfirst = h->gfirst.as<u64>();
-    P.table_mask = gcap - 1;
-    P.cnt = h->d_cnt;
-    DistMergeParams D;
-    memset(&D, 0, sizeof(D));
-    D.keys = (const uint8_t*)dev_keys_all;
-    D.tile_base = (const uint8_t*)dev_tile_base_all;
-    D.key_stride = key_stride;
-    D.tile_stride = tile_stride;
-    D.world = world;
-    for (int s = 0; s < world; s++) { D.n_keys[s] = n_keys[s]; D.rec_base[s] = rec_base[s]; }
-    if (total_keys) {
-        KScope ks(h, "k_dist_insert");
-        k_dist_insert<<<grid_for(total_keys / world + 1, 256), 256, 0, h->stream>>>(P, D);
+    const int W = h->dxp.world;
+    for (int s = 0; s < W; s++)
+        if (!h->dxp.arena[s] || !h->dxp.ctl[s]) { h->err = "multi-GPU peers are not connected"; return G2N_ERR_INVALID; }
+    if (stage == 0) {
+        if (!p) return G2N_ERR_INVALID;
+        if (p->weight_tag && p->weight_tag_len > 0) { h->err = "multi-GPU builds are unweighted in this version"; return G2N_ERR_UNSUPPORTED; }
+        h->built = false;
+        h->dx_spec = speculative != 0;
+        if (h->dx_spec) {
+            if (!h->hint_valid) { h->err = "speculative multi-GPU build without a previous build on this handle"; return G2N_ERR_INVALID; }
+            int rc = tokenize_phase(h, text, nbytes, p, true, false);
+            if (rc) return rc;
+        } else if (!h->dx_probed) {
+            h->err = "g2n_dist_probe must precede a host-planned multi-GPU build";
+            return G2N_ERR_INVALID;
+        }
+        h->dx_probed = false;
+        h->dxp.epoch++;
+        if (!h->dx_spec) {  // a repeated host-planned pass over the same probe: the bitmap must start clean
+            CK(cudaMemsetAsync(h->zids.p, 0, h->zids_bytes, h->stream));
+        }
+        CK(cudaMemsetAsync(h->dx_loc.p, 0, sizeof(DxLocal), h->stream));
+        CK(cudaMemsetAsync(h->dx_zg.p, 0, (size_t)h->dx_gcap * (sizeof(TKey) + sizeof(u64)), h->stream));
+        const u64 words = (4 * h->cap_R + 31) / 32 + 1;
+        CK(h->wprefix.ensure((words + 2) * sizeof(u32)));
+        CK(h->slot_id.ensure((size_t)h->table_cap * sizeof(u32)));
+        CK(h->dx_sent.ensure((size_t)h->table_cap * sizeof(u32)));
+        CK(h->id2slot.ensure((h->cap_n + 1) * sizeof(u32)));
+        CK(h->name_len.ensure((h->cap_n + 1) * sizeof(u32)));
+        CK(h->name_off.ensure((h->cap_n + 2) * sizeof(u64)));
+        h->slab_mode = true;
+        h->names_sized = false;
+        h->names_ready = false;
+        h->tsv_ready = false;
     }
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(&hc, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    if (hc.flags & CF_TABLE_FULL) { h->err = "global table overflow"; return G2N_ERR_INTERNAL; }
-    const u64 n = hc.n_keys;
-    if (n > 0x7FFFFFFFull) { h->err = "more than 2^31-1 nodes (int64 indices) is out of scope"; return G2N_ERR_UNSUPPORTED; }
-    h->n_global = n;
-    *n_global_out = n;
-    // global IDs: same bitmap ranking, the order already is the bit index
-    const u64 words = (4 * total_records + 31) / 32 + 1;
-    {
-        int rc0 = layout_zids(h, total_records);
-        if (rc0) return rc0;
-    }
-    CK(h->wprefix.ensure((words + 2) * sizeof(u32)));
-    CK(h->id2slot.ensure((n + 1) * sizeof(u32)));
-    CK(h->name_len.ensure((n + 1) * sizeof(u32)));
-    CK(h->name_off.ensure((n + 2) * sizeof(u64)));
-    CK(h->slot_id.ensure((size_t)h->table_cap * sizeof(u32)));
-    if (n > 0) {
-        CK(cudaMemsetAsync(h->zids.p, 0, h->zids_bytes, h->stream));
-        { KScope ks(h, "k_dist_mark"); k_dist_mark<<<grid_for(gcap, 256), 256, 0, h->stream>>>(h->gtable.as<TKey>(), h->gfirst.as<u64>(), gcap, h->d_bitmap); }
-        LoadPopc lp{h->d_bitmap};
-        int rc = launch_scan<u32>(h, lp, h->wprefix.as<u32>(), nullptr, words, nullptr, h->d_scan_words);
-        if (rc) return rc;
-        { KScope ks(h, "k_dist_assign"); k_dist_assign<<<grid_for(gcap, 256), 256, 0, h->stream>>>(h->gtable.as<TKey>(), h->gfirst.as<u64>(), gcap, h->d_bitmap, h->wprefix.as<u32>(), h->gslot_id.as<u32>(), h->id2slot.as<u32>(), h->name_len.as<u32>()); }
-        LoadArray<u32> ln{h->name_len.as<u32>()};
-        rc = launch_scan<u64>(h, ln, (u64*)h->name_off.as<u64>(), nullptr, n, nullptr, nullptr);
-        if (rc) return rc;
-        CK(cudaMemcpyAsync(&h->h_tail[1], h->name_off.as<u64>() + n, sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
-        { KScope ks(h, "k_dist_localmap"); k_dist_localmap<<<grid_for(h->table_cap, 256), 256, 0, h->stream>>>(h->d_tkeys, h->table_cap, h->gtable.as<TKey>(), gcap - 1, h->gslot_id.as<u32>(), h->slot_id.as<u32>()); }
-        CK(cudaGetLastError());
-    } else {
-        CK(cudaMemsetAsync(h->name_off.p, 0, 2 * sizeof(u64), h->stream));
-        h->h_tail[1] = 0;
-    }
-    CK(cudaStreamSynchronize(h->stream));
-    h->names_bytes = h->h_tail[1];
-    h->names_sized = true;
-    h->have_edges = true;
-    h->edges_are_ids = false;
-    return G2N_OK;
-}
-
-int g2n_dist_entries(g2n_handle* h, int world, uint64_t rows_per_rank, uint64_t edge_base, void* dev_send, uint64_t send_cap,
-                     uint64_t* dest_counts)
-{
-    if (!h || !dest_counts || world < 1 || world > 8 || rows_per_rank == 0) return G2N_ERR_INVALID;
-    CK(cudaSetDevice(h->device));
+    const DxPeers X = h->dxp;
+    const DxLayout L = h->dxl;
+    DxLocal* loc = h->dx_loc.as<DxLocal>();
+    const DxCtl* my = h->dx_ctl.as<DxCtl>();
+    const u32 cap = h->table_cap;
+    DxOwner G;
+    G.gkeys = h->dx_zg.as<TKey>();
+    G.gfirst = (u64*)(h->dx_zg.as<uint8_t>() + (size_t)h->dx_gcap * sizeof(TKey));
+    G.gmask = h->dx_gcap - 1;
+    G.gslot = h->dx_gslot.as<u32>();
+    G.gpos = h->dx_gpos.as<u32>();
+    const u32 kgrid = grid_for(L.kcap, 256, 8);
     const int sym = h->symmax ? 1 : 0;
-    (void)edge_base;  // unweighted entries carry no emission index
-    const u64 M = h->n_edges * (u64)h->tpe * (sym ? 2 : 1);
-    if (M > send_cap) { h->err = "send buffer too small"; return G2N_ERR_INVALID; }
     const int csc = (!sym && h->params.want_format == G2N_FMT_CSC) ? 1 : 0;
-    CK(h->dest_cnt.ensure(64 * sizeof(u32)));
-    u32* cnt = h->dest_cnt.as<u32>();
-    CK(cudaMemsetAsync(cnt, 0, 64 * sizeof(u32), h->stream));
-    EmitParams E = emit_params(h);
-    E.write_ids = 1;
-    const u32 egrid = grid_for((u64)h->n_tiles * 32, 256);
-    if (M) {
-        { KScope ks(h, "k_dist_dest_count"); k_dist_dest_count<<<egrid, 256, 0, h->stream>>>(E, sym, csc, (u32)rows_per_rank, cnt); }
-        CK(cudaGetLastError());
+    switch (stage) {
+    case 0: {
+        { KScope ks(h, "k_dx_export"); k_dx_export<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->d_tkeys, h->d_tfirst, cap, h->tile_base.as<u64>(), h->d_ds, X, L, loc, h->dx_sent.as<u32>()); }
+        DX_SIGNAL(0, loc->cur_keys, L.kcap, nullptr);
+        break;
+    }
+    case 1: {
+        { KScope ks(h, "k_dx_insert"); k_dx_insert<<<kgrid, 256, 0, h->stream>>>(X, L, my, loc, G, h->d_cnt); }
+        { KScope ks(h, "k_dx_reply_first"); k_dx_reply_first<<<grid_for(L.kcap / 4 + 1, 256, 8), 256, 0, h->stream>>>(X, L, my, G); }
+        DX_SIGNAL(1, nullptr, 0, nullptr);
+        break;
+    }
+    case 2: {
+        { KScope ks(h, "k_dx_mark"); k_dx_mark<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->d_tkeys, h->d_tfirst, cap, h->tile_base.as<u64>(), h->d_ds, X, L, my, loc, h->dx_sent.as<u32>(), h->d_bitmap); }
+        const u64 words = (4 * h->cap_R + 31) / 32 + 1;
+        LoadPopc lp{h->d_bitmap};
+        int rc = launch_scan<u32>(h, lp, h->wprefix.as<u32>(), nullptr, words, &h->d_ds->words, h->d_scan_words);
+        if (rc) return rc;
+        { KScope ks(h, "k_dx_send_rank"); k_dx_send_rank<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->d_tkeys, h->d_tfirst, cap, h->tile_base.as<u64>(), h->d_ds, X, L, h->dx_sent.as<u32>(), h->d_bitmap, h->wprefix.as<u32>(), h->id2slot.as<u32>(), h->name_len.as<u32>()); }
+        DX_SIGNAL(2, nullptr, 0, h->wprefix.as<u32>());
+        break;
+    }
+    case 3: {
+        { KScope ks(h, "k_dx_reply_ids"); k_dx_reply_ids<<<kgrid, 256, 0, h->stream>>>(X, L, my, loc, G); }
+        DX_SIGNAL(3, nullptr, 0, nullptr);
+        break;
+    }
+    case 4: {
+        const u32 rows_cap = h->dx_spec ? (u32)h->dx_rows_cap : 0xFFFFFFFFu;
+        { KScope ks(h, "k_dx_localmap"); k_dx_localmap<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->d_tkeys, cap, h->d_ds, X, L, my, loc, h->dx_sent.as<u32>(), h->slot_id.as<u32>(), rows_cap); }
+        const u32 egrid = grid_for((h->cap_E + 256 * DXE_BATCH - 1) / (256 * DXE_BATCH), 1, 8);
+        u32* es = h->edge_slots.as<u32>();
+        {
+            KScope ks(h, "k_dx_entries");
+            switch (h->tpe) {
+                case 1: k_dx_entries<1><<<egrid, 256, 0, h->stream>>>(es, h->slot_id.as<u32>(), h->d_ds, sym, csc, X, L, loc); break;
+                case 2: k_dx_entries<2><<<egrid, 256, 0, h->stream>>>(es, h->slot_id.as<u32>(), h->d_ds, sym, csc, X, L, loc); break;
+                default: k_dx_entries<4><<<egrid, 256, 0, h->stream>>>(es, h->slot_id.as<u32>(), h->d_ds, sym, csc, X, L, loc); break;
+            }
+        }
         h->edges_are_ids = true;
-        E.ids_ready = 1;
-        E.write_ids = 0;
+        DX_SIGNAL(4, loc->cur_pairs, L.pcap, nullptr);
+        break;
     }
-    u32 hcnt[8];
-    CK(cudaMemcpyAsync(hcnt, cnt, 8 * sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    u32 off[8];
-    u32 run = 0;
-    for (int d = 0; d < 8; d++) { off[d] = run; run += d < world ? hcnt[d] : 0; }
-    for (int d = 0; d < world; d++) dest_counts[d] = hcnt[d];
-    if (M) {
-        CK(cudaMemcpyAsync(cnt + 16, off, 8 * sizeof(u32), cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemsetAsync(cnt + 32, 0, 8 * sizeof(u32), h->stream));
-        { KScope ks(h, "k_dist_dest_scatter"); k_dist_dest_scatter<<<egrid, 256, 0, h->stream>>>(E, sym, csc, (u32)rows_per_rank, world, cnt + 16, cnt + 32, (DistPair*)dev_send); }
-        CK(cudaGetLastError());  // no synchronisation: the exchange that follows is ordered on the same stream
+    case 5: {
+        u64 rows_cap = h->dx_rows_cap, recv_cap = h->dx_recv_cap;
+        { KScope ks(h, "k_dx_slab_sizes"); k_dx_slab_sizes<<<1, 32, 0, h->stream>>>(X, L, my, loc, h->d_ds, h->dx_spec ? (u32)recv_cap : 0xFFFFFFF0u, h->dx_spec ? (u32)rows_cap : 0xFFFFFFFFu); }
+        if (!h->dx_spec) {
+            // host-planned pass: size the slab buffers exactly (one extra round trip)
+            CK(cudaMemcpyAsync(h->h_loc, loc, sizeof(DxLocal), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            rows_cap = h->h_loc->n_rows;
+            recv_cap = h->h_loc->n_recv;
+            h->dx_rows_cap = rows_cap;
+            h->dx_recv_cap = recv_cap;
+        }
+        DX_SIGNAL(5, nullptr, 0, nullptr);
+        if (recv_cap >= 0xFFFFFFF0ull) { h->err = "more than 2^32 entries in one slab"; return G2N_ERR_UNSUPPORTED; }
+        CK(h->entries.ensure((recv_cap + 1) * sizeof(u32)));
+        {
+            int rc0 = layout_zrows(h, rows_cap);
+            if (rc0) return rc0;
+        }
+        h->spec = false;
+        CK(cudaMemsetAsync(h->zrows.p, 0, h->zrows_bytes, h->stream));
+        h->result_format = csc ? G2N_FMT_CSC : G2N_FMT_CSR;
+        const u32 pgrid = grid_for(recv_cap / (u64)W + 1, 256, 8);
+        { KScope ks(h, "k_pairs_count"); k_pairs_count<<<pgrid, 256, 0, h->stream>>>(X, L, loc, h->d_ds, h->d_rowcnt, &loc->bad); }
+        int rc = rows_scan(h, rows_cap, &h->d_ds->rows);
+        if (rc) return rc;
+        { KScope ks(h, "k_pairs_scatter"); k_pairs_scatter<<<pgrid, 256, 0, h->stream>>>(X, L, loc, h->d_ds, h->cursor.as<u32>(), h->entries.as<u32>()); }
+        CK(cudaGetLastError());
+        rc = rows_finalize(h, h->params.dtype, false, recv_cap, rows_cap, sym, nullptr, nullptr);
+        if (rc) return rc;
+        break;
     }
+    case 6: {
+        { KScope ks(h, "k_dx_final"); k_dx_final<<<1, 32, 0, h->stream>>>(X, my, loc); }
+        CK(cudaEventRecord(h->ev[EV_REDUCE], h->stream));
+        CK(cudaMemcpyAsync(h->h_loc, loc, sizeof(DxLocal), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, h->stream));
+        break;
+    }
+    }
+    CK(cudaGetLastError());
     return G2N_OK;
 }
 
-int g2n_dist_slab(g2n_handle* h, const void* dev_pairs, uint64_t n_pairs, uint64_t row0, uint64_t n_rows)
+// The one host round trip of a multi-GPU build.  G2N_ERR_RETRY: some rank exceeded a capacity (the same
+// verdict on every rank): repeat with g2n_dist_probe + a host-planned pass.
+int g2n_dist_finish(g2n_handle* h, g2n_dist_result* out)
 {
-    if (!h || (!dev_pairs && n_pairs)) return G2N_ERR_INVALID;
+    if (!h || !out || !h->dx_inited) return G2N_ERR_INVALID;
     CK(cudaSetDevice(h->device));
-    const int sym = h->symmax ? 1 : 0;
-    h->slab_mode = true;
-    h->slab_rows = n_rows;
-    h->n_nodes = h->n_global;
-    h->result_format = (!sym && h->params.want_format == G2N_FMT_CSC) ? G2N_FMT_CSC : G2N_FMT_CSR;
-    if (n_pairs >= 0xFFFFFFF0ull) { h->err = "more than 2^32 entries in one slab"; return G2N_ERR_UNSUPPORTED; }
-    CK(h->entries.ensure((n_pairs + 1) * sizeof(u32)));
-    {
-        int rc0 = layout_zrows(h, n_rows);
-        if (rc0) return rc0;
-    }
-    h->spec = false;
-    CK(cudaMemsetAsync(h->zrows.p, 0, h->zrows_bytes, h->stream));
-    k_set_sizes<<<1, 32, 0, h->stream>>>(h->d_ds, (u32)n_rows, (u32)n_pairs);
-    if (n_pairs) {
-        KScope ks(h, "k_pairs_count");
-        k_pairs_count<<<grid_for(n_pairs, 256), 256, 0, h->stream>>>((const DistPair*)dev_pairs, n_pairs, (u32)row0, h->d_rowcnt);
-    }
-    CK(cudaGetLastError());
-    int rc = rows_scan(h, n_rows, nullptr);
-    if (rc) return rc;
-    if (n_pairs) {
-        KScope ks(h, "k_pairs_scatter");
-        k_pairs_scatter<<<grid_for(n_pairs, 256), 256, 0, h->stream>>>((const DistPair*)dev_pairs, n_pairs, (u32)row0, h->cursor.as<u32>(), h->entries.as<u32>());
-    }
-    CK(cudaGetLastError());
-    rc = rows_finalize(h, h->params.dtype, false, n_pairs, n_rows, sym, nullptr, nullptr);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(&h->h_ctl->s, h->d_ds, sizeof(DevSizes), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    const DxLocal& l = *h->h_loc;
+    memset(out, 0, sizeof(*out));
+    out->bad = l.final_bad;
+    out->n_global = l.n_global;
+    out->row0 = l.row0;
+    out->n_rows = l.n_rows;
+    out->n_recv = l.n_recv;
+    out->n_first = l.n_first;
+    out->id0 = l.idbase[h->dxp.rank];
+    out->n_keys = l.n_keys;
+    out->n_records = l.n_records;
+    out->n_edge_records = l.n_edges;
+    for (int d = 0; d < h->dxp.world; d++) { out->keys_to[d] = l.cur_keys[d]; out->pairs_to[d] = l.cur_pairs[d]; }
+    h->diag.gpu_launches = h->launches;
+    if (l.final_bad) {
+        char b[96];
+        snprintf(b, sizeof b, "multi-GPU build has to be repeated (status bits 0x%x)", l.final_bad);
+        h->err = b;
+        return (l.final_bad & DXB_TIMEOUT) ? G2N_ERR_INTERNAL : G2N_ERR_RETRY;
+    }
+    h->n_global = l.n_global;
+    h->n_nodes = l.n_global;
+    h->slab_rows = l.n_rows;
+    h->names_n = l.n_first;
+    h->names_id0 = l.idbase[h->dxp.rank];
+    h->n_edges = l.n_edges;
+    h->n_records = l.n_records;
     h->nnz = h->h_ctl->s.nnz;
+    out->nnz = h->nnz;
+    h->diag.n_records = l.n_records;
+    h->diag.n_edge_records = l.n_edges;
+    h->diag.n_triplets = (u64)l.n_edges * (u64)h->tpe;
+    h->diag.speculative = h->dx_spec ? 1 : 0;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, h->ev[EV_START], h->ev[EV_REDUCE]) == cudaSuccess) h->diag.ms_total = ms;
+    h->have_edges = false;  // g2n_convert does not apply to a slab
     h->built = true;
     return G2N_OK;
 }

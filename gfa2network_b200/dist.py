@@ -1,40 +1,46 @@
-"""Multi-GPU GFA -> CSR build: one process per GPU, `torch.distributed` (NCCL) for the plumbing,
-libg2n.so for every device phase (include/g2n.h "multi-GPU phases").
+"""Multi-GPU GFA -> CSR build: one process per GPU (include/g2n.h "multi-GPU build").
 
-    rank r holds its own newline-aligned byte range of the text
-    1. g2n_dist_scan      tokenize the shard (local table, local first-appearance order)
-    2. all_gather         distinct keys (32 B each) + per-tile record prefix of every rank
-       g2n_dist_merge     same global dictionary on every rank -> global node IDs (the reference's
-                          numbering over the concatenated shards, builders.py:194-198, 219-221)
-    3. g2n_dist_entries   row entries bucketed by owner(row) = row // rows_per_rank
-       all_to_all_single  entries travel to the rank that owns their row block
-       g2n_dist_slab      duplicate sum / max(S, S^T) -> this rank's CSR slab (builders.py:279-283)
+    rank r holds its own newline-aligned byte range of the text (file order = rank order)
+    stage 0  tokenize the shard; distinct keys -> owner = hash(key) % world
+    stage 1  owners find the global first appearance of every key, tell the sources
+    stage 2  every shard ranks the keys that first appear in it; ranks -> owners
+    stage 3  owners hand every source the node ID of each of its keys (the reference's numbering over the
+             concatenated shards, builders.py:194-198, 219-221)
+    stage 4  row entries -> owner(row) = row // ceil(n / world)
+    stage 5  duplicate sum / max(S, S^T) -> this rank's CSR slab (builders.py:279-283, utils.py:55)
+    stage 6  the build's verdict, the same on every rank (a capacity miss anywhere repeats the build everywhere)
 
-The exchange steps are real NCCL collectives over NVLink; phase 1 has no collective.
-`LocalRank` holds the device work of one rank, `DistBuilder` adds the collectives; tests drive several
-`LocalRank`s on one GPU with the exchanges done by tensor slicing (logical shards).
+The data never touches this file: libg2n's kernels write straight into the peers' exchange arenas over
+NVLink (CUDA IPC mappings) and synchronise through flags in device memory (csrc/dist.cuh).
+`torch.distributed` is only the bootstrap channel -- shard counts, IPC handles, error agreement -- and is
+used only by host-planned builds (the first build of a shape, or after a capacity miss); a repeated build
+queues its stages without any host round trip and synchronises once, at the end.
+`LocalRank` wraps one rank's handle, `DistBuilder` adds the bootstrap; tests drive several `LocalRank`s
+on one GPU (logical shards: same kernels, peers are plain device pointers).
 Restrictions of this version: unweighted builds, node names <= 15 bytes, <= 8 ranks."""
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass
+from dataclasses import dataclass, field
 
 import numpy as np
 import scipy.sparse as sp
 
 from . import _capi
 
-PAIR_WORDS = 1  # int64 words per exchanged row entry {entry u32 = col << 1 | dir, row u32}
-KEY_WORDS = 4   # int64 words per exchanged key {k0, k1, order, pad}
-META_WORDS = 8  # int64 words of per-rank counts at the head of an exchanged block
 MAX_WORLD = 8
+N_STAGES = 7
 
 
-def block_layout(key_stride: int, tile_stride: int) -> tuple[int, int, int]:
-    """One all-gathered block per rank: [meta | keys | tile prefix]; returns (block words, key offset, tile offset)."""
-    key_off = META_WORDS
-    tile_off = key_off + key_stride * KEY_WORDS
-    return tile_off + tile_stride, key_off, tile_off
+def plan_caps(infos: list[dict], world: int, attempt: int = 0) -> tuple[int, int]:
+    """Capacities every rank derives from the gathered shard counts: keys per (source, owner) segment
+    (hash partition: max shard / world plus slack that grows with every retry) and row entries per
+    (source, row owner) segment (a shard may send everything to one owner)."""
+    max_keys = max(i["n_keys"] for i in infos)
+    max_ent = max(i["n_entries"] for i in infos)
+    kcap = int(max_keys / world * (1.25 + 0.5 * attempt)) + 4096
+    pcap = max_ent + max_ent // 16 + 1024
+    return kcap, pcap
 
 
 # ------------------------------------------------------------------ host logic (pure, CPU-testable)
@@ -90,6 +96,9 @@ def assemble_slabs(slabs, n_global: int, fmt: str = "csr"):
 
 
 # ------------------------------------------------------------------ one rank's device work
+_MODE_KEYS = ("directed", "bidirected", "keep_directed_bidir", "asymmetric", "strip_orientation", "dtype", "matrix_format")
+
+
 class LocalRank:
     def __init__(self, device_index: int, rank: int, world: int, stream_ptr: int | None = None):
         import torch
@@ -101,72 +110,98 @@ class LocalRank:
         self.dev = torch.device("cuda", device_index)
         self.h = _capi.Handle(device_index)
         self.h.set_stream(stream_ptr if stream_ptr is not None else torch.cuda.current_stream(self.dev).cuda_stream)
+        self.h.check(self.h.lib.g2n_dist_init(self.h.h, rank, world))
+        self.params = None
+        self.text = None
 
-    def scan(self, text_dev, *, directed=True, bidirected=False, keep_directed_bidir=False, asymmetric=False,
-             strip_orientation=False, dtype="float64", matrix_format="csr") -> list[int]:
+    def set_input(self, text_dev, *, directed=True, bidirected=False, keep_directed_bidir=False, asymmetric=False,
+                  strip_orientation=False, dtype="float64", matrix_format="csr"):
         want = {"csr": _capi.FMT_CSR, "csc": _capi.FMT_CSC}[matrix_format]
         self.params = _capi.Params(int(directed), int(bidirected), int(keep_directed_bidir), int(asymmetric), int(strip_orientation),
                                    _capi.DTYPES[np.dtype(dtype).name], want, 1, None, 0, 0)
         self.text = text_dev
-        nbytes = int(text_dev.numel())
+        self.nbytes = int(text_dev.numel())
+        self.text_ptr = C.c_void_p(text_dev.data_ptr() if self.nbytes else 0)
+
+    def probe(self) -> dict:
+        """Host-planned tokenizer pass over this shard.  Never raises for what the input holds: the
+        status travels to every rank first, so that all of them raise the same exception."""
         info = _capi.DistInfo()
-        rc = self.h.lib.g2n_dist_scan(self.h.h, C.c_void_p(text_dev.data_ptr() if nbytes else 0), nbytes, C.byref(self.params), C.byref(info))
-        self.scan_rc = rc
-        self.h.check(rc)
-        self.info = info
-        return [int(info.n_keys), int(info.n_tiles), int(info.n_records), int(info.n_edge_records), int(info.n_entries)]
+        rc = self.h.lib.g2n_dist_probe(self.h.h, self.text_ptr, self.nbytes, C.byref(self.params), C.byref(info))
+        d = self.h.status()
+        return dict(rc=int(rc), msg=self.h.last_error() if rc else "", n_keys=int(info.n_keys), n_tiles=int(info.n_tiles),
+                    n_records=int(info.n_records), n_edge_records=int(info.n_edge_records), n_entries=int(info.n_entries),
+                    err_kind=int(d.err_kind), err_offset=int(d.err_offset), unknown_byte=int(d.unknown_byte), unknown_offset=int(d.unknown_offset),
+                    nbytes=self.nbytes)
 
-    def export_block(self, mine: list[int], key_stride: int, tile_stride: int):
-        """This rank's block [meta | keys | tile prefix] for the all-gather.  If the shard holds more keys or
-        tiles than the strides allow, only the meta words are valid (every rank sees that and re-plans)."""
-        t = self.torch
-        words, key_off, tile_off = block_layout(key_stride, tile_stride)
-        block = t.empty(words, dtype=t.int64, device=self.dev)
-        meta = list(mine) + [key_stride, tile_stride] + [0] * (META_WORDS - len(mine) - 2)
-        block[:META_WORDS] = t.tensor(meta, dtype=t.int64)  # one small H2D copy, ordered on the stream
-        if mine[0] <= key_stride and mine[1] + 1 <= tile_stride:
-            self.h.check(self.h.lib.g2n_dist_export(self.h.h, C.c_void_p(block.data_ptr() + 8 * key_off), C.c_void_p(block.data_ptr() + 8 * tile_off)))
-        return block
+    def plan(self, kcap: int, pcap: int, rows_cap: int = 0, recv_cap: int = 0, dry_run: bool = False) -> bool:
+        re = C.c_int(0)
+        self.h.check(self.h.lib.g2n_dist_plan(self.h.h, kcap, pcap, rows_cap, recv_cap, int(dry_run), C.byref(re)))
+        return bool(re.value)
 
-    def merge(self, blocks_all, key_stride, tile_stride, meta) -> int:
-        """blocks_all: the `world` blocks of export_block(), rank order, one buffer."""
-        W = self.world
-        words, key_off, tile_off = block_layout(key_stride, tile_stride)
-        u64a = C.c_uint64 * MAX_WORLD
-        n_keys = [m[0] for m in meta] + [0] * (MAX_WORLD - W)
-        rec_base = exclusive_prefix([m[2] for m in meta]) + [0] * (MAX_WORLD - W)
-        n_global = C.c_uint64()
-        base = blocks_all.data_ptr()
-        self.h.check(self.h.lib.g2n_dist_merge(self.h.h, C.c_void_p(base + 8 * key_off), 8 * words, u64a(*n_keys),
-                                               C.c_void_p(base + 8 * tile_off), 8 * words, u64a(*rec_base), sum(m[2] for m in meta), W,
-                                               C.byref(n_global)))
-        self.n_global = int(n_global.value)
-        return self.n_global
+    def local_mem(self) -> tuple[int, int, bytes]:
+        a, c = C.c_void_p(), C.c_void_p()
+        ipc = (C.c_uint8 * 128)()
+        self.h.check(self.h.lib.g2n_dist_local_mem(self.h.h, C.byref(a), C.byref(c), ipc))
+        return int(a.value), int(c.value), bytes(ipc)
 
-    def entries(self, meta):
-        t = self.torch
-        edge_base = exclusive_prefix([m[3] for m in meta])[self.rank]
-        n_ent = int(self.info.n_entries)
-        send = t.empty(max(1, n_ent) * PAIR_WORDS, dtype=t.int64, device=self.dev)
-        dest = (C.c_uint64 * MAX_WORLD)()
-        self.h.check(self.h.lib.g2n_dist_entries(self.h.h, self.world, rows_per_rank(self.n_global, self.world), edge_base,
-                                                 C.c_void_p(send.data_ptr()), n_ent, dest))
-        return send, [int(dest[d]) for d in range(self.world)]
+    def set_peers(self, arenas: list[int], ctls: list[int]):
+        vp = C.c_void_p * MAX_WORLD
+        pad = [0] * (MAX_WORLD - len(arenas))
+        self.h.check(self.h.lib.g2n_dist_set_peers(self.h.h, vp(*(list(arenas) + pad)), vp(*(list(ctls) + pad))))
 
-    def slab(self, recv, n_recv: int):
-        row0, n_rows = slab_bounds(self.n_global, self.rank, self.world)
-        self.h.check(self.h.lib.g2n_dist_slab(self.h.h, C.c_void_p(recv.data_ptr()), n_recv, row0, n_rows))
-        self._recv = recv
-        return row0, n_rows
+    def open_peers(self, ipc_all: bytes):
+        self.h.check(self.h.lib.g2n_dist_open_peers(self.h.h, ipc_all))
+
+    def close_peers(self):
+        self.h.check(self.h.lib.g2n_dist_close_peers(self.h.h))
+
+    def stage(self, k: int, speculative: bool):
+        self.h.check(self.h.lib.g2n_dist_stage(self.h.h, k, self.text_ptr, self.nbytes, C.byref(self.params), int(speculative)))
+
+    def finish(self) -> tuple[int, _capi.DistResult]:
+        res = _capi.DistResult()
+        rc = self.h.lib.g2n_dist_finish(self.h.h, C.byref(res))
+        if rc not in (_capi.G2N_OK, _capi.G2N_ERR_RETRY):
+            self.h.check(rc)
+        return rc, res
+
+    def remember(self, res: _capi.DistResult, kcap: int, pcap: int):
+        """Slab capacities of the next (speculative) build of this shape: this build's sizes plus slack."""
+        self.plan(kcap, pcap, int(res.n_rows) + int(res.n_rows) // 16 + 1024, int(res.n_recv) + int(res.n_recv) // 16 + 1024)
 
     def fetch_slab(self):
         _, indptr, indices, data = self.h.fetch_matrix()
         return indptr, indices, data
 
     def node_list(self, raw_bytes_id: bool = False):
+        """(ID of the first name, names): the nodes that first appear in this rank's shard."""
         from .builders import _node_list
 
-        return _node_list(self.h, raw_bytes_id)
+        names = _node_list(self.h, raw_bytes_id)
+        return int(self.h.sizes().names_id0), names
+
+
+def raise_agreed(infos: list[dict]):
+    """The exception parse_gfa raises for the concatenated shards (the first offending line
+    in file order = the lowest rank that reports one; a warning for an unsupported record only if it
+    precedes that line), raised identically on every rank."""
+    import warnings
+
+    from .builders import _ERRORS as _PARSE_ERRORS
+
+    bad = next((i for i in infos if i["rc"] != _capi.G2N_OK), None)
+    first_unknown = next(((r, i) for r, i in enumerate(infos) if i["unknown_byte"] >= 0), None)
+    if first_unknown is not None and (bad is None or first_unknown[0] <= infos.index(bad)):
+        warnings.warn("Skipping unsupported record: " + bytes([first_unknown[1]["unknown_byte"]]).decode(errors="replace"), RuntimeWarning, stacklevel=3)
+    if bad is None:
+        return
+    if bad["rc"] == _capi.G2N_ERR_PARSE:
+        exc, msg = _PARSE_ERRORS.get(bad["err_kind"], (ValueError, "malformed record"))
+        raise exc(msg)
+    if bad["rc"] == _capi.G2N_ERR_UNSUPPORTED:
+        raise NotImplementedError(bad["msg"])
+    raise _capi.G2NError(f"libg2n status {bad['rc']}: {bad['msg']}")
 
 
 @dataclass
@@ -175,12 +210,19 @@ class DistResult:
     row0: int
     n_rows: int
     nnz_local: int
-    info: dict
+    info: dict = field(default_factory=dict)
 
 
-# ------------------------------------------------------------------ collectives
+def _result(res: _capi.DistResult, world: int, speculative: bool) -> DistResult:
+    return DistResult(int(res.n_global), int(res.row0), int(res.n_rows), int(res.nnz),
+                      dict(n_recv=int(res.n_recv), n_first=int(res.n_first), id0=int(res.id0), n_keys=int(res.n_keys),
+                           n_records=int(res.n_records), n_edge_records=int(res.n_edge_records), speculative=speculative,
+                           keys_to=[int(res.keys_to[d]) for d in range(world)], pairs_to=[int(res.pairs_to[d]) for d in range(world)]))
+
+
+# ------------------------------------------------------------------ bootstrap over torch.distributed
 class DistBuilder:
-    """Per-rank driver: LocalRank + NCCL collectives (`torch.distributed`, default or given group)."""
+    """Per-rank driver: LocalRank + the bootstrap channel (`torch.distributed`, default or given group)."""
 
     def __init__(self, device_index: int, group=None):
         import torch
@@ -191,78 +233,54 @@ class DistBuilder:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.local = LocalRank(device_index, self.rank, self.world)
         self.dev = self.local.dev
-        self.strides = None  # (key_stride, tile_stride) of the exchanged blocks, remembered between builds
+        self.caps = None        # (kcap, pcap) every rank agreed on; None until a host-planned build succeeded
+        self.mode = None        # the mode those capacities were planned for (the same on every rank)
+        self.connected = False  # peers' arenas are mapped
+
+    def _gather(self, obj):
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj, group=self.group)
+        return out
 
     def build(self, text_dev, **mode) -> DistResult:
-        torch, dist, W, L = self.torch, self.dist, self.world, self.local
-        import os
-        import time
-        dbg = os.environ.get("G2N_DIST_DEBUG")
-        marks = []
-
-        def mark(name):
-            if dbg:
-                torch.cuda.synchronize()
-                marks.append((name, time.perf_counter()))
-
-        mark("start")
-        mine = L.scan(text_dev, **mode)
-        mark("scan")
-        # ---- phase 2: dictionary merge.  ONE all-gather of [meta | keys | tile prefix] blocks; the block
-        # strides are those of the previous build of this builder (+ slack) -- if any rank's shard does not
-        # fit, every rank sees it in the gathered meta words and the exchange is repeated with exact strides.
-        meta = None
-        for attempt in range(2):
-            if self.strides is None:
-                if W > 1:
-                    t = torch.tensor(mine, dtype=torch.int64, device=self.dev)
-                    out = torch.empty(W * len(mine), dtype=torch.int64, device=self.dev)
-                    dist.all_gather_into_tensor(out, t, group=self.group)
-                    meta = out.view(W, len(mine)).tolist()
-                else:
-                    meta = [mine]
-                ks, ts = max(max(m[0] for m in meta), 1), max(m[1] for m in meta) + 1
-                self.strides = (ks + ks // 16 + 64, ts + ts // 16 + 8)
-            key_stride, tile_stride = self.strides
-            block = L.export_block(mine, key_stride, tile_stride)
-            mark("export")
-            if W > 1:
-                blocks_all = torch.empty(W * block.numel(), dtype=torch.int64, device=self.dev)
-                dist.all_gather_into_tensor(blocks_all, block, group=self.group)
+        L, W = self.local, self.world
+        L.set_input(text_dev, **mode)
+        mode_key = tuple(sorted(mode.items()))
+        if self.caps is not None and self.mode != mode_key:
+            self.caps = None
+        self.mode = mode_key
+        if self.caps is not None:
+            # speculative: no host round trip, no collective; every rank reaches the same verdict
+            for k in range(N_STAGES):
+                L.stage(k, True)
+            rc, res = L.finish()
+            if rc == _capi.G2N_OK:
+                L.remember(res, *self.caps)
+                return _result(res, W, True)
+            self.caps = None
+        for attempt in range(6):
+            infos = self._gather(L.probe())
+            raise_agreed(infos)
+            kcap, pcap = plan_caps(infos, W, attempt)
+            if L.plan(kcap, pcap, dry_run=True) or not self.connected:  # same decision on every rank
+                L.close_peers()
+                self._gather(0)  # nobody frees an arena that a peer still maps
+                L.plan(kcap, pcap)
+                handles = self._gather(L.local_mem()[2])
+                L.open_peers(b"".join(handles))
+                self.connected = True
             else:
-                blocks_all = block
-            got = blocks_all.view(W, -1)[:, :META_WORDS].tolist()
-            meta = [g[:len(mine)] for g in got]
-            if all(m[0] <= key_stride and m[1] + 1 <= tile_stride for m in meta):
-                break
-            self.strides = None  # some shard outgrew the remembered strides: plan again (same decision on every rank)
-        mark("allgather")
-        ng = L.merge(blocks_all, key_stride, tile_stride, meta)
-        mark("merge")
-        # ---- phase 3: edge exchange by owner row block
-        send, send_counts = L.entries(meta)
-        mark("entries")
-        if W > 1:
-            sc = torch.tensor(send_counts, dtype=torch.int64, device=self.dev)
-            rcnt = torch.empty(W, dtype=torch.int64, device=self.dev)
-            dist.all_to_all_single(rcnt, sc, group=self.group)
-            recv_counts = rcnt.tolist()
-            n_recv = sum(recv_counts)
-            recv = torch.empty(max(1, n_recv) * PAIR_WORDS, dtype=torch.int64, device=self.dev)
-            dist.all_to_all_single(recv[: n_recv * PAIR_WORDS], send[: sum(send_counts) * PAIR_WORDS],
-                                   [c * PAIR_WORDS for c in recv_counts], [c * PAIR_WORDS for c in send_counts], group=self.group)
-        else:
-            recv, n_recv = send, send_counts[0]
-        mark("alltoall")
-        row0, n_rows = L.slab(recv, n_recv)
-        mark("slab")
-        if dbg and self.rank == 0:
-            import sys
-            print("dist phases (ms): " + ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.3f}" for a, b in zip(marks, marks[1:])), file=sys.stderr)
-        s = L.h.sizes()
-        return DistResult(ng, row0, n_rows, int(s.nnz), dict(meta=meta, send_counts=send_counts, n_recv=n_recv,
-                                                            key_bytes=W * key_stride * KEY_WORDS * 8,
-                                                            pair_bytes=sum(send_counts) * PAIR_WORDS * 8))
+                L.plan(kcap, pcap)
+            for k in range(N_STAGES):
+                L.stage(k, False)
+            rc, res = L.finish()
+            if rc == _capi.G2N_OK:
+                self.caps = (kcap, pcap)
+                L.remember(res, kcap, pcap)
+                return _result(res, W, False)
+        raise _capi.G2NError("multi-GPU build: capacity retries exhausted")
 
     def fetch_slab(self):
         return self.local.fetch_slab()
@@ -270,11 +288,13 @@ class DistBuilder:
     def gather_matrix(self, result: DistResult, fmt: str = "csr"):
         """Assemble the full matrix on every rank (parity tests; production keeps the slabs)."""
         slab = tuple(np.array(a) for a in self.fetch_slab())
-        if self.world == 1:
-            return assemble_slabs([slab], result.n_global, fmt)
-        objs = [None] * self.world
-        self.dist.all_gather_object(objs, slab, group=self.group)
-        return assemble_slabs(objs, result.n_global, fmt)
+        return assemble_slabs(self._gather(slab), result.n_global, fmt)
 
     def node_list(self, raw_bytes_id: bool = False):
-        return self.local.node_list(raw_bytes_id)
+        """The whole node list on every rank (parity tests; production keeps each shard's names)."""
+        parts = self._gather(self.local.node_list(raw_bytes_id))
+        out = []
+        for id0, names in parts:
+            assert id0 == len(out), (id0, len(out))
+            out.extend(names)
+        return out

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define G2N_ABI_VERSION 1
+#define G2N_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------------------- */
 #define G2N_OK 0
@@ -36,6 +36,8 @@ extern "C" {
 #define G2N_ERR_PARSE 3       /* the input holds a record the reference raises on: see g2n_diag */
 #define G2N_ERR_UNSUPPORTED 4 /* declared out of scope (e.g. > 2^31-1 nodes, weight tag > 64 bytes) */
 #define G2N_ERR_INTERNAL 5
+#define G2N_ERR_RETRY 6       /* multi-GPU: a remembered capacity was exceeded on some rank (same verdict on every
+                                 rank): repeat the build with g2n_dist_probe + a host-planned pass */
 
 /* ---- first-error kinds (g2n_diag.err_kind); map 1:1 to the reference's exceptions ------ */
 #define G2N_PE_NONE 0
@@ -88,6 +90,9 @@ typedef struct g2n_sizes_t {
     int32_t dtype;         /* G2N_DTYPE_* of the data array */
     int32_t reserved;
     uint64_t slab_rows;    /* rows held by this handle (== n_nodes except for a multi-GPU slab) */
+    uint64_t names_count;  /* node names held by this handle (== n_nodes except for a multi-GPU slab: the nodes
+                              whose first appearance is in this rank's shard) */
+    uint64_t names_id0;    /* ID of the first of them (0 on one GPU) */
 } g2n_sizes_t;
 
 typedef struct g2n_diag {
@@ -193,19 +198,33 @@ int g2n_coo_to_compressed(g2n_handle *h, const int32_t *row, const int32_t *col,
                           uint64_t nnz_in, uint64_t n, int32_t dtype, int32_t want_format,
                           int32_t *indptr, int32_t *indices, void *data_out, uint64_t *nnz_out);
 
-/* ---- multi-GPU phases -----------------------------------------------------
- * One process and one handle per GPU.  The library does the device work of each phase; the caller
- * moves the exchange buffers between ranks (gfa2network_b200/dist.py uses torch.distributed / NCCL):
- *   g2n_dist_scan     tokenize this rank's byte range (parser.py:114-361, builders.py:190-234 locally)
- *   g2n_dist_export   distinct local node keys + first local appearance, and the per-tile record prefix
- *   (all-gather)
- *   g2n_dist_merge    global dictionary: every rank derives the same global node IDs (the reference's
- *                     first-appearance numbering over the concatenated shards) and maps its edges to them
- *   g2n_dist_entries  row entries bucketed by owner rank (row block = rows_per_rank consecutive IDs)
- *   (all-to-all)
- *   g2n_dist_slab     duplicate sum / max(S, S^T) for the rows this rank owns -> CSR slab
- *                     (builders.py:279-283, utils.py:55); fetch with g2n_sizes / g2n_fetch_matrix
- * Restrictions of this version: unweighted builds, node names of <= 15 bytes, <= 8 ranks. */
+/* ---- multi-GPU build -------------------------------------------------------
+ * One process and one handle per GPU; each rank holds a newline-aligned byte range of the text (file
+ * order = rank order).  The result on every rank is the CSR/CSC slab of its row block
+ * [rank * ceil(n / world), ...) of the matrix parse_gfa + convert_format return on one GPU
+ * (builders.py:190-234, 279-283; utils.py:55), and the names of the nodes that first appear in its shard
+ * (consecutive IDs from g2n_sizes().names_id0).  The library moves the data itself: kernels write into
+ * the peers' exchange arenas over NVLink and signal through flags in the peers' control blocks
+ * (gfa2network_b200/csrc/dist.cuh); the caller only bootstraps -- it agrees on capacities, passes the
+ * CUDA IPC handles around (any out-of-band channel; dist.py uses torch.distributed) and queues the stages.
+ *
+ *   g2n_dist_init        rank / world of this handle
+ *   g2n_dist_probe       host-planned pass: tokenize the shard, report its counts (or its parse error)
+ *   g2n_dist_plan        capacities every rank agreed on: keys per (source, owner) segment, row entries per
+ *                        (source, row owner) segment, rows and received entries of the slab (the last two
+ *                        are only used by speculative builds).  dry_run: only report whether the arena
+ *                        would have to grow (peers must close their mappings first)
+ *   g2n_dist_local_mem   this rank's arena / control block: pointers (ranks sharing a process) and the
+ *                        two 64-byte CUDA IPC handles (ranks in other processes)
+ *   g2n_dist_set_peers / g2n_dist_open_peers / g2n_dist_close_peers
+ *   g2n_dist_stage       queue stage 0..6 on the handle's stream (no host synchronisation in a speculative
+ *                        build; `text`, `nbytes`, `p` are read by stage 0 only).  speculative = 1: the shard is
+ *                        tokenized inside stage 0 with the sizes remembered from the previous build;
+ *                        0: the tokenizer results of g2n_dist_probe are used
+ *   g2n_dist_finish      the one host round trip: G2N_OK, or G2N_ERR_RETRY on every rank
+ * Ranks that share a process (tests: several logical ranks on one GPU) must queue stage k on every rank
+ * before stage k+1 on any.  Restrictions of this version: unweighted builds, node names of <= 15 bytes,
+ * <= 8 ranks. */
 typedef struct g2n_dist_info {
     uint64_t n_keys;         /* distinct node keys in this shard */
     uint64_t n_tiles;
@@ -215,20 +234,28 @@ typedef struct g2n_dist_info {
     uint64_t reserved;
 } g2n_dist_info;
 
-int g2n_dist_scan(g2n_handle *h, const uint8_t *text, uint64_t nbytes, const g2n_params *p, g2n_dist_info *out);
-/* dev_keys: n_keys x 32 bytes {key[16], order u64, pad u64}; dev_tile_base: (n_tiles + 1) x u64 */
-int g2n_dist_export(g2n_handle *h, void *dev_keys, void *dev_tile_base);
-/* dev_keys_all / dev_tile_base_all: rank s's exported keys / tile prefix start at base + s * stride,
- * strides in BYTES (so both may point into one all-gathered buffer of per-rank blocks) */
-int g2n_dist_merge(g2n_handle *h, const void *dev_keys_all, uint64_t key_stride, const uint64_t *n_keys,
-                   const void *dev_tile_base_all, uint64_t tile_stride, const uint64_t *rec_base,
-                   uint64_t total_records, int world, uint64_t *n_global_out);
-/* edge_base: edge records of all lower ranks (unused by unweighted builds, kept for weighted ones);
- * dev_send: n_entries x 8 bytes {entry u32 = col << 1 | dir, row u32}, grouped by destination;
- * dest_counts[world] out */
-int g2n_dist_entries(g2n_handle *h, int world, uint64_t rows_per_rank, uint64_t edge_base, void *dev_send,
-                     uint64_t send_cap, uint64_t *dest_counts);
-int g2n_dist_slab(g2n_handle *h, const void *dev_pairs, uint64_t n_pairs, uint64_t row0, uint64_t n_rows);
+typedef struct g2n_dist_result {
+    uint64_t bad;            /* 0, or the DXB_* status bits (dist.cuh) that made the build repeat */
+    uint64_t n_global;       /* nodes of the whole graph */
+    uint64_t row0, n_rows;   /* this rank's row block */
+    uint64_t nnz;            /* stored entries of the slab */
+    uint64_t n_recv;         /* row entries received */
+    uint64_t n_first, id0;   /* nodes first seen in this shard; ID of the first of them */
+    uint64_t n_keys, n_records, n_edge_records; /* this shard */
+    uint64_t keys_to[8];     /* keys sent to each owner rank */
+    uint64_t pairs_to[8];    /* row entries sent to each row owner */
+} g2n_dist_result;
+
+int g2n_dist_init(g2n_handle *h, int rank, int world);
+int g2n_dist_probe(g2n_handle *h, const uint8_t *text, uint64_t nbytes, const g2n_params *p, g2n_dist_info *out);
+int g2n_dist_plan(g2n_handle *h, uint64_t key_cap, uint64_t pair_cap, uint64_t rows_cap, uint64_t recv_cap,
+                  int dry_run, int *will_realloc);
+int g2n_dist_local_mem(g2n_handle *h, void **arena, void **ctl, uint8_t *ipc128);
+int g2n_dist_set_peers(g2n_handle *h, void *const *arenas, void *const *ctls);
+int g2n_dist_open_peers(g2n_handle *h, const uint8_t *ipc_all /* world x 128 bytes, rank order */);
+int g2n_dist_close_peers(g2n_handle *h);
+int g2n_dist_stage(g2n_handle *h, int stage, const uint8_t *text, uint64_t nbytes, const g2n_params *p, int speculative);
+int g2n_dist_finish(g2n_handle *h, g2n_dist_result *out);
 
 #ifdef __cplusplus
 }

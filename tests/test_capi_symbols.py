@@ -23,14 +23,15 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), name
     assert sorted(_capi.EXPORTS) == names
-    assert lib.g2n_abi_version() == 1
+    assert lib.g2n_abi_version() == _capi.ABI_VERSION
 
 
 def test_struct_layouts_match_header():
     from gfa2network_b200 import _capi
 
     assert ctypes.sizeof(_capi.Params) == 48
-    assert ctypes.sizeof(_capi.Sizes) == 48
+    assert ctypes.sizeof(_capi.Sizes) == 64
+    assert ctypes.sizeof(_capi.DistResult) == 11 * 8 + 2 * 64
     assert ctypes.sizeof(_capi.DistInfo) == 48
     assert ctypes.sizeof(_capi.Diag) == 112
 

@@ -1,62 +1,74 @@
-"""Multi-GPU path on ONE GPU: G logical ranks (one LocalRank/handle each) with the NCCL exchanges
-replaced by tensor slicing -- the same kernels and the same host logic as `DistBuilder`, compared
-bit-for-bit with the single-GPU build and the CPU oracle."""
+"""Multi-GPU path on ONE GPU: G logical ranks (one LocalRank / handle / exchange arena each) whose peers
+are plain device pointers -- the same kernels, protocol and host logic as `DistBuilder` (the stages are
+queued rank by rank, so every signal is already there when its consumer runs) -- compared bit-for-bit
+with the CPU oracle.  Both kinds of build are covered: host-planned (first build of a shape) and
+speculative (no host round trip), and the capacity-miss path between them."""
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
 
 
-def _run_logical(text: np.ndarray, G: int, **mode):
+def _shards(text: np.ndarray, G: int):
     import torch
 
     from gfa2network_b200 import dist as D
 
-    dev = torch.device("cuda", 0)
     tb = text.tobytes()
-    ranks, shards = [], []
+    out = []
     for r in range(G):
         lo, hi = D.shard_range(len(tb), r, G, lambda p: tb.find(b"\n", p))
-        shards.append(torch.from_numpy(text[lo:hi].copy()).to(dev))
-        ranks.append(D.LocalRank(0, r, G))
-    meta = [ranks[r].scan(shards[r], **mode) for r in range(G)]
-    key_stride = max(max(m[0] for m in meta), 1)
-    tile_stride = max(m[1] for m in meta) + 1
-    blocks_all = torch.cat([ranks[r].export_block(meta[r], key_stride, tile_stride) for r in range(G)])
-    ng = {ranks[r].merge(blocks_all, key_stride, tile_stride, meta) for r in range(G)}
+        out.append(torch.from_numpy(text[lo:hi].copy()).cuda())
+    return out
+
+
+def _connect(ranks):
+    mems = [r.local_mem() for r in ranks]
+    for r in ranks:
+        r.set_peers([m[0] for m in mems], [m[1] for m in mems])
+
+
+def _build(ranks, shards, speculative, caps=None, attempt=0, **mode):
+    """One build over all logical ranks; returns ([(rc, result)], caps)."""
+    from gfa2network_b200 import dist as D
+
+    G = len(ranks)
+    for r, t in zip(ranks, shards):
+        r.set_input(t, **mode)
+    if not speculative:
+        infos = [r.probe() for r in ranks]
+        D.raise_agreed(infos)
+        if caps is None:
+            caps = D.plan_caps(infos, G, attempt)
+        for r in ranks:
+            r.plan(*caps)
+        _connect(ranks)
+    for k in range(D.N_STAGES):
+        for r in ranks:
+            r.stage(k, speculative)
+    out = [r.finish() for r in ranks]
+    return out, caps
+
+
+def _assemble(ranks, out, fmt):
+    from gfa2network_b200 import dist as D
+
+    ng = {int(res.n_global) for _, res in out}
     assert len(ng) == 1
     ng = ng.pop()
-    sends = [ranks[r].entries(meta) for r in range(G)]
-    slabs = []
-    for dst in range(G):
-        parts = []
-        for src in range(G):
-            send, counts = sends[src]
-            off = sum(counts[:dst]) * D.PAIR_WORDS
-            parts.append(send[off: off + counts[dst] * D.PAIR_WORDS])
-        recv = torch.cat(parts) if parts else torch.empty(0, dtype=torch.int64, device=dev)
-        n_recv = recv.numel() // D.PAIR_WORDS
-        if n_recv == 0:
-            recv = torch.zeros(2, dtype=torch.int64, device=dev)
-        ranks[dst].slab(recv, n_recv)
-        slabs.append(tuple(np.array(a) for a in ranks[dst].fetch_slab()))
-    A = D.assemble_slabs(slabs, ng, mode.get("matrix_format", "csr"))
-    nodes = ranks[0].node_list()
+    slabs = [tuple(np.array(a) for a in r.fetch_slab()) for r in ranks]
+    A = D.assemble_slabs(slabs, ng, fmt)
+    nodes = []
+    for r in ranks:
+        id0, names = r.node_list()
+        assert id0 == len(nodes)
+        nodes.extend(names)
     return A, nodes
 
 
-MODES = [dict(), dict(directed=False), dict(asymmetric=True), dict(bidirected=True), dict(bidirected=True, keep_directed_bidir=True),
-         dict(directed=False, matrix_format="csc"), dict(dtype="bool")]
-
-
-@pytest.mark.parametrize("G", [1, 2, 3, 8])
-@pytest.mark.parametrize("mode", MODES, ids=[str(m) for m in MODES])
-def test_logical_shards_match_oracle(G, mode):
-    from gfa2network_b200.synth import synth_gfa
+def _check(A, nodes, text, mode):
     from oracle.oracle import oracle_convert_format, oracle_parse_gfa
 
-    text = synth_gfa(30_000, 90_000, seed=9, kind=1, interleave=2048, n_paths=1)
-    A, nodes = _run_logical(text, G, **mode)
     omode = {k: v for k, v in mode.items() if k != "matrix_format"}
     fmt = mode.get("matrix_format", "csr")
     B, onodes = oracle_parse_gfa(text, return_node_list=True, **omode)
@@ -67,19 +79,145 @@ def test_logical_shards_match_oracle(G, mode):
     assert nodes == onodes
 
 
-def test_dist_refuses_weights_and_long_names():
+MODES = [dict(), dict(directed=False), dict(asymmetric=True), dict(bidirected=True), dict(bidirected=True, keep_directed_bidir=True),
+         dict(directed=False, matrix_format="csc"), dict(dtype="bool")]
+
+
+@pytest.mark.parametrize("G", [1, 2, 3, 8])
+@pytest.mark.parametrize("mode", MODES, ids=[str(m) for m in MODES])
+def test_logical_shards_match_oracle(G, mode):
+    from gfa2network_b200 import _capi
+    from gfa2network_b200 import dist as D
+    from gfa2network_b200.synth import synth_gfa
+
+    text = synth_gfa(30_000, 90_000, seed=9, kind=1, interleave=2048, n_paths=1)
+    shards = _shards(text, G)
+    ranks = [D.LocalRank(0, r, G) for r in range(G)]
+    fmt = mode.get("matrix_format", "csr")
+    out, caps = _build(ranks, shards, False, **mode)  # host-planned
+    assert all(rc == _capi.G2N_OK for rc, _ in out)
+    _check(*_assemble(ranks, out, fmt), text, mode)
+    for r, (_, res) in zip(ranks, out):
+        r.remember(res, *caps)
+    out, _ = _build(ranks, shards, True, **mode)  # speculative: same kernels, sizes read on the device
+    assert all(rc == _capi.G2N_OK for rc, _ in out), [hex(int(res.bad)) for _, res in out]
+    assert all(r.h.status().speculative == 1 for r in ranks)
+    _check(*_assemble(ranks, out, fmt), text, mode)
+
+
+def test_capacity_miss_repeats_everywhere():
+    """A speculative build whose input outgrew the remembered plan ends with the same verdict on every
+    rank (G2N_ERR_RETRY), and the host-planned build that follows is right."""
+    from gfa2network_b200 import _capi
+    from gfa2network_b200 import dist as D
+    from gfa2network_b200.synth import synth_gfa
+
+    G = 3
+    small = synth_gfa(4_000, 12_000, seed=5, kind=1)
+    big = synth_gfa(20_000, 60_000, seed=6, kind=1, interleave=512)
+    ranks = [D.LocalRank(0, r, G) for r in range(G)]
+    out, caps = _build(ranks, _shards(small, G), False)
+    assert all(rc == _capi.G2N_OK for rc, _ in out)
+    for r, (_, res) in zip(ranks, out):
+        r.remember(res, *caps)
+    out, _ = _build(ranks, _shards(big, G), True)
+    assert all(rc == _capi.G2N_ERR_RETRY for rc, _ in out)
+    assert len({int(res.bad) for _, res in out}) == 1 and int(out[0][1].bad) != 0
+    out, caps = _build(ranks, _shards(big, G), False)
+    assert all(rc == _capi.G2N_OK for rc, _ in out)
+    _check(*_assemble(ranks, out, "csr"), big, {})
+    # only ONE shard changes: the others still fit their remembered sizes, the verdict is shared all the same
+    for r, (_, res) in zip(ranks, out):
+        r.remember(res, *caps)
+    import torch
+
+    extra = np.frombuffer(b"".join(b"S\textra%d\t*\n" % i for i in range(30_000)), dtype=np.uint8)
+    grown = np.concatenate([big, extra])
+    sh = _shards(big, G)
+    sh[G - 1] = torch.from_numpy(np.concatenate([sh[G - 1].cpu().numpy(), extra])).cuda()
+    out, _ = _build(ranks, sh, True)
+    assert all(rc == _capi.G2N_ERR_RETRY for rc, _ in out)
+    out, _ = _build(ranks, sh, False)
+    assert all(rc == _capi.G2N_OK for rc, _ in out)
+    _check(*_assemble(ranks, out, "csr"), grown, {})
+
+
+def test_key_segment_overflow_is_a_retry():
+    from gfa2network_b200 import _capi
+    from gfa2network_b200 import dist as D
+    from gfa2network_b200.synth import synth_gfa
+
+    G = 2
+    text = synth_gfa(20_000, 40_000, seed=3, kind=1)
+    ranks = [D.LocalRank(0, r, G) for r in range(G)]
+    out, _ = _build(ranks, _shards(text, G), False, caps=(1024, 200_000))  # 1024 keys per segment cannot hold ~5000
+    assert all(rc == _capi.G2N_ERR_RETRY for rc, _ in out)
+    assert all(int(res.bad) & 2 for _, res in out)  # DXB_KEYS, known to every rank
+    out, _ = _build(ranks, _shards(text, G), False)
+    assert all(rc == _capi.G2N_OK for rc, _ in out)
+    _check(*_assemble(ranks, out, "csr"), text, {})
+
+
+def test_errors_and_warnings_are_agreed():
+    import torch
+
+    from gfa2network_b200 import dist as D
+
+    G = 2
+    ranks = [D.LocalRank(0, r, G) for r in range(G)]
+
+    def probe(parts):
+        for r, p in zip(ranks, parts):
+            r.set_input(torch.from_numpy(np.frombuffer(p, dtype=np.uint8).copy()).cuda())
+        return [r.probe() for r in ranks]
+
+    # the malformed record sits in the second shard, the unsupported record before it in the first
+    infos = probe([b"S\ta\t*\nW\tz\n", b"S\tb\t*\nL\ta\t+\n"])
+    with pytest.warns(RuntimeWarning, match="Skipping unsupported record: W"):
+        with pytest.raises(ValueError, match="Malformed L record"):
+            D.raise_agreed(infos)
+    # an unsupported record AFTER the error line is never reported (SURVEY Q11)
+    infos = probe([b"S\ta\t*\nP\tonly\n", b"#\tcomment\nS\tb\t*\n"])
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        with pytest.raises(ValueError, match="Malformed P record"):
+            D.raise_agreed(infos)
+    infos = probe([b"S\ta\t*\n", b"S\tthis_name_is_longer_than_15_bytes\t*\n"])
+    with pytest.raises(NotImplementedError):
+        D.raise_agreed(infos)
+
+
+def test_dist_refuses_weights():
+    import ctypes as C
+
     import torch
 
     from gfa2network_b200 import _capi
     from gfa2network_b200 import dist as D
 
     r = D.LocalRank(0, 0, 1)
-    long_text = torch.from_numpy(np.frombuffer(b"S\tthis_name_is_longer_than_15_bytes\t*\n", dtype=np.uint8).copy()).cuda()
-    with pytest.raises(NotImplementedError):
-        r.scan(long_text)
+    t = torch.from_numpy(np.frombuffer(b"S\ta\t*\n", dtype=np.uint8).copy()).cuda()
     params = _capi.Params(1, 0, 0, 0, 0, 0, 1, 1, b"RC", 2, 0)
     info = _capi.DistInfo()
-    import ctypes as C
-
-    rc = r.h.lib.g2n_dist_scan(r.h.h, C.c_void_p(long_text.data_ptr()), long_text.numel(), C.byref(params), C.byref(info))
+    rc = r.h.lib.g2n_dist_probe(r.h.h, C.c_void_p(t.data_ptr()), t.numel(), C.byref(params), C.byref(info))
     assert rc == _capi.G2N_ERR_UNSUPPORTED
+
+
+def test_empty_and_lopsided_shards():
+    """Shards without any record, shards without segments (links only) and a world larger than the node count."""
+    from gfa2network_b200 import _capi
+    from gfa2network_b200 import dist as D
+
+    import torch
+
+    parts = [b"H\tVN:Z:1.0\n", b"S\ta\t*\nS\tb\t*\nS\tc\t*\n", b"", b"L\tc\t+\ta\t-\t0M\nL\ta\t+\tb\t+\t0M\nL\td\t+\ta\t+\t0M\n"]
+    text = np.frombuffer(b"".join(parts), dtype=np.uint8)
+    G = len(parts)
+    ranks = [D.LocalRank(0, r, G) for r in range(G)]
+    shards = [torch.from_numpy(np.frombuffer(p, dtype=np.uint8).copy()).cuda() if p else torch.empty(0, dtype=torch.uint8, device="cuda") for p in parts]
+    for mode in (dict(), dict(directed=False), dict(bidirected=True)):
+        out, caps = _build(ranks, shards, False, **mode)
+        assert all(rc == _capi.G2N_OK for rc, _ in out)
+        _check(*_assemble(ranks, out, "csr"), text, mode)
