@@ -385,6 +385,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, TK_MIN_BLOCKS) k_tokenize(const
     if (lane == 0 && tile < P.tile_end && tma_ok(tile)) tma_load(S.win[0], P.text + ((u64)tile * WT_TILE - WT_PRE), WT_WIN, &S.bar[0], pol_text);
     u32 aborted = 0;
     bool pending = false;  // a window fetch for the NEXT tile is in flight
+    bool quick = false;    // this warp's previous tile held at most one record: look for a line start before building masks
     for (; tile < P.tile_end && !aborted; tile += n_warps, buf ^= 1) {
         const u64 t0 = (u64)tile * WT_TILE;
         const u64 wbase = t0 - WT_PRE;  // wraps for tile 0: only ever used as wbase + offset
@@ -421,6 +422,29 @@ __global__ void __launch_bounds__(WT_WARPS * 32, TK_MIN_BLOCKS) k_tokenize(const
                 reinterpret_cast<uint4*>(win)[piece] = v;
             }
             __syncwarp();
+        }
+        // ---- long-line regime (P / W / sequence lines of megabytes, SURVEY 8a row 9: "skipped at full bandwidth"):
+        // when this warp's previous tile held at most one record, first look for a line start at all -- a '\n' in
+        // window bytes [WT_PRE - 1, WT_PRE + WT_TILE - 1) -- and leave the tile without building any mask if there is none
+        if (quick) {
+            u32 f = 0;
+#pragma unroll
+            for (int k = 0; k < WT_TILE / 16 / 32; k++) {
+                const uint4 v = reinterpret_cast<const uint4*>(win)[WT_PRE / 16 + lane + 32 * k];
+                f |= eq_bytes(v.x, 0x0A0A0A0Au) | eq_bytes(v.y, 0x0A0A0A0Au) | eq_bytes(v.z, 0x0A0A0A0Au) | eq_bytes(v.w, 0x0A0A0A0Au);
+            }
+            // byte WT_PRE - 1 starts a line at the tile's first byte (the tile's last byte is looked at too: harmless, the
+            // full path decides)
+            if (lane == 0 && win[WT_PRE - 1] == '\n') f |= 1u;
+            if (!__any_sync(0xffffffffu, f != 0)) {
+                if (lane == 0) {
+                    TileInfo ti;
+                    ti.n_rec = 0; ti.n_edge = 0; ti.edge_alloc = 0; ti.pad = 0;
+                    P.tile_info[tile] = ti;
+                }
+                __syncwarp();
+                continue;
+            }
         }
         // ---- classify '\n' and '\t' 16 bytes at a time into the two bitmasks
 #pragma unroll
@@ -522,6 +546,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, TK_MIN_BLOCKS) k_tokenize(const
             P.tile_info[tile] = ti;
         }
         aborted = __shfl_sync(0xffffffffu, flags_l0, 0) & (CF_TABLE_FULL | CF_DEFER_FULL);
+        quick = n_rec_tile <= 1;
         // new keys of this tile: one fire-and-forget atomic per warp (the host checks the load factor)
 #pragma unroll
         for (int d = 16; d; d >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, d);
