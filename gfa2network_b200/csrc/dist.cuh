@@ -2,9 +2,9 @@
 //
 // Nothing here goes through the host or through a collective library: every exchange is a kernel that
 // WRITES STRAIGHT INTO THE PEER'S MEMORY over NVLink (peer pointers from CUDA IPC, or plain pointers when
-// several logical ranks share one device) followed by a one-warp signal kernel that publishes per-source
-// headers and an epoch flag in the peer's control block; the consuming kernel of the peer spins on those
-// flags (acquire, system scope) before it touches the data.  A whole build is queued on the stream
+// several logical ranks share one device); the last CTA of that kernel to finish publishes a per-source
+// header and an epoch flag in the peer's control block (release, system scope), and the consuming kernel
+// of the peer spins on those flags (acquire, system scope) before it touches the data.  A whole build is queued on the stream
 // without a host round trip; the host synchronises once, at the end.
 //
 //   stage 0  k_tokenize (this rank's byte range: local table, local first-appearance order)
@@ -66,7 +66,8 @@ struct DxLocal {  // zeroed at the start of every build; never written by peers
     u32 seg_off[DX_MAXW + 1];  // received entries: exclusive prefix over sources
     u32 n_keys, n_records, n_edges;  // this shard (copied from DevSizes before the slab overwrites it)
     u32 final_bad;
-    u32 pad[8];
+    u32 done[DX_NEX];  // CTAs of the producing kernel of exchange e that have finished
+    u32 pad[2];
 };
 
 struct DxLayout {  // the exchange arena of one rank (same layout on every rank)
@@ -117,23 +118,42 @@ __device__ __forceinline__ void dx_wait(const DxCtl* my, int e, const DxPeers& X
     __syncthreads();
 }
 
-// One warp: headers, then the epoch flag, into every peer's control block.
-// `aux_words`: the popcount prefix of the first-appearance bitmap -- its total is this shard's number of firsts (x3)
-__global__ void k_dx_signal(const DxPeers X, int e, DxLocal* loc, const u32* counts, u64 cap, const u32* aux_words, const DevSizes* ds)
+// Publishes this rank's header of exchange `e` and the epoch flag in every peer's control block.
+// Called by the first `world` threads of ONE CTA once all of this rank's writes of the exchange are ordered
+// before it (dx_tail_signal).  st.release.sys: the header (and, cumulatively, everything ordered before)
+// is visible to whoever acquires the flag.
+__device__ __forceinline__ void dx_publish(const DxPeers& X, int e, DxLocal* loc, const u32* counts, u64 cap, u64 aux)
 {
     const u32 d = threadIdx.x;
     if (d >= (u32)X.world) return;
     DxHdr h;
-    u64 c = counts ? counts[d] : 0u;
+    u64 c = counts ? *(const volatile u32*)&counts[d] : 0u;
     if (c > cap) c = cap;
     h.count = c;
-    h.bad = loc->bad;
-    h.aux = (aux_words && ds->ok) ? aux_words[ds->words] : 0ull;
+    h.bad = *(const volatile u32*)&loc->bad;
+    h.aux = aux;
     h.pad = 0;
     DxCtl* pc = X.ctl[d];
     pc->hdr[e][X.rank] = h;
-    __threadfence_system();
     st_release_sys_u32(&pc->sig[e][X.rank], X.epoch);
+}
+
+// End of a producing kernel (every thread of every CTA gets here): the LAST CTA to arrive signals.
+// Each CTA orders its writes into peer memory before its ticket (bar.sync + release fence at system
+// scope), the last CTA acquires the tickets before it publishes: no separate signal launch, and the
+// peers' consumers can start while this kernel's other CTAs are already gone.
+__device__ __forceinline__ void dx_tail_signal(const DxPeers& X, int e, DxLocal* loc, const u32* counts, u64 cap, u64 aux)
+{
+    __shared__ u32 s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
+        const u32 ticket = atomicAdd(&loc->done[e], 1u);
+        s_last = ticket == gridDim.x - 1;
+        if (s_last) asm volatile("fence.acq_rel.sys;" ::: "memory");
+    }
+    __syncthreads();
+    if (s_last) dx_publish(X, e, loc, counts, cap, aux);
 }
 
 // ---------------------------------------------------------------- x1: local keys -> owners
@@ -142,12 +162,9 @@ __global__ void __launch_bounds__(256) k_dx_export(const TKey* __restrict__ tkey
                                                     const u64* __restrict__ tile_base, const DevSizes* __restrict__ ds,
                                                     const DxPeers X, const DxLayout L, DxLocal* __restrict__ loc, u32* __restrict__ sent)
 {
-    if (!ds->ok) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&loc->bad, DXB_TOK);
-        return;
-    }
+    if (!ds->ok && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&loc->bad, DXB_TOK);
     const u32 lane = threadIdx.x & 31;
-    for (u32 i0 = blockIdx.x * blockDim.x; i0 < cap; i0 += gridDim.x * blockDim.x) {  // cap is a multiple of 256
+    for (u32 i0 = blockIdx.x * blockDim.x; ds->ok && i0 < cap; i0 += gridDim.x * blockDim.x) {  // cap is a multiple of 256
         const u32 i = i0 + threadIdx.x;
         const TKey k = tkeys[i];
         const bool occ = !(k.x == 0 && k.y == 0);
@@ -166,6 +183,7 @@ __global__ void __launch_bounds__(256) k_dx_export(const TKey* __restrict__ tkey
         reinterpret_cast<u32*>(a + L.off_ord)[j] = order_bit(tile_base, ~tfirst[i]);
         sent[i] = (d << 29) | pos;
     }
+    dx_tail_signal(X, 0, loc, loc->cur_keys, L.kcap, 0);
 }
 
 struct DxOwner {  // the owner's table over the keys it is responsible for
@@ -217,7 +235,7 @@ __global__ void __launch_bounds__(256) k_dx_insert(const DxPeers X, const DxLayo
 
 // ---------------------------------------------------------------- x2: owner -> sources, one byte per key
 // four keys per thread: one 32-bit store into the peer's memory
-__global__ void __launch_bounds__(256) k_dx_reply_first(const DxPeers X, const DxLayout L, const DxCtl* my, const DxOwner G)
+__global__ void __launch_bounds__(256) k_dx_reply_first(const DxPeers X, const DxLayout L, const DxCtl* my, DxLocal* __restrict__ loc, const DxOwner G)
 {
     for (u32 s = 0; s < (u32)X.world; s++) {
         const u32 n = dx_count(my, 0, s, L.kcap);
@@ -240,6 +258,7 @@ __global__ void __launch_bounds__(256) k_dx_reply_first(const DxPeers X, const D
             out[q] = word;
         }
     }
+    dx_tail_signal(X, 1, loc, nullptr, 0, 0);
 }
 
 // ---------------------------------------------------------------- x2 consumer: bitmap of this shard's global firsts
@@ -271,11 +290,12 @@ __global__ void __launch_bounds__(256) k_dx_mark(const TKey* __restrict__ tkeys,
 __global__ void __launch_bounds__(256) k_dx_send_rank(const TKey* __restrict__ tkeys, const u64* __restrict__ tfirst, u32 cap,
                                                        const u64* __restrict__ tile_base, const DevSizes* __restrict__ ds, const DxPeers X,
                                                        const DxLayout L, const u32* __restrict__ sent, const u32* __restrict__ bitmap,
-                                                       const u32* __restrict__ wprefix, u32* __restrict__ id2slot, u32* __restrict__ name_len)
+                                                       const u32* __restrict__ wprefix, u32* __restrict__ id2slot, u32* __restrict__ name_len,
+                                                       DxLocal* __restrict__ loc)
 {
-    if (!ds->ok) return;
+    const bool ok = ds->ok != 0;
     const uint8_t* first = X.arena[X.rank] + L.off_first;
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; ok && i < cap; i += gridDim.x * blockDim.x) {
         const TKey k = tkeys[i];
         if (k.x == 0 && k.y == 0) continue;
         const u32 sv = sent[i];
@@ -289,6 +309,8 @@ __global__ void __launch_bounds__(256) k_dx_send_rank(const TKey* __restrict__ t
         id2slot[r] = i;
         name_len[r] = slot_key_len(k.y);
     }
+    // the popcount prefix ends with the number of marked bits = this shard's global firsts
+    dx_tail_signal(X, 2, loc, nullptr, 0, ok ? (u64)wprefix[ds->words] : 0ull);
 }
 
 // ---------------------------------------------------------------- x4: owner -> sources, the node ID of every key
@@ -336,6 +358,7 @@ __global__ void __launch_bounds__(256) k_dx_reply_ids(const DxPeers X, const DxL
             out[j] = id;
         }
     }
+    dx_tail_signal(X, 3, loc, nullptr, 0, 0);
 }
 
 // ---------------------------------------------------------------- x4 consumer: local slot -> global node ID
@@ -375,8 +398,7 @@ __global__ void __launch_bounds__(256) k_dx_entries(u32* __restrict__ edge_slots
     __shared__ u32 s_cnt[DX_MAXW], s_base[DX_MAXW], s_go;
     if (threadIdx.x == 0) s_go = ds->ok && !loc->bad;  // one decision per CTA (another CTA may raise `bad` meanwhile)
     __syncthreads();
-    if (!s_go) return;
-    const u32 E = ds->E;
+    const u32 E = s_go ? ds->E : 0u;
     const u32 rpr = loc->rows_per;
     const u32 lane = threadIdx.x & 31;
     const u32 per_round = 256 * DXE_BATCH;
@@ -444,6 +466,7 @@ __global__ void __launch_bounds__(256) k_dx_entries(u32* __restrict__ edge_slots
             }
         }
     }
+    dx_tail_signal(X, 4, loc, loc->cur_pairs, L.pcap, 0);
 }
 
 // ---------------------------------------------------------------- x5 consumer: this rank's slab
@@ -452,7 +475,7 @@ __global__ void k_dx_slab_sizes(const DxPeers X, const DxLayout L, const DxCtl* 
                                 DevSizes* __restrict__ ds, u32 recv_cap, u32 rows_cap)
 {
     dx_wait(my, 4, X, loc);
-    if (threadIdx.x) return;
+    if (threadIdx.x == 0) {
     u32 bad = loc->bad, run = 0;
     for (int s = 0; s < X.world; s++) {
         bad |= dx_bad(my, 4, (u32)s);
@@ -468,6 +491,9 @@ __global__ void k_dx_slab_sizes(const DxPeers X, const DxLayout L, const DxCtl* 
     memset(&s, 0, sizeof(s));
     if (!bad) { s.n = loc->n_rows; s.rows = loc->n_rows; s.M = run; s.T = run; s.ok = 1; }
     *ds = s;
+    }
+    __syncthreads();  // one CTA: thread 0's status precedes the headers
+    dx_publish(X, 5, loc, nullptr, 0, 0);
 }
 
 __global__ void __launch_bounds__(256) k_pairs_count(const DxPeers X, const DxLayout L, const DxLocal* __restrict__ loc, const DevSizes* __restrict__ ds,

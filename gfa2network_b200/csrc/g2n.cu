@@ -1502,12 +1502,6 @@ int g2n_dist_probe(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2
     return G2N_OK;
 }
 
-#define DX_SIGNAL(E, COUNTS, CAP, AUX)                                                                                                   \
-    do {                                                                                                                                 \
-        KScope ks(h, "k_dx_signal");                                                                                                     \
-        k_dx_signal<<<1, 32, 0, h->stream>>>(X, (E), loc, (COUNTS), (u64)(CAP), (AUX), h->d_ds);                                         \
-    } while (0)
-
 int g2n_dist_stage(g2n_handle* h, int stage, const uint8_t* text, uint64_t nbytes, const g2n_params* p, int speculative)
 {
     if (!h || !h->dx_inited || stage < 0 || stage > 6) return G2N_ERR_INVALID;
@@ -1564,13 +1558,11 @@ int g2n_dist_stage(g2n_handle* h, int stage, const uint8_t* text, uint64_t nbyte
     switch (stage) {
     case 0: {
         { KScope ks(h, "k_dx_export"); k_dx_export<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->d_tkeys, h->d_tfirst, cap, h->tile_base.as<u64>(), h->d_ds, X, L, loc, h->dx_sent.as<u32>()); }
-        DX_SIGNAL(0, loc->cur_keys, L.kcap, nullptr);
         break;
     }
     case 1: {
         { KScope ks(h, "k_dx_insert"); k_dx_insert<<<kgrid, 256, 0, h->stream>>>(X, L, my, loc, G, h->d_cnt); }
-        { KScope ks(h, "k_dx_reply_first"); k_dx_reply_first<<<grid_for(L.kcap / 4 + 1, 256, 8), 256, 0, h->stream>>>(X, L, my, G); }
-        DX_SIGNAL(1, nullptr, 0, nullptr);
+        { KScope ks(h, "k_dx_reply_first"); k_dx_reply_first<<<grid_for(L.kcap / 4 + 1, 256, 8), 256, 0, h->stream>>>(X, L, my, loc, G); }
         break;
     }
     case 2: {
@@ -1579,13 +1571,11 @@ int g2n_dist_stage(g2n_handle* h, int stage, const uint8_t* text, uint64_t nbyte
         LoadPopc lp{h->d_bitmap};
         int rc = launch_scan<u32>(h, lp, h->wprefix.as<u32>(), nullptr, words, &h->d_ds->words, h->d_scan_words);
         if (rc) return rc;
-        { KScope ks(h, "k_dx_send_rank"); k_dx_send_rank<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->d_tkeys, h->d_tfirst, cap, h->tile_base.as<u64>(), h->d_ds, X, L, h->dx_sent.as<u32>(), h->d_bitmap, h->wprefix.as<u32>(), h->id2slot.as<u32>(), h->name_len.as<u32>()); }
-        DX_SIGNAL(2, nullptr, 0, h->wprefix.as<u32>());
+        { KScope ks(h, "k_dx_send_rank"); k_dx_send_rank<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->d_tkeys, h->d_tfirst, cap, h->tile_base.as<u64>(), h->d_ds, X, L, h->dx_sent.as<u32>(), h->d_bitmap, h->wprefix.as<u32>(), h->id2slot.as<u32>(), h->name_len.as<u32>(), loc); }
         break;
     }
     case 3: {
         { KScope ks(h, "k_dx_reply_ids"); k_dx_reply_ids<<<kgrid, 256, 0, h->stream>>>(X, L, my, loc, G); }
-        DX_SIGNAL(3, nullptr, 0, nullptr);
         break;
     }
     case 4: {
@@ -1602,7 +1592,6 @@ int g2n_dist_stage(g2n_handle* h, int stage, const uint8_t* text, uint64_t nbyte
             }
         }
         h->edges_are_ids = true;
-        DX_SIGNAL(4, loc->cur_pairs, L.pcap, nullptr);
         break;
     }
     case 5: {
@@ -1617,7 +1606,6 @@ int g2n_dist_stage(g2n_handle* h, int stage, const uint8_t* text, uint64_t nbyte
             h->dx_rows_cap = rows_cap;
             h->dx_recv_cap = recv_cap;
         }
-        DX_SIGNAL(5, nullptr, 0, nullptr);
         if (recv_cap >= 0xFFFFFFF0ull) { h->err = "more than 2^32 entries in one slab"; return G2N_ERR_UNSUPPORTED; }
         CK(h->entries.ensure((recv_cap + 1) * sizeof(u32)));
         {
