@@ -28,20 +28,31 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
+    """Several ranks of one job may get here at the same time (torchrun): one of them builds under a file
+    lock into a temporary name and renames it into place, the others wait and find it up to date."""
     if not force and not needs_build():
         return LIB
-    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    if not Path(nvcc).exists():
-        raise RuntimeError("nvcc not found: libg2n.so cannot be built (there is no CPU fallback)")
-    extra = os.environ.get("G2N_NVCC_EXTRA", "").split()
-    cmd = [nvcc, *NVCC_FLAGS, *extra, "-o", str(LIB), str(CSRC / "g2n.cu")]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
-    if verbose:
-        print(r.stderr)
+    import fcntl
+
+    with open(PKG / ".build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not needs_build():
+            return LIB
+        nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+        if not Path(nvcc).exists():
+            raise RuntimeError("nvcc not found: libg2n.so cannot be built (there is no CPU fallback)")
+        extra = os.environ.get("G2N_NVCC_EXTRA", "").split()
+        tmp = LIB.with_name(f".libg2n.{os.getpid()}.so")
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-o", str(tmp), str(CSRC / "g2n.cu")]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            tmp.unlink(missing_ok=True)
+            raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+        os.replace(tmp, LIB)
+        if verbose:
+            print(r.stderr)
     return LIB
 
 

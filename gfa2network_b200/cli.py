@@ -1,6 +1,6 @@
-"""``gfa2network convert`` surface (gfa2network/cli.py:22-135, 193-250) over the GPU path.
-Same flags, defaults, stdout/stderr strings and exit behaviour for ``convert --matrix``;
-the sub-commands that are not on the GFA->matrix path are not provided here."""
+"""``gfa2network convert`` (gfa2network/cli.py:22-135, 193-250) and ``gfa2network export --format edge-list``
+(cli.py:137-150, 264-281) over the GPU path.  Same flags, defaults, stdout/stderr strings and exit
+behaviour; the sub-commands and formats that are not on the GFA->matrix path are not provided here."""
 from __future__ import annotations
 
 import argparse
@@ -41,12 +41,25 @@ def _parser() -> argparse.ArgumentParser:
     c.add_argument("--keep-directed-bidir", action="store_true", help="Keep original directed bidirected behaviour")
     c.add_argument("--verbose", action="store_true")
     c.add_argument("-o", "--output", metavar="PATH", help="Write graph pickle to PATH")
+    e = sub.add_parser("export", help="Stream edges in simple formats")
+    e.add_argument("gfa")
+    e.add_argument("--format", default="edge-list", choices=["edge-list", "graphml", "gexf", "json"])
+    e.add_argument("--bidirected", action="store_true")
+    e.add_argument("--keep-directed-bidir", action="store_true", help="Keep original directed bidirected behaviour")
+    e.add_argument("--output", help="Output path", default="-")
     return ap
 
 
 def main(argv: list[str] | None = None) -> None:
     ap = _parser()
     args = ap.parse_args(argv)
+    if args.cmd == "export":
+        if args.format != "edge-list":  # graphml / gexf / json go through a NetworkX object graph (cli.py:282-300)
+            raise NotImplementedError(f"export --format {args.format} needs the NetworkX graph half of the reference")
+        from .export import export_edge_list
+
+        export_edge_list(args.gfa, bidirected=args.bidirected, output=args.output)
+        return
     if not args.graph and not args.matrix:
         ap.error("convert requires --graph or --matrix")  # cli.py:194-195
     print(f"Using backend: {args.backend}")  # cli.py:198

@@ -25,7 +25,8 @@
 // Per-rank work is proportional to the rank's own shard (keys are hash-partitioned, nobody holds the
 // whole dictionary).  Node names stay with the shard of their first appearance: shard s names the
 // consecutive IDs [idbase[s], idbase[s] + firsts[s]).
-// Restricted to inline (<= 15 byte) keys and unweighted builds; the host mirror refuses anything else.
+// Restricted to unweighted builds (the host mirror refuses a weight tag).  Keys longer than 15 bytes travel as
+// their 128-bit tagged hash (table.cuh: make_key, same seed on every rank); their bytes stay with the shards.
 #pragma once
 #include "rowsort.cuh"
 

@@ -70,7 +70,9 @@ struct g2n_handle {
     // device buffers (kept between builds: a warm handle allocates nothing)
     DevBuf text, defer, edge_slots, edge_w, longs, tile_info, tile_base, wprefix, slot_id, id2slot, name_len, name_off, names;
     DevBuf rowptr, cursor, entries, w_emit, biglist, ucnt, indptr, indices, data, row, col, scan_state;
-    DevBuf up_row, up_col, up_data, tsv, tsv_off;
+    DevBuf up_row, up_col, up_data, tsv, tsv_off, el_len, el_off, el_text;
+    bool el_ready = false;
+    u64 el_bytes = 0;
     bool tsv_ready = false;
     u64 tsv_bytes = 0;
     // zero-initialised state, one memset per arena and build:
@@ -105,6 +107,7 @@ struct g2n_handle {
     bool speculate = true;  // g2n_set_option("speculate", 0) turns it off
     bool spec = false;      // the current build is speculative
     bool slow_ran = false;
+    bool reseeded = false;  // the last tokenizer pass changed the hash seed of long keys (collision retry)
     u32 tk_attr = 0;     // tokenizer specialisations whose dynamic shared memory opt-in was set on this device
     u32 n_pieces = 0;    // host text of the current build: copy pieces still to be waited for (0: text is on the device)
     u64 piece_bytes = 0;
@@ -544,7 +547,7 @@ void g2n_destroy(g2n_handle* h)
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->text, &h->zearly, &h->zids, &h->zrows, &h->defer, &h->edge_slots, &h->edge_w, &h->longs, &h->tile_info, &h->tile_base, &h->wprefix,
                       &h->slot_id, &h->id2slot, &h->name_len, &h->name_off, &h->names, &h->rowptr, &h->cursor, &h->entries, &h->w_emit, &h->biglist, &h->ucnt, &h->indptr, &h->indices, &h->data, &h->row, &h->col,
-                      &h->scan_state, &h->up_row, &h->up_col, &h->up_data, &h->tsv, &h->tsv_off, &h->dx_arena, &h->dx_ctl, &h->dx_loc, &h->dx_zg, &h->dx_gslot, &h->dx_gpos, &h->dx_sent};
+                      &h->scan_state, &h->up_row, &h->up_col, &h->up_data, &h->tsv, &h->tsv_off, &h->el_len, &h->el_off, &h->el_text, &h->dx_arena, &h->dx_ctl, &h->dx_loc, &h->dx_zg, &h->dx_gslot, &h->dx_gpos, &h->dx_sent};
     if (h->dx_inited) g2n_dist_close_peers(h);
     for (DevBuf* b : bufs) b->release();
     if (h->h_loc) cudaFreeHost(h->h_loc);
@@ -694,6 +697,7 @@ static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, c
     h->have_edges = false;
     h->names_ready = false;
     h->tsv_ready = false;
+    h->el_ready = false;
     h->edges_are_ids = false;
     h->spec = spec;
     if (p->dtype < G2N_DTYPE_F64 || p->dtype > G2N_DTYPE_BOOL) { h->err = "unknown dtype"; return G2N_ERR_INVALID; }
@@ -821,6 +825,7 @@ static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, c
     if (spec) edge_cap += edge_cap / 16;
     if (const char* kc = getenv("G2N_DBG_KEYS")) keys_cap = (u64)atoll(kc);  // timing experiments: table size of a warm handle
     u64 seed = 0x51ed270b7a2d4c1full;
+    h->reseeded = false;
     Counters& hc = *h->h_cnt;
     for (u32 attempt = 0;; attempt++) {
         if (attempt > 12) { h->err = "capacity retry limit exceeded"; return G2N_ERR_INTERNAL; }
@@ -986,7 +991,7 @@ static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, c
         if (hc.flags & CF_TABLE_FULL) { keys_cap = keys_cap * 4 > hc.n_keys * 2ull ? keys_cap * 4 : hc.n_keys * 2ull; retry = true; }
         if (hc.flags & CF_EDGE_FULL) { edge_cap = (u64)hc.edge_alloc + 64; retry = true; }
         if (hc.flags & CF_LONG_FULL) { long_cap = (u64)hc.n_long * 2 + 1024; retry = true; }
-        if (!retry && hc.collision) { seed = seed * 6364136223846793005ull + 1442695040888963407ull; retry = true; }
+        if (!retry && hc.collision) { seed = seed * 6364136223846793005ull + 1442695040888963407ull; retry = true; h->reseeded = true; }
         if (!retry) break;
     }
     SizeCaps caps;
@@ -1291,6 +1296,61 @@ int g2n_fetch_nodes_tsv(g2n_handle* h, uint8_t* out)
     return G2N_OK;
 }
 
+// "<u>\t<v>\n" per edge record in file order (cli.py:267-281), made on the device from the last build
+static int build_edge_list(g2n_handle* h)
+{
+    if (h->el_ready) return G2N_OK;
+    if (h->slab_mode || !h->have_edges) { h->err = "the edge list needs a single-GPU build"; return G2N_ERR_INVALID; }
+    const u64 E = h->n_edges;
+    CK(h->el_len.ensure((E + 2) * sizeof(u32)));
+    CK(h->el_off.ensure((E + 2) * sizeof(u64)));
+    h->el_bytes = 0;
+    if (E > 0) {
+        h->spec = false;
+        EmitParams EP = emit_params(h);
+        EP.ids_ready = 1;  // hand the stored words through untouched; NameSrc maps IDs back to slots if need be
+        EP.write_ids = 0;
+        NameSrc N;
+        N.tkeys = h->d_tkeys; N.trep = h->d_trep; N.longs = h->longs.as<LongDesc>(); N.text = h->d_text;
+        N.id2slot = h->edges_are_ids ? h->id2slot.as<u32>() : nullptr;
+        const u32 egrid = grid_for((u64)h->n_tiles * 32, 256);
+        { KScope ks(h, "k_edge_line_len"); k_edge_line_len<<<egrid, 256, 0, h->stream>>>(EP, N, h->el_len.as<u32>()); }
+        CK(cudaGetLastError());
+        LoadArray<u32> ll{h->el_len.as<u32>()};
+        int rc = launch_scan<u64>(h, ll, h->el_off.as<u64>(), nullptr, E, nullptr, nullptr);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(&h->h_tail[5], h->el_off.as<u64>() + E, sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        h->el_bytes = h->h_tail[5];
+        CK(h->el_text.ensure(h->el_bytes + 16));
+        { KScope ks(h, "k_edge_line_write"); k_edge_line_write<<<egrid, 256, 0, h->stream>>>(EP, N, h->el_off.as<u64>(), h->el_text.as<uint8_t>()); }
+        CK(cudaGetLastError());
+    }
+    h->el_ready = true;
+    return G2N_OK;
+}
+
+int g2n_edge_list_bytes(g2n_handle* h, uint64_t* out)
+{
+    if (!h || !out || !h->built) return G2N_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    int rc = build_edge_list(h);
+    if (rc) return rc;
+    *out = h->el_bytes;
+    return G2N_OK;
+}
+
+int g2n_fetch_edge_list(g2n_handle* h, uint8_t* out)
+{
+    if (!h || !h->built) return G2N_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    int rc = build_edge_list(h);
+    if (rc) return rc;
+    if (h->el_bytes) CK(cudaMemcpyAsync(out, h->el_text.p, h->el_bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return G2N_OK;
+}
+
 int g2n_coo_to_compressed(g2n_handle* h, const int32_t* row, const int32_t* col, const void* data, uint64_t nnz_in, uint64_t n,
                           int32_t dtype, int32_t want_format, int32_t* indptr, int32_t* indices, void* data_out, uint64_t* nnz_out)
 {
@@ -1490,7 +1550,9 @@ int g2n_dist_probe(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2
     if (p && p->weight_tag && p->weight_tag_len > 0) { h->err = "multi-GPU builds are unweighted in this version"; return G2N_ERR_UNSUPPORTED; }
     int rc = tokenize_phase(h, text, nbytes, p, false, false);
     if (rc) return rc;
-    if (h->n_long) { h->err = "multi-GPU builds need node names of <= 15 bytes (13 with --bidirected) in this version"; return G2N_ERR_UNSUPPORTED; }
+    // names beyond the 15-byte inline key travel as their 128-bit tagged hash (table.cuh: make_key); every rank must
+    // hash with the same seed, so a shard that had to re-seed (a collision among ITS long names) cannot take part
+    if (h->reseeded) { h->err = "multi-GPU build: hash collision among long node names (re-seeded table)"; return G2N_ERR_UNSUPPORTED; }
     out->n_keys = h->n_nodes;
     out->n_tiles = h->n_tiles;
     out->n_records = h->n_records;

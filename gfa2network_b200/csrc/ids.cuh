@@ -267,6 +267,57 @@ __device__ __forceinline__ void record_triplet(const u32 (&id)[4], int k, u32& r
     if (k & 1) { r = b; c = a; } else { r = a; c = b; }
 }
 
+// ---------------------------------------------------------------- edge list as text (cli.py:267-281)
+// `export --format edge-list`: one line "<u>\t<v>\n" per L / E / C record in file order, where u and v are the
+// record's endpoint keys -- exactly the node keys of a build with the same --bidirected flag (u:of, v:ot).
+// Two passes over the edge records (line lengths, exclusive scan, bytes), same emission order as the COO.
+struct NameSrc {
+    const TKey* tkeys;
+    const u32* trep;
+    const LongDesc* longs;
+    const uint8_t* text;
+    const u32* id2slot;  // non-NULL: edge_slots already hold node IDs
+    __device__ __forceinline__ u32 slot_of(u32 v) const { return id2slot ? id2slot[v] : v; }
+    __device__ __forceinline__ u32 len(u32 slot) const
+    {
+        const TKey k = tkeys[slot];
+        if ((u32)(k.y >> 56) != 0xFF) return slot_key_len(k.y);
+        const LongDesc d = longs[trep[slot] - 1];
+        return d.base_len + (d.has_ori ? 1 + d.ori_len : 0);
+    }
+    __device__ __forceinline__ u32 copy(u32 slot, uint8_t* dst) const
+    {
+        const TKey k = tkeys[slot];
+        if ((u32)(k.y >> 56) != 0xFF) {
+            const u32 L = slot_key_len(k.y);
+            for (u32 j = 0; j < L; j++) dst[j] = (uint8_t)((j < 8 ? k.x >> (8 * j) : k.y >> (8 * (j - 8))) & 0xFF);
+            return L;
+        }
+        const LongDesc d = longs[trep[slot] - 1];
+        const u32 L = d.base_len + (d.has_ori ? 1 + d.ori_len : 0);
+        for (u32 j = 0; j < L; j++) dst[j] = long_byte(text, d, j);
+        return L;
+    }
+};
+
+__global__ void __launch_bounds__(256) k_edge_line_len(const EmitParams E, const NameSrc N, u32* __restrict__ line_len)
+{
+    for_each_edge(E, [&](u32, u32 t0, const u32 (&id)[4]) {
+        line_len[t0 / (u32)E.tpe] = N.len(N.slot_of(id[0])) + N.len(N.slot_of(id[1])) + 2u;
+    });
+}
+
+__global__ void __launch_bounds__(256) k_edge_line_write(const EmitParams E, const NameSrc N, const u64* __restrict__ line_off, uint8_t* __restrict__ out)
+{
+    for_each_edge(E, [&](u32, u32 t0, const u32 (&id)[4]) {
+        uint8_t* dst = out + line_off[t0 / (u32)E.tpe];
+        dst += N.copy(N.slot_of(id[0]), dst);
+        *dst++ = '\t';
+        dst += N.copy(N.slot_of(id[1]), dst);
+        *dst = '\n';
+    });
+}
+
 // raw COO in emission order: row, col (int32) and data (dtype)
 template <typename T>
 __global__ void __launch_bounds__(256) k_emit_coo(const EmitParams E, int32_t* __restrict__ row, int32_t* __restrict__ col, T* __restrict__ data)

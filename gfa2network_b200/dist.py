@@ -17,7 +17,7 @@ used only by host-planned builds (the first build of a shape, or after a capacit
 queues its stages without any host round trip and synchronises once, at the end.
 `LocalRank` wraps one rank's handle, `DistBuilder` adds the bootstrap; tests drive several `LocalRank`s
 on one GPU (logical shards: same kernels, peers are plain device pointers).
-Restrictions of this version: unweighted builds, node names <= 15 bytes, <= 8 ranks."""
+Restrictions of this version: unweighted builds, <= 8 ranks."""
 from __future__ import annotations
 
 import ctypes as C

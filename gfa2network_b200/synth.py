@@ -22,9 +22,18 @@ class _SP(C.Structure):
 
 
 def build(force: bool = False) -> Path:
-    if force or not LIB.exists() or LIB.stat().st_mtime < SRC.stat().st_mtime:
-        cc = shutil.which("gcc") or "cc"
-        subprocess.run([cc, "-O2", "-fPIC", "-shared", "-std=c11", "-o", str(LIB), str(SRC)], check=True)
+    stale = lambda: not LIB.exists() or LIB.stat().st_mtime < SRC.stat().st_mtime  # noqa: E731
+    if force or stale():
+        import fcntl
+        import os
+
+        with open(PKG / ".build.lock", "w") as lock:  # several ranks of one job may get here together
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            if force or stale():
+                cc = shutil.which("gcc") or "cc"
+                tmp = LIB.with_name(f".libg2nsynth.{os.getpid()}.so")
+                subprocess.run([cc, "-O2", "-fPIC", "-shared", "-std=c11", "-o", str(tmp), str(SRC)], check=True)
+                os.replace(tmp, LIB)
     return LIB
 
 

@@ -166,6 +166,12 @@ int g2n_fetch_names(g2n_handle *h, uint8_t *names, uint64_t *offsets);
 int g2n_nodes_tsv_bytes(g2n_handle *h, uint64_t *out);
 int g2n_fetch_nodes_tsv(g2n_handle *h, uint8_t *out);
 
+/* `export --format edge-list` (cli.py:267-281): "<from>\t<to>\n" per L / E / C record in file order, produced on
+ * the device from the last single-GPU build.  The endpoints are that build's node keys, so build with the same
+ * `bidirected` flag as the export (from:orientation / to:orientation) and without strip_orientation. */
+int g2n_edge_list_bytes(g2n_handle *h, uint64_t *out);
+int g2n_fetch_edge_list(g2n_handle *h, uint8_t *out);
+
 /* Device pointers of the resident result (for device-side consumers / benchmarks). */
 int g2n_device_result(g2n_handle *h, void **a0, void **a1, void **data);
 
@@ -223,8 +229,9 @@ int g2n_coo_to_compressed(g2n_handle *h, const int32_t *row, const int32_t *col,
  *                        0: the tokenizer results of g2n_dist_probe are used
  *   g2n_dist_finish      the one host round trip: G2N_OK, or G2N_ERR_RETRY on every rank
  * Ranks that share a process (tests: several logical ranks on one GPU) must queue stage k on every rank
- * before stage k+1 on any.  Restrictions of this version: unweighted builds, node names of <= 15 bytes,
- * <= 8 ranks. */
+ * before stage k+1 on any.  Restrictions of this version: unweighted builds, <= 8 ranks.  Node names longer than
+ * the 15-byte inline key are exchanged as their 128-bit tagged hash (equality of two DIFFERENT long names on
+ * different ranks is decided by that hash alone; inside a shard the bytes are compared as on one GPU). */
 typedef struct g2n_dist_info {
     uint64_t n_keys;         /* distinct node keys in this shard */
     uint64_t n_tiles;

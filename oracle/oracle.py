@@ -185,3 +185,42 @@ def oracle_convert_format(A, fmt: str):
     if fmt == "coo":
         return A
     return A.asformat(fmt)
+
+
+def oracle_edge_list(text, *, bidirected=False):
+    """``export --format edge-list`` (cli.py:264-281), CPU oracle: (bytes written, exception or None, warnings).
+
+    The endpoint strings the reference writes (``from_segment[:orientation]``, ``to_segment[:orientation]``) are
+    the node keys of the matrix builder in its one-triplet-per-record mode (builders.py:211-212, 222-226), so
+    the restated tokenizer/builder is reused: row/col of the k-th triplet name the k-th line.  On a malformed
+    record the reference has already written every earlier line (the loop of cli.py:269-279 raises inside
+    ``GFAParser``): those bytes are the edge list of the text in front of the offending line."""
+    buf = _as_u8(text)
+    res = oracle_triplets(buf, directed=True, bidirected=bidirected, keep_directed_bidir=True)
+    warns = []
+    if res["unknown_byte"] >= 0:
+        warns.append("Skipping unsupported record: " + bytes([res["unknown_byte"]]).decode())
+    exc = None
+    if res["err_kind"]:
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                _raise_for(res, buf)
+        except Exception as e:  # noqa: BLE001
+            exc = e
+        res = oracle_triplets(buf[: res["err_offset"]], directed=True, bidirected=bidirected, keep_directed_bidir=True)
+        assert res["err_kind"] == 0
+    off = res["name_off"]
+    nb = res["name_bytes"].tobytes()
+    names = [nb[off[i]:off[i + 1]] for i in range(res["n_nodes"])]
+    lines = []
+    for r, c in zip(res["rows"].tolist(), res["cols"].tolist()):
+        u, v = names[r], names[c]
+        if exc is None:
+            try:
+                u.decode(), v.decode()  # cli.py:278
+            except UnicodeDecodeError as e:
+                exc = e
+                break
+        lines.append(u + b"\t" + v + b"\n")
+    return b"".join(lines), exc, warns

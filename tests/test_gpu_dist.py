@@ -184,9 +184,6 @@ def test_errors_and_warnings_are_agreed():
         warnings.simplefilter("error")
         with pytest.raises(ValueError, match="Malformed P record"):
             D.raise_agreed(infos)
-    infos = probe([b"S\ta\t*\n", b"S\tthis_name_is_longer_than_15_bytes\t*\n"])
-    with pytest.raises(NotImplementedError):
-        D.raise_agreed(infos)
 
 
 def test_dist_refuses_weights():
@@ -219,5 +216,34 @@ def test_empty_and_lopsided_shards():
     shards = [torch.from_numpy(np.frombuffer(p, dtype=np.uint8).copy()).cuda() if p else torch.empty(0, dtype=torch.uint8, device="cuda") for p in parts]
     for mode in (dict(), dict(directed=False), dict(bidirected=True)):
         out, caps = _build(ranks, shards, False, **mode)
+        assert all(rc == _capi.G2N_OK for rc, _ in out)
+        _check(*_assemble(ranks, out, "csr"), text, mode)
+
+
+@pytest.mark.parametrize("mode", [dict(), dict(bidirected=True), dict(directed=False)], ids=str)
+def test_long_names_across_shards(mode):
+    """Names beyond the 15-byte inline key (hashed keys, bytes kept by the shard that saw them first),
+    mentioned from several shards, next to short ones."""
+    from gfa2network_b200 import _capi
+    from gfa2network_b200 import dist as D
+
+    rng = np.random.default_rng(4)
+    names = [b"s%d" % i for i in range(300)] + [b"chromosome_segment_with_a_long_name_%06d" % i for i in range(300)] + [b"exactly15bytes_%d" % (i % 10) for i in range(10)] + [b"sixteen_bytes_ab%d" % (i % 10) for i in range(10)]
+    lines = [b"H\tVN:Z:1.0"]
+    for k in rng.permutation(len(names))[:400]:
+        lines.append(b"S\t" + names[k] + b"\t*")
+    for _ in range(3000):
+        u, v = rng.integers(0, len(names), 2)
+        lines.append(b"L\t" + names[u] + b"\t" + b"+-"[rng.integers(0, 2):][:1] + b"\t" + names[v] + b"\t" + b"+-"[rng.integers(0, 2):][:1] + b"\t0M")
+    text = np.frombuffer(b"\n".join(lines) + b"\n", dtype=np.uint8)
+    for G in (2, 5):
+        ranks = [D.LocalRank(0, r, G) for r in range(G)]
+        shards = _shards(text, G)
+        out, caps = _build(ranks, shards, False, **mode)
+        assert all(rc == _capi.G2N_OK for rc, _ in out)
+        _check(*_assemble(ranks, out, "csr"), text, mode)
+        for r, (_, res) in zip(ranks, out):
+            r.remember(res, *caps)
+        out, _ = _build(ranks, shards, True, **mode)
         assert all(rc == _capi.G2N_OK for rc, _ in out)
         _check(*_assemble(ranks, out, "csr"), text, mode)
