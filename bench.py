@@ -33,7 +33,7 @@ sys.path.insert(0, str(ROOT))
 HBM_FALLBACK_GBS = 6650.0  # B200_PROFILING.md fallback, used only if MEASURED_PEAKS.json is absent
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
 # (profiles/*.md name the capture each figure comes from); null where no capture exists yet
-TRAFFIC = {("C2", "k_tokenize"): 143_073_792}  # profiles/r1_ncu_full.md (dram read 129.0 MB + write 14.1 MB per launch)
+TRAFFIC = {("C2", "k_tokenize"): 143_427_072}  # profiles/r1_ncu_full.md (dram read 129.15 MB + write 14.28 MB per launch)
 
 
 def peaks():
