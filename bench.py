@@ -208,8 +208,6 @@ def run_ours(args):
     if world > 1:
         from gfa2network_b200.dist import DistBuilder
 
-        if mode.get("weight_tag"):
-            raise SystemExit("multi-GPU bench: weighted configurations are not supported yet")
         builder = DistBuilder(local)
         h = builder.local.h
     else:
@@ -222,7 +220,7 @@ def run_ours(args):
                           int(mode.get("asymmetric", False)), 0, _capi.DTYPES["float64"], want, 1, wtb, len(wtb) if wtb else 0, 0)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    dmode = {k: v for k, v in mode.items() if k != "weight_tag"}
+    dmode = dict(mode)
     state = {}
 
     def step():

@@ -17,6 +17,7 @@
 //   stage 3  k_dx_reply_ids  owner -> every source: ID = (firsts of lower shards) + rank               [x4]
 //   stage 4  k_dx_localmap   local slot -> global node ID
 //            k_dx_entries    row entries --> owner(row) = row / ceil(n / world)                         [x5]
+//            (with a weight tag: k_dxw_count / scan / k_dxw_scatter, entries in emission order + weight)
 //   stage 5  k_dx_slab_sizes, k_pairs_count / scan / k_pairs_scatter + the single-GPU row kernels:
 //            duplicate sum / max(S, S^T) -> this rank's CSR slab (builders.py:279-283, utils.py:55)
 //            status word to every rank                                                                  [x6]
@@ -25,7 +26,7 @@
 // Per-rank work is proportional to the rank's own shard (keys are hash-partitioned, nobody holds the
 // whole dictionary).  Node names stay with the shard of their first appearance: shard s names the
 // consecutive IDs [idbase[s], idbase[s] + firsts[s]).
-// Restricted to unweighted builds (the host mirror refuses a weight tag).  Keys longer than 15 bytes travel as
+// Keys longer than 15 bytes travel as
 // their 128-bit tagged hash (table.cuh: make_key, same seed on every rank); their bytes stay with the shards.
 #pragma once
 #include "rowsort.cuh"
@@ -74,6 +75,7 @@ struct DxLocal {  // zeroed at the start of every build; never written by peers
 struct DxLayout {  // the exchange arena of one rank (same layout on every rank)
     u64 kcap, pcap;  // elements per (source, destination) segment
     u64 off_key, off_ord, off_first, off_rank, off_id, off_pair, bytes;
+    u64 pair_bytes;  // 8 (DistPair) | 16 (DistPairW, weighted builds)
 };
 
 struct DxPeers {
@@ -83,9 +85,14 @@ struct DxPeers {
     u32 epoch;
 };
 
-struct DistPair {  // multi-GPU builds are unweighted: no emission index travels (rowsort.cuh: Ent32)
+struct DistPair {  // unweighted builds: no emission index travels (rowsort.cuh: Ent32)
     u32 entry;  // minor << 1 | dir
     u32 major;
+};
+struct DistPairW {  // weighted builds: the POSITION in the (source, owner) segment is the emission order
+    u32 entry;  // minor << 1 | dir
+    u32 major;
+    double w;
 };
 
 __device__ __forceinline__ u32 ld_acquire_sys_u32(const u32* p)
@@ -528,6 +535,137 @@ __global__ void __launch_bounds__(256) k_pairs_scatter(const DxPeers X, const Dx
             const DistPair p = pairs[i];
             const u32 r = p.major - row0;
             if (r < n_rows) entries[atomicAdd(&cursor[r], 1u)] = p.entry;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- weighted builds: x5 in emission order
+// Duplicate weights are summed in emission order (SciPy's order for rows of <= 16 stored entries, SURVEY 8a
+// row 13), so the order of the entries inside a (source, owner) segment must be the file order -- the
+// receiver then numbers them (segments in rank order = file order) and uses that number as the emission
+// index of the single-GPU row kernels.  Two passes, one warp per tile, no atomics on positions:
+//   k_dxw_count    entries per (tile, owner)            -> exclusive scan over [owner][tile]
+//   k_dxw_scatter  position = scan value + rank inside the tile (records in order, entries of a record in
+//                  the order of builders.py:222-234), written straight into the owner's segment
+// entry counts of one lane's record per owner: 8 x 16-bit fields in two 64-bit words
+__device__ __forceinline__ void dxw_add(u64& lo, u64& hi, u32 d) { if (d < 4) lo += 1ull << (16 * d); else hi += 1ull << (16 * (d - 4)); }
+__device__ __forceinline__ u32 dxw_get(u64 lo, u64 hi, u32 d) { return (u32)((d < 4 ? lo >> (16 * d) : hi >> (16 * (d - 4))) & 0xFFFFu); }
+
+template <bool WRITE>
+__device__ __forceinline__ void dxw_tiles(const EmitParams& E, int sym, int csc, const DxPeers& X, const DxLayout& L, const DxLocal* loc,
+                                          u32* __restrict__ tile_cnt, const u32* __restrict__ tile_off, u32* bad)
+{
+    const u32 lane = threadIdx.x & 31;
+    const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const u32 rpr = loc->rows_per, W = (u32)X.world, nt = E.n_tiles;
+    for (u32 tile = warp; tile < nt; tile += n_warps) {
+        const TileInfo ti = E.tile_info[tile];
+        u64 run_lo = 0, run_hi = 0;  // entries of this tile per owner so far (same in every lane)
+        for (u32 j0 = 0; j0 < ti.n_edge; j0 += 32) {  // uniform trip count
+            const u32 j = j0 + lane;
+            const bool valid = j < ti.n_edge;
+            u32 id[4] = {0, 0, 0, 0};
+            double w = 1.0;
+            if (valid) {
+                const u32 stored = ti.edge_alloc + j;
+                const u32* sl = E.edge_slots + (u64)stored * E.slots_per_edge;
+                id[0] = sl[0]; id[1] = sl[1];
+                if (E.slots_per_edge == 4) { id[2] = sl[2]; id[3] = sl[3]; }
+                if (!E.ids_ready) {  // table slots -> node IDs
+                    id[0] = E.slot_id[id[0]]; id[1] = E.slot_id[id[1]];
+                    if (E.slots_per_edge == 4) { id[2] = E.slot_id[id[2]]; id[3] = E.slot_id[id[3]]; }
+                }
+                if (WRITE && E.edge_w) w = E.edge_w[stored];
+            }
+            // my record's entries per owner
+            u64 c_lo = 0, c_hi = 0;
+            if (valid) record_entries(id, E.tpe, 0u, sym, csc, [&](u32 major, u32, u32, u32) { dxw_add(c_lo, c_hi, min(major / rpr, W - 1)); });
+            const u64 i_lo = warp_incl_scan64(c_lo), i_hi = warp_incl_scan64(c_hi);  // 16-bit fields: <= 32 x 8 entries
+            if (WRITE && valid) {
+                u64 m_lo = run_lo + i_lo - c_lo, m_hi = run_hi + i_hi - c_hi;  // entries before mine, per owner
+                record_entries(id, E.tpe, 0u, sym, csc, [&](u32 major, u32 minor, u32 dir, u32) {
+                    const u32 d = min(major / rpr, W - 1);
+                    const u32 pos = tile_off[(u64)d * nt + tile] - tile_off[(u64)d * nt] + dxw_get(m_lo, m_hi, d);
+                    dxw_add(m_lo, m_hi, d);
+                    if (pos < L.pcap) {
+                        DistPairW p;
+                        p.entry = Ent32::make(minor, dir, 0u);
+                        p.major = major;
+                        p.w = w;
+                        reinterpret_cast<DistPairW*>(X.arena[d] + L.off_pair)[(u64)X.rank * L.pcap + pos] = p;
+                    } else {
+                        atomicOr(bad, DXB_PAIRS);
+                    }
+                });
+            }
+            run_lo += __shfl_sync(0xffffffffu, i_lo, 31);
+            run_hi += __shfl_sync(0xffffffffu, i_hi, 31);
+        }
+        if (!WRITE && lane < W) tile_cnt[(u64)lane * nt + tile] = dxw_get(run_lo, run_hi, lane);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_dxw_count(const EmitParams E, int sym, int csc, const DxPeers X, const DxLayout L, DxLocal* __restrict__ loc,
+                                                    u32* __restrict__ tile_cnt)
+{
+    __shared__ u32 s_go;
+    if (threadIdx.x == 0) s_go = E.ds->ok && !loc->bad;
+    __syncthreads();
+    if (s_go) dxw_tiles<false>(E, sym, csc, X, L, loc, tile_cnt, nullptr, &loc->bad);
+    else {
+        // the scan that follows must see defined counts
+        for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < (u64)X.world * E.n_tiles; i += (u64)gridDim.x * blockDim.x) tile_cnt[i] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_dxw_scatter(const EmitParams E, int sym, int csc, const DxPeers X, const DxLayout L, DxLocal* __restrict__ loc,
+                                                      const u32* __restrict__ tile_off)
+{
+    __shared__ u32 s_go;
+    if (threadIdx.x == 0) s_go = E.ds->ok && !loc->bad;
+    __syncthreads();
+    if (s_go) {
+        dxw_tiles<true>(E, sym, csc, X, L, loc, nullptr, tile_off, &loc->bad);
+        if (blockIdx.x == 0 && threadIdx.x < (u32)X.world) {  // entries per owner: the header's count
+            const u64 nt = E.n_tiles, d = threadIdx.x;
+            loc->cur_pairs[d] = tile_off[(d + 1) * nt] - tile_off[d * nt];
+        }
+    }
+    dx_tail_signal(X, 4, loc, loc->cur_pairs, L.pcap, 0);
+}
+
+// receiver: row histogram, then entries numbered in arrival = emission order, weights laid out by that number
+__global__ void __launch_bounds__(256) k_pairsw_count(const DxPeers X, const DxLayout L, const DxLocal* __restrict__ loc, const DevSizes* __restrict__ ds,
+                                                       u32* __restrict__ cnt, u32* __restrict__ bad_out)
+{
+    if (!ds->ok) return;
+    const u32 row0 = loc->row0, n_rows = loc->n_rows;
+    const DistPairW* base = reinterpret_cast<const DistPairW*>(X.arena[X.rank] + L.off_pair);
+    for (u32 s = 0; s < (u32)X.world; s++) {
+        const u32 n = loc->seg_off[s + 1] - loc->seg_off[s];
+        const DistPairW* pairs = base + (u64)s * L.pcap;
+        for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const u32 r = pairs[i].major - row0;
+            if (r < n_rows) atomicAdd(&cnt[r], 1u);
+            else atomicOr(bad_out, DXB_RANGE);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_pairsw_scatter(const DxPeers X, const DxLayout L, const DxLocal* __restrict__ loc, const DevSizes* __restrict__ ds,
+                                                         u32* __restrict__ cursor, u64* __restrict__ entries, double* __restrict__ w_emit)
+{
+    if (!ds->ok) return;
+    const u32 row0 = loc->row0, n_rows = loc->n_rows;
+    const DistPairW* base = reinterpret_cast<const DistPairW*>(X.arena[X.rank] + L.off_pair);
+    for (u32 s = 0; s < (u32)X.world; s++) {
+        const u32 off = loc->seg_off[s], n = loc->seg_off[s + 1] - off;
+        const DistPairW* pairs = base + (u64)s * L.pcap;
+        for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const DistPairW p = pairs[i];
+            const u32 r = p.major - row0;
+            w_emit[off + i] = p.w;
+            if (r < n_rows) entries[atomicAdd(&cursor[r], 1u)] = Ent64::make(Ent32::minor(p.entry), Ent32::dir(p.entry), off + i);
         }
     }
 }

@@ -136,7 +136,7 @@ struct g2n_handle {
     bool dx_inited = false, dx_probed = false, dx_spec = false;
     DxPeers dxp;   // rank, world, epoch, peer arenas / control blocks
     DxLayout dxl;  // layout of every rank's exchange arena
-    DevBuf dx_arena, dx_ctl, dx_loc, dx_zg, dx_gslot, dx_gpos, dx_sent;
+    DevBuf dx_arena, dx_ctl, dx_loc, dx_zg, dx_gslot, dx_gpos, dx_sent, dx_tcnt, dx_toff;
     DxLocal* h_loc = nullptr;  // pinned copy of the build's local status
     bool dx_peer_open[DX_MAXW] = {false, false, false, false, false, false, false, false};
     u32 dx_gcap = 0;
@@ -547,7 +547,7 @@ void g2n_destroy(g2n_handle* h)
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->text, &h->zearly, &h->zids, &h->zrows, &h->defer, &h->edge_slots, &h->edge_w, &h->longs, &h->tile_info, &h->tile_base, &h->wprefix,
                       &h->slot_id, &h->id2slot, &h->name_len, &h->name_off, &h->names, &h->rowptr, &h->cursor, &h->entries, &h->w_emit, &h->biglist, &h->ucnt, &h->indptr, &h->indices, &h->data, &h->row, &h->col,
-                      &h->scan_state, &h->up_row, &h->up_col, &h->up_data, &h->tsv, &h->tsv_off, &h->el_len, &h->el_off, &h->el_text, &h->dx_arena, &h->dx_ctl, &h->dx_loc, &h->dx_zg, &h->dx_gslot, &h->dx_gpos, &h->dx_sent};
+                      &h->scan_state, &h->up_row, &h->up_col, &h->up_data, &h->tsv, &h->tsv_off, &h->el_len, &h->el_off, &h->el_text, &h->dx_arena, &h->dx_ctl, &h->dx_loc, &h->dx_zg, &h->dx_gslot, &h->dx_gpos, &h->dx_sent, &h->dx_tcnt, &h->dx_toff};
     if (h->dx_inited) g2n_dist_close_peers(h);
     for (DevBuf* b : bufs) b->release();
     if (h->h_loc) cudaFreeHost(h->h_loc);
@@ -1413,17 +1413,18 @@ int g2n_coo_to_compressed(g2n_handle* h, const int32_t* row, const int32_t* col,
 
 static size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-static void dx_make_layout(DxLayout& L, int world, u64 kcap, u64 pcap)
+static void dx_make_layout(DxLayout& L, int world, u64 kcap, u64 pcap, u64 pair_bytes)
 {
     L.kcap = kcap;
     L.pcap = pcap;
+    L.pair_bytes = pair_bytes;
     size_t o = 0;
     L.off_key = o;   o += up256((size_t)world * kcap * sizeof(TKey));
     L.off_ord = o;   o += up256((size_t)world * kcap * sizeof(u32));
     L.off_first = o; o += up256((size_t)world * kcap);
     L.off_rank = o;  o += up256((size_t)world * kcap * sizeof(u32));
     L.off_id = o;    o += up256((size_t)world * kcap * sizeof(u32));
-    L.off_pair = o;  o += up256((size_t)world * pcap * sizeof(DistPair));
+    L.off_pair = o;  o += up256((size_t)world * pcap * pair_bytes);
     L.bytes = o;
 }
 
@@ -1454,7 +1455,8 @@ int g2n_dist_plan(g2n_handle* h, uint64_t key_cap, uint64_t pair_cap, uint64_t r
     const u64 kcap = (key_cap + 255) & ~255ull, pcap = (pair_cap + 255) & ~255ull;
     if (kcap >= (1ull << 29) || pcap >= 0xFFFFFF00ull) { h->err = "multi-GPU exchange segment too large"; return G2N_ERR_UNSUPPORTED; }
     DxLayout L;
-    dx_make_layout(L, h->dxp.world, kcap, pcap);
+    // the mode of the last g2n_dist_probe / stage 0 decides the entry format: 16 bytes with a weight, 8 without
+    dx_make_layout(L, h->dxp.world, kcap, pcap, h->params.weight_tag_len > 0 ? sizeof(DistPairW) : sizeof(DistPair));
     const bool re = L.bytes > h->dx_arena.cap;
     if (will_realloc) *will_realloc = re ? 1 : 0;
     if (dry_run) return G2N_OK;
@@ -1547,7 +1549,6 @@ int g2n_dist_probe(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2
     if (!h || !out || !h->dx_inited) return G2N_ERR_INVALID;
     memset(out, 0, sizeof(*out));
     h->dx_probed = false;
-    if (p && p->weight_tag && p->weight_tag_len > 0) { h->err = "multi-GPU builds are unweighted in this version"; return G2N_ERR_UNSUPPORTED; }
     int rc = tokenize_phase(h, text, nbytes, p, false, false);
     if (rc) return rc;
     // names beyond the 15-byte inline key travel as their 128-bit tagged hash (table.cuh: make_key); every rank must
@@ -1558,7 +1559,7 @@ int g2n_dist_probe(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const g2
     out->n_records = h->n_records;
     out->n_edge_records = h->n_edges;
     out->n_entries = h->n_edges * (u64)h->tpe * (h->symmax ? 2 : 1);
-    h->hint_sig = shape_signature(p, nbytes, 0);
+    h->hint_sig = shape_signature(p, nbytes, h->params.weight_tag_len);
     h->hint_valid = true;
     h->dx_probed = true;
     return G2N_OK;
@@ -1573,7 +1574,6 @@ int g2n_dist_stage(g2n_handle* h, int stage, const uint8_t* text, uint64_t nbyte
         if (!h->dxp.arena[s] || !h->dxp.ctl[s]) { h->err = "multi-GPU peers are not connected"; return G2N_ERR_INVALID; }
     if (stage == 0) {
         if (!p) return G2N_ERR_INVALID;
-        if (p->weight_tag && p->weight_tag_len > 0) { h->err = "multi-GPU builds are unweighted in this version"; return G2N_ERR_UNSUPPORTED; }
         h->built = false;
         h->dx_spec = speculative != 0;
         if (h->dx_spec) {
@@ -1585,6 +1585,10 @@ int g2n_dist_stage(g2n_handle* h, int stage, const uint8_t* text, uint64_t nbyte
             return G2N_ERR_INVALID;
         }
         h->dx_probed = false;
+        if ((h->params.weight_tag_len > 0) != (h->dxl.pair_bytes == sizeof(DistPairW))) {
+            h->err = "the multi-GPU plan was made for a different mode (weight tag)";
+            return G2N_ERR_INVALID;
+        }
         h->dxp.epoch++;
         if (!h->dx_spec) {  // a repeated host-planned pass over the same probe: the bitmap must start clean
             CK(cudaMemsetAsync(h->zids.p, 0, h->zids_bytes, h->stream));
@@ -1643,6 +1647,21 @@ int g2n_dist_stage(g2n_handle* h, int stage, const uint8_t* text, uint64_t nbyte
     case 4: {
         const u32 rows_cap = h->dx_spec ? (u32)h->dx_rows_cap : 0xFFFFFFFFu;
         { KScope ks(h, "k_dx_localmap"); k_dx_localmap<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->d_tkeys, cap, h->d_ds, X, L, my, loc, h->dx_sent.as<u32>(), h->slot_id.as<u32>(), rows_cap); }
+        if (h->params.weight_tag_len > 0) {
+            // weighted: positions follow the emission order (count per tile and owner, scan, ordered scatter)
+            const u64 cells = (u64)W * h->n_tiles;
+            CK(h->dx_tcnt.ensure((cells + 2) * sizeof(u32)));
+            CK(h->dx_toff.ensure((cells + 2) * sizeof(u32)));
+            EmitParams EP = emit_params(h);
+            const u32 tgrid = grid_for((u64)h->n_tiles * 32 + 1, 256);
+            { KScope ks(h, "k_dxw_count"); k_dxw_count<<<tgrid, 256, 0, h->stream>>>(EP, sym, csc, X, L, loc, h->dx_tcnt.as<u32>()); }
+            CK(cudaGetLastError());
+            LoadArray<u32> lt{h->dx_tcnt.as<u32>()};
+            int rc = launch_scan<u32>(h, lt, h->dx_toff.as<u32>(), nullptr, cells, nullptr, nullptr);
+            if (rc) return rc;
+            { KScope ks(h, "k_dxw_scatter"); k_dxw_scatter<<<tgrid, 256, 0, h->stream>>>(EP, sym, csc, X, L, loc, h->dx_toff.as<u32>()); }
+            break;
+        }
         const u32 egrid = grid_for((h->cap_E + 256 * DXE_BATCH - 1) / (256 * DXE_BATCH), 1, 8);
         u32* es = h->edge_slots.as<u32>();
         {
@@ -1669,7 +1688,9 @@ int g2n_dist_stage(g2n_handle* h, int stage, const uint8_t* text, uint64_t nbyte
             h->dx_recv_cap = recv_cap;
         }
         if (recv_cap >= 0xFFFFFFF0ull) { h->err = "more than 2^32 entries in one slab"; return G2N_ERR_UNSUPPORTED; }
-        CK(h->entries.ensure((recv_cap + 1) * sizeof(u32)));
+        const bool weighted = h->params.weight_tag_len > 0;
+        CK(h->entries.ensure((recv_cap + 1) * (weighted ? sizeof(u64) : sizeof(u32))));
+        if (weighted) CK(h->w_emit.ensure((recv_cap + 1) * sizeof(double)));
         {
             int rc0 = layout_zrows(h, rows_cap);
             if (rc0) return rc0;
@@ -1678,12 +1699,14 @@ int g2n_dist_stage(g2n_handle* h, int stage, const uint8_t* text, uint64_t nbyte
         CK(cudaMemsetAsync(h->zrows.p, 0, h->zrows_bytes, h->stream));
         h->result_format = csc ? G2N_FMT_CSC : G2N_FMT_CSR;
         const u32 pgrid = grid_for(recv_cap / (u64)W + 1, 256, 8);
-        { KScope ks(h, "k_pairs_count"); k_pairs_count<<<pgrid, 256, 0, h->stream>>>(X, L, loc, h->d_ds, h->d_rowcnt, &loc->bad); }
+        if (weighted) { KScope ks(h, "k_pairsw_count"); k_pairsw_count<<<pgrid, 256, 0, h->stream>>>(X, L, loc, h->d_ds, h->d_rowcnt, &loc->bad); }
+        else { KScope ks(h, "k_pairs_count"); k_pairs_count<<<pgrid, 256, 0, h->stream>>>(X, L, loc, h->d_ds, h->d_rowcnt, &loc->bad); }
         int rc = rows_scan(h, rows_cap, &h->d_ds->rows);
         if (rc) return rc;
-        { KScope ks(h, "k_pairs_scatter"); k_pairs_scatter<<<pgrid, 256, 0, h->stream>>>(X, L, loc, h->d_ds, h->cursor.as<u32>(), h->entries.as<u32>()); }
+        if (weighted) { KScope ks(h, "k_pairsw_scatter"); k_pairsw_scatter<<<pgrid, 256, 0, h->stream>>>(X, L, loc, h->d_ds, h->cursor.as<u32>(), h->entries.as<u64>(), h->w_emit.as<double>()); }
+        else { KScope ks(h, "k_pairs_scatter"); k_pairs_scatter<<<pgrid, 256, 0, h->stream>>>(X, L, loc, h->d_ds, h->cursor.as<u32>(), h->entries.as<u32>()); }
         CK(cudaGetLastError());
-        rc = rows_finalize(h, h->params.dtype, false, recv_cap, rows_cap, sym, nullptr, nullptr);
+        rc = rows_finalize(h, h->params.dtype, weighted, recv_cap, rows_cap, sym, weighted ? h->w_emit.as<double>() : nullptr, nullptr);
         if (rc) return rc;
         break;
     }

@@ -6,7 +6,8 @@
     stage 2  every shard ranks the keys that first appear in it; ranks -> owners
     stage 3  owners hand every source the node ID of each of its keys (the reference's numbering over the
              concatenated shards, builders.py:194-198, 219-221)
-    stage 4  row entries -> owner(row) = row // ceil(n / world)
+    stage 4  row entries -> owner(row) = row // ceil(n / world)  (with a weight tag: in emission order, so that
+             duplicate weights are summed in the reference's order)
     stage 5  duplicate sum / max(S, S^T) -> this rank's CSR slab (builders.py:279-283, utils.py:55)
     stage 6  the build's verdict, the same on every rank (a capacity miss anywhere repeats the build everywhere)
 
@@ -17,7 +18,7 @@ used only by host-planned builds (the first build of a shape, or after a capacit
 queues its stages without any host round trip and synchronises once, at the end.
 `LocalRank` wraps one rank's handle, `DistBuilder` adds the bootstrap; tests drive several `LocalRank`s
 on one GPU (logical shards: same kernels, peers are plain device pointers).
-Restrictions of this version: unweighted builds, <= 8 ranks."""
+Restriction of this version: <= 8 ranks."""
 from __future__ import annotations
 
 import ctypes as C
@@ -96,9 +97,6 @@ def assemble_slabs(slabs, n_global: int, fmt: str = "csr"):
 
 
 # ------------------------------------------------------------------ one rank's device work
-_MODE_KEYS = ("directed", "bidirected", "keep_directed_bidir", "asymmetric", "strip_orientation", "dtype", "matrix_format")
-
-
 class LocalRank:
     def __init__(self, device_index: int, rank: int, world: int, stream_ptr: int | None = None):
         import torch
@@ -115,10 +113,11 @@ class LocalRank:
         self.text = None
 
     def set_input(self, text_dev, *, directed=True, bidirected=False, keep_directed_bidir=False, asymmetric=False,
-                  strip_orientation=False, dtype="float64", matrix_format="csr"):
+                  strip_orientation=False, dtype="float64", matrix_format="csr", weight_tag=None):
         want = {"csr": _capi.FMT_CSR, "csc": _capi.FMT_CSC}[matrix_format]
+        self._wt = weight_tag.encode() if weight_tag else None  # kept alive: Params holds a pointer to it
         self.params = _capi.Params(int(directed), int(bidirected), int(keep_directed_bidir), int(asymmetric), int(strip_orientation),
-                                   _capi.DTYPES[np.dtype(dtype).name], want, 1, None, 0, 0)
+                                   _capi.DTYPES[np.dtype(dtype).name], want, 1, self._wt, len(self._wt) if self._wt else 0, 0)
         self.text = text_dev
         self.nbytes = int(text_dev.numel())
         self.text_ptr = C.c_void_p(text_dev.data_ptr() if self.nbytes else 0)

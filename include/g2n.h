@@ -229,7 +229,9 @@ int g2n_coo_to_compressed(g2n_handle *h, const int32_t *row, const int32_t *col,
  *                        0: the tokenizer results of g2n_dist_probe are used
  *   g2n_dist_finish      the one host round trip: G2N_OK, or G2N_ERR_RETRY on every rank
  * Ranks that share a process (tests: several logical ranks on one GPU) must queue stage k on every rank
- * before stage k+1 on any.  Restrictions of this version: unweighted builds, <= 8 ranks.  Node names longer than
+ * before stage k+1 on any.  Restriction of this version: <= 8 ranks.  With a weight tag the row entries
+ * travel in emission order together with their weight, so duplicate sums match the single-GPU result bit for bit.
+ * Node names longer than
  * the 15-byte inline key are exchanged as their 128-bit tagged hash (equality of two DIFFERENT long names on
  * different ranks is decided by that hash alone; inside a shard the bytes are compared as on one GPU). */
 typedef struct g2n_dist_info {

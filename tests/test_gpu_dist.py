@@ -186,20 +186,65 @@ def test_errors_and_warnings_are_agreed():
             D.raise_agreed(infos)
 
 
-def test_dist_refuses_weights():
-    import ctypes as C
+def _weighted_text(seed: int, n: int = 6000) -> np.ndarray:
+    """Chain links with inexact float weights, duplicates and reverse duplicates in shuffled order: duplicate
+    sums depend on the summation order, rows stay below SciPy's 16-entry insertion-sort regime."""
+    rng = np.random.default_rng(seed)
+    lines = [b"S\ts%d\t*" % i for i in range(n)]
+    links = []
+    for i in range(n - 1):
+        links.append(b"L\ts%d\t+\ts%d\t-\t0M\tRC:f:%.3f" % (i, i + 1, rng.integers(1, 9000) / 7))
+        if rng.random() < 0.5:
+            links.append(b"L\ts%d\t+\ts%d\t-\t0M\tRC:f:%.3f" % (i, i + 1, rng.integers(1, 9000) / 11))
+        if rng.random() < 0.3:
+            links.append(b"L\ts%d\t-\ts%d\t+\t0M\tXX:i:3\tRC:i:%d" % (i + 1, i, rng.integers(-5, 50)))
+        if rng.random() < 0.1:
+            links.append(b"L\ts%d\t+\ts%d\t-\t0M" % (i, i + 1))  # no tag: weight 1.0
+    order = rng.permutation(len(links))
+    lines += [links[k] for k in order]
+    return np.frombuffer(b"\n".join(lines) + b"\n", dtype=np.uint8)
 
-    import torch
 
+WMODES = [dict(), dict(directed=False), dict(asymmetric=True), dict(bidirected=True), dict(bidirected=True, keep_directed_bidir=True),
+          dict(dtype="float32"), dict(dtype="int32", directed=False, matrix_format="csc")]
+
+
+@pytest.mark.parametrize("G", [2, 5])
+@pytest.mark.parametrize("mode", WMODES, ids=[str(m) for m in WMODES])
+def test_weighted_logical_shards_match_oracle(G, mode):
+    """With a weight tag the row entries travel in emission order with their weight: duplicate sums are bit-identical
+    to the reference's (SciPy's) order although the duplicates sit in different shards."""
     from gfa2network_b200 import _capi
     from gfa2network_b200 import dist as D
 
-    r = D.LocalRank(0, 0, 1)
-    t = torch.from_numpy(np.frombuffer(b"S\ta\t*\n", dtype=np.uint8).copy()).cuda()
-    params = _capi.Params(1, 0, 0, 0, 0, 0, 1, 1, b"RC", 2, 0)
-    info = _capi.DistInfo()
-    rc = r.h.lib.g2n_dist_probe(r.h.h, C.c_void_p(t.data_ptr()), t.numel(), C.byref(params), C.byref(info))
-    assert rc == _capi.G2N_ERR_UNSUPPORTED
+    text = _weighted_text(17)
+    mode = dict(mode, weight_tag="RC")
+    shards = _shards(text, G)
+    ranks = [D.LocalRank(0, r, G) for r in range(G)]
+    fmt = mode.get("matrix_format", "csr")
+    out, caps = _build(ranks, shards, False, **mode)
+    assert all(rc == _capi.G2N_OK for rc, _ in out)
+    _check(*_assemble(ranks, out, fmt), text, mode)
+    for r, (_, res) in zip(ranks, out):
+        r.remember(res, *caps)
+    out, _ = _build(ranks, shards, True, **mode)
+    assert all(rc == _capi.G2N_OK for rc, _ in out), [hex(int(res.bad)) for _, res in out]
+    _check(*_assemble(ranks, out, fmt), text, mode)
+
+
+def test_weighted_c3_dialect_shards():
+    """The C3 shape (reference E-dialect with RC:f tags, bidirected) over 3 logical ranks."""
+    from gfa2network_b200 import _capi
+    from gfa2network_b200 import dist as D
+    from gfa2network_b200.synth import synth_gfa
+
+    text = synth_gfa(20_000, 60_000, seed=3, kind=2)
+    mode = dict(bidirected=True, weight_tag="RC")
+    G = 3
+    ranks = [D.LocalRank(0, r, G) for r in range(G)]
+    out, _ = _build(ranks, _shards(text, G), False, **mode)
+    assert all(rc == _capi.G2N_OK for rc, _ in out)
+    _check(*_assemble(ranks, out, "csr"), text, mode)
 
 
 def test_empty_and_lopsided_shards():

@@ -86,9 +86,7 @@ def main():
     text_dev = torch.from_numpy(text_np).to(dev)
     del text_np
     gen_s = time.perf_counter() - t0
-    mode = {k: v for k, v in cfg["mode"].items() if k != "weight_tag"}
-    if cfg["mode"].get("weight_tag"):
-        raise SystemExit("multi-GPU builds are unweighted in this version")
+    mode = dict(cfg["mode"])
     sym = bool(mode.get("keep_directed_bidir") or (not mode.get("bidirected") and mode.get("directed", True))) and not mode.get("asymmetric")
     b = DistBuilder(local)
     stream = torch.cuda.current_stream()
@@ -140,7 +138,8 @@ def main():
         s_rc, s_cr = f(rows, cols), f(cols, rows)
         tot = lambda s: ((allsum(s >> 31) << 31) + allsum(s & 0x7FFFFFFF)) % (1 << 64)  # noqa: E731 - exact sum over ranks, mod 2^64
         checks["symmetric_checksum"] = tot(s_rc) == tot(s_cr)
-        checks["weights_are_positive_integers"] = allsum(int(bool(((dt >= 1.0) & (dt == dt.floor())).all().item()))) == world
+        if not mode.get("weight_tag"):
+            checks["weights_are_positive_integers"] = allsum(int(bool(((dt >= 1.0) & (dt == dt.floor())).all().item()))) == world
         del rows, cols
 
     # ---- bit-exact comparison with the single-GPU build of the concatenated shards
@@ -166,8 +165,9 @@ def main():
             del parts
             hs = _capi.Handle(local)
             hs.set_stream(stream.cuda_stream)
+            wtb = mode["weight_tag"].encode() if mode.get("weight_tag") else None
             params = _capi.Params(int(mode.get("directed", True)), int(mode.get("bidirected", False)), int(mode.get("keep_directed_bidir", False)),
-                                  int(mode.get("asymmetric", False)), 0, _capi.DTYPES["float64"], _capi.FMT_CSR, 1, None, 0, 0)
+                                  int(mode.get("asymmetric", False)), 0, _capi.DTYPES["float64"], _capi.FMT_CSR, 1, wtb, len(wtb) if wtb else 0, 0)
             hs.check(hs.build(full.data_ptr(), int(full.numel()), params))
             sip, six, sdt = device_result(hs, torch, dev)
             from gfa2network_b200.builders import _node_list
