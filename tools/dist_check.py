@@ -128,7 +128,7 @@ def main():
     checks["rows_partition_nodes"] = allsum(res.n_rows) == res.n_global
     checks["names_partition_nodes"] = allsum(res.info["n_first"]) == res.n_global
     checks["entries_sent_eq_received"] = allsum(sum(res.info["pairs_to"])) == allsum(res.info["n_recv"])
-    checks["node_count_eq_segments"] = res.n_global == world * n_seg
+    checks["node_count_eq_segments"] = res.n_global == world * n_seg * (2 if mode.get("bidirected") else 1)  # S registers id:+ and id:-
     total_nnz = allsum(nnz)
     if sym:
         rows = torch.repeat_interleave(torch.arange(res.row0, res.row0 + res.n_rows, device=dev, dtype=torch.int64), (ip[1:] - ip[:-1]).long())
