@@ -165,10 +165,12 @@ __device__ __forceinline__ void dx_tail_signal(const DxPeers& X, int e, DxLocal*
 }
 
 // ---------------------------------------------------------------- x1: local keys -> owners
-// sent[slot] = owner << 29 | position in the owner's segment of this rank
+// klist[owner][position in the owner's segment of this rank] = local order bit << 32 | table slot: the later passes
+// of this rank (mark, send_rank, localmap) walk these compact lists next to the owners' replies, which sit at
+// the same positions -- sequential reads instead of three more scans of the (half empty) table
 __global__ void __launch_bounds__(256) k_dx_export(const TKey* __restrict__ tkeys, const u64* __restrict__ tfirst, u32 cap,
                                                     const u64* __restrict__ tile_base, const DevSizes* __restrict__ ds,
-                                                    const DxPeers X, const DxLayout L, DxLocal* __restrict__ loc, u32* __restrict__ sent)
+                                                    const DxPeers X, const DxLayout L, DxLocal* __restrict__ loc, u64* __restrict__ klist)
 {
     if (!ds->ok && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&loc->bad, DXB_TOK);
     const u32 lane = threadIdx.x & 31;
@@ -184,12 +186,13 @@ __global__ void __launch_bounds__(256) k_dx_export(const TKey* __restrict__ tkey
         if ((int)lane == leader) base = atomicAdd(&loc->cur_keys[d], (u32)__popc(m));
         base = __shfl_sync(m, base, leader);
         const u32 pos = base + __popc(m & ((1u << lane) - 1u));
-        if (pos >= L.kcap) { atomicOr(&loc->bad, DXB_KEYS); sent[i] = 0xFFFFFFFFu; continue; }
+        if (pos >= L.kcap) { atomicOr(&loc->bad, DXB_KEYS); continue; }
         uint8_t* a = X.arena[d];
         const u64 j = (u64)X.rank * L.kcap + pos;
+        const u32 bit = order_bit(tile_base, ~tfirst[i]);
         reinterpret_cast<TKey*>(a + L.off_key)[j] = k;
-        reinterpret_cast<u32*>(a + L.off_ord)[j] = order_bit(tile_base, ~tfirst[i]);
-        sent[i] = (d << 29) | pos;
+        reinterpret_cast<u32*>(a + L.off_ord)[j] = bit;
+        klist[(u64)d * L.kcap + pos] = ((u64)bit << 32) | i;
     }
     dx_tail_signal(X, 0, loc, loc->cur_keys, L.kcap, 0);
 }
@@ -270,10 +273,14 @@ __global__ void __launch_bounds__(256) k_dx_reply_first(const DxPeers X, const D
 }
 
 // ---------------------------------------------------------------- x2 consumer: bitmap of this shard's global firsts
-__global__ void __launch_bounds__(256) k_dx_mark(const TKey* __restrict__ tkeys, const u64* __restrict__ tfirst, u32 cap,
-                                                  const u64* __restrict__ tile_base, const DevSizes* __restrict__ ds, const DxPeers X,
-                                                  const DxLayout L, const DxCtl* my, DxLocal* __restrict__ loc,
-                                                  const u32* __restrict__ sent, u32* __restrict__ bitmap)
+__device__ __forceinline__ u32 dx_sent_count(const DxLocal* loc, u32 d, u64 kcap)
+{
+    const u32 c = loc->cur_keys[d];
+    return (u32)(c < kcap ? c : kcap);
+}
+
+__global__ void __launch_bounds__(256) k_dx_mark(const DevSizes* __restrict__ ds, const DxPeers X, const DxLayout L, const DxCtl* my,
+                                                  DxLocal* __restrict__ loc, const u64* __restrict__ klist, u32* __restrict__ bitmap)
 {
     dx_wait(my, 1, X, loc);
     if (blockIdx.x == 0 && threadIdx.x < (u32)X.world) {
@@ -282,40 +289,38 @@ __global__ void __launch_bounds__(256) k_dx_mark(const TKey* __restrict__ tkeys,
     }
     if (!ds->ok) return;
     const uint8_t* first = X.arena[X.rank] + L.off_first;
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
-        const TKey k = tkeys[i];
-        if (k.x == 0 && k.y == 0) continue;
-        const u32 sv = sent[i];
-        if (sv == 0xFFFFFFFFu) continue;
-        if (!first[(u64)(sv >> 29) * L.kcap + (sv & 0x1FFFFFFFu)]) continue;
-        const u32 bit = order_bit(tile_base, ~tfirst[i]);
-        atomicOr(&bitmap[bit >> 5], 1u << (bit & 31));
+    for (u32 d = 0; d < (u32)X.world; d++) {
+        const u32 n = dx_sent_count(loc, d, L.kcap);
+        for (u32 pos = blockIdx.x * blockDim.x + threadIdx.x; pos < n; pos += gridDim.x * blockDim.x) {
+            if (!first[(u64)d * L.kcap + pos]) continue;
+            const u32 bit = (u32)(klist[(u64)d * L.kcap + pos] >> 32);
+            atomicOr(&bitmap[bit >> 5], 1u << (bit & 31));
+        }
     }
 }
 
 // ---------------------------------------------------------------- x3: first source -> owner, rank inside the shard
 // also this shard's name table: id2slot / name_len are indexed by that rank
-__global__ void __launch_bounds__(256) k_dx_send_rank(const TKey* __restrict__ tkeys, const u64* __restrict__ tfirst, u32 cap,
-                                                       const u64* __restrict__ tile_base, const DevSizes* __restrict__ ds, const DxPeers X,
-                                                       const DxLayout L, const u32* __restrict__ sent, const u32* __restrict__ bitmap,
+__global__ void __launch_bounds__(256) k_dx_send_rank(const TKey* __restrict__ tkeys, const DevSizes* __restrict__ ds, const DxPeers X,
+                                                       const DxLayout L, const u64* __restrict__ klist, const u32* __restrict__ bitmap,
                                                        const u32* __restrict__ wprefix, u32* __restrict__ id2slot, u32* __restrict__ name_len,
                                                        DxLocal* __restrict__ loc)
 {
     const bool ok = ds->ok != 0;
     const uint8_t* first = X.arena[X.rank] + L.off_first;
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; ok && i < cap; i += gridDim.x * blockDim.x) {
-        const TKey k = tkeys[i];
-        if (k.x == 0 && k.y == 0) continue;
-        const u32 sv = sent[i];
-        if (sv == 0xFFFFFFFFu) continue;
-        const u32 d = sv >> 29, pos = sv & 0x1FFFFFFFu;
-        if (!first[(u64)d * L.kcap + pos]) continue;
-        const u32 ob = order_bit(tile_base, ~tfirst[i]);
-        const u32 wd = ob >> 5, bit = ob & 31;
-        const u32 r = wprefix[wd] + __popc(bitmap[wd] & ((1u << bit) - 1u));
-        reinterpret_cast<u32*>(X.arena[d] + L.off_rank)[(u64)X.rank * L.kcap + pos] = r;
-        id2slot[r] = i;
-        name_len[r] = slot_key_len(k.y);
+    for (u32 d = 0; ok && d < (u32)X.world; d++) {
+        const u32 n = dx_sent_count(loc, d, L.kcap);
+        u32* out = reinterpret_cast<u32*>(X.arena[d] + L.off_rank) + (u64)X.rank * L.kcap;
+        for (u32 pos = blockIdx.x * blockDim.x + threadIdx.x; pos < n; pos += gridDim.x * blockDim.x) {
+            if (!first[(u64)d * L.kcap + pos]) continue;
+            const u64 e = klist[(u64)d * L.kcap + pos];
+            const u32 ob = (u32)(e >> 32), slot = (u32)e;
+            const u32 wd = ob >> 5, bit = ob & 31;
+            const u32 r = wprefix[wd] + __popc(bitmap[wd] & ((1u << bit) - 1u));
+            out[pos] = r;
+            id2slot[r] = slot;
+            name_len[r] = slot_key_len(tkeys[slot].y);
+        }
     }
     // the popcount prefix ends with the number of marked bits = this shard's global firsts
     dx_tail_signal(X, 2, loc, nullptr, 0, ok ? (u64)wprefix[ds->words] : 0ull);
@@ -370,9 +375,8 @@ __global__ void __launch_bounds__(256) k_dx_reply_ids(const DxPeers X, const DxL
 }
 
 // ---------------------------------------------------------------- x4 consumer: local slot -> global node ID
-__global__ void __launch_bounds__(256) k_dx_localmap(const TKey* __restrict__ tkeys, u32 cap, const DevSizes* __restrict__ ds, const DxPeers X,
-                                                      const DxLayout L, const DxCtl* my, DxLocal* __restrict__ loc,
-                                                      const u32* __restrict__ sent, u32* __restrict__ slot_id, u32 rows_cap)
+__global__ void __launch_bounds__(256) k_dx_localmap(const DevSizes* __restrict__ ds, const DxPeers X, const DxLayout L, const DxCtl* my,
+                                                      DxLocal* __restrict__ loc, const u64* __restrict__ klist, u32* __restrict__ slot_id, u32 rows_cap)
 {
     dx_wait(my, 3, X, loc);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -384,11 +388,10 @@ __global__ void __launch_bounds__(256) k_dx_localmap(const TKey* __restrict__ tk
     }
     if (!ds->ok) return;
     const u32* ids = reinterpret_cast<const u32*>(X.arena[X.rank] + L.off_id);
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
-        const TKey k = tkeys[i];
-        if (k.x == 0 && k.y == 0) continue;
-        const u32 sv = sent[i];
-        slot_id[i] = sv == 0xFFFFFFFFu ? 0u : ids[(u64)(sv >> 29) * L.kcap + (sv & 0x1FFFFFFFu)];
+    for (u32 d = 0; d < (u32)X.world; d++) {
+        const u32 n = dx_sent_count(loc, d, L.kcap);
+        for (u32 pos = blockIdx.x * blockDim.x + threadIdx.x; pos < n; pos += gridDim.x * blockDim.x)
+            slot_id[(u32)klist[(u64)d * L.kcap + pos]] = ids[(u64)d * L.kcap + pos];
     }
 }
 

@@ -1598,7 +1598,7 @@ int g2n_dist_stage(g2n_handle* h, int stage, const uint8_t* text, uint64_t nbyte
         const u64 words = (4 * h->cap_R + 31) / 32 + 1;
         CK(h->wprefix.ensure((words + 2) * sizeof(u32)));
         CK(h->slot_id.ensure((size_t)h->table_cap * sizeof(u32)));
-        CK(h->dx_sent.ensure((size_t)h->table_cap * sizeof(u32)));
+        CK(h->dx_sent.ensure((size_t)W * h->dxl.kcap * sizeof(u64) + 256));  // klist: [owner][position] -> order bit | slot
         CK(h->id2slot.ensure((h->cap_n + 1) * sizeof(u32)));
         CK(h->name_len.ensure((h->cap_n + 1) * sizeof(u32)));
         CK(h->name_off.ensure((h->cap_n + 2) * sizeof(u64)));
@@ -1623,7 +1623,7 @@ int g2n_dist_stage(g2n_handle* h, int stage, const uint8_t* text, uint64_t nbyte
     const int csc = (!sym && h->params.want_format == G2N_FMT_CSC) ? 1 : 0;
     switch (stage) {
     case 0: {
-        { KScope ks(h, "k_dx_export"); k_dx_export<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->d_tkeys, h->d_tfirst, cap, h->tile_base.as<u64>(), h->d_ds, X, L, loc, h->dx_sent.as<u32>()); }
+        { KScope ks(h, "k_dx_export"); k_dx_export<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->d_tkeys, h->d_tfirst, cap, h->tile_base.as<u64>(), h->d_ds, X, L, loc, h->dx_sent.as<u64>()); }
         break;
     }
     case 1: {
@@ -1632,12 +1632,12 @@ int g2n_dist_stage(g2n_handle* h, int stage, const uint8_t* text, uint64_t nbyte
         break;
     }
     case 2: {
-        { KScope ks(h, "k_dx_mark"); k_dx_mark<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->d_tkeys, h->d_tfirst, cap, h->tile_base.as<u64>(), h->d_ds, X, L, my, loc, h->dx_sent.as<u32>(), h->d_bitmap); }
+        { KScope ks(h, "k_dx_mark"); k_dx_mark<<<kgrid, 256, 0, h->stream>>>(h->d_ds, X, L, my, loc, h->dx_sent.as<u64>(), h->d_bitmap); }
         const u64 words = (4 * h->cap_R + 31) / 32 + 1;
         LoadPopc lp{h->d_bitmap};
         int rc = launch_scan<u32>(h, lp, h->wprefix.as<u32>(), nullptr, words, &h->d_ds->words, h->d_scan_words);
         if (rc) return rc;
-        { KScope ks(h, "k_dx_send_rank"); k_dx_send_rank<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->d_tkeys, h->d_tfirst, cap, h->tile_base.as<u64>(), h->d_ds, X, L, h->dx_sent.as<u32>(), h->d_bitmap, h->wprefix.as<u32>(), h->id2slot.as<u32>(), h->name_len.as<u32>(), loc); }
+        { KScope ks(h, "k_dx_send_rank"); k_dx_send_rank<<<kgrid, 256, 0, h->stream>>>(h->d_tkeys, h->d_ds, X, L, h->dx_sent.as<u64>(), h->d_bitmap, h->wprefix.as<u32>(), h->id2slot.as<u32>(), h->name_len.as<u32>(), loc); }
         break;
     }
     case 3: {
@@ -1646,7 +1646,7 @@ int g2n_dist_stage(g2n_handle* h, int stage, const uint8_t* text, uint64_t nbyte
     }
     case 4: {
         const u32 rows_cap = h->dx_spec ? (u32)h->dx_rows_cap : 0xFFFFFFFFu;
-        { KScope ks(h, "k_dx_localmap"); k_dx_localmap<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->d_tkeys, cap, h->d_ds, X, L, my, loc, h->dx_sent.as<u32>(), h->slot_id.as<u32>(), rows_cap); }
+        { KScope ks(h, "k_dx_localmap"); k_dx_localmap<<<kgrid, 256, 0, h->stream>>>(h->d_ds, X, L, my, loc, h->dx_sent.as<u64>(), h->slot_id.as<u32>(), rows_cap); }
         if (h->params.weight_tag_len > 0) {
             // weighted: positions follow the emission order (count per tile and owner, scan, ordered scatter)
             const u64 cells = (u64)W * h->n_tiles;
