@@ -121,13 +121,32 @@ def cpu_oracle_run(text, mode, fmt):
     return time.perf_counter() - t, A
 
 
+REFERENCE_BUDGET_S = 150.0  # CPU seconds the whole --impl reference run may take
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path = the oracle port (the
-    reference itself is Python under /root/reference, which does not exist on the GPU box)."""
+    reference itself is Python under /root/reference, which does not exist on the GPU box; it is
+    single-threaded, and so is the port: cores = 1).  Every step is one pass over a text of the
+    configuration's shape; when K full-size passes would not fit the time budget the text is scaled down
+    (same generator, same mix of records) and `sample` says so -- GB/s is size-normalised."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cfg, text, n_seg, n_link = make_text(args.config, args.scale)
+    n_pass = args.steps + max(0, min(args.warmup, 1))
+    # rate estimate on a 5 % text, then the largest scale whose passes fit the budget
+    cfg, probe, _, _ = make_text(args.config, min(args.scale, 0.05))
+    dt, _A = cpu_oracle_run(probe, cfg["mode"], cfg["fmt"])
+    rate = probe.size / dt
+    _, full, _, _ = make_text(args.config, args.scale) if CONFIG_BYTES_HINT.get(args.config, 0) * args.scale < 2e9 else (None, None, None, None)
+    full_bytes = full.size if full is not None else CONFIG_BYTES_HINT[args.config] * args.scale
+    scale = args.scale * min(1.0, rate * REFERENCE_BUDGET_S / n_pass / full_bytes)
+    if scale >= args.scale * 0.999 and full is not None:
+        cfg, text, n_seg, n_link = make_text(args.config, args.scale)
+        scale = args.scale
+    else:
+        cfg, text, n_seg, n_link = make_text(args.config, scale)
+    del full, probe
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_oracle_run(text, cfg["mode"], cfg["fmt"])
     times = []
@@ -136,17 +155,30 @@ def run_reference(args):
         times.append(dt)
     ms = 1e3 * sum(times) / len(times)
     gbs = text.size / (ms * 1e6)
+    sample = (f"full {args.config} text ({text.size} B)" if scale == args.scale else
+              f"{args.config} shape scaled to {scale / args.scale:.3f} of the workload ({text.size} B per pass) to keep {n_pass} passes within {REFERENCE_BUDGET_S:.0f} s")
     line = {
         "impl": "reference", "metric": "gfa_to_csr_parse_build_GBps", "value": gbs, "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/int32/f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.config, args.scale, n_seg, n_link, cfg), "text_bytes": int(text.size)},
+        "config": {"workload": workload_name(args.config, args.scale, *make_sizes(args.config, args.scale), cfg), "text_bytes": int(full_bytes)},
         "edges_per_s": n_link / (ms / 1e3),
-        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": 1, "kind": "port",
-                         "sample": f"full {args.config} text ({text.size} B), {args.steps} runs, C port of parser.py/builders.py + SciPy"},
+        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": 1, "kind": "port", "host_cores_available": os.cpu_count(),
+                         "sample": sample + f", {args.steps} passes, C port of parser.py/builders.py + SciPy"},
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+# approximate text bytes of the full configurations (only to decide whether generating them is affordable)
+CONFIG_BYTES_HINT = {"C2": 86e6, "C3": 1.67e9, "C4": 11.9e9, "C5": 39.8e9}
+
+
+def make_sizes(cfg_name: str, scale: float):
+    from gfa2network_b200.synth import CONFIGS
+
+    cfg = CONFIGS[cfg_name]
+    return max(2, int(cfg["n_seg"] * scale)), max(1, int(cfg["n_link"] * scale))
 
 
 def workload_name(cfg_name, scale, n_seg, n_link, cfg):

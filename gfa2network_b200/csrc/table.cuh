@@ -16,7 +16,9 @@ namespace g2n {
 #define WT_LOOK 992
 #define WT_WIN (WT_PRE + WT_TILE + WT_LOOK)  // 3072 bytes staged per tile
 #define WT_WORDS (WT_WIN / 32)               // 32-bit mask words covering the window
+#ifndef WT_WARPS
 #define WT_WARPS 8                           // warps (tiles in flight) per CTA
+#endif
 #define WT_LIST 256                          // record lines per batch of the compacted list
 #define TK_NF 0xFFFFFFFFu
 
