@@ -394,7 +394,7 @@ def run_ours(args):
     path_ach = (nbytes + out_bytes) / (ms_step * 1e6)
     # ---- CPU baseline on this host (rank 0, N=1 only; bounded: one full pass of the same text)
     cpu_base = None
-    if world == 1:
+    if world == 1 and not os.environ.get("G2N_BENCH_NO_CPU"):  # (kernel experiments skip the CPU pass)
         cpu_dt, _B = cpu_oracle_run(text_np, mode, fmt)
         cpu_base = {"value": nbytes / (cpu_dt * 1e9), "unit": "GB/s", "cores": 1, "kind": "port",
                     "sample": f"full {args.config} text ({nbytes} B), 1 run: C port of parser.py/builders.py + SciPy tocsr/maximum",

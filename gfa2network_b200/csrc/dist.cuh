@@ -508,7 +508,7 @@ __global__ void k_dx_slab_sizes(const DxPeers X, const DxLayout L, const DxCtl* 
 }
 
 __global__ void __launch_bounds__(256) k_pairs_count(const DxPeers X, const DxLayout L, const DxLocal* __restrict__ loc, const DevSizes* __restrict__ ds,
-                                                      u32* __restrict__ cnt, u32* __restrict__ bad_out)
+                                                      u32* __restrict__ cnt, u32* __restrict__ bad_out, const RowRange rr)
 {
     if (!ds->ok) return;
     const u32 row0 = loc->row0, n_rows = loc->n_rows;
@@ -518,15 +518,15 @@ __global__ void __launch_bounds__(256) k_pairs_count(const DxPeers X, const DxLa
         const DistPair* pairs = base + (u64)s * L.pcap;
         for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
             const u32 r = pairs[i].major - row0;
-            if (r < n_rows) atomicAdd(&cnt[r], 1u);
-            else atomicOr(bad_out, DXB_RANGE);
+            if (r >= n_rows) atomicOr(bad_out, DXB_RANGE);
+            else if (rr.has(r)) atomicAdd(&cnt[r], 1u);
         }
     }
 }
 
 // multi-GPU builds are unweighted: the slab keeps 32-bit entries (minor << 1 | dir), see Ent32
 __global__ void __launch_bounds__(256) k_pairs_scatter(const DxPeers X, const DxLayout L, const DxLocal* __restrict__ loc, const DevSizes* __restrict__ ds,
-                                                        u32* __restrict__ cursor, u32* __restrict__ entries)
+                                                        u32* __restrict__ cursor, u32* __restrict__ entries, const RowRange rr)
 {
     if (!ds->ok) return;
     const u32 row0 = loc->row0, n_rows = loc->n_rows;
@@ -537,7 +537,7 @@ __global__ void __launch_bounds__(256) k_pairs_scatter(const DxPeers X, const Dx
         for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
             const DistPair p = pairs[i];
             const u32 r = p.major - row0;
-            if (r < n_rows) entries[atomicAdd(&cursor[r], 1u)] = p.entry;
+            if (r < n_rows && rr.has(r)) entries[atomicAdd(&cursor[r], 1u)] = p.entry;
         }
     }
 }
@@ -639,7 +639,7 @@ __global__ void __launch_bounds__(256) k_dxw_scatter(const EmitParams E, int sym
 
 // receiver: row histogram, then entries numbered in arrival = emission order, weights laid out by that number
 __global__ void __launch_bounds__(256) k_pairsw_count(const DxPeers X, const DxLayout L, const DxLocal* __restrict__ loc, const DevSizes* __restrict__ ds,
-                                                       u32* __restrict__ cnt, u32* __restrict__ bad_out)
+                                                       u32* __restrict__ cnt, u32* __restrict__ bad_out, const RowRange rr)
 {
     if (!ds->ok) return;
     const u32 row0 = loc->row0, n_rows = loc->n_rows;
@@ -649,14 +649,14 @@ __global__ void __launch_bounds__(256) k_pairsw_count(const DxPeers X, const DxL
         const DistPairW* pairs = base + (u64)s * L.pcap;
         for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
             const u32 r = pairs[i].major - row0;
-            if (r < n_rows) atomicAdd(&cnt[r], 1u);
-            else atomicOr(bad_out, DXB_RANGE);
+            if (r >= n_rows) atomicOr(bad_out, DXB_RANGE);
+            else if (rr.has(r)) atomicAdd(&cnt[r], 1u);
         }
     }
 }
 
 __global__ void __launch_bounds__(256) k_pairsw_scatter(const DxPeers X, const DxLayout L, const DxLocal* __restrict__ loc, const DevSizes* __restrict__ ds,
-                                                         u32* __restrict__ cursor, u64* __restrict__ entries, double* __restrict__ w_emit)
+                                                         u32* __restrict__ cursor, u64* __restrict__ entries, double* __restrict__ w_emit, const RowRange rr)
 {
     if (!ds->ok) return;
     const u32 row0 = loc->row0, n_rows = loc->n_rows;
@@ -667,8 +667,10 @@ __global__ void __launch_bounds__(256) k_pairsw_scatter(const DxPeers X, const D
         for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
             const DistPairW p = pairs[i];
             const u32 r = p.major - row0;
-            w_emit[off + i] = p.w;
-            if (r < n_rows) entries[atomicAdd(&cursor[r], 1u)] = Ent64::make(Ent32::minor(p.entry), Ent32::dir(p.entry), off + i);
+            if (r < n_rows && rr.has(r)) {
+                w_emit[off + i] = p.w;
+                entries[atomicAdd(&cursor[r], 1u)] = Ent64::make(Ent32::minor(p.entry), Ent32::dir(p.entry), off + i);
+            }
         }
     }
 }

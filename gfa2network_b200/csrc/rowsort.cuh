@@ -4,7 +4,8 @@
 // radix sort of (row, col) keys the build is a counting sort by row followed by an in-row sort:
 //   k_rows_count     one atomic per triplet into cnt[major]                       (histogram)
 //   exclusive scan   cnt -> rowptr + cursors; rows longer than RS_SMALL are listed on the way (common.cuh)
-//   k_rows_scatter   entry (minor, dir[, emission index]) -> atomicAdd(cursor[major]) (any order inside a row)
+//   k_rows_scatter_flat / k_edges_scatter_flat   entry (minor, dir[, emission index]) -> atomicAdd(cursor[major]) (any order inside a
+//                    row), one pass per row range when the row arrays are far larger than L2 (RowRange)
 //   k_rows_big       rows longer than RS_SMALL are sorted in place by a whole CTA (bitonic; rare)
 //   k_rows_sort      one CTA per chunk of RF_ROWS consecutive rows, one lane per row: the chunk's entries
 //                    are staged in shared memory (coalesced), every row is sorted -- rows of <= 16
@@ -55,6 +56,15 @@ struct Ent32 {  // unweighted builds: every weight is 1.0, node IDs are below 2^
     static __device__ __forceinline__ u32 t(u32) { return 0; }
 };
 
+// Row range of one bucketing pass.  When the row histogram, the cursors and the entries together are far
+// larger than L2, the count / scatter kernels run once per range of majors (every pass re-reads the edge
+// records, a sequential stream, and touches only its slice of the random-access arrays, which then stays
+// L2-resident) instead of spraying partial sectors over hundreds of megabytes of DRAM.
+struct RowRange {
+    u32 lo, n;  // majors [lo, lo + n)
+    __device__ __forceinline__ bool has(u32 major) const { return major - lo < n; }
+};
+
 // Entries of one edge record:  g(major, minor, dir, t)
 //   sym == 0: one entry per triplet, major = row (CSR) or col (CSC)
 //   sym == 1: two entries per triplet: (row, col, dir 0) and (col, row, dir 1)   [max(S, S^T)]
@@ -91,7 +101,8 @@ __device__ __forceinline__ void record_entries_t(const u32 (&id)[4], u32 t0, int
 #define EF_BATCH 4
 template <int TPE>
 __global__ void __launch_bounds__(256) k_edges_count_flat(u32* __restrict__ edge_slots, const u32* __restrict__ slot_id,
-                                                           const DevSizes* __restrict__ ds, int sym, int csc, u32* __restrict__ cnt)
+                                                           const DevSizes* __restrict__ ds, int sym, int csc, u32* __restrict__ cnt,
+                                                           const RowRange rr, int translate)
 {
     constexpr int SPE = TPE == 4 ? 4 : 2;
     if (!ds->ok) return;
@@ -113,20 +124,24 @@ __global__ void __launch_bounds__(256) k_edges_count_flat(u32* __restrict__ edge
                 }
             }
         }
+        if (translate) {  // first pass: table slots -> node IDs, left in place for the later passes
 #pragma unroll
-        for (int u = 0; u < EF_BATCH; u++) {
-            if (e0 + u * stride < E) {
+            for (int u = 0; u < EF_BATCH; u++) {
+                if (e0 + u * stride < E) {
 #pragma unroll
-                for (int k = 0; k < SPE; k++) id[u][k] = slot_id[id[u][k]];
+                    for (int k = 0; k < SPE; k++) id[u][k] = slot_id[id[u][k]];
+                }
             }
         }
 #pragma unroll
         for (int u = 0; u < EF_BATCH; u++) {
             const u32 e = e0 + u * stride;
             if (e < E) {
-                if (SPE == 4) reinterpret_cast<uint4*>(edge_slots)[e] = make_uint4(id[u][0], id[u][1], id[u][2], id[u][3]);
-                else reinterpret_cast<uint2*>(edge_slots)[e] = make_uint2(id[u][0], id[u][1]);
-                record_entries_t<TPE>(id[u], 0u, sym, csc, [&](u32 major, u32, u32, u32) { atomicAdd(&cnt[major], 1u); });
+                if (translate) {
+                    if (SPE == 4) reinterpret_cast<uint4*>(edge_slots)[e] = make_uint4(id[u][0], id[u][1], id[u][2], id[u][3]);
+                    else reinterpret_cast<uint2*>(edge_slots)[e] = make_uint2(id[u][0], id[u][1]);
+                }
+                record_entries_t<TPE>(id[u], 0u, sym, csc, [&](u32 major, u32, u32, u32) { if (rr.has(major)) atomicAdd(&cnt[major], 1u); });
             }
         }
     }
@@ -134,7 +149,7 @@ __global__ void __launch_bounds__(256) k_edges_count_flat(u32* __restrict__ edge
 
 template <int TPE>
 __global__ void __launch_bounds__(256) k_edges_scatter_flat(const u32* __restrict__ edge_ids, const DevSizes* __restrict__ ds, int sym, int csc,
-                                                             u32* __restrict__ cursor, u32* __restrict__ entries)
+                                                             u32* __restrict__ cursor, u32* __restrict__ entries, const RowRange rr)
 {
     constexpr int SPE = TPE == 4 ? 4 : 2;
     if (!ds->ok) return;
@@ -160,7 +175,7 @@ __global__ void __launch_bounds__(256) k_edges_scatter_flat(const u32* __restric
         for (int u = 0; u < EF_BATCH; u++) {
             if (e0 + u * stride < E)
                 record_entries_t<TPE>(id[u], 0u, sym, csc, [&](u32 major, u32 minor, u32 dir, u32) {
-                    entries[atomicAdd(&cursor[major], 1u)] = Ent32::make(minor, dir, 0u);
+                    if (rr.has(major)) entries[atomicAdd(&cursor[major], 1u)] = Ent32::make(minor, dir, 0u);
                 });
         }
     }
@@ -168,10 +183,12 @@ __global__ void __launch_bounds__(256) k_edges_scatter_flat(const u32* __restric
 
 // histogram of majors; translates edge_slots to node IDs in place and lays the weights out in emission
 // order (w_emit[t]) when there are any
-__global__ void __launch_bounds__(256) k_rows_count(const EmitParams E, int sym, int csc, u32* __restrict__ cnt, double* __restrict__ w_emit)
+__global__ void __launch_bounds__(256) k_rows_count(const EmitParams E, int sym, int csc, u32* __restrict__ cnt, double* __restrict__ w_emit,
+                                                     const RowRange rr, u32* __restrict__ emit_t0)
 {
     for_each_edge(E, [&](u32 stored, u32 t0, const u32 (&id)[4]) {
-        record_entries(id, E.tpe, t0, sym, csc, [&](u32 major, u32, u32, u32) { atomicAdd(&cnt[major], 1u); });
+        if (emit_t0) emit_t0[stored] = t0;  // emission index of the record's first triplet, for the flat scatter passes
+        record_entries(id, E.tpe, t0, sym, csc, [&](u32 major, u32, u32, u32) { if (rr.has(major)) atomicAdd(&cnt[major], 1u); });
         if (w_emit) {
             const double w = E.edge_w[stored];
             for (int k = 0; k < E.tpe; k++) w_emit[t0 + k] = w;
@@ -181,14 +198,42 @@ __global__ void __launch_bounds__(256) k_rows_count(const EmitParams E, int sym,
 
 // cursor[major] starts at rowptr[major]; one atomicAdd hands out the entry's position inside the row's
 // range (order inside the range is arbitrary; the in-row sort restores a total order)
-template <class ENT>
-__global__ void __launch_bounds__(256) k_rows_scatter(const EmitParams E, int sym, int csc, u32* __restrict__ cursor, typename ENT::type* __restrict__ entries)
+// Weighted scatter as a flat pass over the stored edge records (node IDs in place, emission index of every
+// record from emit_t0): no per-tile bookkeeping, so a pass per row range is cheap (see RowRange).
+template <int TPE>
+__global__ void __launch_bounds__(256) k_rows_scatter_flat(const u32* __restrict__ edge_ids, const u32* __restrict__ emit_t0, const DevSizes* __restrict__ ds,
+                                                            int sym, int csc, u32* __restrict__ cursor, u64* __restrict__ entries, const RowRange rr)
 {
-    for_each_edge(E, [&](u32, u32 t0, const u32 (&id)[4]) {
-        record_entries(id, E.tpe, t0, sym, csc, [&](u32 major, u32 minor, u32 dir, u32 t) {
-            entries[atomicAdd(&cursor[major], 1u)] = ENT::make(minor, dir, t);
-        });
-    });
+    constexpr int SPE = TPE == 4 ? 4 : 2;
+    if (!ds->ok) return;
+    const u32 E = ds->E;
+    const u32 stride = gridDim.x * blockDim.x;
+    for (u32 e0 = blockIdx.x * blockDim.x + threadIdx.x; e0 < E; e0 += stride * EF_BATCH) {
+        u32 id[EF_BATCH][4], t0[EF_BATCH];
+#pragma unroll
+        for (int u = 0; u < EF_BATCH; u++) {
+            const u32 e = e0 + u * stride;
+            id[u][0] = id[u][1] = id[u][2] = id[u][3] = 0;
+            t0[u] = 0;
+            if (e < E) {
+                if (SPE == 4) {
+                    const uint4 q = reinterpret_cast<const uint4*>(edge_ids)[e];
+                    id[u][0] = q.x; id[u][1] = q.y; id[u][2] = q.z; id[u][3] = q.w;
+                } else {
+                    const uint2 q = reinterpret_cast<const uint2*>(edge_ids)[e];
+                    id[u][0] = q.x; id[u][1] = q.y;
+                }
+                t0[u] = emit_t0[e];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < EF_BATCH; u++) {
+            if (e0 + u * stride < E)
+                record_entries_t<TPE>(id[u], t0[u], sym, csc, [&](u32 major, u32 minor, u32 dir, u32 t) {
+                    if (rr.has(major)) entries[atomicAdd(&cursor[major], 1u)] = Ent64::make(minor, dir, t);
+                });
+        }
+    }
 }
 
 // same two steps for caller-provided COO arrays (g2n_coo_to_compressed)

@@ -292,3 +292,19 @@ def test_long_names_across_shards(mode):
         out, _ = _build(ranks, shards, True, **mode)
         assert all(rc == _capi.G2N_OK for rc, _ in out)
         _check(*_assemble(ranks, out, "csr"), text, mode)
+
+
+@pytest.mark.parametrize("mode", [dict(), dict(weight_tag="RC", bidirected=True)], ids=str)
+def test_slab_row_range_passes(monkeypatch, mode):
+    """The slab's bucketing kernels in several row-range passes (forced)."""
+    from gfa2network_b200 import _capi
+    from gfa2network_b200 import dist as D
+    from gfa2network_b200.synth import synth_gfa
+
+    monkeypatch.setenv("G2N_DBG_ROWPASS", "5")
+    text = synth_gfa(20_000, 60_000, seed=8, kind=2 if mode else 1)
+    G = 3
+    ranks = [D.LocalRank(0, r, G) for r in range(G)]
+    out, _ = _build(ranks, _shards(text, G), False, **mode)
+    assert all(rc == _capi.G2N_OK for rc, _ in out)
+    _check(*_assemble(ranks, out, "csr"), text, mode)

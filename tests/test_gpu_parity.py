@@ -228,6 +228,27 @@ def test_conditional_first_appearance_variant(monkeypatch):
         assert nodes == onodes
 
 
+@pytest.mark.parametrize("passes", ["3", "64"])
+def test_row_range_passes_variant(monkeypatch, passes):
+    """The bucketing kernels run once per slice of rows when the row arrays are far larger than L2 (rowsort.cuh:
+    RowRange); forced on small inputs: same results in every mode, on repeated (speculative) builds and after a convert."""
+    from gfa2network_b200 import convert_format, parse_gfa
+    from gfa2network_b200.synth import synth_gfa
+    from oracle.oracle import oracle_convert_format, oracle_parse_gfa
+
+    monkeypatch.setenv("G2N_DBG_ROWPASS", passes)
+    plain = synth_gfa(30_000, 90_000, seed=44, kind=1, n_paths=1, interleave=7)
+    wtd = synth_gfa(10_000, 30_000, seed=45, kind=2)
+    for text, mode in ((plain, dict()), (plain, dict(directed=False)), (plain, dict(bidirected=True)), (plain, dict(asymmetric=True)),
+                       (wtd, dict(bidirected=True, weight_tag="RC")), (wtd, dict(weight_tag="RC")), (wtd, dict(weight_tag="RC", asymmetric=True))):
+        for rep in range(2):
+            A = parse_gfa(text, build_graph=False, build_matrix=True, **mode)
+            B = oracle_parse_gfa(text, **mode)
+            _same(A, B, f"rowpass {mode} rep {rep}")
+            for fmt in ("csr", "csc"):
+                _same(convert_format(A, fmt), oracle_convert_format(B, fmt), f"rowpass {mode} {fmt}")
+
+
 def test_unaligned_device_text():
     """A device pointer that is not 16-byte aligned (a slice of a larger tensor) is accepted."""
     import torch
