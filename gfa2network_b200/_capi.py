@@ -23,7 +23,7 @@ EXPORTS = [
     "g2n_abi_version", "g2n_create", "g2n_destroy", "g2n_set_stream", "g2n_host_alloc", "g2n_host_free",
     "g2n_build", "g2n_build_file", "g2n_convert", "g2n_sizes", "g2n_fetch_matrix", "g2n_names_bytes", "g2n_fetch_names", "g2n_device_result",
     "g2n_status", "g2n_last_error", "g2n_coo_to_compressed", "g2n_set_profile", "g2n_set_speculation", "g2n_kernel_times", "g2n_nodes_tsv_bytes", "g2n_fetch_nodes_tsv",
-    "g2n_edge_list_bytes", "g2n_fetch_edge_list",
+    "g2n_edge_list_bytes", "g2n_fetch_edge_list", "g2n_bfs", "g2n_levels_reduce", "g2n_fetch_levels",
     "g2n_dist_init", "g2n_dist_probe", "g2n_dist_plan", "g2n_dist_local_mem", "g2n_dist_set_peers", "g2n_dist_open_peers",
     "g2n_dist_close_peers", "g2n_dist_stage", "g2n_dist_finish",
 ]
@@ -125,6 +125,9 @@ def load():
     lib.g2n_nodes_tsv_bytes.argtypes = [vp, C.POINTER(u64)]
     lib.g2n_fetch_nodes_tsv.argtypes = [vp, vp]
     lib.g2n_kernel_times.argtypes = [vp, C.POINTER(KTime), C.c_int]
+    lib.g2n_bfs.argtypes = [vp, vp, u64, i32, i32]
+    lib.g2n_levels_reduce.argtypes = [vp, i32, vp, u64, vp]
+    lib.g2n_fetch_levels.argtypes = [vp, i32, vp]
     lib.g2n_edge_list_bytes.argtypes = [vp, C.POINTER(u64)]
     lib.g2n_fetch_edge_list.argtypes = [vp, vp]
     _lib = lib

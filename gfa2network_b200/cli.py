@@ -1,6 +1,7 @@
-"""``gfa2network convert`` (gfa2network/cli.py:22-135, 193-250) and ``gfa2network export --format edge-list``
-(cli.py:137-150, 264-281) over the GPU path.  Same flags, defaults, stdout/stderr strings and exit
-behaviour; the sub-commands and formats that are not on the GFA->matrix path are not provided here."""
+"""``gfa2network convert`` (gfa2network/cli.py:22-135, 193-250), ``export --format edge-list`` (cli.py:137-150,
+264-281), ``distance --path`` (cli.py:161-175, 302-334) and ``distance-matrix`` (cli.py:177-190, 335-350) over the
+GPU path.  Same flags, defaults, stdout/stderr strings and exit behaviour; the sub-commands and formats that need
+the NetworkX object graph (``stats``, ``distance --seq``, graph exports) are not provided here."""
 from __future__ import annotations
 
 import argparse
@@ -47,6 +48,22 @@ def _parser() -> argparse.ArgumentParser:
     e.add_argument("--bidirected", action="store_true")
     e.add_argument("--keep-directed-bidir", action="store_true", help="Keep original directed bidirected behaviour")
     e.add_argument("--output", help="Output path", default="-")
+    d = sub.add_parser("distance", help="Compute distances")
+    d.add_argument("gfa", help="Input *.gfa* file")
+    g3 = d.add_mutually_exclusive_group(required=True)
+    g3.add_argument("--seq", nargs=2, metavar=("SEQ_A", "SEQ_B"))
+    g3.add_argument("--path", nargs=2, metavar=("PATH_A", "PATH_B"))
+    g4 = d.add_mutually_exclusive_group()
+    g4.add_argument("--directed", dest="directed", action="store_true", default=True)
+    g4.add_argument("--undirected", dest="directed", action="store_false")
+    d.add_argument("--backend", choices=["networkx", "igraph"], default="networkx", help="Graph backend to use")
+    d.add_argument("--verbose", action="store_true")
+    m = sub.add_parser("distance-matrix", help="Pairwise distances between paths")
+    m.add_argument("gfa", help="Input *.gfa* file")
+    m.add_argument("-o", "--output", required=True, help="Write matrix to PATH (.csv|.npy|.npz)")
+    m.add_argument("--method", choices=["min", "mean"], default="min")
+    m.add_argument("--backend", choices=["networkx", "igraph"], default="networkx", help="Graph backend to use")
+    m.add_argument("--verbose", action="store_true")
     return ap
 
 
@@ -59,6 +76,32 @@ def main(argv: list[str] | None = None) -> None:
         from .export import export_edge_list
 
         export_edge_list(args.gfa, bidirected=args.bidirected, output=args.output)
+        return
+    if args.cmd == "distance":
+        if args.seq:  # needs the node sequences of the object graph (cli.py:303-316)
+            raise NotImplementedError("distance --seq needs the NetworkX graph half of the reference (store_seq)")
+        if args.backend != "networkx":
+            raise NotImplementedError("backend='igraph' is outside the B200 path")
+        from .analysis import genome_distance, load_paths
+
+        paths = load_paths(args.gfa, raw_bytes=args.raw_bytes_id)  # cli.py:318
+        name_a, name_b = args.path
+        try:
+            nodes_a = paths[name_a if not args.raw_bytes_id else name_a.encode()]
+            nodes_b = paths[name_b if not args.raw_bytes_id else name_b.encode()]
+        except KeyError as exc:  # cli.py:325-329
+            msg = exc.args[0]
+            raise SystemExit(f"unknown path: {msg.decode() if isinstance(msg, bytes) else msg}") from exc
+        print(genome_distance(args.gfa, nodes_a, nodes_b, directed=args.directed, raw_bytes_id=args.raw_bytes_id))  # cli.py:330-334
+        return
+    if args.cmd == "distance-matrix":
+        from .analysis import genome_distance_matrix
+
+        M = genome_distance_matrix(args.gfa, method=args.method, raw_bytes_id=args.raw_bytes_id, backend=args.backend, verbose=args.verbose)
+        try:
+            save_matrix(M, Path(args.output), verbose=args.verbose, max_dense_gb=args.max_dense_gb)  # cli.py:343-350
+        except MemoryError as exc:
+            raise SystemExit(str(exc)) from exc
         return
     if not args.graph and not args.matrix:
         ap.error("convert requires --graph or --matrix")  # cli.py:194-195

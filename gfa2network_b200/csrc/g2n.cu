@@ -21,6 +21,7 @@
 
 #include "../../include/g2n.h"
 #include "dist.cuh"
+#include "bfs.cuh"
 
 using namespace g2n;
 
@@ -71,6 +72,9 @@ struct g2n_handle {
     DevBuf text, defer, edge_slots, edge_w, longs, tile_info, tile_base, wprefix, slot_id, id2slot, name_len, name_off, names;
     DevBuf rowptr, cursor, entries, w_emit, biglist, ucnt, indptr, indices, data, row, col, scan_state;
     DevBuf up_row, up_col, up_data, tsv, tsv_off, el_len, el_off, el_text, emit_t0;
+    DevBuf bfs_levels, bfs_q0, bfs_q1, bfs_ctl, bfs_nodes, bfs_out;  // distances on the resident CSR (bfs.cuh)
+    int bfs_slots = 0;
+    u64 bfs_n = 0;
     bool el_ready = false;
     u64 el_bytes = 0;
     bool tsv_ready = false;
@@ -595,7 +599,7 @@ void g2n_destroy(g2n_handle* h)
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->text, &h->zearly, &h->zids, &h->zrows, &h->defer, &h->edge_slots, &h->edge_w, &h->longs, &h->tile_info, &h->tile_base, &h->wprefix,
                       &h->slot_id, &h->id2slot, &h->name_len, &h->name_off, &h->names, &h->rowptr, &h->cursor, &h->entries, &h->w_emit, &h->biglist, &h->ucnt, &h->indptr, &h->indices, &h->data, &h->row, &h->col,
-                      &h->scan_state, &h->up_row, &h->up_col, &h->up_data, &h->tsv, &h->tsv_off, &h->el_len, &h->el_off, &h->el_text, &h->emit_t0, &h->dx_arena, &h->dx_ctl, &h->dx_loc, &h->dx_zg, &h->dx_gslot, &h->dx_gpos, &h->dx_sent, &h->dx_tcnt, &h->dx_toff};
+                      &h->scan_state, &h->up_row, &h->up_col, &h->up_data, &h->tsv, &h->tsv_off, &h->el_len, &h->el_off, &h->el_text, &h->emit_t0, &h->bfs_levels, &h->bfs_q0, &h->bfs_q1, &h->bfs_ctl, &h->bfs_nodes, &h->bfs_out, &h->dx_arena, &h->dx_ctl, &h->dx_loc, &h->dx_zg, &h->dx_gslot, &h->dx_gpos, &h->dx_sent, &h->dx_tcnt, &h->dx_toff};
     if (h->dx_inited) g2n_dist_close_peers(h);
     for (DevBuf* b : bufs) b->release();
     if (h->h_loc) cudaFreeHost(h->h_loc);
@@ -1395,6 +1399,89 @@ int g2n_fetch_edge_list(g2n_handle* h, uint8_t* out)
     int rc = build_edge_list(h);
     if (rc) return rc;
     if (h->el_bytes) CK(cudaMemcpyAsync(out, h->el_text.p, h->el_bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return G2N_OK;
+}
+
+// ---- distances on the resident CSR (analysis.py:116-161, 180-272)
+static int bfs_check(g2n_handle* h, int32_t slot)
+{
+    if (!h->built || h->slab_mode || h->result_format == G2N_FMT_COO) { h->err = "distances need the CSR/CSC result of a single-GPU build"; return G2N_ERR_INVALID; }
+    if (slot < 0 || slot >= h->bfs_slots || h->bfs_n != h->n_nodes) { h->err = "no such level slot (g2n_bfs first)"; return G2N_ERR_INVALID; }
+    return G2N_OK;
+}
+
+int g2n_bfs(g2n_handle* h, const int32_t* sources, uint64_t n_sources, int32_t slot, int32_t n_slots)
+{
+    if (!h || (!sources && n_sources) || n_slots < 1 || slot < 0 || slot >= n_slots) return G2N_ERR_INVALID;
+    if (!h->built || h->slab_mode || h->result_format == G2N_FMT_COO) { h->err = "distances need the CSR/CSC result of a single-GPU build"; return G2N_ERR_INVALID; }
+    CK(cudaSetDevice(h->device));
+    const u64 n = h->n_nodes;
+    if (h->bfs_slots != n_slots || h->bfs_n != n) {
+        CK(h->bfs_levels.ensure((size_t)n_slots * (n + 1) * sizeof(int32_t)));
+        h->bfs_slots = n_slots;
+        h->bfs_n = n;
+    }
+    CK(h->bfs_q0.ensure((n + 1) * sizeof(u32)));
+    CK(h->bfs_q1.ensure((n + 1) * sizeof(u32)));
+    CK(h->bfs_ctl.ensure(sizeof(BfsCtl)));
+    CK(h->bfs_nodes.ensure((n_sources + 1) * sizeof(int32_t)));
+    int32_t* level = h->bfs_levels.as<int32_t>() + (size_t)slot * (n + 1);
+    CK(cudaMemsetAsync(level, 0xFF, (n + 1) * sizeof(int32_t), h->stream));
+    CK(cudaMemsetAsync(h->bfs_ctl.p, 0, sizeof(BfsCtl), h->stream));
+    if (n == 0 || n_sources == 0) return G2N_OK;
+    CK(cudaMemcpyAsync(h->bfs_nodes.p, sources, n_sources * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    { KScope ks(h, "k_bfs_seed"); k_bfs_seed<<<grid_for(n_sources, 256), 256, 0, h->stream>>>(h->bfs_nodes.as<int32_t>(), n_sources, (u32)n, level, h->bfs_q0.as<u32>(), h->bfs_ctl.as<BfsCtl>()); }
+    CK(cudaGetLastError());
+    {
+        KScope ks(h, "k_bfs_gang");
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bfs_gang, 256, 0));
+        if (per_sm < 1) { h->err = "k_bfs_gang cannot be made co-resident"; return G2N_ERR_INTERNAL; }
+        const dim3 grid((unsigned)(G2N_SM_COUNT * (per_sm > 4 ? 4 : per_sm)));
+        const int32_t* indptr = h->indptr.as<int32_t>();
+        const int32_t* indices = h->indices.as<int32_t>();
+        u32 *q0 = h->bfs_q0.as<u32>(), *q1 = h->bfs_q1.as<u32>();
+        BfsCtl* ctl = h->bfs_ctl.as<BfsCtl>();
+        void* args[] = {(void*)&indptr, (void*)&indices, (void*)&level, (void*)&q0, (void*)&q1, (void*)&ctl};
+        CK(cudaLaunchCooperativeKernel((const void*)k_bfs_gang, grid, dim3(256), args, 0, h->stream));
+    }
+    return G2N_OK;
+}
+
+int g2n_levels_reduce(g2n_handle* h, int32_t slot, const int32_t* nodes, uint64_t n_nodes, int64_t* out3)
+{
+    if (!h || !out3 || (!nodes && n_nodes)) return G2N_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    int rc = bfs_check(h, slot);
+    if (rc) return rc;
+    const u64 n = h->n_nodes;
+    CK(h->bfs_nodes.ensure((n_nodes + 1) * sizeof(int32_t)));
+    CK(h->bfs_out.ensure(4 * sizeof(long long)));
+    const long long init[3] = {0x7fffffffffffffffLL, 0, 0};
+    CK(cudaMemcpyAsync(h->bfs_out.p, init, sizeof init, cudaMemcpyHostToDevice, h->stream));
+    if (n_nodes) {
+        CK(cudaMemcpyAsync(h->bfs_nodes.p, nodes, n_nodes * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        KScope ks(h, "k_levels_reduce");
+        k_levels_reduce<<<grid_for(n_nodes, 256), 256, 0, h->stream>>>(h->bfs_levels.as<int32_t>() + (size_t)slot * (n + 1), h->bfs_nodes.as<int32_t>(), n_nodes, (u32)n, h->bfs_out.as<long long>());
+    }
+    long long res[3];
+    CK(cudaMemcpyAsync(res, h->bfs_out.p, sizeof res, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    out3[0] = res[2] ? res[0] : -1;
+    out3[1] = res[1];
+    out3[2] = res[2];
+    return G2N_OK;
+}
+
+int g2n_fetch_levels(g2n_handle* h, int32_t slot, int32_t* out)
+{
+    if (!h || !out) return G2N_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    int rc = bfs_check(h, slot);
+    if (rc) return rc;
+    const u64 n = h->n_nodes;
+    if (n) CK(cudaMemcpyAsync(out, h->bfs_levels.as<int32_t>() + (size_t)slot * (n + 1), n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return G2N_OK;
 }

@@ -172,6 +172,16 @@ int g2n_fetch_nodes_tsv(g2n_handle *h, uint8_t *out);
 int g2n_edge_list_bytes(g2n_handle *h, uint64_t *out);
 int g2n_fetch_edge_list(g2n_handle *h, uint8_t *out);
 
+/* Distances on the resident CSR/CSC result of the last single-GPU build (analysis.py:116-161, 180-272: the
+ * reference runs networkx.multi_source_dijkstra_path_length on the graph it builds WITHOUT a weight tag, i.e.
+ * hop counts along out-edges).  g2n_bfs: multi-source breadth-first search from `sources` (node IDs) into
+ * level slot `slot` of `n_slots` (all levels of one search run inside one cooperative kernel);
+ * g2n_levels_reduce: out3 = {min level or -1, sum of levels, count} over the reachable nodes of a node list
+ * (duplicates count as often as they occur); g2n_fetch_levels: the n_nodes hop counts of a slot, -1 = unreachable. */
+int g2n_bfs(g2n_handle *h, const int32_t *sources, uint64_t n_sources, int32_t slot, int32_t n_slots);
+int g2n_levels_reduce(g2n_handle *h, int32_t slot, const int32_t *nodes, uint64_t n_nodes, int64_t *out3);
+int g2n_fetch_levels(g2n_handle *h, int32_t slot, int32_t *out);
+
 /* Device pointers of the resident result (for device-side consumers / benchmarks). */
 int g2n_device_result(g2n_handle *h, void **a0, void **a1, void **data);
 

@@ -224,3 +224,73 @@ def oracle_edge_list(text, *, bidirected=False):
                 break
         lines.append(u + b"\t" + v + b"\n")
     return b"".join(lines), exc, warns
+
+
+def oracle_load_paths(text, *, raw_bytes=False):
+    """analysis.py:164-177 over parser.py:114-134, 229-247, 343-361: P / O records, later names overwrite."""
+    buf = _as_u8(text).tobytes()
+    paths = {}
+    for line in buf.split(b"\n"):
+        if not line or line[0] not in b"PO":
+            continue
+        fields = line.split(b"\t")
+        if fields[0] not in (b"P", b"O"):
+            continue
+        if len(fields) < 3:
+            raise ValueError(f"Malformed {fields[0].decode()} record")
+        segs = []
+        for entry in fields[2].split(b","):
+            seg = entry[:-1] if entry.endswith((b"+", b"-")) else entry
+            segs.append(seg if raw_bytes else seg.decode("ascii"))
+        paths[fields[1] if raw_bytes else fields[1].decode("ascii")] = segs
+    return paths
+
+
+def oracle_distance_matrix(text, method="min"):
+    """analysis.py:180-272, CPU oracle: (labels, matrix).  The reference's graph is the DiGraph of
+    parse_gfa(build_graph=True) without weights (builders.py:141, 246-256): nodes and out-edges are those of
+    the asymmetric COO the matrix half emits, every edge counts 1 -- multi-source BFS with SciPy's csgraph."""
+    from scipy.sparse.csgraph import dijkstra
+
+    buf = _as_u8(text)
+    A, nodes = oracle_parse_gfa(buf, asymmetric=True, return_node_list=True)  # raises / warns like the reference's parser
+    paths = oracle_load_paths(buf)
+    index = {n: i for i, n in enumerate(nodes)}
+    S = A.tocsr()
+    S.data[:] = 1.0
+    names = list(paths)
+    n = len(names)
+    lengths = []
+    for name in names:
+        src = []
+        for s in paths[name]:
+            if s not in index:
+                import networkx as nx
+
+                raise nx.NodeNotFound(f"Node {s} not found in graph")
+            src.append(index[s])
+        if S.shape[0] and src:
+            lengths.append(dijkstra(S, directed=True, indices=sorted(set(src)), unweighted=True, min_only=True))
+        else:
+            lengths.append(np.full(S.shape[0], np.inf))
+    M = np.zeros((n, n))
+    for i in range(n):
+        for j in range(i, n):
+            if i == j:
+                d = 0.0
+            elif method == "min":
+                ds = [lengths[i][index[v]] for v in paths[names[j]] if v in index and np.isfinite(lengths[i][index[v]])]
+                d = min(ds) if ds else float("inf")
+            else:
+                tot, cnt = 0.0, 0
+                for u in paths[names[i]]:
+                    if u in index and np.isfinite(lengths[j][index[u]]):
+                        tot += lengths[j][index[u]]
+                        cnt += 1
+                for v in paths[names[j]]:
+                    if v in index and np.isfinite(lengths[i][index[v]]):
+                        tot += lengths[i][index[v]]
+                        cnt += 1
+                d = tot / cnt if cnt else float("inf")
+            M[i, j] = M[j, i] = d
+    return names, M
