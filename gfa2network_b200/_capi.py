@@ -24,6 +24,7 @@ EXPORTS = [
     "g2n_build", "g2n_build_file", "g2n_convert", "g2n_sizes", "g2n_fetch_matrix", "g2n_names_bytes", "g2n_fetch_names", "g2n_device_result",
     "g2n_status", "g2n_last_error", "g2n_coo_to_compressed", "g2n_set_profile", "g2n_set_speculation", "g2n_kernel_times", "g2n_nodes_tsv_bytes", "g2n_fetch_nodes_tsv",
     "g2n_edge_list_bytes", "g2n_fetch_edge_list", "g2n_bfs", "g2n_levels_reduce", "g2n_fetch_levels",
+    "g2n_paths_load", "g2n_path_info", "g2n_path_bfs", "g2n_path_reduce", "g2n_fetch_path_nodes", "g2n_fetch_text",
     "g2n_dist_init", "g2n_dist_probe", "g2n_dist_plan", "g2n_dist_local_mem", "g2n_dist_set_peers", "g2n_dist_open_peers",
     "g2n_dist_close_peers", "g2n_dist_stage", "g2n_dist_finish",
 ]
@@ -55,6 +56,11 @@ class DistResult(C.Structure):
     _fields_ = [("bad", C.c_uint64), ("n_global", C.c_uint64), ("row0", C.c_uint64), ("n_rows", C.c_uint64), ("nnz", C.c_uint64),
                 ("n_recv", C.c_uint64), ("n_first", C.c_uint64), ("id0", C.c_uint64), ("n_keys", C.c_uint64), ("n_records", C.c_uint64),
                 ("n_edge_records", C.c_uint64), ("keys_to", C.c_uint64 * 8), ("pairs_to", C.c_uint64 * 8)]
+
+
+class PathInfo(C.Structure):
+    _fields_ = [("line_offset", C.c_uint64), ("name_offset", C.c_uint64), ("n_entries", C.c_uint64), ("missing_entry", C.c_int64),
+                ("missing_offset", C.c_uint64), ("name_len", C.c_uint32), ("missing_len", C.c_uint32)]
 
 
 class Diag(C.Structure):
@@ -125,6 +131,12 @@ def load():
     lib.g2n_nodes_tsv_bytes.argtypes = [vp, C.POINTER(u64)]
     lib.g2n_fetch_nodes_tsv.argtypes = [vp, vp]
     lib.g2n_kernel_times.argtypes = [vp, C.POINTER(KTime), C.c_int]
+    lib.g2n_paths_load.argtypes = [vp, C.POINTER(u64)]
+    lib.g2n_path_info.argtypes = [vp, u64, C.POINTER(PathInfo)]
+    lib.g2n_path_bfs.argtypes = [vp, u64, i32, i32]
+    lib.g2n_path_reduce.argtypes = [vp, i32, u64, vp]
+    lib.g2n_fetch_path_nodes.argtypes = [vp, u64, vp]
+    lib.g2n_fetch_text.argtypes = [vp, u64, u64, vp]
     lib.g2n_bfs.argtypes = [vp, vp, u64, i32, i32]
     lib.g2n_levels_reduce.argtypes = [vp, i32, vp, u64, vp]
     lib.g2n_fetch_levels.argtypes = [vp, i32, vp]

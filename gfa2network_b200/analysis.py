@@ -72,14 +72,15 @@ def load_paths(path, *, raw_bytes: bool = False):
 class _Graph:
     """The device-resident adjacency of one file plus the name -> node ID map (the reference's ``G``)."""
 
-    def __init__(self, path, *, directed: bool = True, raw_bytes_id: bool = False, verbose: bool = False, device=None):
+    def __init__(self, path, *, directed: bool = True, raw_bytes_id: bool = False, verbose: bool = False, device=None, want_index: bool = True):
         # DiGraph: rows = out-neighbours = the asymmetric CSR; Graph: the undirected build (builders.py:138-142, 226-228)
         kw = dict(asymmetric=True) if directed else dict(directed=False)
-        self.A, nodes = parse_gfa(path, build_graph=False, build_matrix=True, return_node_list=True, raw_bytes_id=raw_bytes_id,
-                                  matrix_format="csr", verbose=verbose, device=device, **kw)
+        res = parse_gfa(path, build_graph=False, build_matrix=True, return_node_list=want_index, raw_bytes_id=raw_bytes_id,
+                        matrix_format="csr", verbose=verbose, device=device, **kw)
+        self.A, nodes = res if want_index else (res, [])
         self.handle = self.A._g2n_session.handle
-        self.index = {n: i for i, n in enumerate(nodes)}
-        self.n_slots = 0
+        self._keep = path  # a device tensor given as the source must outlive the searches (the text is read in place)
+        self.index = {n: i for i, n in enumerate(nodes)}  # name -> node ID (callers that bring their own node names)
 
     def ids(self, names, *, strict: bool) -> np.ndarray:
         out = []
@@ -129,30 +130,81 @@ def genome_distance(gfa_path, nodes_a, nodes_b, *, method: str = "min", directed
     return mn
 
 
+class _DevicePaths:
+    """The P / O records of the file behind a `_Graph`, resolved to node IDs on the device (csrc/paths.cuh): names and
+    entry counts come to the host, the node lists do not."""
+
+    def __init__(self, G: "_Graph", raw_bytes: bool):
+        self.G, h = G, G.handle
+        n = C.c_uint64()
+        h.check(h.lib.g2n_paths_load(h.h, C.byref(n)))
+        self.infos = []
+        for i in range(n.value):
+            info = _capi.PathInfo()
+            h.check(h.lib.g2n_path_info(h.h, i, C.byref(info)))
+            self.infos.append(info)
+        # dict semantics of analysis.py:170-176: a later record of the same name replaces the list, not the position
+        self.index: dict = {}
+        for i, info in enumerate(self.infos):
+            name = self._text(info.name_offset, info.name_len)
+            self.index[name if raw_bytes else name.decode("ascii")] = i
+        self.raw_bytes = raw_bytes
+
+    def _text(self, off: int, n: int) -> bytes:
+        h = self.G.handle
+        buf = (C.c_uint8 * max(n, 1))()
+        h.check(h.lib.g2n_fetch_text(h.h, off, n, buf))
+        return bytes(buf[:n])
+
+    def check_sources(self, i: int):
+        """nx.multi_source_dijkstra raises for the first source that is not a node (analysis.py:237-239)."""
+        info = self.infos[i]
+        if info.missing_entry >= 0:
+            name = self._text(info.missing_offset, info.missing_len)
+            raise _node_not_found(name if self.raw_bytes else name.decode("ascii"))
+
+    def bfs(self, i: int, slot: int, n_slots: int):
+        h = self.G.handle
+        h.check(h.lib.g2n_path_bfs(h.h, i, slot, n_slots))
+
+    def reduce(self, slot: int, i: int):
+        h = self.G.handle
+        out = (C.c_int64 * 3)()
+        h.check(h.lib.g2n_path_reduce(h.h, slot, i, out))
+        return int(out[0]), int(out[1]), int(out[2])
+
+    def nodes(self, i: int) -> np.ndarray:
+        h = self.G.handle
+        out = np.empty(int(self.infos[i].n_entries), dtype=np.int32)
+        h.check(h.lib.g2n_fetch_path_nodes(h.h, i, C.c_void_p(out.ctypes.data)))
+        return out
+
+
 def genome_distance_matrix(gfa_path, method: str = "min", *, raw_bytes_id: bool = False, backend: str = "networkx", verbose: bool = False, device=None):
-    """Return pairwise distances between all paths in *gfa_path* (analysis.py:180-272)."""
+    """Return pairwise distances between all paths in *gfa_path* (analysis.py:180-272).  Nothing per path entry
+    happens on the host: the records' node lists are resolved, searched from and reduced over on the device."""
     if backend != "networkx":
         raise NotImplementedError("backend='igraph' is outside the B200 path")
-    G = _Graph(gfa_path, directed=True, raw_bytes_id=raw_bytes_id, verbose=verbose, device=device)
-    paths = _split_paths(_text_bytes(gfa_path), raw_bytes_id)  # analysis.py:217 (the build above already validated the file)
-    names = list(paths)
+    G = _Graph(gfa_path, directed=True, raw_bytes_id=raw_bytes_id, verbose=verbose, device=device, want_index=False)
+    P = _DevicePaths(G, raw_bytes_id)  # analysis.py:217 (the build above already validated the file)
+    names = list(P.index)
+    recs = [P.index[k] for k in names]
     n = len(names)
     M = np.zeros((n, n), dtype=float)
     # one multi-source search per path (analysis.py:236-240), all level arrays kept in HBM
-    lists = []
-    for k, name in enumerate(names):
-        G.bfs(G.ids(paths[name], strict=True), k, max(n, 1))
-        lists.append(G.ids(paths[name], strict=False))
+    for k, r in enumerate(recs):
+        P.check_sources(r)
+        P.bfs(r, k, max(n, 1))
     for i in range(n):
         for j in range(i, n):
             if i == j:
                 dist = 0.0
             elif method == "min":
-                mn, _, cnt = G.reduce(i, lists[j])  # analysis.py:250-251
+                mn, _, cnt = P.reduce(i, recs[j])  # analysis.py:250-251
                 dist = float(mn) if cnt else float("inf")
             else:  # mean of node-to-path distances, analysis.py:252-264
-                _, s1, c1 = G.reduce(j, lists[i])
-                _, s2, c2 = G.reduce(i, lists[j])
+                _, s1, c1 = P.reduce(j, recs[i])
+                _, s2, c2 = P.reduce(i, recs[j])
                 dist = (float(s1) + float(s2)) / (c1 + c2) if (c1 + c2) else float("inf")
             M[i, j] = M[j, i] = dist
     try:

@@ -22,6 +22,9 @@
 #include "../../include/g2n.h"
 #include "dist.cuh"
 #include "bfs.cuh"
+#include "paths.cuh"
+
+#include <algorithm>
 
 using namespace g2n;
 
@@ -75,6 +78,13 @@ struct g2n_handle {
     DevBuf bfs_levels, bfs_q0, bfs_q1, bfs_ctl, bfs_nodes, bfs_out;  // distances on the resident CSR (bfs.cuh)
     int bfs_slots = 0;
     u64 bfs_n = 0;
+    // P / O records of the last build's text, resolved to node IDs on the device (paths.cuh)
+    DevBuf path_starts, path_recs, path_cnt, path_off, path_ids, path_misc;
+    std::vector<PathRec> h_paths;
+    std::vector<u64> h_path_entry0;  // n_paths + 1
+    std::vector<u64> h_path_blkoff;
+    bool paths_ready = false;
+    u64 seed_used = 0;
     bool el_ready = false;
     u64 el_bytes = 0;
     bool tsv_ready = false;
@@ -599,7 +609,7 @@ void g2n_destroy(g2n_handle* h)
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->text, &h->zearly, &h->zids, &h->zrows, &h->defer, &h->edge_slots, &h->edge_w, &h->longs, &h->tile_info, &h->tile_base, &h->wprefix,
                       &h->slot_id, &h->id2slot, &h->name_len, &h->name_off, &h->names, &h->rowptr, &h->cursor, &h->entries, &h->w_emit, &h->biglist, &h->ucnt, &h->indptr, &h->indices, &h->data, &h->row, &h->col,
-                      &h->scan_state, &h->up_row, &h->up_col, &h->up_data, &h->tsv, &h->tsv_off, &h->el_len, &h->el_off, &h->el_text, &h->emit_t0, &h->bfs_levels, &h->bfs_q0, &h->bfs_q1, &h->bfs_ctl, &h->bfs_nodes, &h->bfs_out, &h->dx_arena, &h->dx_ctl, &h->dx_loc, &h->dx_zg, &h->dx_gslot, &h->dx_gpos, &h->dx_sent, &h->dx_tcnt, &h->dx_toff};
+                      &h->scan_state, &h->up_row, &h->up_col, &h->up_data, &h->tsv, &h->tsv_off, &h->el_len, &h->el_off, &h->el_text, &h->emit_t0, &h->bfs_levels, &h->bfs_q0, &h->bfs_q1, &h->bfs_ctl, &h->bfs_nodes, &h->bfs_out, &h->path_starts, &h->path_recs, &h->path_cnt, &h->path_off, &h->path_ids, &h->path_misc, &h->dx_arena, &h->dx_ctl, &h->dx_loc, &h->dx_zg, &h->dx_gslot, &h->dx_gpos, &h->dx_sent, &h->dx_tcnt, &h->dx_toff};
     if (h->dx_inited) g2n_dist_close_peers(h);
     for (DevBuf* b : bufs) b->release();
     if (h->h_loc) cudaFreeHost(h->h_loc);
@@ -750,6 +760,7 @@ static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, c
     h->names_ready = false;
     h->tsv_ready = false;
     h->el_ready = false;
+    h->paths_ready = false;
     h->edges_are_ids = false;
     h->spec = spec;
     if (p->dtype < G2N_DTYPE_F64 || p->dtype > G2N_DTYPE_BOOL) { h->err = "unknown dtype"; return G2N_ERR_INVALID; }
@@ -936,6 +947,7 @@ static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, c
             P.wt_len = h->params.weight_tag_len;
             P.dtype = p->dtype;
             P.seed = seed;
+            h->seed_used = seed;
             memcpy(P.wt, h->weight_tag, sizeof(P.wt));
             P.tile_begin = 0;
             P.tile_end = n_tiles;
@@ -1411,7 +1423,7 @@ static int bfs_check(g2n_handle* h, int32_t slot)
     return G2N_OK;
 }
 
-int g2n_bfs(g2n_handle* h, const int32_t* sources, uint64_t n_sources, int32_t slot, int32_t n_slots)
+static int bfs_run(g2n_handle* h, const int32_t* sources, uint64_t n_sources, bool on_device, int32_t slot, int32_t n_slots)
 {
     if (!h || (!sources && n_sources) || n_slots < 1 || slot < 0 || slot >= n_slots) return G2N_ERR_INVALID;
     if (!h->built || h->slab_mode || h->result_format == G2N_FMT_COO) { h->err = "distances need the CSR/CSC result of a single-GPU build"; return G2N_ERR_INVALID; }
@@ -1425,13 +1437,17 @@ int g2n_bfs(g2n_handle* h, const int32_t* sources, uint64_t n_sources, int32_t s
     CK(h->bfs_q0.ensure((n + 1) * sizeof(u32)));
     CK(h->bfs_q1.ensure((n + 1) * sizeof(u32)));
     CK(h->bfs_ctl.ensure(sizeof(BfsCtl)));
-    CK(h->bfs_nodes.ensure((n_sources + 1) * sizeof(int32_t)));
     int32_t* level = h->bfs_levels.as<int32_t>() + (size_t)slot * (n + 1);
     CK(cudaMemsetAsync(level, 0xFF, (n + 1) * sizeof(int32_t), h->stream));
     CK(cudaMemsetAsync(h->bfs_ctl.p, 0, sizeof(BfsCtl), h->stream));
     if (n == 0 || n_sources == 0) return G2N_OK;
-    CK(cudaMemcpyAsync(h->bfs_nodes.p, sources, n_sources * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-    { KScope ks(h, "k_bfs_seed"); k_bfs_seed<<<grid_for(n_sources, 256), 256, 0, h->stream>>>(h->bfs_nodes.as<int32_t>(), n_sources, (u32)n, level, h->bfs_q0.as<u32>(), h->bfs_ctl.as<BfsCtl>()); }
+    const int32_t* dsrc = sources;
+    if (!on_device) {
+        CK(h->bfs_nodes.ensure((n_sources + 1) * sizeof(int32_t)));
+        CK(cudaMemcpyAsync(h->bfs_nodes.p, sources, n_sources * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        dsrc = h->bfs_nodes.as<int32_t>();
+    }
+    { KScope ks(h, "k_bfs_seed"); k_bfs_seed<<<grid_for(n_sources, 256), 256, 0, h->stream>>>(dsrc, n_sources, (u32)n, level, h->bfs_q0.as<u32>(), h->bfs_ctl.as<BfsCtl>()); }
     CK(cudaGetLastError());
     {
         KScope ks(h, "k_bfs_gang");
@@ -1449,21 +1465,30 @@ int g2n_bfs(g2n_handle* h, const int32_t* sources, uint64_t n_sources, int32_t s
     return G2N_OK;
 }
 
-int g2n_levels_reduce(g2n_handle* h, int32_t slot, const int32_t* nodes, uint64_t n_nodes, int64_t* out3)
+int g2n_bfs(g2n_handle* h, const int32_t* sources, uint64_t n_sources, int32_t slot, int32_t n_slots)
+{
+    return bfs_run(h, sources, n_sources, false, slot, n_slots);
+}
+
+static int levels_reduce_run(g2n_handle* h, int32_t slot, const int32_t* nodes, uint64_t n_nodes, bool on_device, int64_t* out3)
 {
     if (!h || !out3 || (!nodes && n_nodes)) return G2N_ERR_INVALID;
     CK(cudaSetDevice(h->device));
     int rc = bfs_check(h, slot);
     if (rc) return rc;
     const u64 n = h->n_nodes;
-    CK(h->bfs_nodes.ensure((n_nodes + 1) * sizeof(int32_t)));
     CK(h->bfs_out.ensure(4 * sizeof(long long)));
     const long long init[3] = {0x7fffffffffffffffLL, 0, 0};
     CK(cudaMemcpyAsync(h->bfs_out.p, init, sizeof init, cudaMemcpyHostToDevice, h->stream));
     if (n_nodes) {
-        CK(cudaMemcpyAsync(h->bfs_nodes.p, nodes, n_nodes * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        const int32_t* dn = nodes;
+        if (!on_device) {
+            CK(h->bfs_nodes.ensure((n_nodes + 1) * sizeof(int32_t)));
+            CK(cudaMemcpyAsync(h->bfs_nodes.p, nodes, n_nodes * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+            dn = h->bfs_nodes.as<int32_t>();
+        }
         KScope ks(h, "k_levels_reduce");
-        k_levels_reduce<<<grid_for(n_nodes, 256), 256, 0, h->stream>>>(h->bfs_levels.as<int32_t>() + (size_t)slot * (n + 1), h->bfs_nodes.as<int32_t>(), n_nodes, (u32)n, h->bfs_out.as<long long>());
+        k_levels_reduce<<<grid_for(n_nodes, 256), 256, 0, h->stream>>>(h->bfs_levels.as<int32_t>() + (size_t)slot * (n + 1), dn, n_nodes, (u32)n, h->bfs_out.as<long long>());
     }
     long long res[3];
     CK(cudaMemcpyAsync(res, h->bfs_out.p, sizeof res, cudaMemcpyDeviceToHost, h->stream));
@@ -1471,6 +1496,156 @@ int g2n_levels_reduce(g2n_handle* h, int32_t slot, const int32_t* nodes, uint64_
     out3[0] = res[2] ? res[0] : -1;
     out3[1] = res[1];
     out3[2] = res[2];
+    return G2N_OK;
+}
+
+int g2n_levels_reduce(g2n_handle* h, int32_t slot, const int32_t* nodes, uint64_t n_nodes, int64_t* out3)
+{
+    return levels_reduce_run(h, slot, nodes, n_nodes, false, out3);
+}
+
+// ---- P / O records resolved on the device (paths.cuh)
+int g2n_paths_load(g2n_handle* h, uint64_t* n_paths)
+{
+    if (!h || !n_paths) return G2N_ERR_INVALID;
+    if (!h->built || h->slab_mode || !h->have_edges) { h->err = "paths need a single-GPU build"; return G2N_ERR_INVALID; }
+    CK(cudaSetDevice(h->device));
+    if (h->paths_ready) { *n_paths = h->h_paths.size(); return G2N_OK; }
+    const u64 N = h->nbytes;
+    h->h_paths.clear();
+    h->h_path_entry0.assign(1, 0);
+    CK(h->path_misc.ensure(256));
+    u32 cap = 1u << 16, found = 0;
+    for (int attempt = 0; attempt < 2 && N; attempt++) {
+        CK(h->path_starts.ensure((size_t)cap * sizeof(u64)));
+        CK(cudaMemsetAsync(h->path_misc.p, 0, 256, h->stream));
+        { KScope ks(h, "k_paths_find"); k_paths_find<<<grid_for((N + 15) / 16, 256), 256, 0, h->stream>>>(h->d_text, N, h->path_starts.as<u64>(), cap, h->path_misc.as<u32>()); }
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&found, h->path_misc.p, sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (found <= cap) break;
+        cap = found;
+    }
+    const u32 R = found;
+    if (R) {
+        std::vector<u64> starts(R);
+        CK(cudaMemcpy(starts.data(), h->path_starts.p, (size_t)R * sizeof(u64), cudaMemcpyDeviceToHost));
+        std::sort(starts.begin(), starts.end());
+        h->h_paths.resize(R);
+        for (u32 r = 0; r < R; r++) { memset(&h->h_paths[r], 0, sizeof(PathRec)); h->h_paths[r].line = starts[r]; }
+        CK(h->path_recs.ensure((size_t)R * sizeof(PathRec)));
+        CK(cudaMemcpyAsync(h->path_recs.p, h->h_paths.data(), (size_t)R * sizeof(PathRec), cudaMemcpyHostToDevice, h->stream));
+        { KScope ks(h, "k_path_fields"); k_path_fields<<<R < 4u * G2N_SM_COUNT ? R : 4u * G2N_SM_COUNT, 256, 0, h->stream>>>(h->d_text, N, h->path_recs.as<PathRec>(), R); }
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h->h_paths.data(), h->path_recs.p, (size_t)R * sizeof(PathRec), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        u64 n_blocks = 0;
+        for (u32 r = 0; r < R; r++) {
+            h->h_paths[r].first_blk = n_blocks;
+            n_blocks += (h->h_paths[r].list_end - h->h_paths[r].list_off + 1 + PB_BYTES - 1) / PB_BYTES;
+        }
+        CK(cudaMemcpyAsync(h->path_recs.p, h->h_paths.data(), (size_t)R * sizeof(PathRec), cudaMemcpyHostToDevice, h->stream));
+        CK(h->path_cnt.ensure((n_blocks + 1) * sizeof(u32)));
+        CK(h->path_off.ensure((n_blocks + 2) * sizeof(u64)));
+        { KScope ks(h, "k_path_count"); k_path_count<<<grid_for(n_blocks, 1, 16), 256, 0, h->stream>>>(h->d_text, h->path_recs.as<PathRec>(), R, n_blocks, h->path_cnt.as<u32>()); }
+        CK(cudaGetLastError());
+        LoadArray<u32> lc{h->path_cnt.as<u32>()};
+        int rc = launch_scan<u64>(h, lc, h->path_off.as<u64>(), nullptr, n_blocks, nullptr, nullptr);
+        if (rc) return rc;
+        h->h_path_blkoff.resize(n_blocks + 1);
+        CK(cudaMemcpyAsync(h->h_path_blkoff.data(), h->path_off.p, (n_blocks + 1) * sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        const u64 total = h->h_path_blkoff[n_blocks];
+        if (total >= 0x7FFFFFFF00ull) { h->err = "too many path entries"; return G2N_ERR_UNSUPPORTED; }
+        CK(h->path_ids.ensure((total + 1) * sizeof(int32_t)));
+        PathLookup T;
+        T.tkeys = h->d_tkeys; T.trep = h->d_trep; T.longs = h->longs.as<LongDesc>(); T.slot_id = h->slot_id.as<u32>();
+        T.mask = h->table_cap - 1; T.seed = h->seed_used; T.bidirected = h->params.bidirected ? 1 : 0;
+        { KScope ks(h, "k_path_lookup"); k_path_lookup<<<grid_for(n_blocks, 1, 16), 256, 0, h->stream>>>(h->d_text, h->path_recs.as<PathRec>(), R, n_blocks, h->path_off.as<u64>(), T, h->path_ids.as<int32_t>()); }
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h->h_paths.data(), h->path_recs.p, (size_t)R * sizeof(PathRec), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        h->h_path_entry0.resize(R + 1);
+        for (u32 r = 0; r < R; r++) h->h_path_entry0[r] = h->h_path_blkoff[h->h_paths[r].first_blk];
+        h->h_path_entry0[R] = total;
+    }
+    h->paths_ready = true;
+    *n_paths = R;
+    return G2N_OK;
+}
+
+int g2n_path_info(g2n_handle* h, uint64_t i, g2n_path_info_t* out)
+{
+    if (!h || !out || !h->paths_ready || i >= h->h_paths.size()) return G2N_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    const PathRec& R = h->h_paths[i];
+    memset(out, 0, sizeof(*out));
+    out->line_offset = R.line;
+    out->name_offset = R.name_off;
+    out->name_len = R.name_len;
+    out->n_entries = h->h_path_entry0[i + 1] - h->h_path_entry0[i];
+    out->missing_entry = R.missing == ~0ull ? -1 : (int64_t)R.missing;
+    if (R.missing != ~0ull) {
+        // where that entry's text is: the block that holds the entry index, then at most 4 KiB of commas
+        const u64 target = h->h_path_entry0[i] + R.missing;
+        const u64 nb = h->h_path_blkoff.size() - 1;
+        u64 a = R.first_blk, z = (i + 1 < h->h_paths.size() ? h->h_paths[i + 1].first_blk : nb);
+        while (z - a > 1) { const u64 m = (a + z) >> 1; if (h->h_path_blkoff[m] <= target) a = m; else z = m; }
+        const u64 lo = R.list_off + (a - R.first_blk) * PB_BYTES;
+        const u64 hi = std::min<u64>(lo + PB_BYTES, R.list_end + 1);
+        const u64 from = lo ? lo - 1 : 0, to = std::min<u64>(R.list_end, hi + (1u << 16));
+        std::vector<uint8_t> buf(to - from + 1);
+        if (to > from) CK(cudaMemcpy(buf.data(), h->d_text + from, to - from, cudaMemcpyDeviceToHost));
+        u64 k = h->h_path_blkoff[a];
+        for (u64 p = lo; p < hi; p++) {
+            const bool start = p == R.list_off || buf[p - 1 - from] == ',';
+            if (!start) continue;
+            if (k == target) {
+                u64 e = p;
+                while (e < R.list_end && e - from < buf.size() - 1 && buf[e - from] != ',') e++;
+                u64 len = e - p;
+                if (len && (buf[e - 1 - from] == '+' || buf[e - 1 - from] == '-')) len--;
+                out->missing_offset = p;
+                out->missing_len = (uint32_t)len;
+                break;
+            }
+            k++;
+        }
+    }
+    return G2N_OK;
+}
+
+int g2n_fetch_text(g2n_handle* h, uint64_t offset, uint64_t len, uint8_t* out)
+{
+    if (!h || (!out && len) || !h->built || offset + len > h->nbytes) return G2N_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (len) CK(cudaMemcpyAsync(out, h->d_text + offset, len, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return G2N_OK;
+}
+
+int g2n_path_bfs(g2n_handle* h, uint64_t i, int32_t slot, int32_t n_slots)
+{
+    if (!h || !h->paths_ready || i >= h->h_paths.size()) return G2N_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    const u64 e0 = h->h_path_entry0[i], n = h->h_path_entry0[i + 1] - e0;
+    return bfs_run(h, h->path_ids.as<int32_t>() + e0, n, true, slot, n_slots);
+}
+
+int g2n_path_reduce(g2n_handle* h, int32_t slot, uint64_t i, int64_t* out3)
+{
+    if (!h || !h->paths_ready || i >= h->h_paths.size()) return G2N_ERR_INVALID;
+    const u64 e0 = h->h_path_entry0[i], n = h->h_path_entry0[i + 1] - e0;
+    return levels_reduce_run(h, slot, h->path_ids.as<int32_t>() + e0, n, true, out3);
+}
+
+int g2n_fetch_path_nodes(g2n_handle* h, uint64_t i, int32_t* out)
+{
+    if (!h || !out || !h->paths_ready || i >= h->h_paths.size()) return G2N_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    const u64 e0 = h->h_path_entry0[i], n = h->h_path_entry0[i + 1] - e0;
+    if (n) CK(cudaMemcpyAsync(out, h->path_ids.as<int32_t>() + e0, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return G2N_OK;
 }
 

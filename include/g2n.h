@@ -182,6 +182,28 @@ int g2n_bfs(g2n_handle *h, const int32_t *sources, uint64_t n_sources, int32_t s
 int g2n_levels_reduce(g2n_handle *h, int32_t slot, const int32_t *nodes, uint64_t n_nodes, int64_t *out3);
 int g2n_fetch_levels(g2n_handle *h, int32_t slot, int32_t *out);
 
+/* The P / O records of the last build's text (analysis.py:164-177 over parser.py:229-247, 343-361), resolved on the
+ * device: g2n_paths_load finds the records (file order) and turns every "<segment>[+-]" entry of their lists into the
+ * node ID of that segment (-1: not a node); g2n_path_info describes record i (name = bytes of the text; the first
+ * entry that is not a node, which the reference answers with NodeNotFound); g2n_path_bfs / g2n_path_reduce are g2n_bfs /
+ * g2n_levels_reduce with record i's node list, which never leaves the device; g2n_fetch_path_nodes copies it out. */
+typedef struct g2n_path_info_t {
+    uint64_t line_offset;    /* first byte of the record */
+    uint64_t name_offset;    /* fields[1] */
+    uint64_t n_entries;      /* entries of fields[2].split(",") */
+    int64_t missing_entry;   /* index of the first entry that is not a node, -1 if all are */
+    uint64_t missing_offset; /* that entry's name (sign stripped) in the text */
+    uint32_t name_len;
+    uint32_t missing_len;
+} g2n_path_info_t;
+int g2n_paths_load(g2n_handle *h, uint64_t *n_paths);
+int g2n_path_info(g2n_handle *h, uint64_t i, g2n_path_info_t *out);
+int g2n_path_bfs(g2n_handle *h, uint64_t i, int32_t slot, int32_t n_slots);
+int g2n_path_reduce(g2n_handle *h, int32_t slot, uint64_t i, int64_t *out3);
+int g2n_fetch_path_nodes(g2n_handle *h, uint64_t i, int32_t *out);
+/* `len` bytes of the device-resident text of the last build (names of records, offending entries) */
+int g2n_fetch_text(g2n_handle *h, uint64_t offset, uint64_t len, uint8_t *out);
+
 /* Device pointers of the resident result (for device-side consumers / benchmarks). */
 int g2n_device_result(g2n_handle *h, void **a0, void **a1, void **data);
 

@@ -131,3 +131,32 @@ def test_cli_distance_commands(tmp_path):
     assert r.stdout.strip() == "396"
     r = subprocess.run([sys.executable, "-m", "gfa2network_b200", "distance", str(chain), "--path", "tail", "head", "--undirected"], capture_output=True, text=True, check=True)
     assert r.stdout.strip() == "396"
+
+
+@pytest.mark.gpu
+def test_device_path_nodes_match_host_split():
+    """The node lists resolved on the device (csrc/paths.cuh) against the host split of the same records: lines far
+    longer than one 4 KiB block, O records, unsigned / empty / unknown entries, a trailing comma, long names."""
+    from gfa2network_b200.analysis import _DevicePaths, _Graph
+    from gfa2network_b200.synth import synth_gfa
+    from oracle.oracle import oracle_load_paths
+
+    big = synth_gfa(60_000, 120_000, seed=31, kind=1, n_paths=3, n_walks=1).tobytes()
+    extra = (b"S\ta_segment_name_longer_than_fifteen_bytes\t*\nL\ta_segment_name_longer_than_fifteen_bytes\t+\ts7\t-\t0M\n"
+             b"O\two\ts5-,s6,a_segment_name_longer_than_fifteen_bytes+,s5--\textra\n"
+             b"P\todd\ts1+,,nope+,s2+,\t*\n"
+             b"P\thap0\ts9+\t*\n"      # replaces the list of the first record, keeps its position
+             b"P\tlast\ts3+")          # no newline at the end of the file
+    text = big + extra
+    G = _Graph(text)
+    P = _DevicePaths(G, False)
+    want = oracle_load_paths(text)
+    assert list(P.index) == list(want)
+    for name, segs in want.items():
+        got = P.nodes(P.index[name])
+        exp = np.array([G.index.get(s, -1) for s in segs], dtype=np.int32)
+        assert np.array_equal(got, exp), name
+    info = P.infos[P.index["odd"]]
+    assert info.missing_entry == 1 and info.missing_len == 0  # the empty entry comes first
+    with pytest.raises(Exception, match="Node  not found in graph"):
+        P.check_sources(P.index["odd"])
