@@ -95,3 +95,62 @@ def test_two_rank_gloo_exchange_and_assembly():
     for p in procs:
         p.join(30)
     assert res == [(0, True), (1, True)]
+
+
+def _info(rc=0, **kw):
+    d = dict(rc=rc, msg="", n_keys=10, n_tiles=1, n_records=20, n_edge_records=10, n_entries=20, err_kind=0, err_offset=0,
+             unknown_byte=-1, unknown_offset=0, nbytes=100)
+    d.update(kw)
+    return d
+
+
+def test_agreed_exceptions_follow_file_order():
+    """Every rank raises what parse_gfa raises for the concatenated shards: the lowest rank's error,
+    the unsupported-record warning only if it does not come after that error."""
+    import warnings
+
+    from gfa2network_b200 import _capi
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        D.raise_agreed([_info(), _info()])  # nothing to report
+    with pytest.raises(ValueError, match="Malformed E record"):
+        D.raise_agreed([_info(), _info(rc=_capi.G2N_ERR_PARSE, err_kind=2), _info(rc=_capi.G2N_ERR_PARSE, err_kind=1)])
+    with pytest.warns(RuntimeWarning, match="Skipping unsupported record: #"):
+        D.raise_agreed([_info(unknown_byte=ord("#")), _info(unknown_byte=ord("W"))])  # the first one in file order
+    with pytest.warns(RuntimeWarning, match="Skipping unsupported record: W"):
+        with pytest.raises(IndexError):
+            D.raise_agreed([_info(unknown_byte=ord("W")), _info(rc=_capi.G2N_ERR_PARSE, err_kind=6)])
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")  # the unsupported record sits in a LATER shard than the error: never reported
+        with pytest.raises(ValueError, match="Malformed P record"):
+            D.raise_agreed([_info(rc=_capi.G2N_ERR_PARSE, err_kind=4), _info(unknown_byte=ord("W"))])
+    with pytest.raises(NotImplementedError, match="hash collision"):
+        D.raise_agreed([_info(), _info(rc=_capi.G2N_ERR_UNSUPPORTED, msg="multi-GPU build: hash collision among long node names")])
+    with pytest.raises(_capi.G2NError):
+        D.raise_agreed([_info(rc=_capi.G2N_ERR_CUDA, msg="out of memory")])
+
+
+def test_plan_caps_grow_with_retries_and_cover_one_sided_shards():
+    infos = [_info(n_keys=1_000_000, n_entries=6_000_000), _info(n_keys=1_300_000, n_entries=100)]
+    for world in (2, 4, 8):
+        k0, p0 = D.plan_caps(infos, world, 0)
+        k1, p1 = D.plan_caps(infos, world, 1)
+        assert k0 >= 1_300_000 / world * 1.2 and k1 > k0  # hash partition + slack, more slack after a miss
+        assert p0 >= 6_000_000 and p1 == p0               # a shard may send every entry to ONE owner
+    assert D.plan_caps([_info(n_keys=0, n_entries=0)], 1)[0] > 0
+
+
+def test_dist_result_reports_what_moved():
+    import ctypes
+
+    from gfa2network_b200 import _capi
+
+    res = _capi.DistResult()
+    res.n_global, res.row0, res.n_rows, res.nnz, res.n_recv, res.n_first, res.id0 = 100, 25, 25, 60, 70, 30, 20
+    for d in range(4):
+        res.keys_to[d], res.pairs_to[d] = 10 + d, 20 + d
+    r = D._result(res, 4, True)
+    assert (r.n_global, r.row0, r.n_rows, r.nnz_local) == (100, 25, 25, 60)
+    assert r.info["keys_to"] == [10, 11, 12, 13] and r.info["pairs_to"] == [20, 21, 22, 23] and r.info["speculative"] is True
+    assert ctypes.sizeof(_capi.PathInfo) == 48
