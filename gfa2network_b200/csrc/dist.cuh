@@ -120,7 +120,7 @@ __device__ __forceinline__ void dx_wait(const DxCtl* my, int e, const DxPeers& X
         u32 spins = 0;
         while ((int)(ld_acquire_sys_u32(f) - X.epoch) < 0) {
             __nanosleep(200);
-            if (++spins > 8000000u) { atomicOr(&loc->bad, DXB_TIMEOUT); break; }
+            if (++spins > 30000000u) { atomicOr(&loc->bad, DXB_TIMEOUT); break; }  // >= 6 s: a peer that is merely slow (first-touch allocations) is waited for
         }
     }
     __syncthreads();
