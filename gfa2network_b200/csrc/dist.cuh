@@ -168,31 +168,76 @@ __device__ __forceinline__ void dx_tail_signal(const DxPeers& X, int e, DxLocal*
 // klist[owner][position in the owner's segment of this rank] = local order bit << 32 | table slot: the later passes
 // of this rank (mark, send_rank, localmap) walk these compact lists next to the owners' replies, which sit at
 // the same positions -- sequential reads instead of three more scans of the (half empty) table
+// A CTA handles DXK_SLOTS table slots per round: its keys are grouped by owner in shared memory, the CTA's range
+// in every owner's segment is reserved with ONE global atomic per owner, and consecutive threads write
+// consecutive elements -- the peers receive whole 128-byte-and-larger pieces instead of one key per lane group.
+#define DXK_PER 4
+#define DXK_SLOTS (256 * DXK_PER)
 __global__ void __launch_bounds__(256) k_dx_export(const TKey* __restrict__ tkeys, const u64* __restrict__ tfirst, u32 cap,
                                                     const u64* __restrict__ tile_base, const DevSizes* __restrict__ ds,
                                                     const DxPeers X, const DxLayout L, DxLocal* __restrict__ loc, u64* __restrict__ klist)
 {
+    __shared__ TKey s_key[DXK_SLOTS];
+    __shared__ u64 s_meta[DXK_SLOTS];  // order bit << 32 | slot
+    __shared__ u32 s_cnt[DX_MAXW], s_off[DX_MAXW + 1], s_base[DX_MAXW];
     if (!ds->ok && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&loc->bad, DXB_TOK);
     const u32 lane = threadIdx.x & 31;
-    for (u32 i0 = blockIdx.x * blockDim.x; ds->ok && i0 < cap; i0 += gridDim.x * blockDim.x) {  // cap is a multiple of 256
-        const u32 i = i0 + threadIdx.x;
-        const TKey k = tkeys[i];
-        const bool occ = !(k.x == 0 && k.y == 0);
-        const u32 d = occ ? dx_owner(k.x, k.y, X.world) : 0xFFu;
-        const u32 m = __match_any_sync(0xffffffffu, d);
-        if (!occ) continue;
-        const int leader = __ffs(m) - 1;
-        u32 base = 0;
-        if ((int)lane == leader) base = atomicAdd(&loc->cur_keys[d], (u32)__popc(m));
-        base = __shfl_sync(m, base, leader);
-        const u32 pos = base + __popc(m & ((1u << lane) - 1u));
-        if (pos >= L.kcap) { atomicOr(&loc->bad, DXB_KEYS); continue; }
-        uint8_t* a = X.arena[d];
-        const u64 j = (u64)X.rank * L.kcap + pos;
-        const u32 bit = order_bit(tile_base, ~tfirst[i]);
-        reinterpret_cast<TKey*>(a + L.off_key)[j] = k;
-        reinterpret_cast<u32*>(a + L.off_ord)[j] = bit;
-        klist[(u64)d * L.kcap + pos] = ((u64)bit << 32) | i;
+    for (u32 i0 = blockIdx.x * DXK_SLOTS; ds->ok && i0 < cap; i0 += gridDim.x * DXK_SLOTS) {  // cap is a multiple of 1024
+        if (threadIdx.x < DX_MAXW) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        TKey k[DXK_PER];
+        u32 d[DXK_PER], r[DXK_PER];
+#pragma unroll
+        for (int u = 0; u < DXK_PER; u++) {
+            const u32 i = i0 + u * 256 + threadIdx.x;
+            k[u] = tkeys[i];
+            const bool occ = !(k[u].x == 0 && k[u].y == 0);
+            d[u] = occ ? dx_owner(k[u].x, k[u].y, X.world) : 0xFFu;
+            const u32 m = __match_any_sync(0xffffffffu, d[u]);
+            r[u] = 0;
+            if (occ) {
+                const int leader = __ffs(m) - 1;
+                u32 base = 0;
+                if ((int)lane == leader) base = atomicAdd(&s_cnt[d[u]], (u32)__popc(m));
+                r[u] = __shfl_sync(m, base, leader) + __popc(m & ((1u << lane) - 1u));
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            u32 run = 0;
+            for (int w = 0; w < X.world; w++) { s_off[w] = run; run += s_cnt[w]; }
+            s_off[X.world] = run;
+        }
+        if (threadIdx.x < (u32)X.world) {
+            const u32 c = s_cnt[threadIdx.x];
+            const u32 b = c ? atomicAdd(&loc->cur_keys[threadIdx.x], c) : 0u;
+            if ((u64)b + c > L.kcap) atomicOr(&loc->bad, DXB_KEYS);
+            s_base[threadIdx.x] = b;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < DXK_PER; u++) {
+            if (d[u] == 0xFFu) continue;
+            const u32 i = i0 + u * 256 + threadIdx.x;
+            const u32 q = s_off[d[u]] + r[u];
+            s_key[q] = k[u];
+            s_meta[q] = ((u64)order_bit(tile_base, ~tfirst[i]) << 32) | i;
+        }
+        __syncthreads();
+        const u32 total = s_off[X.world];
+        for (u32 q = threadIdx.x; q < total; q += 256) {
+            u32 w = 0;
+            while (q >= s_off[w + 1]) w++;  // staged elements are grouped by owner
+            const u32 pos = s_base[w] + (q - s_off[w]);
+            if (pos >= L.kcap) continue;
+            uint8_t* a = X.arena[w];
+            const u64 jj = (u64)X.rank * L.kcap + pos;
+            const u64 meta = s_meta[q];
+            reinterpret_cast<TKey*>(a + L.off_key)[jj] = s_key[q];
+            reinterpret_cast<u32*>(a + L.off_ord)[jj] = (u32)(meta >> 32);
+            klist[(u64)w * L.kcap + pos] = meta;
+        }
+        __syncthreads();
     }
     dx_tail_signal(X, 0, loc, loc->cur_keys, L.kcap, 0);
 }

@@ -1933,7 +1933,7 @@ int g2n_dist_stage(g2n_handle* h, int stage, const uint8_t* text, uint64_t nbyte
     const int csc = (!sym && h->params.want_format == G2N_FMT_CSC) ? 1 : 0;
     switch (stage) {
     case 0: {
-        { KScope ks(h, "k_dx_export"); k_dx_export<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->d_tkeys, h->d_tfirst, cap, h->tile_base.as<u64>(), h->d_ds, X, L, loc, h->dx_sent.as<u64>()); }
+        { KScope ks(h, "k_dx_export"); k_dx_export<<<grid_for(cap, DXK_SLOTS), 256, 0, h->stream>>>(h->d_tkeys, h->d_tfirst, cap, h->tile_base.as<u64>(), h->d_ds, X, L, loc, h->dx_sent.as<u64>()); }
         break;
     }
     case 1: {
