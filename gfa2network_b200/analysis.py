@@ -8,8 +8,7 @@
   without a weight tag -- hop counts along out-edges.  Here the adjacency stays in HBM as the CSR the matrix
   path builds (asymmetric for the default DiGraph, undirected for ``directed=False``) and every search is one
   cooperative multi-level BFS kernel (csrc/bfs.cuh); the per-pair minima / means are reduced on the device too.
-Not provided (they need node sequences / per-pair Dijkstra on the object graph): ``sequence_distance``,
-``genome_distance(method="mean")``, ``compute_stats``, the igraph backend."""
+Not provided (they need node sequences / the object graph): ``sequence_distance``, ``compute_stats``, the igraph backend."""
 from __future__ import annotations
 
 import ctypes as C
@@ -110,24 +109,45 @@ class _Graph:
         return out
 
 
+def _no_path(msg: str):
+    try:
+        import networkx as nx
+
+        return nx.NetworkXNoPath(msg)
+    except ImportError:  # pragma: no cover
+        return ValueError(msg)
+
+
 def genome_distance(gfa_path, nodes_a, nodes_b, *, method: str = "min", directed: bool = True, raw_bytes_id: bool = False, device=None) -> float:
-    """analysis.py:116-161 for ``method="min"``: the hop distance between two node sets of the graph of *gfa_path*
-    (the reference takes the NetworkX graph; here the graph is the device-resident CSR of the file)."""
-    if method == "mean":
-        raise NotImplementedError("genome_distance(method='mean') runs one Dijkstra per node pair on the object graph (analysis.py:147-159)")
-    if method != "min":
+    """analysis.py:116-161: the hop distance between two node sets of the graph of *gfa_path* (the reference takes the
+    NetworkX graph; here the graph is the device-resident CSR of the file).  ``min``: one multi-source search from
+    *nodes_a*; ``mean``: one search per node of *nodes_a*, averaged over the reachable pairs (analysis.py:141-159)."""
+    import os
+
+    nodes_a, nodes_b = list(nodes_a), list(nodes_b)
+    if method not in ("min", "mean"):
         raise ValueError(f"unknown method: {method}")
     G = _Graph(gfa_path, directed=directed, raw_bytes_id=raw_bytes_id, device=device)
-    G.bfs(G.ids(list(nodes_a), strict=True), 0, 1)
-    mn, _, cnt = G.reduce(0, G.ids(list(nodes_b), strict=False))
-    if cnt == 0:
-        try:
-            import networkx as nx
-
-            raise nx.NetworkXNoPath("no path between node sets")
-        except ImportError:  # pragma: no cover
-            raise ValueError("no path between node sets") from None
-    return mn
+    if method == "min":
+        G.bfs(G.ids(nodes_a, strict=True), 0, 1)
+        mn, _, cnt = G.reduce(0, G.ids(nodes_b, strict=False))
+        if cnt == 0:
+            raise _no_path("no path between node sets")
+        return mn
+    if len(nodes_a) * len(nodes_b) > 1000 and os.getenv("GFANET_DISABLE_WARNINGS") != "1":
+        warnings.warn("Mean distance scales quadratically; this may be very slow on large sets", RuntimeWarning)
+    targets = G.ids(nodes_b, strict=False)  # a target that is not a node is "no path" for nx.shortest_path_length: skipped
+    total, count = 0.0, 0
+    for u in nodes_a:
+        if not nodes_b:
+            break
+        G.bfs(G.ids([u], strict=True), 0, 1)
+        _, s, c = G.reduce(0, targets)
+        total += s
+        count += c
+    if count == 0:
+        raise _no_path("no path between node sets")
+    return total / count
 
 
 class _DevicePaths:

@@ -160,3 +160,27 @@ def test_device_path_nodes_match_host_split():
     assert info.missing_entry == 1 and info.missing_len == 0  # the empty entry comes first
     with pytest.raises(Exception, match="Node  not found in graph"):
         P.check_sources(P.index["odd"])
+
+
+@pytest.mark.gpu
+def test_genome_distance_min_and_mean_semantics():
+    """analysis.py:116-161 on a small graph; the expected values were produced by the real reference
+    (genome_distance on the NetworkX graph of the same text)."""
+    from gfa2network_b200.analysis import genome_distance
+
+    text = b"S\ta\t*\nS\tb\t*\nS\tc\t*\nS\td\t*\nL\ta\t+\tb\t+\t0M\nL\tb\t+\tc\t+\t0M\nL\td\t+\ta\t+\t0M\n"
+
+    def run(A, B, method):
+        try:
+            return genome_distance(text, A, B, method=method)
+        except Exception as e:  # noqa: BLE001
+            return (type(e).__name__, str(e))
+
+    assert run(["a"], ["c"], "mean") == 2.0 and run(["a", "b"], ["c", "c"], "mean") == 1.5 and run(["a"], ["a"], "mean") == 0.0
+    assert run(["c"], ["a"], "mean") == ("NetworkXNoPath", "no path between node sets")
+    assert run(["a", "zz"], ["c"], "mean") == ("NodeNotFound", "Node zz not found in graph")
+    assert run(["a"], ["zz", "c"], "mean") == 2.0  # a target that is not a node is skipped
+    assert run(["a"], ["c"], "min") == 2 and run(["c"], ["a"], "min") == ("NetworkXNoPath", "no path between node sets")
+    assert run(["zz"], ["a"], "min") == ("NodeNotFound", "Node zz not found in graph")
+    assert run(["a"], ["zz"], "min") == ("NetworkXNoPath", "no path between node sets")
+    assert run(["a"], ["c"], "bogus") == ("ValueError", "unknown method: bogus")
