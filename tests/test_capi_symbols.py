@@ -26,6 +26,19 @@ def test_library_exports_every_declared_symbol():
     assert lib.g2n_abi_version() == _capi.ABI_VERSION
 
 
+def test_header_is_plain_c():
+    """include/g2n.h is the boundary a C / cgo / JNI binding would include: it must compile as C99 on its own."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    for std, lang in (("-std=c99", "c"), ("-std=c++17", "c++")):
+        r = subprocess.run([gcc, std, "-Wall", "-Wextra", "-pedantic", "-fsyntax-only", "-x", lang, str(ROOT / "include" / "g2n.h")], capture_output=True, text=True)
+        assert r.returncode == 0 and not r.stderr.strip(), r.stderr
+
+
 def test_struct_layouts_match_header():
     from gfa2network_b200 import _capi
 
@@ -34,6 +47,21 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_capi.DistResult) == 11 * 8 + 2 * 64
     assert ctypes.sizeof(_capi.DistInfo) == 48
     assert ctypes.sizeof(_capi.Diag) == 112
+    assert ctypes.sizeof(_capi.PathInfo) == 48
+    # the C compiler's view of the same structs
+    import shutil
+    import subprocess
+    import tempfile
+
+    gcc = shutil.which("gcc")
+    if gcc:
+        src = '#include <stdio.h>\n#include "g2n.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(g2n_params), sizeof(g2n_sizes_t), sizeof(g2n_dist_info), sizeof(g2n_diag), sizeof(g2n_dist_result), sizeof(g2n_path_info_t));return 0;}\n'
+        with tempfile.TemporaryDirectory() as d:
+            c = Path(d) / "s.c"
+            c.write_text(src)
+            subprocess.run([gcc, "-I", str(ROOT / "include"), "-o", str(Path(d) / "s"), str(c)], check=True)
+            out = subprocess.run([str(Path(d) / "s")], capture_output=True, text=True, check=True).stdout.split()
+        assert [int(x) for x in out] == [ctypes.sizeof(t) for t in (_capi.Params, _capi.Sizes, _capi.DistInfo, _capi.Diag, _capi.DistResult, _capi.PathInfo)]
 
 
 def test_no_cpu_fallback():
