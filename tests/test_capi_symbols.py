@@ -91,3 +91,28 @@ def test_product_never_imports_oracle():
     for p in (ROOT / "gfa2network_b200").rglob("*"):
         if p.suffix in {".py", ".cu", ".cuh", ".h", ".c"}:
             assert "oracle" not in p.read_text().replace("CPU oracle", "").replace("the oracle", "").lower() or p.name in {"synth.c", "synth.py"}, p
+
+
+def test_plain_c_example_links_against_the_library(tmp_path):
+    """examples/convert.c uses the ABI from C exactly as a cgo / JNI binding would; it must compile, link against
+    libg2n.so and -- without a GPU -- fail loudly at g2n_create (no CPU fallback)."""
+    import shutil
+    import subprocess
+
+    import torch
+
+    from gfa2network_b200 import _capi
+
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    _capi.load()
+    lib_dir = _capi.lib_path().parent
+    exe = tmp_path / "convert"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-I", str(ROOT / "include"), "-o", str(exe), str(ROOT / "examples" / "convert.c"),
+                    "-L", str(lib_dir), "-lg2n", f"-Wl,-rpath,{lib_dir}"], check=True)
+    r = subprocess.run([str(exe), str(ROOT / "tests" / "golden" / "DRB1-3123_unsorted.gfa")], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and "nodes 3214  nnz 8751" in r.stdout, (r.stdout, r.stderr)  # SURVEY 8c: C1 default directed CSR
+    else:
+        assert r.returncode == 1 and "no CPU fallback" in r.stderr
