@@ -142,57 +142,115 @@ def cpu_oracle_run(text, mode, fmt):
     return time.perf_counter() - t, A
 
 
-REFERENCE_BUDGET_S = 150.0  # CPU seconds the whole --impl reference run may take
+REFERENCE_BUDGET_S = 150.0  # CPU seconds the whole --impl reference run may take (both legs together)
+
+
+def _mode_text(cfg):
+    return ",".join(f"{k}={v}" for k, v in cfg["mode"].items()) or "directed(default)"
+
+
+def _time_passes(fn, n_warm, n_steps):
+    for _ in range(n_warm):
+        fn()
+    ts = []
+    for _ in range(n_steps):
+        t = time.perf_counter()
+        fn()
+        ts.append(time.perf_counter() - t)
+    return sum(ts) / len(ts)
+
+
+def _scaled_text(cfg_name, target_bytes, full_scale):
+    """Text of the configuration's shape with about target_bytes (same generator, same mix of records)."""
+    frac = min(1.0, target_bytes / (CONFIG_BYTES_HINT[cfg_name] * full_scale))
+    return make_text(cfg_name, full_scale * frac) + (frac,)
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path = the oracle port (the
-    reference itself is Python under /root/reference, which does not exist on the GPU box; it is
-    single-threaded, and so is the port: cores = 1).  Every step is one pass over a text of the
-    configuration's shape; when K full-size passes would not fit the time budget the text is scaled down
-    (same generator, same mix of records) and `sample` says so -- GB/s is size-normalised."""
+    """--impl reference: the reference's own CPU implementation of the path on this host.
+
+    Leg 1 (the line's `value`, cpu_baseline.kind = "reference"): the UNMODIFIED reference package, staged from
+    /root/reference into oracle/_ref by oracle/stage_ref.py (pure Python: `gfa2network.parse_gfa(path,
+    build_graph=False, build_matrix=True, ...)` + `convert_format`, file in the page cache).  It is single-
+    threaded: cores = 1.
+    Leg 2 (`cpu_baseline_port`, kind "port"): the C restatement of its algorithm + SciPy (oracle/), the stronger
+    baseline -- about 25x the reference's own speed on the same core.
+    Every step is one pass over a text of the configuration's shape, sized so that W + K passes of each leg fit the
+    time budget (GB/s is size-normalised; `sample` says what was run).  If oracle/_ref is absent the port is the line."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_pass = args.steps + max(0, min(args.warmup, 1))
-    # rate estimate on a 5 % text, then the largest scale whose passes fit the budget
-    cfg, probe, _, _ = make_text(args.config, min(args.scale, 0.05))
-    dt, _A = cpu_oracle_run(probe, cfg["mode"], cfg["fmt"])
+    n_warm = max(0, min(args.warmup, 1))
+    n_pass = args.steps + n_warm
+    cfg0 = make_text(args.config, min(args.scale, 0.002))[0]
+    mode, fmt = cfg0["mode"], cfg0["fmt"]
+    full_bytes = CONFIG_BYTES_HINT[args.config] * args.scale
+    # ---- leg 2: the port (rate estimate on a small text, then the largest text whose passes fit a third of the budget)
+    _, probe, _, _ = make_text(args.config, min(args.scale, 0.02))
+    dt, _A = cpu_oracle_run(probe, mode, fmt)
     rate = probe.size / dt
-    _, full, _, _ = make_text(args.config, args.scale) if CONFIG_BYTES_HINT.get(args.config, 0) * args.scale < 2e9 else (None, None, None, None)
-    full_bytes = full.size if full is not None else CONFIG_BYTES_HINT[args.config] * args.scale
-    scale = args.scale * min(1.0, rate * REFERENCE_BUDGET_S / n_pass / full_bytes)
-    if scale >= args.scale * 0.999 and full is not None:
-        cfg, text, n_seg, n_link = make_text(args.config, args.scale)
-        scale = args.scale
-    else:
-        cfg, text, n_seg, n_link = make_text(args.config, scale)
-    del full, probe
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_oracle_run(text, cfg["mode"], cfg["fmt"])
-    times = []
-    for _ in range(args.steps):
-        dt, _A = cpu_oracle_run(text, cfg["mode"], cfg["fmt"])
-        times.append(dt)
-    ms = 1e3 * sum(times) / len(times)
-    gbs = text.size / (ms * 1e6)
-    sample = (f"full {args.config} text ({text.size} B)" if scale == args.scale else
-              f"{args.config} shape scaled to {scale / args.scale:.3f} of the workload ({text.size} B per pass) to keep {n_pass} passes within {REFERENCE_BUDGET_S:.0f} s")
+    cfg, text, n_seg, n_link, frac = _scaled_text(args.config, rate * (REFERENCE_BUDGET_S / 3) / n_pass, args.scale)
+    port_s = _time_passes(lambda: cpu_oracle_run(text, mode, fmt), n_warm, args.steps)
+    port = {"value": text.size / (port_s * 1e9), "unit": "GB/s", "cores": 1, "kind": "port", "host_cores_available": os.cpu_count(),
+            "sample": (f"{args.config} shape at {frac:.4f} of the workload ({text.size} B per pass)" if frac < 1 else f"full {args.config} text ({text.size} B)")
+                      + f", {args.steps} passes, C port of parser.py/builders.py + SciPy",
+            "ms_per_step": port_s * 1e3, "edges_per_s": n_link / port_s}
+    line_leg, ms, n_link_leg = port, port_s * 1e3, n_link
+    # ---- leg 1: the reference itself
+    ref_leg = None
+    try:
+        from oracle.stage_ref import check as ref_check, import_reference
+
+        ref = import_reference()
+    except Exception as exc:  # noqa: BLE001
+        ref, ref_err = None, repr(exc)
+    if ref is not None:
+        import tempfile
+
+        tmpdir = "/dev/shm" if os.path.isdir("/dev/shm") else None
+        _, probe, _, _ = make_text(args.config, min(args.scale, 0.002))
+        with tempfile.NamedTemporaryFile(suffix=".gfa", dir=tmpdir) as fh:
+            fh.write(probe.tobytes())
+            fh.flush()
+
+            def ref_run(path=fh.name):
+                A = ref.parse_gfa(path, build_graph=False, build_matrix=True, **mode)
+                return ref.convert_format(A, fmt)
+            t = time.perf_counter()
+            ref_run()
+            rrate = probe.size / (time.perf_counter() - t)
+        cfg, rtext, r_seg, r_link, rfrac = _scaled_text(args.config, rrate * (REFERENCE_BUDGET_S * 2 / 3) / n_pass, args.scale)
+        with tempfile.NamedTemporaryFile(suffix=".gfa", dir=tmpdir) as fh:
+            fh.write(rtext.tobytes())
+            fh.flush()
+
+            def ref_run2(path=fh.name):
+                A = ref.parse_gfa(path, build_graph=False, build_matrix=True, **mode)
+                return ref.convert_format(A, fmt)
+            ref_s = _time_passes(ref_run2, n_warm, args.steps)
+        ref_leg = {"value": rtext.size / (ref_s * 1e9), "unit": "GB/s", "cores": 1, "kind": "reference", "host_cores_available": os.cpu_count(),
+                   "sample": f"{args.config} shape at {rfrac:.5f} of the workload ({rtext.size} B per pass, file in /dev/shm), {args.steps} passes of the unmodified "
+                             f"reference (oracle/_ref/gfa2network {getattr(ref, '__version__', '?')}: parse_gfa + convert_format, manifest ok: {ref_check()})",
+                   "ms_per_step": ref_s * 1e3, "edges_per_s": r_link / ref_s}
+        line_leg, ms, n_link_leg = ref_leg, ref_s * 1e3, r_link
+    gbs = line_leg["value"]
     line = {
         "impl": "reference", "metric": "gfa_to_csr_parse_build_GBps", "value": gbs, "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/int32/f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.config, args.scale, *make_sizes(args.config, args.scale), cfg), "text_bytes": int(full_bytes)},
-        "edges_per_s": n_link / (ms / 1e3),
-        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": 1, "kind": "port", "host_cores_available": os.cpu_count(),
-                         "sample": sample + f", {args.steps} passes, C port of parser.py/builders.py + SciPy"},
+        "config": {"workload": workload_name(args.config, args.scale, *make_sizes(args.config, args.scale), cfg), "text_bytes_per_gpu": int(full_bytes)},
+        "edges_per_s": n_link_leg / (ms / 1e3),
+        "cpu_baseline": {k: v for k, v in line_leg.items() if k not in ("ms_per_step", "edges_per_s")},
+        "cpu_baseline_port": port,
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if ref_leg is None:
+        line["reference_package"] = "oracle/_ref is absent (oracle/stage_ref.py stages it where /root/reference exists): the line is the port"
     print(json.dumps(line))
 
 
 # approximate text bytes of the full configurations (only to decide whether generating them is affordable)
-CONFIG_BYTES_HINT = {"C2": 86e6, "C3": 1.67e9, "C4": 11.9e9, "C5": 39.8e9}
+CONFIG_BYTES_HINT = {"C2": 86e6, "C3": 1.67e9, "C4": 11.9e9, "C4d": 11.9e9, "C5": 39.8e9}
 
 
 def make_sizes(cfg_name: str, scale: float):
@@ -286,7 +344,13 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()  # before the warm-up: nvidia-smi's first row takes a few hundred ms
-    for _ in range(max(args.warmup, 3)):
+    # the very first build of this process: buffer allocation, capacity discovery (no size hints yet), host round trips
+    torch.cuda.synchronize()
+    t_first = time.perf_counter()
+    step()
+    torch.cuda.synchronize()
+    first_call_ms = (time.perf_counter() - t_first) * 1e3
+    for _ in range(max(args.warmup, 3) - 1):
         flush.zero_()
         step()
     torch.cuda.synchronize()
@@ -314,6 +378,34 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     ms_step = total_ms / args.steps
+    # ---- the same steps with speculation off: sizes are read back after the tokenizer and every buffer is sized from
+    # them, as for a text this handle has not seen before (a `convert` sees each file once)
+    ms_nonspec = None
+    if builder is None:
+        h.set_speculation(False)
+        nsteps = max(1, min(args.steps, 20))
+        nev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nsteps)]
+        for i in range(nsteps):
+            flush.zero_()
+            nev[i][0].record(stream)
+            step()
+            nev[i][1].record(stream)
+        torch.cuda.synchronize()
+        ms_nonspec = sum(a.elapsed_time(b) for a, b in nev) / nsteps
+        h.set_speculation(True)
+        step()  # (re-learn the hints)
+        torch.cuda.synchronize()
+    # ---- H2D ingest alone: the pinned text copied to the device, nothing else (reported separately, BASELINE north_star)
+    iev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+    for a, b in iev:
+        a.record(stream)
+        text_dev.copy_(pinned, non_blocking=True)
+        b.record(stream)
+    torch.cuda.synchronize()
+    ti = torch.tensor([min(a.elapsed_time(b) for a, b in iev)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ti, op=dist.ReduceOp.MAX)
+    ingest_ms = float(ti.item())
     # per-kernel durations: a second pass of the same steps with one CUDA-event pair around every launch
     # (g2n_set_profile); kept out of the timed region because the event records themselves cost time
     h.set_profile(True)
@@ -411,8 +503,15 @@ def run_ours(args):
             roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                     "frac": ach / peak, "traffic": TRAFFIC.get((args.config, dom)) if args.scale == 1.0 and world == 1 else None, "algorithmic_bytes_per_launch": ab, "ms_per_launch": per_launch_ms,
                     "share_of_step": kern[dom]["ms_per_step"] / ms_step}
-    # whole-path algorithmic bytes: text in + CSR + node names out
-    out_bytes = 4 * (sz.n_nodes + 1) + 12 * sz.nnz + sz.names_bytes + 8 * (sz.n_nodes + 1)
+    # whole-path algorithmic bytes: text in + result arrays out.  The node-name table (names + offsets,
+    # SURVEY's last term) is NOT counted: it is gathered on demand (k_gather_names, when the caller asks for the node
+    # list) and not inside the timed step.
+    idx = 4
+    dsz = 8
+    if sz.format == _capi.FMT_COO:
+        out_bytes = (2 * idx + dsz) * sz.nnz
+    else:
+        out_bytes = idx * (sz.n_nodes + 1) + (idx + dsz) * sz.nnz
     path_ach = (nbytes + out_bytes) / (ms_step * 1e6)
     # ---- CPU baseline on this host (rank 0, N=1 only; bounded: one full pass of the same text)
     cpu_base = None
@@ -422,6 +521,15 @@ def run_ours(args):
                     "sample": f"full {args.config} text ({nbytes} B), 1 run: C port of parser.py/builders.py + SciPy tocsr/maximum",
                     "host_cores_available": os.cpu_count()}
     gbs = world * nbytes / (ms_step * 1e6)
+    stage_ms = {k: float(diag.ms_stage[i]) for i, k in ((0, "tokenize+hash"), (1, "ids"), (3, "emit"), (4, "sort"), (5, "reduce"))}
+    if world > 1:
+        # the multi-GPU build queues its stages without the single-GPU stage events: group the per-kernel times (rank 0)
+        groups = {"tokenize+hash": ("k_tokenize", "k_tokenize_slow"), "dictionary": ("k_dx_export", "k_dx_owner", "k_dx_insert", "k_dx_reply_first", "k_dx_mark", "k_dx_send_rank",
+                                                                                       "k_dx_reply_ids", "k_dx_localmap", "k_dx_ids", "k_dx_rank"),
+                  "entries": ("k_dx_entries", "k_dxw_count", "k_dxw_scatter", "k_dx_slab_sizes"), "slab": ("k_pairs_count", "k_pairs_scatter", "k_pairsw_count", "k_pairsw_scatter",
+                                                                                                           "k_rows_big", "k_rows_sort", "k_rows_write", "k_dx_final")}
+        stage_ms = {g: sum(kern[k]["ms_per_step"] for k in ks if k in kern) for g, ks in groups.items()}
+        stage_ms["scans"] = sum(v["ms_per_step"] for k, v in kern.items() if k.startswith("k_scan"))
     line = {
         "metric": "gfa_to_csr_parse_build_GBps", "value": gbs, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -436,7 +544,14 @@ def run_ours(args):
         "roofline": roof,
         "kernels": kern,
         "kernel_timing": {"how": "second pass with a CUDA-event pair around every launch", "steps": ksteps, "ms_per_step_with_events": ms_step_profiled},
-        "stage_ms": {k: float(diag.ms_stage[i]) for i, k in ((0, "tokenize+hash"), (1, "ids"), (3, "emit"), (4, "sort"), (5, "reduce"))},
+        "stage_ms": stage_ms,
+        "value_nonspeculative": (world * nbytes / (ms_nonspec * 1e6)) if ms_nonspec else None,
+        "ms_per_step_nonspeculative": ms_nonspec,
+        "first_call_ms": first_call_ms,
+        "speculation": "the timed steps rebuild a text of the same size and mode: buffers are sized from the previous build and the host looks at the "
+                       "counters once, at the end (g2n_set_speculation); value_nonspeculative = the same steps with the host round trip after the "
+                       "tokenizer, first_call_ms = the first build of the process (allocation + capacity discovery, wall clock)",
+        "ingest": {"value": world * nbytes / (ingest_ms * 1e6), "unit": "GB/s", "ms": ingest_ms, "what": "pinned host text -> device copy alone (best of 5, max over ranks)"},
         "cpu_baseline": cpu_base,
         "e2e": {"value": world * nbytes / (e2e_s * 1e9), "unit": "GB/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_s * 1e3, "host_cpus_near_gpu": near,
@@ -455,7 +570,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--config", default="C2", choices=["C2", "C3", "C4", "C5"])
+    ap.add_argument("--config", default="C2", choices=["C2", "C3", "C4", "C4d", "C5"])
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()

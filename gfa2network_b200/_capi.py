@@ -162,6 +162,7 @@ class Handle:
                 "g2n_create failed: no usable CUDA device (the GFA->matrix path has no CPU fallback)")
         self.h = h
         self.device = device
+        self.generation = 0  # bumped by every call that replaces the device-resident result (build, build_file, coo_to_compressed)
 
     def close(self):
         if getattr(self, "h", None):
@@ -231,10 +232,21 @@ class Handle:
         return s
 
     def build(self, text_ptr: int, nbytes: int, params: Params) -> int:
+        self.generation += 1
         return self.lib.g2n_build(self.h, C.c_void_p(text_ptr), nbytes, C.byref(params))
 
     def build_file(self, path: str, params: Params) -> int:
+        self.generation += 1
         return self.lib.g2n_build_file(self.h, os.fsencode(path), C.byref(params))
+
+    def coo_to_compressed(self, row, col, data, nnz: int, n: int, code: int, want: int, indptr, indices, dout) -> int:
+        """Stage K4 alone on caller-provided triplets (g2n_coo_to_compressed); it reuses the handle's device
+        scratch, so whatever build was resident is gone afterwards."""
+        self.generation += 1
+        nnz_out = C.c_uint64()
+        self.check(self.lib.g2n_coo_to_compressed(self.h, row.ctypes.data, col.ctypes.data, data.ctypes.data, nnz, n, code, want,
+                                                  indptr.ctypes.data, indices.ctypes.data, dout.ctypes.data, C.byref(nnz_out)))
+        return int(nnz_out.value)
 
     def convert(self, fmt: int):
         self.check(self.lib.g2n_convert(self.h, fmt))

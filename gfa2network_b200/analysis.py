@@ -63,9 +63,21 @@ def _split_paths(text: bytes, raw_bytes: bool):
 
 def load_paths(path, *, raw_bytes: bool = False):
     """Return mapping of path/walk names to their node lists (analysis.py:164-177)."""
-    # GFAParser streams the WHOLE file: unsupported-record warning and malformed-record errors come from there
-    parse_gfa(path, build_graph=False, build_matrix=True, asymmetric=True)
-    return _split_paths(_text_bytes(path), raw_bytes)
+    # GFAParser streams the WHOLE file: unsupported-record warning and malformed-record errors come from there.
+    # The source is consumed ONCE (stdin, a FIFO or a file object cannot be read twice): the device build and the
+    # host split of the P / O lines see the same bytes.
+    host, dev_ptr, _nbytes, keep = _read_source(path)
+    if isinstance(keep, _FileSource):
+        parse_gfa(keep.path, build_graph=False, build_matrix=True, asymmetric=True)
+        with open(keep.path, "rb") as fh:
+            text = fh.read()
+    elif dev_ptr is not None:
+        parse_gfa(path, build_graph=False, build_matrix=True, asymmetric=True)
+        text = _text_bytes(path)
+    else:
+        parse_gfa(host, build_graph=False, build_matrix=True, asymmetric=True)
+        text = host.tobytes() if not isinstance(keep, (bytes, bytearray)) else bytes(keep)
+    return _split_paths(text, raw_bytes)
 
 
 class _Graph:

@@ -43,19 +43,17 @@ def _default_device() -> int:
 
 
 class _Session:
-    """Ties a returned SciPy matrix to the device-resident result it was fetched from, so that
-    ``convert_format`` can finish COO -> CSR/CSC on the GPU (utils.py:55)."""
-
-    _serial = 0
+    """Ties a returned SciPy matrix to the device-resident result it was fetched from (node map, edge list,
+    distances and the CLI's format conversion are made from that result).  The tie holds only while the result is
+    still the handle's current one: ``Handle.generation`` is bumped by every call that replaces it (``build``,
+    ``build_file``, ``coo_to_compressed``)."""
 
     def __init__(self, handle: _capi.Handle):
-        _Session._serial += 1
         self.handle = handle
-        self.token = _Session._serial
-        handle._current_token = self.token
+        self.generation = handle.generation
 
     def live(self) -> bool:
-        return self.handle.h is not None and getattr(self.handle, "_current_token", None) == self.token
+        return self.handle.h is not None and self.handle.generation == self.generation
 
 
 class _FileSource:
@@ -94,9 +92,19 @@ def _read_source(path):
         else:
             # parser.py:111 open(path, "rb"): the library reads the file itself (g2n_build_file: reader threads ->
             # pinned staging buffers -> device, tokenized piece by piece behind the copy)
-            with open(p, "rb"):  # same FileNotFoundError / PermissionError / IsADirectoryError as the reference
-                pass
-            return None, None, os.path.getsize(p), _FileSource(p)
+            import stat as _stat
+
+            st = os.stat(p)  # FileNotFoundError as the reference's open()
+            if not _stat.S_ISREG(st.st_mode):
+                # FIFOs, /dev/stdin, <(zcat x.gz): read once on the host like the reference's buffered open()
+                # (IsADirectoryError for a directory); never opened twice -- a second open of a FIFO would SIGPIPE the writer
+                with open(p, "rb") as fh:
+                    raw = fh.read()
+                arr = np.frombuffer(raw, dtype=np.uint8)
+                return arr, None, arr.size, raw
+            if not os.access(p, os.R_OK):
+                raise PermissionError(13, "Permission denied", p)
+            return None, None, st.st_size, _FileSource(p)
         arr = np.frombuffer(raw, dtype=np.uint8)
         return arr, None, arr.size, raw
     if hasattr(path, "read"):  # binary file object, parser.py:90-92
@@ -243,9 +251,8 @@ def parse_gfa(
         warnings.warn("overflow encountered in cast", RuntimeWarning, stacklevel=2)
     if not build_matrix:
         return None
-    session = _Session(handle)
     A = _matrix_from_handle(handle)
-    A._g2n_session = session
+    A._g2n_session = _Session(handle)
     if return_node_list:
         return A, _node_list(handle, raw_bytes_id)
     return A

@@ -125,7 +125,7 @@ def main(argv: list[str] | None = None) -> None:
         tsv = sess.handle.fetch_nodes_tsv()
         if not args.raw_bytes_id:
             tsv.tobytes().decode()  # builders.py:287 node.decode() raises UnicodeDecodeError here
-    A = convert_format(A, args.matrix_format, verbose=args.verbose)  # cli.py:239
+    A = convert_format(A, args.matrix_format, verbose=args.verbose, _untouched=True)  # cli.py:239 (A is exactly what parse_gfa returned)
     try:
         save_matrix(A, Path(args.matrix), verbose=args.verbose, max_dense_gb=args.max_dense_gb)
     except MemoryError as exc:  # cli.py:247-248

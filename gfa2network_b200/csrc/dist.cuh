@@ -173,7 +173,7 @@ __device__ __forceinline__ void dx_tail_signal(const DxPeers& X, int e, DxLocal*
 // consecutive elements -- the peers receive whole 128-byte-and-larger pieces instead of one key per lane group.
 #define DXK_PER 4
 #define DXK_SLOTS (256 * DXK_PER)
-__global__ void __launch_bounds__(256) k_dx_export(const TKey* __restrict__ tkeys, const u64* __restrict__ tfirst, u32 cap,
+__global__ void __launch_bounds__(256) k_dx_export(const Slot* __restrict__ slots, u32 cap,
                                                     const u64* __restrict__ tile_base, const DevSizes* __restrict__ ds,
                                                     const DxPeers X, const DxLayout L, DxLocal* __restrict__ loc, u64* __restrict__ klist)
 {
@@ -186,11 +186,15 @@ __global__ void __launch_bounds__(256) k_dx_export(const TKey* __restrict__ tkey
         if (threadIdx.x < DX_MAXW) s_cnt[threadIdx.x] = 0;
         __syncthreads();
         TKey k[DXK_PER];
+        u64 fst[DXK_PER];
         u32 d[DXK_PER], r[DXK_PER];
 #pragma unroll
         for (int u = 0; u < DXK_PER; u++) {
             const u32 i = i0 + u * 256 + threadIdx.x;
-            k[u] = tkeys[i];
+            u64 v[4];
+            ld_slot_stream(&slots[i], v);
+            k[u] = make_ulonglong2(v[0], v[1]);
+            fst[u] = v[2];
             const bool occ = !(k[u].x == 0 && k[u].y == 0);
             d[u] = occ ? dx_owner(k[u].x, k[u].y, X.world) : 0xFFu;
             const u32 m = __match_any_sync(0xffffffffu, d[u]);
@@ -221,7 +225,7 @@ __global__ void __launch_bounds__(256) k_dx_export(const TKey* __restrict__ tkey
             const u32 i = i0 + u * 256 + threadIdx.x;
             const u32 q = s_off[d[u]] + r[u];
             s_key[q] = k[u];
-            s_meta[q] = ((u64)order_bit(tile_base, ~tfirst[i]) << 32) | i;
+            s_meta[q] = ((u64)order_bit(tile_base, ~fst[u]) << 32) | i;
         }
         __syncthreads();
         const u32 total = s_off[X.world];
@@ -243,8 +247,7 @@ __global__ void __launch_bounds__(256) k_dx_export(const TKey* __restrict__ tkey
 }
 
 struct DxOwner {  // the owner's table over the keys it is responsible for
-    TKey* gkeys;
-    u64* gfirst;  // ~min(source rank << 32 | local order)
+    Slot* gslots;  // first = ~min(source rank << 32 | local order)
     u32 gmask;
     u32* gslot;   // [source][position]: table slot of the received key
     u32* gpos;    // [table slot]: position of the key in the segment of its FIRST source
@@ -269,8 +272,8 @@ __global__ void __launch_bounds__(256) k_dx_insert(const DxPeers X, const DxLayo
         if (b) atomicOr(&loc->bad, b);
     }
     ScanParams P;
-    P.tkeys = G.gkeys;
-    P.tfirst = G.gfirst;
+    P.slots = G.gslots;
+    P.slot_cnt = nullptr;
     P.table_mask = G.gmask;
     P.cnt = cnt;
     P.bidirected = 0;
@@ -282,7 +285,7 @@ __global__ void __launch_bounds__(256) k_dx_insert(const DxPeers X, const DxLayo
         const u32* ord = reinterpret_cast<const u32*>(a + L.off_ord) + (u64)s * L.kcap;
         for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
             const TKey k = keys[j];
-            const u32 slot = table_probe(P, k.x, k.y, ((u64)s << 32) | ord[j], claimed);
+            const u32 slot = table_probe(P, k.x, k.y, ((u64)s << 32) | ord[j], false, claimed);
             if (slot == 0xFFFFFFFFu) atomicOr(&loc->bad, DXB_GTABLE);
             G.gslot[(u64)s * L.kcap + j] = slot;
         }
@@ -305,7 +308,7 @@ __global__ void __launch_bounds__(256) k_dx_reply_first(const DxPeers X, const D
                 if (j >= n) break;
                 const u32 g = gs[j];
                 if (g == 0xFFFFFFFFu) continue;
-                const u64 f = ~G.gfirst[g];
+                const u64 f = ~G.gslots[g].first;
                 if ((u32)(f >> 32) == s) {
                     word |= 1u << (8 * t);
                     G.gpos[g] = j;
@@ -346,7 +349,7 @@ __global__ void __launch_bounds__(256) k_dx_mark(const DevSizes* __restrict__ ds
 
 // ---------------------------------------------------------------- x3: first source -> owner, rank inside the shard
 // also this shard's name table: id2slot / name_len are indexed by that rank
-__global__ void __launch_bounds__(256) k_dx_send_rank(const TKey* __restrict__ tkeys, const DevSizes* __restrict__ ds, const DxPeers X,
+__global__ void __launch_bounds__(256) k_dx_send_rank(const Slot* __restrict__ slots, const DevSizes* __restrict__ ds, const DxPeers X,
                                                        const DxLayout L, const u64* __restrict__ klist, const u32* __restrict__ bitmap,
                                                        const u32* __restrict__ wprefix, u32* __restrict__ id2slot, u32* __restrict__ name_len,
                                                        DxLocal* __restrict__ loc)
@@ -364,7 +367,7 @@ __global__ void __launch_bounds__(256) k_dx_send_rank(const TKey* __restrict__ t
             const u32 r = wprefix[wd] + __popc(bitmap[wd] & ((1u << bit) - 1u));
             out[pos] = r;
             id2slot[r] = slot;
-            name_len[r] = slot_key_len(tkeys[slot].y);
+            name_len[r] = slot_key_len(slots[slot].k1);
         }
     }
     // the popcount prefix ends with the number of marked bits = this shard's global firsts
@@ -407,7 +410,7 @@ __global__ void __launch_bounds__(256) k_dx_reply_ids(const DxPeers X, const DxL
             const u32 g = gs[j];
             u32 id = 0;
             if (g != 0xFFFFFFFFu) {
-                const u32 fs = (u32)((~G.gfirst[g]) >> 32);
+                const u32 fs = (u32)((~G.gslots[g].first) >> 32);
                 if (fs < (u32)X.world) {
                     const u32 p = G.gpos[g];
                     if (p < L.kcap) id = s_base[fs] + ranks[(u64)fs * L.kcap + p];

@@ -94,9 +94,9 @@ struct g2n_handle {
     //   zids    first-appearance bitmap, look-back state of its scan
     //   zrows   row histogram, long-row counter, look-back state of the two row scans
     DevBuf zearly, zids, zrows;
-    TKey* d_tkeys = nullptr;
-    u64* d_tfirst = nullptr;
-    u32* d_trep = nullptr;
+    Slot* d_slots = nullptr;
+    u32* d_slot_cnt = nullptr;  // row counters bumped by the tokenizer (NULL: the build counts with a pass over the edge records)
+    int count_mode = CM_NONE;
     Ctl* d_ctl = nullptr;
     Counters* d_cnt = nullptr;
     DevSizes* d_ds = nullptr;
@@ -391,7 +391,7 @@ EmitParams emit_params(g2n_handle* h)
 // Sizes on the host are this build's capacities (cap_n nodes, cap_E edge records): exact after a host
 // round trip, hints in a speculative build; the kernels read the actual ones from DevSizes.
 // `zeroed`: the zrows arena was already laid out and cleared for this build.
-int build_compressed(g2n_handle* h, int fmt, bool zeroed)
+int build_compressed(g2n_handle* h, int fmt, bool zeroed, bool counted)
 {
     const u64 n = h->cap_n;
     const u64 T = h->cap_E * (u64)h->tpe;
@@ -418,7 +418,7 @@ int build_compressed(g2n_handle* h, int fmt, bool zeroed)
         // the histogram (4 bytes per row) stays L2-resident by itself: one pass; the scatter below, whose entries do
         // not, runs once per row range
         const RowPasses rp = row_passes(M, sizeof(u32), n);
-        {
+        if (!counted) {  // (the tokenizer did not count the rows: table far larger than L2, or a later convert)
             const RowRange rr = ROW_RANGE_ALL;
             // IDs are in place already after an earlier convert of the same build
             const int translate = h->edges_are_ids ? 0 : 1;
@@ -428,20 +428,22 @@ int build_compressed(g2n_handle* h, int fmt, bool zeroed)
                 case 2: k_edges_count_flat<2><<<fgrid, 256, 0, h->stream>>>(es, h->slot_id.as<u32>(), h->d_ds, sym, csc, h->d_rowcnt, rr, translate); break;
                 default: k_edges_count_flat<4><<<fgrid, 256, 0, h->stream>>>(es, h->slot_id.as<u32>(), h->d_ds, sym, csc, h->d_rowcnt, rr, translate); break;
             }
+            CK(cudaGetLastError());
+            h->edges_are_ids = true;
         }
-        CK(cudaGetLastError());
-        h->edges_are_ids = true;
         rc = rows_scan(h, n, &h->d_ds->rows);
         if (rc) return rc;
         CK(cudaEventRecord(h->ev[EV_EMIT], h->stream));
         for (u32 ps = 0; ps < rp.count; ps++) {
             const RowRange rr = rp.at(ps, n);
+            const u32* sid = h->edges_are_ids ? nullptr : h->slot_id.as<u32>();  // first pass after a counting tokenizer: slots -> IDs here
             KScope ks(h, "k_edges_scatter_flat");
             switch (h->tpe) {
-                case 1: k_edges_scatter_flat<1><<<fgrid, 256, 0, h->stream>>>(es, h->d_ds, sym, csc, h->cursor.as<u32>(), h->entries.as<u32>(), rr); break;
-                case 2: k_edges_scatter_flat<2><<<fgrid, 256, 0, h->stream>>>(es, h->d_ds, sym, csc, h->cursor.as<u32>(), h->entries.as<u32>(), rr); break;
-                default: k_edges_scatter_flat<4><<<fgrid, 256, 0, h->stream>>>(es, h->d_ds, sym, csc, h->cursor.as<u32>(), h->entries.as<u32>(), rr); break;
+                case 1: k_edges_scatter_flat<1><<<fgrid, 256, 0, h->stream>>>(es, sid, h->d_ds, sym, csc, h->cursor.as<u32>(), h->entries.as<u32>(), rr); break;
+                case 2: k_edges_scatter_flat<2><<<fgrid, 256, 0, h->stream>>>(es, sid, h->d_ds, sym, csc, h->cursor.as<u32>(), h->entries.as<u32>(), rr); break;
+                default: k_edges_scatter_flat<4><<<fgrid, 256, 0, h->stream>>>(es, sid, h->d_ds, sym, csc, h->cursor.as<u32>(), h->entries.as<u32>(), rr); break;
             }
+            h->edges_are_ids = true;
         }
         CK(cudaGetLastError());
     } else {
@@ -453,7 +455,7 @@ int build_compressed(g2n_handle* h, int fmt, bool zeroed)
             E.ids_ready = h->edges_are_ids ? 1 : 0;
             E.write_ids = E.ids_ready ? 0 : 1;
             KScope ks(h, "k_rows_count");
-            k_rows_count<<<egrid, 256, 0, h->stream>>>(E, sym, csc, h->d_rowcnt, h->w_emit.as<double>(), ROW_RANGE_ALL, h->emit_t0.as<u32>());
+            k_rows_count<<<egrid, 256, 0, h->stream>>>(E, sym, csc, counted ? nullptr : h->d_rowcnt, h->w_emit.as<double>(), ROW_RANGE_ALL, h->emit_t0.as<u32>());
         }
         CK(cudaGetLastError());
         h->edges_are_ids = true;
@@ -695,22 +697,21 @@ int g2n_status(g2n_handle* h, g2n_diag* out)
     return G2N_OK;
 }
 
-// zearly arena: keys | first | rep | counters + DevSizes | look-back state of the tile scan
-static int layout_zearly(g2n_handle* h, u32 cap, u32 n_tiles, size_t* bytes)
+// zearly arena: table slots | per-slot row counters (optional) | counters + DevSizes | look-back state of the tile scan
+static int layout_zearly(g2n_handle* h, u32 cap, u32 n_tiles, bool slot_counters, size_t* bytes)
 {
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    const size_t a = up((size_t)cap * sizeof(TKey)), b = up((size_t)cap * sizeof(u64)), c = up((size_t)cap * sizeof(u32));
+    const size_t a = up((size_t)cap * sizeof(Slot)), c = slot_counters ? up((size_t)cap * sizeof(u32)) : 0;
     const size_t d = up(sizeof(Ctl)), e = up(scan_state_bytes(n_tiles));
-    CK(h->zearly.ensure(a + b + c + d + e));
+    CK(h->zearly.ensure(a + c + d + e));
     uint8_t* base = h->zearly.as<uint8_t>();
-    h->d_tkeys = (TKey*)base;
-    h->d_tfirst = (u64*)(base + a);
-    h->d_trep = (u32*)(base + a + b);
-    h->d_ctl = (Ctl*)(base + a + b + c);
+    h->d_slots = (Slot*)base;
+    h->d_slot_cnt = slot_counters ? (u32*)(base + a) : nullptr;
+    h->d_ctl = (Ctl*)(base + a + c);
     h->d_cnt = &h->d_ctl->c;
     h->d_ds = &h->d_ctl->s;
-    h->d_scan_tiles = (u64*)(base + a + b + c + d);
-    *bytes = a + b + c + d + e;
+    h->d_scan_tiles = (u64*)(base + a + c + d);
+    *bytes = a + c + d + e;
     return G2N_OK;
 }
 
@@ -901,7 +902,19 @@ static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, c
         h->table_cap = cap;
         size_t zbytes = 0;
         {
-            int rc = layout_zearly(h, cap, n_tiles, &zbytes);
+            // The tokenizer counts the rows itself (one fire-and-forget atomic per counted mention into a 4-byte-per-slot
+            // side array) while table + counters stay L2-resident; beyond that the flat count pass over the edge records,
+            // whose histogram is 4 bytes per NODE, is cheaper (tools/ubench/randmem.cu: atomics on a working set >> L2 run
+            // at 20 G/s).  Weighted builds walk the tiles for the emission order anyway and count there.
+            bool tokcnt = late_rows && !weighted && (size_t)cap * (sizeof(Slot) + sizeof(u32)) <= ((size_t)80 << 20);
+            if (const char* tc = getenv("G2N_DBG_TOKCNT")) tokcnt = late_rows && !weighted && atoi(tc) != 0;
+            h->count_mode = CM_NONE;
+            if (tokcnt) {
+                const bool sym = h->symmax;
+                if (sym || h->tpe >= 2) h->count_mode = CM_ALL;
+                else h->count_mode = p->want_format == G2N_FMT_CSC ? CM_DST : CM_SRC;
+            }
+            int rc = layout_zearly(h, cap, n_tiles, tokcnt, &zbytes);
             if (rc) return rc;
         }
         CK(cudaMemsetAsync(h->zearly.p, 0, zbytes, h->stream));
@@ -925,9 +938,9 @@ static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, c
         if (n_tiles > 0) {
             P.text = h->d_text;
             P.nbytes = nbytes;
-            P.tkeys = h->d_tkeys;
-            P.tfirst = h->d_tfirst;
-            P.trep = h->d_trep;
+            P.slots = h->d_slots;
+            P.slot_cnt = h->d_slot_cnt;
+            P.count_mode = h->count_mode;
             P.table_mask = cap - 1;
             P.table_max_keys = (u32)(cap / 2 + cap / 4);
             P.n_tiles = n_tiles;
@@ -951,10 +964,7 @@ static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, c
             memcpy(P.wt, h->weight_tag, sizeof(P.wt));
             P.tile_begin = 0;
             P.tile_end = n_tiles;
-            int tm = (P.bidirected ? TM_BIDIR : 0) | (P.slots_per_edge == 4 ? TM_FOUR : 0) | (P.wt_len > 0 ? TM_WEIGHT : 0);
-            // keys + first words far beyond the 126 MB L2: skip the first-appearance atomic when the loaded value says so
-            if ((size_t)cap * (sizeof(TKey) + sizeof(u64)) > ((size_t)96 << 20)) tm |= TM_COND;
-            if (const char* fc = getenv("G2N_DBG_COND")) tm = (tm & ~TM_COND) | (atoi(fc) ? TM_COND : 0);
+            const int tm = (P.bidirected ? TM_BIDIR : 0) | (P.slots_per_edge == 4 ? TM_FOUR : 0) | (P.wt_len > 0 ? TM_WEIGHT : 0);
             // one launch per arrived piece of a host text (the copy of the next piece overlaps this launch)
             const u32 n_launch = h->n_pieces > 1 ? h->n_pieces : 1;
             u32 t_begin = 0;
@@ -981,10 +991,8 @@ static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, c
         }                                                                                                                 \
         k_tokenize<M><<<grid, block, TK_SMEM_BYTES, h->stream>>>(P);                                                      \
     } break;
-                switch (tm) {  // bidirected keys x four slots x weights (the combinations parse_gfa can ask for) x table regime
+                switch (tm) {  // bidirected keys x four slots x weights (the combinations parse_gfa can ask for)
                     G2N_TK(0) G2N_TK(TM_WEIGHT) G2N_TK(TM_BIDIR) G2N_TK(TM_BIDIR | TM_WEIGHT) G2N_TK(TM_BIDIR | TM_FOUR) G2N_TK(TM_BIDIR | TM_FOUR | TM_WEIGHT)
-                    G2N_TK(TM_COND) G2N_TK(TM_COND | TM_WEIGHT) G2N_TK(TM_COND | TM_BIDIR) G2N_TK(TM_COND | TM_BIDIR | TM_WEIGHT)
-                    G2N_TK(TM_COND | TM_BIDIR | TM_FOUR) G2N_TK(TM_COND | TM_BIDIR | TM_FOUR | TM_WEIGHT)
                     default: h->err = "no tokenizer specialisation for this mode"; return G2N_ERR_INTERNAL;
                 }
 #undef G2N_TK
@@ -1006,8 +1014,7 @@ static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, c
                 for (int rep = 0; rep < 5; rep++) {
                     CK(cudaMemsetAsync(h->zearly.p, 0, zbytes, h->stream));
                     cudaEventRecord(e0, h->stream);
-                    if (getenv("G2N_DBG_COND") && atoi(getenv("G2N_DBG_COND"))) k_tokenize<TM_COND><<<grid_for(n_tiles, WT_WARPS, TK_MIN_BLOCKS), WT_WARPS * 32, TK_SMEM_BYTES, h->stream>>>(P);
-                    else k_tokenize<0><<<grid_for(n_tiles, WT_WARPS, TK_MIN_BLOCKS), WT_WARPS * 32, TK_SMEM_BYTES, h->stream>>>(P);
+                    k_tokenize<0><<<grid_for(n_tiles, WT_WARPS, TK_MIN_BLOCKS), WT_WARPS * 32, TK_SMEM_BYTES, h->stream>>>(P);
                     cudaEventRecord(e1, h->stream);
                     CK(cudaStreamSynchronize(h->stream));
                     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
@@ -1114,12 +1121,13 @@ static int ids_phase(g2n_handle* h)
     CK(h->name_len.ensure((n + 1) * sizeof(u32)));
     CK(h->name_off.ensure((n + 2) * sizeof(u64)));
     if (n > 0) {
-        { KScope ks(h, "k_mark_first"); k_mark_first<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->d_tkeys, h->d_tfirst, cap, h->tile_base.as<u64>(), h->d_bitmap, h->d_ds); }
+        { KScope ks(h, "k_mark_first"); k_mark_first<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->d_slots, cap, h->tile_base.as<u64>(), h->d_bitmap, h->d_ds); }
         LoadPopc lp{h->d_bitmap};
         int rc = launch_scan<u32>(h, lp, h->wprefix.as<u32>(), nullptr, words, &h->d_ds->words, h->d_scan_words);
         if (rc) return rc;
-        { KScope ks(h, "k_assign_ids"); k_assign_ids<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->d_tkeys, h->d_tfirst, cap, h->tile_base.as<u64>(), h->d_bitmap, h->wprefix.as<u32>(),
-                                                                 h->slot_id.as<u32>(), h->id2slot.as<u32>(), h->name_len.as<u32>(), h->d_ds); }
+        { KScope ks(h, "k_assign_ids"); k_assign_ids<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->d_slots, cap, h->tile_base.as<u64>(), h->d_bitmap, h->wprefix.as<u32>(),
+                                                                 h->slot_id.as<u32>(), h->id2slot.as<u32>(), h->name_len.as<u32>(), h->d_ds,
+                                                                 h->count_mode != CM_NONE ? h->d_slot_cnt : nullptr, h->d_rowcnt); }
         CK(cudaGetLastError());
     }
     h->names_sized = false;  // name offsets are scanned on demand (g2n_names_bytes / g2n_fetch_names)
@@ -1161,9 +1169,10 @@ static int build_once(g2n_handle* h, const uint8_t* text, uint64_t nbytes, const
     rc = ids_phase(h);
     if (rc) return rc;
     // ---- K3 + K4
-    if (h->symmax) rc = build_compressed(h, p->want_format == G2N_FMT_CSC ? G2N_FMT_CSC : G2N_FMT_CSR, true);
+    const bool counted = h->count_mode != CM_NONE;  // the rows were counted by the tokenizer (rowcnt filled by k_assign_ids)
+    if (h->symmax) rc = build_compressed(h, p->want_format == G2N_FMT_CSC ? G2N_FMT_CSC : G2N_FMT_CSR, true, counted);
     else if (p->want_format == G2N_FMT_NATIVE) rc = build_coo(h);
-    else rc = build_compressed(h, p->want_format, true);
+    else rc = build_compressed(h, p->want_format, true, counted);
     if (rc) return rc;
     return finish_result(h);
 }
@@ -1222,7 +1231,7 @@ int g2n_convert(g2n_handle* h, int32_t want_format)
     h->spec = false;
     h->cap_n = h->n_nodes;
     h->cap_E = h->n_edges;
-    int rc = build_compressed(h, want_format, false);
+    int rc = build_compressed(h, want_format, false, false);
     if (rc) return rc;
     return finish_result(h);
 }
@@ -1298,7 +1307,7 @@ int g2n_fetch_names(g2n_handle* h, uint8_t* names, uint64_t* offsets)
         CK(h->names.ensure(h->names_bytes + 16));
         const u64 nn = names_count(h);
         if (nn > 0) {
-            { KScope ks(h, "k_gather_names"); k_gather_names<<<grid_for(nn, 256), 256, 0, h->stream>>>(h->d_tkeys, h->d_trep, h->id2slot.as<u32>(), h->name_off.as<u64>(),
+            { KScope ks(h, "k_gather_names"); k_gather_names<<<grid_for(nn, 256), 256, 0, h->stream>>>(h->d_slots, h->id2slot.as<u32>(), h->name_off.as<u64>(),
                                                                               (u32)nn, h->d_text, h->longs.as<LongDesc>(),
                                                                               h->names.as<uint8_t>()); }
             CK(cudaGetLastError());
@@ -1331,7 +1340,7 @@ static int build_tsv(g2n_handle* h)
     CK(h->tsv.ensure(h->tsv_bytes + 16));
     if (n > 0) {
         KScope ks(h, "k_tsv_write");
-        k_tsv_write<<<grid_for(n, 256), 256, 0, h->stream>>>(h->d_tkeys, h->d_trep, h->id2slot.as<u32>(), h->tsv_off.as<u64>(), (u32)n, h->d_text,
+        k_tsv_write<<<grid_for(n, 256), 256, 0, h->stream>>>(h->d_slots, h->id2slot.as<u32>(), h->tsv_off.as<u64>(), (u32)n, h->d_text,
                                                               h->longs.as<LongDesc>(), h->tsv.as<uint8_t>());
         CK(cudaGetLastError());
     }
@@ -1375,7 +1384,7 @@ static int build_edge_list(g2n_handle* h)
         EP.ids_ready = 1;  // hand the stored words through untouched; NameSrc maps IDs back to slots if need be
         EP.write_ids = 0;
         NameSrc N;
-        N.tkeys = h->d_tkeys; N.trep = h->d_trep; N.longs = h->longs.as<LongDesc>(); N.text = h->d_text;
+        N.slots = h->d_slots; N.longs = h->longs.as<LongDesc>(); N.text = h->d_text;
         N.id2slot = h->edges_are_ids ? h->id2slot.as<u32>() : nullptr;
         const u32 egrid = grid_for((u64)h->n_tiles * 32, 256);
         { KScope ks(h, "k_edge_line_len"); k_edge_line_len<<<egrid, 256, 0, h->stream>>>(EP, N, h->el_len.as<u32>()); }
@@ -1559,7 +1568,7 @@ int g2n_paths_load(g2n_handle* h, uint64_t* n_paths)
         if (total >= 0x7FFFFFFF00ull) { h->err = "too many path entries"; return G2N_ERR_UNSUPPORTED; }
         CK(h->path_ids.ensure((total + 1) * sizeof(int32_t)));
         PathLookup T;
-        T.tkeys = h->d_tkeys; T.trep = h->d_trep; T.longs = h->longs.as<LongDesc>(); T.slot_id = h->slot_id.as<u32>();
+        T.slots = h->d_slots; T.longs = h->longs.as<LongDesc>(); T.slot_id = h->slot_id.as<u32>();
         T.mask = h->table_cap - 1; T.seed = h->seed_used; T.bidirected = h->params.bidirected ? 1 : 0;
         { KScope ks(h, "k_path_lookup"); k_path_lookup<<<grid_for(n_blocks, 1, 16), 256, 0, h->stream>>>(h->d_text, h->path_recs.as<PathRec>(), R, n_blocks, h->path_off.as<u64>(), T, h->path_ids.as<int32_t>()); }
         CK(cudaGetLastError());
@@ -1686,7 +1695,7 @@ int g2n_coo_to_compressed(g2n_handle* h, const int32_t* row, const int32_t* col,
     CK(h->entries.ensure((nnz_in + 1) * sizeof(u64)));
     {
         size_t zb = 0;
-        int rc0 = layout_zearly(h, 1024, 0, &zb);  // only the control block is used here
+        int rc0 = layout_zearly(h, 1024, 0, false, &zb);  // only the control block is used here
         if (rc0) return rc0;
         rc0 = layout_zrows(h, n);
         if (rc0) return rc0;
@@ -1782,7 +1791,7 @@ int g2n_dist_plan(g2n_handle* h, uint64_t key_cap, uint64_t pair_cap, uint64_t r
     h->dx_recv_cap = recv_cap;
     const u64 want = (u64)h->dxp.world * kcap;
     h->dx_gcap = next_pow2(want + want / 2 < 1024 ? 1024 : want + want / 2);
-    CK(h->dx_zg.ensure((size_t)h->dx_gcap * (sizeof(TKey) + sizeof(u64))));
+    CK(h->dx_zg.ensure((size_t)h->dx_gcap * sizeof(Slot)));
     CK(h->dx_gslot.ensure((size_t)want * sizeof(u32) + 256));
     CK(h->dx_gpos.ensure((size_t)h->dx_gcap * sizeof(u32)));
     return G2N_OK;
@@ -1904,7 +1913,7 @@ int g2n_dist_stage(g2n_handle* h, int stage, const uint8_t* text, uint64_t nbyte
             CK(cudaMemsetAsync(h->zids.p, 0, h->zids_bytes, h->stream));
         }
         CK(cudaMemsetAsync(h->dx_loc.p, 0, sizeof(DxLocal), h->stream));
-        CK(cudaMemsetAsync(h->dx_zg.p, 0, (size_t)h->dx_gcap * (sizeof(TKey) + sizeof(u64)), h->stream));
+        CK(cudaMemsetAsync(h->dx_zg.p, 0, (size_t)h->dx_gcap * sizeof(Slot), h->stream));
         const u64 words = (4 * h->cap_R + 31) / 32 + 1;
         CK(h->wprefix.ensure((words + 2) * sizeof(u32)));
         CK(h->slot_id.ensure((size_t)h->table_cap * sizeof(u32)));
@@ -1923,8 +1932,7 @@ int g2n_dist_stage(g2n_handle* h, int stage, const uint8_t* text, uint64_t nbyte
     const DxCtl* my = h->dx_ctl.as<DxCtl>();
     const u32 cap = h->table_cap;
     DxOwner G;
-    G.gkeys = h->dx_zg.as<TKey>();
-    G.gfirst = (u64*)(h->dx_zg.as<uint8_t>() + (size_t)h->dx_gcap * sizeof(TKey));
+    G.gslots = h->dx_zg.as<Slot>();
     G.gmask = h->dx_gcap - 1;
     G.gslot = h->dx_gslot.as<u32>();
     G.gpos = h->dx_gpos.as<u32>();
@@ -1933,7 +1941,7 @@ int g2n_dist_stage(g2n_handle* h, int stage, const uint8_t* text, uint64_t nbyte
     const int csc = (!sym && h->params.want_format == G2N_FMT_CSC) ? 1 : 0;
     switch (stage) {
     case 0: {
-        { KScope ks(h, "k_dx_export"); k_dx_export<<<grid_for(cap, DXK_SLOTS), 256, 0, h->stream>>>(h->d_tkeys, h->d_tfirst, cap, h->tile_base.as<u64>(), h->d_ds, X, L, loc, h->dx_sent.as<u64>()); }
+        { KScope ks(h, "k_dx_export"); k_dx_export<<<grid_for(cap, DXK_SLOTS), 256, 0, h->stream>>>(h->d_slots, cap, h->tile_base.as<u64>(), h->d_ds, X, L, loc, h->dx_sent.as<u64>()); }
         break;
     }
     case 1: {
@@ -1947,7 +1955,7 @@ int g2n_dist_stage(g2n_handle* h, int stage, const uint8_t* text, uint64_t nbyte
         LoadPopc lp{h->d_bitmap};
         int rc = launch_scan<u32>(h, lp, h->wprefix.as<u32>(), nullptr, words, &h->d_ds->words, h->d_scan_words);
         if (rc) return rc;
-        { KScope ks(h, "k_dx_send_rank"); k_dx_send_rank<<<kgrid, 256, 0, h->stream>>>(h->d_tkeys, h->d_ds, X, L, h->dx_sent.as<u64>(), h->d_bitmap, h->wprefix.as<u32>(), h->id2slot.as<u32>(), h->name_len.as<u32>(), loc); }
+        { KScope ks(h, "k_dx_send_rank"); k_dx_send_rank<<<kgrid, 256, 0, h->stream>>>(h->d_slots, h->d_ds, X, L, h->dx_sent.as<u64>(), h->d_bitmap, h->wprefix.as<u32>(), h->id2slot.as<u32>(), h->name_len.as<u32>(), loc); }
         break;
     }
     case 3: {

@@ -60,14 +60,21 @@ __global__ void k_set_sizes(DevSizes* __restrict__ ds, u32 rows, u32 M)
 }
 
 // bit (global record ordinal << 2 | sub-rank) of `bitmap` set for every occupied slot
-__global__ void __launch_bounds__(256) k_mark_first(const TKey* __restrict__ tkeys, const u64* __restrict__ tfirst, u32 cap,
+// streaming read of one slot: {k0, k1, first, rep}
+__device__ __forceinline__ void ld_slot_stream(const Slot* s, u64 (&v)[4])
+{
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(s));
+}
+
+__global__ void __launch_bounds__(256) k_mark_first(const Slot* __restrict__ slots, u32 cap,
                                                      const u64* __restrict__ tile_base, u32* __restrict__ bitmap, const DevSizes* __restrict__ ds)
 {
     if (!ds->ok) return;
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
-        const TKey k = tkeys[i];
-        if (k.x == 0 && k.y == 0) continue;
-        const u32 bit = order_bit(tile_base, ~tfirst[i]);
+        u64 v[4];
+        ld_slot_stream(&slots[i], v);
+        if (v[0] == 0 && v[1] == 0) continue;
+        const u32 bit = order_bit(tile_base, ~v[2]);
         atomicOr(&bitmap[bit >> 5], 1u << (bit & 31));
     }
 }
@@ -78,41 +85,44 @@ __device__ __forceinline__ u32 slot_key_len(u64 k1)
     return top == 0xFF ? (u32)((k1 >> 32) & 0xFFFFFF) : top - 1;
 }
 
-// slot -> id ; id -> slot ; id -> name length
-__global__ void __launch_bounds__(256) k_assign_ids(const TKey* __restrict__ tkeys, const u64* __restrict__ tfirst, u32 cap,
+// slot -> id ; id -> slot ; id -> name length ; id -> entries of the node's row (when the tokenizer counted them)
+__global__ void __launch_bounds__(256) k_assign_ids(const Slot* __restrict__ slots, u32 cap,
                                                      const u64* __restrict__ tile_base, const u32* __restrict__ bitmap,
                                                      const u32* __restrict__ wprefix, u32* __restrict__ slot_id,
-                                                     u32* __restrict__ id2slot, u32* __restrict__ name_len, const DevSizes* __restrict__ ds)
+                                                     u32* __restrict__ id2slot, u32* __restrict__ name_len, const DevSizes* __restrict__ ds,
+                                                     const u32* __restrict__ slot_cnt, u32* __restrict__ rowcnt)
 {
     if (!ds->ok) return;
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
-        const TKey k = tkeys[i];
-        if (k.x == 0 && k.y == 0) continue;
-        const u32 ob = order_bit(tile_base, ~tfirst[i]);
+        u64 v[4];
+        ld_slot_stream(&slots[i], v);
+        if (v[0] == 0 && v[1] == 0) continue;
+        const u32 ob = order_bit(tile_base, ~v[2]);
         const u32 wd = ob >> 5, bit = ob & 31;
         const u32 id = wprefix[wd] + __popc(bitmap[wd] & ((1u << bit) - 1u));
         slot_id[i] = id;
         id2slot[id] = i;
-        name_len[id] = slot_key_len(k.y);
+        name_len[id] = slot_key_len(v[1]);
+        if (slot_cnt) rowcnt[id] = slot_cnt[i];
     }
 }
 
 // names[name_off[id] ...] = key bytes of node id (builders.py:284-288 node list, raw bytes)
-__global__ void __launch_bounds__(256) k_gather_names(const TKey* __restrict__ tkeys, const u32* __restrict__ trep,
+__global__ void __launch_bounds__(256) k_gather_names(const Slot* __restrict__ slots,
                                                        const u32* __restrict__ id2slot, const u64* __restrict__ name_off, u32 n,
                                                        const uint8_t* __restrict__ text, const LongDesc* __restrict__ longs,
                                                        uint8_t* __restrict__ names)
 {
     for (u32 id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
         const u32 slot = id2slot[id];
-        const TKey k = tkeys[slot];
+        const Slot k = slots[slot];
         uint8_t* dst = names + name_off[id];
-        const u32 top = (u32)(k.y >> 56);
+        const u32 top = (u32)(k.k1 >> 56);
         if (top != 0xFF) {
             const u32 L = top - 1;
-            for (u32 j = 0; j < L; j++) dst[j] = (uint8_t)((j < 8 ? k.x >> (8 * j) : k.y >> (8 * (j - 8))) & 0xFF);
+            for (u32 j = 0; j < L; j++) dst[j] = (uint8_t)((j < 8 ? k.k0 >> (8 * j) : k.k1 >> (8 * (j - 8))) & 0xFF);
         } else {
-            const LongDesc d = longs[trep[slot] - 1];
+            const LongDesc d = longs[k.rep - 1];
             const u32 L = d.base_len + (d.has_ori ? 1 + d.ori_len : 0);
             for (u32 j = 0; j < L; j++) dst[j] = long_byte(text, d, j);
         }
@@ -132,7 +142,7 @@ struct LoadTsvLen {  // bytes of node i's line
     __device__ __forceinline__ u64 operator()(u64 i) const { return (u64)dec_digits((u32)i) + name_len[i] + 2; }
     __device__ __forceinline__ u64 peek(u64 i) const { return (*this)(i); }
 };
-__global__ void __launch_bounds__(256) k_tsv_write(const TKey* __restrict__ tkeys, const u32* __restrict__ trep,
+__global__ void __launch_bounds__(256) k_tsv_write(const Slot* __restrict__ slots,
                                                     const u32* __restrict__ id2slot, const u64* __restrict__ line_off, u32 n,
                                                     const uint8_t* __restrict__ text, const LongDesc* __restrict__ longs,
                                                     uint8_t* __restrict__ out)
@@ -145,14 +155,14 @@ __global__ void __launch_bounds__(256) k_tsv_write(const TKey* __restrict__ tkey
         dst += nd;
         *dst++ = '\t';
         const u32 slot = id2slot[id];
-        const TKey k = tkeys[slot];
-        const u32 top = (u32)(k.y >> 56);
+        const Slot k = slots[slot];
+        const u32 top = (u32)(k.k1 >> 56);
         u32 L;
         if (top != 0xFF) {
             L = top - 1;
-            for (u32 j = 0; j < L; j++) dst[j] = (uint8_t)((j < 8 ? k.x >> (8 * j) : k.y >> (8 * (j - 8))) & 0xFF);
+            for (u32 j = 0; j < L; j++) dst[j] = (uint8_t)((j < 8 ? k.k0 >> (8 * j) : k.k1 >> (8 * (j - 8))) & 0xFF);
         } else {
-            const LongDesc d = longs[trep[slot] - 1];
+            const LongDesc d = longs[k.rep - 1];
             L = d.base_len + (d.has_ori ? 1 + d.ori_len : 0);
             for (u32 j = 0; j < L; j++) dst[j] = long_byte(text, d, j);
         }
@@ -272,28 +282,27 @@ __device__ __forceinline__ void record_triplet(const u32 (&id)[4], int k, u32& r
 // record's endpoint keys -- exactly the node keys of a build with the same --bidirected flag (u:of, v:ot).
 // Two passes over the edge records (line lengths, exclusive scan, bytes), same emission order as the COO.
 struct NameSrc {
-    const TKey* tkeys;
-    const u32* trep;
+    const Slot* slots;
     const LongDesc* longs;
     const uint8_t* text;
     const u32* id2slot;  // non-NULL: edge_slots already hold node IDs
     __device__ __forceinline__ u32 slot_of(u32 v) const { return id2slot ? id2slot[v] : v; }
     __device__ __forceinline__ u32 len(u32 slot) const
     {
-        const TKey k = tkeys[slot];
-        if ((u32)(k.y >> 56) != 0xFF) return slot_key_len(k.y);
-        const LongDesc d = longs[trep[slot] - 1];
+        const Slot k = slots[slot];
+        if ((u32)(k.k1 >> 56) != 0xFF) return slot_key_len(k.k1);
+        const LongDesc d = longs[k.rep - 1];
         return d.base_len + (d.has_ori ? 1 + d.ori_len : 0);
     }
     __device__ __forceinline__ u32 copy(u32 slot, uint8_t* dst) const
     {
-        const TKey k = tkeys[slot];
-        if ((u32)(k.y >> 56) != 0xFF) {
-            const u32 L = slot_key_len(k.y);
-            for (u32 j = 0; j < L; j++) dst[j] = (uint8_t)((j < 8 ? k.x >> (8 * j) : k.y >> (8 * (j - 8))) & 0xFF);
+        const Slot k = slots[slot];
+        if ((u32)(k.k1 >> 56) != 0xFF) {
+            const u32 L = slot_key_len(k.k1);
+            for (u32 j = 0; j < L; j++) dst[j] = (uint8_t)((j < 8 ? k.k0 >> (8 * j) : k.k1 >> (8 * (j - 8))) & 0xFF);
             return L;
         }
-        const LongDesc d = longs[trep[slot] - 1];
+        const LongDesc d = longs[k.rep - 1];
         const u32 L = d.base_len + (d.has_ori ? 1 + d.ori_len : 0);
         for (u32 j = 0; j < L; j++) dst[j] = long_byte(text, d, j);
         return L;

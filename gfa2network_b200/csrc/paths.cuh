@@ -141,8 +141,7 @@ __global__ void __launch_bounds__(256) k_path_count(const uint8_t* __restrict__ 
 }
 
 struct PathLookup {
-    const TKey* tkeys;
-    const u32* trep;
+    const Slot* slots;
     const LongDesc* longs;
     const u32* slot_id;
     u32 mask;
@@ -176,20 +175,18 @@ __device__ __forceinline__ int32_t path_find_node(const PathLookup& T, const uin
     u32 visited = 0;
     while (true) {
         const u32 j = q.slot();
-        const TKey x = T.tkeys[j], y = T.tkeys[j + 1];
-        u32 found = 0xFFFFFFFFu;
-        if (x.x == k0 && x.y == k1) found = j;
-        else if (y.x == k0 && y.y == k1) found = j + 1;
-        if (found != 0xFFFFFFFFu) {
+        const Slot x = T.slots[j];
+        if (x.k0 == k0 && x.k1 == k1) {
+            const u32 found = j;
             if (is_long) {  // same hash: compare the bytes kept for the slot
-                const LongDesc d = T.longs[T.trep[found] - 1];
+                const LongDesc d = T.longs[x.rep - 1];
                 if (d.base_len + (d.has_ori ? 1 + d.ori_len : 0) != len) return -1;
                 for (u32 i = 0; i < len; i++)
                     if (long_byte(text, d, i) != text[a + i]) return -1;
             }
             return (int32_t)T.slot_id[found];
         }
-        if ((x.x == 0 && x.y == 0) || (y.x == 0 && y.y == 0)) return -1;
+        if (x.k0 == 0 && x.k1 == 0) return -1;
         if (!q.next(T.mask, visited)) return -1;
     }
 }

@@ -147,8 +147,10 @@ __global__ void __launch_bounds__(256) k_edges_count_flat(u32* __restrict__ edge
     }
 }
 
+// `slot_id` non-NULL: the records still hold table slots (the tokenizer counted the rows, so no count pass has
+// translated them): translate here and leave the node IDs in place for later passes / converts.
 template <int TPE>
-__global__ void __launch_bounds__(256) k_edges_scatter_flat(const u32* __restrict__ edge_ids, const DevSizes* __restrict__ ds, int sym, int csc,
+__global__ void __launch_bounds__(256) k_edges_scatter_flat(u32* __restrict__ edge_ids, const u32* __restrict__ slot_id, const DevSizes* __restrict__ ds, int sym, int csc,
                                                              u32* __restrict__ cursor, u32* __restrict__ entries, const RowRange rr)
 {
     constexpr int SPE = TPE == 4 ? 4 : 2;
@@ -171,6 +173,23 @@ __global__ void __launch_bounds__(256) k_edges_scatter_flat(const u32* __restric
                 }
             }
         }
+        if (slot_id) {
+#pragma unroll
+            for (int u = 0; u < EF_BATCH; u++) {
+                if (e0 + u * stride < E) {
+#pragma unroll
+                    for (int k = 0; k < SPE; k++) id[u][k] = slot_id[id[u][k]];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < EF_BATCH; u++) {
+                const u32 e = e0 + u * stride;
+                if (e < E) {
+                    if (SPE == 4) reinterpret_cast<uint4*>(edge_ids)[e] = make_uint4(id[u][0], id[u][1], id[u][2], id[u][3]);
+                    else reinterpret_cast<uint2*>(edge_ids)[e] = make_uint2(id[u][0], id[u][1]);
+                }
+            }
+        }
 #pragma unroll
         for (int u = 0; u < EF_BATCH; u++) {
             if (e0 + u * stride < E)
@@ -181,14 +200,14 @@ __global__ void __launch_bounds__(256) k_edges_scatter_flat(const u32* __restric
     }
 }
 
-// histogram of majors; translates edge_slots to node IDs in place and lays the weights out in emission
-// order (w_emit[t]) when there are any
+// histogram of majors (cnt == NULL: the tokenizer counted the rows already); translates edge_slots to node IDs in
+// place and lays the weights out in emission order (w_emit[t]) when there are any
 __global__ void __launch_bounds__(256) k_rows_count(const EmitParams E, int sym, int csc, u32* __restrict__ cnt, double* __restrict__ w_emit,
                                                      const RowRange rr, u32* __restrict__ emit_t0)
 {
     for_each_edge(E, [&](u32 stored, u32 t0, const u32 (&id)[4]) {
         if (emit_t0) emit_t0[stored] = t0;  // emission index of the record's first triplet, for the flat scatter passes
-        record_entries(id, E.tpe, t0, sym, csc, [&](u32 major, u32, u32, u32) { if (rr.has(major)) atomicAdd(&cnt[major], 1u); });
+        if (cnt) record_entries(id, E.tpe, t0, sym, csc, [&](u32 major, u32, u32, u32) { if (rr.has(major)) atomicAdd(&cnt[major], 1u); });
         if (w_emit) {
             const double w = E.edge_w[stored];
             for (int k = 0; k < E.tpe; k++) w_emit[t0 + k] = w;

@@ -37,15 +37,24 @@ struct TileInfo {
     unsigned pad;
 };
 
-// Hash table: open addressing over 32-byte buckets of two 16-byte keys (one 256-bit load = one L2
-// sector per probe step), structure-of-arrays so that the part every mention touches stays small
-// enough to live in L2 (1 M nodes: 32 MB of keys + 16 MB of `first`):
-//   tkeys[slot]  16-byte key: <= 15 inline bytes + (len+1) in the top byte, or a 0xFF-tagged hash for
-//                long keys
-//   tfirst[slot] ~min(order) as u64 (atomicMax, fire and forget)
-//   trep[slot]   long keys only: 1 + index of a LongDesc holding the key's bytes
-typedef ulonglong2 TKey;
-#define TB_SLOTS 2  // keys per bucket
+// Hash table: open addressing over 32-byte slots -- ONE slot = ONE L2 / DRAM sector, fetched with one
+// 256-bit load, so a mention of a known key costs exactly one sector however large the table is (the
+// first-appearance word and the row counter ride in the sector the key compare needs anyway):
+//   k0, k1  16-byte key: <= 15 inline bytes + (len+1) in the top byte, or a 0xFF-tagged hash for long keys
+//   first   ~min(order) over the key's mentions (atomicMax; skipped when the loaded value already covers the mention)
+//   rep     long keys only: 1 + index of a LongDesc holding the key's bytes
+// Measured on B200 (tools/ubench/randmem.cu, profiles/r2_randmem.txt): random 32-byte reads run at 216 G/s from L2 and
+// 43 G/s from HBM (1 GiB working set), 64-byte reads at half that -- DRAM traffic is sector-granular, so the slot must
+// not straddle sectors and nothing a plain mention needs may live in a second array.  A read followed by an atomic
+// on the SAME sector runs at 62 G/s (L2) / 16 G/s (HBM): that is why the per-node row counter is NOT in the slot but
+// in a compact side array (slot_cnt, 4 bytes per slot, only when that array stays L2-resident).
+struct alignas(32) Slot {
+    u64 k0, k1;
+    u64 first;
+    u32 rep;
+    u32 spare;
+};
+typedef ulonglong2 TKey;  // a bare key (exchange arenas of the multi-GPU build)
 
 struct DeferEnt {
     u64 off;  // global offset of the first byte of the line
@@ -98,6 +107,15 @@ struct Ctl {
     DevSizes s;
 };
 
+// slot_cnt = entries of the node's row (K4 major): every endpoint of every edge record when both (r, c) and
+// (c, r) are stored (undirected triplets, max(S, S^T)); the source only for a directed CSR, the target for a
+// directed CSC; nothing when the result is the raw COO
+#define CM_NONE 0
+#define CM_ALL 1
+#define CM_SRC 2
+#define CM_DST 3
+__host__ __device__ __forceinline__ bool cm_counts(int mode, unsigned sub) { return mode == CM_ALL || (mode == CM_SRC && sub == 0) || (mode == CM_DST && sub == 1); }
+
 #define CF_TABLE_FULL 1u
 #define CF_EDGE_FULL 2u
 #define CF_LONG_FULL 4u
@@ -107,10 +125,9 @@ struct Ctl {
 struct ScanParams {
     const uint8_t* text;
     u64 nbytes;
-    TKey* tkeys;
-    u64* tfirst;
-    u32* trep;
-    u32 table_mask;  // slots - 1 (slots is a power of two >= TB_SLOTS)
+    Slot* slots;
+    u32* slot_cnt;   // per slot: row entries the node will own as a K4 major (NULL: counted by a pass over the edge records)
+    u32 table_mask;  // slots - 1 (slots is a power of two >= TG_SLOTS)
     u32 table_max_keys;
     u32* edge_slots;
     double* edge_w;
@@ -129,6 +146,7 @@ struct ScanParams {
     int strip_orientation;
     int wt_len;
     int dtype;  // G2N_DTYPE_* the weights will be cast to (only used to flag float32 overflow)
+    int count_mode;  // which mentions of an edge record bump slot_cnt: CM_* below
     u64 seed;
     uint8_t wt[64];
 };
@@ -188,7 +206,7 @@ __device__ __forceinline__ u64 mix64(u64 x)
     return x;
 }
 
-__device__ __forceinline__ void cas128(TKey* s, u64 n0, u64 n1, u64& o0, u64& o1)
+__device__ __forceinline__ void cas128(Slot* s, u64 n0, u64 n1, u64& o0, u64& o1)
 {
     asm volatile(
         "{\n\t"
@@ -203,7 +221,7 @@ __device__ __forceinline__ void cas128(TKey* s, u64 n0, u64 n1, u64& o0, u64& o1
         : "memory");
 }
 
-// two keys (one 32-byte sector) per 256-bit load; table sectors are kept in L2 (evict_last) while the
+// one slot (one 32-byte sector) per 256-bit load; table sectors are kept in L2 (evict_last) while the
 // text streams through (evict_first)
 __device__ __forceinline__ u64 table_policy()
 {
@@ -211,12 +229,17 @@ __device__ __forceinline__ u64 table_policy()
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
-__device__ __forceinline__ void ld_key2(const TKey* s, u64 (&k)[4], u64 pol)
+// v = {k0, k1, first, rep}
+__device__ __forceinline__ void ld_slot(const Slot* s, u64 (&v)[4], u64 pol)
 {
     asm volatile("ld.global.cg.L2::cache_hint.v4.u64 {%0, %1, %2, %3}, [%4], %5;"
-                 : "=l"(k[0]), "=l"(k[1]), "=l"(k[2]), "=l"(k[3])
+                 : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3])
                  : "l"(s), "l"(pol)
                  : "memory");
+}
+__device__ __forceinline__ void prefetch_slot(const Slot* s)
+{
+    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(s));
 }
 
 // Build the 128-bit table key for a node key.
@@ -255,24 +278,30 @@ __device__ __forceinline__ uint8_t long_byte(const uint8_t* text, const LongDesc
     return text[d.ori_off + (i - d.base_len - 1)];
 }
 
-// Lookup-or-insert of a ready 128-bit key, split in two so that several probes can be in flight:
-// probe_issue() starts the loads of the home slot, probe_finish() walks the probe sequence.
 // Probe sequence.  Sequence graphs name their segments in runs (s1041, s1042, ... / 1041+, 1041-), and
 // links join neighbours, so keys that differ only in their last character are used together.  The
 // table therefore hashes the key WITHOUT its last name character to a group of TG_SLOTS consecutive
-// slots (512 B of keys: a few DRAM bursts / L2 sectors) and lets that character (and the orientation of a
-// bidirected key) pick the bucket inside the group; the sequence continues with the same bucket of
+// slots (1 KiB: one DRAM page burst / eight L2 lines) and lets that character (and the orientation of a
+// bidirected key) pick the slot inside the group; the sequence continues with the same slot of
 // other groups (double hashing over groups).  Any key set works -- clustering only shortens the
-// distance between keys that are likely to be touched together; per-bucket load is that of plain
-// bucketed hashing because the bucket offset is rotated by the hash.
-#define TG_SLOTS 32                      // slots per group
-#define TG_BUCKETS (TG_SLOTS / TB_SLOTS)  // 16 buckets per group
+// distance between keys that are likely to be touched together; per-slot load is that of plain
+// double hashing because the slot offset is rotated by the hash.
+#define TG_SLOTS 32  // slots per group
+// group stride of a key's probe sequence, in slots: an odd number of groups; a function of the whole key so that
+// the hot kernel can compute it lazily (only a mention whose home slot holds another key needs it)
+__device__ __forceinline__ u32 probe_step(u64 k0, u64 k1, u32 mask)
+{
+    u32 s = ((u32)k0 * 0x9E3779B1u) ^ ((u32)(k0 >> 32) * 0x85EBCA77u) ^ ((u32)k1 * 0xC2B2AE3Du) ^ ((u32)(k1 >> 32) * 0x27D4EB2Fu);
+    s ^= s >> 15;
+    return (((s << 1) | 1u) * TG_SLOTS) & mask;
+}
+
 struct ProbeSeq {
     u32 g;     // first slot of the current group
-    u32 boff;  // slot offset of the key's bucket inside every group
-    u32 step;  // group stride in slots: an odd number of groups
+    u32 boff;  // offset of the key's slot inside every group
+    u32 step;  // probe_step of the key
     __device__ __forceinline__ u32 slot() const { return g + boff; }
-    // moves to the next bucket; false when every group has been visited
+    // moves to the next slot; false when every group has been visited
     __device__ __forceinline__ bool next(u32 mask, u32& visited)
     {
         visited += TG_SLOTS;
@@ -282,20 +311,16 @@ struct ProbeSeq {
     }
 };
 
-// (h0, h1): the key with its cluster byte zeroed; c: that byte; ori: 1 for the '-' twin of a bidirected key
-__device__ __forceinline__ ProbeSeq probe_seq_core(u64 h0, u64 h1, u32 c, u32 ori, u32 mask)
+// home slot.  (h0, h1): the key with its cluster byte zeroed; c: that byte; ori: 1 for the '-' twin of a bidirected key
+__device__ __forceinline__ u32 probe_home(u64 h0, u64 h1, u32 c, u32 ori, u32 mask)
 {
     // 32-bit multiply-xorshift mix of the four key words (the quality only matters for speed)
     u32 a = (u32)h0 ^ ((u32)(h0 >> 32) * 0x9E3779B1u) ^ ((u32)h1 * 0x85EBCA77u) ^ ((u32)(h1 >> 32) * 0xC2B2AE3Du);
     a ^= a >> 16; a *= 0x21F0AAADu; a ^= a >> 15; a *= 0x735A2D97u; a ^= a >> 15;
-    const u32 b = (a ^ (u32)(h0 >> 32) ^ (u32)h1) * 0x9E3779B1u;  // further bits: bucket rotation and group stride
-    ProbeSeq q;
+    const u32 b = (a ^ (u32)(h0 >> 32) ^ (u32)h1) * 0x9E3779B1u;  // further bits: slot rotation and group stride
     const u32 gmask = mask & ~(u32)(TG_SLOTS - 1);  // tables are at least TG_SLOTS slots
-    q.g = a & gmask;
-    // ten digits -> ten of the sixteen buckets, rotated per group of keys; the '-' twin sits ten further
-    q.boff = ((c + (b >> 28) + 10u * ori) & (TG_BUCKETS - 1)) * TB_SLOTS;
-    q.step = (((b << 1) | 1u) * TG_SLOTS) & mask;
-    return q;
+    // ten digits -> ten of the thirty-two slots, rotated per group of keys; the '-' twin sits ten further
+    return (a & gmask) + ((c + (b >> 27) + 10u * ori) & (TG_SLOTS - 1));
 }
 
 // The cluster byte of a key is positional: the last byte, or -- for the keys of a bidirected build, which
@@ -317,134 +342,64 @@ __device__ __forceinline__ ProbeSeq probe_seq(u64 k0, u64 k1, u32 mask, int bidi
         c = byte_at(pos);
         if (pos < 8) h0 &= ~(0xFFull << (8 * pos)); else h1 &= ~(0xFFull << (8 * (pos - 8)));
     }
-    return probe_seq_core(h0, h1, c, ori, mask);
-}
-
-struct Probe {
-    u64 k0, k1;
-    u64 b[4];  // the two keys of the current bucket
-    u64 f[2];  // ~min(order) of the two slots of the HOME bucket, loaded together with its keys
+    const u32 home = probe_home(h0, h1, c, ori, mask);
     ProbeSeq q;
-    u32 visited;  // slots' worth of groups left behind (0: still at the home bucket)
-};
-
-__device__ __forceinline__ void ld_first2(const u64* p, u64 (&f)[2], u64 pol)
-{
-    asm volatile("ld.global.cg.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(f[0]), "=l"(f[1]) : "l"(p), "l"(pol) : "memory");
+    q.g = home & ~(u32)(TG_SLOTS - 1);
+    q.boff = home & (TG_SLOTS - 1);
+    q.step = probe_step(k0, k1, mask);
+    return q;
 }
 
-// the loads of the home bucket, for a probe whose sequence (pr.q) is set
-template <bool COND>
-__device__ __forceinline__ void probe_load(const ScanParams& P, Probe& pr, u64 pol)
+// Examines slot i, whose 32 bytes were loaded as v: claims it if it is empty.  True: the slot holds the key now
+// -- min(order) is recorded (atomicMax(~order), skipped when the value that came with the key already covers this
+// mention: files are read roughly in order, so all but the first mention of a key take that exit and never dirty
+// the sector for it) and the row counter is bumped for a counted mention.  False: another key lives here.
+__device__ __forceinline__ bool slot_try(const ScanParams& P, u32 i, u64 k0, u64 k1, const u64 (&v)[4], u64 order, bool count, u32& claimed)
 {
-    pr.visited = 0;
-#ifndef TK_DBG_NOPROBE
-    const u32 i = pr.q.slot();
-    ld_key2(&P.tkeys[i], pr.b, pol);
-    if (COND) ld_first2(&P.tfirst[i], pr.f, pol);
-#endif
-}
-
-// COND: also load the home bucket's `first` words, so that probe_finish can skip the atomic (worth it
-// when the table is much larger than L2: the atomic dirties a DRAM line per mention; measured slower
-// when the table is L2-resident)
-template <bool COND>
-__device__ __forceinline__ void probe_issue(const ScanParams& P, Probe& pr, u64 pol)
-{
-    pr.q = probe_seq(pr.k0, pr.k1, P.table_mask, P.bidirected);
-    probe_load<COND>(P, pr, pol);
-}
-
-// Examines one slot whose key was loaded as (s0, s1): claims it if empty.  Returns true if the slot
-// now holds our key.
-__device__ __forceinline__ bool probe_slot(const ScanParams& P, u32 slot, u64 k0, u64 k1, u64 s0, u64 s1, u32& claimed)
-{
+    u64 s0 = v[0], s1 = v[1], seen = v[2];
     if (s0 == 0 && s1 == 0) {
-        cas128(&P.tkeys[slot], k0, k1, s0, s1);
-        if (s0 == 0 && s1 == 0) { claimed++; return true; }
+        cas128(&P.slots[i], k0, k1, s0, s1);
+        if (s0 == 0 && s1 == 0) { claimed++; s0 = k0; s1 = k1; }
+        seen = 0;  // whoever owns the slot now: its first-appearance word was not loaded with the key
     }
-    return s0 == k0 && s1 == k1;
-}
-
-// One step of a probe whose current bucket is loaded.  True: resolved, `slot` holds the key's slot
-// (0xFFFFFFFF if the table is full; `claimed` is incremented if this call created the key; min(order) is
-// recorded as atomicMax(~order), fire and forget).  False: the next bucket's load is in flight.
-template <bool COND>
-__device__ __forceinline__ bool probe_step(const ScanParams& P, Probe& pr, u64 order, u32& claimed, u64 pol, u32& slot)
-{
-    const u32 i = pr.q.slot();
-#ifdef TK_DBG_NOPROBE
-    slot = i + (u32)(order & 1);  // timing experiment: no table access at all
-    return true;
-#endif
-    // slots are examined in order; an empty slot ends the probe sequence (it is claimed)
-    bool hit = false;
-    if (probe_slot(P, i, pr.k0, pr.k1, pr.b[0], pr.b[1], claimed)) { slot = i; hit = true; }
-    else if (probe_slot(P, i + 1, pr.k0, pr.k1, pr.b[2], pr.b[3], claimed)) { slot = i + 1; hit = true; }
-    if (hit) {
+    if (s0 != k0 || s1 != k1) return false;
 #ifndef TK_DBG_NOMAX
-        // tfirst only ever grows, so a mention that is not earlier than the value loaded with the home bucket
-        // needs no atomic (a stale value can only cause a redundant one).  Files are read roughly in order:
-        // all but the first mention of a key take this exit, and the slot's line is never dirtied again.
-        if (COND) {
-            const u64 seen = pr.visited ? 0ull : (slot == i ? pr.f[0] : pr.f[1]);
-            if (~order > seen) atomicMax(&P.tfirst[slot], ~order);
-        } else {
-            atomicMax(&P.tfirst[slot], ~order);
-        }
+    if (~order > seen) atomicMax(&P.slots[i].first, ~order);
 #endif
-        return true;
-    }
-    if (!pr.q.next(P.table_mask, pr.visited) || pr.visited > 4096u * TG_SLOTS) {
-        atomicOr(&P.cnt->flags, CF_TABLE_FULL);
-        slot = 0xFFFFFFFFu;
-        return true;
-    }
-    ld_key2(&P.tkeys[pr.q.slot()], pr.b, pol);
-    return false;
+    if (count && P.slot_cnt) atomicAdd(&P.slot_cnt[i], 1u);
+    return true;
 }
 
-template <bool COND>
-__device__ __forceinline__ u32 probe_finish(const ScanParams& P, Probe& pr, u64 order, u32& claimed, u64 pol)
-{
-    u32 slot;
-    while (!probe_step<COND>(P, pr, order, claimed, pol, slot)) {}
-    return slot;
-}
-
-// Two probes side by side: when both need another bucket, both loads are in flight before either is
-// waited for (the slower chain of the two sets the pace, not their sum).
-template <bool COND>
-__device__ __forceinline__ void probe_finish2(const ScanParams& P, Probe& a, u64 order_a, Probe& b, u64 order_b, u32& claimed, u64 pol, u32& slot_a, u32& slot_b)
-{
-    bool da = false, db = false;
-    do {
-        if (!da) da = probe_step<COND>(P, a, order_a, claimed, pol, slot_a);
-        if (!db) db = probe_step<COND>(P, b, order_b, claimed, pol, slot_b);
-    } while (!(da && db));
-}
-
-__device__ __forceinline__ u32 table_probe(const ScanParams& P, u64 k0, u64 k1, u64 order, u32& claimed)
+// Lookup-or-insert of a ready 128-bit key; returns its slot (0xFFFFFFFF if the table is full).
+__device__ __forceinline__ u32 table_probe(const ScanParams& P, u64 k0, u64 k1, u64 order, bool count, u32& claimed)
 {
     const u64 pol = table_policy();
-    Probe pr;
-    pr.k0 = k0; pr.k1 = k1;
-    probe_issue<false>(P, pr, pol);
-    return probe_finish<false>(P, pr, order, claimed, pol);
+    ProbeSeq q = probe_seq(k0, k1, P.table_mask, P.bidirected);
+    u32 visited = 0;
+    while (true) {
+        const u32 i = q.slot();
+        u64 v[4];
+        ld_slot(&P.slots[i], v, pol);
+        if (slot_try(P, i, k0, k1, v, order, count, claimed)) return i;
+        if (!q.next(P.table_mask, visited) || visited > 4096u * TG_SLOTS) {
+            atomicOr(&P.cnt->flags, CF_TABLE_FULL);
+            return 0xFFFFFFFFu;
+        }
+    }
 }
 
 // Generic lookup-or-insert from a key descriptor (any length, any orientation string).
-__device__ __forceinline__ u32 table_insert(const ScanParams& P, const Win& w, const KeyDesc& kd, u64 order, u32& claimed)
+__device__ __forceinline__ u32 table_insert(const ScanParams& P, const Win& w, const KeyDesc& kd, u64 order, bool count, u32& claimed)
 {
     u64 k0, k1;
     bool is_long;
     make_key(w, kd, P.seed, k0, k1, is_long);
-    const u32 i = table_probe(P, k0, k1, order, claimed);
+    const u32 i = table_probe(P, k0, k1, order, count, claimed);
     if (i == 0xFFFFFFFFu) return i;
     if (is_long) {
         // keep / verify the bytes behind a hashed key: every arrival is compared with some earlier
         // arrival, so all mentions that share the slot are byte-equal unless `collision` is raised
-        u32 r = ld_volatile_u32(&P.trep[i]);
+        u32 r = ld_volatile_u32(&P.slots[i].rep);
         if (r == 0) {
             const u32 idx = atomicAdd(&P.cnt->n_long, 1u);
             if (idx >= P.long_cap) { atomicOr(&P.cnt->flags, CF_LONG_FULL); return i; }
@@ -453,7 +408,7 @@ __device__ __forceinline__ u32 table_insert(const ScanParams& P, const Win& w, c
             d.ori_len = kd.ori_len; d.ori_char = kd.ori_char; d.has_ori = kd.has_ori;
             P.longs[idx] = d;
             __threadfence();
-            r = atomicExch(&P.trep[i], idx + 1);
+            r = atomicExch(&P.slots[i].rep, idx + 1);
         }
         if (r != 0) {
             __threadfence();

@@ -3,11 +3,17 @@
 //
 // One pass over the text, no dependency between tiles.  Each WARP owns 2 KiB tiles (64 bytes per
 // lane): the tile plus a look-ahead window is fetched into shared memory by the TMA unit (one bulk copy
-// per window, double-buffered: the next window arrives while this one is parsed), the warp classifies
-// '\n' and '\t' 16 bytes at a time into bitmasks, compacts the starts of its record lines with warp shuffles, and
-// parses one line per lane per round from the separator bitmask (no byte loops, no block barriers).
-// Node keys of <= 15 bytes are packed inline into a 128-bit table key and inserted with a 128-bit CAS;
-// the table keeps, per key, the minimum `order` = (tile, record index in tile, sub-rank) -- file
+// per window; the next window is requested as soon as the last line of this one has been parsed and arrives
+// while the tile's node mentions are still being looked up), the warp classifies '\n' and '\t' 16 bytes at a
+// time into bitmasks, compacts the starts of its record lines with warp shuffles, and parses one line per
+// lane per round from the separator bitmask (no byte loops, no block barriers).
+// Parsing and hashing are decoupled: a parsed line only APPENDS its node mentions -- the packed 128-bit
+// key (<= 15 name bytes inline), the key's home slot and where the result goes -- to a per-warp queue in
+// shared memory; the queue is drained 32 mentions at a time, one per lane, so the table code runs with
+// every lane busy and the same instructions whatever mix of S / L / E lines the tile holds (a line-per-
+// lane probe ran at 9 of 32 lanes, profiles/r1_ncu_full.md).  A mention of a known key is ONE 32-byte
+// sector (table.cuh: Slot); new keys are claimed with a 128-bit CAS.
+// The table keeps, per key, the minimum `order` = (tile, record index in tile, sub-rank) -- file
 // order, i.e. the reference's first-appearance order (builders.py:194-198, 219-221) -- so no prefix
 // over earlier tiles is needed while parsing.  Edge records are written to a per-tile range of
 // edge_slots claimed with one atomicAdd; per-tile counts go to tile_info and are scanned afterwards.
@@ -29,7 +35,6 @@ struct Tile {
     const u32* nlm;      // bit o: window byte o is '\n'
     const u32* spm;      // bit o: window byte o is '\t' or '\n'
     u64 wbase;           // global offset of window byte 0 (wraps for tile 0)
-    u64 pol;             // L2 evict_last policy for hash-table sectors
 };
 
 // first separator (TAB or newline) at or after window offset pos; TK_NF if none inside the window
@@ -149,24 +154,6 @@ __device__ __forceinline__ bool fast_weight(const ScanParams& P, const Tile& t, 
 #define TM_BIDIR 1
 #define TM_FOUR 2
 #define TM_WEIGHT 4
-#define TM_COND 8  // conditional first-appearance atomic (table much larger than L2), see probe_issue
-
-template <int MODE>
-__device__ __forceinline__ void node_issue(const ScanParams& P, const Tile& t, Probe& pr, u32 off, u32 len, u32 ori)
-{
-    key_inline(t, off, len, (MODE & TM_BIDIR) != 0, ori, pr.k0, pr.k1);
-    if (len == 0) {
-        probe_issue<(MODE & TM_COND) != 0>(P, pr, t.pol);
-        return;
-    }
-    // the probe sequence from what the parser already knows (same result as probe_seq on the packed key):
-    // the cluster byte is the last character of the name, at key position len - 1
-    const u32 pos = len - 1;
-    u64 h0 = pr.k0, h1 = pr.k1;
-    if (pos < 8) h0 &= ~(0xFFull << (8 * pos)); else h1 &= ~(0xFFull << (8 * (pos - 8)));
-    pr.q = probe_seq_core(h0, h1, t.win[off + pos], ((MODE & TM_BIDIR) && ori == '-') ? 1u : 0u, P.table_mask);
-    probe_load<(MODE & TM_COND) != 0>(P, pr, t.pol);
-}
 
 // the first separators of a short line from one 64-bit slice of the separator mask starting at `pos`
 __device__ __forceinline__ u64 sep_slice(const Tile& t, u32 pos)
@@ -189,38 +176,37 @@ __device__ __forceinline__ void defer_line(const ScanParams& P, u64 off, u32 til
     }
 }
 
-// Common record shapes, parsed from the separator bitmask.  Returns false when the line must go to the
-// generic parser (rare shapes, errors, long keys, fields running past the window).
-// what an edge record leaves behind: the table slots of its endpoints (and the weight); stored by the
-// caller once the tile's range of edge_slots is known
-struct EdgeOut {
-    u32 s0, s1, s2, s3;
+// What a parsed line leaves behind: where its node names sit in the window and how many node mentions it
+// makes (builders.py:190-198 for S, :218-234 for edge records).
+struct LineOut {
+    u32 uo, ul, vo, vl;  // window offset / length of the two names (an S line: both describe its id)
+    u32 ocu, ocv;        // orientation characters (bidirected keys)
+    u32 nm;              // mentions: 0 (P / O), 1 or 2 (S), 2 or 4 (edge record)
+    bool edge;
     double w;
-    bool has;
 };
 
+// Common record shapes, parsed from the separator bitmask.  Returns false when the line must go to the
+// generic parser (rare shapes, errors, long keys, fields running past the window).
 template <int MODE>
-__device__ __forceinline__ bool parse_line_fast(const ScanParams& P, const Tile& t, u32 s, u64 order0, EdgeOut& eo, u32& claimed)
+__device__ __forceinline__ bool parse_line_fast(const ScanParams& P, const Tile& t, u32 s, LineOut& lo)
 {
     constexpr bool BIDIR = (MODE & TM_BIDIR) != 0;
     constexpr bool FOUR = (MODE & TM_FOUR) != 0;
     constexpr bool want_w = (MODE & TM_WEIGHT) != 0;
     const uint8_t c0 = t.win[s];
+    lo.nm = 0; lo.edge = false; lo.w = 1.0;
     if (t.win[s + 1] != '\t') return false;  // record with no fields at all: error paths
     const u32 p1 = s + 2;
     const u32 e1 = find_sep(t, p1);
     if (e1 == TK_NF) return false;
     const u32 maxlen = BIDIR ? 13u : 15u;  // longest base that still fits the inline key
     if (c0 == 'S') {
-        // parser.py:135-163 -> builders.py:190-198: only fields[1] matters
+        // parser.py:135-163 -> builders.py:190-198: only fields[1] matters; bidirected: id:+ then id:-
         const u32 len = e1 - p1;
         if (len > maxlen) return false;
-        Probe a, b;
-        node_issue<MODE>(P, t, a, p1, len, '+');
-        if (BIDIR) node_issue<MODE>(P, t, b, p1, len, '-');
-        u32 sa, sb;
-        if (BIDIR) probe_finish2<(MODE & TM_COND) != 0>(P, a, order0, b, order0 | 1, claimed, t.pol, sa, sb);
-        else probe_finish<(MODE & TM_COND) != 0>(P, a, order0, claimed, t.pol);
+        lo.uo = lo.vo = p1; lo.ul = lo.vl = len; lo.ocu = '+'; lo.ocv = '-';
+        lo.nm = BIDIR ? 2u : 1u;
         return true;
     }
     if (c0 == 'P' || c0 == 'O') return t.win[e1] == '\t';  // >= 3 fields; otherwise the generic parser raises
@@ -277,32 +263,91 @@ __device__ __forceinline__ bool parse_line_fast(const ScanParams& P, const Tile&
     }
     if (P.strip_orientation) { ul = rstrip_pm_win(t, uo, ul); vl = rstrip_pm_win(t, vo, vl); }
     if (ul > maxlen || vl > maxlen) return false;
-    double wv = 1.0;
-    if (want_w && !fast_weight(P, t, tag_from, wv)) return false;
-    // registration order u:of, v:ot, v:flip(ot), u:flip(of)  (builders.py:230-234); two probes in flight
-    Probe na, nb;
-    node_issue<MODE>(P, t, na, uo, ul, oc_u);
-    node_issue<MODE>(P, t, nb, vo, vl, oc_v);
-    u32 su, sv;
-    probe_finish2<(MODE & TM_COND) != 0>(P, na, order0, nb, order0 | 1, claimed, t.pol, su, sv);
-    if (FOUR) {
-        node_issue<MODE>(P, t, na, vo, vl, oc_v == '+' ? '-' : '+');
-        node_issue<MODE>(P, t, nb, uo, ul, oc_u == '+' ? '-' : '+');
-        probe_finish2<(MODE & TM_COND) != 0>(P, na, order0 | 2, nb, order0 | 3, claimed, t.pol, eo.s2, eo.s3);
-    }
-    eo.s0 = su; eo.s1 = sv; eo.w = wv; eo.has = true;
+    if (want_w && !fast_weight(P, t, tag_from, lo.w)) return false;
+    lo.uo = uo; lo.ul = ul; lo.vo = vo; lo.vl = vl; lo.ocu = oc_u; lo.ocv = oc_v;
+    lo.nm = FOUR ? 4u : 2u;
+    lo.edge = true;
     return true;
 }
 
+// ---------------------------------------------------------------- the mention queue
+// One entry per node mention: the packed key, the key's home slot (probe_home) and `meta`:
+//   [11:0]  low bits of the mention's order: record index in the tile << 2 | sub-rank (make_order)
+//   [21:12] index of the edge record inside the tile (the sub-rank is also the position in the record's slot tuple)
+//   [22]    the mention belongs to an edge record (its slot is stored)      [23] it bumps the node's row counter
+#define QM_EDGE (1u << 22)
+#define QM_CNT (1u << 23)
+#define WT_QCAP 160  // <= 31 left over + 32 lines x 4 mentions per round
+
+// per-warp shared memory: the text window, the two bitmasks, the compacted line list, the mention queue, one mbarrier
+struct alignas(128) WarpSmem {
+    uint8_t win[WT_WIN + 32];  // + 32 bytes of '\n' slack read by key_inline
+    ulonglong2 qk[WT_QCAP];
+    u32 list[WT_LIST];  // [15:0] window offset of the line, [31:16] edge index within the tile
+    u32 qs[WT_QCAP];
+    u32 qm[WT_QCAP];
+    u32 nl[WT_WORDS];
+    u32 sp[WT_WORDS + 2];  // + 2 words of slack for sep_slice
+    u64 bar;
+};
+#define TK_SMEM_BYTES (WT_WARPS * sizeof(WarpSmem))
+
 template <int MODE>
-__device__ __forceinline__ void store_edge(const ScanParams& P, const EdgeOut& eo, u32 edge_ord)
+__device__ __forceinline__ void enqueue_mention(const ScanParams& P, const Tile& t, WarpSmem& S, u32 pos, u32 off, u32 len, u32 ori, u32 meta)
 {
-    if (edge_ord >= P.edge_cap) return;  // the host sees edge_alloc > edge_cap and retries with room
-    if (MODE & TM_FOUR) reinterpret_cast<uint4*>(P.edge_slots)[edge_ord] = make_uint4(eo.s0, eo.s1, eo.s2, eo.s3);
-    else reinterpret_cast<uint2*>(P.edge_slots)[edge_ord] = make_uint2(eo.s0, eo.s1);
-    if (MODE & TM_WEIGHT) {
-        P.edge_w[edge_ord] = eo.w;
-        if (P.dtype == G2N_DTYPE_F32 && isfinite(eo.w) && isinf((float)eo.w)) atomicOr(&P.cnt->flags, CF_CAST_OVERFLOW);
+    u64 k0, k1;
+    key_inline(t, off, len, (MODE & TM_BIDIR) != 0, ori, k0, k1);
+    u32 home;
+    if (len == 0) {
+        const ProbeSeq q = probe_seq(k0, k1, P.table_mask, P.bidirected);
+        home = q.slot();
+    } else {
+        // the home slot from what the parser already knows (same result as probe_seq on the packed key):
+        // the cluster byte is the last character of the name, at key position len - 1
+        const u32 cp = len - 1;
+        u64 h0 = k0, h1 = k1;
+        if (cp < 8) h0 &= ~(0xFFull << (8 * cp)); else h1 &= ~(0xFFull << (8 * (cp - 8)));
+        home = probe_home(h0, h1, t.win[off + cp], ((MODE & TM_BIDIR) && ori == '-') ? 1u : 0u, P.table_mask);
+    }
+#ifdef TK_PREFETCH
+    prefetch_slot(&P.slots[home]);
+#endif
+    S.qk[pos] = make_ulonglong2(k0, k1);
+    S.qs[pos] = home;
+    S.qm[pos] = meta;
+}
+
+// One group of <= 32 queued mentions, one per lane: lookup-or-insert, first-appearance order, row counter, the
+// slot into the edge record.  Every lane runs the same instructions; only a mention whose home slot holds another
+// key walks on (double hashing over groups, probe_step).
+template <int MODE>
+__device__ __forceinline__ void drain_group(const ScanParams& P, WarpSmem& S, u32 j, bool live, u32 tile, u32 alloc, u64 pol, u32& claimed)
+{
+    constexpr u32 SPE = (MODE & TM_FOUR) ? 4u : 2u;
+    if (!live) return;
+    const ulonglong2 k = S.qk[j];
+    u32 i = S.qs[j];
+    const u32 meta = S.qm[j];
+    const u64 order = ((u64)tile << 12) | (meta & 0xFFFu);
+    u32 visited = 0, step = 0;
+#ifndef TK_DBG_NOPROBE
+    while (true) {
+        u64 v[4];
+        ld_slot(&P.slots[i], v, pol);
+        if (slot_try(P, i, k.x, k.y, v, order, (meta & QM_CNT) != 0, claimed)) break;
+        if (visited == 0) step = probe_step(k.x, k.y, P.table_mask);
+        visited += TG_SLOTS;
+        if (visited > P.table_mask || visited > 4096u * TG_SLOTS) {
+            atomicOr(&P.cnt->flags, CF_TABLE_FULL);
+            i = 0xFFFFFFFFu;
+            break;
+        }
+        i = ((((i & ~(u32)(TG_SLOTS - 1)) + step) & P.table_mask) | (i & (TG_SLOTS - 1)));
+    }
+#endif
+    if (meta & QM_EDGE) {
+        const u32 edge_ord = alloc + ((meta >> 12) & 1023u);
+        if (edge_ord < P.edge_cap) P.edge_slots[(u64)edge_ord * SPE + (meta & 3u)] = i;  // the host sees edge_alloc > edge_cap and retries with room
     }
 }
 
@@ -310,17 +355,6 @@ __device__ __forceinline__ void store_edge(const ScanParams& P, const EdgeOut& e
 #ifndef TK_MIN_BLOCKS
 #define TK_MIN_BLOCKS 3
 #endif
-
-// per-warp shared memory: two text windows (the next tile's window is fetched by the TMA unit while
-// this one is parsed), the two bitmasks, the compacted line list, two mbarriers
-struct alignas(128) WarpSmem {
-    uint8_t win[2][WT_WIN + 32];  // + 32 bytes of '\n' slack read by key_inline
-    u32 nl[WT_WORDS];
-    u32 sp[WT_WORDS + 2];  // + 2 words of slack for sep_slice
-    u32 list[WT_LIST];     // [15:0] window offset of the line, [31:16] edge index within the tile
-    u64 bar[2];
-};
-#define TK_SMEM_BYTES (WT_WARPS * sizeof(WarpSmem))
 
 __device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
 
@@ -358,22 +392,19 @@ __device__ __forceinline__ u32 flags4(u32 f) { return (f * 0x00204081u) >> 28; }
 template <int MODE>
 __global__ void __launch_bounds__(WT_WARPS * 32, TK_MIN_BLOCKS) k_tokenize(const __grid_constant__ ScanParams P)
 {
+    constexpr bool BIDIR = (MODE & TM_BIDIR) != 0;
     extern __shared__ __align__(128) uint8_t s_raw[];
     const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     WarpSmem& S = reinterpret_cast<WarpSmem*>(s_raw)[wid];
     u32* nlm = S.nl;
     u32* spm = S.sp;
     u32* list = S.list;
+    uint8_t* win = S.win;
     const u64 pol_text = policy_evict_first();
     const u64 pol_table = table_policy();
-    if (lane < 8) {
-        reinterpret_cast<u32*>(S.win[0] + WT_WIN)[lane] = 0x0A0A0A0Au;
-        reinterpret_cast<u32*>(S.win[1] + WT_WIN)[lane] = 0x0A0A0A0Au;
-    }
-    if (lane < 2) {
-        spm[WT_WORDS + lane] = 0;
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&S.bar[lane])) : "memory");
-    }
+    if (lane < 8) reinterpret_cast<u32*>(win + WT_WIN)[lane] = 0x0A0A0A0Au;
+    if (lane < 2) spm[WT_WORDS + lane] = 0;
+    if (lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&S.bar)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
     const u32 n_warps = gridDim.x * WT_WARPS;
@@ -381,27 +412,29 @@ __global__ void __launch_bounds__(WT_WARPS * 32, TK_MIN_BLOCKS) k_tokenize(const
     const u64 n16 = P.nbytes & ~15ull;
     auto tma_ok = [&](u32 tile) { return tile > 0 && (u64)tile * WT_TILE - WT_PRE + WT_WIN <= n16; };
     u32 tile = P.tile_begin + blockIdx.x * WT_WARPS + wid;
-    u32 buf = 0, parity = 0;  // bit b of parity: phase the next wait on bar[b] expects
-    if (lane == 0 && tile < P.tile_end && tma_ok(tile)) tma_load(S.win[0], P.text + ((u64)tile * WT_TILE - WT_PRE), WT_WIN, &S.bar[0], pol_text);
+    u32 parity = 0;  // phase the next wait on the mbarrier expects
+    bool fetched = false;  // the window of `tile` has been requested from the TMA unit
+    if (tile < P.tile_end && tma_ok(tile)) {
+        if (lane == 0) tma_load(win, P.text + ((u64)tile * WT_TILE - WT_PRE), WT_WIN, &S.bar, pol_text);
+        fetched = true;
+    }
     u32 aborted = 0;
-    bool pending = false;  // a window fetch for the NEXT tile is in flight
-    bool quick = false;    // this warp's previous tile held at most one record: look for a line start before building masks
-    for (; tile < P.tile_end && !aborted; tile += n_warps, buf ^= 1) {
+    bool quick = false;  // this warp's previous tile held at most one record: look for a line start before building masks
+    for (; tile < P.tile_end && !aborted; tile += n_warps) {
         const u64 t0 = (u64)tile * WT_TILE;
         const u64 wbase = t0 - WT_PRE;  // wraps for tile 0: only ever used as wbase + offset
-        uint8_t* win = S.win[buf];
-        // ---- the other buffer is free (every lane passed the barrier that ends the previous tile): fetch the next window
-        {
-            const u32 nxt = tile + n_warps;
-            pending = nxt < P.tile_end && tma_ok(nxt);
-            if (lane == 0 && pending) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of that buffer vs the async write
-                tma_load(S.win[buf ^ 1], P.text + ((u64)nxt * WT_TILE - WT_PRE), WT_WIN, &S.bar[buf ^ 1], pol_text);
+        const u32 nxt = tile + n_warps;
+        const bool nxt_tma = nxt < P.tile_end && tma_ok(nxt);
+        // requests the next tile's window; every lane is done with this one (called after a __syncwarp)
+        auto fetch_next = [&]() {
+            if (lane == 0 && nxt_tma) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of the window vs the async write
+                tma_load(win, P.text + ((u64)nxt * WT_TILE - WT_PRE), WT_WIN, &S.bar, pol_text);
             }
-        }
-        if (tma_ok(tile)) {
-            mbar_wait(&S.bar[buf], (parity >> buf) & 1u);
-            parity ^= 1u << buf;
+        };
+        if (fetched) {
+            mbar_wait(&S.bar, parity);
+            parity ^= 1u;
         } else {
             // first and last windows: virtual '\n' before byte 0 and after the last byte
 #pragma unroll
@@ -423,6 +456,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, TK_MIN_BLOCKS) k_tokenize(const
             }
             __syncwarp();
         }
+        fetched = nxt_tma;
         // ---- long-line regime (P / W / sequence lines of megabytes, SURVEY 8a row 9: "skipped at full bandwidth"):
         // when this warp's previous tile held at most one record, first look for a line start at all -- a '\n' in
         // window bytes [WT_PRE - 1, WT_PRE + WT_TILE - 1) -- and leave the tile without building any mask if there is none
@@ -443,6 +477,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, TK_MIN_BLOCKS) k_tokenize(const
                     P.tile_info[tile] = ti;
                 }
                 __syncwarp();
+                fetch_next();
                 continue;
             }
         }
@@ -462,7 +497,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, TK_MIN_BLOCKS) k_tokenize(const
             reinterpret_cast<unsigned short*>(spm)[piece] = (unsigned short)(mn | mt);
         }
         __syncwarp();
-        Tile t{win, nlm, spm, wbase, pol_table};
+        Tile t{win, nlm, spm, wbase};
         // ---- line starts in my 64-byte chunk: a line starts right after every '\n'
         const u32 c = 1 + lane * 2;  // mask word of my first 32 bytes (window offset 32 + 64 lane)
         const u64 nl = (u64)nlm[c] | ((u64)nlm[c + 1] << 32);
@@ -493,7 +528,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, TK_MIN_BLOCKS) k_tokenize(const
         const u32 n_rec_tile = tot >> 16, n_edge_tile = tot & 0xFFFFu;
         const u32 my_rec0 = (inc - packed) >> 16, my_edge0 = (inc - packed) & 0xFFFFu;
         // one atomicAdd claims this tile's range of edge_slots; the abort flag rides along.  Both results are
-        // consumed only after the first round of lines has been parsed and probed, so their latency is hidden.
+        // consumed only after the first round of lines has been parsed, so their latency is hidden.
         u32 alloc_l0 = 0, flags_l0 = 0;
         if (lane == 0) {
             if (n_edge_tile) alloc_l0 = atomicAdd(&P.cnt->edge_alloc, n_edge_tile);
@@ -502,9 +537,10 @@ __global__ void __launch_bounds__(WT_WARPS * 32, TK_MIN_BLOCKS) k_tokenize(const
         u32 alloc = 0;
         bool alloc_ready = false;
         u32 claimed = 0;
-        // ---- parse, hash, emit.  Record lines are compacted into `list` (WT_LIST per batch; one batch
+        u32 qn = 0;  // queued mentions (warp-uniform)
+        // ---- parse and enqueue.  Record lines are compacted into `list` (WT_LIST per batch; one batch
         // unless the tile holds very short lines) and handed out one line per lane per round, so
-        // neighbouring lanes parse neighbouring lines.
+        // neighbouring lanes parse neighbouring lines; full groups of 32 mentions are drained after every round.
         for (u32 lo = 0; lo < n_rec_tile; lo += WT_LIST) {
             {
                 u32 ri = my_rec0, ei = my_edge0;
@@ -517,29 +553,72 @@ __global__ void __launch_bounds__(WT_WARPS * 32, TK_MIN_BLOCKS) k_tokenize(const
             }
             __syncwarp();
             const u32 nb = min(n_rec_tile - lo, (u32)WT_LIST);
-            for (u32 i0 = 0; i0 < nb; i0 += 32) {  // uniform trip count: the shuffle below needs every lane
+            for (u32 i0 = 0; i0 < nb; i0 += 32) {  // uniform trip count: the shuffles below need every lane
                 const u32 i = i0 + lane;
-                EdgeOut eo;
-                eo.has = false;
+                LineOut L;
+                L.nm = 0; L.edge = false;
                 bool ok = true;
                 u32 off = 0, eidx = 0;
                 if (i < nb) {
                     const u32 ent = list[i];
                     off = ent & 0xFFFFu;
                     eidx = ent >> 16;
-                    ok = parse_line_fast<MODE>(P, t, off, make_order(tile, lo + i, 0), eo, claimed);
+                    ok = parse_line_fast<MODE>(P, t, off, L);
                 }
                 if (!alloc_ready) {
                     alloc = __shfl_sync(0xffffffffu, alloc_l0, 0);
                     alloc_ready = true;
                 }
-                if (i < nb) {
-                    if (!ok) defer_line(P, wbase + off, tile, lo + i, eidx);
-                    else if (eo.has) store_edge<MODE>(P, eo, alloc + eidx);
+                if (i < nb && !ok) defer_line(P, wbase + off, tile, lo + i, eidx);
+                if (!ok) L.nm = 0;
+                // positions of my mentions in the queue
+                const u32 ninc = warp_incl_scan(L.nm);
+                const u32 pos0 = qn + ninc - L.nm;
+                if (L.nm) {
+                    const u32 rbits = (lo + i) << 2;
+                    u32 meta = rbits;
+                    if (L.edge) {
+                        meta |= (eidx << 12) | QM_EDGE;
+                        if ((MODE & TM_WEIGHT) && alloc + eidx < P.edge_cap) {
+                            P.edge_w[alloc + eidx] = L.w;
+                            if (P.dtype == G2N_DTYPE_F32 && isfinite(L.w) && isinf((float)L.w)) atomicOr(&P.cnt->flags, CF_CAST_OVERFLOW);
+                        }
+                    }
+                    // registration order u:of, v:ot, v:flip(ot), u:flip(of)  (builders.py:230-234); S: id[:+], id:-
+                    const u32 c0m = (L.edge && cm_counts(P.count_mode, 0)) ? QM_CNT : 0u;
+                    enqueue_mention<MODE>(P, t, S, pos0, L.uo, L.ul, L.ocu, meta | c0m);
+                    if (L.nm >= 2) {
+                        const u32 c1m = (L.edge && cm_counts(P.count_mode, 1)) ? QM_CNT : 0u;
+                        enqueue_mention<MODE>(P, t, S, pos0 + 1, L.vo, L.vl, L.ocv, meta | 1u | c1m);
+                    }
+                    if ((MODE & TM_FOUR) && L.nm == 4) {
+                        const u32 cm = cm_counts(P.count_mode, 2) ? QM_CNT : 0u;
+                        enqueue_mention<MODE>(P, t, S, pos0 + 2, L.vo, L.vl, L.ocv == '+' ? '-' : '+', meta | 2u | cm);
+                        enqueue_mention<MODE>(P, t, S, pos0 + 3, L.uo, L.ul, L.ocu == '+' ? '-' : '+', meta | 3u | cm);
+                    }
+                }
+                qn += __shfl_sync(0xffffffffu, ninc, 31);
+                __syncwarp();
+                // drain the full groups; what is left (< 32 mentions) moves to the front of the queue
+                if (qn >= 32) {
+                    const u32 full = qn & ~31u;
+                    for (u32 g = 0; g < full; g += 32) drain_group<MODE>(P, S, g + lane, true, tile, alloc, pol_table, claimed);
+                    const u32 rem = qn - full;
+                    ulonglong2 mk = make_ulonglong2(0, 0);
+                    u32 ms = 0, mm = 0;
+                    if (lane < rem) { mk = S.qk[full + lane]; ms = S.qs[full + lane]; mm = S.qm[full + lane]; }
+                    __syncwarp();
+                    if (lane < rem) { S.qk[lane] = mk; S.qs[lane] = ms; S.qm[lane] = mm; }
+                    qn = rem;
+                    __syncwarp();
                 }
             }
-            __syncwarp();
         }
+        // ---- the window is no longer needed: request the next one, then finish the queue while it arrives
+        __syncwarp();
+        fetch_next();
+        if (!alloc_ready) alloc = __shfl_sync(0xffffffffu, alloc_l0, 0);
+        if (qn) drain_group<MODE>(P, S, lane, lane < qn, tile, alloc, pol_table, claimed);
         if (lane == 0) {
             TileInfo ti;
             ti.n_rec = n_rec_tile; ti.n_edge = n_edge_tile; ti.edge_alloc = alloc_l0; ti.pad = 0;
@@ -551,10 +630,10 @@ __global__ void __launch_bounds__(WT_WARPS * 32, TK_MIN_BLOCKS) k_tokenize(const
 #pragma unroll
         for (int d = 16; d; d >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, d);
         if (lane == 0 && claimed) atomicAdd(&P.cnt->n_keys, claimed);
-        __syncwarp();  // every lane is done with this tile's window, masks and list
+        __syncwarp();  // every lane is done with this tile's masks, list and queue
     }
     // an aborted pass (table / defer list full) must not leave a bulk copy in flight towards its shared memory
-    if (aborted && pending) mbar_wait(&S.bar[buf], (parity >> buf) & 1u);
+    if (aborted && fetched) mbar_wait(&S.bar, parity);
 }
 
 }  // namespace g2n

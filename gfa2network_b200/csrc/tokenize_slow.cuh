@@ -162,12 +162,12 @@ __device__ __forceinline__ void parse_line_body(const ScanParams& P, const Win& 
         if (!next_field(w, cur, f1)) { report_error(P.cnt, p, G2N_PE_S_NO_ID); return; }
         if (P.bidirected) {
             KeyDesc k = node_key(P, w, f1, f1, '+', true);
-            table_insert(P, w, k, order0, claimed);
+            table_insert(P, w, k, order0, false, claimed);
             k.ori_char = '-';
-            table_insert(P, w, k, order0 | 1, claimed);
+            table_insert(P, w, k, order0 | 1, false, claimed);
         } else {
             KeyDesc k = node_key(P, w, f1, f1, 0, true);
-            table_insert(P, w, k, order0, claimed);
+            table_insert(P, w, k, order0, false, claimed);
         }
         return;
     }
@@ -243,8 +243,8 @@ __device__ __forceinline__ void parse_line_body(const ScanParams& P, const Win& 
     // registration order u:of, v:ot, v:flip(ot), u:flip(of)  (builders.py:230-234)
     KeyDesc ku = node_key(P, w, u, e.of, e.ofc, e.of_lit);
     KeyDesc kv = node_key(P, w, v, e.ot, e.otc, e.ot_lit);
-    const u32 su = table_insert(P, w, ku, order0, claimed);
-    const u32 sv = table_insert(P, w, kv, order0 | 1, claimed);
+    const u32 su = table_insert(P, w, ku, order0, cm_counts(P.count_mode, 0), claimed);
+    const u32 sv = table_insert(P, w, kv, order0 | 1, cm_counts(P.count_mode, 1), claimed);
     u32 sv2 = 0, su2 = 0;
     if (P.slots_per_edge == 4) {
         // rev = "-" if ori == "+" else "+"   (builders.py:232-233)
@@ -253,8 +253,8 @@ __device__ __forceinline__ void parse_line_body(const ScanParams& P, const Win& 
         KeyDesc kv2 = kv, ku2 = ku;
         kv2.ori_len = 1; kv2.ori_char = ot_plus ? '-' : '+';
         ku2.ori_len = 1; ku2.ori_char = of_plus ? '-' : '+';
-        sv2 = table_insert(P, w, kv2, order0 | 2, claimed);
-        su2 = table_insert(P, w, ku2, order0 | 3, claimed);
+        sv2 = table_insert(P, w, kv2, order0 | 2, cm_counts(P.count_mode, 2), claimed);
+        su2 = table_insert(P, w, ku2, order0 | 3, cm_counts(P.count_mode, 3), claimed);
     }
     if (edge_ord < P.edge_cap) {
         if (P.slots_per_edge == 4) {

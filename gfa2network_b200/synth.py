@@ -69,6 +69,9 @@ def synth_gfa(n_seg: int, n_link: int, *, seed: int = 2, kind: int = 1, seq_mean
 CONFIGS = {
     "C2": dict(n_seg=1_000_000, n_link=3_000_000, seed=2, kind=1, mode=dict(directed=False), fmt="csr"),
     "C3": dict(n_seg=10_000_000, n_link=30_000_000, seed=3, kind=2, mode=dict(bidirected=True, weight_tag="RC"), fmt="csr"),
+    # BASELINE "directed COO": by the reference's quirk Q6 (builders.py:282-283, utils.py:47-48) `--matrix-format coo` in default
+    # directed mode saves max(S, S^T) as CSR (C4d); only with --asymmetric is the result the raw COO (C4)
     "C4": dict(n_seg=20_000_000, n_link=60_000_000, seed=4, kind=1, n_paths=25, n_walks=25, mode=dict(asymmetric=True), fmt="coo"),
+    "C4d": dict(n_seg=20_000_000, n_link=60_000_000, seed=4, kind=1, n_paths=25, n_walks=25, mode=dict(), fmt="coo"),
     "C5": dict(n_seg=100_000_000, n_link=400_000_000, seed=5, kind=1, seq_mean=270, mode=dict(), fmt="csr"),
 }

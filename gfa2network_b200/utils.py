@@ -20,10 +20,12 @@ def _np_dtype_code(dt: np.dtype):
     return _capi.DTYPES.get(dt.name)
 
 
-def convert_format(A, fmt: str, *, verbose: bool = False):
+def convert_format(A, fmt: str, *, verbose: bool = False, _untouched: bool = False):
     """Convert COO -> *fmt* (``utils.py:40-63``).  ``coo`` returns *A* untouched even when *A*
-    is CSR.  COO -> csr/csc runs on the device: from the resident result of the
-    ``parse_gfa`` call that produced *A*, or by uploading the triplets of any other COO matrix."""
+    is CSR.  COO -> csr/csc runs on the device (stage K4) on the triplets *A* holds NOW, so
+    edits made to ``A.data`` / ``A.row`` / ``A.col`` after ``parse_gfa`` are honoured exactly like the
+    reference's ``A.asformat`` honours them.  ``_untouched`` (internal: the CLI, which converts the matrix it
+    has just parsed) lets the conversion start from the device-resident build instead of re-uploading."""
     fmt = fmt.lower()
     if fmt not in {"csr", "csc", "coo", "dok"}:
         raise ValueError("matrix-format must be csr|csc|coo|dok")
@@ -32,18 +34,18 @@ def convert_format(A, fmt: str, *, verbose: bool = False):
     if verbose:
         start = time.perf_counter()
         print(f"[convert] -> {fmt} …", end="", file=sys.stderr, flush=True)
-    out = _convert(A, fmt)
+    out = _convert(A, fmt, _untouched)
     if verbose:
         print(f" done in {time.perf_counter() - start:,.1f}s", file=sys.stderr)
     return out
 
 
-def _convert(A, fmt: str):
+def _convert(A, fmt: str, untouched: bool = False):
     if A.format == fmt:
         return A  # scipy/_base.py:471-501 asformat: same format -> self
     want = {"csr": _capi.FMT_CSR, "csc": _capi.FMT_CSC}.get(fmt)
     session = getattr(A, "_g2n_session", None)
-    if want is not None and session is not None and session.live() and A.format in ("coo", "csr"):
+    if untouched and want is not None and session is not None and A.format in ("coo", "csr") and session.live():
         from .builders import _matrix_from_handle
 
         session.handle.convert(want)
@@ -64,10 +66,7 @@ def _convert(A, fmt: str):
         indptr = np.empty(n + 1, np.int32)
         indices = np.empty(nnz, np.int32)
         dout = np.empty(nnz, A.dtype)
-        nnz_out = C.c_uint64()
-        h.check(h.lib.g2n_coo_to_compressed(h.h, row.ctypes.data, col.ctypes.data, data.ctypes.data, nnz, n, code, want,
-                                             indptr.ctypes.data, indices.ctypes.data, dout.ctypes.data, C.byref(nnz_out)))
-        k = nnz_out.value
+        k = h.coo_to_compressed(row, col, data, nnz, n, code, want, indptr, indices, dout)
         cls = sp.csr_matrix if fmt == "csr" else sp.csc_matrix
         return cls((dout[:k].copy(), indices[:k].copy(), indptr), shape=A.shape)
     # host-only object formats (dok) and conversions that are not on the GFA->matrix path

@@ -101,8 +101,10 @@ def save_npz_parallel(dest, A, *, level: int = 6, threads: int | None = None) ->
     """Write *A* as a compressed .npz that `scipy.sparse.load_npz` reads back unchanged."""
     dest = Path(dest)
     members = _members(A)
-    if any(v.nbytes >= 0xFFFF0000 for _, v in members):
-        sp.save_npz(dest, A)  # ZIP64 members: leave them to numpy's zipfile writer
+    # no ZIP64 records here: every member AND every offset (so the whole archive; deflate never grows a block by more
+    # than a few bytes per 16 KiB) must stay below 4 GiB -- otherwise leave the file to numpy's zipfile writer
+    if sum(v.nbytes + v.nbytes // 1000 + 4096 for _, v in members) >= 0xFFFF0000:
+        sp.save_npz(dest, A)
         return
     threads = threads or os.cpu_count() or 1
     with ThreadPoolExecutor(max_workers=threads) as pool:
@@ -120,7 +122,8 @@ def save_npz_parallel(dest, A, *, level: int = 6, threads: int | None = None) ->
                 jobs.append(pool.submit(_deflate_block, (parts, j + 1 == len(cuts), level)))
             futures.append((name, jobs))
         central = []
-        with open(dest, "wb") as fh:
+        tmp = dest.with_name(f".{dest.name}.{os.getpid()}.tmp")  # a failure never leaves a truncated archive under the final name
+        with open(tmp, "wb") as fh:
             for name, jobs in futures:
                 fname = (name + ".npy").encode()
                 blocks, crc, usize = [], 0, 0
@@ -132,7 +135,7 @@ def save_npz_parallel(dest, A, *, level: int = 6, threads: int | None = None) ->
                 csize = sum(len(b) for b in blocks)
                 offset = fh.tell()
                 if max(usize, csize, offset) >= 0xFFFFFFFF:
-                    raise OverflowError("member needs ZIP64")  # guarded by the size check above
+                    raise OverflowError("member needs ZIP64")  # (unreachable: guarded by the total-size check above)
                 # local file header: version 2.0, no flags, deflate, DOS date 1980-01-01 (the timestamp is not part of the data)
                 fh.write(struct.pack("<IHHHHHIIIHH", 0x04034B50, 20, 0, 8, 0, 0x0021, crc, csize, usize, len(fname), 0))
                 fh.write(fname)
@@ -146,6 +149,7 @@ def save_npz_parallel(dest, A, *, level: int = 6, threads: int | None = None) ->
                 fh.write(fname)
             cd_size = fh.tell() - cd_start
             fh.write(struct.pack("<IHHHHIIH", 0x06054B50, 0, 0, len(central), len(central), cd_size, cd_start, 0))
+        os.replace(tmp, dest)
 
 
 def write_node_map(handle, dest) -> int:

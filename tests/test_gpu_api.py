@@ -83,6 +83,39 @@ def test_warm_handle_reuse_across_shapes():
         _same(convert_format(A, "csc"), oracle_convert_format(B, "csc"), str(mode))
 
 
+def test_convert_format_honours_the_matrix_it_is_given():
+    """convert_format must convert what A holds NOW (utils.py:55 A.asformat), not a device result that a
+    later build, export or convert has replaced, and not the build's triplets when A was edited in place."""
+    from gfa2network_b200 import convert_format, parse_gfa
+    from gfa2network_b200.export import edge_list_bytes
+    from gfa2network_b200.synth import synth_gfa
+
+    a = synth_gfa(3_000, 9_000, seed=31)
+    b = synth_gfa(2_000, 5_000, seed=32)
+    for mode in (dict(directed=False), dict(asymmetric=True), dict()):
+        A = parse_gfa(a, build_graph=False, build_matrix=True, **mode)
+        want = A.copy().asformat("csr")
+        edge_list_bytes(b)  # rebuilds the shared default handle with another text
+        _same(convert_format(A, "csr"), want, f"after export {mode}")
+        A = parse_gfa(a, build_graph=False, build_matrix=True, **mode)
+        parse_gfa(b, build_graph=False, build_matrix=False)  # build_matrix=False also replaces the device result
+        _same(convert_format(A, "csc"), A.copy().asformat("csc"), f"after parse {mode}")
+        A = parse_gfa(a, build_graph=False, build_matrix=True, **mode)
+        convert_format(A, "csr")  # (the upload replaces the handle's resident result)
+        _same(convert_format(A, "csc"), A.copy().asformat("csc"), f"second convert {mode}")
+        # in-place edits between parse and convert are part of the matrix
+        A = parse_gfa(a, build_graph=False, build_matrix=True, **mode)
+        A.data[:] = 3.0
+        A.data[::7] = 0.5
+        _same(convert_format(A, "csr"), A.copy().asformat("csr"), f"edited {mode}")
+    with pytest.raises(Exception):
+        parse_gfa(b"L\tonly\n", build_graph=False, build_matrix=True)
+    A = parse_gfa(a, build_graph=False, build_matrix=True, directed=False)
+    with pytest.raises(Exception):
+        parse_gfa(b"L\tonly\n", build_graph=False, build_matrix=True)  # a failed parse leaves no result behind
+    _same(convert_format(A, "csr"), A.copy().asformat("csr"), "after a parse error")
+
+
 BAD_LINES = [b"L\ta\n", b"L\ta+\tb-\t0M\n", b"S\n", b"P\tonly\n", b"O\tx\n", b"E\t*\ta\t+\tb\n", b"C\ta\t+\tb\n", b"L\t\tb+\t0M\tx\n",
              b"L\ta\t+\tb\t+\t0M\tRC:i:" + b"9" * 400 + b"\n", b"W\tw\t1\n", b"# c\n", b"\n", b"x\ty\n", b"L\ta\t+\tb\t\xff\t0M\n"]
 

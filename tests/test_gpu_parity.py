@@ -17,12 +17,26 @@ DRB1 = pu.load_json("drb1.json")
 
 
 def _api():
+    """parse + convert.  convert() checks BOTH conversion paths against each other: from the device-resident build
+    (what the CLI does, g2n_convert) while the matrix's session is live, and from the triplets the matrix holds
+    (the public convert_format: upload + stage K4, g2n_coo_to_compressed)."""
     from gfa2network_b200 import convert_format, parse_gfa
 
     def parse(text, **kw):
         return parse_gfa(text, build_graph=False, build_matrix=True, **kw)
 
-    return parse, convert_format
+    def convert(A, fmt):
+        sess = getattr(A, "_g2n_session", None)
+        resident = {f: convert_format(A, f, _untouched=True) for f in ("csr", "csc")} if sess is not None and sess.live() else {}
+        out = convert_format(A, fmt)
+        if fmt in resident:
+            r = resident[fmt]
+            assert r.format == out.format and r.dtype == out.dtype and r.shape == out.shape
+            for x, y in ((r.indptr, out.indptr), (r.indices, out.indices), (r.data, out.data)):
+                assert x.dtype == y.dtype and np.array_equal(x, y, equal_nan=True), fmt
+        return out
+
+    return parse, convert
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
