@@ -13,13 +13,17 @@ namespace g2n {
 // Tokenizer geometry: one warp owns one 2 KiB tile (64 bytes per lane) plus a look-ahead window.
 #define WT_TILE 2048
 #define WT_PRE 32
-#define WT_LOOK 992
-#define WT_WIN (WT_PRE + WT_TILE + WT_LOOK)  // 3072 bytes staged per tile
+#ifndef WT_LOOK
+#define WT_LOOK 480  // look-ahead past the tile: what a line that starts in the tile may use; longer lines go to the generic parser
+#endif
+#define WT_WIN (WT_PRE + WT_TILE + WT_LOOK)  // 2560 bytes staged per tile
 #define WT_WORDS (WT_WIN / 32)               // 32-bit mask words covering the window
 #ifndef WT_WARPS
 #define WT_WARPS 8                           // warps (tiles in flight) per CTA
 #endif
+#ifndef WT_LIST
 #define WT_LIST 256                          // record lines per batch of the compacted list
+#endif
 #define TK_NF 0xFFFFFFFFu
 
 // `order` of a node mention: [63:12] tile, [11:2] record index within the tile (a 2 KiB tile holds at
@@ -76,18 +80,23 @@ struct Counters {  // all-zero at the start of a build (one memset)
     u64 first_unknown_inv;  // max ~(line_offset << 8 | first byte); 0 if none
     u32 n_records;
     u32 n_edges;
-    u32 n_keys;
     u32 n_long;
     u32 flags;
-    u32 edge_alloc;  // edge_slots entries handed out so far (one atomicAdd per tile)
     u32 scan_ticket;
     u32 collision;
     u32 n_defer;
     u32 pad0;
     u64 nnz;
     u64 aux[4];
-    u64 phase[8];  // -DTK_TIMING: clock64() cycles per kernel phase, summed over CTAs (thread 0 view)
+    u64 pad1[5];
+    // the two words every tile of the tokenizer bumps sit in 128-byte lines of their own: the L2 serialises atomics per
+    // line, and the tile's `flags` poll must not queue behind them
+    u32 edge_alloc;  // edge_slots entries handed out so far (one atomicAdd per tile)
+    u32 pad2[31];
+    u32 n_keys;
+    u32 pad3[31];
 };
+static_assert(sizeof(Counters) == 128 * 3, "Counters layout");
 // Sizes of the current build, resident in device memory so that no kernel after the tokenizer needs a
 // host round trip: k_sizes (ids.cuh) derives them from the counters, later kernels read what they need.
 struct DevSizes {

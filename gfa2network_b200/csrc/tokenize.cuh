@@ -271,29 +271,44 @@ __device__ __forceinline__ bool parse_line_fast(const ScanParams& P, const Tile&
 }
 
 // ---------------------------------------------------------------- the mention queue
-// One entry per node mention: the packed key, the key's home slot (probe_home) and `meta`:
-//   [11:0]  low bits of the mention's order: record index in the tile << 2 | sub-rank (make_order)
-//   [21:12] index of the edge record inside the tile (the sub-rank is also the position in the record's slot tuple)
-//   [22]    the mention belongs to an edge record (its slot is stored)      [23] it bumps the node's row counter
-#define QM_EDGE (1u << 22)
-#define QM_CNT (1u << 23)
-#define WT_QCAP 160  // <= 31 left over + 32 lines x 4 mentions per round
+// A ring per warp that lives ACROSS tiles.  One entry per node mention: the packed key and
+//   x.x  the slot to look at next (home slot first: probe_home)        x.z  tile (high bits of the mention's order)
+//   x.w  where the result goes: index of the edge record in edge_slots (absolute)
+//   x.y  meta: [11:0] low bits of the order (record index in the tile << 2 | sub-rank = position in the record's slot tuple)
+//              [12] the mention belongs to an edge record (its slot is stored)   [13] it bumps the node's row counter
+//              [31:24] probes made so far
+// The queue is drained in groups of 32, one mention per lane, and a group does ONE probe step: a mention whose slot
+// holds another key goes back to the tail with its next slot (double hashing over groups, probe_step) and is looked at
+// again with a later group.  So every lane is busy in the table code whatever the chain lengths are (looping inside the
+// group ran at 10 - 14 of 32 lanes, profiles/r2_ncu_tokenize.md), the line mix of a tile does not matter, and tiles with
+// a handful of records (segments with long sequences) share groups with their successors.  (Measured and dropped:
+// prefetching the home slot into L2 at enqueue time with the drain lagging a round behind -- C5 shape at 5 %: 2.91 ms
+// against 2.69 ms without; the extra L2 request per mention costs more than the shorter wait saves.)
+#define QM_EDGE (1u << 12)
+#define QM_CNT (1u << 13)
+#ifndef WT_QCAP
+#define WT_QCAP 160  // <= TK_LAG + 31 left over + 32 lines x 2 mentions per round, or 31 + 32 x 4 for bidirected records
+#endif
+#ifndef TK_LAG
+#define TK_LAG 64    // mentions left queued by the drain that follows a round (records with two mentions)
+#endif
 
 // per-warp shared memory: the text window, the two bitmasks, the compacted line list, the mention queue, one mbarrier
 struct alignas(128) WarpSmem {
     uint8_t win[WT_WIN + 32];  // + 32 bytes of '\n' slack read by key_inline
     ulonglong2 qk[WT_QCAP];
+    uint4 qx[WT_QCAP];
     u32 list[WT_LIST];  // [15:0] window offset of the line, [31:16] edge index within the tile
-    u32 qs[WT_QCAP];
-    u32 qm[WT_QCAP];
     u32 nl[WT_WORDS];
     u32 sp[WT_WORDS + 2];  // + 2 words of slack for sep_slice
     u64 bar;
 };
 #define TK_SMEM_BYTES (WT_WARPS * sizeof(WarpSmem))
 
+__device__ __forceinline__ u32 q_wrap(u32 pos) { return pos >= WT_QCAP ? pos - WT_QCAP : pos; }
+
 template <int MODE>
-__device__ __forceinline__ void enqueue_mention(const ScanParams& P, const Tile& t, WarpSmem& S, u32 pos, u32 off, u32 len, u32 ori, u32 meta)
+__device__ __forceinline__ void enqueue_mention(const ScanParams& P, const Tile& t, WarpSmem& S, u32 idx, u32 off, u32 len, u32 ori, u32 meta, u32 tile, u32 edge_ord)
 {
     u64 k0, k1;
     key_inline(t, off, len, (MODE & TM_BIDIR) != 0, ori, k0, k1);
@@ -309,45 +324,85 @@ __device__ __forceinline__ void enqueue_mention(const ScanParams& P, const Tile&
         if (cp < 8) h0 &= ~(0xFFull << (8 * cp)); else h1 &= ~(0xFFull << (8 * (cp - 8)));
         home = probe_home(h0, h1, t.win[off + cp], ((MODE & TM_BIDIR) && ori == '-') ? 1u : 0u, P.table_mask);
     }
-#ifdef TK_PREFETCH
-    prefetch_slot(&P.slots[home]);
-#endif
-    S.qk[pos] = make_ulonglong2(k0, k1);
-    S.qs[pos] = home;
-    S.qm[pos] = meta;
+    S.qk[idx] = make_ulonglong2(k0, k1);
+    S.qx[idx] = make_uint4(home, meta, tile, edge_ord);
 }
 
-// One group of <= 32 queued mentions, one per lane: lookup-or-insert, first-appearance order, row counter, the
-// slot into the edge record.  Every lane runs the same instructions; only a mention whose home slot holds another
-// key walks on (double hashing over groups, probe_step).
+// the slot sector of the mention at ring position qh + ahead + lane (the lookup's only long-latency access)
+__device__ __forceinline__ void group_load(const ScanParams& P, const WarpSmem& S, u32 qh, u32 qn, u32 ahead, u64 pol, u64 (&v)[4])
+{
+    const u32 lane = threadIdx.x & 31;
+#ifndef TK_DBG_NOPROBE
+    if (ahead + lane < qn) ld_slot(&P.slots[S.qx[q_wrap(qh + ahead + lane)].x], v, pol);
+#endif
+}
+
+// One group of <= 32 queued mentions from the head of the ring, one per lane, ONE probe step each (the slot was
+// loaded into v by group_load): lookup-or-insert, first-appearance order, row counter, the slot into the edge record;
+// unresolved mentions go back to the tail.
 template <int MODE>
-__device__ __forceinline__ void drain_group(const ScanParams& P, WarpSmem& S, u32 j, bool live, u32 tile, u32 alloc, u64 pol, u32& claimed)
+__device__ __forceinline__ void drain_group(const ScanParams& P, WarpSmem& S, u32& qh, u32& qn, const u64 (&v)[4], u32& claimed)
 {
     constexpr u32 SPE = (MODE & TM_FOUR) ? 4u : 2u;
-    if (!live) return;
-    const ulonglong2 k = S.qk[j];
-    u32 i = S.qs[j];
-    const u32 meta = S.qm[j];
-    const u64 order = ((u64)tile << 12) | (meta & 0xFFFu);
-    u32 visited = 0, step = 0;
+    const u32 lane = threadIdx.x & 31;
+    const u32 take = qn < 32u ? qn : 32u;
+    const bool live = lane < take;
+    bool miss = false;
+    ulonglong2 k = make_ulonglong2(0, 0);
+    uint4 x = make_uint4(0, 0, 0, 0);
+    if (live) {
+        const u32 j = q_wrap(qh + lane);
+        k = S.qk[j];
+        x = S.qx[j];
+        u32 i = x.x;
 #ifndef TK_DBG_NOPROBE
-    while (true) {
-        u64 v[4];
-        ld_slot(&P.slots[i], v, pol);
-        if (slot_try(P, i, k.x, k.y, v, order, (meta & QM_CNT) != 0, claimed)) break;
-        if (visited == 0) step = probe_step(k.x, k.y, P.table_mask);
-        visited += TG_SLOTS;
-        if (visited > P.table_mask || visited > 4096u * TG_SLOTS) {
-            atomicOr(&P.cnt->flags, CF_TABLE_FULL);
-            i = 0xFFFFFFFFu;
-            break;
+        const u64 order = ((u64)x.z << 12) | (x.y & 0xFFFu);
+        if (!slot_try(P, i, k.x, k.y, v, order, (x.y & QM_CNT) != 0, claimed)) {
+            const u32 probes = (x.y >> 24) + 1u;
+            if (probes >= 255u || probes * TG_SLOTS > P.table_mask) {
+                atomicOr(&P.cnt->flags, CF_TABLE_FULL);  // the host repeats the pass with a larger table
+                i = 0xFFFFFFFFu;
+            } else {
+                miss = true;
+                x.x = ((((i & ~(u32)(TG_SLOTS - 1)) + probe_step(k.x, k.y, P.table_mask)) & P.table_mask) | (i & (TG_SLOTS - 1)));
+                x.y += 1u << 24;
+            }
         }
-        i = ((((i & ~(u32)(TG_SLOTS - 1)) + step) & P.table_mask) | (i & (TG_SLOTS - 1)));
-    }
 #endif
-    if (meta & QM_EDGE) {
-        const u32 edge_ord = alloc + ((meta >> 12) & 1023u);
-        if (edge_ord < P.edge_cap) P.edge_slots[(u64)edge_ord * SPE + (meta & 3u)] = i;  // the host sees edge_alloc > edge_cap and retries with room
+        if (!miss && (x.y & QM_EDGE) && x.w < P.edge_cap) P.edge_slots[(u64)x.w * SPE + (x.y & 3u)] = i;  // (edge_alloc > edge_cap: the host retries with room)
+    }
+    const u32 mb = __ballot_sync(0xffffffffu, miss);  // every lane has read its entry: the group's places may be reused
+    qh = q_wrap(qh + take);
+    qn -= take;
+    if (miss) {
+        const u32 j = q_wrap(qh + qn + (u32)__popc(mb & ((1u << lane) - 1u)));
+        S.qk[j] = k;
+        S.qx[j] = x;
+    }
+    qn += (u32)__popc(mb);
+    __syncwarp();
+}
+
+// Drains groups while more than `keep` mentions are queued.  The slot sectors of the NEXT group are requested before
+// the current group is worked on, so one L2 / HBM round trip is always in flight behind the table code.
+template <int MODE>
+__device__ __forceinline__ void drain(const ScanParams& P, WarpSmem& S, u32& qh, u32& qn, u32 keep, u64 pol, u32& claimed)
+{
+    if (qn <= keep) return;
+    u64 v[4] = {0, 0, 0, 0}, w[4] = {0, 0, 0, 0};
+    group_load(P, S, qh, qn, 0, pol, v);
+    while (true) {
+        // a second group is certain to be drained if it is there now (what the current group puts back only adds to it)
+        const bool more = qn > keep + 32u;
+        if (more) group_load(P, S, qh, qn, 32, pol, w);
+        drain_group<MODE>(P, S, qh, qn, v, claimed);
+        if (more) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) v[q] = w[q];
+        } else {
+            if (qn <= keep) break;
+            group_load(P, S, qh, qn, 0, pol, v);  // only what the last group put back is left above `keep`
+        }
     }
 }
 
@@ -420,6 +475,9 @@ __global__ void __launch_bounds__(WT_WARPS * 32, TK_MIN_BLOCKS) k_tokenize(const
     }
     u32 aborted = 0;
     bool quick = false;  // this warp's previous tile held at most one record: look for a line start before building masks
+    u32 qh = 0, qn = 0;  // the mention ring: head and fill (warp-uniform)
+    u32 claimed = 0;
+    const u32 lag = 0;  // mentions the drain after a round leaves queued (TK_LAG: measured, no gain -- see the ring's comment)
     for (; tile < P.tile_end && !aborted; tile += n_warps) {
         const u64 t0 = (u64)tile * WT_TILE;
         const u64 wbase = t0 - WT_PRE;  // wraps for tile 0: only ever used as wbase + offset
@@ -457,6 +515,12 @@ __global__ void __launch_bounds__(WT_WARPS * 32, TK_MIN_BLOCKS) k_tokenize(const
             __syncwarp();
         }
         fetched = nxt_tma;
+        // the next window is requested from the TMA unit only when this tile's lines are parsed (one window buffer per warp):
+        // ask L2 for its lines now, so that the bulk copy finds them there
+        if (nxt_tma && lane < (WT_WIN + 127) / 128 + 1) {
+            const u64 po = ((u64)nxt * WT_TILE - WT_PRE) + (u64)lane * 128;
+            if (po < P.nbytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.text + po));
+        }
         // ---- long-line regime (P / W / sequence lines of megabytes, SURVEY 8a row 9: "skipped at full bandwidth"):
         // when this warp's previous tile held at most one record, first look for a line start at all -- a '\n' in
         // window bytes [WT_PRE - 1, WT_PRE + WT_TILE - 1) -- and leave the tile without building any mask if there is none
@@ -536,8 +600,6 @@ __global__ void __launch_bounds__(WT_WARPS * 32, TK_MIN_BLOCKS) k_tokenize(const
         }
         u32 alloc = 0;
         bool alloc_ready = false;
-        u32 claimed = 0;
-        u32 qn = 0;  // queued mentions (warp-uniform)
         // ---- parse and enqueue.  Record lines are compacted into `list` (WT_LIST per batch; one batch
         // unless the tile holds very short lines) and handed out one line per lane per round, so
         // neighbouring lanes parse neighbouring lines; full groups of 32 mentions are drained after every round.
@@ -571,54 +633,40 @@ __global__ void __launch_bounds__(WT_WARPS * 32, TK_MIN_BLOCKS) k_tokenize(const
                 }
                 if (i < nb && !ok) defer_line(P, wbase + off, tile, lo + i, eidx);
                 if (!ok) L.nm = 0;
-                // positions of my mentions in the queue
+                // positions of my mentions in the ring
                 const u32 ninc = warp_incl_scan(L.nm);
-                const u32 pos0 = qn + ninc - L.nm;
+                const u32 pos0 = qh + qn + ninc - L.nm;
                 if (L.nm) {
-                    const u32 rbits = (lo + i) << 2;
-                    u32 meta = rbits;
+                    u32 meta = (lo + i) << 2;
+                    const u32 edge_ord = alloc + eidx;
                     if (L.edge) {
-                        meta |= (eidx << 12) | QM_EDGE;
-                        if ((MODE & TM_WEIGHT) && alloc + eidx < P.edge_cap) {
-                            P.edge_w[alloc + eidx] = L.w;
+                        meta |= QM_EDGE;
+                        if ((MODE & TM_WEIGHT) && edge_ord < P.edge_cap) {
+                            P.edge_w[edge_ord] = L.w;
                             if (P.dtype == G2N_DTYPE_F32 && isfinite(L.w) && isinf((float)L.w)) atomicOr(&P.cnt->flags, CF_CAST_OVERFLOW);
                         }
                     }
                     // registration order u:of, v:ot, v:flip(ot), u:flip(of)  (builders.py:230-234); S: id[:+], id:-
                     const u32 c0m = (L.edge && cm_counts(P.count_mode, 0)) ? QM_CNT : 0u;
-                    enqueue_mention<MODE>(P, t, S, pos0, L.uo, L.ul, L.ocu, meta | c0m);
+                    enqueue_mention<MODE>(P, t, S, q_wrap(pos0), L.uo, L.ul, L.ocu, meta | c0m, tile, edge_ord);
                     if (L.nm >= 2) {
                         const u32 c1m = (L.edge && cm_counts(P.count_mode, 1)) ? QM_CNT : 0u;
-                        enqueue_mention<MODE>(P, t, S, pos0 + 1, L.vo, L.vl, L.ocv, meta | 1u | c1m);
+                        enqueue_mention<MODE>(P, t, S, q_wrap(pos0 + 1), L.vo, L.vl, L.ocv, meta | 1u | c1m, tile, edge_ord);
                     }
                     if ((MODE & TM_FOUR) && L.nm == 4) {
                         const u32 cm = cm_counts(P.count_mode, 2) ? QM_CNT : 0u;
-                        enqueue_mention<MODE>(P, t, S, pos0 + 2, L.vo, L.vl, L.ocv == '+' ? '-' : '+', meta | 2u | cm);
-                        enqueue_mention<MODE>(P, t, S, pos0 + 3, L.uo, L.ul, L.ocu == '+' ? '-' : '+', meta | 3u | cm);
+                        enqueue_mention<MODE>(P, t, S, q_wrap(pos0 + 2), L.vo, L.vl, L.ocv == '+' ? '-' : '+', meta | 2u | cm, tile, edge_ord);
+                        enqueue_mention<MODE>(P, t, S, q_wrap(pos0 + 3), L.uo, L.ul, L.ocu == '+' ? '-' : '+', meta | 3u | cm, tile, edge_ord);
                     }
                 }
                 qn += __shfl_sync(0xffffffffu, ninc, 31);
                 __syncwarp();
-                // drain the full groups; what is left (< 32 mentions) moves to the front of the queue
-                if (qn >= 32) {
-                    const u32 full = qn & ~31u;
-                    for (u32 g = 0; g < full; g += 32) drain_group<MODE>(P, S, g + lane, true, tile, alloc, pol_table, claimed);
-                    const u32 rem = qn - full;
-                    ulonglong2 mk = make_ulonglong2(0, 0);
-                    u32 ms = 0, mm = 0;
-                    if (lane < rem) { mk = S.qk[full + lane]; ms = S.qs[full + lane]; mm = S.qm[full + lane]; }
-                    __syncwarp();
-                    if (lane < rem) { S.qk[lane] = mk; S.qs[lane] = ms; S.qm[lane] = mm; }
-                    qn = rem;
-                    __syncwarp();
-                }
+                if (qn >= lag + 32u) drain<MODE>(P, S, qh, qn, lag + 31u, pol_table, claimed);
             }
         }
-        // ---- the window is no longer needed: request the next one, then finish the queue while it arrives
+        // ---- the window is no longer needed: request the next one
         __syncwarp();
         fetch_next();
-        if (!alloc_ready) alloc = __shfl_sync(0xffffffffu, alloc_l0, 0);
-        if (qn) drain_group<MODE>(P, S, lane, lane < qn, tile, alloc, pol_table, claimed);
         if (lane == 0) {
             TileInfo ti;
             ti.n_rec = n_rec_tile; ti.n_edge = n_edge_tile; ti.edge_alloc = alloc_l0; ti.pad = 0;
@@ -630,10 +678,18 @@ __global__ void __launch_bounds__(WT_WARPS * 32, TK_MIN_BLOCKS) k_tokenize(const
 #pragma unroll
         for (int d = 16; d; d >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, d);
         if (lane == 0 && claimed) atomicAdd(&P.cnt->n_keys, claimed);
-        __syncwarp();  // every lane is done with this tile's masks, list and queue
+        claimed = 0;
+        __syncwarp();  // every lane is done with this tile's masks and list
     }
     // an aborted pass (table / defer list full) must not leave a bulk copy in flight towards its shared memory
     if (aborted && fetched) mbar_wait(&S.bar, parity);
+    // ---- what is still queued (the pass is repeated anyway after an abort)
+    if (!aborted) {
+        drain<MODE>(P, S, qh, qn, 0u, pol_table, claimed);
+#pragma unroll
+        for (int d = 16; d; d >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, d);
+        if (lane == 0 && claimed) atomicAdd(&P.cnt->n_keys, claimed);
+    }
 }
 
 }  // namespace g2n
