@@ -241,6 +241,7 @@ int launch_scan(g2n_handle* h, LoadOp load, Tout* out, Tout* out2, u64 n_cap, co
         state_region = h->scan_state.as<u64>();
     }
     const u32 grid = grid_for(n_tiles, 1, 4);
+    if (h->gang_scan && getenv("G2N_DBG_NOGANG")) h->gang_scan = false;  // timing experiments: look-back scan
     if (h->gang_scan) {
         // all CTAs co-resident (cooperative launch): reduce, grid barrier, scan -- no look-back chain
         KScope ks(h, "k_scan_gang");
@@ -982,14 +983,14 @@ static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, c
                 P.tile_begin = t_begin;
                 P.tile_end = t_end;
                 KScope ks(h, "k_tokenize");
-                const dim3 grid(grid_for(t_end - t_begin, WT_WARPS, TK_MIN_BLOCKS)), block(WT_WARPS * 32);
+                const dim3 block(WT_WARPS * 32);
 #define G2N_TK(M)                                                                                                         \
     case M: {                                                                                                             \
         if (!(h->tk_attr & (1u << (M)))) { /* per handle = per device: the opt-in is a per-device function attribute */ \
-            CK(cudaFuncSetAttribute(k_tokenize<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TK_SMEM_BYTES));    \
+            CK(cudaFuncSetAttribute(k_tokenize<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tk_smem_bytes<M>())); \
             h->tk_attr |= 1u << (M);                                                                                      \
         }                                                                                                                 \
-        k_tokenize<M><<<grid, block, TK_SMEM_BYTES, h->stream>>>(P);                                                      \
+        k_tokenize<M><<<grid_for(t_end - t_begin, WT_WARPS, tk_min_blocks<M>()), block, tk_smem_bytes<M>(), h->stream>>>(P); \
     } break;
                 switch (tm) {  // bidirected keys x four slots x weights (the combinations parse_gfa can ask for)
                     G2N_TK(0) G2N_TK(TM_WEIGHT) G2N_TK(TM_BIDIR) G2N_TK(TM_BIDIR | TM_WEIGHT) G2N_TK(TM_BIDIR | TM_FOUR) G2N_TK(TM_BIDIR | TM_FOUR | TM_WEIGHT)
@@ -1014,7 +1015,7 @@ static int tokenize_phase(g2n_handle* h, const uint8_t* text, uint64_t nbytes, c
                 for (int rep = 0; rep < 5; rep++) {
                     CK(cudaMemsetAsync(h->zearly.p, 0, zbytes, h->stream));
                     cudaEventRecord(e0, h->stream);
-                    k_tokenize<0><<<grid_for(n_tiles, WT_WARPS, TK_MIN_BLOCKS), WT_WARPS * 32, TK_SMEM_BYTES, h->stream>>>(P);
+                    k_tokenize<0><<<grid_for(n_tiles, WT_WARPS, tk_min_blocks<0>()), WT_WARPS * 32, tk_smem_bytes<0>(), h->stream>>>(P);
                     cudaEventRecord(e1, h->stream);
                     CK(cudaStreamSynchronize(h->stream));
                     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);

@@ -286,29 +286,30 @@ __device__ __forceinline__ bool parse_line_fast(const ScanParams& P, const Tile&
 // against 2.69 ms without; the extra L2 request per mention costs more than the shorter wait saves.)
 #define QM_EDGE (1u << 12)
 #define QM_CNT (1u << 13)
-#ifndef WT_QCAP
-#define WT_QCAP 160  // <= TK_LAG + 31 left over + 32 lines x 2 mentions per round, or 31 + 32 x 4 for bidirected records
-#endif
-#ifndef TK_LAG
-#define TK_LAG 64    // mentions left queued by the drain that follows a round (records with two mentions)
-#endif
+// ring capacity: one group stays in flight across a round of lines (< 64 mentions queued) + 32 lines x 2 mentions; or < 32
+// mentions left over + 32 lines x 4 mentions for the records of a bidirected build (which carries no group across rounds:
+// a 192-entry ring at two CTAs per SM was measured slower, C3 shape at 25 %: 1.85 ms against 1.59 ms)
+template <int MODE> struct QCap { static constexpr u32 value = 160u; };
 
 // per-warp shared memory: the text window, the two bitmasks, the compacted line list, the mention queue, one mbarrier
-struct alignas(128) WarpSmem {
+template <u32 QCAP>
+struct alignas(128) WarpSmemT {
+    static constexpr u32 kCap = QCAP;
     uint8_t win[WT_WIN + 32];  // + 32 bytes of '\n' slack read by key_inline
-    ulonglong2 qk[WT_QCAP];
-    uint4 qx[WT_QCAP];
+    ulonglong2 qk[QCAP];
+    uint4 qx[QCAP];
     u32 list[WT_LIST];  // [15:0] window offset of the line, [31:16] edge index within the tile
     u32 nl[WT_WORDS];
     u32 sp[WT_WORDS + 2];  // + 2 words of slack for sep_slice
     u64 bar;
+    static __device__ __forceinline__ u32 wrap(u32 pos) { return pos >= QCAP ? pos - QCAP : pos; }
 };
-#define TK_SMEM_BYTES (WT_WARPS * sizeof(WarpSmem))
-
-__device__ __forceinline__ u32 q_wrap(u32 pos) { return pos >= WT_QCAP ? pos - WT_QCAP : pos; }
+template <int MODE> using WarpSmem = WarpSmemT<QCap<MODE>::value>;
+template <int MODE> constexpr size_t tk_smem_bytes() { return WT_WARPS * sizeof(WarpSmem<MODE>); }
+template <int MODE> constexpr int tk_min_blocks() { return 3; }
 
 template <int MODE>
-__device__ __forceinline__ void enqueue_mention(const ScanParams& P, const Tile& t, WarpSmem& S, u32 idx, u32 off, u32 len, u32 ori, u32 meta, u32 tile, u32 edge_ord)
+__device__ __forceinline__ void enqueue_mention(const ScanParams& P, const Tile& t, WarpSmem<MODE>& S, u32 idx, u32 off, u32 len, u32 ori, u32 meta, u32 tile, u32 edge_ord)
 {
     u64 k0, k1;
     key_inline(t, off, len, (MODE & TM_BIDIR) != 0, ori, k0, k1);
@@ -329,11 +330,12 @@ __device__ __forceinline__ void enqueue_mention(const ScanParams& P, const Tile&
 }
 
 // the slot sector of the mention at ring position qh + ahead + lane (the lookup's only long-latency access)
-__device__ __forceinline__ void group_load(const ScanParams& P, const WarpSmem& S, u32 qh, u32 qn, u32 ahead, u64 pol, u64 (&v)[4])
+template <class SM>
+__device__ __forceinline__ void group_load(const ScanParams& P, const SM& S, u32 qh, u32 qn, u32 ahead, u64 pol, u64 (&v)[4])
 {
     const u32 lane = threadIdx.x & 31;
 #ifndef TK_DBG_NOPROBE
-    if (ahead + lane < qn) ld_slot(&P.slots[S.qx[q_wrap(qh + ahead + lane)].x], v, pol);
+    if (ahead + lane < qn) ld_slot(&P.slots[S.qx[SM::wrap(qh + ahead + lane)].x], v, pol);
 #endif
 }
 
@@ -341,8 +343,9 @@ __device__ __forceinline__ void group_load(const ScanParams& P, const WarpSmem& 
 // loaded into v by group_load): lookup-or-insert, first-appearance order, row counter, the slot into the edge record;
 // unresolved mentions go back to the tail.
 template <int MODE>
-__device__ __forceinline__ void drain_group(const ScanParams& P, WarpSmem& S, u32& qh, u32& qn, const u64 (&v)[4], u32& claimed)
+__device__ __forceinline__ void drain_group(const ScanParams& P, WarpSmem<MODE>& S, u32& qh, u32& qn, const u64 (&v)[4], u32& claimed)
 {
+    typedef WarpSmem<MODE> SM;
     constexpr u32 SPE = (MODE & TM_FOUR) ? 4u : 2u;
     const u32 lane = threadIdx.x & 31;
     const u32 take = qn < 32u ? qn : 32u;
@@ -351,7 +354,7 @@ __device__ __forceinline__ void drain_group(const ScanParams& P, WarpSmem& S, u3
     ulonglong2 k = make_ulonglong2(0, 0);
     uint4 x = make_uint4(0, 0, 0, 0);
     if (live) {
-        const u32 j = q_wrap(qh + lane);
+        const u32 j = SM::wrap(qh + lane);
         k = S.qk[j];
         x = S.qx[j];
         u32 i = x.x;
@@ -372,10 +375,10 @@ __device__ __forceinline__ void drain_group(const ScanParams& P, WarpSmem& S, u3
         if (!miss && (x.y & QM_EDGE) && x.w < P.edge_cap) P.edge_slots[(u64)x.w * SPE + (x.y & 3u)] = i;  // (edge_alloc > edge_cap: the host retries with room)
     }
     const u32 mb = __ballot_sync(0xffffffffu, miss);  // every lane has read its entry: the group's places may be reused
-    qh = q_wrap(qh + take);
+    qh = SM::wrap(qh + take);
     qn -= take;
     if (miss) {
-        const u32 j = q_wrap(qh + qn + (u32)__popc(mb & ((1u << lane) - 1u)));
+        const u32 j = SM::wrap(qh + qn + (u32)__popc(mb & ((1u << lane) - 1u)));
         S.qk[j] = k;
         S.qx[j] = x;
     }
@@ -383,33 +386,35 @@ __device__ __forceinline__ void drain_group(const ScanParams& P, WarpSmem& S, u3
     __syncwarp();
 }
 
-// Drains groups while more than `keep` mentions are queued.  The slot sectors of the NEXT group are requested before
-// the current group is worked on, so one L2 / HBM round trip is always in flight behind the table code.
+// Drains the ring's full groups -- all of it when `final`.  Latency hiding: the slot sectors of the group BEHIND the
+// current one are requested before the current group is worked on, and the last full group of a call is left IN FLIGHT
+// (`have`: its sectors are in v) while the warp parses its next round of lines; it is the first group of the next call.
 template <int MODE>
-__device__ __forceinline__ void drain(const ScanParams& P, WarpSmem& S, u32& qh, u32& qn, u32 keep, u64 pol, u32& claimed)
+__device__ __forceinline__ void drain(const ScanParams& P, WarpSmem<MODE>& S, u32& qh, u32& qn, bool final, u64 pol, u32& claimed, u64 (&v)[4], bool& have)
 {
-    if (qn <= keep) return;
-    u64 v[4] = {0, 0, 0, 0}, w[4] = {0, 0, 0, 0};
-    group_load(P, S, qh, qn, 0, pol, v);
+    if (!have) {
+        if (qn == 0 || (!final && qn < 32u)) return;
+        group_load(P, S, qh, qn, 0, pol, v);
+        have = true;
+    }
+    constexpr bool CARRY = (MODE & TM_FOUR) == 0;
     while (true) {
-        // a second group is certain to be drained if it is there now (what the current group puts back only adds to it)
-        const bool more = qn > keep + 32u;
+        const bool more = qn >= 64u;  // a full group behind the one in flight (what the current group puts back only adds to it)
+        if (CARRY && !more && !final) return;
+        u64 w[4] = {0, 0, 0, 0};
         if (more) group_load(P, S, qh, qn, 32, pol, w);
         drain_group<MODE>(P, S, qh, qn, v, claimed);
         if (more) {
 #pragma unroll
             for (int q = 0; q < 4; q++) v[q] = w[q];
         } else {
-            if (qn <= keep) break;
-            group_load(P, S, qh, qn, 0, pol, v);  // only what the last group put back is left above `keep`
+            if (qn == 0 || (!final && qn < 32u)) { have = false; return; }
+            group_load(P, S, qh, qn, 0, pol, v);  // what the last group put back
         }
     }
 }
 
 // ---------------------------------------------------------------- the kernel
-#ifndef TK_MIN_BLOCKS
-#define TK_MIN_BLOCKS 3
-#endif
 
 __device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
 
@@ -445,12 +450,13 @@ __device__ __forceinline__ u32 eq_bytes(u32 w, u32 c)
 __device__ __forceinline__ u32 flags4(u32 f) { return (f * 0x00204081u) >> 28; }
 
 template <int MODE>
-__global__ void __launch_bounds__(WT_WARPS * 32, TK_MIN_BLOCKS) k_tokenize(const __grid_constant__ ScanParams P)
+__global__ void __launch_bounds__(WT_WARPS * 32, tk_min_blocks<MODE>()) k_tokenize(const __grid_constant__ ScanParams P)
 {
     constexpr bool BIDIR = (MODE & TM_BIDIR) != 0;
     extern __shared__ __align__(128) uint8_t s_raw[];
     const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    WarpSmem& S = reinterpret_cast<WarpSmem*>(s_raw)[wid];
+    typedef WarpSmem<MODE> SM;
+    SM& S = reinterpret_cast<SM*>(s_raw)[wid];
     u32* nlm = S.nl;
     u32* spm = S.sp;
     u32* list = S.list;
@@ -477,7 +483,8 @@ __global__ void __launch_bounds__(WT_WARPS * 32, TK_MIN_BLOCKS) k_tokenize(const
     bool quick = false;  // this warp's previous tile held at most one record: look for a line start before building masks
     u32 qh = 0, qn = 0;  // the mention ring: head and fill (warp-uniform)
     u32 claimed = 0;
-    const u32 lag = 0;  // mentions the drain after a round leaves queued (TK_LAG: measured, no gain -- see the ring's comment)
+    u64 fly[4] = {0, 0, 0, 0};  // slot sectors of the ring's head group while it is in flight (drain)
+    bool have_fly = false;
     for (; tile < P.tile_end && !aborted; tile += n_warps) {
         const u64 t0 = (u64)tile * WT_TILE;
         const u64 wbase = t0 - WT_PRE;  // wraps for tile 0: only ever used as wbase + offset
@@ -648,20 +655,20 @@ __global__ void __launch_bounds__(WT_WARPS * 32, TK_MIN_BLOCKS) k_tokenize(const
                     }
                     // registration order u:of, v:ot, v:flip(ot), u:flip(of)  (builders.py:230-234); S: id[:+], id:-
                     const u32 c0m = (L.edge && cm_counts(P.count_mode, 0)) ? QM_CNT : 0u;
-                    enqueue_mention<MODE>(P, t, S, q_wrap(pos0), L.uo, L.ul, L.ocu, meta | c0m, tile, edge_ord);
+                    enqueue_mention<MODE>(P, t, S, SM::wrap(pos0), L.uo, L.ul, L.ocu, meta | c0m, tile, edge_ord);
                     if (L.nm >= 2) {
                         const u32 c1m = (L.edge && cm_counts(P.count_mode, 1)) ? QM_CNT : 0u;
-                        enqueue_mention<MODE>(P, t, S, q_wrap(pos0 + 1), L.vo, L.vl, L.ocv, meta | 1u | c1m, tile, edge_ord);
+                        enqueue_mention<MODE>(P, t, S, SM::wrap(pos0 + 1), L.vo, L.vl, L.ocv, meta | 1u | c1m, tile, edge_ord);
                     }
                     if ((MODE & TM_FOUR) && L.nm == 4) {
                         const u32 cm = cm_counts(P.count_mode, 2) ? QM_CNT : 0u;
-                        enqueue_mention<MODE>(P, t, S, q_wrap(pos0 + 2), L.vo, L.vl, L.ocv == '+' ? '-' : '+', meta | 2u | cm, tile, edge_ord);
-                        enqueue_mention<MODE>(P, t, S, q_wrap(pos0 + 3), L.uo, L.ul, L.ocu == '+' ? '-' : '+', meta | 3u | cm, tile, edge_ord);
+                        enqueue_mention<MODE>(P, t, S, SM::wrap(pos0 + 2), L.vo, L.vl, L.ocv == '+' ? '-' : '+', meta | 2u | cm, tile, edge_ord);
+                        enqueue_mention<MODE>(P, t, S, SM::wrap(pos0 + 3), L.uo, L.ul, L.ocu == '+' ? '-' : '+', meta | 3u | cm, tile, edge_ord);
                     }
                 }
                 qn += __shfl_sync(0xffffffffu, ninc, 31);
                 __syncwarp();
-                if (qn >= lag + 32u) drain<MODE>(P, S, qh, qn, lag + 31u, pol_table, claimed);
+                drain<MODE>(P, S, qh, qn, false, pol_table, claimed, fly, have_fly);
             }
         }
         // ---- the window is no longer needed: request the next one
@@ -685,7 +692,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, TK_MIN_BLOCKS) k_tokenize(const
     if (aborted && fetched) mbar_wait(&S.bar, parity);
     // ---- what is still queued (the pass is repeated anyway after an abort)
     if (!aborted) {
-        drain<MODE>(P, S, qh, qn, 0u, pol_table, claimed);
+        drain<MODE>(P, S, qh, qn, true, pol_table, claimed, fly, have_fly);
 #pragma unroll
         for (int d = 16; d; d >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, d);
         if (lane == 0 && claimed) atomicAdd(&P.cnt->n_keys, claimed);
