@@ -59,6 +59,8 @@ def main():
     ap.add_argument("--scale", type=float, default=0.01)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--verify-single", action="store_true")
+    ap.add_argument("--sha", action="store_true", help="sha256 of every rank's slab (indptr | indices | data) and of its node names: compared "
+                    "offline with tools/oracle_slab_sha.py (the CPU oracle over the concatenated shards)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -109,8 +111,22 @@ def main():
     torch.cuda.synchronize()
     ms = allmax(sum(a.elapsed_time(e) for a, e in ev) / max(1, args.steps)) if args.steps else float("nan")
 
-    # ---- properties of the resident result
+    # ---- per-kernel times of this rank (event pair around every launch; not part of the timed builds above)
     h = b.local.h
+    kern = {}
+    h.set_profile(True)
+    for _ in range(2):
+        if world > 1:
+            dist.barrier()
+        res = b.build(text_dev, matrix_format="csr", **mode)
+        torch.cuda.synchronize()
+        for k, (m, c) in h.kernel_times().items():
+            kern[k] = round(kern.get(k, 0.0) + m / 2, 4)
+    h.set_profile(False)
+    res = b.build(text_dev, matrix_format="csr", **mode)
+    torch.cuda.synchronize()
+
+    # ---- properties of the resident result
     ip, ix, dt = device_result(h, torch, dev)
     nnz = int(res.nnz_local)
     checks = {}
@@ -209,6 +225,24 @@ def main():
                         and bool(torch.equal(got[2].view(torch.int64), dt.view(torch.int64))) and exp_names == my_names)
         verified = allsum(int(same)) == world
 
+    # ---- fingerprints of this rank's slab and names, for the offline comparison with the CPU oracle
+    slabs = None
+    if args.sha:
+        import hashlib
+
+        hip, hix, hdt = b.fetch_slab()
+        hsh = hashlib.sha256()
+        for a in (hip, hix, hdt):
+            hsh.update(np.ascontiguousarray(a).tobytes())
+        _, my_names2 = b.local.node_list(raw_bytes_id=True)
+        mine = dict(rank=rank, row0=int(res.row0), n_rows=int(res.n_rows), nnz=int(nnz), id0=int(res.info["id0"]), n_first=int(res.info["n_first"]),
+                    sha_slab=hsh.hexdigest(), sha_names=hashlib.sha256(b"\n".join(my_names2)).hexdigest(), text_bytes=nbytes)
+        del hip, hix, hdt, my_names2
+        slabs = [mine]
+        if world > 1:
+            slabs = [None] * world
+            dist.all_gather_object(slabs, mine)
+
     total_bytes = allsum(nbytes)
     line = {
         "tool": "dist_check", "config": args.config, "scale_per_gpu": args.scale, "n_gpus": world,
@@ -218,6 +252,9 @@ def main():
         "speculative_steps": spec, "first_build_s": first_s, "generate_s": gen_s, "checks": checks, "verified_against_single_gpu": verified,
         "mode": mode or "directed (default): CSR of max(S, S^T)",
     }
+    line["kernels_rank0_ms"] = kern
+    if slabs is not None:
+        line["slabs"] = slabs
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
