@@ -1768,6 +1768,69 @@ int g2n_dist_init(g2n_handle* h, int rank, int world)
     return G2N_OK;
 }
 
+// Ranks that share a process but sit on different GPUs reach each other's arenas through plain device pointers:
+// peer access from this handle's device to `peer_device` has to be on (a no-op for the same device).
+int g2n_dist_enable_peer(g2n_handle* h, int peer_device)
+{
+    if (!h) return G2N_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (peer_device == h->device) return G2N_OK;
+    int can = 0;
+    CK(cudaDeviceCanAccessPeer(&can, h->device, peer_device));
+    if (!can) { h->err = "no peer access between the two devices"; return G2N_ERR_UNSUPPORTED; }
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); return G2N_OK; }
+    CK(e);
+    return G2N_OK;
+}
+
+// This rank's byte range of a file -> the handle's text buffer on the device (pread into two pinned staging buffers,
+// the copy of one piece overlaps the read of the next).  *dev_text is 16-byte aligned and stays valid until the handle
+// loads another text; pass it to g2n_dist_probe / g2n_dist_stage with text_on_device = 1.
+int g2n_load_file_range(g2n_handle* h, const char* path, uint64_t offset, uint64_t nbytes, void** dev_text)
+{
+    if (!h || !path || !dev_text) return G2N_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) { h->err = std::string("cannot open ") + path; return G2N_ERR_INVALID; }
+    int rc = G2N_OK;
+    do {
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = G2N_ERR_CUDA; break; }
+        if (h->text.ensure(nbytes + 64) != cudaSuccess) { h->err = "out of device memory for the text"; rc = G2N_ERR_CUDA; break; }
+        const u64 piece = G2N_H2D_PIECE;
+        while (h->stage.size() < 2) {
+            void* b = nullptr;
+            if (cudaHostAlloc(&b, piece, cudaHostAllocDefault) != cudaSuccess) { rc = G2N_ERR_CUDA; break; }
+            h->stage.push_back(b);
+            cudaEvent_t e;
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { rc = G2N_ERR_CUDA; break; }
+            h->stage_ev.push_back(e);
+        }
+        if (rc) break;
+        u32 k = 0;
+        for (u64 a = 0; a < nbytes && !rc; a += piece, k++) {
+            const u32 sb = k & 1;
+            cudaEventSynchronize(h->stage_ev[sb]);  // the previous copy out of this staging buffer is done
+            const u64 len = a + piece < nbytes ? piece : nbytes - a;
+            u64 got = 0;
+            while (got < len) {
+                const ssize_t n = pread(fd, (uint8_t*)h->stage[sb] + got, len - got, (off_t)(offset + a + got));
+                if (n <= 0) { h->err = "reading the input file failed"; rc = G2N_ERR_INVALID; break; }
+                got += (u64)n;
+            }
+            if (rc) break;
+            if (cudaMemcpyAsync(h->text.as<uint8_t>() + a, h->stage[sb], len, cudaMemcpyHostToDevice, h->copy_stream) != cudaSuccess ||
+                cudaEventRecord(h->stage_ev[sb], h->copy_stream) != cudaSuccess) { h->err = "queueing a copy of the input file failed"; rc = G2N_ERR_CUDA; }
+        }
+        if (!rc && cudaStreamSynchronize(h->copy_stream) != cudaSuccess) rc = G2N_ERR_CUDA;
+    } while (0);
+    close(fd);
+    if (rc) return rc;
+    h->built = false;
+    *dev_text = h->text.p;
+    return G2N_OK;
+}
+
 int g2n_dist_plan(g2n_handle* h, uint64_t key_cap, uint64_t pair_cap, uint64_t rows_cap, uint64_t recv_cap, int dry_run, int* will_realloc)
 {
     if (!h || !h->dx_inited) return G2N_ERR_INVALID;

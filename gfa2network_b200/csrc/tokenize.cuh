@@ -270,6 +270,41 @@ __device__ __forceinline__ bool parse_line_fast(const ScanParams& P, const Tile&
     return true;
 }
 
+// Sparse tiles (a handful of records per 2 KiB: segments with their sequences): no separator mask is built at all,
+// the few fields that matter are found byte by byte.  Only S / P / O lines get here (a tile with an edge record gets
+// the separator mask after all); same results as parse_line_fast.
+template <int MODE>
+__device__ __forceinline__ bool parse_line_sparse(const Tile& t, u32 s, LineOut& lo)
+{
+    constexpr bool BIDIR = (MODE & TM_BIDIR) != 0;
+    const uint8_t c0 = t.win[s];
+    lo.nm = 0; lo.edge = false; lo.w = 1.0;
+    if (t.win[s + 1] != '\t') return false;
+    const u32 p1 = s + 2;
+    const u32 maxlen = BIDIR ? 13u : 15u;
+    if (c0 == 'S') {
+        u32 len = 0;
+        while (len <= maxlen) {
+            const uint8_t c = t.win[p1 + len];
+            if (c == '\t' || c == '\n') break;
+            len++;
+        }
+        if (len > maxlen) return false;  // long key: generic parser
+        lo.uo = lo.vo = p1; lo.ul = lo.vl = len; lo.ocu = '+'; lo.ocv = '-';
+        lo.nm = BIDIR ? 2u : 1u;
+        return true;
+    }
+    if (c0 == 'P' || c0 == 'O') {  // >= 3 fields <=> the name field ends with a TAB; a long name: generic parser
+        for (u32 q = p1; q < p1 + 64u && q < WT_WIN; q++) {
+            const uint8_t c = t.win[q];
+            if (c == '\t') return true;
+            if (c == '\n') return false;
+        }
+        return false;
+    }
+    return false;
+}
+
 // ---------------------------------------------------------------- the mention queue
 // A ring per warp that lives ACROSS tiles.  One entry per node mention: the packed key and
 //   x.x  the slot to look at next (home slot first: probe_home)        x.z  tile (high bits of the mention's order)
@@ -289,7 +324,7 @@ __device__ __forceinline__ bool parse_line_fast(const ScanParams& P, const Tile&
 // ring capacity: one group stays in flight across a round of lines (< 64 mentions queued) + 32 lines x 2 mentions; or < 32
 // mentions left over + 32 lines x 4 mentions for the records of a bidirected build (which carries no group across rounds:
 // a 192-entry ring at two CTAs per SM was measured slower, C3 shape at 25 %: 1.85 ms against 1.59 ms)
-template <int MODE> struct QCap { static constexpr u32 value = 160u; };
+template <int MODE> struct QCap { static constexpr u32 value = (MODE & TM_FOUR) ? 160u : 128u; };
 
 // per-warp shared memory: the text window, the two bitmasks, the compacted line list, the mention queue, one mbarrier
 template <u32 QCAP>
@@ -302,7 +337,7 @@ struct alignas(128) WarpSmemT {
     u32 nl[WT_WORDS];
     u32 sp[WT_WORDS + 2];  // + 2 words of slack for sep_slice
     u64 bar;
-    static __device__ __forceinline__ u32 wrap(u32 pos) { return pos >= QCAP ? pos - QCAP : pos; }
+    static __device__ __forceinline__ u32 wrap(u32 pos) { return (QCAP & (QCAP - 1)) == 0 ? (pos & (QCAP - 1)) : (pos >= QCAP ? pos - QCAP : pos); }
 };
 template <int MODE> using WarpSmem = WarpSmemT<QCap<MODE>::value>;
 template <int MODE> constexpr size_t tk_smem_bytes() { return WT_WARPS * sizeof(WarpSmem<MODE>); }
@@ -480,7 +515,8 @@ __global__ void __launch_bounds__(WT_WARPS * 32, tk_min_blocks<MODE>()) k_tokeni
         fetched = true;
     }
     u32 aborted = 0;
-    bool quick = false;  // this warp's previous tile held at most one record: look for a line start before building masks
+    bool quick = false;   // this warp's previous tile held at most one record: look for a line start before building masks
+    bool sparse = false;  // ... held a handful of records and no edge record: build the newline mask only
     u32 qh = 0, qn = 0;  // the mention ring: head and fill (warp-uniform)
     u32 claimed = 0;
     u64 fly[4] = {0, 0, 0, 0};  // slot sectors of the ring's head group while it is in flight (drain)
@@ -552,20 +588,36 @@ __global__ void __launch_bounds__(WT_WARPS * 32, tk_min_blocks<MODE>()) k_tokeni
                 continue;
             }
         }
-        // ---- classify '\n' and '\t' 16 bytes at a time into the two bitmasks
+        // ---- classify '\n' and '\t' 16 bytes at a time into the two bitmasks; a tile that follows a sparse one gets the
+        // newline mask only (less than half the work) and the separator mask later, if it turns out to need one
+        bool dense = !sparse;
+        if (dense) {
 #pragma unroll
-        for (int k = 0; k < WT_WIN / 16 / 32; k++) {
-            const u32 piece = lane + 32 * k;
-            const uint4 v = reinterpret_cast<const uint4*>(win)[piece];
-            const u32 ww[4] = {v.x, v.y, v.z, v.w};
-            u32 mn = 0, mt = 0;
+            for (int k = 0; k < WT_WIN / 16 / 32; k++) {
+                const u32 piece = lane + 32 * k;
+                const uint4 v = reinterpret_cast<const uint4*>(win)[piece];
+                const u32 ww[4] = {v.x, v.y, v.z, v.w};
+                u32 mn = 0, mt = 0;
 #pragma unroll
-            for (int b = 0; b < 4; b++) {
-                mn |= flags4(eq_bytes(ww[b], 0x0A0A0A0Au)) << (4 * b);
-                mt |= flags4(eq_bytes(ww[b], 0x09090909u)) << (4 * b);
+                for (int b = 0; b < 4; b++) {
+                    mn |= flags4(eq_bytes(ww[b], 0x0A0A0A0Au)) << (4 * b);
+                    mt |= flags4(eq_bytes(ww[b], 0x09090909u)) << (4 * b);
+                }
+                reinterpret_cast<unsigned short*>(nlm)[piece] = (unsigned short)mn;
+                reinterpret_cast<unsigned short*>(spm)[piece] = (unsigned short)(mn | mt);
             }
-            reinterpret_cast<unsigned short*>(nlm)[piece] = (unsigned short)mn;
-            reinterpret_cast<unsigned short*>(spm)[piece] = (unsigned short)(mn | mt);
+        } else {
+            // line starts lie in window bytes [WT_PRE - 1, WT_PRE + WT_TILE): mask words 0 .. WT_TILE / 32
+#pragma unroll
+            for (int k = 0; k < (WT_PRE + WT_TILE) / 16 / 32 + 1; k++) {
+                const u32 piece = lane + 32 * k;
+                if (piece < (WT_PRE + WT_TILE) / 16) {
+                    const uint4 v = reinterpret_cast<const uint4*>(win)[piece];
+                    const u32 mn = flags4(eq_bytes(v.x, 0x0A0A0A0Au)) | (flags4(eq_bytes(v.y, 0x0A0A0A0Au)) << 4) |
+                                   (flags4(eq_bytes(v.z, 0x0A0A0A0Au)) << 8) | (flags4(eq_bytes(v.w, 0x0A0A0A0Au)) << 12);
+                    reinterpret_cast<unsigned short*>(nlm)[piece] = (unsigned short)mn;
+                }
+            }
         }
         __syncwarp();
         Tile t{win, nlm, spm, wbase};
@@ -598,6 +650,25 @@ __global__ void __launch_bounds__(WT_WARPS * 32, tk_min_blocks<MODE>()) k_tokeni
         const u32 tot = __shfl_sync(0xffffffffu, inc, 31);
         const u32 n_rec_tile = tot >> 16, n_edge_tile = tot & 0xFFFFu;
         const u32 my_rec0 = (inc - packed) >> 16, my_edge0 = (inc - packed) & 0xFFFFu;
+        if (!dense && (n_edge_tile != 0 || n_rec_tile > 24u)) {
+            // not that sparse after all: the separator mask (and the newline mask of the look-ahead) now
+#pragma unroll
+            for (int k = 0; k < WT_WIN / 16 / 32; k++) {
+                const u32 piece = lane + 32 * k;
+                const uint4 v = reinterpret_cast<const uint4*>(win)[piece];
+                const u32 ww[4] = {v.x, v.y, v.z, v.w};
+                u32 mn = 0, mt = 0;
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    mn |= flags4(eq_bytes(ww[b], 0x0A0A0A0Au)) << (4 * b);
+                    mt |= flags4(eq_bytes(ww[b], 0x09090909u)) << (4 * b);
+                }
+                reinterpret_cast<unsigned short*>(nlm)[piece] = (unsigned short)mn;
+                reinterpret_cast<unsigned short*>(spm)[piece] = (unsigned short)(mn | mt);
+            }
+            dense = true;
+            __syncwarp();
+        }
         // one atomicAdd claims this tile's range of edge_slots; the abort flag rides along.  Both results are
         // consumed only after the first round of lines has been parsed, so their latency is hidden.
         u32 alloc_l0 = 0, flags_l0 = 0;
@@ -632,7 +703,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, tk_min_blocks<MODE>()) k_tokeni
                     const u32 ent = list[i];
                     off = ent & 0xFFFFu;
                     eidx = ent >> 16;
-                    ok = parse_line_fast<MODE>(P, t, off, L);
+                    ok = dense ? parse_line_fast<MODE>(P, t, off, L) : parse_line_sparse<MODE>(t, off, L);
                 }
                 if (!alloc_ready) {
                     alloc = __shfl_sync(0xffffffffu, alloc_l0, 0);
@@ -681,6 +752,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, tk_min_blocks<MODE>()) k_tokeni
         }
         aborted = __shfl_sync(0xffffffffu, flags_l0, 0) & (CF_TABLE_FULL | CF_DEFER_FULL);
         quick = n_rec_tile <= 1;
+        sparse = n_rec_tile <= 12u && n_edge_tile == 0;
         // new keys of this tile: one fire-and-forget atomic per warp (the host checks the load factor)
 #pragma unroll
         for (int d = 16; d; d >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, d);

@@ -288,6 +288,13 @@ typedef struct g2n_dist_result {
 } g2n_dist_result;
 
 int g2n_dist_init(g2n_handle *h, int rank, int world);
+/* ranks of one process on different GPUs: peer access from this handle's device to peer_device (their arenas are then
+ * exchanged as plain pointers, g2n_dist_local_mem / g2n_dist_set_peers) */
+int g2n_dist_enable_peer(g2n_handle *h, int peer_device);
+/* bytes [offset, offset + nbytes) of a file -> this handle's device text buffer (*dev_text: 16-byte aligned, valid until
+ * the handle loads another text).  The multi-GPU counterpart of g2n_build_file: every rank loads its own newline-aligned
+ * range (parser.py:111 reads the file; SURVEY 8e step 1 splits it) */
+int g2n_load_file_range(g2n_handle *h, const char *path, uint64_t offset, uint64_t nbytes, void **dev_text);
 int g2n_dist_probe(g2n_handle *h, const uint8_t *text, uint64_t nbytes, const g2n_params *p, g2n_dist_info *out);
 int g2n_dist_plan(g2n_handle *h, uint64_t key_cap, uint64_t pair_cap, uint64_t rows_cap, uint64_t recv_cap,
                   int dry_run, int *will_realloc);

@@ -66,7 +66,7 @@ def main():
         out.append(dict(rank=s["rank"], row0=row0, n_rows=n_rows, nnz_oracle=hi - lo, nnz_gpu=s["nnz"], slab_equal=h.hexdigest() == s["sha_slab"],
                         names_equal=hn == s["sha_names"], sha_slab_oracle=h.hexdigest(), sha_names_oracle=hn))
     res = dict(tool="oracle_slab_sha", config=cfg_name, scale_per_gpu=scale, n_gpus=world, nodes=int(A.shape[0]), nnz=int(A.nnz), text_bytes=d["text_bytes"],
-               bit_exact=bool(ok), generate_s=round(gen_s, 1), oracle_parse_s=round(parse_s, 1), oracle_convert_s=round(conv_s, 1), slabs=out)
+               bit_exact=bool(ok), peak_rss_gb=round(__import__("resource").getrusage(__import__("resource").RUSAGE_SELF).ru_maxrss / 1e6, 1), generate_s=round(gen_s, 1), oracle_parse_s=round(parse_s, 1), oracle_convert_s=round(conv_s, 1), slabs=out)
     print(json.dumps(res))
     if args.out:
         Path(args.out).write_text(json.dumps(res) + "\n")
