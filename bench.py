@@ -472,6 +472,43 @@ def run_ours(args):
     else:
         d2h = A.indptr.nbytes + A.indices.nbytes + A.data.nbytes
 
+    # ---- N > 1: the north-star workload as well -- every GPU holds 1/8 of C5 (12.5 M segments with sequences / 50 M
+    # links, ~5 GB of text per GPU; at N = 8 that is BASELINE's config 5 in full: 100 M segments / 400 M links / ~40 GB).
+    # Device-resident build of ONE graph over the N shards, CUDA events, max over ranks; reported beside the line's
+    # metric (which stays the C2-shaped shard per GPU, so that the N = 1 .. 8 values form one weak-scaling curve).
+    ns = None
+    if world > 1 and args.config == "C2" and args.scale == 1.0 and not os.environ.get("G2N_BENCH_NO_C5"):
+        try:
+            text_dev = pinned = flush = None  # (referenced by closures above: rebinding, not del)
+            torch.cuda.empty_cache()
+            c5cfg, c5np, c5seg, c5link = make_text("C5", 0.125, rank=rank, world=world)
+            c5bytes = int(c5np.size)
+            c5dev = torch.from_numpy(c5np).to(dev)
+            del c5np
+            c5mode = dict(c5cfg["mode"])
+            for _ in range(3):
+                builder.build(c5dev, matrix_format="csr", **c5mode)
+            torch.cuda.synchronize()
+            nstep = 5
+            cev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nstep)]
+            for a, b in cev:
+                dist.barrier()
+                a.record(stream)
+                c5res = builder.build(c5dev, matrix_format="csr", **c5mode)
+                b.record(stream)
+            torch.cuda.synchronize()
+            tc = torch.tensor([sum(a.elapsed_time(b) for a, b in cev) / nstep, float(c5bytes), float(c5res.nnz_local)], device=dev, dtype=torch.float64)
+            tmax = tc.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tc, op=dist.ReduceOp.SUM)
+            c5ms, c5total, c5nnz = float(tmax[0].item()), float(tc[1].item()), int(tc[2].item())
+            ns = {"workload": f"C5 shape, 1/8 of it per GPU: {world * c5seg} segments / {world * c5link} links, directed (default), CSR of max(S, S^T)",
+                  "text_bytes": int(c5total), "nodes": int(c5res.n_global), "nnz": c5nnz, "ms_per_build": c5ms, "value": c5total / (c5ms * 1e6), "unit": "GB/s",
+                  "edges_per_s": world * c5link / (c5ms / 1e3), "hbm_frac_of_aggregate_peak": c5total / (c5ms * 1e6) / (world * peaks()[0]), "steps": nstep,
+                  "parity": "profiles/r2_dist_c5full_8gpu_oracle_sha.json: every slab and name range of this build at N = 8 is sha256-identical to the CPU oracle"}
+            del c5dev
+        except Exception as exc:  # noqa: BLE001 - the extra measurement must never take the line down
+            ns = {"error": repr(exc)[:300]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -560,6 +597,8 @@ def run_ours(args):
         "gpu_launches": launches,
         "clocks": clocks,
     }
+    if ns is not None:
+        line["north_star_shards"] = ns
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -188,13 +188,17 @@ def parse_gfa(
     split_on_alignment: bool = False,
     matrix_format: str | None = None,
     device: int | None = None,
+    devices: list[int] | None = None,
 ):
     """Parse *path* on the GPU and return the adjacency matrix (and node list).
 
     Drop-in for ``gfa2network.parse_gfa(..., build_graph=False, build_matrix=True)``
-    (``builders.py:30-50``).  Extensions, both optional: ``matrix_format`` ("csr"/"csc") fuses
-    ``convert_format`` into the device build; ``device`` selects the CUDA device.  ``path`` may
-    also be a bytes-like object, a uint8 NumPy array or a CUDA uint8 torch tensor.
+    (``builders.py:30-50``).  Extensions, all optional: ``matrix_format`` ("csr"/"csc") fuses
+    ``convert_format`` into the device build; ``device`` selects the CUDA device; ``devices=[...]``
+    (two to eight GPUs of this host) splits the FILE at newline boundaries, one byte range per GPU, and
+    builds one graph over all of them (``dist.MultiGpuBuilder``: each GPU ends with the CSR/CSC slab of its
+    row block; the slabs and name ranges are concatenated for the caller).  ``path`` may also be a
+    bytes-like object, a uint8 NumPy array or a CUDA uint8 torch tensor (single device only).
     """
     if backend == "igraph":
         raise NotImplementedError("backend='igraph' is outside the B200 GFA->matrix path (builders.py:95-109)")
@@ -218,6 +222,13 @@ def parse_gfa(
             raise ValueError("matrix-format must be csr|csc|coo|dok")  # utils.py:46
         want = {"csr": _capi.FMT_CSR, "csc": _capi.FMT_CSC}.get(mf, _capi.FMT_NATIVE)
 
+    if devices is not None and len(devices) > 1:
+        return _parse_gfa_multi(path, list(devices), build_matrix=build_matrix, directed=directed, weight_tag=weight_tag,
+                                strip_orientation=strip_orientation, verbose=verbose, bidirected=bidirected,
+                                keep_directed_bidir=keep_directed_bidir, dtype=dt.name, asymmetric=asymmetric,
+                                raw_bytes_id=raw_bytes_id, return_node_list=return_node_list, matrix_format=matrix_format)
+    if devices is not None and len(devices) == 1 and device is None:
+        device = devices[0]
     host, dev_ptr, nbytes, keep = _read_source(path)
     handle = _capi.default_handle(_default_device() if device is None else device)
     wt = weight_tag.encode() if weight_tag else None  # builders.py:206 "if weight_tag and ..."
@@ -255,4 +266,61 @@ def parse_gfa(
     A._g2n_session = _Session(handle)
     if return_node_list:
         return A, _node_list(handle, raw_bytes_id)
+    return A
+
+
+_multi: dict[tuple, object] = {}
+
+
+def _parse_gfa_multi(path, devices, *, build_matrix, directed, weight_tag, strip_orientation, verbose, bidirected,
+                     keep_directed_bidir, dtype, asymmetric, raw_bytes_id, return_node_list, matrix_format):
+    """parse_gfa over several GPUs of this host (one process): the file is split at newline boundaries, one byte range
+    per GPU (north_star; reference surface cli.py:206-225).  Returns what parse_gfa returns on one GPU for the modes whose
+    result is compressed: the CSR of max(S, S^T) in the default directed mode (builders.py:282-283), or the CSR / CSC asked
+    for with ``matrix_format``.  A raw COO in emission order (non-symmetric modes without ``matrix_format``) is a single-GPU result."""
+    from .dist import MultiGpuBuilder
+
+    if not isinstance(path, (str, Path)) or str(path) in ("", "-") or str(path).endswith(".gz"):
+        raise NotImplementedError("devices=[...] reads a plain file by byte ranges: give a path to an uncompressed GFA file")
+    p = str(path)
+    st = os.stat(p)
+    import stat as _stat
+
+    if not _stat.S_ISREG(st.st_mode):
+        raise NotImplementedError("devices=[...] needs a regular file (byte ranges are read by offset)")
+    graph_directed = keep_directed_bidir or (not bidirected and directed)  # builders.py:143
+    symmax = graph_directed and not asymmetric
+    fmt = (matrix_format or "").lower()
+    if fmt and fmt not in {"csr", "csc", "coo", "dok"}:
+        raise ValueError("matrix-format must be csr|csc|coo|dok")
+    if fmt not in ("csr", "csc"):
+        if not symmax:
+            raise NotImplementedError("a multi-GPU build ends in CSR / CSC slabs: pass matrix_format='csr' or 'csc' "
+                                      "(the raw COO in emission order is the single-GPU result)")
+        fmt = "csr"
+    key = tuple(devices)
+    mg = _multi.get(key)
+    if mg is None:
+        mg = _multi[key] = MultiGpuBuilder(devices)
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        try:
+            mg.build_file(p, directed=directed, bidirected=bidirected, keep_directed_bidir=keep_directed_bidir, asymmetric=asymmetric,
+                          strip_orientation=strip_orientation, dtype=dtype, matrix_format=fmt, weight_tag=weight_tag)
+            exc = None
+        except Exception as e:  # noqa: BLE001 - re-raised below, after the warning that precedes it in the file
+            exc = e
+    for w in caught:
+        warnings.warn(str(w.message), w.category, stacklevel=3)
+    if exc is not None:
+        raise exc
+    if verbose:
+        for k in range(500_000, mg.diag_records() + 1, 500_000):  # builders.py:257-258
+            print(f"\r[{k:,} lines]", end="", file=sys.stderr)
+        print("\r[parse_gfa] done")  # builders.py:261
+    if not build_matrix:
+        return None
+    A = mg.matrix(fmt)
+    if return_node_list:
+        return A, mg.node_list(raw_bytes_id)
     return A

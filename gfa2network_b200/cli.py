@@ -41,6 +41,8 @@ def _parser() -> argparse.ArgumentParser:
     c.add_argument("--bidirected", action="store_true", help="Use bidirected representation")
     c.add_argument("--keep-directed-bidir", action="store_true", help="Keep original directed bidirected behaviour")
     c.add_argument("--verbose", action="store_true")
+    c.add_argument("--devices", metavar="I,J,...", help="Build on these GPUs of this host: the file is split at newline boundaries, one byte "
+                   "range per GPU (B200 extension; default: one GPU)")
     c.add_argument("-o", "--output", metavar="PATH", help="Write graph pickle to PATH")
     e = sub.add_parser("export", help="Stream edges in simple formats")
     e.add_argument("gfa")
@@ -107,6 +109,31 @@ def main(argv: list[str] | None = None) -> None:
         ap.error("convert requires --graph or --matrix")  # cli.py:194-195
     print(f"Using backend: {args.backend}")  # cli.py:198
     want_nodes = bool(args.matrix) and not args.no_node_map  # cli.py:222
+    devs = [int(x) for x in args.devices.split(",")] if getattr(args, "devices", None) else None
+    if devs and len(devs) > 1:
+        # one graph over several GPUs: the result is already in its final compressed format (utils.py:47-48: `coo` keeps
+        # whatever parse_gfa returned -- the CSR of max(S, S^T) in the default directed mode)
+        from .utils import save_node_map
+
+        mf = args.matrix_format.lower()
+        if mf not in {"csr", "csc", "coo", "dok"}:
+            raise ValueError("matrix-format must be csr|csc|coo|dok")
+        res = parse_gfa(
+            args.gfa, build_graph=args.graph, build_matrix=bool(args.matrix), directed=args.directed, weight_tag=args.weight_tag,
+            strip_orientation=args.strip_orientation, verbose=args.verbose, bidirected=args.bidirected,
+            keep_directed_bidir=args.keep_directed_bidir, backend=args.backend, dtype=args.dtype, asymmetric=args.asymmetric,
+            raw_bytes_id=args.raw_bytes_id, return_node_list=want_nodes, split_on_alignment=args.split_on_alignment,
+            matrix_format=mf if mf in ("csr", "csc") else None, devices=devs)
+        A, nodes = res if want_nodes else (res, None)
+        if mf == "dok":
+            A = A.asformat("dok")
+        try:
+            save_matrix(A, Path(args.matrix), verbose=args.verbose, max_dense_gb=args.max_dense_gb)
+        except MemoryError as exc:  # cli.py:247-248
+            raise SystemExit(str(exc)) from exc
+        if want_nodes:
+            save_node_map(nodes, str(args.matrix) + ".nodes.tsv")  # cli.py:249-250
+        return
     result = parse_gfa(
         args.gfa, build_graph=args.graph, build_matrix=bool(args.matrix), directed=args.directed,
         weight_tag=args.weight_tag, store_seq=args.store_seq, store_tags=args.store_tags,

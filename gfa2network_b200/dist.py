@@ -98,16 +98,23 @@ def assemble_slabs(slabs, n_global: int, fmt: str = "csr"):
 
 # ------------------------------------------------------------------ one rank's device work
 class LocalRank:
-    def __init__(self, device_index: int, rank: int, world: int, stream_ptr: int | None = None):
-        import torch
-
+    def __init__(self, device_index: int, rank: int, world: int, stream_ptr: int | None = None, own_stream: bool = False):
+        """own_stream: the handle's own non-blocking stream (no torch needed: the single-process multi-GPU driver);
+        else `stream_ptr`, or torch's current stream of the device."""
         if not 1 <= world <= MAX_WORLD:
             raise ValueError(f"world size {world} not in 1..{MAX_WORLD}")
-        self.torch = torch
         self.rank, self.world = rank, world
-        self.dev = torch.device("cuda", device_index)
+        self.device_index = device_index
         self.h = _capi.Handle(device_index)
-        self.h.set_stream(stream_ptr if stream_ptr is not None else torch.cuda.current_stream(self.dev).cuda_stream)
+        if own_stream:
+            self.h.set_stream(None)
+            self.dev = device_index
+        else:
+            import torch
+
+            self.torch = torch
+            self.dev = torch.device("cuda", device_index)
+            self.h.set_stream(stream_ptr if stream_ptr is not None else torch.cuda.current_stream(self.dev).cuda_stream)
         self.h.check(self.h.lib.g2n_dist_init(self.h.h, rank, world))
         self.params = None
         self.text = None
@@ -118,9 +125,25 @@ class LocalRank:
         self._wt = weight_tag.encode() if weight_tag else None  # kept alive: Params holds a pointer to it
         self.params = _capi.Params(int(directed), int(bidirected), int(keep_directed_bidir), int(asymmetric), int(strip_orientation),
                                    _capi.DTYPES[np.dtype(dtype).name], want, 1, self._wt, len(self._wt) if self._wt else 0, 0)
-        self.text = text_dev
-        self.nbytes = int(text_dev.numel())
-        self.text_ptr = C.c_void_p(text_dev.data_ptr() if self.nbytes else 0)
+        if isinstance(text_dev, tuple):  # (device pointer, nbytes): a text the handle loaded itself (load_file_range)
+            self.text = None
+            ptr, self.nbytes = int(text_dev[0]), int(text_dev[1])
+            self.text_ptr = C.c_void_p(ptr if self.nbytes else 0)
+        else:
+            self.text = text_dev
+            self.nbytes = int(text_dev.numel())
+            self.text_ptr = C.c_void_p(text_dev.data_ptr() if self.nbytes else 0)
+
+    def load_file_range(self, path: str, offset: int, nbytes: int) -> tuple[int, int]:
+        """This rank's byte range of a file -> the handle's device text buffer; returns (device pointer, nbytes)."""
+        import os
+
+        out = C.c_void_p()
+        self.h.check(self.h.lib.g2n_load_file_range(self.h.h, os.fsencode(path), offset, nbytes, C.byref(out)))
+        return int(out.value or 0), nbytes
+
+    def enable_peer(self, device_index: int):
+        self.h.check(self.h.lib.g2n_dist_enable_peer(self.h.h, device_index))
 
     def probe(self) -> dict:
         """Host-planned tokenizer pass over this shard.  Never raises for what the input holds: the
@@ -297,3 +320,120 @@ class DistBuilder:
             assert id0 == len(out), (id0, len(out))
             out.extend(names)
         return out
+
+
+# ------------------------------------------------------------------ one process, several GPUs, one file
+def file_cuts(path: str, world: int) -> list[tuple[int, int]]:
+    """Newline-aligned byte ranges of a file, one per rank: `shard_range` with the newline search
+    done by reading 1 MiB windows of the file around every cut."""
+    import os
+
+    nbytes = os.path.getsize(path)
+    with open(path, "rb") as fh:
+        def find_newline(pos: int) -> int:
+            while pos < nbytes:
+                fh.seek(pos)
+                buf = fh.read(1 << 20)
+                j = buf.find(b"\n")
+                if j >= 0:
+                    return pos + j
+                pos += len(buf)
+            return -1
+        return [shard_range(nbytes, r, world, find_newline) for r in range(world)]
+
+
+class MultiGpuBuilder:
+    """`parse_gfa(path, devices=[...])` / `convert --devices`: ONE process drives one handle per GPU.  Every rank loads
+    its own newline-aligned byte range of the file straight into its GPU (g2n_load_file_range, ranks in parallel
+    threads), the stages of the multi-GPU build are queued on every device's own stream (the kernels exchange
+    through peer pointers: no IPC, no torch.distributed, no collective library), and the slabs / name ranges are
+    assembled on request.  Same protocol, kernels and results as `DistBuilder`."""
+
+    def __init__(self, devices: list[int]):
+        if not 1 <= len(devices) <= MAX_WORLD:
+            raise ValueError(f"1..{MAX_WORLD} devices, got {len(devices)}")
+        if len(set(devices)) != len(devices):
+            raise ValueError("devices must be distinct")
+        self.devices = list(devices)
+        self.world = len(devices)
+        self.ranks = [LocalRank(d, r, self.world, own_stream=True) for r, d in enumerate(devices)]
+        for a in self.ranks:
+            for b in self.ranks:
+                if a is not b:
+                    a.enable_peer(b.device_index)
+        self.caps = None
+        self.mode = None
+        self.result = None
+
+    def _connect(self):
+        mems = [r.local_mem() for r in self.ranks]
+        for r in self.ranks:
+            r.set_peers([m[0] for m in mems], [m[1] for m in mems])
+
+    def _load(self, path: str):
+        from concurrent.futures import ThreadPoolExecutor
+
+        cuts = file_cuts(path, self.world)
+        with ThreadPoolExecutor(self.world) as pool:  # ctypes drops the GIL: the ranks read and copy in parallel
+            return list(pool.map(lambda rc: rc[0].load_file_range(path, rc[1][0], rc[1][1] - rc[1][0]), zip(self.ranks, cuts)))
+
+    def build_file(self, path: str, **mode) -> DistResult:
+        texts = self._load(str(path))
+        return self.build(texts, **mode)
+
+    def build(self, texts, **mode) -> DistResult:
+        """texts: per rank a CUDA uint8 tensor on that rank's device or a (device pointer, nbytes) pair."""
+        W = self.world
+        for r, t in zip(self.ranks, texts):
+            r.set_input(t, **mode)
+        mode_key = tuple(sorted(mode.items()))
+        if self.caps is not None and self.mode != mode_key:
+            self.caps = None
+        self.mode = mode_key
+        if self.caps is not None:
+            for k in range(N_STAGES):
+                for r in self.ranks:
+                    r.stage(k, True)
+            outs = [r.finish() for r in self.ranks]
+            if all(rc == _capi.G2N_OK for rc, _ in outs):
+                for r, (_, res) in zip(self.ranks, outs):
+                    r.remember(res, *self.caps)
+                self.result = [_result(res, W, True) for _, res in outs]
+                return self.result[0]
+            self.caps = None
+        from concurrent.futures import ThreadPoolExecutor
+
+        for attempt in range(6):
+            with ThreadPoolExecutor(W) as pool:  # the host-planned tokenizer passes of the shards run side by side
+                infos = list(pool.map(lambda r: r.probe(), self.ranks))
+            raise_agreed(infos)
+            kcap, pcap = plan_caps(infos, W, attempt)
+            for r in self.ranks:
+                r.plan(kcap, pcap)
+            self._connect()
+            for k in range(N_STAGES):
+                for r in self.ranks:
+                    r.stage(k, False)
+            outs = [r.finish() for r in self.ranks]
+            if all(rc == _capi.G2N_OK for rc, _ in outs):
+                self.caps = (kcap, pcap)
+                for r, (_, res) in zip(self.ranks, outs):
+                    r.remember(res, kcap, pcap)
+                self.result = [_result(res, W, False) for _, res in outs]
+                return self.result[0]
+        raise _capi.G2NError("multi-GPU build: capacity retries exhausted")
+
+    def matrix(self, fmt: str = "csr"):
+        slabs = [tuple(np.array(a) for a in r.fetch_slab()) for r in self.ranks]
+        return assemble_slabs(slabs, self.result[0].n_global, fmt)
+
+    def node_list(self, raw_bytes_id: bool = False):
+        out = []
+        for r in self.ranks:
+            id0, names = r.node_list(raw_bytes_id)
+            assert id0 == len(out), (id0, len(out))
+            out.extend(names)
+        return out
+
+    def diag_records(self) -> int:
+        return sum(int(x.info["n_records"]) for x in self.result)

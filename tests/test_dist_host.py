@@ -154,3 +154,26 @@ def test_dist_result_reports_what_moved():
     assert (r.n_global, r.row0, r.n_rows, r.nnz_local) == (100, 25, 25, 60)
     assert r.info["keys_to"] == [10, 11, 12, 13] and r.info["pairs_to"] == [20, 21, 22, 23] and r.info["speculative"] is True
     assert ctypes.sizeof(_capi.PathInfo) == 48
+
+
+def test_file_cuts_partition_the_file_at_newlines(tmp_path):
+    """dist.file_cuts: the byte ranges parse_gfa(path, devices=[...]) hands to the GPUs."""
+    import random
+
+    from gfa2network_b200.dist import file_cuts
+
+    r = random.Random(4)
+    for trial in range(30):
+        lines = [bytes(r.choice(b"SLPabc\t+-0123") for _ in range(r.choice([0, 1, 3, 17, 200, 5000]))) + b"\n" for _ in range(r.randrange(0, 40))]
+        data = b"".join(lines)
+        if trial % 3 == 0 and data:
+            data = data[:-1]  # no final newline
+        f = tmp_path / f"t{trial}.gfa"
+        f.write_bytes(data)
+        for world in (1, 2, 3, 8):
+            cuts = file_cuts(str(f), world)
+            assert cuts[0][0] == 0 and cuts[-1][1] == len(data)
+            for (a, b), (c, d) in zip(cuts, cuts[1:]):
+                assert b == c and a <= b
+            for a, b in cuts:
+                assert a == 0 or a == len(data) or data[a - 1:a] == b"\n"

@@ -308,3 +308,85 @@ def test_slab_row_range_passes(monkeypatch, mode):
     out, _ = _build(ranks, _shards(text, G), False, **mode)
     assert all(rc == _capi.G2N_OK for rc, _ in out)
     _check(*_assemble(ranks, out, "csr"), text, mode)
+
+
+def _n_gpus():
+    import torch
+
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("mode", [dict(), dict(directed=False, matrix_format="csr"), dict(bidirected=True, matrix_format="csc", return_node_list=True),
+                                  dict(weight_tag="RC", matrix_format="csr")], ids=str)
+def test_parse_gfa_devices_file_split(tmp_path, mode):
+    """parse_gfa(path, devices=[...]): ONE process, one byte range of the FILE per GPU (newline-aligned cuts, each rank
+    loads its own range), same matrix and node list as the oracle over the whole file.  Needs >= 2 GPUs (skipped on
+    the single-GPU test box; run with `gpurun --gpus 2`)."""
+    if _n_gpus() < 2:
+        pytest.skip("needs two GPUs")
+    from gfa2network_b200 import parse_gfa
+    from gfa2network_b200.synth import synth_gfa
+    from oracle.oracle import oracle_convert_format, oracle_parse_gfa
+
+    kind = 2 if mode.get("weight_tag") else 1
+    text = synth_gfa(40_000, 120_000, seed=11, kind=kind, interleave=1024, n_paths=1, n_walks=1)
+    f = tmp_path / "g.gfa"
+    f.write_bytes(text.tobytes())
+    devices = list(range(min(_n_gpus(), 4)))
+    omode = {k: v for k, v in mode.items() if k not in ("matrix_format", "return_node_list")}
+    fmt = mode.get("matrix_format", "csr")
+    import warnings
+
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        got = parse_gfa(str(f), build_graph=False, build_matrix=True, devices=devices, **mode)
+    assert [str(x.message) for x in w] == ["Skipping unsupported record: W"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        B, onodes = oracle_parse_gfa(text, return_node_list=True, **omode)
+    B = oracle_convert_format(B, fmt)
+    A, nodes = got if mode.get("return_node_list") else (got, None)
+    assert A.format == B.format and A.shape == B.shape and A.dtype == B.dtype
+    assert np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices) and A.data.tobytes() == B.data.tobytes()
+    if nodes is not None:
+        assert nodes == onodes
+    # the second build of the same shape is speculative (no host round trip) and gives the same result
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        A2 = parse_gfa(str(f), build_graph=False, build_matrix=True, devices=devices, **{k: v for k, v in mode.items() if k != "return_node_list"})
+    assert np.array_equal(A2.indptr, B.indptr) and np.array_equal(A2.indices, B.indices) and A2.data.tobytes() == B.data.tobytes()
+
+
+def test_parse_gfa_devices_errors(tmp_path):
+    if _n_gpus() < 2:
+        pytest.skip("needs two GPUs")
+    from gfa2network_b200 import parse_gfa
+
+    f = tmp_path / "bad.gfa"
+    f.write_bytes(b"S\ta\t*\n" * 50 + b"W\tx\n" + b"S\tb\t*\n" * 50 + b"L\tonly\n" + b"S\tc\t*\n" * 50)
+    with pytest.warns(RuntimeWarning, match="Skipping unsupported record: W"):
+        with pytest.raises(ValueError, match="Malformed L record"):
+            parse_gfa(str(f), build_graph=False, build_matrix=True, devices=[0, 1])
+    with pytest.raises(NotImplementedError):
+        parse_gfa(str(f), build_graph=False, build_matrix=True, devices=[0, 1], asymmetric=True)
+
+
+def test_cli_convert_devices(tmp_path):
+    if _n_gpus() < 2:
+        pytest.skip("needs two GPUs")
+    import scipy.sparse as sp
+
+    from gfa2network_b200.cli import main
+    from gfa2network_b200.synth import synth_gfa
+    from oracle.oracle import oracle_parse_gfa
+
+    text = synth_gfa(5_000, 15_000, seed=12)
+    f = tmp_path / "g.gfa"
+    f.write_bytes(text.tobytes())
+    out = tmp_path / "m.npz"
+    main(["convert", str(f), "--matrix", str(out), "--devices", "0,1"])
+    A = sp.load_npz(out)
+    B, onodes = oracle_parse_gfa(text, return_node_list=True)
+    assert A.format == "csr" and np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices) and np.array_equal(A.data, B.data)
+    lines = (tmp_path / "m.npz.nodes.tsv").read_text().splitlines()
+    assert lines == [f"{i}\t{n}" for i, n in enumerate(onodes)]

@@ -16,7 +16,16 @@ from gfa2network_b200 import _capi  # noqa: E402
 name = sys.argv[1] if len(sys.argv) > 1 else "C2"
 scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
-cfg, text, _, _ = make_text(name, scale)
+if name == "custom":  # custom n_seg n_link seq_mean [steps]: GFA-1 text of that shape, default directed CSR
+    from gfa2network_b200.synth import synth_gfa
+
+    n_seg, n_link, seq_mean = int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+    steps = int(sys.argv[5]) if len(sys.argv) > 5 else 5
+    text = synth_gfa(n_seg, n_link, seed=5, kind=1, seq_mean=seq_mean)
+    cfg = dict(mode=dict(), fmt="csr")
+    scale = 0.0
+else:
+    cfg, text, _, _ = make_text(name, scale)
 t = torch.from_numpy(text).cuda()
 mode = cfg["mode"]
 h = _capi.Handle(0)
@@ -47,5 +56,5 @@ for _ in range(steps):
     torch.cuda.synchronize()
     for k, (m, c) in h.kernel_times().items():
         tot[k] = tot.get(k, 0.0) + m / steps
-print(json.dumps({"lib": os.environ.get("G2N_LIB", "default"), "env": {k: v for k, v in os.environ.items() if k.startswith("G2N_DBG")}, "config": name, "scale": scale,
+print(json.dumps({"lib": os.environ.get("G2N_LIB", "default"), "env": {k: v for k, v in os.environ.items() if k.startswith("G2N_DBG")}, "config": name if name != "custom" else " ".join(sys.argv[1:5]), "scale": scale, "text_mb": round(text.size / 1e6, 1),
                   "ms_step": round(ms, 4), "kernels": {k: round(v, 4) for k, v in tot.items()}}))
