@@ -43,7 +43,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             raise RuntimeError("nvcc not found: libg2n.so cannot be built (there is no CPU fallback)")
         extra = os.environ.get("G2N_NVCC_EXTRA", "").split()
         tmp = LIB.with_name(f".libg2n.{os.getpid()}.so")
-        cmd = [nvcc, *NVCC_FLAGS, *extra, "-o", str(tmp), str(CSRC / "g2n.cu")]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-o", str(tmp), str(CSRC / "g2n.cu"), "-lz"]  # zlib: *.gz input (g2n_build_gz)
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)

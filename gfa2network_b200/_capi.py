@@ -21,7 +21,7 @@ DTYPE_NP = {0: np.float64, 1: np.float32, 2: np.int32, 3: np.int8, 4: np.bool_}
 
 EXPORTS = [
     "g2n_abi_version", "g2n_create", "g2n_destroy", "g2n_set_stream", "g2n_host_alloc", "g2n_host_free",
-    "g2n_build", "g2n_build_file", "g2n_convert", "g2n_sizes", "g2n_fetch_matrix", "g2n_names_bytes", "g2n_fetch_names", "g2n_device_result",
+    "g2n_build", "g2n_build_file", "g2n_build_gz", "g2n_convert", "g2n_sizes", "g2n_fetch_matrix", "g2n_names_bytes", "g2n_fetch_names", "g2n_device_result",
     "g2n_status", "g2n_last_error", "g2n_coo_to_compressed", "g2n_set_profile", "g2n_set_speculation", "g2n_kernel_times", "g2n_nodes_tsv_bytes", "g2n_fetch_nodes_tsv",
     "g2n_edge_list_bytes", "g2n_fetch_edge_list", "g2n_bfs", "g2n_levels_reduce", "g2n_fetch_levels",
     "g2n_paths_load", "g2n_path_info", "g2n_path_bfs", "g2n_path_reduce", "g2n_fetch_path_nodes", "g2n_fetch_text",
@@ -106,6 +106,7 @@ def load():
     lib.g2n_host_free.restype = None
     lib.g2n_build.argtypes = [vp, vp, u64, C.POINTER(Params)]
     lib.g2n_build_file.argtypes = [vp, C.c_char_p, C.POINTER(Params)]
+    lib.g2n_build_gz.argtypes = [vp, C.c_char_p, C.POINTER(Params)]
     lib.g2n_convert.argtypes = [vp, i32]
     lib.g2n_sizes.argtypes = [vp, C.POINTER(Sizes)]
     lib.g2n_fetch_matrix.argtypes = [vp, vp, vp, vp]
@@ -240,6 +241,10 @@ class Handle:
     def build_file(self, path: str, params: Params) -> int:
         self.generation += 1
         return self.lib.g2n_build_file(self.h, os.fsencode(path), C.byref(params))
+
+    def build_gz(self, path: str, params: Params) -> int:
+        self.generation += 1
+        return self.lib.g2n_build_gz(self.h, os.fsencode(path), C.byref(params))
 
     def coo_to_compressed(self, row, col, data, nnz: int, n: int, code: int, want: int, indptr, indices, dout) -> int:
         """Stage K4 alone on caller-provided triplets (g2n_coo_to_compressed); it reuses the handle's device

@@ -32,7 +32,7 @@ def _node_not_found(name):
 def _text_bytes(path) -> bytes:
     host, dev_ptr, nbytes, keep = _read_source(path)
     if isinstance(keep, _FileSource):
-        return keep.read_at(0, nbytes)
+        return keep.read_all()
     if dev_ptr is not None:
         return bytes(keep.cpu().numpy().tobytes())
     return host.tobytes()
@@ -69,8 +69,7 @@ def load_paths(path, *, raw_bytes: bool = False):
     host, dev_ptr, _nbytes, keep = _read_source(path)
     if isinstance(keep, _FileSource):
         parse_gfa(keep.path, build_graph=False, build_matrix=True, asymmetric=True)
-        with open(keep.path, "rb") as fh:
-            text = fh.read()
+        text = keep.read_all()
     elif dev_ptr is not None:
         parse_gfa(path, build_graph=False, build_matrix=True, asymmetric=True)
         text = _text_bytes(path)

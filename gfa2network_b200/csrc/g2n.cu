@@ -10,8 +10,10 @@
 #include <string.h>
 
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <zlib.h>
 
 #include <atomic>
 #include <memory>
@@ -130,6 +132,8 @@ struct g2n_handle {
     bool src_resident = false;  // the file is already in h->text (second pass of the same g2n_build_file call)
     std::vector<void*> stage;
     std::vector<cudaEvent_t> stage_ev;
+    void* gz_stage[2] = {nullptr, nullptr};  // pinned 64 MiB windows of inflated text (g2n_build_gz)
+    cudaEvent_t gz_ev[2] = {nullptr, nullptr};
     std::vector<std::thread> readers;
     std::unique_ptr<std::atomic<int>[]> piece_issued;
     std::atomic<int> reader_err{0};
@@ -623,6 +627,7 @@ void g2n_destroy(g2n_handle* h)
     for (cudaEvent_t e : h->copy_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : h->stage_ev) cudaEventDestroy(e);
     for (void* b : h->stage) cudaFreeHost(b);
+    for (int k = 0; k < 2; k++) { if (h->gz_stage[k]) cudaFreeHost(h->gz_stage[k]); if (h->gz_ev[k]) cudaEventDestroy(h->gz_ev[k]); }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -1216,6 +1221,199 @@ int g2n_build_file(g2n_handle* h, const char* path, const g2n_params* p)
     h->src_resident = false;
     close(fd);
     return rc;
+}
+
+// ---- *.gz input (parser.py:108-109 gzip.open).  The reference inflates the whole stream on one core before
+// anything else happens; here the compressed file is mapped, inflated in windows of 64 MiB into two pinned staging
+// buffers and every finished window is copied to the device while the next one is being inflated.  A BGZF file
+// (bgzip: independent <= 64 KiB deflate blocks that announce their size in a gzip extra field) is inflated by all
+// host cores, a plain gzip stream (one or several members) by one, as fast as zlib goes.  The build then runs on the
+// device-resident text.  Any irregularity in the container -> G2N_ERR_INVALID: the caller falls back to the
+// reference's own host inflate, which raises the reference's own exception.
+namespace {
+
+#define G2N_GZ_WINDOW ((u64)64 << 20)
+
+struct BgzfBlock { u64 in_off; u32 in_len, out_len; u64 out_off; };
+
+// walks the members of a BGZF file; false if any member is not a BGZF block
+bool bgzf_index(const uint8_t* z, u64 n, std::vector<BgzfBlock>& blocks, u64& total)
+{
+    u64 p = 0;
+    total = 0;
+    while (p < n) {
+        if (n - p < 28 || z[p] != 0x1f || z[p + 1] != 0x8b || z[p + 2] != 8 || !(z[p + 3] & 4)) return false;
+        const u32 xlen = z[p + 10] | (z[p + 11] << 8);
+        if (n - p < 12 + (u64)xlen + 8) return false;
+        u32 bsize = 0;
+        bool found = false;
+        for (u32 q = 0; q + 4 <= xlen;) {
+            const uint8_t* f = z + p + 12 + q;
+            const u32 slen = f[2] | (f[3] << 8);
+            if (f[0] == 'B' && f[1] == 'C' && slen == 2 && q + 6 <= xlen) { bsize = (f[4] | (f[5] << 8)) + 1u; found = true; }
+            q += 4 + slen;
+        }
+        if (!found || (z[p + 3] & ~4) || bsize < 12 + xlen + 8 || p + bsize > n) return false;
+        BgzfBlock b;
+        b.in_off = p + 12 + xlen;
+        b.in_len = bsize - 12 - xlen - 8;
+        const uint8_t* tr = z + p + bsize - 4;
+        b.out_len = tr[0] | (tr[1] << 8) | (tr[2] << 16) | ((u32)tr[3] << 24);
+        b.out_off = total;
+        if (b.out_len > (1u << 16)) return false;
+        total += b.out_len;
+        blocks.push_back(b);
+        p += bsize;
+    }
+    return true;
+}
+
+bool bgzf_inflate(const uint8_t* z, const BgzfBlock& b, uint8_t* out)
+{
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (inflateInit2(&zs, -15) != Z_OK) return false;
+    zs.next_in = const_cast<Bytef*>(z + b.in_off);
+    zs.avail_in = b.in_len;
+    zs.next_out = out;
+    zs.avail_out = b.out_len;
+    const int rc = b.out_len || b.in_len ? inflate(&zs, Z_FINISH) : Z_STREAM_END;
+    const bool ok = rc == Z_STREAM_END && zs.avail_out == 0;
+    inflateEnd(&zs);
+    if (!ok) return false;
+    const uint8_t* tr = z + b.in_off + b.in_len;  // CRC32 | ISIZE
+    const u32 want = tr[0] | (tr[1] << 8) | (tr[2] << 16) | ((u32)tr[3] << 24);
+    return (u32)crc32(crc32(0L, Z_NULL, 0), out, b.out_len) == want;
+}
+
+}  // namespace
+
+int g2n_build_gz(g2n_handle* h, const char* path, const g2n_params* p)
+{
+    if (!h || !path || !p) return G2N_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) { h->err = std::string("cannot open ") + path; return G2N_ERR_INVALID; }
+    struct stat st;
+    if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) { close(fd); h->err = "not a regular file"; return G2N_ERR_INVALID; }
+    const u64 zn = (u64)st.st_size;
+    const uint8_t* z = zn ? (const uint8_t*)mmap(nullptr, zn, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;
+    close(fd);
+    if (zn && z == (const uint8_t*)MAP_FAILED) { h->err = "cannot map the compressed file"; return G2N_ERR_INVALID; }
+    int rc = G2N_OK;
+    u64 total = 0;
+    auto fail = [&](const char* msg) { h->err = msg; rc = G2N_ERR_INVALID; };
+    do {
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = G2N_ERR_CUDA; break; }
+        for (int k = 0; k < 2 && !rc && !h->gz_stage[1]; k++) {  // two pinned staging windows (the file reader's 8 MiB pieces are too small)
+            if (h->gz_stage[k]) continue;
+            if (cudaHostAlloc(&h->gz_stage[k], G2N_GZ_WINDOW, cudaHostAllocDefault) != cudaSuccess ||
+                cudaEventCreateWithFlags(&h->gz_ev[k], cudaEventDisableTiming) != cudaSuccess) { h->err = "pinned staging for gz input"; rc = G2N_ERR_CUDA; }
+        }
+        if (rc) break;
+        std::vector<BgzfBlock> blocks;
+        const bool bgzf = zn > 0 && bgzf_index(z, zn, blocks, total);
+        if (bgzf) {
+            // ---- block-parallel: windows of whole blocks, all host cores per window
+            if (h->text.ensure(total + 64) != cudaSuccess) { h->err = "out of device memory for the text"; rc = G2N_ERR_CUDA; break; }
+            const unsigned T = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+            size_t b0 = 0;
+            u32 w = 0;
+            while (b0 < blocks.size() && !rc) {
+                size_t b1 = b0;
+                while (b1 < blocks.size() && blocks[b1].out_off + blocks[b1].out_len - blocks[b0].out_off <= G2N_GZ_WINDOW) b1++;
+                const u32 sb = w & 1;
+                cudaEventSynchronize(h->gz_ev[sb]);
+                uint8_t* stage = (uint8_t*)h->gz_stage[sb];
+                const u64 base = blocks[b0].out_off;
+                std::atomic<size_t> next{b0};
+                std::atomic<int> bad{0};
+                std::vector<std::thread> pool;
+                for (unsigned t = 0; t < T; t++)
+                    pool.emplace_back([&]() {
+                        for (;;) {
+                            const size_t i = next.fetch_add(8);
+                            if (i >= b1) break;
+                            for (size_t j = i; j < std::min(i + 8, b1); j++)
+                                if (!bgzf_inflate(z, blocks[j], stage + (blocks[j].out_off - base))) bad.store(1);
+                        }
+                    });
+                for (std::thread& t : pool) t.join();
+                if (bad.load()) { fail("corrupt BGZF block"); break; }
+                const u64 len = blocks[b1 - 1].out_off + blocks[b1 - 1].out_len - base;
+                if (len && (cudaMemcpyAsync(h->text.as<uint8_t>() + base, stage, len, cudaMemcpyHostToDevice, h->copy_stream) != cudaSuccess ||
+                            cudaEventRecord(h->gz_ev[sb], h->copy_stream) != cudaSuccess)) { h->err = "queueing a copy of the inflated text failed"; rc = G2N_ERR_CUDA; }
+                b0 = b1;
+                w++;
+            }
+        } else {
+            // ---- one gzip stream (possibly several concatenated members): streaming inflate, window by window
+            z_stream zs;
+            memset(&zs, 0, sizeof zs);
+            if (inflateInit2(&zs, 15 + 16) != Z_OK) { fail("zlib init"); break; }
+            zs.next_in = const_cast<Bytef*>(z);
+            u64 in_left = zn;
+            u64 cap = 0;
+            {
+                // size guess: ISIZE of the last member (exact for one member below 4 GiB), at least 3x the compressed size
+                u64 guess = zn * 3;
+                if (zn >= 18) { const uint8_t* tr = z + zn - 4; const u64 isz = tr[0] | (tr[1] << 8) | (tr[2] << 16) | ((u64)tr[3] << 24); if (isz > guess) guess = isz; }
+                cap = guess + (1 << 20);
+                if (h->text.ensure(cap + 64) != cudaSuccess) { h->err = "out of device memory for the text"; rc = G2N_ERR_CUDA; inflateEnd(&zs); break; }
+                cap = h->text.cap - 64;
+            }
+            bool done = zn == 0;
+            u32 w = 0;
+            if (zn == 0) fail("empty gz file");
+            while (!done && !rc) {
+                const u32 sb = w & 1;
+                cudaEventSynchronize(h->gz_ev[sb]);
+                uint8_t* stage = (uint8_t*)h->gz_stage[sb];
+                u64 filled = 0;
+                while (filled < G2N_GZ_WINDOW && !done && !rc) {
+                    const u64 room = G2N_GZ_WINDOW - filled;
+                    zs.next_out = stage + filled;
+                    zs.avail_out = (uInt)std::min<u64>(room, 1u << 30);
+                    if (zs.avail_in == 0 && in_left) { const u64 take = std::min<u64>(in_left, 1u << 30); zs.avail_in = (uInt)take; in_left -= take; }
+                    const uInt before = zs.avail_out;
+                    const int zr = inflate(&zs, Z_NO_FLUSH);
+                    filled += before - zs.avail_out;
+                    if (zr == Z_STREAM_END) {
+                        if (zs.avail_in == 0 && in_left == 0) done = true;
+                        else if (inflateReset(&zs) != Z_OK) fail("zlib reset");  // next member
+                    } else if (zr != Z_OK) {
+                        fail(zr == Z_BUF_ERROR ? "truncated gz stream" : "corrupt gz stream");
+                    } else if (zs.avail_in == 0 && in_left == 0 && before == zs.avail_out) {
+                        fail("truncated gz stream");
+                    }
+                }
+                if (rc) break;
+                if (total + filled > cap) {
+                    // the guess was too small: a larger buffer, what is on the device already moves over
+                    if (cudaStreamSynchronize(h->copy_stream) != cudaSuccess) { rc = G2N_ERR_CUDA; break; }
+                    void* bigger = nullptr;
+                    const u64 want = (total + filled) * 2 + (64 << 20);
+                    if (cudaMalloc(&bigger, want + 64) != cudaSuccess) { h->err = "out of device memory for the text"; rc = G2N_ERR_CUDA; break; }
+                    if (total && cudaMemcpy(bigger, h->text.p, total, cudaMemcpyDeviceToDevice) != cudaSuccess) { cudaFree(bigger); rc = G2N_ERR_CUDA; break; }
+                    cudaFree(h->text.p);
+                    h->text.p = bigger;
+                    h->text.cap = want + 64;
+                    cap = want;
+                }
+                if (filled && (cudaMemcpyAsync(h->text.as<uint8_t>() + total, stage, filled, cudaMemcpyHostToDevice, h->copy_stream) != cudaSuccess ||
+                               cudaEventRecord(h->gz_ev[sb], h->copy_stream) != cudaSuccess)) { h->err = "queueing a copy of the inflated text failed"; rc = G2N_ERR_CUDA; }
+                total += filled;
+                w++;
+            }
+            inflateEnd(&zs);
+        }
+        if (!rc && cudaStreamSynchronize(h->copy_stream) != cudaSuccess) rc = G2N_ERR_CUDA;
+    } while (0);
+    if (zn) munmap((void*)z, zn);
+    if (rc) return rc;
+    g2n_params q = *p;
+    q.text_on_device = 1;
+    return g2n_build(h, h->text.as<uint8_t>(), total, &q);
 }
 
 int g2n_convert(g2n_handle* h, int32_t want_format)

@@ -20,7 +20,12 @@ from .builders import _FileSource, _default_device, _raise_parse_error, _read_so
 def _edge_list_bytes(handle, host, dev_ptr, nbytes, keep, bidirected: bool):
     """Returns (bytes of the edge list, diag, rc) for the given source."""
     params = _capi.Params(1, int(bool(bidirected)), 1, 1, 0, _capi.DTYPES["float64"], _capi.FMT_NATIVE, 0 if dev_ptr is None else 1, None, 0, 0)
-    if isinstance(keep, _FileSource):
+    if isinstance(keep, _FileSource) and keep.gz:
+        rc = handle.build_gz(keep.path, params)
+        if rc == _capi.G2N_ERR_INVALID:  # damaged container: the reference's own inflate raises its exception
+            raw = np.frombuffer(keep.read_all(), dtype=np.uint8)
+            rc = handle.build(raw.ctypes.data if raw.size else 0, raw.size, params)
+    elif isinstance(keep, _FileSource):
         rc = handle.build_file(keep.path, params)
     else:
         ptr = dev_ptr if dev_ptr is not None else (host.ctypes.data if nbytes else 0)

@@ -140,8 +140,16 @@ int g2n_build(g2n_handle *h, const uint8_t *text, uint64_t nbytes, const g2n_par
 /* Same build with the text read from a regular file (the reference opens the path itself,
  * parser.py:100-112): reader threads pread() 8 MiB pieces into pinned staging buffers, the pieces are
  * copied to the device as they arrive and tokenized behind the copy.  `p->text_on_device` is ignored.
- * stdin and .gz sources stay with the caller (read / inflate on the host, then g2n_build). */
+ * stdin stays with the caller (read on the host, then g2n_build). */
 int g2n_build_file(g2n_handle *h, const char *path, const g2n_params *p);
+
+/* Same build from a gzip-compressed file (parser.py:108-109 gzip.open): the compressed file is mapped and inflated
+ * in 64 MiB windows into two pinned staging buffers; every finished window is copied to the device while the next one
+ * is inflated.  BGZF files (bgzip: independent blocks that announce their size in a gzip extra field) are inflated
+ * by all host cores, any other gzip stream (one or several members) by one core.  CRC32 / ISIZE of BGZF blocks and
+ * zlib's own checks of plain streams are honoured.  G2N_ERR_INVALID: the container is damaged or not gzip -- the caller
+ * falls back to the reference's own host inflate, which raises the reference's exception. */
+int g2n_build_gz(g2n_handle *h, const char *path, const g2n_params *p);
 
 /* Convert the device-resident raw COO of the last build to CSR/CSC in place of calling
  * convert_format(A, fmt) on the host (utils.py:55).  No-op if already in that format. */

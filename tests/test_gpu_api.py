@@ -116,6 +116,74 @@ def test_convert_format_honours_the_matrix_it_is_given():
     _same(convert_format(A, "csr"), A.copy().asformat("csr"), "after a parse error")
 
 
+def _bgzf(data: bytes, block: int = 0xFF00) -> bytes:
+    """A BGZF file (bgzip's container: independent deflate blocks, size announced in the 'BC' extra field) + EOF block."""
+    import struct
+    import zlib
+
+    out = []
+    for a in list(range(0, len(data), block)) + [None]:
+        chunk = data[a:a + block] if a is not None else b""
+        c = zlib.compressobj(6, zlib.DEFLATED, -15)
+        body = c.compress(chunk) + c.flush()
+        bsize = 12 + 6 + len(body) + 8
+        out.append(b"\x1f\x8b\x08\x04" + b"\0" * 4 + b"\x00\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1) + body
+                   + struct.pack("<II", zlib.crc32(chunk), len(chunk)))
+    return b"".join(out)
+
+
+def test_gz_sources_inflated_by_the_library(tmp_path):
+    """*.gz paths (parser.py:108-109, tests/test_parser.py:98-104): plain gzip, several members, BGZF (block-parallel),
+    a stream larger than one 64 MiB window; damaged containers raise what gzip.open().read() raises."""
+    import gzip
+
+    from gfa2network_b200 import parse_gfa
+    from gfa2network_b200.export import edge_list_bytes
+    from gfa2network_b200.synth import synth_gfa
+    from oracle.oracle import oracle_parse_gfa
+
+    small = synth_gfa(3_000, 9_000, seed=41).tobytes()
+    big = synth_gfa(700_000, 2_100_000, seed=42, seq_mean=40).tobytes()  # > 64 MiB inflated
+    assert len(big) > (64 << 20)
+    cases = {
+        "plain.gfa.gz": (gzip.compress(small, 6), small),
+        "members.gfa.gz": (gzip.compress(small[: len(small) // 2], 1) + gzip.compress(small[len(small) // 2:], 9), small),
+        "bgzf.gfa.gz": (_bgzf(small), small),
+        "bgzf_big.gfa.gz": (_bgzf(big), big),
+        "plain_big.gfa.gz": (gzip.compress(big, 1), big),
+        "empty_member.gfa.gz": (gzip.compress(b""), b""),
+    }
+    for name, (blob, text) in cases.items():
+        f = tmp_path / name
+        f.write_bytes(blob)
+        assert gzip.open(f).read() == text
+        A, nodes = parse_gfa(str(f), build_graph=False, build_matrix=True, return_node_list=True)
+        B, onodes = oracle_parse_gfa(text, return_node_list=True)
+        _same(A, B, name)
+        assert nodes == onodes, name
+    el, exc, _ = edge_list_bytes(str(tmp_path / "bgzf.gfa.gz"))
+    assert exc is None and el.tobytes() == edge_list_bytes(small)[0].tobytes()
+    # damaged containers: the exception of the reference's own gzip.open(...).read()
+    good = cases["plain.gfa.gz"][0]
+    bz = cases["bgzf.gfa.gz"][0]
+    bad = {"trunc.gfa.gz": good[: len(good) // 2], "notgz.gfa.gz": small[:5000], "crc.gfa.gz": good[:-8] + b"\0\0\0\0" + good[-4:],
+           "bgzf_crc.gfa.gz": bz[:200] + bytes([bz[200] ^ 0x55]) + bz[201:], "zero.gfa.gz": b""}
+    for name, blob in bad.items():
+        f = tmp_path / name
+        f.write_bytes(blob)
+        try:
+            want_text = gzip.open(f).read()
+            want_exc = None
+        except Exception as e:  # noqa: BLE001
+            want_text, want_exc = None, e
+        if want_exc is None:
+            A = parse_gfa(str(f), build_graph=False, build_matrix=True)
+            _same(A, oracle_parse_gfa(want_text), name)
+        else:
+            with pytest.raises(type(want_exc)):
+                parse_gfa(str(f), build_graph=False, build_matrix=True)
+
+
 BAD_LINES = [b"L\ta\n", b"L\ta+\tb-\t0M\n", b"S\n", b"P\tonly\n", b"O\tx\n", b"E\t*\ta\t+\tb\n", b"C\ta\t+\tb\n", b"L\t\tb+\t0M\tx\n",
              b"L\ta\t+\tb\t+\t0M\tRC:i:" + b"9" * 400 + b"\n", b"W\tw\t1\n", b"# c\n", b"\n", b"x\ty\n", b"L\ta\t+\tb\t\xff\t0M\n"]
 
