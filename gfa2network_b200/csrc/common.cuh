@@ -3,9 +3,20 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <assert.h>
+
 namespace g2n {
 
 #define G2N_SM_COUNT 148
+
+// -DG2N_CHECKED: bounds assertions on every computed index of the hot kernels (ring positions, table slots, edge
+// records, row cursors, IDs).  compute-sanitizer is closed on the B200 pool, so tools/sanitize_run.py is run against a
+// checked build instead (profiles/r2_checked_build.md); the product build compiles them away.
+#ifdef G2N_CHECKED
+#define G2N_CHECK(cond) assert(cond)
+#else
+#define G2N_CHECK(cond) ((void)0)
+#endif
 
 typedef unsigned long long u64;
 typedef unsigned int u32;

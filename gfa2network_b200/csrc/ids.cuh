@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(256) k_mark_first(const Slot* __restrict__ slo
         ld_slot_stream(&slots[i], v);
         if (v[0] == 0 && v[1] == 0) continue;
         const u32 bit = order_bit(tile_base, ~v[2]);
+        G2N_CHECK((bit >> 5) < ds->words);
         atomicOr(&bitmap[bit >> 5], 1u << (bit & 31));
     }
 }
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(256) k_assign_ids(const Slot* __restrict__ slo
         const u32 ob = order_bit(tile_base, ~v[2]);
         const u32 wd = ob >> 5, bit = ob & 31;
         const u32 id = wprefix[wd] + __popc(bitmap[wd] & ((1u << bit) - 1u));
+        G2N_CHECK(wd < ds->words && id < ds->n);
         slot_id[i] = id;
         id2slot[id] = i;
         name_len[id] = slot_key_len(v[1]);

@@ -194,7 +194,12 @@ __global__ void __launch_bounds__(256) k_edges_scatter_flat(u32* __restrict__ ed
         for (int u = 0; u < EF_BATCH; u++) {
             if (e0 + u * stride < E)
                 record_entries_t<TPE>(id[u], 0u, sym, csc, [&](u32 major, u32 minor, u32 dir, u32) {
-                    if (rr.has(major)) entries[atomicAdd(&cursor[major], 1u)] = Ent32::make(minor, dir, 0u);
+                    if (rr.has(major)) {
+                        G2N_CHECK(major < ds->rows && minor < ds->n);
+                        const u32 pos = atomicAdd(&cursor[major], 1u);
+                        G2N_CHECK(pos < ds->M);
+                        entries[pos] = Ent32::make(minor, dir, 0u);
+                    }
                 });
         }
     }
@@ -249,7 +254,12 @@ __global__ void __launch_bounds__(256) k_rows_scatter_flat(const u32* __restrict
         for (int u = 0; u < EF_BATCH; u++) {
             if (e0 + u * stride < E)
                 record_entries_t<TPE>(id[u], t0[u], sym, csc, [&](u32 major, u32 minor, u32 dir, u32 t) {
-                    if (rr.has(major)) entries[atomicAdd(&cursor[major], 1u)] = Ent64::make(minor, dir, t);
+                    if (rr.has(major)) {
+                        G2N_CHECK(major < ds->rows && minor < ds->n && t < ds->T);
+                        const u32 pos = atomicAdd(&cursor[major], 1u);
+                        G2N_CHECK(pos < ds->M);
+                        entries[pos] = Ent64::make(minor, dir, t);
+                    }
                 });
         }
     }

@@ -360,6 +360,7 @@ __device__ __forceinline__ void enqueue_mention(const ScanParams& P, const Tile&
         if (cp < 8) h0 &= ~(0xFFull << (8 * cp)); else h1 &= ~(0xFFull << (8 * (cp - 8)));
         home = probe_home(h0, h1, t.win[off + cp], ((MODE & TM_BIDIR) && ori == '-') ? 1u : 0u, P.table_mask);
     }
+    G2N_CHECK(idx < WarpSmem<MODE>::kCap && home <= P.table_mask && off + len <= WT_WIN);
     S.qk[idx] = make_ulonglong2(k0, k1);
     S.qx[idx] = make_uint4(home, meta, tile, edge_ord);
 }
@@ -370,7 +371,11 @@ __device__ __forceinline__ void group_load(const ScanParams& P, const SM& S, u32
 {
     const u32 lane = threadIdx.x & 31;
 #ifndef TK_DBG_NOPROBE
-    if (ahead + lane < qn) ld_slot(&P.slots[S.qx[SM::wrap(qh + ahead + lane)].x], v, pol);
+    if (ahead + lane < qn) {
+        const u32 i = S.qx[SM::wrap(qh + ahead + lane)].x;
+        G2N_CHECK(i <= P.table_mask && qn <= SM::kCap);
+        ld_slot(&P.slots[i], v, pol);
+    }
 #endif
 }
 
@@ -407,6 +412,7 @@ __device__ __forceinline__ void drain_group(const ScanParams& P, WarpSmem<MODE>&
             }
         }
 #endif
+        G2N_CHECK(miss ? x.x <= P.table_mask : (i <= P.table_mask || i == 0xFFFFFFFFu));
         if (!miss && (x.y & QM_EDGE) && x.w < P.edge_cap) P.edge_slots[(u64)x.w * SPE + (x.y & 3u)] = i;  // (edge_alloc > edge_cap: the host retries with room)
     }
     const u32 mb = __ballot_sync(0xffffffffu, miss);  // every lane has read its entry: the group's places may be reused
@@ -414,6 +420,7 @@ __device__ __forceinline__ void drain_group(const ScanParams& P, WarpSmem<MODE>&
     qn -= take;
     if (miss) {
         const u32 j = SM::wrap(qh + qn + (u32)__popc(mb & ((1u << lane) - 1u)));
+        G2N_CHECK(j < SM::kCap && qn + (u32)__popc(mb) <= SM::kCap);
         S.qk[j] = k;
         S.qx[j] = x;
     }
@@ -686,6 +693,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, tk_min_blocks<MODE>()) k_tokeni
                 u32 ri = my_rec0, ei = my_edge0;
                 for (u64 m = rec; m; m &= m - 1) {
                     const int bit = __ffsll((long long)m) - 1;
+                    G2N_CHECK(woff0 + bit < WT_WIN && ei < 0x10000u);
                     if (ri - lo < WT_LIST) list[ri - lo] = (woff0 + bit) | (ei << 16);
                     ri++;
                     ei += (u32)((edg >> bit) & 1);
@@ -738,6 +746,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, tk_min_blocks<MODE>()) k_tokeni
                     }
                 }
                 qn += __shfl_sync(0xffffffffu, ninc, 31);
+                G2N_CHECK(qn <= SM::kCap);
                 __syncwarp();
                 drain<MODE>(P, S, qh, qn, false, pol_table, claimed, fly, have_fly);
             }
