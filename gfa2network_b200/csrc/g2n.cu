@@ -294,7 +294,7 @@ size_t dtype_size(int dt)
 // duplicates, write the result.  M and n are host-side bounds (exact or capacities); the kernels read the
 // actual row count from DevSizes.
 template <typename T, class ENT>
-int rows_finalize_typed(g2n_handle* h, u64 M, u64 n, int sym, const double* w_emit, const T* w_typed)
+int rows_finalize_typed(g2n_handle* h, u64 M, u64 n, int sym, const WEmit w_emit, const T* w_typed)
 {
     typedef typename ENT::type E;
     const u32* n_dev = &h->d_ds->rows;
@@ -315,9 +315,9 @@ int rows_finalize_typed(g2n_handle* h, u64 M, u64 n, int sym, const double* w_em
 }
 
 // weighted: 64-bit entries that carry the emission index; unweighted: 32-bit entries
-int rows_finalize(g2n_handle* h, int dtype, bool weighted, u64 M, u64 n, int sym, const double* w_emit, const void* w_typed)
+int rows_finalize(g2n_handle* h, int dtype, bool weighted, u64 M, u64 n, int sym, const WEmit w_emit, const void* w_typed)
 {
-#define G2N_FIN(T) (weighted ? rows_finalize_typed<T, Ent64>(h, M, n, sym, w_emit, (const T*)w_typed) : rows_finalize_typed<T, Ent32>(h, M, n, sym, nullptr, nullptr))
+#define G2N_FIN(T) (weighted ? rows_finalize_typed<T, Ent64>(h, M, n, sym, w_emit, (const T*)w_typed) : rows_finalize_typed<T, Ent32>(h, M, n, sym, WEmit{nullptr, 0u}, nullptr))
     switch (dtype) {
         case G2N_DTYPE_F64: return G2N_FIN(double);
         case G2N_DTYPE_F32: return G2N_FIN(float);
@@ -413,7 +413,7 @@ int build_compressed(g2n_handle* h, int fmt, bool zeroed, bool counted)
         CK(cudaMemsetAsync(h->zrows.p, 0, h->zrows_bytes, h->stream));
     }
     CK(h->entries.ensure((M + 1) * (weighted ? sizeof(u64) : sizeof(u32))));
-    if (weighted) CK(h->w_emit.ensure((T + 1) * sizeof(double)));
+    if (weighted) CK(h->w_emit.ensure((h->cap_E + 1) * sizeof(double)));
     EmitParams E = emit_params(h);
     int rc;
     if (!weighted) {
@@ -483,7 +483,8 @@ int build_compressed(g2n_handle* h, int fmt, bool zeroed, bool counted)
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(h->ev[EV_SORT], h->stream));
-    rc = rows_finalize(h, h->params.dtype, weighted, M, n, sym, weighted ? h->w_emit.as<double>() : nullptr, nullptr);
+    // one weight per edge record: the record's tpe triplets find it at (emission index) >> log2(tpe)
+    rc = rows_finalize(h, h->params.dtype, weighted, M, n, sym, WEmit{weighted ? h->w_emit.as<double>() : nullptr, h->tpe == 4 ? 2u : (h->tpe == 2 ? 1u : 0u)}, nullptr);
     if (rc) return rc;
     CK(cudaEventRecord(h->ev[EV_REDUCE], h->stream));
     return G2N_OK;
@@ -1909,7 +1910,7 @@ int g2n_coo_to_compressed(g2n_handle* h, const int32_t* row, const int32_t* col,
     if (rc) return rc;
     { KScope ks(h, "k_coo_scatter"); k_coo_scatter<<<grid_for(nnz_in, 256), 256, 0, h->stream>>>(h->up_row.as<int32_t>(), h->up_col.as<int32_t>(), nnz_in, csc, h->cursor.as<u32>(), h->entries.as<u64>()); }
     CK(cudaGetLastError());
-    rc = rows_finalize(h, dtype, true, nnz_in, n, 0, nullptr, h->up_data.p);
+    rc = rows_finalize(h, dtype, true, nnz_in, n, 0, WEmit{nullptr, 0u}, h->up_data.p);
     if (rc) return rc;
     CK(cudaMemcpyAsync(&h->h_ctl->s, h->d_ds, sizeof(DevSizes), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -2293,7 +2294,7 @@ int g2n_dist_stage(g2n_handle* h, int stage, const uint8_t* text, uint64_t nbyte
             else { KScope ks(h, "k_pairs_scatter"); k_pairs_scatter<<<pgrid, 256, 0, h->stream>>>(X, L, loc, h->d_ds, h->cursor.as<u32>(), h->entries.as<u32>(), rr); }
         }
         CK(cudaGetLastError());
-        rc = rows_finalize(h, h->params.dtype, weighted, recv_cap, rows_cap, sym, weighted ? h->w_emit.as<double>() : nullptr, nullptr);
+        rc = rows_finalize(h, h->params.dtype, weighted, recv_cap, rows_cap, sym, WEmit{weighted ? h->w_emit.as<double>() : nullptr, 0u}, nullptr);
         if (rc) return rc;
         break;
     }

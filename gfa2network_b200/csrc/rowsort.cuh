@@ -206,17 +206,14 @@ __global__ void __launch_bounds__(256) k_edges_scatter_flat(u32* __restrict__ ed
 }
 
 // histogram of majors (cnt == NULL: the tokenizer counted the rows already); translates edge_slots to node IDs in
-// place and lays the weights out in emission order (w_emit[t]) when there are any
-__global__ void __launch_bounds__(256) k_rows_count(const EmitParams E, int sym, int csc, u32* __restrict__ cnt, double* __restrict__ w_emit,
+// place and lays the weights out by emission ordinal of the record (WEmit) when there are any
+__global__ void __launch_bounds__(256) k_rows_count(const EmitParams E, int sym, int csc, u32* __restrict__ cnt, double* __restrict__ w_rec,
                                                      const RowRange rr, u32* __restrict__ emit_t0)
 {
     for_each_edge(E, [&](u32 stored, u32 t0, const u32 (&id)[4]) {
         if (emit_t0) emit_t0[stored] = t0;  // emission index of the record's first triplet, for the flat scatter passes
         if (cnt) record_entries(id, E.tpe, t0, sym, csc, [&](u32 major, u32, u32, u32) { if (rr.has(major)) atomicAdd(&cnt[major], 1u); });
-        if (w_emit) {
-            const double w = E.edge_w[stored];
-            for (int k = 0; k < E.tpe; k++) w_emit[t0 + k] = w;
-        }
+        if (w_rec) w_rec[t0 / (u32)E.tpe] = E.edge_w[stored];  // one weight per record, at its emission ordinal
     });
 }
 
@@ -358,19 +355,26 @@ struct RowAcc {
     }
 };
 
+// Weights of a build, one per edge RECORD in emission order: the 1 / 2 / 4 triplets of a record share it, so the
+// triplet's emission index t finds it at t >> shift (shift 0: one weight per entry -- multi-GPU slabs)
+struct WEmit {
+    const double* p;
+    u32 shift;
+};
+
 template <typename T, class ENT>
-__device__ __forceinline__ T entry_weight(typename ENT::type e, const double* __restrict__ w_emit, const T* __restrict__ w_typed)
+__device__ __forceinline__ T entry_weight(typename ENT::type e, const WEmit w_emit, const T* __restrict__ w_typed)
 {
     if (ENT::kWeighted) {
         if (w_typed) return w_typed[ENT::t(e)];
-        if (w_emit) return cast_weight<T>(w_emit[ENT::t(e)]);
+        if (w_emit.p) return cast_weight<T>(w_emit.p[ENT::t(e) >> w_emit.shift]);
     }
     return cast_weight<T>(1.0);
 }
 
 // Walks one sorted row; emit(k, minor, value) is called for every stored result.  Returns their count.
 template <typename T, class ENT, class Emit>
-__device__ __forceinline__ u32 walk_row(const typename ENT::type* a, u32 len, int sym, const double* w_emit, const T* w_typed, Emit emit)
+__device__ __forceinline__ u32 walk_row(const typename ENT::type* a, u32 len, int sym, const WEmit w_emit, const T* w_typed, Emit emit)
 {
     u32 out = 0;
     u32 i = 0;
@@ -432,7 +436,7 @@ __device__ __forceinline__ void sort_network(E (&v)[16])
 
 // the sorted row in registers (entries past `len` are all-ones); same contract as walk_row
 template <int N, typename T, class ENT, class Emit>
-__device__ __forceinline__ u32 walk_regs(const typename ENT::type (&v)[N], u32 len, int sym, const double* w_emit, const T* w_typed, Emit emit)
+__device__ __forceinline__ u32 walk_regs(const typename ENT::type (&v)[N], u32 len, int sym, const WEmit w_emit, const T* w_typed, Emit emit)
 {
     u32 out = 0;
     RowAcc<T> acc;
@@ -463,7 +467,7 @@ __device__ __forceinline__ void load_row(typename ENT::type (&v)[N], const typen
 
 // phase 1: sort the row (written back in place) and count the entries it will store
 template <int N, typename T, class ENT>
-__device__ __forceinline__ u32 row_sort_count(typename ENT::type* a, u32 len, int sym, const double* w_emit, const T* w_typed)
+__device__ __forceinline__ u32 row_sort_count(typename ENT::type* a, u32 len, int sym, const WEmit w_emit, const T* w_typed)
 {
     typename ENT::type v[N];
     load_row<N, ENT>(v, a, len);
@@ -480,7 +484,7 @@ __device__ __forceinline__ u32 row_sort_count(typename ENT::type* a, u32 len, in
 
 // phase 2: walk the sorted row and write its results
 template <int N, typename T, class ENT>
-__device__ __forceinline__ void row_emit(const typename ENT::type* a, u32 len, int sym, const double* w_emit, const T* w_typed, u32 out0,
+__device__ __forceinline__ void row_emit(const typename ENT::type* a, u32 len, int sym, const WEmit w_emit, const T* w_typed, u32 out0,
                                          int32_t* __restrict__ indices, T* __restrict__ data)
 {
     typename ENT::type v[N];
@@ -519,7 +523,7 @@ __device__ __forceinline__ void stage_chunk(E* s_ent, const E* __restrict__ src,
 // entries each row will store goes to ucnt.  No CTA depends on another one.
 template <typename T, class ENT>
 __global__ void __launch_bounds__(RF_ROWS) k_rows_sort(const u32* __restrict__ rowptr, typename ENT::type* __restrict__ entries,
-                                                        const u32* __restrict__ n_dev, int sym, const double* __restrict__ w_emit,
+                                                        const u32* __restrict__ n_dev, int sym, const WEmit w_emit,
                                                         const T* __restrict__ w_typed, u32* __restrict__ ucnt)
 {
     typedef typename ENT::type E;
@@ -565,7 +569,7 @@ __global__ void __launch_bounds__(RF_ROWS) k_rows_sort(const u32* __restrict__ r
 // row, write indices / data.
 template <typename T, class ENT>
 __global__ void __launch_bounds__(RF_ROWS) k_rows_write(const u32* __restrict__ rowptr, const typename ENT::type* __restrict__ entries,
-                                                         const u32* __restrict__ n_dev, int sym, const double* __restrict__ w_emit,
+                                                         const u32* __restrict__ n_dev, int sym, const WEmit w_emit,
                                                          const T* __restrict__ w_typed, const int32_t* __restrict__ indptr,
                                                          int32_t* __restrict__ indices, T* __restrict__ data, u32* __restrict__ nnz_out)
 {

@@ -156,12 +156,29 @@ __device__ __forceinline__ bool fast_weight(const ScanParams& P, const Tile& t, 
 #define TM_WEIGHT 4
 
 // the first separators of a short line from one 64-bit slice of the separator mask starting at `pos`
-__device__ __forceinline__ u64 sep_slice(const Tile& t, u32 pos)
+__device__ __forceinline__ u64 mask_slice(const u32* m, u32 pos)
 {
     const u32 w = pos >> 5, sh = pos & 31;
-    const u32 a = t.spm[w], b = t.spm[w + 1], c = t.spm[w + 2];  // spm has two words of slack
+    const u32 a = m[w], b = m[w + 1], c = m[w + 2];  // both masks have two words of slack
     const u32 lo = __funnelshift_r(a, b, sh), hi = __funnelshift_r(b, c, sh);
     return (u64)lo | ((u64)hi << 32);
+}
+__device__ __forceinline__ u64 sep_slice(const Tile& t, u32 pos) { return mask_slice(t.spm, pos); }
+
+// the <= 8 window bytes [off, off + len) as a little-endian u64, bytes past len = '0'
+__device__ __forceinline__ u64 load8_digits(const Tile& t, u32 off, u32 len)
+{
+    const u32* wp = reinterpret_cast<const u32*>(t.win + (off & ~3u));
+    const u32 sh = (off & 3u) * 8u;
+    const u32 a0 = wp[0], a1 = wp[1], a2 = wp[2];
+    const u64 x = (u64)__funnelshift_r(a0, a1, sh) | ((u64)__funnelshift_r(a1, a2, sh) << 32);
+    const u64 keep = len >= 8 ? ~0ull : ((1ull << (8 * len)) - 1ull);
+    return (x & keep) | (0x3030303030303030ull & ~keep);
+}
+// every byte of x is an ASCII digit (borrows / carries only travel upwards from a byte that is already invalid)
+__device__ __forceinline__ bool all_digits8(u64 x)
+{
+    return (((x + 0x4646464646464646ull) | (x - 0x3030303030303030ull) | x) & 0x8080808080808080ull) == 0;
 }
 
 __device__ __forceinline__ void defer_line(const ScanParams& P, u64 off, u32 tile, u32 rec_idx, u32 edge_idx)
@@ -236,11 +253,27 @@ __device__ __forceinline__ bool parse_line_fast(const ScanParams& P, const Tile&
         // coord form (parser.py:254-288): E id u+- s e v+- s e cigar tags...
         u32 e[9];
         e[1] = e1;
+        // the seven separators after fields[1] from one 64-bit slice of the separator mask when the nine fields are that
+        // short (they are: ids and coordinates); none of the first six may be the line's end
+        u64 m = sep_slice(t, e1 + 1);
+        if (__popcll(m) >= 7) {
+            const u64 nlm64 = mask_slice(t.nlm, e1 + 1);
+            u64 first6 = 0;
 #pragma unroll
-        for (int k = 2; k <= 8; k++) {
-            if (t.win[e[k - 1]] != '\t') return false;
-            e[k] = find_sep(t, e[k - 1] + 1);
-            if (e[k] == TK_NF) return false;
+            for (int k = 2; k <= 8; k++) {
+                const u64 low = m & (0 - m);
+                e[k] = e1 + 1 + (u32)__ffsll((long long)m) - 1;
+                if (k <= 7) first6 |= low;
+                m &= m - 1;
+            }
+            if (nlm64 & first6) return false;
+        } else {
+#pragma unroll
+            for (int k = 2; k <= 8; k++) {
+                if (t.win[e[k - 1]] != '\t') return false;
+                e[k] = find_sep(t, e[k - 1] + 1);
+                if (e[k] == TK_NF) return false;
+            }
         }
         // int() probes on fields 3, 4, 6, 7: plain ASCII digits only on the fast path
 #pragma unroll
@@ -248,8 +281,12 @@ __device__ __forceinline__ bool parse_line_fast(const ScanParams& P, const Tile&
             if (k == 5) continue;
             const u32 a = e[k - 1] + 1, b = e[k];
             if (b == a || b - a > 18) return false;
-            for (u32 q = a; q < b; q++)
-                if ((uint8_t)(t.win[q] - '0') > 9) return false;
+            if (b - a <= 8) {
+                if (!all_digits8(load8_digits(t, a, b - a))) return false;
+            } else {
+                for (u32 q = a; q < b; q++)
+                    if ((uint8_t)(t.win[q] - '0') > 9) return false;
+            }
         }
         uo = e[1] + 1; ul = e[2] - uo; vo = e[4] + 1; vl = e[5] - vo;
         if (ul == 0 || vl == 0) return false;
@@ -334,8 +371,8 @@ struct alignas(128) WarpSmemT {
     ulonglong2 qk[QCAP];
     uint4 qx[QCAP];
     u32 list[WT_LIST];  // [15:0] window offset of the line, [31:16] edge index within the tile
-    u32 nl[WT_WORDS];
-    u32 sp[WT_WORDS + 2];  // + 2 words of slack for sep_slice
+    u32 nl[WT_WORDS + 2];  // + 2 words of slack for mask_slice
+    u32 sp[WT_WORDS + 2];
     u64 bar;
     static __device__ __forceinline__ u32 wrap(u32 pos) { return (QCAP & (QCAP - 1)) == 0 ? (pos & (QCAP - 1)) : (pos >= QCAP ? pos - QCAP : pos); }
 };
@@ -506,7 +543,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, tk_min_blocks<MODE>()) k_tokeni
     const u64 pol_text = policy_evict_first();
     const u64 pol_table = table_policy();
     if (lane < 8) reinterpret_cast<u32*>(win + WT_WIN)[lane] = 0x0A0A0A0Au;
-    if (lane < 2) spm[WT_WORDS + lane] = 0;
+    if (lane < 2) { spm[WT_WORDS + lane] = 0; nlm[WT_WORDS + lane] = 0; }
     if (lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&S.bar)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
