@@ -472,6 +472,28 @@ def run_ours(args):
     else:
         d2h = A.indptr.nbytes + A.indices.nbytes + A.data.nbytes
 
+    # ---- the host<->device copy floor of the e2e call on this box: the same bytes in (pinned -> device) and out
+    # (device -> pinned), nothing else, all ranks at once.  e2e cannot be faster than this; with N processes sharing the
+    # host's PCIe root complexes and memory controllers it is what bends the e2e scaling curve.
+    out_dev = torch.empty(int(d2h), dtype=torch.uint8, device=dev)
+    out_host = torch.empty(int(d2h), dtype=torch.uint8).pin_memory()
+    copy_times = []
+    for i in range(6):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        text_dev.copy_(pinned, non_blocking=True)
+        out_host.copy_(out_dev, non_blocking=True)
+        torch.cuda.synchronize()
+        if i:
+            copy_times.append(time.perf_counter() - t0)
+    tcp = torch.tensor([sum(copy_times) / len(copy_times)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tcp, op=dist.ReduceOp.MAX)
+    copy_floor_ms = float(tcp.item()) * 1e3
+    del out_dev, out_host
+
     # ---- N > 1: the north-star workload as well -- every GPU holds 1/8 of C5 (12.5 M segments with sequences / 50 M
     # links, ~5 GB of text per GPU; at N = 8 that is BASELINE's config 5 in full: 100 M segments / 400 M links / ~40 GB).
     # Device-resident build of ONE graph over the N shards, CUDA events, max over ranks; reported beside the line's
@@ -592,6 +614,7 @@ def run_ours(args):
         "cpu_baseline": cpu_base,
         "e2e": {"value": world * nbytes / (e2e_s * 1e9), "unit": "GB/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_s * 1e3, "host_cpus_near_gpu": near,
+                "copy_floor_ms": copy_floor_ms, "copy_floor": "the same bytes pinned -> device and device -> pinned with no build in between, all ranks at once (max over ranks)",
                 "api": "gfa2network_b200.parse_gfa(pinned uint8 buffer, matrix_format=...)" if world == 1 else
                        "gfa2network_b200.dist.DistBuilder.build(shard) + fetch_slab() per rank (bytes are per rank)"},
         "gpu_launches": launches,

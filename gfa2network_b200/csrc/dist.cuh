@@ -363,15 +363,14 @@ __global__ void __launch_bounds__(256) k_dx_send_rank(const Slot* __restrict__ s
             if (!first[(u64)d * L.kcap + pos]) continue;
             const u64 e = klist[(u64)d * L.kcap + pos];
             const u32 ob = (u32)(e >> 32), slot = (u32)e;
-            const u32 wd = ob >> 5, bit = ob & 31;
-            const u32 r = wprefix[wd] + __popc(bitmap[wd] & ((1u << bit) - 1u));
+            const u32 r = bitmap_rank(bitmap, wprefix, ob);
             out[pos] = r;
             id2slot[r] = slot;
             name_len[r] = slot_key_len(slots[slot].k1);
         }
     }
     // the popcount prefix ends with the number of marked bits = this shard's global firsts
-    dx_tail_signal(X, 2, loc, nullptr, 0, ok ? (u64)wprefix[ds->words] : 0ull);
+    dx_tail_signal(X, 2, loc, nullptr, 0, ok ? (u64)wprefix[ds->wgroups] : 0ull);
 }
 
 // ---------------------------------------------------------------- x4: owner -> sources, the node ID of every key

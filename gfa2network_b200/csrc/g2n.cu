@@ -725,9 +725,9 @@ static int layout_zearly(g2n_handle* h, u32 cap, u32 n_tiles, bool slot_counters
 // zids arena: first-appearance bitmap | look-back state of its popcount scan
 static int layout_zids(g2n_handle* h, u64 R_cap)
 {
-    const u64 words = (4 * R_cap + 31) / 32 + 1;
+    const u64 words = ((4 * R_cap + 31) / 32 + 1 + BM_GROUP) / BM_GROUP * BM_GROUP;  // whole groups of BM_GROUP words
     const size_t a = (words * sizeof(u32) + 255) & ~(size_t)255;
-    const size_t b = (scan_state_bytes(words) + 255) & ~(size_t)255;
+    const size_t b = (scan_state_bytes(words / BM_GROUP + 1) + 255) & ~(size_t)255;
     CK(h->zids.ensure(a + b));
     h->d_bitmap = h->zids.as<u32>();
     h->d_scan_words = (u64*)(h->zids.as<uint8_t>() + a);
@@ -1129,8 +1129,8 @@ static int ids_phase(g2n_handle* h)
     CK(h->name_off.ensure((n + 2) * sizeof(u64)));
     if (n > 0) {
         { KScope ks(h, "k_mark_first"); k_mark_first<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->d_slots, cap, h->tile_base.as<u64>(), h->d_bitmap, h->d_ds); }
-        LoadPopc lp{h->d_bitmap};
-        int rc = launch_scan<u32>(h, lp, h->wprefix.as<u32>(), nullptr, words, &h->d_ds->words, h->d_scan_words);
+        LoadPopc8 lp{h->d_bitmap};
+        int rc = launch_scan<u32>(h, lp, h->wprefix.as<u32>(), nullptr, words / BM_GROUP + 1, &h->d_ds->wgroups, h->d_scan_words);
         if (rc) return rc;
         { KScope ks(h, "k_assign_ids"); k_assign_ids<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->d_slots, cap, h->tile_base.as<u64>(), h->d_bitmap, h->wprefix.as<u32>(),
                                                                  h->slot_id.as<u32>(), h->id2slot.as<u32>(), h->name_len.as<u32>(), h->d_ds,
@@ -2215,8 +2215,8 @@ int g2n_dist_stage(g2n_handle* h, int stage, const uint8_t* text, uint64_t nbyte
     case 2: {
         { KScope ks(h, "k_dx_mark"); k_dx_mark<<<kgrid, 256, 0, h->stream>>>(h->d_ds, X, L, my, loc, h->dx_sent.as<u64>(), h->d_bitmap); }
         const u64 words = (4 * h->cap_R + 31) / 32 + 1;
-        LoadPopc lp{h->d_bitmap};
-        int rc = launch_scan<u32>(h, lp, h->wprefix.as<u32>(), nullptr, words, &h->d_ds->words, h->d_scan_words);
+        LoadPopc8 lp{h->d_bitmap};
+        int rc = launch_scan<u32>(h, lp, h->wprefix.as<u32>(), nullptr, words / BM_GROUP + 1, &h->d_ds->wgroups, h->d_scan_words);
         if (rc) return rc;
         { KScope ks(h, "k_dx_send_rank"); k_dx_send_rank<<<kgrid, 256, 0, h->stream>>>(h->d_slots, h->d_ds, X, L, h->dx_sent.as<u64>(), h->d_bitmap, h->wprefix.as<u32>(), h->id2slot.as<u32>(), h->name_len.as<u32>(), loc); }
         break;

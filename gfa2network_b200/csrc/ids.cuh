@@ -43,7 +43,7 @@ __global__ void k_sizes(const Counters* __restrict__ cnt, const u64* __restrict_
     DevSizes s;
     memset(&s, 0, sizeof(s));
     if (ok) {
-        s.n = (u32)n; s.E = (u32)E; s.R = (u32)R; s.words = (u32)((4 * R + 31) / 32 + 1);
+        s.n = (u32)n; s.E = (u32)E; s.R = (u32)R; s.words = (u32)((4 * R + 31) / 32 + 1); s.wgroups = (s.words + BM_GROUP - 1) / BM_GROUP;
         s.T = (u32)T; s.M = (u32)M; s.ok = 1; s.nnz = (u32)T; s.rows = (u32)n;
     }
     *ds = s;
@@ -99,9 +99,8 @@ __global__ void __launch_bounds__(256) k_assign_ids(const Slot* __restrict__ slo
         ld_slot_stream(&slots[i], v);
         if (v[0] == 0 && v[1] == 0) continue;
         const u32 ob = order_bit(tile_base, ~v[2]);
-        const u32 wd = ob >> 5, bit = ob & 31;
-        const u32 id = wprefix[wd] + __popc(bitmap[wd] & ((1u << bit) - 1u));
-        G2N_CHECK(wd < ds->words && id < ds->n);
+        const u32 id = bitmap_rank(bitmap, wprefix, ob);
+        G2N_CHECK((ob >> 5) < ds->words && id < ds->n);
         slot_id[i] = id;
         id2slot[id] = i;
         name_len[id] = slot_key_len(v[1]);

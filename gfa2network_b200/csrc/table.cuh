@@ -109,7 +109,8 @@ struct DevSizes {
     u32 ok;     // 0: a capacity was exceeded or the host has to look at the input: later kernels do nothing
     u32 nnz;    // stored entries of the result (written by the last kernel of the build)
     u32 rows;   // rows of the matrix this GPU builds (n, or the rows of its slab)
-    u32 pad[7];
+    u32 wgroups;  // groups of BM_GROUP bitmap words (what the rank scan runs over)
+    u32 pad[6];
 };
 struct Ctl {
     Counters c;

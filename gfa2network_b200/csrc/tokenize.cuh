@@ -604,9 +604,15 @@ __global__ void __launch_bounds__(WT_WARPS * 32, tk_min_blocks<MODE>()) k_tokeni
         fetched = nxt_tma;
         // the next window is requested from the TMA unit only when this tile's lines are parsed (one window buffer per warp):
         // ask L2 for its lines now, so that the bulk copy finds them there
-        if (nxt_tma && lane < (WT_WIN + 127) / 128 + 1) {
-            const u64 po = ((u64)nxt * WT_TILE - WT_PRE) + (u64)lane * 128;
-            if (po < P.nbytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.text + po));
+#ifndef TK_PF_DIST
+#define TK_PF_DIST 1
+#endif
+        {
+            const u64 pft = (u64)tile + (u64)TK_PF_DIST * n_warps;
+            if (pft < P.tile_end && lane < (WT_WIN + 127) / 128 + 1) {
+                const u64 po = (pft * WT_TILE - WT_PRE) + (u64)lane * 128;
+                if (po < P.nbytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.text + po));
+            }
         }
         // ---- long-line regime (P / W / sequence lines of megabytes, SURVEY 8a row 9: "skipped at full bandwidth"):
         // when this warp's previous tile held at most one record, first look for a line start at all -- a '\n' in
