@@ -321,16 +321,22 @@ struct ProbeSeq {
     }
 };
 
-// home slot.  (h0, h1): the key with its cluster byte zeroed; c: that byte; ori: 1 for the '-' twin of a bidirected key
-__device__ __forceinline__ u32 probe_home(u64 h0, u64 h1, u32 c, u32 ori, u32 mask)
+// home slot.  (h0, h1): the key with its cluster byte (and, for the keys of a bidirected build, its '+' / '-'
+// orientation byte) zeroed; c: the cluster byte; pair: bidirected build; ori: 1 for the '-' twin.
+// A miss in L2 costs a whole 128-byte line of HBM traffic whatever the load's size (tools/ubench/randmem.cu under ncu:
+// 133 bytes of DRAM reads per random 32-byte load), i.e. four slots: the two orientations of a segment -- registered
+// together by every S line and mentioned together by every edge record of a bidirected build (builders.py:190-198,
+// 230-234) -- therefore sit in ADJACENT slots of one line.
+__device__ __forceinline__ u32 probe_home(u64 h0, u64 h1, u32 c, u32 pair, u32 ori, u32 mask)
 {
     // 32-bit multiply-xorshift mix of the four key words (the quality only matters for speed)
     u32 a = (u32)h0 ^ ((u32)(h0 >> 32) * 0x9E3779B1u) ^ ((u32)h1 * 0x85EBCA77u) ^ ((u32)(h1 >> 32) * 0xC2B2AE3Du);
     a ^= a >> 16; a *= 0x21F0AAADu; a ^= a >> 15; a *= 0x735A2D97u; a ^= a >> 15;
     const u32 b = (a ^ (u32)(h0 >> 32) ^ (u32)h1) * 0x9E3779B1u;  // further bits: slot rotation and group stride
     const u32 gmask = mask & ~(u32)(TG_SLOTS - 1);  // tables are at least TG_SLOTS slots
-    // ten digits -> ten of the thirty-two slots, rotated per group of keys; the '-' twin sits ten further
-    return (a & gmask) + ((c + (b >> 27) + 10u * ori) & (TG_SLOTS - 1));
+    // ten digits -> ten of the thirty-two slots (ten of sixteen slot pairs), rotated per group of keys
+    const u32 r = c + (b >> 27);
+    return (a & gmask) + ((pair ? ((r << 1) | ori) : r) & (TG_SLOTS - 1));
 }
 
 // The cluster byte of a key is positional: the last byte, or -- for the keys of a bidirected build, which
@@ -346,13 +352,18 @@ __device__ __forceinline__ ProbeSeq probe_seq(u64 k0, u64 k1, u32 mask, int bidi
         auto byte_at = [&](u32 p) { return (u32)((p < 8 ? k0 >> (8 * p) : k1 >> (8 * (p - 8))) & 0xFF); };
         u32 pos = L - 1;
         if (bidir) {
-            ori = byte_at(L - 1) == '-';
+            const u32 ob = byte_at(L - 1);
+            if (ob == '+' || ob == '-') {  // the twins differ in this byte only: same group, adjacent slots
+                ori = ob == '-';
+                if (L - 1 < 8) h0 &= ~(0xFFull << (8 * (L - 1))); else h1 &= ~(0xFFull << (8 * (L - 1 - 8)));
+            }
             if (L >= 3) pos = L - 3;
         }
         c = byte_at(pos);
         if (pos < 8) h0 &= ~(0xFFull << (8 * pos)); else h1 &= ~(0xFFull << (8 * (pos - 8)));
     }
-    const u32 home = probe_home(h0, h1, c, ori, mask);
+    // (a hashed long key has no twin structure to exploit: it may sit in any slot of its group)
+    const u32 home = probe_home(h0, h1, c, (bidir && top != 0xFF && top >= 2) ? 1u : 0u, ori, mask);
     ProbeSeq q;
     q.g = home & ~(u32)(TG_SLOTS - 1);
     q.boff = home & (TG_SLOTS - 1);

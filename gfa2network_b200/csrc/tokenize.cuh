@@ -395,7 +395,11 @@ __device__ __forceinline__ void enqueue_mention(const ScanParams& P, const Tile&
         const u32 cp = len - 1;
         u64 h0 = k0, h1 = k1;
         if (cp < 8) h0 &= ~(0xFFull << (8 * cp)); else h1 &= ~(0xFFull << (8 * (cp - 8)));
-        home = probe_home(h0, h1, t.win[off + cp], ((MODE & TM_BIDIR) && ori == '-') ? 1u : 0u, P.table_mask);
+        if ((MODE & TM_BIDIR) && (ori == '+' || ori == '-')) {  // the orientation byte sits at key position len + 1
+            const u32 op = len + 1;
+            if (op < 8) h0 &= ~(0xFFull << (8 * op)); else h1 &= ~(0xFFull << (8 * (op - 8)));
+        }
+        home = probe_home(h0, h1, t.win[off + cp], (MODE & TM_BIDIR) ? 1u : 0u, ((MODE & TM_BIDIR) && ori == '-') ? 1u : 0u, P.table_mask);
     }
     G2N_CHECK(idx < WarpSmem<MODE>::kCap && home <= P.table_mask && off + len <= WT_WIN);
     S.qk[idx] = make_ulonglong2(k0, k1);
