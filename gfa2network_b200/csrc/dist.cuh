@@ -262,6 +262,33 @@ __device__ __forceinline__ u32 dx_count(const DxCtl* my, int e, u32 s, u64 cap)
 __device__ __forceinline__ u32 dx_bad(const DxCtl* my, int e, u32 s) { return (u32) * (const volatile u64*)&my->hdr[e][s].bad; }
 __device__ __forceinline__ u32 dx_aux(const DxCtl* my, int e, u32 s) { return (u32) * (const volatile u64*)&my->hdr[e][s].aux; }
 
+// The per-peer segments of an exchange as ONE index space: a kernel walks q in [0, off[world]) grid-strided and finds
+// (segment, position) by a scan of <= 8 shared words -- one pass with every thread busy instead of `world` short loops in
+// a row, each with its own tail of dependent memory latencies.
+struct DxFlat {
+    u32 off[DX_MAXW + 1];
+    __device__ __forceinline__ u32 seg(u32 q) const
+    {
+        u32 s = 0;
+        while (q >= off[s + 1]) s++;
+        return s;
+    }
+};
+// counts -> prefix (thread 0), visible to the CTA after the barrier; `unit` elements per index (rounded up per segment)
+template <class CountOf>
+__device__ __forceinline__ void dx_flat_init(DxFlat& F, int world, u32 unit, CountOf count_of)
+{
+    if (threadIdx.x == 0) {
+        u32 run = 0;
+        for (int s = 0; s < world; s++) {
+            F.off[s] = run;
+            run += (count_of((u32)s) + unit - 1) / unit;
+        }
+        for (int s = world; s <= DX_MAXW; s++) F.off[s] = run;
+    }
+    __syncthreads();
+}
+
 // ---------------------------------------------------------------- x1 consumer: owner table
 __global__ void __launch_bounds__(256) k_dx_insert(const DxPeers X, const DxLayout L, const DxCtl* my, DxLocal* __restrict__ loc,
                                                     const DxOwner G, Counters* __restrict__ cnt)
@@ -279,16 +306,17 @@ __global__ void __launch_bounds__(256) k_dx_insert(const DxPeers X, const DxLayo
     P.bidirected = 0;
     const uint8_t* a = X.arena[X.rank];
     u32 claimed = 0;
-    for (u32 s = 0; s < (u32)X.world; s++) {
-        const u32 n = dx_count(my, 0, s, L.kcap);
-        const TKey* keys = reinterpret_cast<const TKey*>(a + L.off_key) + (u64)s * L.kcap;
-        const u32* ord = reinterpret_cast<const u32*>(a + L.off_ord) + (u64)s * L.kcap;
-        for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-            const TKey k = keys[j];
-            const u32 slot = table_probe(P, k.x, k.y, ((u64)s << 32) | ord[j], false, claimed);
-            if (slot == 0xFFFFFFFFu) atomicOr(&loc->bad, DXB_GTABLE);
-            G.gslot[(u64)s * L.kcap + j] = slot;
-        }
+    __shared__ DxFlat F;
+    dx_flat_init(F, X.world, 1u, [&](u32 s) { return dx_count(my, 0, s, L.kcap); });
+    const u32 total = F.off[X.world];
+    for (u32 q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+        const u32 s = F.seg(q), j = q - F.off[s];
+        const u64 jj = (u64)s * L.kcap + j;
+        const TKey k = reinterpret_cast<const TKey*>(a + L.off_key)[jj];
+        const u32 o = reinterpret_cast<const u32*>(a + L.off_ord)[jj];
+        const u32 slot = table_probe(P, k.x, k.y, ((u64)s << 32) | o, false, claimed);
+        if (slot == 0xFFFFFFFFu) atomicOr(&loc->bad, DXB_GTABLE);
+        G.gslot[jj] = slot;
     }
 }
 
@@ -296,26 +324,29 @@ __global__ void __launch_bounds__(256) k_dx_insert(const DxPeers X, const DxLayo
 // four keys per thread: one 32-bit store into the peer's memory
 __global__ void __launch_bounds__(256) k_dx_reply_first(const DxPeers X, const DxLayout L, const DxCtl* my, DxLocal* __restrict__ loc, const DxOwner G)
 {
-    for (u32 s = 0; s < (u32)X.world; s++) {
+    __shared__ DxFlat F;
+    dx_flat_init(F, X.world, 4u, [&](u32 s) { return dx_count(my, 0, s, L.kcap); });
+    const u32 total = F.off[X.world];
+    for (u32 qq = blockIdx.x * blockDim.x + threadIdx.x; qq < total; qq += gridDim.x * blockDim.x) {
+        const u32 s = F.seg(qq), q = qq - F.off[s];
         const u32 n = dx_count(my, 0, s, L.kcap);
         const u32* gs = G.gslot + (u64)s * L.kcap;
         u32* out = reinterpret_cast<u32*>(X.arena[s] + L.off_first + (u64)X.rank * L.kcap);  // kcap is a multiple of 4
-        for (u32 q = blockIdx.x * blockDim.x + threadIdx.x; q * 4 < n; q += gridDim.x * blockDim.x) {
-            u32 word = 0;
+        u32 g[4];
+        u64 f[4];
 #pragma unroll
-            for (u32 t = 0; t < 4; t++) {
-                const u32 j = q * 4 + t;
-                if (j >= n) break;
-                const u32 g = gs[j];
-                if (g == 0xFFFFFFFFu) continue;
-                const u64 f = ~G.gslots[g].first;
-                if ((u32)(f >> 32) == s) {
-                    word |= 1u << (8 * t);
-                    G.gpos[g] = j;
-                }
+        for (u32 t = 0; t < 4; t++) g[t] = q * 4 + t < n ? gs[q * 4 + t] : 0xFFFFFFFFu;
+#pragma unroll
+        for (u32 t = 0; t < 4; t++) f[t] = g[t] != 0xFFFFFFFFu ? ~G.gslots[g[t]].first : ~0ull;
+        u32 word = 0;
+#pragma unroll
+        for (u32 t = 0; t < 4; t++) {
+            if (g[t] != 0xFFFFFFFFu && (u32)(f[t] >> 32) == s) {
+                word |= 1u << (8 * t);
+                G.gpos[g[t]] = q * 4 + t;
             }
-            out[q] = word;
         }
+        out[q] = word;
     }
     dx_tail_signal(X, 1, loc, nullptr, 0, 0);
 }
@@ -337,13 +368,14 @@ __global__ void __launch_bounds__(256) k_dx_mark(const DevSizes* __restrict__ ds
     }
     if (!ds->ok) return;
     const uint8_t* first = X.arena[X.rank] + L.off_first;
-    for (u32 d = 0; d < (u32)X.world; d++) {
-        const u32 n = dx_sent_count(loc, d, L.kcap);
-        for (u32 pos = blockIdx.x * blockDim.x + threadIdx.x; pos < n; pos += gridDim.x * blockDim.x) {
-            if (!first[(u64)d * L.kcap + pos]) continue;
-            const u32 bit = (u32)(klist[(u64)d * L.kcap + pos] >> 32);
-            atomicOr(&bitmap[bit >> 5], 1u << (bit & 31));
-        }
+    __shared__ DxFlat F;
+    dx_flat_init(F, X.world, 1u, [&](u32 d) { return dx_sent_count(loc, d, L.kcap); });
+    const u32 total = F.off[X.world];
+    for (u32 q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+        const u32 d = F.seg(q), pos = q - F.off[d];
+        if (!first[(u64)d * L.kcap + pos]) continue;
+        const u32 bit = (u32)(klist[(u64)d * L.kcap + pos] >> 32);
+        atomicOr(&bitmap[bit >> 5], 1u << (bit & 31));
     }
 }
 
@@ -356,18 +388,18 @@ __global__ void __launch_bounds__(256) k_dx_send_rank(const Slot* __restrict__ s
 {
     const bool ok = ds->ok != 0;
     const uint8_t* first = X.arena[X.rank] + L.off_first;
-    for (u32 d = 0; ok && d < (u32)X.world; d++) {
-        const u32 n = dx_sent_count(loc, d, L.kcap);
-        u32* out = reinterpret_cast<u32*>(X.arena[d] + L.off_rank) + (u64)X.rank * L.kcap;
-        for (u32 pos = blockIdx.x * blockDim.x + threadIdx.x; pos < n; pos += gridDim.x * blockDim.x) {
-            if (!first[(u64)d * L.kcap + pos]) continue;
-            const u64 e = klist[(u64)d * L.kcap + pos];
-            const u32 ob = (u32)(e >> 32), slot = (u32)e;
-            const u32 r = bitmap_rank(bitmap, wprefix, ob);
-            out[pos] = r;
-            id2slot[r] = slot;
-            name_len[r] = slot_key_len(slots[slot].k1);
-        }
+    __shared__ DxFlat F;
+    dx_flat_init(F, X.world, 1u, [&](u32 d) { return ok ? dx_sent_count(loc, d, L.kcap) : 0u; });
+    const u32 total = F.off[X.world];
+    for (u32 q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+        const u32 d = F.seg(q), pos = q - F.off[d];
+        if (!first[(u64)d * L.kcap + pos]) continue;
+        const u64 e = klist[(u64)d * L.kcap + pos];
+        const u32 ob = (u32)(e >> 32), slot = (u32)e;
+        const u32 r = bitmap_rank(bitmap, wprefix, ob);
+        (reinterpret_cast<u32*>(X.arena[d] + L.off_rank) + (u64)X.rank * L.kcap)[pos] = r;
+        id2slot[r] = slot;
+        name_len[r] = slot_key_len(slots[slot].k1);
     }
     // the popcount prefix ends with the number of marked bits = this shard's global firsts
     dx_tail_signal(X, 2, loc, nullptr, 0, ok ? (u64)wprefix[ds->wgroups] : 0ull);
@@ -401,22 +433,21 @@ __global__ void __launch_bounds__(256) k_dx_reply_ids(const DxPeers X, const DxL
     }
     __syncthreads();
     const u32* ranks = reinterpret_cast<const u32*>(X.arena[X.rank] + L.off_rank);
-    for (u32 s = 0; s < (u32)X.world; s++) {
-        const u32 n = dx_count(my, 0, s, L.kcap);
-        const u32* gs = G.gslot + (u64)s * L.kcap;
-        u32* out = reinterpret_cast<u32*>(X.arena[s] + L.off_id) + (u64)X.rank * L.kcap;
-        for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-            const u32 g = gs[j];
-            u32 id = 0;
-            if (g != 0xFFFFFFFFu) {
-                const u32 fs = (u32)((~G.gslots[g].first) >> 32);
-                if (fs < (u32)X.world) {
-                    const u32 p = G.gpos[g];
-                    if (p < L.kcap) id = s_base[fs] + ranks[(u64)fs * L.kcap + p];
-                }
+    __shared__ DxFlat F;
+    dx_flat_init(F, X.world, 1u, [&](u32 s) { return dx_count(my, 0, s, L.kcap); });
+    const u32 total = F.off[X.world];
+    for (u32 q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+        const u32 s = F.seg(q), j = q - F.off[s];
+        const u32 g = G.gslot[(u64)s * L.kcap + j];
+        u32 id = 0;
+        if (g != 0xFFFFFFFFu) {
+            const u32 fs = (u32)((~G.gslots[g].first) >> 32);
+            if (fs < (u32)X.world) {
+                const u32 p = G.gpos[g];
+                if (p < L.kcap) id = s_base[fs] + ranks[(u64)fs * L.kcap + p];
             }
-            out[j] = id;
         }
+        (reinterpret_cast<u32*>(X.arena[s] + L.off_id) + (u64)X.rank * L.kcap)[j] = id;
     }
     dx_tail_signal(X, 3, loc, nullptr, 0, 0);
 }
@@ -435,10 +466,12 @@ __global__ void __launch_bounds__(256) k_dx_localmap(const DevSizes* __restrict_
     }
     if (!ds->ok) return;
     const u32* ids = reinterpret_cast<const u32*>(X.arena[X.rank] + L.off_id);
-    for (u32 d = 0; d < (u32)X.world; d++) {
-        const u32 n = dx_sent_count(loc, d, L.kcap);
-        for (u32 pos = blockIdx.x * blockDim.x + threadIdx.x; pos < n; pos += gridDim.x * blockDim.x)
-            slot_id[(u32)klist[(u64)d * L.kcap + pos]] = ids[(u64)d * L.kcap + pos];
+    __shared__ DxFlat F;
+    dx_flat_init(F, X.world, 1u, [&](u32 d) { return dx_sent_count(loc, d, L.kcap); });
+    const u32 total = F.off[X.world];
+    for (u32 q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+        const u32 d = F.seg(q), pos = q - F.off[d];
+        slot_id[(u32)klist[(u64)d * L.kcap + pos]] = ids[(u64)d * L.kcap + pos];
     }
 }
 
@@ -560,14 +593,14 @@ __global__ void __launch_bounds__(256) k_pairs_count(const DxPeers X, const DxLa
     if (!ds->ok) return;
     const u32 row0 = loc->row0, n_rows = loc->n_rows;
     const DistPair* base = reinterpret_cast<const DistPair*>(X.arena[X.rank] + L.off_pair);
-    for (u32 s = 0; s < (u32)X.world; s++) {
-        const u32 n = loc->seg_off[s + 1] - loc->seg_off[s];
-        const DistPair* pairs = base + (u64)s * L.pcap;
-        for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-            const u32 r = pairs[i].major - row0;
-            if (r >= n_rows) atomicOr(bad_out, DXB_RANGE);
-            else if (rr.has(r)) atomicAdd(&cnt[r], 1u);
-        }
+    __shared__ DxFlat F;
+    dx_flat_init(F, X.world, 1u, [&](u32 s) { return loc->seg_off[s + 1] - loc->seg_off[s]; });
+    const u32 total = F.off[X.world];
+    for (u32 q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+        const u32 s = F.seg(q);
+        const u32 r = base[(u64)s * L.pcap + (q - F.off[s])].major - row0;
+        if (r >= n_rows) atomicOr(bad_out, DXB_RANGE);
+        else if (rr.has(r)) atomicAdd(&cnt[r], 1u);
     }
 }
 
@@ -578,14 +611,14 @@ __global__ void __launch_bounds__(256) k_pairs_scatter(const DxPeers X, const Dx
     if (!ds->ok) return;
     const u32 row0 = loc->row0, n_rows = loc->n_rows;
     const DistPair* base = reinterpret_cast<const DistPair*>(X.arena[X.rank] + L.off_pair);
-    for (u32 s = 0; s < (u32)X.world; s++) {
-        const u32 n = loc->seg_off[s + 1] - loc->seg_off[s];
-        const DistPair* pairs = base + (u64)s * L.pcap;
-        for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-            const DistPair p = pairs[i];
-            const u32 r = p.major - row0;
-            if (r < n_rows && rr.has(r)) entries[atomicAdd(&cursor[r], 1u)] = p.entry;
-        }
+    __shared__ DxFlat F;
+    dx_flat_init(F, X.world, 1u, [&](u32 s) { return loc->seg_off[s + 1] - loc->seg_off[s]; });
+    const u32 total = F.off[X.world];
+    for (u32 q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+        const u32 s = F.seg(q);
+        const DistPair p = base[(u64)s * L.pcap + (q - F.off[s])];
+        const u32 r = p.major - row0;
+        if (r < n_rows && rr.has(r)) entries[atomicAdd(&cursor[r], 1u)] = p.entry;
     }
 }
 
@@ -691,14 +724,14 @@ __global__ void __launch_bounds__(256) k_pairsw_count(const DxPeers X, const DxL
     if (!ds->ok) return;
     const u32 row0 = loc->row0, n_rows = loc->n_rows;
     const DistPairW* base = reinterpret_cast<const DistPairW*>(X.arena[X.rank] + L.off_pair);
-    for (u32 s = 0; s < (u32)X.world; s++) {
-        const u32 n = loc->seg_off[s + 1] - loc->seg_off[s];
-        const DistPairW* pairs = base + (u64)s * L.pcap;
-        for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-            const u32 r = pairs[i].major - row0;
-            if (r >= n_rows) atomicOr(bad_out, DXB_RANGE);
-            else if (rr.has(r)) atomicAdd(&cnt[r], 1u);
-        }
+    __shared__ DxFlat F;
+    dx_flat_init(F, X.world, 1u, [&](u32 s) { return loc->seg_off[s + 1] - loc->seg_off[s]; });
+    const u32 total = F.off[X.world];
+    for (u32 q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+        const u32 s = F.seg(q);
+        const u32 r = base[(u64)s * L.pcap + (q - F.off[s])].major - row0;
+        if (r >= n_rows) atomicOr(bad_out, DXB_RANGE);
+        else if (rr.has(r)) atomicAdd(&cnt[r], 1u);
     }
 }
 
@@ -708,16 +741,16 @@ __global__ void __launch_bounds__(256) k_pairsw_scatter(const DxPeers X, const D
     if (!ds->ok) return;
     const u32 row0 = loc->row0, n_rows = loc->n_rows;
     const DistPairW* base = reinterpret_cast<const DistPairW*>(X.arena[X.rank] + L.off_pair);
-    for (u32 s = 0; s < (u32)X.world; s++) {
-        const u32 off = loc->seg_off[s], n = loc->seg_off[s + 1] - off;
-        const DistPairW* pairs = base + (u64)s * L.pcap;
-        for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-            const DistPairW p = pairs[i];
-            const u32 r = p.major - row0;
-            if (r < n_rows && rr.has(r)) {
-                w_emit[off + i] = p.w;
-                entries[atomicAdd(&cursor[r], 1u)] = Ent64::make(Ent32::minor(p.entry), Ent32::dir(p.entry), off + i);
-            }
+    __shared__ DxFlat F;  // = loc->seg_off: the flat index IS the arrival (= emission) number
+    dx_flat_init(F, X.world, 1u, [&](u32 s) { return loc->seg_off[s + 1] - loc->seg_off[s]; });
+    const u32 total = F.off[X.world];
+    for (u32 q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+        const u32 s = F.seg(q);
+        const DistPairW p = base[(u64)s * L.pcap + (q - F.off[s])];
+        const u32 r = p.major - row0;
+        if (r < n_rows && rr.has(r)) {
+            w_emit[q] = p.w;
+            entries[atomicAdd(&cursor[r], 1u)] = Ent64::make(Ent32::minor(p.entry), Ent32::dir(p.entry), q);
         }
     }
 }

@@ -2199,7 +2199,7 @@ int g2n_dist_stage(g2n_handle* h, int stage, const uint8_t* text, uint64_t nbyte
     G.gmask = h->dx_gcap - 1;
     G.gslot = h->dx_gslot.as<u32>();
     G.gpos = h->dx_gpos.as<u32>();
-    const u32 kgrid = grid_for(L.kcap, 256, 8);
+    const u32 kgrid = grid_for((u64)W * L.kcap, 256, 8);  // the kernels walk all per-peer segments as one index space (DxFlat)
     const int sym = h->symmax ? 1 : 0;
     const int csc = (!sym && h->params.want_format == G2N_FMT_CSC) ? 1 : 0;
     switch (stage) {
@@ -2209,7 +2209,7 @@ int g2n_dist_stage(g2n_handle* h, int stage, const uint8_t* text, uint64_t nbyte
     }
     case 1: {
         { KScope ks(h, "k_dx_insert"); k_dx_insert<<<kgrid, 256, 0, h->stream>>>(X, L, my, loc, G, h->d_cnt); }
-        { KScope ks(h, "k_dx_reply_first"); k_dx_reply_first<<<grid_for(L.kcap / 4 + 1, 256, 8), 256, 0, h->stream>>>(X, L, my, loc, G); }
+        { KScope ks(h, "k_dx_reply_first"); k_dx_reply_first<<<grid_for((u64)W * L.kcap / 4 + 1, 256, 8), 256, 0, h->stream>>>(X, L, my, loc, G); }
         break;
     }
     case 2: {
@@ -2279,7 +2279,7 @@ int g2n_dist_stage(g2n_handle* h, int stage, const uint8_t* text, uint64_t nbyte
         h->spec = false;
         CK(cudaMemsetAsync(h->zrows.p, 0, h->zrows_bytes, h->stream));
         h->result_format = csc ? G2N_FMT_CSC : G2N_FMT_CSR;
-        const u32 pgrid = grid_for(recv_cap / (u64)W + 1, 256, 8);
+        const u32 pgrid = grid_for(recv_cap + 1, 256, 8);
         const RowPasses rp = row_passes(recv_cap, weighted ? sizeof(u64) : sizeof(u32), rows_cap);
         {
             const RowRange rr = ROW_RANGE_ALL;
