@@ -281,6 +281,11 @@ def algo_bytes(name, st):
         "k_rows_sort": 2 * ent * M + 8 * n,                        # entries in and (sorted) out, rowptr in, counts out
         "k_rows_write": ent * M + 8 * n + 12 * nnz,                # entries in, rowptr + indptr in, indices/data out
         "k_emit_coo": 4 * spe * E + 16 * M,
+        # bucketed row build (row arrays far larger than L2): records -> bucket-major (major, entry) pairs -> rows
+        "k_bucket_count": 2 * 4 * spe * E,                         # slots in, ids out
+        "k_bucket_scatter": 4 * spe * E + (4 * E if weighted else 0) + (4 + ent) * M,
+        "k_bucket_rows_count": 4 * M + 4 * M,
+        "k_bucket_rows_scatter": (4 + ent) * M + 4 * M + ent * M,
         # multi-GPU (dist.cuh); n = keys of this shard, M = row entries of this shard / slab
         "k_dx_export": 24 * 2 * n + 24 * n,   # local table in (keys + first at load <= 0.5), key + order + position out
         "k_dx_insert": 20 * n + 24 * n + 4 * n,

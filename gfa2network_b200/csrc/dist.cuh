@@ -755,6 +755,118 @@ __global__ void __launch_bounds__(256) k_pairsw_scatter(const DxPeers X, const D
     }
 }
 
+__device__ __forceinline__ void dx_pair_weight(const DistPair&, double*, u32) {}
+__device__ __forceinline__ void dx_pair_weight(const DistPairW& p, double* w_emit, u32 q) { w_emit[q] = p.w; }
+
+// ---------------------------------------------------------------- slabs far larger than L2: bucketed receive
+// Same idea as the single-GPU bucketed build (rowsort.cuh: RowBuckets): the received entries are first partitioned by
+// row bucket of the slab into a bucket-major pair list (local row, entry), and k_bucket_rows_count /
+// k_bucket_rows_scatter stream over that list.  PAIR = DistPair -> Ent32, DistPairW -> Ent64 (the flat arrival
+// number is the emission index, the weight is laid out by it on the way).
+template <class PAIR>
+__global__ void __launch_bounds__(256) k_pairs_bucket_count(const DxPeers X, const DxLayout L, const DxLocal* __restrict__ loc, const DevSizes* __restrict__ ds,
+                                                             const RowBuckets rb, BucketCtl* __restrict__ ctl, u32* __restrict__ bad_out)
+{
+    __shared__ u32 s_cnt[8][RB_MAX];
+    __shared__ DxFlat F;
+    for (u32 i = threadIdx.x; i < 8 * RB_MAX; i += 256) (&s_cnt[0][0])[i] = 0;
+    if (!ds->ok) return;
+    dx_flat_init(F, X.world, 1u, [&](u32 s) { return loc->seg_off[s + 1] - loc->seg_off[s]; });
+    const u32 row0 = loc->row0, n_rows = loc->n_rows, wid = threadIdx.x >> 5;
+    const PAIR* base = reinterpret_cast<const PAIR*>(X.arena[X.rank] + L.off_pair);
+    const u32 total = F.off[X.world];
+    for (u32 q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+        const u32 s = F.seg(q);
+        const u32 r = base[(u64)s * L.pcap + (q - F.off[s])].major - row0;
+        if (r >= n_rows) atomicOr(bad_out, DXB_RANGE);
+        else atomicAdd(&s_cnt[wid][rb.of(r)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < rb.count) {
+        u32 c = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) c += s_cnt[w][threadIdx.x];
+        if (c) atomicAdd(&ctl->cnt[threadIdx.x], c);
+    }
+}
+
+template <class PAIR, class ENT>
+__global__ void __launch_bounds__(256) k_pairs_bucket_scatter(const DxPeers X, const DxLayout L, const DxLocal* __restrict__ loc, const DevSizes* __restrict__ ds,
+                                                               const RowBuckets rb, BucketCtl* __restrict__ ctl, u32* __restrict__ pair_major,
+                                                               typename ENT::type* __restrict__ pair_ent, double* __restrict__ w_emit)
+{
+    typedef typename ENT::type EV;
+    constexpr int PER = RB_ROUND / 256;
+    __shared__ u32 s_off[RB_MAX], s_cnt[RB_MAX], s_lo[RB_MAX + 1], s_base[RB_MAX];
+    __shared__ u32 s_major[RB_ROUND];
+    __shared__ EV s_ent[RB_ROUND];
+    __shared__ DxFlat F;
+    if (!ds->ok) return;
+    dx_flat_init(F, X.world, 1u, [&](u32 s) { return loc->seg_off[s + 1] - loc->seg_off[s]; });
+    if (threadIdx.x == 0) {
+        u32 run = 0;
+        for (u32 b = 0; b < rb.count; b++) { s_off[b] = run; run += ctl->cnt[b]; }
+    }
+    const u32 row0 = loc->row0, n_rows = loc->n_rows;
+    const PAIR* base = reinterpret_cast<const PAIR*>(X.arena[X.rank] + L.off_pair);
+    const u64 total = F.off[X.world];
+    for (u64 q0 = (u64)blockIdx.x * RB_ROUND; q0 < total; q0 += (u64)gridDim.x * RB_ROUND) {  // uniform per CTA
+        if (threadIdx.x < RB_MAX) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        u32 row[PER];
+        EV ent[PER];
+        unsigned short rk[PER];
+#pragma unroll
+        for (int u = 0; u < PER; u++) {
+            const u64 q = q0 + u * 256 + threadIdx.x;
+            row[u] = 0xFFFFFFFFu;
+            ent[u] = (EV)0;
+            if (q < total) {
+                const u32 s = F.seg((u32)q);
+                const PAIR p = base[(u64)s * L.pcap + ((u32)q - F.off[s])];
+                const u32 r = p.major - row0;
+                if (r < n_rows) {
+                    row[u] = r;
+                    ent[u] = ENT::make(Ent32::minor(p.entry), Ent32::dir(p.entry), (u32)q);
+                    dx_pair_weight(p, w_emit, (u32)q);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < PER; u++)
+            if (row[u] != 0xFFFFFFFFu) rk[u] = (unsigned short)atomicAdd(&s_cnt[rb.of(row[u])], 1u);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            u32 run = 0;
+            for (u32 b = 0; b < rb.count; b++) { s_lo[b] = run; run += s_cnt[b]; }
+            s_lo[rb.count] = run;
+        }
+        if (threadIdx.x < rb.count) {
+            const u32 c = s_cnt[threadIdx.x];
+            s_base[threadIdx.x] = s_off[threadIdx.x] + (c ? atomicAdd(&ctl->cur[threadIdx.x], c) : 0u);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < PER; u++) {
+            if (row[u] != 0xFFFFFFFFu) {
+                const u32 p = s_lo[rb.of(row[u])] + rk[u];
+                s_major[p] = row[u];
+                s_ent[p] = ent[u];
+            }
+        }
+        __syncthreads();
+        const u32 n = s_lo[rb.count];
+        for (u32 p = threadIdx.x; p < n; p += 256) {
+            const u32 r = s_major[p];
+            const u32 b = rb.of(r);
+            const u64 pos = (u64)s_base[b] + (p - s_lo[b]);
+            pair_major[pos] = r;
+            pair_ent[pos] = s_ent[p];
+        }
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------- x6 consumer: the build's verdict, same on every rank
 __global__ void k_dx_final(const DxPeers X, const DxCtl* my, DxLocal* __restrict__ loc)
 {

@@ -77,6 +77,7 @@ struct g2n_handle {
     DevBuf text, defer, edge_slots, edge_w, longs, tile_info, tile_base, wprefix, slot_id, id2slot, name_len, name_off, names;
     DevBuf rowptr, cursor, entries, w_emit, biglist, ucnt, indptr, indices, data, row, col, scan_state;
     DevBuf up_row, up_col, up_data, tsv, tsv_off, el_len, el_off, el_text, emit_t0;
+    DevBuf pair_major, pair_ent, bucket_ctl;  // bucketed row build (rowsort.cuh: RowBuckets)
     DevBuf bfs_levels, bfs_q0, bfs_q1, bfs_ctl, bfs_nodes, bfs_out;  // distances on the resident CSR (bfs.cuh)
     int bfs_slots = 0;
     u64 bfs_n = 0;
@@ -346,7 +347,10 @@ struct RowPasses {
 static const RowRange ROW_RANGE_ALL = {0u, 0xFFFFFFFFu};
 static RowPasses row_passes(u64 M, size_t ent_bytes, u64 n)
 {
-    const u64 bytes = M * ent_bytes + n * 8, budget = 96ull << 20;  // C3: 12 passes (4.3-4.5 ms vs 6.7 ms in one), C2: one
+    // one pass / no buckets up to 96 MB of row arrays (C2: one); beyond that buckets of about 32 MB each (C4d: 32 buckets
+    // 13.8 ms against 15.2 ms with 8, profiles/r3_buckets.md; more than 32 changes nothing)
+    const u64 bytes = M * ent_bytes + n * 8;
+    const u64 budget = (bytes <= (96ull << 20) || getenv("G2N_DBG_NOBUCKET")) ? 96ull << 20 : 32ull << 20;
     u64 R = (bytes + budget - 1) / budget;
     if (const char* e = getenv("G2N_DBG_ROWPASS")) R = (u64)atoll(e);
     if (R < 1) R = 1;
@@ -357,6 +361,63 @@ static RowPasses row_passes(u64 M, size_t ent_bytes, u64 n)
     rp.width = (u32)((n + R - 1) / R);
     if (rp.width == 0) rp.width = 1;
     return rp;
+}
+
+int rows_scan(g2n_handle* h, u64 n_cap, const u32* n_dev);
+
+// Row buckets of the partitioned build: a power-of-two number of rows each, about as many buckets as row_passes() asks
+// for passes (never more than RB_MAX).
+static RowBuckets row_buckets(const RowPasses& rp, u64 n)
+{
+    RowBuckets rb;
+    rb.shift = 0;
+    while (rb.shift < 31 && (2ull << rb.shift) <= rp.width) rb.shift++;  // largest power of two <= width
+    while (rb.shift < 31 && ((n ? n - 1 : 0) >> rb.shift) + 1 > RB_MAX) rb.shift++;
+    rb.count = (u32)(((n ? n - 1 : 0) >> rb.shift) + 1);
+    return rb;
+}
+
+// bucketed passes shared by the unweighted and the weighted build: partition the entries of the stored edge records
+// (node IDs in place unless `translate`) by row bucket, histogram (unless the tokenizer counted), row pointers, scatter
+template <class ENT>
+static int bucketed_rows(g2n_handle* h, const RowBuckets rb, u64 M, u64 n, int sym, int csc, bool translate, bool counted, const u32* emit_t0)
+{
+    typedef typename ENT::type EV;
+    CK(h->pair_major.ensure((M + 1) * sizeof(u32)));
+    CK(h->pair_ent.ensure((M + 1) * sizeof(EV)));
+    CK(h->bucket_ctl.ensure(sizeof(BucketCtl)));
+    CK(cudaMemsetAsync(h->bucket_ctl.p, 0, sizeof(BucketCtl), h->stream));
+    BucketCtl* ctl = h->bucket_ctl.as<BucketCtl>();
+    u32* es = h->edge_slots.as<u32>();
+    const u32 fgrid = grid_for((h->cap_E + EF_BATCH - 1) / EF_BATCH, 256);
+    const u32 sgrid = grid_for((h->cap_E + 511) / 512, 1, 8);  // a CTA round takes 512 - 1024 records (RbRecs)
+    const u32 pgrid = grid_for((M + 3) / 4, 256);
+    const u32* sid = translate ? h->slot_id.as<u32>() : nullptr;
+    {
+        KScope ks(h, "k_bucket_count");
+        switch (h->tpe) {
+            case 1: k_bucket_count<1><<<fgrid, 256, 0, h->stream>>>(es, sid, h->d_ds, sym, csc, rb, ctl); break;
+            case 2: k_bucket_count<2><<<fgrid, 256, 0, h->stream>>>(es, sid, h->d_ds, sym, csc, rb, ctl); break;
+            default: k_bucket_count<4><<<fgrid, 256, 0, h->stream>>>(es, sid, h->d_ds, sym, csc, rb, ctl); break;
+        }
+    }
+    h->edges_are_ids = true;
+    {
+        KScope ks(h, "k_bucket_scatter");
+        switch (h->tpe) {
+            case 1: k_bucket_scatter<1, ENT><<<sgrid, 256, 0, h->stream>>>(es, emit_t0, h->d_ds, sym, csc, rb, ctl, h->pair_major.as<u32>(), h->pair_ent.as<EV>()); break;
+            case 2: k_bucket_scatter<2, ENT><<<sgrid, 256, 0, h->stream>>>(es, emit_t0, h->d_ds, sym, csc, rb, ctl, h->pair_major.as<u32>(), h->pair_ent.as<EV>()); break;
+            default: k_bucket_scatter<4, ENT><<<sgrid, 256, 0, h->stream>>>(es, emit_t0, h->d_ds, sym, csc, rb, ctl, h->pair_major.as<u32>(), h->pair_ent.as<EV>()); break;
+        }
+    }
+    if (!counted) { KScope ks(h, "k_bucket_rows_count"); k_bucket_rows_count<<<pgrid, 256, 0, h->stream>>>(h->pair_major.as<u32>(), h->d_ds, ctl, rb.count, h->d_rowcnt); }
+    CK(cudaGetLastError());
+    int rc = rows_scan(h, n, &h->d_ds->rows);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev[EV_EMIT], h->stream));
+    { KScope ks(h, "k_bucket_rows_scatter"); k_bucket_rows_scatter<ENT><<<pgrid, 256, 0, h->stream>>>(h->pair_major.as<u32>(), h->pair_ent.as<EV>(), h->d_ds, ctl, rb.count, h->cursor.as<u32>(), h->entries.as<EV>()); }
+    CK(cudaGetLastError());
+    return G2N_OK;
 }
 
 // rowcnt -> rowptr + cursors; rows longer than RS_SMALL are listed on the way
@@ -423,6 +484,12 @@ int build_compressed(g2n_handle* h, int fmt, bool zeroed, bool counted)
         // the histogram (4 bytes per row) stays L2-resident by itself: one pass; the scatter below, whose entries do
         // not, runs once per row range
         const RowPasses rp = row_passes(M, sizeof(u32), n);
+        const bool bucketed = rp.count > 1 && !getenv("G2N_DBG_NOBUCKET");
+        if (bucketed) {
+            // row arrays far larger than L2: partition the entries by row bucket first (rowsort.cuh: RowBuckets)
+            rc = bucketed_rows<Ent32>(h, row_buckets(rp, n), M, n, sym, csc, !h->edges_are_ids, counted, nullptr);
+            if (rc) return rc;
+        } else {
         if (!counted) {  // (the tokenizer did not count the rows: table far larger than L2, or a later convert)
             const RowRange rr = ROW_RANGE_ALL;
             // IDs are in place already after an earlier convert of the same build
@@ -451,21 +518,27 @@ int build_compressed(g2n_handle* h, int fmt, bool zeroed, bool counted)
             h->edges_are_ids = true;
         }
         CK(cudaGetLastError());
+        }
     } else {
         const u32 egrid = grid_for((u64)h->n_tiles * 32, 256);
         const RowPasses rp = row_passes(M, sizeof(u64), n);
+        const bool bucketed = rp.count > 1 && !getenv("G2N_DBG_NOBUCKET");
         CK(h->emit_t0.ensure((h->cap_E + 1) * sizeof(u32)));
         {
             // leaves node IDs in edge_slots for the scatter passes (and later converts) and lays out the weights
             E.ids_ready = h->edges_are_ids ? 1 : 0;
             E.write_ids = E.ids_ready ? 0 : 1;
             KScope ks(h, "k_rows_count");
-            k_rows_count<<<egrid, 256, 0, h->stream>>>(E, sym, csc, counted ? nullptr : h->d_rowcnt, h->w_emit.as<double>(), ROW_RANGE_ALL, h->emit_t0.as<u32>());
+            k_rows_count<<<egrid, 256, 0, h->stream>>>(E, sym, csc, (counted || bucketed) ? nullptr : h->d_rowcnt, h->w_emit.as<double>(), ROW_RANGE_ALL, h->emit_t0.as<u32>());
         }
         CK(cudaGetLastError());
         h->edges_are_ids = true;
         E.ids_ready = 1;
         E.write_ids = 0;
+        if (bucketed) {
+            rc = bucketed_rows<Ent64>(h, row_buckets(rp, n), M, n, sym, csc, false, counted, h->emit_t0.as<u32>());
+            if (rc) return rc;
+        } else {
         rc = rows_scan(h, n, &h->d_ds->rows);
         if (rc) return rc;
         CK(cudaEventRecord(h->ev[EV_EMIT], h->stream));
@@ -481,6 +554,7 @@ int build_compressed(g2n_handle* h, int fmt, bool zeroed, bool counted)
             }
         }
         CK(cudaGetLastError());
+        }
     }
     CK(cudaEventRecord(h->ev[EV_SORT], h->stream));
     // one weight per edge record: the record's tpe triplets find it at (emission index) >> log2(tpe)
@@ -617,7 +691,7 @@ void g2n_destroy(g2n_handle* h)
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->text, &h->zearly, &h->zids, &h->zrows, &h->defer, &h->edge_slots, &h->edge_w, &h->longs, &h->tile_info, &h->tile_base, &h->wprefix,
                       &h->slot_id, &h->id2slot, &h->name_len, &h->name_off, &h->names, &h->rowptr, &h->cursor, &h->entries, &h->w_emit, &h->biglist, &h->ucnt, &h->indptr, &h->indices, &h->data, &h->row, &h->col,
-                      &h->scan_state, &h->up_row, &h->up_col, &h->up_data, &h->tsv, &h->tsv_off, &h->el_len, &h->el_off, &h->el_text, &h->emit_t0, &h->bfs_levels, &h->bfs_q0, &h->bfs_q1, &h->bfs_ctl, &h->bfs_nodes, &h->bfs_out, &h->path_starts, &h->path_recs, &h->path_cnt, &h->path_off, &h->path_ids, &h->path_misc, &h->dx_arena, &h->dx_ctl, &h->dx_loc, &h->dx_zg, &h->dx_gslot, &h->dx_gpos, &h->dx_sent, &h->dx_tcnt, &h->dx_toff};
+                      &h->scan_state, &h->up_row, &h->up_col, &h->up_data, &h->tsv, &h->tsv_off, &h->el_len, &h->el_off, &h->el_text, &h->emit_t0, &h->bfs_levels, &h->bfs_q0, &h->bfs_q1, &h->bfs_ctl, &h->bfs_nodes, &h->bfs_out, &h->path_starts, &h->path_recs, &h->path_cnt, &h->path_off, &h->path_ids, &h->path_misc, &h->dx_arena, &h->dx_ctl, &h->dx_loc, &h->dx_zg, &h->dx_gslot, &h->dx_gpos, &h->dx_sent, &h->dx_tcnt, &h->dx_toff, &h->pair_major, &h->pair_ent, &h->bucket_ctl};
     if (h->dx_inited) g2n_dist_close_peers(h);
     for (DevBuf* b : bufs) b->release();
     if (h->h_loc) cudaFreeHost(h->h_loc);
@@ -2281,6 +2355,34 @@ int g2n_dist_stage(g2n_handle* h, int stage, const uint8_t* text, uint64_t nbyte
         h->result_format = csc ? G2N_FMT_CSC : G2N_FMT_CSR;
         const u32 pgrid = grid_for(recv_cap + 1, 256, 8);
         const RowPasses rp = row_passes(recv_cap, weighted ? sizeof(u64) : sizeof(u32), rows_cap);
+        if (rp.count > 1 && !getenv("G2N_DBG_NOBUCKET")) {
+            // slab far larger than L2: partition the received entries by row bucket, then stream (dist.cuh / rowsort.cuh)
+            const RowBuckets rb = row_buckets(rp, rows_cap);
+            CK(h->pair_major.ensure((recv_cap + 1) * sizeof(u32)));
+            CK(h->pair_ent.ensure((recv_cap + 1) * (weighted ? sizeof(u64) : sizeof(u32))));
+            CK(h->bucket_ctl.ensure(sizeof(BucketCtl)));
+            CK(cudaMemsetAsync(h->bucket_ctl.p, 0, sizeof(BucketCtl), h->stream));
+            BucketCtl* ctl = h->bucket_ctl.as<BucketCtl>();
+            const u32 sgrid = grid_for((recv_cap + RB_ROUND) / RB_ROUND, 1, 8);
+            const u32 bgrid = grid_for((recv_cap + 3) / 4 + 1, 256);
+            if (weighted) {
+                { KScope ks(h, "k_pairs_bucket_count"); k_pairs_bucket_count<DistPairW><<<pgrid, 256, 0, h->stream>>>(X, L, loc, h->d_ds, rb, ctl, &loc->bad); }
+                { KScope ks(h, "k_pairs_bucket_scatter"); k_pairs_bucket_scatter<DistPairW, Ent64><<<sgrid, 256, 0, h->stream>>>(X, L, loc, h->d_ds, rb, ctl, h->pair_major.as<u32>(), h->pair_ent.as<u64>(), h->w_emit.as<double>()); }
+            } else {
+                { KScope ks(h, "k_pairs_bucket_count"); k_pairs_bucket_count<DistPair><<<pgrid, 256, 0, h->stream>>>(X, L, loc, h->d_ds, rb, ctl, &loc->bad); }
+                { KScope ks(h, "k_pairs_bucket_scatter"); k_pairs_bucket_scatter<DistPair, Ent32><<<sgrid, 256, 0, h->stream>>>(X, L, loc, h->d_ds, rb, ctl, h->pair_major.as<u32>(), h->pair_ent.as<u32>(), nullptr); }
+            }
+            { KScope ks(h, "k_bucket_rows_count"); k_bucket_rows_count<<<bgrid, 256, 0, h->stream>>>(h->pair_major.as<u32>(), h->d_ds, ctl, rb.count, h->d_rowcnt); }
+            CK(cudaGetLastError());
+            int rc = rows_scan(h, rows_cap, &h->d_ds->rows);
+            if (rc) return rc;
+            if (weighted) { KScope ks(h, "k_bucket_rows_scatter"); k_bucket_rows_scatter<Ent64><<<bgrid, 256, 0, h->stream>>>(h->pair_major.as<u32>(), h->pair_ent.as<u64>(), h->d_ds, ctl, rb.count, h->cursor.as<u32>(), h->entries.as<u64>()); }
+            else { KScope ks(h, "k_bucket_rows_scatter"); k_bucket_rows_scatter<Ent32><<<bgrid, 256, 0, h->stream>>>(h->pair_major.as<u32>(), h->pair_ent.as<u32>(), h->d_ds, ctl, rb.count, h->cursor.as<u32>(), h->entries.as<u32>()); }
+            CK(cudaGetLastError());
+            rc = rows_finalize(h, h->params.dtype, weighted, recv_cap, rows_cap, sym, WEmit{weighted ? h->w_emit.as<double>() : nullptr, 0u}, nullptr);
+            if (rc) return rc;
+            break;
+        }
         {
             const RowRange rr = ROW_RANGE_ALL;
             if (weighted) { KScope ks(h, "k_pairsw_count"); k_pairsw_count<<<pgrid, 256, 0, h->stream>>>(X, L, loc, h->d_ds, h->d_rowcnt, &loc->bad, rr); }

@@ -262,6 +262,249 @@ __global__ void __launch_bounds__(256) k_rows_scatter_flat(const u32* __restrict
     }
 }
 
+// ---------------------------------------------------------------- row arrays far larger than L2: bucketed build
+// The histogram and the scatter above touch a random row per entry.  Once rowcnt + cursors + entries are hundreds of
+// megabytes every such access is a DRAM sector of its own (tools/ubench/randmem.cu: atomics on a working set >> L2 run
+// at 20 - 30 G/s against 190 G/s inside L2); a pass per row range keeps them in L2 but re-reads and re-filters all edge
+// records once per range.  Instead the entries are first PARTITIONED by row bucket (rows >> shift, <= RB_MAX buckets
+// sized to stay L2-resident) into a bucket-major pair list -- sequential reads, writes that fill each bucket's frontier
+// in pieces reserved per CTA round -- and the histogram / scatter passes then stream over that list: at any moment
+// the grid works inside one or two buckets, so their random accesses hit L2.
+//   k_bucket_count        flat over the edge records: slots -> IDs in place, entries per bucket (shared-memory histogram)
+//   k_bucket_scatter      flat again: (major, entry) -> its bucket's range, one global atomic per bucket and CTA round
+//   k_bucket_rows_count   flat over the pair list: cnt[major]++        (skipped when the tokenizer counted the rows)
+//   k_bucket_rows_scatter flat over the pair list: entries[cursor[major]++] = entry
+#define RB_MAX 64
+struct RowBuckets {
+    u32 shift, count;  // bucket of a row = min(row >> shift, count - 1)
+    __device__ __forceinline__ u32 of(u32 major) const
+    {
+        const u32 b = major >> shift;
+        return b < count ? b : count - 1;
+    }
+};
+struct BucketCtl {  // zeroed before k_bucket_count
+    u32 cnt[RB_MAX];  // entries per bucket
+    u32 cur[RB_MAX];  // entries placed so far (k_bucket_scatter)
+};
+
+// the entries of one record with a compile-time index each (max(S, S^T) only exists for one-triplet records: symmax
+// implies graph_directed, g2n.cu tokenize_phase), so that per-entry state stays in registers
+template <int TPE, class G>
+__device__ __forceinline__ void rb_entries(const u32 (&id)[4], u32 t0, int sym, int csc, G g)
+{
+#pragma unroll
+    for (int k = 0; k < TPE; k++) {
+        const u32 a = id[k & 2], b = id[(k & 2) + 1];
+        const u32 r = (k & 1) ? b : a, c = (k & 1) ? a : b;
+        if (TPE == 1 && sym) { g(0, r, c, 0u, t0); g(1, c, r, 1u, t0); }
+        else if (csc) g(k, c, r, 0u, t0 + k);
+        else g(k, r, c, 0u, t0 + k);
+    }
+}
+
+template <int SPE>
+__device__ __forceinline__ void rb_load(const u32* __restrict__ recs, u32 e, u32 (&id)[4])
+{
+    if (SPE == 4) {
+        const uint4 q = reinterpret_cast<const uint4*>(recs)[e];
+        id[0] = q.x; id[1] = q.y; id[2] = q.z; id[3] = q.w;
+    } else {
+        const uint2 q = reinterpret_cast<const uint2*>(recs)[e];
+        id[0] = q.x; id[1] = q.y; id[2] = 0; id[3] = 0;
+    }
+}
+
+template <int TPE>
+__global__ void __launch_bounds__(256) k_bucket_count(u32* __restrict__ edge_slots, const u32* __restrict__ slot_id, const DevSizes* __restrict__ ds,
+                                                       int sym, int csc, const RowBuckets rb, BucketCtl* __restrict__ ctl)
+{
+    constexpr int SPE = TPE == 4 ? 4 : 2;
+    __shared__ u32 s_cnt[8][RB_MAX];  // one histogram per warp: less contention on the shared-memory atomics
+    for (u32 i = threadIdx.x; i < 8 * RB_MAX; i += 256) (&s_cnt[0][0])[i] = 0;
+    __syncthreads();
+    if (!ds->ok) return;
+    const u32 E = ds->E, wid = threadIdx.x >> 5;
+    const u32 stride = gridDim.x * blockDim.x;
+    for (u32 e0 = blockIdx.x * blockDim.x + threadIdx.x; e0 < E; e0 += stride * EF_BATCH) {
+        u32 id[EF_BATCH][4];
+#pragma unroll
+        for (int u = 0; u < EF_BATCH; u++) {
+            id[u][0] = id[u][1] = id[u][2] = id[u][3] = 0;
+            if (e0 + u * stride < E) rb_load<SPE>(edge_slots, e0 + u * stride, id[u]);
+        }
+        if (slot_id) {  // table slots -> node IDs, left in place for the later passes
+#pragma unroll
+            for (int u = 0; u < EF_BATCH; u++) {
+                if (e0 + u * stride < E) {
+#pragma unroll
+                    for (int k = 0; k < SPE; k++) id[u][k] = slot_id[id[u][k]];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < EF_BATCH; u++) {
+                const u32 e = e0 + u * stride;
+                if (e < E) {
+                    if (SPE == 4) reinterpret_cast<uint4*>(edge_slots)[e] = make_uint4(id[u][0], id[u][1], id[u][2], id[u][3]);
+                    else reinterpret_cast<uint2*>(edge_slots)[e] = make_uint2(id[u][0], id[u][1]);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < EF_BATCH; u++) {
+            if (e0 + u * stride < E)
+                rb_entries<TPE>(id[u], 0u, sym, csc, [&](int, u32 major, u32, u32, u32) { atomicAdd(&s_cnt[wid][rb.of(major)], 1u); });
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < rb.count) {
+        u32 c = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) c += s_cnt[w][threadIdx.x];
+        if (c) atomicAdd(&ctl->cnt[threadIdx.x], c);
+    }
+}
+
+// ENT = Ent32 (unweighted: emit_t0 == NULL) | Ent64 (weighted: the record's first emission index comes from emit_t0)
+// A CTA round takes 256 x RB_RECS<TPE> records = at most RB_ROUND entries: they are grouped by bucket in shared memory
+// (rank inside the round from a shared-memory atomic, group offsets from a 64-element prefix), the round's range in
+// every bucket is reserved with one global atomic, and consecutive threads then copy consecutive staged elements -- the
+// bucket frontiers receive whole runs instead of one 4-byte store per lane (uncoalesced stores ran the partition at
+// 0.5 TB/s with 32 buckets, profiles/r3_buckets.md).
+#define RB_ROUND 2048
+template <int TPE> struct RbRecs { static constexpr int value = TPE == 4 ? 2 : 4; };  // records per thread and round
+template <int TPE, class ENT>
+__global__ void __launch_bounds__(256) k_bucket_scatter(const u32* __restrict__ edge_ids, const u32* __restrict__ emit_t0, const DevSizes* __restrict__ ds,
+                                                         int sym, int csc, const RowBuckets rb, BucketCtl* __restrict__ ctl,
+                                                         u32* __restrict__ pair_major, typename ENT::type* __restrict__ pair_ent)
+{
+    typedef typename ENT::type EV;
+    constexpr int SPE = TPE == 4 ? 4 : 2;
+    constexpr int EPR = TPE == 1 ? 2 : TPE;  // entries of one record at most (TPE == 1: two when sym)
+    constexpr int RECS = RbRecs<TPE>::value;
+    static_assert(256 * RECS * EPR <= RB_ROUND, "round size");
+    __shared__ u32 s_off[RB_MAX], s_cnt[RB_MAX], s_lo[RB_MAX + 1], s_base[RB_MAX];
+    __shared__ u32 s_major[RB_ROUND];
+    __shared__ EV s_ent[RB_ROUND];
+    if (!ds->ok) return;
+    if (threadIdx.x == 0) {
+        u32 run = 0;
+        for (u32 b = 0; b < rb.count; b++) { s_off[b] = run; run += ctl->cnt[b]; }
+    }
+    const u32 E = ds->E, M = ds->M;
+    const u32 per_round = 256 * RECS;
+    for (u64 r0 = (u64)blockIdx.x * per_round; r0 < E; r0 += (u64)gridDim.x * per_round) {  // uniform per CTA
+        if (threadIdx.x < RB_MAX) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        u32 id[RECS][4], t0[RECS];
+        unsigned short rk[RECS][EPR];  // rank of my entries among the round's entries of the same bucket
+#pragma unroll
+        for (int u = 0; u < RECS; u++) {
+            const u64 e = r0 + u * 256 + threadIdx.x;
+            id[u][0] = id[u][1] = id[u][2] = id[u][3] = 0;
+            t0[u] = 0;
+            if (e < E) {
+                rb_load<SPE>(edge_ids, (u32)e, id[u]);
+                if (ENT::kWeighted) t0[u] = emit_t0[e];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < RECS; u++) {
+            if (r0 + u * 256 + threadIdx.x < E)
+                rb_entries<TPE>(id[u], 0u, sym, csc, [&](int q, u32 major, u32, u32, u32) { rk[u][q] = (unsigned short)atomicAdd(&s_cnt[rb.of(major)], 1u); });
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            u32 run = 0;
+            for (u32 b = 0; b < rb.count; b++) { s_lo[b] = run; run += s_cnt[b]; }
+            s_lo[rb.count] = run;
+        }
+        if (threadIdx.x < rb.count) {
+            const u32 c = s_cnt[threadIdx.x];
+            s_base[threadIdx.x] = s_off[threadIdx.x] + (c ? atomicAdd(&ctl->cur[threadIdx.x], c) : 0u);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < RECS; u++) {
+            if (r0 + u * 256 + threadIdx.x < E)
+                rb_entries<TPE>(id[u], t0[u], sym, csc, [&](int q, u32 major, u32 minor, u32 dir, u32 t) {
+                    const u32 p = s_lo[rb.of(major)] + rk[u][q];
+                    s_major[p] = major;
+                    s_ent[p] = ENT::make(minor, dir, t);
+                });
+        }
+        __syncthreads();
+        const u32 total = s_lo[rb.count];
+        for (u32 p = threadIdx.x; p < total; p += 256) {
+            const u32 major = s_major[p];
+            const u32 b = rb.of(major);
+            const u32 pos = s_base[b] + (p - s_lo[b]);
+            G2N_CHECK(pos < M);
+            if (pos < M) {
+                pair_major[pos] = major;
+                pair_ent[pos] = s_ent[p];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// entries in the pair list = sum of the bucket counters (= DevSizes.M on one GPU; a multi-GPU slab may have dropped
+// entries of a failed exchange)
+__device__ __forceinline__ u64 rb_total(const BucketCtl* ctl, u32 nb)
+{
+    __shared__ u64 s_total;
+    if (threadIdx.x == 0) {
+        u64 t = 0;
+        for (u32 b = 0; b < nb; b++) t += ctl->cnt[b];
+        s_total = t;
+    }
+    __syncthreads();
+    return s_total;
+}
+
+__global__ void __launch_bounds__(256) k_bucket_rows_count(const u32* __restrict__ pair_major, const DevSizes* __restrict__ ds, const BucketCtl* __restrict__ ctl, u32 nb,
+                                                            u32* __restrict__ cnt)
+{
+    if (!ds->ok) return;
+    const u64 M = rb_total(ctl, nb), stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i0 = (u64)blockIdx.x * blockDim.x + threadIdx.x; i0 < M; i0 += stride * 4) {
+        u32 m[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) m[u] = i0 + u * stride < M ? pair_major[i0 + u * stride] : 0xFFFFFFFFu;
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (m[u] != 0xFFFFFFFFu) { G2N_CHECK(m[u] < ds->rows); atomicAdd(&cnt[m[u]], 1u); }
+    }
+}
+
+template <class ENT>
+__global__ void __launch_bounds__(256) k_bucket_rows_scatter(const u32* __restrict__ pair_major, const typename ENT::type* __restrict__ pair_ent,
+                                                              const DevSizes* __restrict__ ds, const BucketCtl* __restrict__ ctl, u32 nb,
+                                                              u32* __restrict__ cursor, typename ENT::type* __restrict__ entries)
+{
+    if (!ds->ok) return;
+    const u64 M = rb_total(ctl, nb), stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i0 = (u64)blockIdx.x * blockDim.x + threadIdx.x; i0 < M; i0 += stride * 4) {
+        u32 m[4];
+        typename ENT::type v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const bool in = i0 + u * stride < M;
+            m[u] = in ? pair_major[i0 + u * stride] : 0xFFFFFFFFu;
+            v[u] = in ? pair_ent[i0 + u * stride] : (typename ENT::type)0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (m[u] != 0xFFFFFFFFu) {
+                const u32 pos = atomicAdd(&cursor[m[u]], 1u);
+                G2N_CHECK(m[u] < ds->rows && pos < M);
+                entries[pos] = v[u];
+            }
+        }
+    }
+}
+
 // same two steps for caller-provided COO arrays (g2n_coo_to_compressed)
 __global__ void __launch_bounds__(256) k_coo_count(const int32_t* __restrict__ row, const int32_t* __restrict__ col, u64 nnz, int csc, u32* __restrict__ cnt)
 {

@@ -242,10 +242,14 @@ def test_conditional_first_appearance_variant(monkeypatch):
         assert nodes == onodes
 
 
+@pytest.mark.parametrize("bucketed", [True, False], ids=["buckets", "row-range-passes"])
 @pytest.mark.parametrize("passes", ["3", "64"])
-def test_row_range_passes_variant(monkeypatch, passes):
-    """The bucketing kernels run once per slice of rows when the row arrays are far larger than L2 (rowsort.cuh:
-    RowRange); forced on small inputs: same results in every mode, on repeated (speculative) builds and after a convert."""
+def test_row_range_passes_variant(monkeypatch, passes, bucketed):
+    """Row arrays far larger than L2: the entries are partitioned by row bucket before the histogram / scatter passes
+    (rowsort.cuh: RowBuckets) -- or, G2N_DBG_NOBUCKET, the bucketing kernels run once per slice of rows (RowRange).
+    Forced on small inputs: same results in every mode, on repeated (speculative) builds and after a convert."""
+    if not bucketed:
+        monkeypatch.setenv("G2N_DBG_NOBUCKET", "1")
     from gfa2network_b200 import convert_format, parse_gfa
     from gfa2network_b200.synth import synth_gfa
     from oracle.oracle import oracle_convert_format, oracle_parse_gfa
