@@ -797,7 +797,7 @@ __global__ void __launch_bounds__(256) k_pairs_bucket_scatter(const DxPeers X, c
 {
     typedef typename ENT::type EV;
     constexpr int PER = RB_ROUND / 256;
-    __shared__ u32 s_off[RB_MAX], s_cnt[RB_MAX], s_lo[RB_MAX + 1], s_base[RB_MAX];
+    __shared__ u32 s_off[RB_MAX], s_cnt[RB_MAX], s_lo[RB_MAX + 1], s_base[RB_MAX], s_ws[8];
     __shared__ u32 s_major[RB_ROUND];
     __shared__ EV s_ent[RB_ROUND];
     __shared__ DxFlat F;
@@ -835,12 +835,7 @@ __global__ void __launch_bounds__(256) k_pairs_bucket_scatter(const DxPeers X, c
 #pragma unroll
         for (int u = 0; u < PER; u++)
             if (row[u] != 0xFFFFFFFFu) rk[u] = (unsigned short)atomicAdd(&s_cnt[rb.of(row[u])], 1u);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            u32 run = 0;
-            for (u32 b = 0; b < rb.count; b++) { s_lo[b] = run; run += s_cnt[b]; }
-            s_lo[rb.count] = run;
-        }
+        rb_prefix256(s_cnt, rb.count, s_lo, s_ws);
         if (threadIdx.x < rb.count) {
             const u32 c = s_cnt[threadIdx.x];
             s_base[threadIdx.x] = s_off[threadIdx.x] + (c ? atomicAdd(&ctl->cur[threadIdx.x], c) : 0u);

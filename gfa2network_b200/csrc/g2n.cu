@@ -77,7 +77,8 @@ struct g2n_handle {
     DevBuf text, defer, edge_slots, edge_w, longs, tile_info, tile_base, wprefix, slot_id, id2slot, name_len, name_off, names;
     DevBuf rowptr, cursor, entries, w_emit, biglist, ucnt, indptr, indices, data, row, col, scan_state;
     DevBuf up_row, up_col, up_data, tsv, tsv_off, el_len, el_off, el_text, emit_t0;
-    DevBuf pair_major, pair_ent, bucket_ctl;  // bucketed row build (rowsort.cuh: RowBuckets)
+    DevBuf pair_major, pair_ent, bucket_ctl, pair2_major, pair2_ent, sub_ctl, sub_off;  // bucketed row build (rowsort.cuh: RowBuckets, SubBuckets)
+    u32 place_attr = 0;  // k_sub_rows_place instantiations whose dynamic shared memory opt-in was set on this device
     DevBuf bfs_levels, bfs_q0, bfs_q1, bfs_ctl, bfs_nodes, bfs_out;  // distances on the resident CSR (bfs.cuh)
     int bfs_slots = 0;
     u64 bfs_n = 0;
@@ -335,6 +336,7 @@ int rows_finalize(g2n_handle* h, int dtype, bool weighted, u64 M, u64 n, int sym
 // cursors) is near the L2 size, else one per slice of rows that is.  G2N_DBG_ROWPASS forces a count (tests).
 struct RowPasses {
     u32 count, width;
+    bool bucketed;  // partition the entries by row bucket first (rowsort.cuh: RowBuckets) instead of one pass per row range
     RowRange at(u32 p, u64 n) const
     {
         RowRange r;
@@ -347,16 +349,20 @@ struct RowPasses {
 static const RowRange ROW_RANGE_ALL = {0u, 0xFFFFFFFFu};
 static RowPasses row_passes(u64 M, size_t ent_bytes, u64 n)
 {
-    // one pass / no buckets up to 96 MB of row arrays (C2: one); beyond that buckets of about 32 MB each (C4d: 32 buckets
-    // 13.8 ms against 15.2 ms with 8, profiles/r3_buckets.md; more than 32 changes nothing)
+    // Row arrays up to 96 MB: one pass (C2).  Up to 384 MB: one pass per 96 MB slice of rows (C5 shape at 5 %: three
+    // passes 1.00 ms, buckets 1.01 ms).  Beyond: buckets of about 32 MB (C4d, 800 MB: 8 passes 5.84 ms, 39 buckets 4.04 ms;
+    // C3, 1.1 GB: 7.0 -> 5.1 ms; more than 32 buckets changes nothing -- profiles/r3_buckets.md).
     const u64 bytes = M * ent_bytes + n * 8;
-    const u64 budget = (bytes <= (96ull << 20) || getenv("G2N_DBG_NOBUCKET")) ? 96ull << 20 : 32ull << 20;
+    const bool forced = getenv("G2N_DBG_ROWPASS") != nullptr;
+    const bool bucketed = (forced || bytes > (384ull << 20)) && !getenv("G2N_DBG_NOBUCKET");
+    const u64 budget = bucketed ? 32ull << 20 : 96ull << 20;
     u64 R = (bytes + budget - 1) / budget;
     if (const char* e = getenv("G2N_DBG_ROWPASS")) R = (u64)atoll(e);
     if (R < 1) R = 1;
     if (R > 64) R = 64;
     if (R > n) R = n ? n : 1;
     RowPasses rp;
+    rp.bucketed = bucketed && R > 1;
     rp.count = (u32)R;
     rp.width = (u32)((n + R - 1) / R);
     if (rp.width == 0) rp.width = 1;
@@ -377,12 +383,101 @@ static RowBuckets row_buckets(const RowPasses& rp, u64 n)
     return rb;
 }
 
-// bucketed passes shared by the unweighted and the weighted build: partition the entries of the stored edge records
-// (node IDs in place unless `translate`) by row bucket, histogram (unless the tokenizer counted), row pointers, scatter
+// Both levels of the partitioned build (rowsort.cuh).  Sub-buckets: a power-of-two number of rows with about half the
+// shared-memory capacity in entries on average; buckets: at most SB_FAN sub-buckets each, at most RB_MAX buckets.
+struct BucketPlan {
+    RowBuckets rb;
+    SubBuckets sb;
+    bool two_level;
+    u32 smem_entries;  // staged entries the placement kernel's shared memory is sized for
+};
+static BucketPlan plan_buckets(const RowPasses& rp, u64 M, u64 n, size_t ent_bytes)
+{
+    BucketPlan P;
+    memset(&P, 0, sizeof(P));
+    P.rb = row_buckets(rp, n);
+    if (getenv("G2N_DBG_NOSUB")) return P;
+    const u32 nominal = ent_bytes == 8 ? 12288u : 16384u;  // 96 KB / 64 KB of staged entries + 16 KB of cursors
+    const double avg = (n && M > n) ? (double)M / (double)n : 1.0;
+    u32 shift2 = 0;
+    while (shift2 < 12 && (double)(2u << shift2) * avg <= nominal / 2) shift2++;
+    u32 shift1 = P.rb.shift;
+    if (shift1 < shift2) shift2 = shift1;  // small inputs (forced in tests): one sub-bucket per bucket
+    if (shift1 - shift2 > 8) shift1 = shift2 + 8;
+    const u64 last = n ? n - 1 : 0;
+    while ((last >> shift1) + 1 > RB_MAX) {
+        shift1++;
+        if (shift1 - shift2 > 8) shift2++;
+    }
+    if (shift2 > 12) return P;  // more than SB_ROWS_MAX rows per sub-bucket: one level only
+    P.rb.shift = shift1;
+    P.rb.count = (u32)((last >> shift1) + 1);
+    P.sb.shift2 = shift2;
+    P.sb.fan_shift = shift1 - shift2;
+    P.sb.n_sub = P.rb.count << P.sb.fan_shift;
+    P.sb.cap = nominal;
+    if (const char* e = getenv("G2N_DBG_SUBCAP")) { const u32 v = (u32)atoll(e); if (v < nominal) P.sb.cap = v; }  // tests: force the fallback
+    P.smem_entries = nominal;
+    P.two_level = true;
+    return P;
+}
+
+// From the bucket-major pair list (pair_major / pair_ent, counts in bucket_ctl) to rowptr + entries grouped by row.
+// `M` and `n` are host-side capacities; `counted`: d_rowcnt already holds the row histogram.
 template <class ENT>
-static int bucketed_rows(g2n_handle* h, const RowBuckets rb, u64 M, u64 n, int sym, int csc, bool translate, bool counted, const u32* emit_t0)
+static int bucketed_tail(g2n_handle* h, const BucketPlan& P, u64 M, u64 n, bool counted)
 {
     typedef typename ENT::type EV;
+    BucketCtl* ctl = h->bucket_ctl.as<BucketCtl>();
+    const u32 pgrid = grid_for((M + 3) / 4, 256);
+    if (!P.two_level) {
+        if (!counted) { KScope ks(h, "k_bucket_rows_count"); k_bucket_rows_count<<<pgrid, 256, 0, h->stream>>>(h->pair_major.as<u32>(), h->d_ds, ctl, P.rb.count, h->d_rowcnt); }
+        CK(cudaGetLastError());
+        int rc = rows_scan(h, n, &h->d_ds->rows);
+        if (rc) return rc;
+        CK(cudaEventRecord(h->ev[EV_EMIT], h->stream));
+        { KScope ks(h, "k_bucket_rows_scatter"); k_bucket_rows_scatter<ENT><<<pgrid, 256, 0, h->stream>>>(h->pair_major.as<u32>(), h->pair_ent.as<EV>(), h->d_ds, ctl, P.rb.count, h->cursor.as<u32>(), h->entries.as<EV>()); }
+        CK(cudaGetLastError());
+        return G2N_OK;
+    }
+    const SubBuckets sb = P.sb;
+    CK(h->pair2_major.ensure((M + 1) * sizeof(u32)));
+    CK(h->pair2_ent.ensure((M + 1) * sizeof(EV)));
+    CK(h->sub_ctl.ensure(2 * (size_t)sb.n_sub * sizeof(u32)));
+    CK(h->sub_off.ensure(((size_t)sb.n_sub + 2) * sizeof(u32)));
+    CK(cudaMemsetAsync(h->sub_ctl.p, 0, 2 * (size_t)sb.n_sub * sizeof(u32), h->stream));
+    u32* sub_cnt = h->sub_ctl.as<u32>();
+    u32* sub_cur = sub_cnt + sb.n_sub;
+    { KScope ks(h, "k_sub_count"); k_sub_count<<<grid_for((M + SB_CHUNK - 1) / SB_CHUNK, 1, 8), 256, 0, h->stream>>>(h->pair_major.as<u32>(), h->d_ds, ctl, P.rb, sb, sub_cnt); }
+    CK(cudaGetLastError());
+    LoadArray<u32> lsc{sub_cnt};
+    int rc = launch_scan<u32>(h, lsc, h->sub_off.as<u32>(), nullptr, sb.n_sub, nullptr, nullptr);
+    if (rc) return rc;
+    { KScope ks(h, "k_sub_scatter"); k_sub_scatter<ENT><<<grid_for((M + RB_ROUND - 1) / RB_ROUND, 1, 8), 256, 0, h->stream>>>(h->pair_major.as<u32>(), h->pair_ent.as<EV>(), h->d_ds, ctl, P.rb, sb, h->sub_off.as<u32>(), sub_cur, h->pair2_major.as<u32>(), h->pair2_ent.as<EV>()); }
+    const u32 cgrid = grid_for(sb.n_sub, 1, 8);
+    if (!counted) { KScope ks(h, "k_sub_rows_count"); k_sub_rows_count<<<cgrid, 256, 0, h->stream>>>(h->pair2_major.as<u32>(), h->d_ds, sb, h->sub_off.as<u32>(), h->d_rowcnt); }
+    CK(cudaGetLastError());
+    rc = rows_scan(h, n, &h->d_ds->rows);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev[EV_EMIT], h->stream));
+    const size_t smem = SB_ROWS_MAX * sizeof(u32) + (size_t)P.smem_entries * sizeof(EV);
+    const u32 bit = sizeof(EV) == 8 ? 2u : 1u;
+    if (!(h->place_attr & bit)) {
+        CK(cudaFuncSetAttribute(k_sub_rows_place<ENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        h->place_attr |= bit;
+    }
+    { KScope ks(h, "k_sub_rows_place"); k_sub_rows_place<ENT><<<grid_for(sb.n_sub, 1, 2), SB_PT, smem, h->stream>>>(h->pair2_major.as<u32>(), h->pair2_ent.as<EV>(), h->d_ds, sb, h->sub_off.as<u32>(), h->rowptr.as<u32>(), h->cursor.as<u32>(), h->entries.as<EV>()); }
+    CK(cudaGetLastError());
+    return G2N_OK;
+}
+
+// bucketed passes shared by the unweighted and the weighted build: partition the entries of the stored edge records
+// (node IDs in place unless `translate`) by row bucket, then bucketed_tail()
+template <class ENT>
+static int bucketed_rows(g2n_handle* h, const BucketPlan& P, u64 M, u64 n, int sym, int csc, bool translate, bool counted, const u32* emit_t0)
+{
+    typedef typename ENT::type EV;
+    const RowBuckets rb = P.rb;
     CK(h->pair_major.ensure((M + 1) * sizeof(u32)));
     CK(h->pair_ent.ensure((M + 1) * sizeof(EV)));
     CK(h->bucket_ctl.ensure(sizeof(BucketCtl)));
@@ -391,7 +486,6 @@ static int bucketed_rows(g2n_handle* h, const RowBuckets rb, u64 M, u64 n, int s
     u32* es = h->edge_slots.as<u32>();
     const u32 fgrid = grid_for((h->cap_E + EF_BATCH - 1) / EF_BATCH, 256);
     const u32 sgrid = grid_for((h->cap_E + 511) / 512, 1, 8);  // a CTA round takes 512 - 1024 records (RbRecs)
-    const u32 pgrid = grid_for((M + 3) / 4, 256);
     const u32* sid = translate ? h->slot_id.as<u32>() : nullptr;
     {
         KScope ks(h, "k_bucket_count");
@@ -410,14 +504,8 @@ static int bucketed_rows(g2n_handle* h, const RowBuckets rb, u64 M, u64 n, int s
             default: k_bucket_scatter<4, ENT><<<sgrid, 256, 0, h->stream>>>(es, emit_t0, h->d_ds, sym, csc, rb, ctl, h->pair_major.as<u32>(), h->pair_ent.as<EV>()); break;
         }
     }
-    if (!counted) { KScope ks(h, "k_bucket_rows_count"); k_bucket_rows_count<<<pgrid, 256, 0, h->stream>>>(h->pair_major.as<u32>(), h->d_ds, ctl, rb.count, h->d_rowcnt); }
     CK(cudaGetLastError());
-    int rc = rows_scan(h, n, &h->d_ds->rows);
-    if (rc) return rc;
-    CK(cudaEventRecord(h->ev[EV_EMIT], h->stream));
-    { KScope ks(h, "k_bucket_rows_scatter"); k_bucket_rows_scatter<ENT><<<pgrid, 256, 0, h->stream>>>(h->pair_major.as<u32>(), h->pair_ent.as<EV>(), h->d_ds, ctl, rb.count, h->cursor.as<u32>(), h->entries.as<EV>()); }
-    CK(cudaGetLastError());
-    return G2N_OK;
+    return bucketed_tail<ENT>(h, P, M, n, counted);
 }
 
 // rowcnt -> rowptr + cursors; rows longer than RS_SMALL are listed on the way
@@ -484,10 +572,10 @@ int build_compressed(g2n_handle* h, int fmt, bool zeroed, bool counted)
         // the histogram (4 bytes per row) stays L2-resident by itself: one pass; the scatter below, whose entries do
         // not, runs once per row range
         const RowPasses rp = row_passes(M, sizeof(u32), n);
-        const bool bucketed = rp.count > 1 && !getenv("G2N_DBG_NOBUCKET");
+        const bool bucketed = rp.bucketed;
         if (bucketed) {
             // row arrays far larger than L2: partition the entries by row bucket first (rowsort.cuh: RowBuckets)
-            rc = bucketed_rows<Ent32>(h, row_buckets(rp, n), M, n, sym, csc, !h->edges_are_ids, counted, nullptr);
+            rc = bucketed_rows<Ent32>(h, plan_buckets(rp, M, n, sizeof(u32)), M, n, sym, csc, !h->edges_are_ids, counted, nullptr);
             if (rc) return rc;
         } else {
         if (!counted) {  // (the tokenizer did not count the rows: table far larger than L2, or a later convert)
@@ -522,7 +610,7 @@ int build_compressed(g2n_handle* h, int fmt, bool zeroed, bool counted)
     } else {
         const u32 egrid = grid_for((u64)h->n_tiles * 32, 256);
         const RowPasses rp = row_passes(M, sizeof(u64), n);
-        const bool bucketed = rp.count > 1 && !getenv("G2N_DBG_NOBUCKET");
+        const bool bucketed = rp.bucketed;
         CK(h->emit_t0.ensure((h->cap_E + 1) * sizeof(u32)));
         {
             // leaves node IDs in edge_slots for the scatter passes (and later converts) and lays out the weights
@@ -536,7 +624,7 @@ int build_compressed(g2n_handle* h, int fmt, bool zeroed, bool counted)
         E.ids_ready = 1;
         E.write_ids = 0;
         if (bucketed) {
-            rc = bucketed_rows<Ent64>(h, row_buckets(rp, n), M, n, sym, csc, false, counted, h->emit_t0.as<u32>());
+            rc = bucketed_rows<Ent64>(h, plan_buckets(rp, M, n, sizeof(u64)), M, n, sym, csc, false, counted, h->emit_t0.as<u32>());
             if (rc) return rc;
         } else {
         rc = rows_scan(h, n, &h->d_ds->rows);
@@ -691,7 +779,7 @@ void g2n_destroy(g2n_handle* h)
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->text, &h->zearly, &h->zids, &h->zrows, &h->defer, &h->edge_slots, &h->edge_w, &h->longs, &h->tile_info, &h->tile_base, &h->wprefix,
                       &h->slot_id, &h->id2slot, &h->name_len, &h->name_off, &h->names, &h->rowptr, &h->cursor, &h->entries, &h->w_emit, &h->biglist, &h->ucnt, &h->indptr, &h->indices, &h->data, &h->row, &h->col,
-                      &h->scan_state, &h->up_row, &h->up_col, &h->up_data, &h->tsv, &h->tsv_off, &h->el_len, &h->el_off, &h->el_text, &h->emit_t0, &h->bfs_levels, &h->bfs_q0, &h->bfs_q1, &h->bfs_ctl, &h->bfs_nodes, &h->bfs_out, &h->path_starts, &h->path_recs, &h->path_cnt, &h->path_off, &h->path_ids, &h->path_misc, &h->dx_arena, &h->dx_ctl, &h->dx_loc, &h->dx_zg, &h->dx_gslot, &h->dx_gpos, &h->dx_sent, &h->dx_tcnt, &h->dx_toff, &h->pair_major, &h->pair_ent, &h->bucket_ctl};
+                      &h->scan_state, &h->up_row, &h->up_col, &h->up_data, &h->tsv, &h->tsv_off, &h->el_len, &h->el_off, &h->el_text, &h->emit_t0, &h->bfs_levels, &h->bfs_q0, &h->bfs_q1, &h->bfs_ctl, &h->bfs_nodes, &h->bfs_out, &h->path_starts, &h->path_recs, &h->path_cnt, &h->path_off, &h->path_ids, &h->path_misc, &h->dx_arena, &h->dx_ctl, &h->dx_loc, &h->dx_zg, &h->dx_gslot, &h->dx_gpos, &h->dx_sent, &h->dx_tcnt, &h->dx_toff, &h->pair_major, &h->pair_ent, &h->bucket_ctl, &h->pair2_major, &h->pair2_ent, &h->sub_ctl, &h->sub_off};
     if (h->dx_inited) g2n_dist_close_peers(h);
     for (DevBuf* b : bufs) b->release();
     if (h->h_loc) cudaFreeHost(h->h_loc);
@@ -2355,16 +2443,16 @@ int g2n_dist_stage(g2n_handle* h, int stage, const uint8_t* text, uint64_t nbyte
         h->result_format = csc ? G2N_FMT_CSC : G2N_FMT_CSR;
         const u32 pgrid = grid_for(recv_cap + 1, 256, 8);
         const RowPasses rp = row_passes(recv_cap, weighted ? sizeof(u64) : sizeof(u32), rows_cap);
-        if (rp.count > 1 && !getenv("G2N_DBG_NOBUCKET")) {
+        if (rp.bucketed) {
             // slab far larger than L2: partition the received entries by row bucket, then stream (dist.cuh / rowsort.cuh)
-            const RowBuckets rb = row_buckets(rp, rows_cap);
+            const BucketPlan BP = plan_buckets(rp, recv_cap, rows_cap, weighted ? sizeof(u64) : sizeof(u32));
+            const RowBuckets rb = BP.rb;
             CK(h->pair_major.ensure((recv_cap + 1) * sizeof(u32)));
             CK(h->pair_ent.ensure((recv_cap + 1) * (weighted ? sizeof(u64) : sizeof(u32))));
             CK(h->bucket_ctl.ensure(sizeof(BucketCtl)));
             CK(cudaMemsetAsync(h->bucket_ctl.p, 0, sizeof(BucketCtl), h->stream));
             BucketCtl* ctl = h->bucket_ctl.as<BucketCtl>();
             const u32 sgrid = grid_for((recv_cap + RB_ROUND) / RB_ROUND, 1, 8);
-            const u32 bgrid = grid_for((recv_cap + 3) / 4 + 1, 256);
             if (weighted) {
                 { KScope ks(h, "k_pairs_bucket_count"); k_pairs_bucket_count<DistPairW><<<pgrid, 256, 0, h->stream>>>(X, L, loc, h->d_ds, rb, ctl, &loc->bad); }
                 { KScope ks(h, "k_pairs_bucket_scatter"); k_pairs_bucket_scatter<DistPairW, Ent64><<<sgrid, 256, 0, h->stream>>>(X, L, loc, h->d_ds, rb, ctl, h->pair_major.as<u32>(), h->pair_ent.as<u64>(), h->w_emit.as<double>()); }
@@ -2372,13 +2460,9 @@ int g2n_dist_stage(g2n_handle* h, int stage, const uint8_t* text, uint64_t nbyte
                 { KScope ks(h, "k_pairs_bucket_count"); k_pairs_bucket_count<DistPair><<<pgrid, 256, 0, h->stream>>>(X, L, loc, h->d_ds, rb, ctl, &loc->bad); }
                 { KScope ks(h, "k_pairs_bucket_scatter"); k_pairs_bucket_scatter<DistPair, Ent32><<<sgrid, 256, 0, h->stream>>>(X, L, loc, h->d_ds, rb, ctl, h->pair_major.as<u32>(), h->pair_ent.as<u32>(), nullptr); }
             }
-            { KScope ks(h, "k_bucket_rows_count"); k_bucket_rows_count<<<bgrid, 256, 0, h->stream>>>(h->pair_major.as<u32>(), h->d_ds, ctl, rb.count, h->d_rowcnt); }
             CK(cudaGetLastError());
-            int rc = rows_scan(h, rows_cap, &h->d_ds->rows);
+            int rc = weighted ? bucketed_tail<Ent64>(h, BP, recv_cap, rows_cap, false) : bucketed_tail<Ent32>(h, BP, recv_cap, rows_cap, false);
             if (rc) return rc;
-            if (weighted) { KScope ks(h, "k_bucket_rows_scatter"); k_bucket_rows_scatter<Ent64><<<bgrid, 256, 0, h->stream>>>(h->pair_major.as<u32>(), h->pair_ent.as<u64>(), h->d_ds, ctl, rb.count, h->cursor.as<u32>(), h->entries.as<u64>()); }
-            else { KScope ks(h, "k_bucket_rows_scatter"); k_bucket_rows_scatter<Ent32><<<bgrid, 256, 0, h->stream>>>(h->pair_major.as<u32>(), h->pair_ent.as<u32>(), h->d_ds, ctl, rb.count, h->cursor.as<u32>(), h->entries.as<u32>()); }
-            CK(cudaGetLastError());
             rc = rows_finalize(h, h->params.dtype, weighted, recv_cap, rows_cap, sym, WEmit{weighted ? h->w_emit.as<double>() : nullptr, 0u}, nullptr);
             if (rc) return rc;
             break;

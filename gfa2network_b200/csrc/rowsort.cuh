@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(256) k_rows_scatter_flat(const u32* __restrict
 //   k_bucket_scatter      flat again: (major, entry) -> its bucket's range, one global atomic per bucket and CTA round
 //   k_bucket_rows_count   flat over the pair list: cnt[major]++        (skipped when the tokenizer counted the rows)
 //   k_bucket_rows_scatter flat over the pair list: entries[cursor[major]++] = entry
-#define RB_MAX 64
+#define RB_MAX 128
 struct RowBuckets {
     u32 shift, count;  // bucket of a row = min(row >> shift, count - 1)
     __device__ __forceinline__ u32 of(u32 major) const
@@ -301,6 +301,25 @@ __device__ __forceinline__ void rb_entries(const u32 (&id)[4], u32 t0, int sym, 
         else if (csc) g(k, c, r, 0u, t0 + k);
         else g(k, r, c, 0u, t0 + k);
     }
+}
+
+// exclusive prefix of n <= 256 shared-memory counters by a 256-thread CTA: lo[j] = sum of cnt[0 .. j), lo[n] = total.
+// `warp_sums`: 8 words of shared memory.  Starts and ends with a CTA barrier.
+__device__ __forceinline__ void rb_prefix256(const u32* cnt, u32 n, u32* lo, u32* warp_sums)
+{
+    __syncthreads();
+    const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const u32 v = threadIdx.x < n ? cnt[threadIdx.x] : 0u;
+    const u32 inc = warp_incl_scan(v);
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    u32 base = 0;
+#pragma unroll
+    for (u32 w = 0; w < 8; w++) base += w < wid ? warp_sums[w] : 0u;
+    if (threadIdx.x < n) lo[threadIdx.x] = base + inc - v;
+    if (threadIdx.x == n) lo[n] = base + inc - v;  // everything below n (v == 0 from n on); n == 256: see below
+    if (n == 256 && threadIdx.x == 255) lo[256] = base + inc;
+    __syncthreads();
 }
 
 template <int SPE>
@@ -383,7 +402,7 @@ __global__ void __launch_bounds__(256) k_bucket_scatter(const u32* __restrict__ 
     constexpr int EPR = TPE == 1 ? 2 : TPE;  // entries of one record at most (TPE == 1: two when sym)
     constexpr int RECS = RbRecs<TPE>::value;
     static_assert(256 * RECS * EPR <= RB_ROUND, "round size");
-    __shared__ u32 s_off[RB_MAX], s_cnt[RB_MAX], s_lo[RB_MAX + 1], s_base[RB_MAX];
+    __shared__ u32 s_off[RB_MAX], s_cnt[RB_MAX], s_lo[RB_MAX + 1], s_base[RB_MAX], s_ws[8];
     __shared__ u32 s_major[RB_ROUND];
     __shared__ EV s_ent[RB_ROUND];
     if (!ds->ok) return;
@@ -413,12 +432,7 @@ __global__ void __launch_bounds__(256) k_bucket_scatter(const u32* __restrict__ 
             if (r0 + u * 256 + threadIdx.x < E)
                 rb_entries<TPE>(id[u], 0u, sym, csc, [&](int q, u32 major, u32, u32, u32) { rk[u][q] = (unsigned short)atomicAdd(&s_cnt[rb.of(major)], 1u); });
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            u32 run = 0;
-            for (u32 b = 0; b < rb.count; b++) { s_lo[b] = run; run += s_cnt[b]; }
-            s_lo[rb.count] = run;
-        }
+        rb_prefix256(s_cnt, rb.count, s_lo, s_ws);
         if (threadIdx.x < rb.count) {
             const u32 c = s_cnt[threadIdx.x];
             s_base[threadIdx.x] = s_off[threadIdx.x] + (c ? atomicAdd(&ctl->cur[threadIdx.x], c) : 0u);
@@ -502,6 +516,212 @@ __global__ void __launch_bounds__(256) k_bucket_rows_scatter(const u32* __restri
                 entries[pos] = v[u];
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------- second level: sub-buckets that fit shared memory
+// Inside an L2-sized bucket every entry still costs an atomic with a return value and a store of its own (about 70 G
+// entries/s whatever the locality: the L2 transaction rate, not its hit rate).  So each bucket is partitioned once more,
+// into <= SB_FAN sub-buckets of a few thousand entries (a power-of-two number of consecutive rows), and the last two
+// passes work on one sub-bucket per CTA entirely in shared memory: the row histogram is written out coalesced, and the
+// entries are grouped by row in shared memory and copied to their final place, which is one contiguous range.
+//   k_sub_count        bucket-major pair list -> entries per sub-bucket
+//   k_sub_scatter      pair list -> sub-bucket-major pair list (same staging as k_bucket_scatter)
+//   k_sub_rows_count   one CTA per sub-bucket: cnt[row] for its rows     (skipped when the tokenizer counted the rows)
+//   k_sub_rows_place   one CTA per sub-bucket: entries of its rows, grouped by row (any order inside a row; a sub-bucket
+//                      that does not fit -- a few very long rows -- goes through the global cursors instead)
+#define SB_FAN 256
+#define SB_ROWS_MAX 4096  // rows of a sub-bucket at most (shared-memory histogram / cursors)
+struct SubBuckets {
+    u32 shift2;     // sub-bucket of a row = row >> shift2 (numbered across buckets: bucket = sub-bucket >> fan_shift)
+    u32 fan_shift;  // bucket shift - shift2, <= 8
+    u32 n_sub;      // buckets << fan_shift
+    u32 cap;        // entries a sub-bucket may hold for the shared-memory placement
+};
+
+// prefix of the bucket counters in shared memory: s_off[0 .. count]
+__device__ __forceinline__ void rb_offsets(const BucketCtl* ctl, u32 count, u32* s_off)
+{
+    if (threadIdx.x == 0) {
+        u32 run = 0;
+        for (u32 b = 0; b < count; b++) { s_off[b] = run; run += ctl->cnt[b]; }
+        s_off[count] = run;
+    }
+    __syncthreads();
+}
+// every bucket that intersects the pair-list range [c0, c1): f(bucket, lo, hi), uniform across the CTA
+template <class F>
+__device__ __forceinline__ void rb_segments(const u32* s_off, u32 count, u64 c0, u64 c1, F f)
+{
+    u32 b = 0;
+    while (b + 1 < count && s_off[b + 1] <= c0) b++;
+    for (; b < count && s_off[b] < c1; b++) {
+        const u64 lo = c0 > s_off[b] ? c0 : s_off[b], hi = c1 < s_off[b + 1] ? c1 : s_off[b + 1];
+        if (lo < hi) f(b, lo, hi);
+    }
+}
+
+#define SB_CHUNK (RB_ROUND * 8)
+__global__ void __launch_bounds__(256) k_sub_count(const u32* __restrict__ pair_major, const DevSizes* __restrict__ ds, const BucketCtl* __restrict__ ctl,
+                                                    const RowBuckets rb, const SubBuckets sb, u32* __restrict__ sub_cnt)
+{
+    __shared__ u32 s_off[RB_MAX + 1];
+    __shared__ u32 s_hist[SB_FAN];
+    if (!ds->ok) return;
+    rb_offsets(ctl, rb.count, s_off);
+    const u64 total = s_off[rb.count];
+    const u32 fan_mask = (1u << sb.fan_shift) - 1u;
+    for (u64 c0 = (u64)blockIdx.x * SB_CHUNK; c0 < total; c0 += (u64)gridDim.x * SB_CHUNK) {
+        rb_segments(s_off, rb.count, c0, c0 + SB_CHUNK, [&](u32 b, u64 lo, u64 hi) {
+            s_hist[threadIdx.x] = 0;  // SB_FAN == blockDim.x
+            __syncthreads();
+            for (u64 i = lo + threadIdx.x; i < hi; i += 256) atomicAdd(&s_hist[(pair_major[i] >> sb.shift2) & fan_mask], 1u);
+            __syncthreads();
+            const u32 c = s_hist[threadIdx.x];
+            if (c) atomicAdd(&sub_cnt[(b << sb.fan_shift) + threadIdx.x], c);
+            __syncthreads();
+        });
+    }
+}
+
+template <class ENT>
+__global__ void __launch_bounds__(256) k_sub_scatter(const u32* __restrict__ pair_major, const typename ENT::type* __restrict__ pair_ent,
+                                                      const DevSizes* __restrict__ ds, const BucketCtl* __restrict__ ctl, const RowBuckets rb, const SubBuckets sb,
+                                                      const u32* __restrict__ sub_off, u32* __restrict__ sub_cur,
+                                                      u32* __restrict__ out_major, typename ENT::type* __restrict__ out_ent)
+{
+    typedef typename ENT::type EV;
+    constexpr int PER = RB_ROUND / 256;
+    __shared__ u32 s_off[RB_MAX + 1];
+    __shared__ u32 s_cnt[SB_FAN], s_lo[SB_FAN + 1], s_base[SB_FAN], s_ws[8];
+    __shared__ u32 s_major[RB_ROUND];
+    __shared__ EV s_ent[RB_ROUND];
+    if (!ds->ok) return;
+    rb_offsets(ctl, rb.count, s_off);
+    const u64 total = s_off[rb.count];
+    const u32 fan = 1u << sb.fan_shift, fan_mask = fan - 1u;
+    for (u64 c0 = (u64)blockIdx.x * RB_ROUND; c0 < total; c0 += (u64)gridDim.x * RB_ROUND) {
+        rb_segments(s_off, rb.count, c0, c0 + RB_ROUND, [&](u32 b, u64 lo, u64 hi) {
+            s_cnt[threadIdx.x] = 0;
+            __syncthreads();
+            u32 mj[PER];
+            EV en[PER];
+            unsigned short rk[PER];
+#pragma unroll
+            for (int u = 0; u < PER; u++) {
+                const u64 i = lo + u * 256 + threadIdx.x;
+                mj[u] = 0xFFFFFFFFu;
+                en[u] = (EV)0;
+                if (i < hi) { mj[u] = pair_major[i]; en[u] = pair_ent[i]; }
+            }
+#pragma unroll
+            for (int u = 0; u < PER; u++)
+                if (mj[u] != 0xFFFFFFFFu) rk[u] = (unsigned short)atomicAdd(&s_cnt[(mj[u] >> sb.shift2) & fan_mask], 1u);
+            rb_prefix256(s_cnt, fan, s_lo, s_ws);
+            if (threadIdx.x < fan) {
+                const u32 c = s_cnt[threadIdx.x], g = (b << sb.fan_shift) + threadIdx.x;
+                s_base[threadIdx.x] = sub_off[g] + (c ? atomicAdd(&sub_cur[g], c) : 0u);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < PER; u++) {
+                if (mj[u] != 0xFFFFFFFFu) {
+                    const u32 p = s_lo[(mj[u] >> sb.shift2) & fan_mask] + rk[u];
+                    s_major[p] = mj[u];
+                    s_ent[p] = en[u];
+                }
+            }
+            __syncthreads();
+            const u32 n = s_lo[fan];
+            for (u32 p = threadIdx.x; p < n; p += 256) {
+                const u32 major = s_major[p];
+                const u32 j = (major >> sb.shift2) & fan_mask;
+                const u64 pos = (u64)s_base[j] + (p - s_lo[j]);
+                out_major[pos] = major;
+                out_ent[pos] = s_ent[p];
+            }
+            __syncthreads();
+        });
+    }
+}
+
+__global__ void __launch_bounds__(256) k_sub_rows_count(const u32* __restrict__ pair_major, const DevSizes* __restrict__ ds, const SubBuckets sb,
+                                                         const u32* __restrict__ sub_off, u32* __restrict__ cnt)
+{
+    __shared__ u32 s_hist[SB_ROWS_MAX];
+    if (!ds->ok) return;
+    const u32 rows = ds->rows, per = 1u << sb.shift2;
+    for (u32 g = blockIdx.x; g < sb.n_sub; g += gridDim.x) {  // uniform per CTA
+        const u32 row0 = g << sb.shift2;
+        if (row0 >= rows) break;
+        const u32 nr = min(per, rows - row0);
+        const u32 lo = sub_off[g], hi = sub_off[g + 1];
+        for (u32 i = threadIdx.x; i < nr; i += 256) s_hist[i] = 0;
+        __syncthreads();
+        for (u32 i = lo + threadIdx.x; i < hi; i += 256) {
+            const u32 r = pair_major[i] - row0;
+            G2N_CHECK(r < nr);
+            atomicAdd(&s_hist[r], 1u);
+        }
+        __syncthreads();
+        for (u32 i = threadIdx.x; i < nr; i += 256) cnt[row0 + i] = s_hist[i];
+        __syncthreads();
+    }
+}
+
+// dynamic shared memory: cursors[SB_ROWS_MAX] (u32) | staged entries[sb.cap].  SB_PT threads per CTA and SB_PB pairs per
+// thread in flight: a sub-bucket is a few thousand entries, so its three phases (row pointers, group, copy out) are one
+// or two memory round trips each -- with one pair per thread and iteration the phases were a chain of 24 dependent round
+// trips (1.8 ms on C4d, profiles/r3_buckets.md).
+#define SB_PT 512
+#define SB_PB 4
+template <class ENT>
+__global__ void __launch_bounds__(SB_PT) k_sub_rows_place(const u32* __restrict__ pair_major, const typename ENT::type* __restrict__ pair_ent,
+                                                           const DevSizes* __restrict__ ds, const SubBuckets sb, const u32* __restrict__ sub_off,
+                                                           const u32* __restrict__ rowptr, u32* __restrict__ cursor, typename ENT::type* __restrict__ entries)
+{
+    typedef typename ENT::type EV;
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    u32* s_cur = reinterpret_cast<u32*>(s_dyn);
+    EV* s_out = reinterpret_cast<EV*>(s_dyn + SB_ROWS_MAX * sizeof(u32));
+    if (!ds->ok) return;
+    const u32 rows = ds->rows, per = 1u << sb.shift2;
+    for (u32 g = blockIdx.x; g < sb.n_sub; g += gridDim.x) {  // uniform per CTA
+        const u32 row0 = g << sb.shift2;
+        if (row0 >= rows) break;
+        const u32 nr = min(per, rows - row0);
+        const u32 lo = sub_off[g], hi = sub_off[g + 1], n = hi - lo;
+        if (n == 0) continue;
+        if (n > sb.cap) {  // does not fit: global cursors (cursor[] starts as a copy of rowptr[])
+            for (u32 i = lo + threadIdx.x; i < hi; i += SB_PT) entries[atomicAdd(&cursor[pair_major[i]], 1u)] = pair_ent[i];
+            continue;
+        }
+        const u32 out0 = rowptr[row0];
+        for (u32 i = threadIdx.x; i < nr; i += SB_PT) s_cur[i] = rowptr[row0 + i] - out0;
+        __syncthreads();
+        for (u32 i0 = lo + threadIdx.x; i0 < hi; i0 += SB_PT * SB_PB) {
+            u32 r[SB_PB];
+            EV v[SB_PB];
+#pragma unroll
+            for (int u = 0; u < SB_PB; u++) {
+                const u32 i = i0 + u * SB_PT;
+                r[u] = 0xFFFFFFFFu;
+                v[u] = (EV)0;
+                if (i < hi) { r[u] = pair_major[i] - row0; v[u] = pair_ent[i]; }
+            }
+#pragma unroll
+            for (int u = 0; u < SB_PB; u++) {
+                if (r[u] != 0xFFFFFFFFu) {
+                    G2N_CHECK(r[u] < nr);
+                    const u32 p = atomicAdd(&s_cur[r[u]], 1u);
+                    G2N_CHECK(p < n);
+                    if (p < n) s_out[p] = v[u];
+                }
+            }
+        }
+        __syncthreads();
+        for (u32 i = threadIdx.x; i < n; i += SB_PT) entries[(u64)out0 + i] = s_out[i];
+        __syncthreads();
     }
 }
 

@@ -294,13 +294,14 @@ def test_long_names_across_shards(mode):
         _check(*_assemble(ranks, out, "csr"), text, mode)
 
 
-@pytest.mark.parametrize("bucketed", [True, False], ids=["buckets", "row-range-passes"])
+@pytest.mark.parametrize("variant", [dict(), dict(G2N_DBG_SUBCAP="8"), dict(G2N_DBG_NOSUB="1"), dict(G2N_DBG_NOBUCKET="1")],
+                         ids=["sub-buckets", "sub-buckets-overflow", "buckets", "row-range-passes"])
 @pytest.mark.parametrize("mode", [dict(), dict(weight_tag="RC", bidirected=True)], ids=str)
-def test_slab_row_range_passes(monkeypatch, mode, bucketed):
+def test_slab_row_range_passes(monkeypatch, mode, variant):
     """A slab far larger than L2 (forced): received entries partitioned by row bucket (dist.cuh: k_pairs_bucket_*), or
     -- G2N_DBG_NOBUCKET -- the bucketing kernels in several row-range passes."""
-    if not bucketed:
-        monkeypatch.setenv("G2N_DBG_NOBUCKET", "1")
+    for k, v in variant.items():
+        monkeypatch.setenv(k, v)
     from gfa2network_b200 import _capi
     from gfa2network_b200 import dist as D
     from gfa2network_b200.synth import synth_gfa

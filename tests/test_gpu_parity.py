@@ -242,14 +242,15 @@ def test_conditional_first_appearance_variant(monkeypatch):
         assert nodes == onodes
 
 
-@pytest.mark.parametrize("bucketed", [True, False], ids=["buckets", "row-range-passes"])
+@pytest.mark.parametrize("variant", [dict(), dict(G2N_DBG_SUBCAP="8"), dict(G2N_DBG_NOSUB="1"), dict(G2N_DBG_NOBUCKET="1")],
+                         ids=["sub-buckets", "sub-buckets-overflow", "buckets", "row-range-passes"])
 @pytest.mark.parametrize("passes", ["3", "64"])
-def test_row_range_passes_variant(monkeypatch, passes, bucketed):
+def test_row_range_passes_variant(monkeypatch, passes, variant):
     """Row arrays far larger than L2: the entries are partitioned by row bucket before the histogram / scatter passes
     (rowsort.cuh: RowBuckets) -- or, G2N_DBG_NOBUCKET, the bucketing kernels run once per slice of rows (RowRange).
     Forced on small inputs: same results in every mode, on repeated (speculative) builds and after a convert."""
-    if not bucketed:
-        monkeypatch.setenv("G2N_DBG_NOBUCKET", "1")
+    for k, v in variant.items():
+        monkeypatch.setenv(k, v)
     from gfa2network_b200 import convert_format, parse_gfa
     from gfa2network_b200.synth import synth_gfa
     from oracle.oracle import oracle_convert_format, oracle_parse_gfa
