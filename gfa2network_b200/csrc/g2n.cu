@@ -349,12 +349,13 @@ struct RowPasses {
 static const RowRange ROW_RANGE_ALL = {0u, 0xFFFFFFFFu};
 static RowPasses row_passes(u64 M, size_t ent_bytes, u64 n)
 {
-    // Row arrays up to 96 MB: one pass (C2).  Up to 384 MB: one pass per 96 MB slice of rows (C5 shape at 5 %: three
-    // passes 1.00 ms, buckets 1.01 ms).  Beyond: buckets of about 32 MB (C4d, 800 MB: 8 passes 5.84 ms, 39 buckets 4.04 ms;
-    // C3, 1.1 GB: 7.0 -> 5.1 ms; more than 32 buckets changes nothing -- profiles/r3_buckets.md).
+    // Row arrays up to 96 MB: one flat pass (C2).  Beyond: partitioned into buckets of about 32 MB and sub-buckets that
+    // fit shared memory (rowsort.cuh) -- C5 shape at 5 % (200 MB): three row-range passes 1.00 ms, partitioned 0.82 ms;
+    // C4d (800 MB): 5.84 -> 3.03 ms; C3 (1.1 GB, weighted): 7.0 -> 3.75 ms (profiles/r3_buckets.md).  G2N_DBG_NOBUCKET:
+    // the older scheme, one pass of the flat kernels per 96 MB slice of rows.
     const u64 bytes = M * ent_bytes + n * 8;
     const bool forced = getenv("G2N_DBG_ROWPASS") != nullptr;
-    const bool bucketed = (forced || bytes > (384ull << 20)) && !getenv("G2N_DBG_NOBUCKET");
+    const bool bucketed = (forced || bytes > (96ull << 20)) && !getenv("G2N_DBG_NOBUCKET");
     const u64 budget = bucketed ? 32ull << 20 : 96ull << 20;
     u64 R = (bytes + budget - 1) / budget;
     if (const char* e = getenv("G2N_DBG_ROWPASS")) R = (u64)atoll(e);
