@@ -78,6 +78,7 @@ struct g2n_handle {
     DevBuf rowptr, cursor, entries, w_emit, biglist, ucnt, indptr, indices, data, row, col, scan_state;
     DevBuf up_row, up_col, up_data, tsv, tsv_off, el_len, el_off, el_text, emit_t0;
     DevBuf pair_major, pair_ent, bucket_ctl, pair2_major, pair2_ent, sub_ctl, sub_off;  // bucketed row build (rowsort.cuh: RowBuckets, SubBuckets)
+    bool rows_presorted = false;  // k_sub_rows_place sorted the short rows and wrote ucnt: rows_finalize runs k_rows_sort_rest
     u32 place_attr = 0;  // k_sub_rows_place instantiations whose dynamic shared memory opt-in was set on this device
     DevBuf bfs_levels, bfs_q0, bfs_q1, bfs_ctl, bfs_nodes, bfs_out;  // distances on the resident CSR (bfs.cuh)
     int bfs_slots = 0;
@@ -306,7 +307,9 @@ int rows_finalize_typed(g2n_handle* h, u64 M, u64 n, int sym, const WEmit w_emit
     { KScope ks(h, "k_rows_big"); k_rows_big<ENT><<<G2N_SM_COUNT, 256, 0, h->stream>>>(h->rowptr.as<u32>(), h->biglist.as<u32>(), h->d_bigcount, h->entries.as<E>()); }
     const u64 n_chunks = (n + RF_ROWS - 1) / RF_ROWS;
     CK(h->ucnt.ensure((n + 2) * sizeof(u32)));
-    { KScope ks(h, "k_rows_sort"); k_rows_sort<T, ENT><<<grid_for(n_chunks, 1, 8), RF_ROWS, 0, h->stream>>>(h->rowptr.as<u32>(), h->entries.as<E>(), n_dev, sym, w_emit, w_typed, h->ucnt.as<u32>()); }
+    if (h->rows_presorted) { KScope ks(h, "k_rows_sort_rest"); k_rows_sort_rest<T, ENT><<<grid_for(n, 256), 256, 0, h->stream>>>(h->rowptr.as<u32>(), h->entries.as<E>(), n_dev, sym, w_emit, w_typed, h->ucnt.as<u32>()); }
+    else { KScope ks(h, "k_rows_sort"); k_rows_sort<T, ENT><<<grid_for(n_chunks, 1, 8), RF_ROWS, 0, h->stream>>>(h->rowptr.as<u32>(), h->entries.as<E>(), n_dev, sym, w_emit, w_typed, h->ucnt.as<u32>()); }
+    h->rows_presorted = false;
     CK(cudaGetLastError());
     LoadArray<u32> ldu{h->ucnt.as<u32>()};
     int rc = launch_scan<int32_t>(h, ldu, h->indptr.as<int32_t>(), nullptr, n, n_dev, h->d_scan_rows[1]);
@@ -426,8 +429,9 @@ static BucketPlan plan_buckets(const RowPasses& rp, u64 M, u64 n, size_t ent_byt
 // From the bucket-major pair list (pair_major / pair_ent, counts in bucket_ctl) to rowptr + entries grouped by row.
 // `M` and `n` are host-side capacities; `counted`: d_rowcnt already holds the row histogram.
 template <class ENT>
-static int bucketed_tail(g2n_handle* h, const BucketPlan& P, u64 M, u64 n, bool counted)
+static int bucketed_tail(g2n_handle* h, const BucketPlan& P, u64 M, u64 n, bool counted, int sym)
 {
+    h->rows_presorted = false;
     typedef typename ENT::type EV;
     BucketCtl* ctl = h->bucket_ctl.as<BucketCtl>();
     const u32 pgrid = grid_for((M + 3) / 4, 256);
@@ -467,7 +471,12 @@ static int bucketed_tail(g2n_handle* h, const BucketPlan& P, u64 M, u64 n, bool 
         CK(cudaFuncSetAttribute(k_sub_rows_place<ENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         h->place_attr |= bit;
     }
-    { KScope ks(h, "k_sub_rows_place"); k_sub_rows_place<ENT><<<grid_for(sb.n_sub, 1, 2), SB_PT, smem, h->stream>>>(h->pair2_major.as<u32>(), h->pair2_ent.as<EV>(), h->d_ds, sb, h->sub_off.as<u32>(), h->rowptr.as<u32>(), h->cursor.as<u32>(), h->entries.as<EV>()); }
+    // the short rows are sorted while their sub-bucket sits in shared memory (not weighted max(S, S^T): k_rows_sort counts
+    // with the summed weights there)
+    const bool fuse_sort = !(ENT::kWeighted && sym) && !getenv("G2N_DBG_NOFUSESORT");
+    if (fuse_sort) CK(h->ucnt.ensure((n + 2) * sizeof(u32)));
+    { KScope ks(h, "k_sub_rows_place"); k_sub_rows_place<ENT><<<grid_for(sb.n_sub, 1, 2), SB_PT, smem, h->stream>>>(h->pair2_major.as<u32>(), h->pair2_ent.as<EV>(), h->d_ds, sb, h->sub_off.as<u32>(), h->rowptr.as<u32>(), h->cursor.as<u32>(), h->entries.as<EV>(), fuse_sort ? h->ucnt.as<u32>() : nullptr); }
+    h->rows_presorted = fuse_sort;
     CK(cudaGetLastError());
     return G2N_OK;
 }
@@ -506,7 +515,7 @@ static int bucketed_rows(g2n_handle* h, const BucketPlan& P, u64 M, u64 n, int s
         }
     }
     CK(cudaGetLastError());
-    return bucketed_tail<ENT>(h, P, M, n, counted);
+    return bucketed_tail<ENT>(h, P, M, n, counted, sym);
 }
 
 // rowcnt -> rowptr + cursors; rows longer than RS_SMALL are listed on the way
@@ -553,6 +562,7 @@ int build_compressed(g2n_handle* h, int fmt, bool zeroed, bool counted)
     const int sym = h->symmax ? 1 : 0;
     const u64 M = sym ? 2 * T : T;
     h->result_format = fmt;
+    h->rows_presorted = false;
     if (M >= 0xFFFFFFF0ull) { h->err = "more than 2^32 triplets in one build"; return G2N_ERR_UNSUPPORTED; }
     const bool weighted = h->params.weight_tag_len > 0;
     // for a symmetric result CSC arrays equal CSR arrays; bucket by row either way
@@ -2440,6 +2450,7 @@ int g2n_dist_stage(g2n_handle* h, int stage, const uint8_t* text, uint64_t nbyte
             if (rc0) return rc0;
         }
         h->spec = false;
+        h->rows_presorted = false;
         CK(cudaMemsetAsync(h->zrows.p, 0, h->zrows_bytes, h->stream));
         h->result_format = csc ? G2N_FMT_CSC : G2N_FMT_CSR;
         const u32 pgrid = grid_for(recv_cap + 1, 256, 8);
@@ -2462,7 +2473,7 @@ int g2n_dist_stage(g2n_handle* h, int stage, const uint8_t* text, uint64_t nbyte
                 { KScope ks(h, "k_pairs_bucket_scatter"); k_pairs_bucket_scatter<DistPair, Ent32><<<sgrid, 256, 0, h->stream>>>(X, L, loc, h->d_ds, rb, ctl, h->pair_major.as<u32>(), h->pair_ent.as<u32>(), nullptr); }
             }
             CK(cudaGetLastError());
-            int rc = weighted ? bucketed_tail<Ent64>(h, BP, recv_cap, rows_cap, false) : bucketed_tail<Ent32>(h, BP, recv_cap, rows_cap, false);
+            int rc = weighted ? bucketed_tail<Ent64>(h, BP, recv_cap, rows_cap, false, sym) : bucketed_tail<Ent32>(h, BP, recv_cap, rows_cap, false, sym);
             if (rc) return rc;
             rc = rows_finalize(h, h->params.dtype, weighted, recv_cap, rows_cap, sym, WEmit{weighted ? h->w_emit.as<double>() : nullptr, 0u}, nullptr);
             if (rc) return rc;

@@ -531,6 +531,7 @@ __global__ void __launch_bounds__(256) k_bucket_rows_scatter(const u32* __restri
 //   k_sub_rows_place   one CTA per sub-bucket: entries of its rows, grouped by row (any order inside a row; a sub-bucket
 //                      that does not fit -- a few very long rows -- goes through the global cursors instead)
 #define SB_FAN 256
+#define SB_UNSORTED 0xFFFFFFFFu  // ucnt of a row the placement did not sort (longer than RS_SMALL, or an overflowing sub-bucket)
 #define SB_ROWS_MAX 4096  // rows of a sub-bucket at most (shared-memory histogram / cursors)
 struct SubBuckets {
     u32 shift2;     // sub-bucket of a row = row >> shift2 (numbered across buckets: bucket = sub-bucket >> fan_shift)
@@ -669,61 +670,7 @@ __global__ void __launch_bounds__(256) k_sub_rows_count(const u32* __restrict__ 
     }
 }
 
-// dynamic shared memory: cursors[SB_ROWS_MAX] (u32) | staged entries[sb.cap].  SB_PT threads per CTA and SB_PB pairs per
-// thread in flight: a sub-bucket is a few thousand entries, so its three phases (row pointers, group, copy out) are one
-// or two memory round trips each -- with one pair per thread and iteration the phases were a chain of 24 dependent round
-// trips (1.8 ms on C4d, profiles/r3_buckets.md).
-#define SB_PT 512
-#define SB_PB 4
-template <class ENT>
-__global__ void __launch_bounds__(SB_PT) k_sub_rows_place(const u32* __restrict__ pair_major, const typename ENT::type* __restrict__ pair_ent,
-                                                           const DevSizes* __restrict__ ds, const SubBuckets sb, const u32* __restrict__ sub_off,
-                                                           const u32* __restrict__ rowptr, u32* __restrict__ cursor, typename ENT::type* __restrict__ entries)
-{
-    typedef typename ENT::type EV;
-    extern __shared__ __align__(16) uint8_t s_dyn[];
-    u32* s_cur = reinterpret_cast<u32*>(s_dyn);
-    EV* s_out = reinterpret_cast<EV*>(s_dyn + SB_ROWS_MAX * sizeof(u32));
-    if (!ds->ok) return;
-    const u32 rows = ds->rows, per = 1u << sb.shift2;
-    for (u32 g = blockIdx.x; g < sb.n_sub; g += gridDim.x) {  // uniform per CTA
-        const u32 row0 = g << sb.shift2;
-        if (row0 >= rows) break;
-        const u32 nr = min(per, rows - row0);
-        const u32 lo = sub_off[g], hi = sub_off[g + 1], n = hi - lo;
-        if (n == 0) continue;
-        if (n > sb.cap) {  // does not fit: global cursors (cursor[] starts as a copy of rowptr[])
-            for (u32 i = lo + threadIdx.x; i < hi; i += SB_PT) entries[atomicAdd(&cursor[pair_major[i]], 1u)] = pair_ent[i];
-            continue;
-        }
-        const u32 out0 = rowptr[row0];
-        for (u32 i = threadIdx.x; i < nr; i += SB_PT) s_cur[i] = rowptr[row0 + i] - out0;
-        __syncthreads();
-        for (u32 i0 = lo + threadIdx.x; i0 < hi; i0 += SB_PT * SB_PB) {
-            u32 r[SB_PB];
-            EV v[SB_PB];
-#pragma unroll
-            for (int u = 0; u < SB_PB; u++) {
-                const u32 i = i0 + u * SB_PT;
-                r[u] = 0xFFFFFFFFu;
-                v[u] = (EV)0;
-                if (i < hi) { r[u] = pair_major[i] - row0; v[u] = pair_ent[i]; }
-            }
-#pragma unroll
-            for (int u = 0; u < SB_PB; u++) {
-                if (r[u] != 0xFFFFFFFFu) {
-                    G2N_CHECK(r[u] < nr);
-                    const u32 p = atomicAdd(&s_cur[r[u]], 1u);
-                    G2N_CHECK(p < n);
-                    if (p < n) s_out[p] = v[u];
-                }
-            }
-        }
-        __syncthreads();
-        for (u32 i = threadIdx.x; i < n; i += SB_PT) entries[(u64)out0 + i] = s_out[i];
-        __syncthreads();
-    }
-}
+// (k_sub_rows_place: at the end of this file, after the row-sorting helpers it uses)
 
 // same two steps for caller-provided COO arrays (g2n_coo_to_compressed)
 __global__ void __launch_bounds__(256) k_coo_count(const int32_t* __restrict__ row, const int32_t* __restrict__ col, u64 nnz, int csc, u32* __restrict__ cnt)
@@ -1028,6 +975,25 @@ __global__ void __launch_bounds__(RF_ROWS) k_rows_sort(const u32* __restrict__ r
     }
 }
 
+// Pass A after a placement that sorted the short rows itself (k_sub_rows_place): only the rows it marked SB_UNSORTED --
+// rows longer than RS_SMALL (sorted by k_rows_big meanwhile) and the rows of overflowing sub-buckets -- in place in
+// global memory, one lane per row.
+template <typename T, class ENT>
+__global__ void __launch_bounds__(256) k_rows_sort_rest(const u32* __restrict__ rowptr, typename ENT::type* __restrict__ entries,
+                                                         const u32* __restrict__ n_dev, int sym, const WEmit w_emit,
+                                                         const T* __restrict__ w_typed, u32* __restrict__ ucnt)
+{
+    typedef typename ENT::type E;
+    const u32 n = *n_dev;
+    for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        if (ucnt[r] != SB_UNSORTED) continue;
+        const u32 lo = rowptr[r], len = rowptr[r + 1] - lo;
+        E* a = entries + lo;
+        if (len > 1 && len <= RS_SMALL) insertion_sort<E>(a, len);
+        ucnt[r] = walk_row<T, ENT>(a, len, sym, w_emit, w_typed, [](u32, u32, T) {});
+    }
+}
+
 // Pass B: indptr (exclusive scan of ucnt) is known.  Same chunking: stage the sorted entries, walk every
 // row, write indices / data.
 template <typename T, class ENT>
@@ -1070,6 +1036,105 @@ __global__ void __launch_bounds__(RF_ROWS) k_rows_write(const u32* __restrict__ 
             });
         }
         __syncthreads();  // s_ent is reused by the next chunk
+    }
+}
+
+// dynamic shared memory: cursors[SB_ROWS_MAX] (u32) | staged entries[sb.cap].  SB_PT threads per CTA and SB_PB pairs per
+// thread in flight: a sub-bucket is a few thousand entries, so its three phases (row pointers, group, copy out) are one
+// or two memory round trips each -- with one pair per thread and iteration the phases were a chain of 24 dependent round
+// trips (1.8 ms on C4d, profiles/r3_buckets.md).
+#define SB_PT 512
+#define SB_PB 4
+// the row sorted in place by a network in registers; returns the number of distinct minors
+template <int N, class ENT>
+__device__ __forceinline__ u32 row_sort_heads(typename ENT::type* a, u32 len)
+{
+    typename ENT::type v[N];
+    load_row<N, ENT>(v, a, len);
+    sort_network(v);
+    u32 heads = 0;
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        if ((u32)k < len) {
+            a[k] = v[k];
+            heads += (k == 0 || ENT::minor(v[k]) != ENT::minor(v[k > 0 ? k - 1 : 0])) ? 1u : 0u;
+        }
+    }
+    return heads;
+}
+// `ucnt` non-NULL: every row of <= RS_SMALL entries is also SORTED while its sub-bucket sits in shared memory and the number
+// of entries it will store (distinct minors) is written to ucnt -- k_rows_sort's whole pass over the entries (read, sort,
+// write back) disappears; the rows left over are marked SB_UNSORTED for k_rows_sort_rest.  (Not for weighted max(S, S^T)
+// builds, whose count depends on the summed weights.)
+template <class ENT>
+__global__ void __launch_bounds__(SB_PT) k_sub_rows_place(const u32* __restrict__ pair_major, const typename ENT::type* __restrict__ pair_ent,
+                                                           const DevSizes* __restrict__ ds, const SubBuckets sb, const u32* __restrict__ sub_off,
+                                                           const u32* __restrict__ rowptr, u32* __restrict__ cursor, typename ENT::type* __restrict__ entries,
+                                                           u32* __restrict__ ucnt)
+{
+    typedef typename ENT::type EV;
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    u32* s_cur = reinterpret_cast<u32*>(s_dyn);
+    EV* s_out = reinterpret_cast<EV*>(s_dyn + SB_ROWS_MAX * sizeof(u32));
+    if (!ds->ok) return;
+    const u32 rows = ds->rows, per = 1u << sb.shift2;
+    for (u32 g = blockIdx.x; g < sb.n_sub; g += gridDim.x) {  // uniform per CTA
+        const u32 row0 = g << sb.shift2;
+        if (row0 >= rows) break;
+        const u32 nr = min(per, rows - row0);
+        const u32 lo = sub_off[g], hi = sub_off[g + 1], n = hi - lo;
+        if (n == 0 || n > sb.cap) {
+            // does not fit: global cursors (cursor[] starts as a copy of rowptr[]); nothing is sorted here
+            for (u32 i = lo + threadIdx.x; i < hi; i += SB_PT) entries[atomicAdd(&cursor[pair_major[i]], 1u)] = pair_ent[i];
+            if (ucnt)
+                for (u32 i = threadIdx.x; i < nr; i += SB_PT) ucnt[row0 + i] = n ? SB_UNSORTED : 0u;
+            continue;
+        }
+        const u32 out0 = rowptr[row0];
+        for (u32 i = threadIdx.x; i < nr; i += SB_PT) s_cur[i] = rowptr[row0 + i] - out0;
+        __syncthreads();
+        for (u32 i0 = lo + threadIdx.x; i0 < hi; i0 += SB_PT * SB_PB) {
+            u32 r[SB_PB];
+            EV v[SB_PB];
+#pragma unroll
+            for (int u = 0; u < SB_PB; u++) {
+                const u32 i = i0 + u * SB_PT;
+                r[u] = 0xFFFFFFFFu;
+                v[u] = (EV)0;
+                if (i < hi) { r[u] = pair_major[i] - row0; v[u] = pair_ent[i]; }
+            }
+#pragma unroll
+            for (int u = 0; u < SB_PB; u++) {
+                if (r[u] != 0xFFFFFFFFu) {
+                    G2N_CHECK(r[u] < nr);
+                    const u32 p = atomicAdd(&s_cur[r[u]], 1u);
+                    G2N_CHECK(p < n);
+                    if (p < n) s_out[p] = v[u];
+                }
+            }
+        }
+        __syncthreads();
+        if (ucnt) {  // s_cur[r] is now the END of row r's range; per warp the longest of its 32 rows picks the path
+            for (u32 r0 = 0; r0 < nr; r0 += SB_PT) {  // uniform trip count: the warp reduction needs every lane
+                const u32 r = r0 + threadIdx.x;
+                const bool live = r < nr;
+                const u32 a0 = (live && r) ? s_cur[r - 1] : 0u, len = live ? s_cur[r] - a0 : 0u;
+                EV* a = s_out + a0;
+                const u32 wmax = __reduce_max_sync(0xffffffffu, len);
+                u32 heads;
+                if (wmax <= 8) heads = row_sort_heads<8, ENT>(a, len);
+                else if (wmax <= 16) heads = row_sort_heads<16, ENT>(a, len);
+                else if (len <= RS_SMALL) {
+                    if (len > 1) insertion_sort<EV>(a, len);
+                    heads = 0;
+                    for (u32 k = 0; k < len; k++) heads += (k == 0 || ENT::minor(a[k]) != ENT::minor(a[k - 1])) ? 1u : 0u;
+                } else heads = SB_UNSORTED;
+                if (live) ucnt[row0 + r] = heads;
+            }
+            __syncthreads();
+        }
+        for (u32 i = threadIdx.x; i < n; i += SB_PT) entries[(u64)out0 + i] = s_out[i];
+        __syncthreads();
     }
 }
 

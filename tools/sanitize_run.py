@@ -7,6 +7,7 @@
 * the reference's DRB1 fixture (tests/golden/DRB1-3123_unsorted.gfa) in five modes incl. weighted / bidirected,
 * a fuzz text with deferred lines, long keys, errors and unknown records (tests/golden_inputs.fuzz_text(11)),
 * a 3-logical-shard multi-GPU build on one GPU (peer flags, owner table, entry exchange) incl. a speculative repeat,
+* the partitioned row build (rowsort.cuh: RowBuckets / SubBuckets) forced on the fixture, single-GPU and slab,
 * a *.gz source, the edge-list export and a path-distance matrix.
 Every result is compared with the CPU oracle, so a run that passes did the real work."""
 import gzip
@@ -64,6 +65,16 @@ for mode in (dict(), dict(weight_tag="RC", directed=False), dict(bidirected=True
         except type(e):
             pass
     n += 1
+# row arrays "far larger than L2" (forced): both bucket levels, the overflow path of a sub-bucket, one level only
+for variant in (dict(), dict(G2N_DBG_SUBCAP="8"), dict(G2N_DBG_NOSUB="1")):
+    os.environ["G2N_DBG_ROWPASS"] = "5"
+    os.environ.update(variant)
+    for mode in (dict(), dict(bidirected=True, weight_tag="RC"), dict(directed=False)):
+        A = parse_gfa(drb1, build_graph=False, build_matrix=True, **mode)
+        same(A, oracle_parse_gfa(drb1, **mode), (variant, mode))
+        n += 1
+    for k in ("G2N_DBG_ROWPASS", *variant):
+        del os.environ[k]
 # gz source, edge list
 with tempfile.TemporaryDirectory() as d:
     f = os.path.join(d, "x.gfa.gz")
@@ -81,7 +92,10 @@ for r in range(G):
     shards.append(torch.from_numpy(text[lo:hi].copy()).cuda())
 ranks = [D.LocalRank(0, r, G) for r in range(G)]
 caps = None
-for spec in (False, True):
+for spec in (False, True, "buckets"):
+    if spec == "buckets":  # the slab's partitioned receive (forced), speculative
+        os.environ["G2N_DBG_ROWPASS"] = "5"
+        spec = True
     for r, t in zip(ranks, shards):
         r.set_input(t)
     if not spec:
