@@ -554,8 +554,11 @@ __device__ __forceinline__ void rb_offsets(const BucketCtl* ctl, u32 count, u32*
 template <class F>
 __device__ __forceinline__ void rb_segments(const u32* s_off, u32 count, u64 c0, u64 c1, F f)
 {
-    u32 b = 0;
-    while (b + 1 < count && s_off[b + 1] <= c0) b++;
+    u32 b = 0, hi_b = count;  // first bucket that ends after c0 (binary search: this runs once per round in every thread)
+    while (b + 1 < hi_b) {
+        const u32 mid = (b + hi_b) >> 1;
+        if (s_off[mid] <= c0) b = mid; else hi_b = mid;
+    }
     for (; b < count && s_off[b] < c1; b++) {
         const u64 lo = c0 > s_off[b] ? c0 : s_off[b], hi = c1 < s_off[b + 1] ? c1 : s_off[b + 1];
         if (lo < hi) f(b, lo, hi);
