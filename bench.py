@@ -31,9 +31,9 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 HBM_FALLBACK_GBS = 6650.0  # B200_PROFILING.md fallback, used only if MEASURED_PEAKS.json is absent
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
-# (profiles/*.md name the capture each figure comes from); null where no capture exists yet
-TRAFFIC = {("C2", "k_tokenize"): 143_427_072}  # profiles/r1_ncu_full.md (dram read 129.15 MB + write 14.28 MB per launch)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full` captures
+# (profiles/r2b_ncu_full.md: C2, C3; profiles/r2_ncu_full.md: C5 shape at 5 %), keyed by (config, scale, kernel)
+TRAFFIC = {("C2", 1.0, "k_tokenize"): 205_775_616, ("C3", 1.0, "k_tokenize"): 19_774_601_000, ("C5", 0.05, "k_tokenize"): 7_395_001_616}
 
 
 def peaks():
@@ -565,7 +565,7 @@ def run_ours(args):
         if ab:
             ach = ab / (per_launch_ms * 1e6)
             roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": TRAFFIC.get((args.config, dom)) if args.scale == 1.0 and world == 1 else None, "algorithmic_bytes_per_launch": ab, "ms_per_launch": per_launch_ms,
+                    "frac": ach / peak, "traffic": TRAFFIC.get((args.config, float(args.scale), dom)) if world == 1 else None, "algorithmic_bytes_per_launch": ab, "ms_per_launch": per_launch_ms,
                     "share_of_step": kern[dom]["ms_per_step"] / ms_step}
     # whole-path algorithmic bytes: text in + result arrays out.  The node-name table (names + offsets,
     # SURVEY's last term) is NOT counted: it is gathered on demand (k_gather_names, when the caller asks for the node

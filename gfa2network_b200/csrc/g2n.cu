@@ -354,7 +354,7 @@ static RowPasses row_passes(u64 M, size_t ent_bytes, u64 n)
 {
     // Row arrays up to 96 MB: one flat pass (C2).  Beyond: partitioned into buckets of about 32 MB and sub-buckets that
     // fit shared memory (rowsort.cuh) -- C5 shape at 5 % (200 MB): three row-range passes 1.00 ms, partitioned 0.82 ms;
-    // C4d (800 MB): 5.84 -> 3.03 ms; C3 (1.1 GB, weighted): 7.0 -> 3.75 ms (profiles/r3_buckets.md).  G2N_DBG_NOBUCKET:
+    // C4d (800 MB): 5.84 -> 3.03 ms; C3 (1.1 GB, weighted): 7.0 -> 3.75 ms (profiles/r2b_buckets.md).  G2N_DBG_NOBUCKET:
     // the older scheme, one pass of the flat kernels per 96 MB slice of rows.
     const u64 bytes = M * ent_bytes + n * 8;
     const bool forced = getenv("G2N_DBG_ROWPASS") != nullptr;

@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(256) k_bucket_count(u32* __restrict__ edge_slo
 // (rank inside the round from a shared-memory atomic, group offsets from a 64-element prefix), the round's range in
 // every bucket is reserved with one global atomic, and consecutive threads then copy consecutive staged elements -- the
 // bucket frontiers receive whole runs instead of one 4-byte store per lane (uncoalesced stores ran the partition at
-// 0.5 TB/s with 32 buckets, profiles/r3_buckets.md).
+// 0.5 TB/s with 32 buckets, profiles/r2b_buckets.md).
 #define RB_ROUND 2048
 template <int TPE> struct RbRecs { static constexpr int value = TPE == 4 ? 2 : 4; };  // records per thread and round
 template <int TPE, class ENT>
@@ -1045,7 +1045,7 @@ __global__ void __launch_bounds__(RF_ROWS) k_rows_write(const u32* __restrict__ 
 // dynamic shared memory: cursors[SB_ROWS_MAX] (u32) | staged entries[sb.cap].  SB_PT threads per CTA and SB_PB pairs per
 // thread in flight: a sub-bucket is a few thousand entries, so its three phases (row pointers, group, copy out) are one
 // or two memory round trips each -- with one pair per thread and iteration the phases were a chain of 24 dependent round
-// trips (1.8 ms on C4d, profiles/r3_buckets.md).
+// trips (1.8 ms on C4d, profiles/r2b_buckets.md).
 #define SB_PT 512
 #define SB_PB 4
 // the row sorted in place by a network in registers; returns the number of distinct minors

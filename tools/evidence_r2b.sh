@@ -1,7 +1,7 @@
 #!/bin/bash
 # One B200: the round's single-GPU evidence (run under gpurun; outputs under gpurun_out/, summarised under profiles/ afterwards).
 set -u
-R=${R:-r3}
+R=${R:-r2b}
 python bench.py > gpurun_out/${R}_bench_C2.json 2> gpurun_out/${R}_bench_C2.err
 python tools/show_bench.py gpurun_out/${R}_bench_C2.json | head -3
 for c in "C3 1.0 5" "C4 1.0 5" "C4d 1.0 5" "C5 0.05 5"; do set -- $c; python bench.py --config $1 --scale $2 --steps $3 --warmup 3 > gpurun_out/${R}_bench_$1.json 2> gpurun_out/${R}_bench_$1.err; python tools/show_bench.py gpurun_out/${R}_bench_$1.json | head -2; done
