@@ -26,7 +26,7 @@ EXPORTS = [
     "g2n_edge_list_bytes", "g2n_fetch_edge_list", "g2n_bfs", "g2n_levels_reduce", "g2n_fetch_levels",
     "g2n_paths_load", "g2n_path_info", "g2n_path_bfs", "g2n_path_reduce", "g2n_fetch_path_nodes", "g2n_fetch_text",
     "g2n_dist_init", "g2n_dist_probe", "g2n_dist_plan", "g2n_dist_local_mem", "g2n_dist_set_peers", "g2n_dist_open_peers",
-    "g2n_dist_close_peers", "g2n_dist_stage", "g2n_dist_finish", "g2n_dist_enable_peer", "g2n_load_file_range",
+    "g2n_dist_close_peers", "g2n_dist_stage", "g2n_dist_finish", "g2n_dist_enable_peer", "g2n_load_file_range", "g2n_plan_row_buckets",
 ]
 
 

@@ -756,6 +756,22 @@ int finish_result(g2n_handle* h)
 extern "C" {
 
 int g2n_abi_version(void) { return G2N_ABI_VERSION; }
+
+int g2n_plan_row_buckets(uint64_t entries, uint64_t rows, int entry_bytes, uint32_t out[8])
+{
+    if (!out || (entry_bytes != 4 && entry_bytes != 8)) return G2N_ERR_INVALID;
+    const RowPasses rp = row_passes(entries, (size_t)entry_bytes, rows);
+    memset(out, 0, 8 * sizeof(uint32_t));
+    out[0] = rp.count;
+    out[1] = rp.bucketed ? 1u : 0u;
+    if (rp.bucketed) {
+        const BucketPlan P = plan_buckets(rp, entries, rows, (size_t)entry_bytes);
+        out[2] = P.rb.count; out[3] = P.rb.shift;
+        out[4] = P.two_level ? 1u : 0u;
+        if (P.two_level) { out[5] = P.sb.n_sub; out[6] = P.sb.shift2; out[7] = P.sb.cap; }
+    }
+    return G2N_OK;
+}
 int g2n_dist_close_peers(g2n_handle* h);
 
 int g2n_create(int device, g2n_handle** out)

@@ -237,6 +237,13 @@ int g2n_status(g2n_handle *h, g2n_diag *out);
 const char *g2n_last_error(g2n_handle *h);
 int g2n_abi_version(void);
 
+/* How a build with `entries` row entries of `entry_bytes` (4: no weights, 8: with) over `rows` rows would organise stage 4
+ * (scipy/_coo.py tocsr's counting sort by row, builders.py:283 / utils.py:55): host logic only, needs no device.
+ *   out[0] passes of the flat kernels (1: row arrays fit L2)   out[1] 1: entries are partitioned by row bucket first
+ *   out[2] buckets, out[3] log2(rows per bucket)               out[4] 1: second level (sub-buckets placed in shared memory)
+ *   out[5] sub-buckets, out[6] log2(rows per sub-bucket), out[7] entries a sub-bucket may hold in shared memory */
+int g2n_plan_row_buckets(uint64_t entries, uint64_t rows, int entry_bytes, uint32_t out[8]);
+
 /* Standalone stage 4 (SciPy COO -> CSR/CSC with duplicate summing, utils.py:55 on a user matrix):
  * host COO arrays in, host compressed arrays out.  *nnz_out receives the stored-entry count;
  * indptr has n+1 entries; indices/data need capacity nnz_in. */
