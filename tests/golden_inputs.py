@@ -218,3 +218,24 @@ def fuzz_text(seed: int, n_lines: int = 12000) -> bytes:
     if seed % 2 == 0:
         text = text[:-1]  # final line without "\n"
     return text
+
+
+def hub_text(seed: int = 9) -> bytes:
+    """1200 ordinary segments, two hub segments linked to hundreds of them (rows of > 500 stored entries), the same link
+    repeated many times (duplicates to sum), integer RC weights: rows far longer than what one lane sorts (rowsort.cuh: RS_SMALL)."""
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    lines = ["H\tVN:Z:1.0"] + [f"S\ts{i}\t*" for i in range(1200)] + ["S\thub\t*", "S\thub2\tACGT"]
+    for i in range(700):
+        j = int(rng.integers(0, 1200))
+        o1, o2 = "+-"[i % 2], "+-"[(i // 2) % 2]
+        lines.append(f"L\thub\t{o1}\ts{j}\t{o2}\t0M\tRC:i:{1 + i % 7}")
+        if i % 3 == 0:
+            lines.append(f"L\ts{j}\t{o2}\thub2\t{o1}\t*\tRC:i:{2 + i % 5}")
+        if i % 5 == 0:
+            lines.append("L\thub\t+\thub2\t-\t0M\tRC:i:3")  # the same link again and again
+    for i in range(3000):
+        a, b = rng.integers(0, 1200, 2)
+        lines.append(f"L\ts{a}\t+\ts{b}\t-\t0M\tRC:i:{1 + i % 3}")
+    return ("\n".join(lines) + "\n").encode()

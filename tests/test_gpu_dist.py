@@ -315,6 +315,26 @@ def test_slab_row_range_passes(monkeypatch, mode, variant):
     _check(*_assemble(ranks, out, "csr"), text, mode)
 
 
+@pytest.mark.parametrize("variant", [dict(), dict(G2N_DBG_SUBCAP="8"), dict(G2N_DBG_NOBUCKET="1")], ids=["sub-buckets", "sub-buckets-overflow", "row-range-passes"])
+@pytest.mark.parametrize("mode", [dict(), dict(weight_tag="RC", bidirected=True)], ids=str)
+def test_slab_partitioned_with_hub_rows(monkeypatch, mode, variant):
+    """Rows of hundreds of entries (hub segments, repeated links) in a slab whose receive side is partitioned (forced):
+    left unsorted by the placement, sorted by k_rows_big, counted by k_rows_sort_rest."""
+    import golden_inputs as gi
+    from gfa2network_b200 import _capi
+    from gfa2network_b200 import dist as D
+
+    monkeypatch.setenv("G2N_DBG_ROWPASS", "3")
+    for k, v in variant.items():
+        monkeypatch.setenv(k, v)
+    text = np.frombuffer(gi.hub_text(), dtype=np.uint8)
+    G = 3
+    ranks = [D.LocalRank(0, r, G) for r in range(G)]
+    out, _ = _build(ranks, _shards(text, G), False, **mode)
+    assert all(rc == _capi.G2N_OK for rc, _ in out)
+    _check(*_assemble(ranks, out, "csr"), text, mode)
+
+
 def _n_gpus():
     import torch
 

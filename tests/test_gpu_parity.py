@@ -268,6 +268,29 @@ def test_row_range_passes_variant(monkeypatch, passes, variant):
                 _same(convert_format(A, fmt), oracle_convert_format(B, fmt), f"rowpass {mode} {fmt}")
 
 
+@pytest.mark.parametrize("variant", [dict(), dict(G2N_DBG_SUBCAP="8"), dict(G2N_DBG_NOSUB="1"), dict(G2N_DBG_NOBUCKET="1")],
+                         ids=["sub-buckets", "sub-buckets-overflow", "buckets", "row-range-passes"])
+def test_partitioned_build_with_hub_rows(monkeypatch, variant):
+    """Rows far longer than RS_SMALL (a hub segment linked to hundreds of others, with repeated links) inside the partitioned
+    build: the placement leaves them unsorted (SB_UNSORTED), k_rows_big sorts them, k_rows_sort_rest counts their stored
+    entries; duplicates are summed (scipy/_coo.py tocsr + sum_duplicates, builders.py:279-283)."""
+    from gfa2network_b200 import convert_format, parse_gfa
+    from oracle.oracle import oracle_convert_format, oracle_parse_gfa
+
+    monkeypatch.setenv("G2N_DBG_ROWPASS", "3")
+    for k, v in variant.items():
+        monkeypatch.setenv(k, v)
+    text = gi.hub_text()
+    for mode in (dict(), dict(directed=False), dict(bidirected=True), dict(asymmetric=True), dict(weight_tag="RC"),
+                 dict(weight_tag="RC", bidirected=True), dict(weight_tag="RC", directed=False, dtype="int32")):
+        for rep in range(2):
+            A = parse_gfa(text, build_graph=False, build_matrix=True, **mode)
+            B = oracle_parse_gfa(text, **mode)
+            _same(A, B, f"hub {variant} {mode} rep {rep}")
+            for fmt in ("csr", "csc"):
+                _same(convert_format(A, fmt), oracle_convert_format(B, fmt), f"hub {variant} {mode} {fmt}")
+
+
 def test_unaligned_device_text():
     """A device pointer that is not 16-byte aligned (a slice of a larger tensor) is accepted."""
     import torch
