@@ -5,7 +5,10 @@
 //   k_rows_count     one atomic per triplet into cnt[major]                       (histogram)
 //   exclusive scan   cnt -> rowptr + cursors; rows longer than RS_SMALL are listed on the way (common.cuh)
 //   k_rows_scatter_flat / k_edges_scatter_flat   entry (minor, dir[, emission index]) -> atomicAdd(cursor[major]) (any order inside a
-//                    row), one pass per row range when the row arrays are far larger than L2 (RowRange)
+//                    row) -- while the row arrays fit L2 (<= 96 MB).  Beyond that the entries are PARTITIONED first: by row
+//                    bucket, then by sub-bucket, and the histogram / placement / short-row sort of a sub-bucket happen in
+//                    shared memory (k_bucket_* / k_sub_* below); the older scheme, one pass of the flat kernels per row
+//                    range (RowRange), is kept behind G2N_DBG_NOBUCKET
 //   k_rows_big       rows longer than RS_SMALL are sorted in place by a whole CTA (bitonic; rare)
 //   k_rows_sort      one CTA per chunk of RF_ROWS consecutive rows, one lane per row: the chunk's entries
 //                    are staged in shared memory (coalesced), every row is sorted -- rows of <= 16
