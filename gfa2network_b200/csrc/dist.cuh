@@ -380,10 +380,10 @@ __global__ void __launch_bounds__(256) k_dx_mark(const DevSizes* __restrict__ ds
 }
 
 // ---------------------------------------------------------------- x3: first source -> owner, rank inside the shard
-// also this shard's name table: id2slot / name_len are indexed by that rank
+// also this shard's name table: id2slot is indexed by that rank (name lengths: ids.cuh LoadNameLen, on demand)
 __global__ void __launch_bounds__(256) k_dx_send_rank(const Slot* __restrict__ slots, const DevSizes* __restrict__ ds, const DxPeers X,
                                                        const DxLayout L, const u64* __restrict__ klist, const u32* __restrict__ bitmap,
-                                                       const u32* __restrict__ wprefix, u32* __restrict__ id2slot, u32* __restrict__ name_len,
+                                                       const u32* __restrict__ wprefix, u32* __restrict__ id2slot,
                                                        DxLocal* __restrict__ loc)
 {
     const bool ok = ds->ok != 0;
@@ -399,7 +399,6 @@ __global__ void __launch_bounds__(256) k_dx_send_rank(const Slot* __restrict__ s
         const u32 r = bitmap_rank(bitmap, wprefix, ob);
         (reinterpret_cast<u32*>(X.arena[d] + L.off_rank) + (u64)X.rank * L.kcap)[pos] = r;
         id2slot[r] = slot;
-        name_len[r] = slot_key_len(slots[slot].k1);
     }
     // the popcount prefix ends with the number of marked bits = this shard's global firsts
     dx_tail_signal(X, 2, loc, nullptr, 0, ok ? (u64)wprefix[ds->wgroups] : 0ull);

@@ -74,7 +74,7 @@ struct g2n_handle {
     std::string err;
     cudaEvent_t ev[EV_COUNT];
     // device buffers (kept between builds: a warm handle allocates nothing)
-    DevBuf text, defer, edge_slots, edge_w, longs, tile_info, tile_base, wprefix, slot_id, id2slot, name_len, name_off, names;
+    DevBuf text, defer, edge_slots, edge_w, longs, tile_info, tile_base, wprefix, slot_id, id2slot, name_off, names;
     DevBuf rowptr, cursor, entries, w_emit, biglist, ucnt, indptr, indices, data, row, col, scan_state;
     DevBuf up_row, up_col, up_data, tsv, tsv_off, el_len, el_off, el_text, emit_t0;
     DevBuf pair_major, pair_ent, bucket_ctl, pair2_major, pair2_ent, sub_ctl, sub_off;  // bucketed row build (rowsort.cuh: RowBuckets, SubBuckets)
@@ -805,7 +805,7 @@ void g2n_destroy(g2n_handle* h)
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->text, &h->zearly, &h->zids, &h->zrows, &h->defer, &h->edge_slots, &h->edge_w, &h->longs, &h->tile_info, &h->tile_base, &h->wprefix,
-                      &h->slot_id, &h->id2slot, &h->name_len, &h->name_off, &h->names, &h->rowptr, &h->cursor, &h->entries, &h->w_emit, &h->biglist, &h->ucnt, &h->indptr, &h->indices, &h->data, &h->row, &h->col,
+                      &h->slot_id, &h->id2slot, &h->name_off, &h->names, &h->rowptr, &h->cursor, &h->entries, &h->w_emit, &h->biglist, &h->ucnt, &h->indptr, &h->indices, &h->data, &h->row, &h->col,
                       &h->scan_state, &h->up_row, &h->up_col, &h->up_data, &h->tsv, &h->tsv_off, &h->el_len, &h->el_off, &h->el_text, &h->emit_t0, &h->bfs_levels, &h->bfs_q0, &h->bfs_q1, &h->bfs_ctl, &h->bfs_nodes, &h->bfs_out, &h->path_starts, &h->path_recs, &h->path_cnt, &h->path_off, &h->path_ids, &h->path_misc, &h->dx_arena, &h->dx_ctl, &h->dx_loc, &h->dx_zg, &h->dx_gslot, &h->dx_gpos, &h->dx_sent, &h->dx_tcnt, &h->dx_toff, &h->pair_major, &h->pair_ent, &h->bucket_ctl, &h->pair2_major, &h->pair2_ent, &h->sub_ctl, &h->sub_off};
     if (h->dx_inited) g2n_dist_close_peers(h);
     for (DevBuf* b : bufs) b->release();
@@ -1314,7 +1314,6 @@ static int ids_phase(g2n_handle* h)
     CK(h->wprefix.ensure((words + 2) * sizeof(u32)));
     CK(h->slot_id.ensure((size_t)cap * sizeof(u32)));
     CK(h->id2slot.ensure((n + 1) * sizeof(u32)));
-    CK(h->name_len.ensure((n + 1) * sizeof(u32)));
     CK(h->name_off.ensure((n + 2) * sizeof(u64)));
     if (n > 0) {
         { KScope ks(h, "k_mark_first"); k_mark_first<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->d_slots, cap, h->tile_base.as<u64>(), h->d_bitmap, h->d_ds); }
@@ -1322,7 +1321,7 @@ static int ids_phase(g2n_handle* h)
         int rc = launch_scan<u32>(h, lp, h->wprefix.as<u32>(), nullptr, words / BM_GROUP + 1, &h->d_ds->wgroups, h->d_scan_words);
         if (rc) return rc;
         { KScope ks(h, "k_assign_ids"); k_assign_ids<<<grid_for(cap, 256), 256, 0, h->stream>>>(h->d_slots, cap, h->tile_base.as<u64>(), h->d_bitmap, h->wprefix.as<u32>(),
-                                                                 h->slot_id.as<u32>(), h->id2slot.as<u32>(), h->name_len.as<u32>(), h->d_ds,
+                                                                 h->slot_id.as<u32>(), h->id2slot.as<u32>(), h->d_ds,
                                                                  h->count_mode != CM_NONE ? h->d_slot_cnt : nullptr, h->d_rowcnt); }
         CK(cudaGetLastError());
     }
@@ -1335,13 +1334,13 @@ static int ids_phase(g2n_handle* h)
 // names held by this handle: all nodes, or -- multi-GPU slab -- the nodes that first appear in this rank's shard
 static u64 names_count(const g2n_handle* h) { return h->slab_mode ? h->names_n : h->n_nodes; }
 
-// name_len -> name_off (exclusive scan) and the total; only when somebody asks for the node names
+// name lengths (from the table slots, ids.cuh: LoadNameLen) -> name_off (exclusive scan) and the total; only when somebody asks for the node names
 static int size_names(g2n_handle* h)
 {
     if (h->names_sized) return G2N_OK;
     const u64 n = names_count(h);
     if (n > 0) {
-        LoadArray<u32> ln{h->name_len.as<u32>()};
+        LoadNameLen ln{h->d_slots, h->id2slot.as<u32>()};
         int rc = launch_scan<u64>(h, ln, (u64*)h->name_off.as<u64>(), nullptr, n, nullptr, nullptr);
         if (rc) return rc;
         CK(cudaMemcpyAsync(&h->h_tail[1], h->name_off.as<u64>() + n, sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
@@ -1717,7 +1716,7 @@ static int build_tsv(g2n_handle* h)
     const u64 n = h->n_nodes;
     CK(h->tsv_off.ensure((n + 2) * sizeof(u64)));
     if (n > 0) {
-        LoadTsvLen ll{h->name_len.as<u32>()};
+        LoadTsvLen ll{LoadNameLen{h->d_slots, h->id2slot.as<u32>()}};
         int rc = launch_scan<u64>(h, ll, h->tsv_off.as<u64>(), nullptr, n, nullptr, nullptr);
         if (rc) return rc;
         CK(cudaMemcpyAsync(&h->h_tail[4], h->tsv_off.as<u64>() + n, sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
@@ -2371,7 +2370,6 @@ int g2n_dist_stage(g2n_handle* h, int stage, const uint8_t* text, uint64_t nbyte
         CK(h->slot_id.ensure((size_t)h->table_cap * sizeof(u32)));
         CK(h->dx_sent.ensure((size_t)W * h->dxl.kcap * sizeof(u64) + 256));  // klist: [owner][position] -> order bit | slot
         CK(h->id2slot.ensure((h->cap_n + 1) * sizeof(u32)));
-        CK(h->name_len.ensure((h->cap_n + 1) * sizeof(u32)));
         CK(h->name_off.ensure((h->cap_n + 2) * sizeof(u64)));
         h->slab_mode = true;
         h->names_sized = false;
@@ -2407,7 +2405,7 @@ int g2n_dist_stage(g2n_handle* h, int stage, const uint8_t* text, uint64_t nbyte
         LoadPopc8 lp{h->d_bitmap};
         int rc = launch_scan<u32>(h, lp, h->wprefix.as<u32>(), nullptr, words / BM_GROUP + 1, &h->d_ds->wgroups, h->d_scan_words);
         if (rc) return rc;
-        { KScope ks(h, "k_dx_send_rank"); k_dx_send_rank<<<kgrid, 256, 0, h->stream>>>(h->d_slots, h->d_ds, X, L, h->dx_sent.as<u64>(), h->d_bitmap, h->wprefix.as<u32>(), h->id2slot.as<u32>(), h->name_len.as<u32>(), loc); }
+        { KScope ks(h, "k_dx_send_rank"); k_dx_send_rank<<<kgrid, 256, 0, h->stream>>>(h->d_slots, h->d_ds, X, L, h->dx_sent.as<u64>(), h->d_bitmap, h->wprefix.as<u32>(), h->id2slot.as<u32>(), loc); }
         break;
     }
     case 3: {

@@ -86,11 +86,20 @@ __device__ __forceinline__ u32 slot_key_len(u64 k1)
     return top == 0xFF ? (u32)((k1 >> 32) & 0xFFFFFF) : top - 1;
 }
 
-// slot -> id ; id -> slot ; id -> name length ; id -> entries of the node's row (when the tokenizer counted them)
+// length of node id's name, from its table slot: only the node-name paths need it (g2n_names_bytes / g2n_fetch_names, the node
+// map), so it is not materialised by the build -- one random 4-byte store per node less in k_assign_ids / k_dx_send_rank
+struct LoadNameLen {
+    const Slot* slots;
+    const u32* id2slot;
+    __device__ __forceinline__ u64 operator()(u64 i) const { return (u64)slot_key_len(slots[id2slot[i]].k1); }
+    __device__ __forceinline__ u64 peek(u64 i) const { return (*this)(i); }
+};
+
+// slot -> id ; id -> slot ; id -> entries of the node's row (when the tokenizer counted them)
 __global__ void __launch_bounds__(256) k_assign_ids(const Slot* __restrict__ slots, u32 cap,
                                                      const u64* __restrict__ tile_base, const u32* __restrict__ bitmap,
                                                      const u32* __restrict__ wprefix, u32* __restrict__ slot_id,
-                                                     u32* __restrict__ id2slot, u32* __restrict__ name_len, const DevSizes* __restrict__ ds,
+                                                     u32* __restrict__ id2slot, const DevSizes* __restrict__ ds,
                                                      const u32* __restrict__ slot_cnt, u32* __restrict__ rowcnt)
 {
     if (!ds->ok) return;
@@ -103,7 +112,6 @@ __global__ void __launch_bounds__(256) k_assign_ids(const Slot* __restrict__ slo
         G2N_CHECK((ob >> 5) < ds->words && id < ds->n);
         slot_id[i] = id;
         id2slot[id] = i;
-        name_len[id] = slot_key_len(v[1]);
         if (slot_cnt) rowcnt[id] = slot_cnt[i];
     }
 }
@@ -139,8 +147,8 @@ __device__ __forceinline__ u32 dec_digits(u32 v)
     return d;
 }
 struct LoadTsvLen {  // bytes of node i's line
-    const u32* name_len;
-    __device__ __forceinline__ u64 operator()(u64 i) const { return (u64)dec_digits((u32)i) + name_len[i] + 2; }
+    LoadNameLen name_len;
+    __device__ __forceinline__ u64 operator()(u64 i) const { return (u64)dec_digits((u32)i) + name_len(i) + 2; }
     __device__ __forceinline__ u64 peek(u64 i) const { return (*this)(i); }
 };
 __global__ void __launch_bounds__(256) k_tsv_write(const Slot* __restrict__ slots,
