@@ -250,7 +250,7 @@ struct DxOwner {  // the owner's table over the keys it is responsible for
     Slot* gslots;  // first = ~min(source rank << 32 | local order)
     u32 gmask;
     u32* gslot;   // [source][position]: table slot of the received key
-    u32* gpos;    // [table slot]: position of the key in the segment of its FIRST source
+    u32* gpos;    // [table slot]: FIRST source of the key << 29 | its position in that source's segment
 };
 
 // headers are read after dx_wait(); volatile: never through the read-only path
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(256) k_dx_reply_first(const DxPeers X, const D
         for (u32 t = 0; t < 4; t++) {
             if (g[t] != 0xFFFFFFFFu && (u32)(f[t] >> 32) == s) {
                 word |= 1u << (8 * t);
-                G.gpos[g[t]] = q * 4 + t;
+                G.gpos[g[t]] = (s << 29) | (q * 4 + t);  // kcap < 2^29 (g2n_dist_plan)
             }
         }
         out[q] = word;
@@ -440,11 +440,9 @@ __global__ void __launch_bounds__(256) k_dx_reply_ids(const DxPeers X, const DxL
         const u32 g = G.gslot[(u64)s * L.kcap + j];
         u32 id = 0;
         if (g != 0xFFFFFFFFu) {
-            const u32 fs = (u32)((~G.gslots[g].first) >> 32);
-            if (fs < (u32)X.world) {
-                const u32 p = G.gpos[g];
-                if (p < L.kcap) id = s_base[fs] + ranks[(u64)fs * L.kcap + p];
-            }
+            const u32 v = G.gpos[g];  // first source and the key's position in its segment, in one word
+            const u32 fs = v >> 29, p = v & ((1u << 29) - 1u);
+            if (fs < (u32)X.world && p < L.kcap) id = s_base[fs] + ranks[(u64)fs * L.kcap + p];
         }
         (reinterpret_cast<u32*>(X.arena[s] + L.off_id) + (u64)X.rank * L.kcap)[j] = id;
     }
